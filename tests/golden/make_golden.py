@@ -1,0 +1,146 @@
+"""Generate the golden fixtures in tests/golden/*.npz.
+
+Runs ONLY in the build container, where the reference checkout is mounted at
+/root/reference:   python tests/golden/make_golden.py
+
+It executes the reference's own, unmodified Python source for the hot path
+(SynthesizeMultiScale, loss_factory -> TotalLoss, pose_rvec2matr_batch_tf/_np,
+photometric_loss_*) over the TensorFlow-API shim in tf_shim.py and stores
+inputs + outputs (+ gradients from torch.autograd standing in for
+tape.gradient).  See tf_shim.py for what this does and does not pin.
+The GPU box has no /root/reference: tests read only the committed .npz files.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("XPT_REFERENCE", "/root/reference")
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+
+import tf_shim  # noqa: E402
+
+F64 = "--f64" in sys.argv
+if F64:
+    tf_shim.FLOAT = torch.float64
+tf_shim.install()
+sys.path.insert(0, REF)
+
+from model.synthesize.synthesize_base import SynthesizeMultiScale  # noqa: E402
+from model.loss_and_metric.loss_factory import loss_factory  # noqa: E402
+import model.loss_and_metric.loss_util as lsu  # noqa: E402
+import utils.convert_pose as cp  # noqa: E402
+import utils.util_funcs as uf  # noqa: E402
+from oracle import xpt_oracle as orc  # noqa: E402  (input generator only)
+
+DT = torch.float64 if F64 else torch.float32
+LOSS_SETS = {
+    # reference config-example.py:76-89 (entries the dataset keys keep), :70-71
+    "T1": ({"L1": 0.5, "L1_R": 0.5, "SSIM": 0.5, "SSIM_R": 0.5, "smoothe": 1.0, "smoothe_R": 1.0,
+            "stereoL1": 0.01, "stereoSSIM": 0.01, "stereoPose": 1.0}, np.array([1.0, 1.0, 1.0, 1.0])),
+    "T2": ({"L1": 0.5, "L1_R": 0.5, "SSIM": 0.5, "SSIM_R": 0.5, "smoothe": 20.0, "smoothe_R": 20.0,
+            "stereoL1": 0.5, "stereoSSIM": 0.5, "stereoPose": 1.0}, np.array([0.4, 0.8, 1.2, 1.6])),
+}
+
+
+def make_inputs(*a, **k):
+    """fp32-rounded inputs in both runs, so the f64 vectors are the exact-arithmetic
+    answer for the very same inputs."""
+    feats, preds = orc.make_inputs(*a, dtype=torch.float32, **k)
+    cv = lambda t: t.to(DT)
+    return ({k_: cv(v) for k_, v in feats.items()},
+            {"depth_ms": [cv(d) for d in preds["depth_ms"]], "disp_ms": [cv(d) for d in preds["disp_ms"]],
+             "pose": cv(preds["pose"])})
+
+
+def np_(t):
+    return t.detach().cpu().numpy()
+
+
+def run_case(name, B, H, W, N, loss_set, seed, adversarial=False, global_batch=None):
+    feats, preds = make_inputs(B, H, W, N=N, seed=seed, adversarial=adversarial)
+    src = feats["image5d"][:, :-1].clone().requires_grad_(True)
+    image5d = torch.cat([src, feats["image5d"][:, -1:]], dim=1)
+    depth = [d.clone().requires_grad_(True) for d in preds["depth_ms"]]
+    disp = [d.clone().requires_grad_(True) for d in preds["disp_ms"]]
+    pose = preds["pose"].clone().requires_grad_(True)
+    loss_weights, scale_weights = LOSS_SETS[loss_set]
+    gb = B if global_batch is None else global_batch
+    total_obj = loss_factory({"image": 1, "intrinsic": 1}, loss_weights, scale_weights,
+                             stereo=False, batch_size=gb)
+    features = {"image5d": image5d, "intrinsic": feats["intrinsic"]}
+    predictions = {"depth_ms": depth, "disp_ms": disp, "pose": pose}
+    total, by_type = total_obj(predictions, features)
+    total.backward()
+    augm = total_obj.append_data(features, predictions)
+    out = {
+        "B": B, "H": H, "W": W, "N": N, "global_batch": gb, "loss_set": loss_set,
+        "loss_names": np.array(list(total_obj.loss_objects.keys())),
+        "loss_weights": np.array([total_obj.loss_weights[k] for k in total_obj.loss_objects]),
+        "scale_weights": scale_weights,
+        "total": np_(total), "d_pose": np_(pose.grad),
+    }
+    for k, v in by_type.items():
+        out["loss_" + k] = np_(v)
+    for s in range(len(depth)):
+        out[f"d_depth_{s}"] = np_(depth[s].grad)
+        out[f"d_disp_{s}"] = np_(disp[s].grad)
+    if not F64:
+        out.update({"image5d": np_(feats["image5d"]), "intrinsic": np_(feats["intrinsic"]),
+                    "pose": np_(preds["pose"]), "d_source": np_(src.grad)})
+        for s in range(len(depth)):
+            out[f"depth_{s}"] = np_(preds["depth_ms"][s])
+            out[f"disp_{s}"] = np_(preds["disp_ms"][s])
+            out[f"synth_{s}"] = np_(augm["synth_target_ms"][s])
+            out[f"target_{s}"] = np_(augm["target_ms"][s])
+    path = os.path.join(HERE, f"{name}_{'f64' if F64 else 'f32'}.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, {k: float(v) for k, v in by_type.items()}, float(total))
+
+
+def run_pieces():
+    """Per-function vectors: pose conversion (tf and numpy twins), per-pixel
+    photometric terms, safe reciprocal, SynthesizeMultiScale alone."""
+    g = torch.Generator().manual_seed(7)
+    poses = (torch.rand(3, 4, 6, generator=g, dtype=torch.float64) * 2 - 1).to(DT)
+    T_tf = cp.pose_rvec2matr_batch_tf(poses)
+    T_np = cp.pose_rvec2matr_batch_np(np_(poses).astype(np.float64))
+    synt = (torch.rand(2, 3, 9, 11, 3, generator=g, dtype=torch.float64) * 2 - 1).to(DT)
+    synt[:, :, 2:4, 3:6] = 0          # black (invalid) pixels
+    synt[:, 1, 0, :] = 0
+    orig = (torch.rand(2, 9, 11, 3, generator=g, dtype=torch.float64) * 2 - 1).to(DT)
+    depth = (torch.rand(2, 4, 6, 1, generator=g, dtype=torch.float64) * 3).to(DT)
+    depth[0, 0, 0, 0] = 0.000001
+    feats, preds = make_inputs(2, 16, 24, N=2, n_scales=2, seed=11)
+    synth_ms = SynthesizeMultiScale()(feats["image5d"][:, :-1], feats["intrinsic"],
+                                      preds["depth_ms"], preds["pose"])
+    tgt_ms = uf.multi_scale_like_depth(feats["image5d"][:, -1], preds["depth_ms"])
+    out = {
+        "poses": np_(poses), "T_tf": np_(T_tf), "T_np": T_np,
+        "synt": np_(synt), "orig": np_(orig),
+        "l1_map": np_(lsu.photometric_loss_l1(synt, orig, False)),
+        "l2_map": np_(lsu.photometric_loss_l2(synt, orig, False)),
+        "ssim_map": np_(lsu.photometric_loss_ssim(synt, orig, False)),
+        "l1": np_(lsu.photometric_loss_l1(synt, orig)), "ssim": np_(lsu.photometric_loss_ssim(synt, orig)),
+        "depth": np_(depth), "disp": np_(uf.safe_reciprocal_number(depth)),
+        "syn_image5d": np_(feats["image5d"]), "syn_intrinsic": np_(feats["intrinsic"]),
+        "syn_pose": np_(preds["pose"]),
+    }
+    for s in range(2):
+        out[f"syn_depth_{s}"] = np_(preds["depth_ms"][s])
+        out[f"syn_synth_{s}"] = np_(synth_ms[s])
+        out[f"syn_target_{s}"] = np_(tgt_ms[s])
+    path = os.path.join(HERE, f"pieces_{'f64' if F64 else 'f32'}.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path)
+
+
+if __name__ == "__main__":
+    run_pieces()
+    run_case("case_small_t1", B=2, H=32, W=64, N=4, loss_set="T1", seed=101)
+    run_case("case_n2_t2", B=3, H=48, W=40, N=2, loss_set="T2", seed=202, global_batch=6)
+    run_case("case_adv_t1", B=2, H=32, W=48, N=4, loss_set="T1", seed=303, adversarial=True)

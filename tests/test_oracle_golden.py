@@ -1,0 +1,84 @@
+"""Oracle vs the golden vectors produced by the reference's own Python source
+(tests/golden/make_golden.py).  Pins the oracle before anything trusts it."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import xpt_oracle as orc
+from helpers import CASES, case_inputs, load_case, relerr
+
+
+def test_pieces_pose_and_photometric_maps():
+    g = load_case("pieces")
+    T = orc.pose_rvec2matr_batch(torch.tensor(g["poses"])).numpy()
+    assert np.abs(T - g["T_tf"]).max() < 1e-6
+    # the reference's numpy twin (utils/convert_pose.py:74-111), run in fp64
+    assert np.abs(T - g["T_np"]).max() < 1e-6
+    synt, orig = torch.tensor(g["synt"]), torch.tensor(g["orig"])
+    assert np.abs(orc.photometric_loss_l1(synt, orig, False).numpy() - g["l1_map"]).max() < 1e-6
+    assert np.abs(orc.photometric_loss_l2(synt, orig, False).numpy() - g["l2_map"]).max() < 1e-6
+    assert np.abs(orc.photometric_loss_ssim(synt, orig, False).numpy() - g["ssim_map"]).max() < 2e-5
+    assert relerr(orc.photometric_loss_l1(synt, orig).numpy(), g["l1"]) < 1e-6
+    assert relerr(orc.photometric_loss_ssim(synt, orig).numpy(), g["ssim"]) < 1e-5
+    d = torch.tensor(g["depth"])
+    assert np.allclose(orc.safe_reciprocal_number(d).numpy(), g["disp"], rtol=1e-6)
+
+
+def test_pieces_synthesize_multi_scale():
+    g = load_case("pieces")
+    img = torch.tensor(g["syn_image5d"])
+    depth_ms = [torch.tensor(g[f"syn_depth_{s}"]) for s in range(2)]
+    out = orc.synthesize_multi_scale(img[:, :-1], torch.tensor(g["syn_intrinsic"]), depth_ms,
+                                     torch.tensor(g["syn_pose"]))
+    tgt = orc.multi_scale_like_depth(img[:, -1], depth_ms)
+    for s in range(2):
+        assert np.abs(out[s].numpy() - g[f"syn_synth_{s}"]).max() < 1e-5
+        assert np.abs(tgt[s].numpy() - g[f"syn_target_{s}"]).max() < 1e-6
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_total_loss_and_gradients_fp32(name):
+    g = load_case(name)
+    feats, preds, lw, sw, gb = case_inputs(g)
+    r = orc.loss_and_grads(feats, preds, lw, sw, gb, want_source_grad=True)
+    assert relerr(r["total"].numpy(), g["total"]) < 1e-5
+    for k in lw:
+        assert relerr(r["by_type"][k].numpy(), g["loss_" + k]) < 1e-5
+    for s in range(len(preds["depth_ms"])):
+        assert np.abs(r["synth_ms"][s].numpy() - g[f"synth_{s}"]).max() < 1e-5
+        assert np.abs(r["target_ms"][s].numpy() - g[f"target_{s}"]).max() < 1e-6
+        assert relerr(r["d_depth_ms"][s].numpy(), g[f"d_depth_{s}"]) < 1e-4
+        assert relerr(r["d_disp_ms"][s].numpy(), g[f"d_disp_{s}"]) < 1e-5
+    assert relerr(r["d_pose"].numpy(), g["d_pose"]) < 1e-4
+    assert relerr(r["d_source"].numpy(), g["d_source"]) < 1e-4
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_total_loss_and_gradients_fp64(name):
+    g, g64 = load_case(name), load_case(name, "f64")
+    feats, preds, lw, sw, gb = case_inputs(g, dtype=torch.float64)
+    r = orc.loss_and_grads(feats, preds, lw, sw, gb)
+    assert relerr(r["total"].numpy(), g64["total"]) < 1e-12
+    assert relerr(r["d_pose"].numpy(), g64["d_pose"]) < 1e-9
+    for s in range(len(preds["depth_ms"])):
+        assert relerr(r["d_depth_ms"][s].numpy(), g64[f"d_depth_{s}"]) < 1e-9
+        assert relerr(r["d_disp_ms"][s].numpy(), g64[f"d_disp_{s}"]) < 1e-9
+
+
+def test_gradients_match_finite_differences_fp64():
+    """No reference test pins gradients: check the autograd answer
+    against central differences on pose in fp64."""
+    feats, preds = orc.make_inputs(1, 16, 24, N=2, seed=5, dtype=torch.float64)
+    lw, sw = orc.LOSS_RIGID_T1, orc.SCALE_WEIGHT_T1
+    r = orc.loss_and_grads(feats, preds, lw, sw)
+    eps = 1e-6
+    for idx in [(0, 0, 0), (0, 1, 2), (0, 0, 3), (0, 1, 5)]:
+        vals = []
+        for sgn in (+1, -1):
+            p = {k: v for k, v in preds.items()}
+            pose = preds["pose"].clone()
+            pose[idx] += sgn * eps
+            p["pose"] = pose
+            vals.append(orc.total_loss(p, feats, lw, sw)[0].item())
+        fd = (vals[0] - vals[1]) / (2 * eps)
+        assert abs(fd - r["d_pose"][idx].item()) < 1e-5 * max(1.0, abs(fd)) + 1e-7
