@@ -1,0 +1,180 @@
+/* xptwarp.h -- C-ABI of libxptwarp.so: B200-native (sm_100a) view synthesis +
+ * photometric SSIM/L1 + edge-aware smoothness loss, forward and backward.
+ *
+ * The reference (goodgodgd/xpt-mde-2021) has NO FFI/plugin interface: the
+ * boundary of this path is a Python call surface.  Each
+ * entry point below therefore names the reference Python interface it stands
+ * behind (file:line relative to the reference checkout); the ctypes binding that
+ * a maintainer would add is in INTEGRATION.md and shipped in
+ * xpt-mde-2021_b200/xptwarp/_cabi.py.
+ *
+ * Conventions
+ *  - plain C: pointers, sizes, POD structs; no torch / TF / DLPack types.
+ *    (The Python host unwraps DLPack capsules to these pointers, zero-copy.)
+ *  - all tensor pointers are DEVICE pointers to fp32, channel-last, dense in the
+ *    inner dims; only the snippet tensor may carry batch / frame strides so that
+ *    source = image5d[:, :-1] and target = image5d[:, -1] are zero-copy views
+ *    (reference model/loss_and_metric/losses.py:77-83).
+ *  - the caller owns every input and output buffer; the library borrows them for
+ *    the duration of the call and owns only the scratch inside xpt_ctx.
+ *  - every call is asynchronous on the cudaStream_t passed as `stream`
+ *    (a void* so that this header needs no CUDA include); 0 = default stream.
+ *  - return value: XPT_OK (0) or a negative xpt_status; xpt_last_error() gives
+ *    the thread-local message.  There is no CPU fallback.
+ *  - one xpt_ctx per (device, host thread); calls on one ctx must be serialised
+ *    by the caller (stream order is enough when one stream is used).
+ */
+#ifndef XPTWARP_H_
+#define XPTWARP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define XPT_API __attribute__((visibility("default")))
+#else
+#define XPT_API
+#endif
+
+#define XPT_VERSION 100        /* 0.1.0 */
+#define XPT_MAX_SCALES 8
+
+typedef enum {
+  XPT_OK = 0,
+  XPT_BAD_ARGUMENT = -1,   /* null pointer, bad enum, bad flag combination        */
+  XPT_BAD_SHAPE = -2,      /* sizes not divisible by the scales, too small, ...   */
+  XPT_CUDA_ERROR = -3,     /* a CUDA runtime call or kernel launch failed         */
+  XPT_NO_DEVICE = -4,      /* no usable sm_100 device                            */
+  XPT_OUT_OF_MEMORY = -5   /* scratch allocation failed                          */
+} xpt_status;
+
+/* photometric term selector: reference loss_util.py:6-25 / :29-48 / :52-96 */
+typedef enum { XPT_PHOTO_L1 = 0, XPT_PHOTO_L2 = 1, XPT_PHOTO_SSIM = 2 } xpt_photo_method;
+
+/* Static description of the problem: the reference reads all of these from
+ * static tensor shapes (synthesize_base.py:61-64) and from config/opts
+ * (config-example.py:22,67-71,76-89).  Bound once at xpt_create.            */
+typedef struct {
+  int32_t batch;            /* B: snippets on THIS rank                               */
+  int32_t num_src;          /* N: source frames per snippet (SNIPPET_LEN-1)           */
+  int32_t height, width;    /* full-resolution H, W                                   */
+  int32_t num_scales;       /* S <= XPT_MAX_SCALES                                    */
+  int32_t scales[XPT_MAX_SCALES];      /* integer down-scale of each level (1,2,4,8) */
+  float scale_weights[XPT_MAX_SCALES]; /* losses.py:147-154                           */
+  float w_l1, w_ssim, w_smooth;        /* loss weights; 0 drops the term (loss_factory.py:41-43) */
+  float img_grad_factor;    /* opts.IMAGE_GRADIENT_FACTOR = 4 (losses.py:429)         */
+  int32_t global_batch;     /* tf.nn.compute_average_loss divisor (losses.py:49); 0 -> batch */
+  int32_t device;           /* CUDA device ordinal                                    */
+  uint32_t flags;           /* XPT_FLAG_*                                             */
+} xpt_config;
+
+/* xpt_total_loss runs one kernel per reference stage with tensors through HBM
+ * (warp -> synth -> loss -> dL/dsynth -> warp adjoint) instead of the fused
+ * tile kernel.  Same results; kept for A/B parity tests and profiling.        */
+#define XPT_FLAG_UNFUSED 1u
+
+/* The snippet frames + intrinsics (features of losses.py:26-37).              */
+typedef struct {
+  const float* source;           /* [B,N,H,W,3]                                       */
+  int64_t source_batch_stride;   /* elements between snippets (5*H*W*3 for an image5d view) */
+  int64_t source_frame_stride;   /* elements between frames   (H*W*3)                 */
+  const float* target;           /* [B,H,W,3]; may be NULL for xpt_synthesize*        */
+  int64_t target_batch_stride;   /* elements between snippets                         */
+  const float* intrinsic;        /* [B,3,3] dense                                     */
+} xpt_frames;
+
+/* Outputs of xpt_total_loss.  Every pointer is optional (NULL = not wanted)
+ * except `losses`.  Arrays are indexed by level 0..S-1.                       */
+typedef struct {
+  float* losses;                       /* [4]: total, L1, SSIM, smoothe -- by-type entries are the
+                                          UNWEIGHTED per-type means (losses.py:49-52), already divided
+                                          by global_batch; multi-rank callers all-reduce(sum) this.   */
+  float* loss_batch;                   /* [3][B] per-snippet L1, SSIM, smoothe (scale-merged)  */
+  float* synth_ms[XPT_MAX_SCALES];     /* [B,N,H_s,W_s,3]  augm_data["synth_target_ms"]         */
+  float* mask_ms[XPT_MAX_SCALES];      /* [B,N,H_s,W_s,1]  validity mask (bilinear_interp.py:53-76) */
+  float* target_ms[XPT_MAX_SCALES];    /* [B,H_s,W_s,3]    augm_data["target_ms"] (level 0 = copy) */
+  float* d_depth_ms[XPT_MAX_SCALES];   /* [B,H_s,W_s,1]    dL/d depth_ms                        */
+  float* d_disp_ms[XPT_MAX_SCALES];    /* [B,H_s,W_s,1]    dL/d disp_ms                         */
+  float* d_pose;                       /* [B,N,6]          dL/d pose                            */
+  float* d_source;                     /* [B,N,H,W,3] dense, dL/d source (through the pyramid)  */
+  float grad_scale;                    /* upstream dL/d total_loss (1 for a plain backward)     */
+} xpt_loss_outputs;
+
+typedef struct xpt_ctx xpt_ctx;
+
+XPT_API int xpt_version(void);
+XPT_API const char* xpt_last_error(void);
+XPT_API const char* xpt_status_string(int status);
+
+/* Binds shapes/weights, allocates scratch on cfg->device.                     */
+XPT_API int xpt_create(xpt_ctx** out, const xpt_config* cfg);
+XPT_API void xpt_destroy(xpt_ctx* ctx);
+XPT_API int xpt_get_config(const xpt_ctx* ctx, xpt_config* out);
+/* bytes of device scratch held by the ctx */
+XPT_API size_t xpt_scratch_bytes(const xpt_ctx* ctx);
+
+/* utils/convert_pose.py:32-71  pose_rvec2matr_batch_tf: [B,N,6] -> [B,N,4,4] */
+XPT_API int xpt_pose_rvec2matr(xpt_ctx* ctx, const float* pose, float* matr, void* stream);
+
+/* utils/util_funcs.py:163-175 multi_scale_like_depth (target pyramid) and
+ * synthesize_base.py:74-85 resize_source_images (source pyramid, kept inside
+ * the ctx).  target_ms[s] may be NULL (level not wanted); level 0 is a copy.  */
+XPT_API int xpt_build_pyramids(xpt_ctx* ctx, const xpt_frames* frames,
+                       float* const target_ms[], void* stream);
+
+/* synthesize_base.py:10-29 SynthesizeMultiScale.__call__ (+ the validity mask
+ * of bilinear_interp.py:53-76 as an extra output; mask_ms may be NULL).       */
+XPT_API int xpt_synthesize(xpt_ctx* ctx, const xpt_frames* frames,
+                   const float* const depth_ms[], const float* pose,
+                   float* const synth_ms[], float* const mask_ms[], void* stream);
+
+/* Backward of xpt_synthesize for an arbitrary upstream gradient
+ * grad_synth_ms[s] = dL/d synth_ms[s] (what tape.gradient does through
+ * synthesize_base.py, train_val.py:85).  d_source may be NULL.                */
+XPT_API int xpt_synthesize_backward(xpt_ctx* ctx, const xpt_frames* frames,
+                            const float* const depth_ms[], const float* pose,
+                            const float* const grad_synth_ms[],
+                            float* const d_depth_ms[], float* d_pose, float* d_source,
+                            void* stream);
+
+/* losses.py:175-195 PhotometricLossMultiScale(method).__call__ on given
+ * tensors -> loss_batch [B].  If d_synth_ms != NULL also writes
+ * d_synth_ms[s] = d(sum_b grad_loss_batch[b]*loss_batch[b]) / d synth_ms[s]
+ * (grad_loss_batch NULL = all ones).                                          */
+XPT_API int xpt_photometric_loss(xpt_ctx* ctx, int method,
+                         const float* const synth_ms[], const float* const target_ms[],
+                         float* loss_batch, const float* grad_loss_batch,
+                         float* const d_synth_ms[], void* stream);
+
+/* losses.py:386-440 SmoothenessLossMultiScale.__call__ -> loss_batch [B];
+ * optional backward to d_disp_ms as above.                                    */
+XPT_API int xpt_smoothness_loss(xpt_ctx* ctx, const float* const disp_ms[],
+                        const float* const target_ms[], float* loss_batch,
+                        const float* grad_loss_batch, float* const d_disp_ms[], void* stream);
+
+/* losses.py:26-55 TotalLoss.__call__ for the loss set {L1, SSIM, smoothe}
+ * (config LOSS_RIGID_T1/T2), forward and -- when any gradient output is
+ * non-NULL -- backward in the same call: pyramids, warp, losses, gradients.   */
+XPT_API int xpt_total_loss(xpt_ctx* ctx, const xpt_frames* frames,
+                   const float* const depth_ms[], const float* const disp_ms[],
+                   const float* pose, const xpt_loss_outputs* out, void* stream);
+
+/* The same call with HOST buffers (pinned or pageable): copies inputs to
+ * device staging owned by the ctx, runs xpt_total_loss, copies back the
+ * outputs that are non-NULL, and synchronises the stream before returning.
+ * `frames` and all pointers in `out` are host pointers here.                  */
+XPT_API int xpt_total_loss_host(xpt_ctx* ctx, const xpt_frames* frames,
+                        const float* const depth_ms[], const float* const disp_ms[],
+                        const float* pose, const xpt_loss_outputs* out, void* stream);
+
+/* number of kernels the last call on this ctx launched (bench's gpu_launches) */
+XPT_API int xpt_last_launch_count(const xpt_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XPTWARP_H_ */

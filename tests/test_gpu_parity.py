@@ -1,0 +1,328 @@
+"""GPU parity tests: the CUDA path (through the ctypes C-ABI) against the golden vectors and
+against the CPU oracle on the same seeded inputs.  Tolerances are BASELINE.json's:
+warped images 1e-4 max-abs, losses 1e-5 relative, gradients 1e-4 relative (max-norm)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import CASES, case_inputs, grad_close, load_case, relerr
+
+pytestmark = pytest.mark.gpu
+
+IMG_TOL, LOSS_TOL, GRAD_TOL = 1e-4, 1e-5, 1e-4
+
+
+@pytest.fixture(scope="module")
+def xw():
+    import xptwarp
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return xptwarp
+
+
+def _to_cuda(feats, preds):
+    f = {k: v.cuda() for k, v in feats.items()}
+    p = {"depth_ms": [d.cuda() for d in preds["depth_ms"]], "disp_ms": [d.cuda() for d in preds["disp_ms"]],
+         "pose": preds["pose"].cuda()}
+    return f, p
+
+
+def _plan_for(xw, feats, preds, lw, sw, gb, flags=0):
+    B, F, H, W, _ = feats["image5d"].shape
+    from xptwarp.engine import infer_scales
+    return xw.get_plan(0, B, F - 1, H, W, infer_scales(H, preds["depth_ms"]), sw, lw.get("L1", 0.0),
+                       lw.get("SSIM", 0.0), lw.get("smoothe", 0.0), gb, flags)
+
+
+def _run_total(plan, f, p, **kw):
+    img = f["image5d"]
+    r = plan.total_loss(img[:, :-1], img[:, -1], f["intrinsic"], p["depth_ms"], p["disp_ms"], p["pose"], **kw)
+    torch.cuda.synchronize()
+    return r
+
+
+@pytest.mark.parametrize("flags", [0, 1], ids=["fused", "unfused"])
+@pytest.mark.parametrize("name", CASES)
+def test_total_loss_against_golden(xw, name, flags):
+    g, g64 = load_case(name), load_case(name, "f64")
+    feats, preds, lw, sw, gb = case_inputs(g)
+    f, p = _to_cuda(feats, preds)
+    plan = _plan_for(xw, f, p, lw, sw, gb, flags)
+    r = _run_total(plan, f, p, want_grad=True, want_synth=True, want_mask=True, want_target_ms=True,
+                   want_source_grad=True, want_loss_batch=True)
+    losses = r["losses"].cpu().numpy()
+    assert relerr(losses[0], g["total"]) < LOSS_TOL and relerr(losses[0], g64["total"]) < LOSS_TOL
+    for i, k in enumerate(("L1", "SSIM", "smoothe")):
+        assert relerr(losses[1 + i], g["loss_" + k]) < LOSS_TOL, k
+        assert relerr(losses[1 + i], g64["loss_" + k]) < LOSS_TOL, k
+    # per-snippet losses sum to the by-type means
+    lb = r["loss_batch"].cpu().numpy()
+    assert np.allclose(lb.sum(axis=1) / gb, losses[1:4], rtol=1e-5)
+    for s in range(plan.S):
+        synth = r["synth_ms"][s].cpu().numpy()
+        assert np.abs(synth - g[f"synth_{s}"]).max() < IMG_TOL
+        assert np.abs(r["target_ms"][s].cpu().numpy() - g[f"target_{s}"]).max() < 1e-6
+        # validity mask: bit-compared against the reference's implied mask (synth == 0 where invalid)
+        mask = r["mask_ms"][s].cpu().numpy()
+        ref_invalid = np.all(g[f"synth_{s}"] == 0, axis=-1, keepdims=True)
+        assert ((mask == 0) != ref_invalid).sum() == 0
+        assert relerr(r["d_depth_ms"][s].cpu().numpy(), g[f"d_depth_{s}"]) < GRAD_TOL
+        assert relerr(r["d_depth_ms"][s].cpu().numpy(), g64[f"d_depth_{s}"]) < GRAD_TOL
+        assert relerr(r["d_disp_ms"][s].cpu().numpy(), g[f"d_disp_{s}"]) < GRAD_TOL
+    assert relerr(r["d_pose"].cpu().numpy(), g["d_pose"]) < GRAD_TOL
+    assert relerr(r["d_pose"].cpu().numpy(), g64["d_pose"]) < GRAD_TOL
+    assert relerr(r["d_source"].cpu().numpy(), g["d_source"]) < GRAD_TOL
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_reference_call_surface_with_autograd(xw, name):
+    """loss_factory -> TotalLoss(predictions, features) -> backward, like train_val.py:78-92."""
+    g = load_case(name)
+    feats, preds, lw, sw, gb = case_inputs(g)
+    f, p = _to_cuda(feats, preds)
+    for t in p["depth_ms"] + p["disp_ms"] + [p["pose"]]:
+        t.requires_grad_(True)
+    weights = dict(lw, L1_R=0.5, stereoPose=1.0, md2L1=0.0)          # dropped by loss_factory like in the reference
+    total_obj = xw.loss_factory({"image": 1, "intrinsic": 1}, weights, np.array(sw), stereo=False, batch_size=gb)
+    assert list(total_obj.loss_objects) == list(lw)
+    total, by_type = total_obj(p, f)
+    (2.0 * total).backward()
+    assert relerr(total.item(), g["total"]) < LOSS_TOL
+    for k in lw:
+        assert relerr(by_type[k].item(), g["loss_" + k]) < LOSS_TOL
+    assert relerr(p["pose"].grad.cpu().numpy(), 2.0 * g["d_pose"]) < GRAD_TOL
+    for s in range(len(p["depth_ms"])):
+        assert p["depth_ms"][s].grad.shape == p["depth_ms"][s].shape
+        assert relerr(p["depth_ms"][s].grad.cpu().numpy(), 2.0 * g[f"d_depth_{s}"]) < GRAD_TOL
+        assert relerr(p["disp_ms"][s].grad.cpu().numpy(), 2.0 * g[f"d_disp_{s}"]) < GRAD_TOL
+
+
+def test_generic_loss_object_loop_matches_fused(xw):
+    """TotalLoss with objects called one by one (reference losses.py:46-52) through the standalone
+    kernels + torch autograd equals the fused launch."""
+    g = load_case("case_small_t1")
+    feats, preds, lw, sw, gb = case_inputs(g)
+    f, p = _to_cuda(feats, preds)
+    for t in p["depth_ms"] + p["disp_ms"] + [p["pose"]]:
+        t.requires_grad_(True)
+    total_obj = xw.loss_factory({"image": 1, "intrinsic": 1}, lw, np.array(sw), batch_size=gb)
+    total_obj._fused_ok = lambda *_: False
+    total, by_type = total_obj(p, f)
+    total.backward()
+    assert relerr(total.item(), g["total"]) < LOSS_TOL
+    for k in lw:
+        assert relerr(by_type[k].item(), g["loss_" + k]) < LOSS_TOL
+    assert relerr(p["pose"].grad.cpu().numpy(), g["d_pose"]) < GRAD_TOL
+    for s in range(4):
+        assert relerr(p["depth_ms"][s].grad.cpu().numpy(), g[f"d_depth_{s}"]) < GRAD_TOL
+        assert relerr(p["disp_ms"][s].grad.cpu().numpy(), g[f"d_disp_{s}"]) < GRAD_TOL
+
+
+def test_pieces_against_golden(xw):
+    g = load_case("pieces")
+    T = xw.pose_rvec2matr_batch_tf(torch.tensor(g["poses"]).cuda()).cpu().numpy()
+    assert np.abs(T - g["T_tf"]).max() < 1e-6 and np.abs(T - g["T_np"]).max() < 1e-6
+    # SynthesizeMultiScale + multi_scale_like_depth
+    img = torch.tensor(g["syn_image5d"]).cuda()
+    depth_ms = [torch.tensor(g[f"syn_depth_{s}"]).cuda() for s in range(2)]
+    synth = xw.SynthesizeMultiScale()(img[:, :-1], torch.tensor(g["syn_intrinsic"]).cuda(), depth_ms,
+                                      torch.tensor(g["syn_pose"]).cuda())
+    tgt = xw.multi_scale_like_depth(img[:, -1], depth_ms)
+    for s in range(2):
+        assert np.abs(synth[s].cpu().numpy() - g[f"syn_synth_{s}"]).max() < IMG_TOL
+        assert np.abs(tgt[s].cpu().numpy() - g[f"syn_target_{s}"]).max() < 1e-6
+    # per-scale photometric terms on given tensors (loss_util.py) with black pixels
+    synt, orig = torch.tensor(g["synt"]).cuda(), torch.tensor(g["orig"]).cuda()
+    augm = {"synth_target_ms": [synt], "target_ms": [orig]}
+    for m, key in (("L1", "l1"), ("SSIM", "ssim")):
+        lb = xw.PhotometricLossMultiScale(m, np.array([1.0]))(None, None, augm).cpu().numpy()
+        assert relerr(lb, g[key]) < LOSS_TOL, m
+    lb = xw.PhotometricLossMultiScale("L2", np.array([1.0]))(None, None, augm).cpu().numpy()
+    assert relerr(lb, g["l2_map"].mean(axis=(1, 2, 3, 4))) < LOSS_TOL
+
+
+@pytest.mark.parametrize("B,H,W,adv", [(2, 128, 384, False), (1, 64, 96, True), (3, 40, 72, False)])
+def test_against_oracle_on_seeded_inputs(xw, B, H, W, adv):
+    from oracle import xpt_oracle as orc
+    feats, preds = orc.make_inputs(B, H, W, seed=777 + B, adversarial=adv)
+    lw, sw = orc.LOSS_RIGID_T2, orc.SCALE_WEIGHT_T2
+    ref = orc.loss_and_grads(feats, preds, lw, sw, None, want_source_grad=True)
+    f64 = {k: v.double() for k, v in feats.items()}
+    p64 = {"depth_ms": [d.double() for d in preds["depth_ms"]], "disp_ms": [d.double() for d in preds["disp_ms"]],
+           "pose": preds["pose"].double()}
+    ref64 = orc.loss_and_grads(f64, p64, lw, sw, None)
+    f, p = _to_cuda(feats, preds)
+    plan = _plan_for(xw, f, p, lw, sw, B)
+    r = _run_total(plan, f, p, want_grad=True, want_synth=True, want_mask=True, want_source_grad=True)
+    losses = r["losses"].cpu().numpy()
+    assert relerr(losses[0], ref64["total"].numpy()) < LOSS_TOL
+    for i, k in enumerate(("L1", "SSIM", "smoothe")):
+        assert relerr(losses[1 + i], ref64["by_type"][k].numpy()) < LOSS_TOL
+    mism = 0
+    for s in range(plan.S):
+        a, b = r["synth_ms"][s].cpu().numpy(), ref["synth_ms"][s].numpy()
+        inv_a, inv_b = (r["mask_ms"][s].cpu().numpy() == 0), np.all(b == 0, axis=-1, keepdims=True)
+        flips = inv_a != inv_b              # 1-ulp coordinate differences flip validity at integer crossings
+        mism += int(flips.sum())
+        keep = ~np.broadcast_to(flips, a.shape)
+        assert np.abs(a - b)[keep].max() < IMG_TOL
+        ok, msg = grad_close(r["d_depth_ms"][s].cpu().numpy(), ref["d_depth_ms"][s].numpy(),
+                             ref64["d_depth_ms"][s].numpy(), GRAD_TOL)
+        assert ok, f"d_depth[{s}]: {msg}"
+        assert relerr(r["d_disp_ms"][s].cpu().numpy(), ref64["d_disp_ms"][s].numpy()) < GRAD_TOL
+    assert mism <= max(2, int(2e-6 * B * 4 * H * W)), f"{mism} validity-mask flips"
+    # the pose gradient sums over every pixel, the discontinuous ones included: it may be as far from
+    # the exact answer as the fp32 oracle itself is (x3), never worse than that
+    pose_tol = max(GRAD_TOL, 3 * relerr(ref["d_pose"].numpy(), ref64["d_pose"].numpy()))
+    assert relerr(r["d_pose"].cpu().numpy(), ref64["d_pose"].numpy()) < pose_tol
+    ok, msg = grad_close(r["d_source"].cpu().numpy(), ref["d_source"].numpy(), ref["d_source"].numpy(), GRAD_TOL)
+    assert ok, f"d_source: {msg}"
+
+
+def test_synthesize_autograd_against_oracle(xw):
+    from oracle import xpt_oracle as orc
+    feats, preds = orc.make_inputs(2, 48, 80, N=3, seed=4242)
+    src = feats["image5d"][:, :-1].clone().requires_grad_(True)
+    depth = [d.clone().requires_grad_(True) for d in preds["depth_ms"]]
+    pose = preds["pose"].clone().requires_grad_(True)
+    out = orc.synthesize_multi_scale(src, feats["intrinsic"], depth, pose)
+    gen = torch.Generator().manual_seed(1)
+    ups = [torch.randn(o.shape, generator=gen) for o in out]
+    sum((o * u).sum() for o, u in zip(out, ups)).backward()
+    csrc = feats["image5d"][:, :-1].cuda().requires_grad_(True)
+    cdepth = [d.cuda().requires_grad_(True) for d in preds["depth_ms"]]
+    cpose = preds["pose"].cuda().requires_grad_(True)
+    cout, cmask = xw.SynthesizeMultiScale()(csrc, feats["intrinsic"].cuda(), cdepth, cpose, return_mask=True)
+    sum((o * u.cuda()).sum() for o, u in zip(cout, ups)).backward()
+    for s in range(4):
+        assert np.abs(cout[s].detach().cpu().numpy() - out[s].detach().numpy()).max() < IMG_TOL
+        ok, msg = grad_close(cdepth[s].grad.cpu().numpy(), depth[s].grad.numpy(), depth[s].grad.numpy(), GRAD_TOL)
+        assert ok, msg
+        assert set(np.unique(cmask[s].cpu().numpy())) <= {0.0, 1.0}
+    assert relerr(cpose.grad.cpu().numpy(), pose.grad.numpy()) < GRAD_TOL
+    assert relerr(csrc.grad.cpu().numpy(), src.grad.numpy()) < GRAD_TOL
+
+
+def test_edge_cases(xw):
+    """all-zero depth (everything invalid), identity-like pose, smallest legal level (2x2)."""
+    from oracle import xpt_oracle as orc
+    feats, preds = orc.make_inputs(1, 16, 16, N=1, seed=9)
+    preds["depth_ms"][0].zero_()
+    lw, sw = orc.LOSS_RIGID_T1, orc.SCALE_WEIGHT_T1
+    ref = orc.loss_and_grads(feats, preds, lw, sw)
+    f, p = _to_cuda(feats, preds)
+    plan = _plan_for(xw, f, p, lw, sw, 1)
+    r = _run_total(plan, f, p, want_grad=True, want_synth=True, want_mask=True)
+    assert float(r["synth_ms"][0].abs().max()) == 0.0 and float(r["mask_ms"][0].max()) == 0.0
+    assert float(r["d_depth_ms"][0].abs().max()) == 0.0
+    assert relerr(r["losses"].cpu().numpy()[0], ref["total"].numpy()) < LOSS_TOL
+    assert relerr(r["d_pose"].cpu().numpy(), ref["d_pose"].numpy()) < GRAD_TOL
+    # zero rotation: forward is the identity rotation; the reference's pose gradient is NaN there
+    preds["pose"][..., 3:] = 0
+    T = xw.pose_rvec2matr_batch_tf(preds["pose"].cuda()).cpu().numpy()
+    assert np.allclose(T[0, 0, :3, :3], np.eye(3))
+
+
+def test_full_size_properties(xw):
+    """BASELINE config 2 (B=8, 128x384): size-independent properties instead of the slow oracle."""
+    from oracle import xpt_oracle as orc
+    feats, preds = orc.make_inputs(8, 128, 384, seed=20211 + 2000)
+    lw, sw = orc.LOSS_RIGID_T1, orc.SCALE_WEIGHT_T1
+    f, p = _to_cuda(feats, preds)
+    plan = _plan_for(xw, f, p, lw, sw, 8)
+    r1 = _run_total(plan, f, p, want_grad=True, want_loss_batch=True, want_synth=True)
+    r1 = {k: ([t.clone() for t in v] if isinstance(v, list) else v.clone()) for k, v in r1.items()}
+    # (a) fused == unfused
+    plan_u = _plan_for(xw, f, p, lw, sw, 8, flags=1)
+    ru = _run_total(plan_u, f, p, want_grad=True, want_loss_batch=True)
+    assert relerr(ru["losses"].cpu().numpy(), r1["losses"].cpu().numpy()) < 1e-6
+    assert relerr(ru["d_pose"].cpu().numpy(), r1["d_pose"].cpu().numpy()) < 1e-5
+    for s in range(4):
+        assert relerr(ru["d_depth_ms"][s].cpu().numpy(), r1["d_depth_ms"][s].cpu().numpy()) < 1e-5
+    # (b) gradients are linear in the upstream gradient
+    r3 = _run_total(plan, f, p, want_grad=True, grad_scale=3.0)
+    assert relerr(r3["d_pose"].cpu().numpy(), 3.0 * r1["d_pose"].cpu().numpy()) < 1e-6
+    assert relerr(r3["d_depth_ms"][1].cpu().numpy(), 3.0 * r1["d_depth_ms"][1].cpu().numpy()) < 1e-6
+    # (c) snippets are independent: permuting the batch permutes the per-snippet results
+    perm = torch.tensor([3, 0, 7, 1, 6, 2, 5, 4])
+    fp = {k: v[perm.cuda()] for k, v in f.items()}
+    pp = {"depth_ms": [d[perm.cuda()] for d in p["depth_ms"]], "disp_ms": [d[perm.cuda()] for d in p["disp_ms"]],
+          "pose": p["pose"][perm.cuda()]}
+    rp = _run_total(plan, fp, pp, want_grad=True, want_loss_batch=True)
+    assert torch.equal(rp["loss_batch"], r1["loss_batch"][:, perm.cuda()])
+    assert torch.equal(rp["d_depth_ms"][0], r1["d_depth_ms"][0][perm.cuda()])
+    assert relerr(rp["losses"].cpu().numpy(), r1["losses"].cpu().numpy()) < 1e-6
+    # (d) the oracle agrees on one snippet of the full-size batch (global batch 8)
+    f1 = {k: v[2:3] for k, v in feats.items()}
+    p1 = {"depth_ms": [d[2:3] for d in preds["depth_ms"]], "disp_ms": [d[2:3] for d in preds["disp_ms"]],
+          "pose": preds["pose"][2:3]}
+    ref = orc.loss_and_grads(f1, p1, lw, sw, global_batch=8)
+    ref64 = orc.loss_and_grads({k: v.double() for k, v in f1.items()},
+                               {"depth_ms": [d.double() for d in p1["depth_ms"]],
+                                "disp_ms": [d.double() for d in p1["disp_ms"]], "pose": p1["pose"].double()},
+                               lw, sw, global_batch=8)
+    pose_tol = max(GRAD_TOL, 3 * relerr(ref["d_pose"].numpy(), ref64["d_pose"].numpy()))
+    assert relerr(r1["d_pose"][2:3].cpu().numpy(), ref64["d_pose"].numpy()) < pose_tol
+    ok, msg = grad_close(r1["d_depth_ms"][0][2:3].cpu().numpy(), ref["d_depth_ms"][0].numpy(),
+                         ref64["d_depth_ms"][0].numpy(), GRAD_TOL)
+    assert ok, msg
+    assert np.abs(r1["synth_ms"][0][2:3].cpu().numpy() - ref["synth_ms"][0].numpy()).max() < IMG_TOL
+
+
+def test_host_buffer_entry_point(xw):
+    """xpt_total_loss_host (host pointers, copies inside) equals the device entry point."""
+    import ctypes as C
+    from xptwarp import _cabi
+    g = load_case("case_small_t1")
+    feats, preds, lw, sw, gb = case_inputs(g)
+    f, p = _to_cuda(feats, preds)
+    plan = _plan_for(xw, f, p, lw, sw, gb)
+    r = _run_total(plan, f, p, want_grad=True)
+    img = feats["image5d"].contiguous().pin_memory()
+    B, F, H, W, _ = img.shape
+    fr = _cabi.XptFrames()
+    fr.source = img.data_ptr()
+    fr.source_batch_stride, fr.source_frame_stride = img.stride(0), img.stride(1)
+    fr.target = img.data_ptr() + (F - 1) * img.stride(1) * 4
+    fr.target_batch_stride = img.stride(0)
+    K = feats["intrinsic"].contiguous()
+    fr.intrinsic = K.data_ptr()
+    out = _cabi.XptLossOutputs()
+    losses, d_pose = torch.zeros(4), torch.zeros(B, F - 1, 6)
+    d_depth = [torch.zeros_like(d) for d in preds["depth_ms"]]
+    out.losses, out.d_pose, out.grad_scale = losses.data_ptr(), d_pose.data_ptr(), 1.0
+    for s, t in enumerate(d_depth):
+        out.d_depth_ms[s] = t.data_ptr()
+    pose = preds["pose"].contiguous()
+    _cabi.check(plan._lib.xpt_total_loss_host(
+        plan.handle, C.byref(fr), C.byref(_cabi.ptr_array([d.data_ptr() for d in preds["depth_ms"]])),
+        C.byref(_cabi.ptr_array([d.data_ptr() for d in preds["disp_ms"]])), pose.data_ptr(), C.byref(out), None))
+    assert torch.equal(losses, r["losses"].cpu())
+    assert torch.equal(d_pose, r["d_pose"].cpu())
+    for s in range(4):
+        assert torch.equal(d_depth[s], r["d_depth_ms"][s].cpu().reshape(d_depth[s].shape))
+
+
+def test_dlpack_only_producer_and_errors(xw):
+    class OnlyDLPack:            # stands in for a TF/CuPy tensor: nothing but the DLPack protocol
+        def __init__(self, t):
+            self._t = t
+
+        def __dlpack__(self, stream=None):
+            return self._t.__dlpack__()
+
+        def __dlpack_device__(self):
+            return self._t.__dlpack_device__()
+    g = load_case("pieces")
+    img = torch.tensor(g["syn_image5d"]).cuda()
+    depth_ms = [torch.tensor(g[f"syn_depth_{s}"]).cuda() for s in range(2)]
+    K, pose = torch.tensor(g["syn_intrinsic"]).cuda(), torch.tensor(g["syn_pose"]).cuda()
+    src = img[:, :-1]
+    a = xw.SynthesizeMultiScale()(OnlyDLPack(src), OnlyDLPack(K), [OnlyDLPack(d) for d in depth_ms], OnlyDLPack(pose))
+    b = xw.SynthesizeMultiScale()(src, K, depth_ms, pose)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    with pytest.raises(xw.WrongInputException):
+        xw.SynthesizeMultiScale()(src.cpu(), K, depth_ms, pose)
+    with pytest.raises(xw.WrongInputException):
+        xw.SynthesizeMultiScale()(src, K, depth_ms, pose[:, :1])
+    with pytest.raises(xw.WrongInputException):
+        xw.SynthesizeMultiScale()(src.double(), K, depth_ms, pose)

@@ -1,0 +1,1047 @@
+// xpt_kernels.cuh -- sm_100a device code for the xpt-mde view-synthesis + loss path.
+//
+// Reference semantics restated in SURVEY.md Appendix A; citations are to the
+// reference checkout (model/synthesize/*.py, model/loss_and_metric/*.py,
+// utils/convert_pose.py).  Everything is fp32 and channel-last; there is no dense
+// contraction here, so no tensor cores: the kernels are gather / stencil /
+// reduction work bounded by HBM and L1/shared-memory bandwidth.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace xpt {
+
+constexpr int kMaxScales = 8;
+constexpr int kMaxSrc = 8;
+constexpr float kC1 = 0.01f * 0.01f;   // loss_util.py:68
+constexpr float kC2 = 0.03f * 0.03f;   // loss_util.py:69
+
+// One pyramid level as the kernels see it.
+struct Level {
+  int s;              // integer down-scale
+  int H, W;           // level size
+  int tiles_x, tiles_y;
+  int slot_base;      // first partial-sum slot of this level inside one snippet
+  const float* src;   // source level [B,N,H,W,3]
+  long long src_bs, src_fs;   // batch / frame strides in elements
+  const float* tgt;   // target level [B,H,W,3]
+  long long tgt_bs;
+};
+
+struct LevelTable {
+  int S;
+  Level lv[kMaxScales];
+};
+
+template <typename T>
+struct PtrTable {
+  T* p[kMaxScales];
+};
+
+// geometry scratch: per (b, level): K_s (9) + inv(K_s) (9); per (b, n): R (9) + t (3)
+constexpr int kGeoK = 18;
+constexpr int kGeoT = 12;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------
+// geometry: pose twist -> [R|t] (utils/convert_pose.py:32-71, negated skew
+// matrix :53-56, identity below 1e-8 :65) and per-level intrinsics
+// (synthesize_base.py:66-71) with their inverses (synthesize_base.py:138).
+// Evaluated in fp64 and rounded once: B*N + B*S tiny problems.
+// ---------------------------------------------------------------------------
+__global__ void k_geometry(const float* __restrict__ pose, const float* __restrict__ intrinsic,
+                           float* __restrict__ geoK, float* __restrict__ geoT,
+                           float* __restrict__ matr_out, int B, int N, LevelTable lt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B * N) {
+    const float* p = pose + (size_t)i * 6;
+    double w1 = p[3], w2 = p[4], w3 = p[5];
+    float thf = sqrtf(p[3] * p[3] + p[4] * p[4] + p[5] * p[5]);
+    double th = sqrt(w1 * w1 + w2 * w2 + w3 * w3);
+    double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    if (!(fabsf(thf) < 1e-8f)) {
+      w1 /= th; w2 /= th; w3 /= th;
+      double Wm[9] = {0, w3, -w2, -w3, 0, w1, w2, -w1, 0};
+      double sn = sin(th), cs = 1.0 - cos(th);
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) {
+          double ww = 0;
+          for (int k = 0; k < 3; ++k) ww += Wm[r * 3 + k] * Wm[k * 3 + c];
+          R[r * 3 + c] += Wm[r * 3 + c] * sn + ww * cs;
+        }
+    }
+    if (geoT) {
+      float* g = geoT + (size_t)i * kGeoT;
+      for (int k = 0; k < 9; ++k) g[k] = (float)R[k];
+      g[9] = p[0]; g[10] = p[1]; g[11] = p[2];
+    }
+    if (matr_out) {
+      float* m = matr_out + (size_t)i * 16;
+      for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) m[r * 4 + c] = (float)R[r * 3 + c];
+        m[r * 4 + 3] = p[r];
+      }
+      m[12] = 0.f; m[13] = 0.f; m[14] = 0.f; m[15] = 1.f;
+    }
+  }
+  if (geoK && i < B * lt.S) {
+    int b = i / lt.S, l = i % lt.S;
+    const float* K = intrinsic + (size_t)b * 9;
+    float sc = (float)lt.lv[l].s;
+    float Ks[9];
+    for (int k = 0; k < 6; ++k) Ks[k] = K[k] / sc;      // rows 0-1 divided, fp32 like the reference
+    Ks[6] = 0.f; Ks[7] = 0.f; Ks[8] = 1.f;
+    double a = Ks[0], bb = Ks[1], c = Ks[2], d = Ks[3], e = Ks[4], f = Ks[5], g = Ks[6], h = Ks[7], k9 = Ks[8];
+    double det = a * (e * k9 - f * h) - bb * (d * k9 - f * g) + c * (d * h - e * g);
+    double inv[9] = {(e * k9 - f * h) / det, (c * h - bb * k9) / det, (bb * f - c * e) / det,
+                     (f * g - d * k9) / det, (a * k9 - c * g) / det, (c * d - a * f) / det,
+                     (d * h - e * g) / det, (bb * g - a * h) / det, (a * e - bb * d) / det};
+    float* o = geoK + (size_t)i * kGeoK;
+    for (int k = 0; k < 9; ++k) { o[k] = Ks[k]; o[9 + k] = (float)inv[k]; }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// pyramids: tf.image.resize(bilinear), TF2 half-pixel centres, no antialias
+// (synthesize_base.py:74-85, util_funcs.py:163-175).  For an integer factor s the
+// sample position is s*d + (s-1)/2: even s -> the centre 2x2 with weights 1/2,
+// evaluated as nested lerps like TF's kernel; odd s -> the centre pixel.
+// One thread per output pixel of (level, frame); frame N of a snippet is the target.
+// ---------------------------------------------------------------------------
+struct PyramidArgs {
+  const float* source; long long src_bs, src_fs;
+  const float* target; long long tgt_bs;
+  int B, N, H, W;
+  int S;                       // number of levels
+  int s[kMaxScales];
+  float* src_out[kMaxScales];  // [B,N,h,w,3] (NULL for s == 1)
+  float* tgt_out[kMaxScales];  // [B,h,w,3]   (NULL = not wanted)
+};
+
+__global__ void k_pyramid(PyramidArgs a) {
+  const int l = blockIdx.y;
+  const int s = a.s[l];
+  const int h = a.H / s, w = a.W / s;
+  const int nfr = a.N + 1;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)a.B * nfr * h * w;
+  if (idx >= total) return;
+  int x = (int)(idx % w);
+  long long r = idx / w;
+  int y = (int)(r % h); r /= h;
+  int f = (int)(r % nfr);
+  int b = (int)(r / nfr);
+  const float* in;
+  float* out;
+  if (f < a.N) {
+    if (a.src_out[l] == nullptr) return;
+    in = a.source + b * a.src_bs + f * a.src_fs;
+    out = a.src_out[l] + (((long long)(b * a.N + f) * h + y) * w + x) * 3;
+  } else {
+    if (a.tgt_out[l] == nullptr || a.target == nullptr) return;
+    in = a.target + b * a.tgt_bs;
+    out = a.tgt_out[l] + (((long long)b * h + y) * w + x) * 3;
+  }
+  const long long rowst = (long long)a.W * 3;
+  if (s == 1) {
+    const float* p = in + y * rowst + x * 3;
+    out[0] = p[0]; out[1] = p[1]; out[2] = p[2];
+  } else if (s & 1) {
+    const float* p = in + (long long)(y * s + s / 2) * rowst + (x * s + s / 2) * 3;
+    out[0] = p[0]; out[1] = p[1]; out[2] = p[2];
+  } else {
+    const float* p0 = in + (long long)(y * s + s / 2 - 1) * rowst + (x * s + s / 2 - 1) * 3;
+    const float* p1 = p0 + rowst;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float tl = __ldg(p0 + c), tr = __ldg(p0 + 3 + c), bl = __ldg(p1 + c), br = __ldg(p1 + 3 + c);
+      float top = tl + (tr - tl) * 0.5f;
+      float bot = bl + (br - bl) * 0.5f;
+      out[c] = top + (bot - top) * 0.5f;
+    }
+  }
+}
+
+// adjoint of the source pyramid: d_source[full] += resize^T(d_source_level) for s > 1
+// (each level pixel spreads 1/4 to its centre 2x2 / 1 to the centre pixel).
+struct PyramidAdjArgs {
+  float* d_source;             // [B,N,H,W,3] dense, already holding the level-0 gradient
+  int BN, H, W, S;
+  int s[kMaxScales];
+  const float* d_level[kMaxScales];   // [B*N,h,w,3] for s > 1
+};
+
+__global__ void k_pyramid_adjoint(PyramidAdjArgs a) {
+  // one thread per full-res pixel of one frame: gathers from every level that touches it
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)a.BN * a.H * a.W;
+  if (idx >= total) return;
+  int x = (int)(idx % a.W);
+  long long r = idx / a.W;
+  int y = (int)(r % a.H);
+  int f = (int)(r / a.H);
+  float acc[3] = {0.f, 0.f, 0.f};
+  for (int l = 0; l < a.S; ++l) {
+    int s = a.s[l];
+    if (s == 1 || a.d_level[l] == nullptr) continue;
+    int h = a.H / s, w = a.W / s;
+    int ys = y / s, xs = x / s, ry = y % s, rx = x % s;
+    float wt;
+    if (s & 1) {
+      if (ry != s / 2 || rx != s / 2) continue;
+      wt = 1.f;
+    } else {
+      if ((ry != s / 2 - 1 && ry != s / 2) || (rx != s / 2 - 1 && rx != s / 2)) continue;
+      wt = 0.25f;
+    }
+    const float* g = a.d_level[l] + (((long long)f * h + ys) * w + xs) * 3;
+    acc[0] += wt * g[0]; acc[1] += wt * g[1]; acc[2] += wt * g[2];
+  }
+  float* o = a.d_source + idx * 3;
+  o[0] += acc[0]; o[1] += acc[1]; o[2] += acc[2];
+}
+
+// ---------------------------------------------------------------------------
+// inverse warp of one target pixel into one source frame.
+// Order of operations follows the reference:
+//   r = inv(K_s) (u,v,1)   synthesize_base.py:138
+//   X = r * D              :141
+//   Y = R X + t            :158
+//   p = K_s Y              :173
+//   (u',v') = p.xy / (p.z + 1e-10)   :176-177  -- no positive-depth test
+// ---------------------------------------------------------------------------
+struct Proj {
+  float u, v, den;     // source pixel coordinates and the divisor
+  float X0, X1, X2;    // target-frame 3-D point
+};
+
+__device__ __forceinline__ void ray_of_pixel(const float* __restrict__ Ki, float uu, float vv,
+                                             float& r0, float& r1, float& r2) {
+  r0 = Ki[0] * uu + Ki[1] * vv + Ki[2];
+  r1 = Ki[3] * uu + Ki[4] * vv + Ki[5];
+  r2 = Ki[6] * uu + Ki[7] * vv + Ki[8];
+}
+
+__device__ __forceinline__ Proj project(const float* __restrict__ K, const float* __restrict__ T,
+                                        float r0, float r1, float r2, float D) {
+  Proj o;
+  o.X0 = r0 * D; o.X1 = r1 * D; o.X2 = r2 * D;
+  float Y0 = T[0] * o.X0 + T[1] * o.X1 + T[2] * o.X2 + T[9];
+  float Y1 = T[3] * o.X0 + T[4] * o.X1 + T[5] * o.X2 + T[10];
+  float Y2 = T[6] * o.X0 + T[7] * o.X1 + T[8] * o.X2 + T[11];
+  float p0 = K[0] * Y0 + K[1] * Y1 + K[2] * Y2;
+  float p1 = K[3] * Y0 + K[4] * Y1 + K[5] * Y2;
+  float p2 = K[6] * Y0 + K[7] * Y1 + K[8] * Y2;
+  o.den = p2 + 1e-10f;
+  o.u = p0 / o.den;
+  o.v = p1 / o.den;
+  return o;
+}
+
+// bilinear tap set of one sample (bilinear_interp.py:34-100)
+struct Taps {
+  bool valid;
+  int iu, iv;                  // floor(u), floor(v)
+  float w_uf, w_uc, w_vf, w_vc;
+};
+
+__device__ __forceinline__ Taps make_taps(float u, float v, float D, int W, int H) {
+  Taps t;
+  float uf = floorf(u), vf = floorf(v);
+  // valid <=> 0 <= floor(u) <= W-2 and 0 <= floor(v) <= H-2 and D != 0 (:53-76); NaN compares false
+  t.valid = (uf >= 0.f) && (uf <= (float)(W - 2)) && (vf >= 0.f) && (vf <= (float)(H - 2)) && (D != 0.f);
+  t.iu = t.valid ? (int)uf : 0;
+  t.iv = t.valid ? (int)vf : 0;
+  t.w_uf = (uf + 1.f) - u;     // u_ceil - u
+  t.w_uc = u - uf;
+  t.w_vf = (vf + 1.f) - v;
+  t.w_vc = v - vf;
+  return t;
+}
+
+__device__ __forceinline__ void gather_taps(const float* __restrict__ img, int W, const Taps& t,
+                                            float I0[3], float I1[3], float I2[3], float I3[3]) {
+  // I0 = (vf,uf), I1 = (vc,uf), I2 = (vf,uc), I3 = (vc,uc)   (bilinear_interp.py:125-128)
+  const float* p = img + ((long long)t.iv * W + t.iu) * 3;
+  const float* q = p + (long long)W * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    I0[c] = __ldg(p + c);
+    I2[c] = __ldg(p + 3 + c);
+    I1[c] = __ldg(q + c);
+    I3[c] = __ldg(q + 3 + c);
+  }
+}
+
+__device__ __forceinline__ void warp_sample(const float* __restrict__ img, int W, int H, float u, float v,
+                                            float D, float y[3], bool& valid) {
+  Taps t = make_taps(u, v, D, W, H);
+  valid = t.valid;
+  if (!t.valid) { y[0] = y[1] = y[2] = 0.f; return; }
+  float I0[3], I1[3], I2[3], I3[3];
+  gather_taps(img, W, t, I0, I1, I2, I3);
+  float w0 = t.w_uf * t.w_vf, w1 = t.w_uf * t.w_vc, w2 = t.w_uc * t.w_vf, w3 = t.w_uc * t.w_vc;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) y[c] = ((I0[c] * w0 + I1[c] * w1) + I2[c] * w2) + I3[c] * w3;
+}
+
+// ---------------------------------------------------------------------------
+// standalone synthesis forward (SynthesizeMultiScale): one thread per target pixel
+// of (level, b), looping over the N sources so depth / ray are computed once.
+// ---------------------------------------------------------------------------
+struct WarpFwdArgs {
+  LevelTable lt;
+  int B, N;
+  const float* geoK; const float* geoT;
+  const float* depth[kMaxScales];
+  float* synth[kMaxScales];
+  float* mask[kMaxScales];     // may be NULL
+};
+
+__global__ void __launch_bounds__(256) k_warp_fwd(WarpFwdArgs a) {
+  const int l = blockIdx.y;
+  const Level& L = a.lt.lv[l];
+  const int P = L.H * L.W;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)a.B * P) return;
+  int b = (int)(idx / P);
+  int pix = (int)(idx % P);
+  int y = pix / L.W, x = pix % L.W;
+  const float* gk = a.geoK + ((size_t)b * a.lt.S + l) * kGeoK;
+  float K[9], Ki[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { K[k] = __ldg(gk + k); Ki[k] = __ldg(gk + 9 + k); }
+  float D = __ldg(a.depth[l] + idx);
+  float r0, r1, r2;
+  ray_of_pixel(Ki, (float)x, (float)y, r0, r1, r2);
+  for (int n = 0; n < a.N; ++n) {
+    const float* gt = a.geoT + ((size_t)b * a.N + n) * kGeoT;
+    float T[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) T[k] = __ldg(gt + k);
+    Proj pr = project(K, T, r0, r1, r2, D);
+    const float* img = L.src + b * L.src_bs + n * L.src_fs;
+    float yv[3]; bool valid;
+    warp_sample(img, L.W, L.H, pr.u, pr.v, D, yv, valid);
+    long long o = ((long long)(b * a.N + n) * P + pix);
+    float* so = a.synth[l] + o * 3;
+    so[0] = yv[0]; so[1] = yv[1]; so[2] = yv[2];
+    if (a.mask[l]) a.mask[l][o] = valid ? 1.f : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// bilinear + projection adjoint for one sample with upstream g = dL/dS.
+// Returns dL/dD contribution; accumulates dL/dR (9) and dL/dt (3) into acc[12];
+// optionally scatters dL/dsource with red.global.add.f32.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float sample_adjoint(const float* __restrict__ img, float* __restrict__ dimg,
+                                                int W, int H, const float* __restrict__ K,
+                                                const float* __restrict__ T, float r0, float r1, float r2,
+                                                float D, const Proj& pr, const float g[3], float acc[12]) {
+  Taps t = make_taps(pr.u, pr.v, D, W, H);
+  if (!t.valid) return 0.f;
+  float I0[3], I1[3], I2[3], I3[3];
+  gather_taps(img, W, t, I0, I1, I2, I3);
+  float gu = 0.f, gv = 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    gu += g[c] * (t.w_vf * (I2[c] - I0[c]) + t.w_vc * (I3[c] - I1[c]));
+    gv += g[c] * (t.w_uf * (I1[c] - I0[c]) + t.w_uc * (I3[c] - I2[c]));
+  }
+  if (dimg) {
+    float w0 = t.w_uf * t.w_vf, w1 = t.w_uf * t.w_vc, w2 = t.w_uc * t.w_vf, w3 = t.w_uc * t.w_vc;
+    float* p = dimg + ((long long)t.iv * W + t.iu) * 3;
+    float* q = p + (long long)W * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      atomicAdd(p + c, w0 * g[c]);
+      atomicAdd(p + 3 + c, w2 * g[c]);
+      atomicAdd(q + c, w1 * g[c]);
+      atomicAdd(q + 3 + c, w3 * g[c]);
+    }
+  }
+  float inv = 1.f / pr.den;
+  float gp0 = gu * inv, gp1 = gv * inv, gp2 = -(gu * pr.u + gv * pr.v) * inv;
+  float gY0 = K[0] * gp0 + K[3] * gp1 + K[6] * gp2;
+  float gY1 = K[1] * gp0 + K[4] * gp1 + K[7] * gp2;
+  float gY2 = K[2] * gp0 + K[5] * gp1 + K[8] * gp2;
+  acc[0] += gY0 * pr.X0; acc[1] += gY0 * pr.X1; acc[2] += gY0 * pr.X2;
+  acc[3] += gY1 * pr.X0; acc[4] += gY1 * pr.X1; acc[5] += gY1 * pr.X2;
+  acc[6] += gY2 * pr.X0; acc[7] += gY2 * pr.X1; acc[8] += gY2 * pr.X2;
+  acc[9] += gY0; acc[10] += gY1; acc[11] += gY2;
+  float gX0 = T[0] * gY0 + T[3] * gY1 + T[6] * gY2;
+  float gX1 = T[1] * gY0 + T[4] * gY1 + T[7] * gY2;
+  float gX2 = T[2] * gY0 + T[5] * gY1 + T[8] * gY2;
+  return gX0 * r0 + gX1 * r1 + gX2 * r2;
+}
+
+// block-level reduction of 12 pose accumulators; thread 0 stores them.
+template <int NT>
+__device__ __forceinline__ void block_reduce_store12(float acc[12], float* __restrict__ out, float* smem /* >= 12*NT/32 */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 12; ++k) {
+    float v = warp_sum(acc[k]);
+    if (lane == 0) smem[wid * 12 + k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 12) {
+    float v = 0.f;
+    for (int w = 0; w < NT / 32; ++w) v += smem[w * 12 + threadIdx.x];
+    out[threadIdx.x] = v;
+  }
+  __syncthreads();
+}
+
+// standalone synthesis backward: chunk of kWarpBwdChunk pixels of one (level, b) per block.
+constexpr int kWarpBwdThreads = 256;
+constexpr int kWarpBwdPix = 4;
+constexpr int kWarpBwdChunk = kWarpBwdThreads * kWarpBwdPix;
+
+struct WarpBwdArgs {
+  LevelTable lt;
+  int B, N;
+  const float* geoK; const float* geoT;
+  const float* depth[kMaxScales];
+  const float* gsynth[kMaxScales];     // dL/d synth
+  float* d_depth[kMaxScales];
+  float* d_src[kMaxScales];            // per-level dL/d source level (NULL = off), same layout as Level.src
+  long long d_src_bs[kMaxScales], d_src_fs[kMaxScales];
+  float* pose_part;                    // [B][slots][N][12]
+  int slots_per_b;
+  int chunk_base[kMaxScales];          // first chunk slot of each level
+};
+
+__global__ void __launch_bounds__(kWarpBwdThreads) k_warp_bwd(WarpBwdArgs a) {
+  __shared__ float red[12 * kWarpBwdThreads / 32];
+  const int l = blockIdx.z;
+  const Level& L = a.lt.lv[l];
+  const int P = L.H * L.W;
+  const int chunk = blockIdx.x;
+  if (chunk * kWarpBwdChunk >= P) return;
+  const int b = blockIdx.y;
+  const float* gk = a.geoK + ((size_t)b * a.lt.S + l) * kGeoK;
+  float K[9], Ki[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { K[k] = __ldg(gk + k); Ki[k] = __ldg(gk + 9 + k); }
+  float gD[kWarpBwdPix];
+  float D[kWarpBwdPix];
+#pragma unroll
+  for (int j = 0; j < kWarpBwdPix; ++j) {
+    int pix = chunk * kWarpBwdChunk + j * kWarpBwdThreads + threadIdx.x;
+    gD[j] = 0.f;
+    D[j] = pix < P ? __ldg(a.depth[l] + (long long)b * P + pix) : 0.f;
+  }
+  for (int n = 0; n < a.N; ++n) {
+    const float* gt = a.geoT + ((size_t)b * a.N + n) * kGeoT;
+    float T[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) T[k] = __ldg(gt + k);
+    const float* img = L.src + b * L.src_bs + n * L.src_fs;
+    float* dimg = a.d_src[l] ? a.d_src[l] + b * a.d_src_bs[l] + n * a.d_src_fs[l] : nullptr;
+    float acc[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int j = 0; j < kWarpBwdPix; ++j) {
+      int pix = chunk * kWarpBwdChunk + j * kWarpBwdThreads + threadIdx.x;
+      if (pix < P) {
+        int y = pix / L.W, x = pix % L.W;
+        float r0, r1, r2;
+        ray_of_pixel(Ki, (float)x, (float)y, r0, r1, r2);
+        Proj pr = project(K, T, r0, r1, r2, D[j]);
+        const float* gp = a.gsynth[l] + ((long long)(b * a.N + n) * P + pix) * 3;
+        float g[3] = {__ldg(gp), __ldg(gp + 1), __ldg(gp + 2)};
+        gD[j] += sample_adjoint(img, dimg, L.W, L.H, K, T, r0, r1, r2, D[j], pr, g, acc);
+      }
+    }
+    float* out = a.pose_part + (((size_t)b * a.slots_per_b + a.chunk_base[l] + chunk) * a.N + n) * 12;
+    block_reduce_store12<kWarpBwdThreads>(acc, out, red);
+  }
+#pragma unroll
+  for (int j = 0; j < kWarpBwdPix; ++j) {
+    int pix = chunk * kWarpBwdChunk + j * kWarpBwdThreads + threadIdx.x;
+    if (pix < P && a.d_depth[l]) a.d_depth[l][(long long)b * P + pix] = gD[j];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// pose epilogue: deterministic fp64 reduction of the per-block partials, then the
+// adjoint of Rodrigues' formula: with S = -[w]x, a = sin(th)/th, b = (1-cos th)/th^2,
+// R = I + a S + b S^2  =>  dR/dw_k = a E_k + a'(w_k/th) S + b (E_k S + S E_k) + b'(w_k/th) S^2.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_pose_epilogue(const float* __restrict__ pose_part, int slots_per_b,
+                                                       int slots_used, const float* __restrict__ pose,
+                                                       float* __restrict__ d_pose, int N, float scale) {
+  __shared__ double red[4][12];
+  const int bn = blockIdx.x;
+  const int b = bn / N, n = bn % N;
+  double acc[12];
+  for (int k = 0; k < 12; ++k) acc[k] = 0.0;
+  for (int sl = threadIdx.x; sl < slots_used; sl += blockDim.x) {
+    const float* p = pose_part + (((size_t)b * slots_per_b + sl) * N + n) * 12;
+    for (int k = 0; k < 12; ++k) acc[k] += (double)p[k];
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int k = 0; k < 12; ++k) {
+    double v = acc[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[wid][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double G[12];
+    for (int k = 0; k < 12; ++k) G[k] = (red[0][k] + red[1][k] + red[2][k] + red[3][k]) * (double)scale;
+    const float* p = pose + (size_t)bn * 6;
+    double w[3] = {p[3], p[4], p[5]};
+    double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+    double th = sqrt(th2);
+    float* o = d_pose + (size_t)bn * 6;
+    o[0] = (float)G[9]; o[1] = (float)G[10]; o[2] = (float)G[11];
+    if (th < 1e-8) {
+      // the reference's gradient is NaN here: propagate that, do not invent a value
+      o[3] = o[4] = o[5] = __int_as_float(0x7fc00000);
+    } else {
+      double Sm[9] = {0, w[2], -w[1], -w[2], 0, w[0], w[1], -w[0], 0};
+      double S2[9];
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) {
+          double v = 0;
+          for (int k = 0; k < 3; ++k) v += Sm[r * 3 + k] * Sm[k * 3 + c];
+          S2[r * 3 + c] = v;
+        }
+      double sn = sin(th), cs = cos(th);
+      double ca = sn / th, cb = (1.0 - cs) / th2;
+      double da = (th * cs - sn) / th2;                    // d(sin th / th)/d th
+      double db = (th * sn - 2.0 * (1.0 - cs)) / (th2 * th);   // d((1-cos th)/th^2)/d th
+      for (int k = 0; k < 3; ++k) {
+        double E[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        // E_k = d S / d w_k
+        if (k == 0) { E[5] = 1; E[7] = -1; }
+        if (k == 1) { E[2] = -1; E[6] = 1; }
+        if (k == 2) { E[1] = 1; E[3] = -1; }
+        double dth = w[k] / th;
+        double s = 0;
+        for (int r = 0; r < 3; ++r)
+          for (int c = 0; c < 3; ++c) {
+            double es = 0;
+            for (int j = 0; j < 3; ++j) es += E[r * 3 + j] * Sm[j * 3 + c] + Sm[r * 3 + j] * E[j * 3 + c];
+            double dR = ca * E[r * 3 + c] + da * dth * Sm[r * 3 + c] + cb * es + db * dth * S2[r * 3 + c];
+            s += G[r * 3 + c] * dR;
+          }
+        o[3 + k] = (float)s;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// photometric tile kernel.  One CTA = one (level, snippet, 32x16 tile), looping
+// over the N sources.  The warped tile y (with halo) lives in shared memory:
+//   FUSED : y is produced by the inverse warp in-kernel (north-star kernels 1+2+3)
+//   !FUSED: y is read from a synth tensor (standalone PhotometricLossMultiScale)
+// L1 (loss_util.py:6-25) and SSIM (loss_util.py:52-96) are evaluated from that
+// tile; with GRAD the SSIM/L1 adjoint is evaluated from the same tile (halo 2) and
+// either written out as dL/dsynth (!FUSED) or pushed straight through the bilinear
+// + projection adjoint (FUSED).
+// ---------------------------------------------------------------------------
+constexpr int kTW = 32, kTH = 16, kPhotoThreads = 256;
+constexpr int kPixPerThread = kTW * kTH / kPhotoThreads;   // 2
+
+struct PhotoArgs {
+  LevelTable lt;
+  int B, N;
+  int tiles_per_b;                     // sum over levels of tiles
+  int first_tile[kMaxScales + 1];      // prefix of tiles per level (per snippet)
+  // inputs
+  const float* synth[kMaxScales];      // !FUSED: [B,N,h,w,3]
+  const float* geoK; const float* geoT;
+  const float* depth[kMaxScales];      // FUSED
+  const float* disp[kMaxScales];       // FUSED + smoothness
+  // loss configuration
+  int l1_kind;                         // 0 none, 1 = L1, 2 = L2 (reported in column 0)
+  int do_ssim;
+  int do_smooth;                       // FUSED only
+  float norm_photo[kMaxScales];        // sw_s / (N*h*w*3)
+  float norm_sm_x[kMaxScales];         // sw_s * 0.5 / (h*(w-1)) / s
+  float norm_sm_y[kMaxScales];         // sw_s * 0.5 / ((h-1)*w) / s
+  float grad_factor;
+  // gradient coefficients: dTotal/d(per-snippet loss k) ; multiplied by gbatch[b] when non-NULL
+  float gcoef_l1, gcoef_ssim, gcoef_smooth;
+  const float* gbatch;
+  // outputs
+  float* loss_part;                    // [B][slots][3]
+  int slots_per_b;
+  float* synth_out[kMaxScales];        // FUSED optional
+  float* mask_out[kMaxScales];         // FUSED optional
+  float* gsynth[kMaxScales];           // !FUSED GRAD: dL/d synth
+  float* d_depth[kMaxScales];          // FUSED GRAD
+  float* d_disp[kMaxScales];           // FUSED GRAD + smoothness
+  float* d_src[kMaxScales];            // FUSED GRAD optional
+  long long d_src_bs[kMaxScales], d_src_fs[kMaxScales];
+  float* pose_part;                    // FUSED GRAD: [B][slots][N][12]
+};
+
+template <bool GRAD>
+struct PhotoSmem {
+  static constexpr int HL = GRAD ? 2 : 1;
+  static constexpr int RW = kTW + 2 * HL, RH = kTH + 2 * HL;        // y / x region
+  static constexpr int SW = kTW + 2 * (HL - 1), SH = kTH + 2 * (HL - 1);   // stats region
+  static constexpr int kRegion = RW * RH, kStats = SW * SH;
+  static constexpr int kFloats = 3 * kRegion * 2 + 3 * kStats * 2 + (GRAD ? 3 * kStats * 3 : 0) + 128;
+  static constexpr size_t kBytes = sizeof(float) * kFloats;
+};
+
+__device__ __forceinline__ float sgnf(float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); }
+
+template <bool FUSED, bool GRAD>
+__global__ void __launch_bounds__(kPhotoThreads) k_photo(PhotoArgs a) {
+  using SM = PhotoSmem<GRAD>;
+  constexpr int HL = SM::HL, RW = SM::RW, SW = SM::SW;
+  constexpr int HS = HL - 1;     // halo of the stats region
+  extern __shared__ float smem[];
+  float* sx = smem;                       // [3][RH][RW] target
+  float* sy = sx + 3 * SM::kRegion;       // [3][RH][RW] warped
+  float* smx = sy + 3 * SM::kRegion;      // [3][SH][SW] mu_x
+  float* ssx = smx + 3 * SM::kStats;      // [3][SH][SW] sigma_x
+  float* sA = ssx + 3 * SM::kStats;       // GRAD: [3][SH][SW] each
+  float* sB = sA + (GRAD ? 3 * SM::kStats : 0);
+  float* sC = sB + (GRAD ? 3 * SM::kStats : 0);
+  float* red = sC + (GRAD ? 3 * SM::kStats : 0);   // 128 floats
+
+  // ---- which tile -------------------------------------------------------
+  int t = blockIdx.x;
+  const int b = blockIdx.y;
+  int l = 0;
+  while (l + 1 < a.lt.S && t >= a.first_tile[l + 1]) ++l;
+  t -= a.first_tile[l];
+  const Level& L = a.lt.lv[l];
+  const int H = L.H, W = L.W, P = H * W;
+  const int ty0 = (t / L.tiles_x) * kTH, tx0 = (t % L.tiles_x) * kTW;
+  const int tid = threadIdx.x;
+  const int slot = L.slot_base + t;
+
+  float K[9], Ki[9];
+  if (FUSED) {
+    const float* gk = a.geoK + ((size_t)b * a.lt.S + l) * kGeoK;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { K[k] = __ldg(gk + k); Ki[k] = __ldg(gk + 9 + k); }
+  }
+
+  // ---- target tile + its window statistics (shared by all N sources) ------
+  const float* tgt = L.tgt + b * L.tgt_bs;
+  for (int i = tid; i < SM::kRegion; i += kPhotoThreads) {
+    int ry = i / RW, rx = i % RW;
+    int gy = ty0 + ry - HL, gx = tx0 + rx - HL;
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+      const float* p = tgt + ((long long)gy * W + gx) * 3;
+      v0 = __ldg(p); v1 = __ldg(p + 1); v2 = __ldg(p + 2);
+    }
+    sx[i] = v0; sx[SM::kRegion + i] = v1; sx[2 * SM::kRegion + i] = v2;
+  }
+  __syncthreads();
+  if (a.do_ssim) {
+    for (int i = tid; i < SM::kStats; i += kPhotoThreads) {
+      int qy = i / SW, qx = i % SW;
+      int gy = ty0 + qy - HS, gx = tx0 + qx - HS;
+      bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
+      int cy = min(gy + 1, H - 1) - max(gy - 1, 0) + 1, cx = min(gx + 1, W - 1) - max(gx - 1, 0) + 1;
+      float inv = in ? 1.f / (float)(cy * cx) : 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float* px = sx + c * SM::kRegion + qy * RW + qx;     // window top-left in region coords
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) { float v = px[dy * RW + dx]; s1 += v; s2 += v * v; }
+        float mu = s1 * inv;
+        smx[c * SM::kStats + i] = mu;
+        ssx[c * SM::kStats + i] = s2 * inv - mu * mu;
+      }
+    }
+  }
+
+  float lsum_l1 = 0.f, lsum_ssim = 0.f, lsum_sm = 0.f;
+  const float gb = (GRAD && a.gbatch) ? __ldg(a.gbatch + b) : 1.f;
+
+  // ---- smoothness on this tile (losses.py:409-440), FUSED only -------------
+  if (FUSED && a.do_smooth) {
+    const float* dsp = a.disp[l] + (long long)b * P;
+    const float nx = a.norm_sm_x[l], ny = a.norm_sm_y[l];
+    const float gcx = a.gcoef_smooth * gb * nx, gcy = a.gcoef_smooth * gb * ny;
+    const float k3 = a.grad_factor;
+#pragma unroll
+    for (int j = 0; j < kPixPerThread; ++j) {
+      int ci = tid + j * kPhotoThreads;
+      int cy_ = ci / kTW, cx_ = ci % kTW;
+      int gy = ty0 + cy_, gx = tx0 + cx_;
+      if (gy < H && gx < W) {
+        int ri = (cy_ + HL) * RW + (cx_ + HL);
+        float d = __ldg(dsp + (long long)gy * W + gx);
+        float gd = 0.f;
+        // forward differences owned by this pixel
+        if (gx + 1 < W) {
+          float e = 0.f;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) e += fabsf((sx[c * SM::kRegion + ri] - sx[c * SM::kRegion + ri + 1]) * k3);
+          float w = expf(-(e / 3.f));
+          float sd = (d - __ldg(dsp + (long long)gy * W + gx + 1)) * w;
+          lsum_sm += fabsf(sd) * nx;
+          gd += gcx * sgnf(sd) * w;
+        }
+        if (gy + 1 < H) {
+          float e = 0.f;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) e += fabsf((sx[c * SM::kRegion + ri] - sx[c * SM::kRegion + ri + RW]) * k3);
+          float w = expf(-(e / 3.f));
+          float sd = (d - __ldg(dsp + (long long)(gy + 1) * W + gx)) * w;
+          lsum_sm += fabsf(sd) * ny;
+          gd += gcy * sgnf(sd) * w;
+        }
+        if (GRAD) {
+          // differences owned by the left / upper neighbour, where this pixel is the subtrahend
+          if (gx >= 1) {
+            float e = 0.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) e += fabsf((sx[c * SM::kRegion + ri - 1] - sx[c * SM::kRegion + ri]) * k3);
+            float w = expf(-(e / 3.f));
+            float sd = (__ldg(dsp + (long long)gy * W + gx - 1) - d) * w;
+            gd -= gcx * sgnf(sd) * w;
+          }
+          if (gy >= 1) {
+            float e = 0.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) e += fabsf((sx[c * SM::kRegion + ri - RW] - sx[c * SM::kRegion + ri]) * k3);
+            float w = expf(-(e / 3.f));
+            float sd = (__ldg(dsp + (long long)(gy - 1) * W + gx) - d) * w;
+            gd -= gcy * sgnf(sd) * w;
+          }
+          if (a.d_disp[l]) a.d_disp[l][(long long)b * P + gy * W + gx] = gd;
+        }
+      }
+    }
+  }
+
+  // ---- per-thread centre pixels -------------------------------------------
+  float gD[kPixPerThread];
+  float Dc[kPixPerThread];
+#pragma unroll
+  for (int j = 0; j < kPixPerThread; ++j) {
+    gD[j] = 0.f; Dc[j] = 0.f;
+    if (FUSED && GRAD) {
+      int ci = tid + j * kPhotoThreads;
+      int gy = ty0 + ci / kTW, gx = tx0 + ci % kTW;
+      if (gy < H && gx < W) Dc[j] = __ldg(a.depth[l] + (long long)b * P + gy * W + gx);
+    }
+  }
+  const float cl1 = a.gcoef_l1 * gb * a.norm_photo[l];
+  const float cssim = a.gcoef_ssim * gb * a.norm_photo[l];
+
+  for (int n = 0; n < a.N; ++n) {
+    float T[12];
+    const float* img = nullptr;
+    if (FUSED) {
+      const float* gt = a.geoT + ((size_t)b * a.N + n) * kGeoT;
+#pragma unroll
+      for (int k = 0; k < 12; ++k) T[k] = __ldg(gt + k);
+      img = L.src + b * L.src_bs + n * L.src_fs;
+    }
+    // ---- phase Y: warped tile with halo into shared memory -----------------
+    for (int i = tid; i < SM::kRegion; i += kPhotoThreads) {
+      int ry = i / RW, rx = i % RW;
+      int gy = ty0 + ry - HL, gx = tx0 + rx - HL;
+      float yv[3] = {0.f, 0.f, 0.f};
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+        if (FUSED) {
+          float D = __ldg(a.depth[l] + (long long)b * P + gy * W + gx);
+          float r0, r1, r2;
+          ray_of_pixel(Ki, (float)gx, (float)gy, r0, r1, r2);
+          Proj pr = project(K, T, r0, r1, r2, D);
+          bool valid;
+          warp_sample(img, W, H, pr.u, pr.v, D, yv, valid);
+          bool centre = ry >= HL && ry < HL + kTH && rx >= HL && rx < HL + kTW;
+          if (centre) {
+            long long o = (long long)(b * a.N + n) * P + gy * W + gx;
+            if (a.synth_out[l]) { float* so = a.synth_out[l] + o * 3; so[0] = yv[0]; so[1] = yv[1]; so[2] = yv[2]; }
+            if (a.mask_out[l]) a.mask_out[l][o] = valid ? 1.f : 0.f;
+          }
+        } else {
+          const float* p = a.synth[l] + ((long long)(b * a.N + n) * P + gy * W + gx) * 3;
+          yv[0] = __ldg(p); yv[1] = __ldg(p + 1); yv[2] = __ldg(p + 2);
+        }
+      }
+      sy[i] = yv[0]; sy[SM::kRegion + i] = yv[1]; sy[2 * SM::kRegion + i] = yv[2];
+    }
+    __syncthreads();
+
+    // ---- phase S: per-pixel L1 / SSIM over the stats region -----------------
+    for (int i = tid; i < SM::kStats; i += kPhotoThreads) {
+      int qy = i / SW, qx = i % SW;
+      int gy = ty0 + qy - HS, gx = tx0 + qx - HS;
+      bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
+      bool centre = in && qy >= HS && qy < HS + kTH && qx >= HS && qx < HS + kTW;
+      int ri = (qy + 1) * RW + (qx + 1);          // this pixel in region coords
+      float y0 = sy[ri], y1 = sy[SM::kRegion + ri], y2 = sy[2 * SM::kRegion + ri];
+      bool masked = ((y0 + y1) + y2) == 0.f;       // mean_c(synth) == 0 (loss_util.py:15-16)
+      if (centre && !masked && a.l1_kind) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float df = sy[c * SM::kRegion + ri] - sx[c * SM::kRegion + ri];
+          lsum_l1 += (a.l1_kind == 1) ? fabsf(df) : df * df;
+        }
+      }
+      if (a.do_ssim) {
+        int cy = min(gy + 1, H - 1) - max(gy - 1, 0) + 1, cx = min(gx + 1, W - 1) - max(gx - 1, 0) + 1;
+        float inv = in ? 1.f / (float)(cy * cx) : 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float A = 0.f, Bq = 0.f, Cq = 0.f;
+          if (in && !masked) {
+            const float* px = sx + c * SM::kRegion + qy * RW + qx;
+            const float* py = sy + c * SM::kRegion + qy * RW + qx;
+            float s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) {
+                float yv = py[dy * RW + dx], xv = px[dy * RW + dx];
+                s1 += yv; s2 += yv * yv; s3 += xv * yv;
+              }
+            float mux = smx[c * SM::kStats + i], sgx = ssx[c * SM::kStats + i];
+            float muy = s1 * inv;
+            float sgy = s2 * inv - muy * muy;
+            float sgxy = s3 * inv - mux * muy;
+            float a1 = 2.f * mux * muy + kC1, a2 = 2.f * sgxy + kC2;
+            float b1 = mux * mux + muy * muy + kC1, b2 = sgx + sgy + kC2;
+            float ssim = (a1 * a2) / (b1 * b2);
+            float lv = (1.f - ssim) * 0.5f;
+            bool pass = (lv >= 0.f) && (lv <= 1.f);          // clip_by_value gradient
+            float lc = fminf(fmaxf(lv, 0.f), 1.f);
+            if (centre) lsum_ssim += lc;
+            if (GRAD && pass) {
+              // h = dL/d ssim at this pixel
+              float h = -0.5f * cssim;
+              float ib1b2 = 1.f / (b1 * b2);
+              float dm = (2.f * mux * (a2 - a1)) * ib1b2 - ssim * (2.f * muy) * (1.f / b1 - 1.f / b2);
+              float dq = -ssim / b2;
+              float dr = 2.f * a1 * ib1b2;
+              A = h * dm * inv; Bq = h * dq * inv; Cq = h * dr * inv;
+            }
+          }
+          if (GRAD) { sA[c * SM::kStats + i] = A; sB[c * SM::kStats + i] = Bq; sC[c * SM::kStats + i] = Cq; }
+        }
+      }
+    }
+
+    // ---- phase G: dL/dy at the centre pixels, then out or through the warp --
+    if (GRAD) {
+      __syncthreads();
+      float acc[12];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) acc[k] = 0.f;
+#pragma unroll
+      for (int j = 0; j < kPixPerThread; ++j) {
+        int ci = tid + j * kPhotoThreads;
+        int cy_ = ci / kTW, cx_ = ci % kTW;
+        int gy = ty0 + cy_, gx = tx0 + cx_;
+        if (gy < H && gx < W) {
+          int ri = (cy_ + HL) * RW + (cx_ + HL);
+          float yv[3] = {sy[ri], sy[SM::kRegion + ri], sy[2 * SM::kRegion + ri]};
+          bool masked = ((yv[0] + yv[1]) + yv[2]) == 0.f;
+          float g[3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float gc = 0.f;
+            float xv = sx[c * SM::kRegion + ri];
+            if (a.do_ssim) {
+              // centre pixel (cy_,cx_) has stats coords (cy_+HS, cx_+HS); its window starts one up-left
+              const float* pA = sA + c * SM::kStats + cy_ * SW + cx_;
+              const float* pB = sB + c * SM::kStats + cy_ * SW + cx_;
+              const float* pC = sC + c * SM::kStats + cy_ * SW + cx_;
+              float sa = 0.f, sb = 0.f, sc = 0.f;
+#pragma unroll
+              for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) { sa += pA[dy * SW + dx]; sb += pB[dy * SW + dx]; sc += pC[dy * SW + dx]; }
+              gc = sa + 2.f * yv[c] * sb + xv * sc;
+            }
+            if (a.l1_kind && !masked) {
+              float df = yv[c] - xv;
+              gc += cl1 * ((a.l1_kind == 1) ? sgnf(df) : 2.f * df);
+            }
+            g[c] = gc;
+          }
+          if (FUSED) {
+            float r0, r1, r2;
+            ray_of_pixel(Ki, (float)gx, (float)gy, r0, r1, r2);
+            Proj pr = project(K, T, r0, r1, r2, Dc[j]);
+            float* dimg = a.d_src[l] ? a.d_src[l] + b * a.d_src_bs[l] + n * a.d_src_fs[l] : nullptr;
+            gD[j] += sample_adjoint(img, dimg, W, H, K, T, r0, r1, r2, Dc[j], pr, g, acc);
+          } else {
+            float* go = a.gsynth[l] + ((long long)(b * a.N + n) * P + gy * W + gx) * 3;
+            go[0] = g[0]; go[1] = g[1]; go[2] = g[2];
+          }
+        }
+      }
+      if (FUSED) {
+        float* out = a.pose_part + (((size_t)b * a.slots_per_b + slot) * a.N + n) * 12;
+        block_reduce_store12<kPhotoThreads>(acc, out, red);
+      }
+    }
+    __syncthreads();     // sy / sA.. are rewritten by the next source
+  }
+
+  if (FUSED && GRAD) {
+#pragma unroll
+    for (int j = 0; j < kPixPerThread; ++j) {
+      int ci = tid + j * kPhotoThreads;
+      int gy = ty0 + ci / kTW, gx = tx0 + ci % kTW;
+      if (gy < H && gx < W && a.d_depth[l]) a.d_depth[l][(long long)b * P + gy * W + gx] = gD[j];
+    }
+  }
+
+  // ---- block reduction of the loss sums -> one partial record per tile ------
+  {
+    float v0 = warp_sum(lsum_l1), v1 = warp_sum(lsum_ssim), v2 = warp_sum(lsum_sm);
+    const int lane = tid & 31, wid = tid >> 5;
+    if (lane == 0) { red[wid * 3] = v0; red[wid * 3 + 1] = v1; red[wid * 3 + 2] = v2; }
+    __syncthreads();
+    if (tid < 3) {
+      float v = 0.f;
+      for (int w = 0; w < kPhotoThreads / 32; ++w) v += red[w * 3 + tid];
+      float nrm = (tid == 2) ? 1.f : a.norm_photo[l];
+      a.loss_part[((size_t)b * a.slots_per_b + slot) * 3 + tid] = v * nrm;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// standalone smoothness (SmoothenessLossMultiScale on given tensors):
+// one thread per pixel of (level, b); forward sums + gather-form backward.
+// ---------------------------------------------------------------------------
+struct SmoothArgs {
+  int S, B;
+  int H[kMaxScales], W[kMaxScales];
+  const float* disp[kMaxScales];
+  const float* tgt[kMaxScales]; long long tgt_bs[kMaxScales];
+  float norm_x[kMaxScales], norm_y[kMaxScales];
+  float grad_factor;
+  const float* gbatch;       // NULL = ones
+  float* d_disp[kMaxScales]; // NULL = forward only
+  float* loss_part;          // [B][slots][3] (column 2)
+  int slots_per_b;
+  int chunk_base[kMaxScales];
+};
+
+__device__ __forceinline__ float smooth_weight(const float* __restrict__ p, const float* __restrict__ q, float k3) {
+  float e = fabsf((__ldg(p) - __ldg(q)) * k3) + fabsf((__ldg(p + 1) - __ldg(q + 1)) * k3) +
+            fabsf((__ldg(p + 2) - __ldg(q + 2)) * k3);
+  return expf(-(e / 3.f));
+}
+
+__global__ void __launch_bounds__(256) k_smooth(SmoothArgs a) {
+  __shared__ float red[8];
+  const int l = blockIdx.z, b = blockIdx.y;
+  const int H = a.H[l], W = a.W[l], P = H * W;
+  if ((int)blockIdx.x * 256 >= P) return;
+  const int pix = blockIdx.x * 256 + threadIdx.x;
+  float ls = 0.f;
+  if (pix < P) {
+    int y = pix / W, x = pix % W;
+    const float* dsp = a.disp[l] + (long long)b * P;
+    const float* img = a.tgt[l] + b * a.tgt_bs[l];
+    const float* ip = img + (long long)pix * 3;
+    float d = __ldg(dsp + pix);
+    float gb = a.gbatch ? __ldg(a.gbatch + b) : 1.f;
+    float gd = 0.f;
+    float nx = a.norm_x[l], ny = a.norm_y[l], k3 = a.grad_factor;
+    if (x + 1 < W) {
+      float w = smooth_weight(ip, ip + 3, k3);
+      float sd = (d - __ldg(dsp + pix + 1)) * w;
+      ls += fabsf(sd) * nx; gd += gb * nx * sgnf(sd) * w;
+    }
+    if (y + 1 < H) {
+      float w = smooth_weight(ip, ip + (long long)W * 3, k3);
+      float sd = (d - __ldg(dsp + pix + W)) * w;
+      ls += fabsf(sd) * ny; gd += gb * ny * sgnf(sd) * w;
+    }
+    if (a.d_disp[l]) {
+      if (x >= 1) {
+        float w = smooth_weight(ip - 3, ip, k3);
+        float sd = (__ldg(dsp + pix - 1) - d) * w;
+        gd -= gb * nx * sgnf(sd) * w;
+      }
+      if (y >= 1) {
+        float w = smooth_weight(ip - (long long)W * 3, ip, k3);
+        float sd = (__ldg(dsp + pix - W) - d) * w;
+        gd -= gb * ny * sgnf(sd) * w;
+      }
+      a.d_disp[l][(long long)b * P + pix] = gd;
+    }
+  }
+  float v = warp_sum(ls);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    float* o = a.loss_part + ((size_t)b * a.slots_per_b + a.chunk_base[l] + blockIdx.x) * 3;
+    o[0] = 0.f; o[1] = 0.f; o[2] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// loss epilogue: deterministic fp64 sum of the per-tile partials.
+//   loss_batch[k][b] = sum_slots part[b][slot][k]          (merge_multi_scale_losses, losses.py:147-154)
+//   mean_k = sum_b loss_batch[k][b] / global_batch        (compute_average_loss, losses.py:49)
+//   total  = sum_k w_k * mean_k                            (losses.py:50-54)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_loss_epilogue(const float* __restrict__ loss_part, int slots_per_b,
+                                                       int slots_used, int B, float inv_global_batch, float w0,
+                                                       float w1, float w2, float* __restrict__ losses,
+                                                       float* __restrict__ loss_batch) {
+  __shared__ double red[8][3];
+  __shared__ double tot[3];
+  if (threadIdx.x < 3) tot[threadIdx.x] = 0.0;
+  __syncthreads();
+  for (int b = 0; b < B; ++b) {
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (int sl = threadIdx.x; sl < slots_used; sl += blockDim.x) {
+      const float* p = loss_part + ((size_t)b * slots_per_b + sl) * 3;
+      acc[0] += p[0]; acc[1] += p[1]; acc[2] += p[2];
+    }
+    for (int k = 0; k < 3; ++k) {
+      double v = acc[k];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      double v = 0.0;
+      for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+      if (loss_batch) loss_batch[threadIdx.x * B + b] = (float)v;
+      tot[threadIdx.x] += v;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && losses) {
+    double m0 = tot[0] * inv_global_batch, m1 = tot[1] * inv_global_batch, m2 = tot[2] * inv_global_batch;
+    losses[0] = (float)(w0 * m0 + w1 * m1 + w2 * m2);
+    losses[1] = (float)m0; losses[2] = (float)m1; losses[3] = (float)m2;
+  }
+}
+
+__global__ void k_fill(float* __restrict__ p, long long n, float v) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+}  // namespace xpt

@@ -1,0 +1,752 @@
+// xptwarp.cu -- C-ABI of libxptwarp.so (see include/xptwarp.h).
+// Host-side orchestration only: argument validation, scratch ownership, kernel
+// launches on the caller's stream.  No CPU fallback: every entry point either
+// launches the sm_100a kernels or returns an error.
+#include "../../include/xptwarp.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "xpt_kernels.cuh"
+
+using namespace xpt;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define XPT_CUDA(call)                                                                         \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess)                                                                     \
+      return fail(XPT_CUDA_ERROR, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),      \
+                  __FILE__, __LINE__);                                                         \
+  } while (0)
+
+#define XPT_LAUNCH_CHECK(name)                                                                 \
+  do {                                                                                         \
+    cudaError_t e_ = cudaGetLastError();                                                       \
+    if (e_ != cudaSuccess)                                                                     \
+      return fail(XPT_CUDA_ERROR, "launch of %s failed: %s", name, cudaGetErrorString(e_));    \
+    ++ctx->launches;                                                                           \
+  } while (0)
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace
+
+struct xpt_ctx {
+  xpt_config cfg;
+  int S, B, N, H, W;
+  int h[kMaxScales], w[kMaxScales], s[kMaxScales];
+  int tiles_x[kMaxScales], tiles_y[kMaxScales], first_tile[kMaxScales + 1];
+  int chunks[kMaxScales], first_chunk[kMaxScales + 1];       // 1024-pixel chunks (k_warp_bwd)
+  int sm_chunks[kMaxScales], first_sm_chunk[kMaxScales + 1]; // 256-pixel chunks (k_smooth)
+  int slots_per_b;
+  size_t scratch_bytes;
+  int launches;
+  // device scratch
+  float* geoK;
+  float* geoT;
+  float* src_pyr[kMaxScales];   // s > 1
+  float* tgt_pyr[kMaxScales];   // s > 1
+  float* loss_part;
+  float* pose_part;
+  // lazily allocated
+  float* synth_scr[kMaxScales];
+  float* gsynth_scr[kMaxScales];
+  float* dsrc_lvl[kMaxScales];  // s > 1
+  float* tgt0_copy;             // unused unless a level-0 copy is wanted without a user buffer
+  // staging for the host-buffer entry point
+  float* st_frames; float* st_K; float* st_pose; float* st_losses; float* st_loss_batch; float* st_dpose;
+  float* st_dsource;
+  float* st_depth[kMaxScales]; float* st_disp[kMaxScales];
+  float* st_ddepth[kMaxScales]; float* st_ddisp[kMaxScales];
+  float* st_synth[kMaxScales]; float* st_mask[kMaxScales]; float* st_target[kMaxScales];
+};
+
+namespace {
+
+int dev_alloc(xpt_ctx* ctx, float** p, size_t nfloats) {
+  if (*p) return XPT_OK;
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, nfloats * sizeof(float));
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return fail(XPT_OUT_OF_MEMORY, "cudaMalloc of %zu bytes failed: %s", nfloats * sizeof(float),
+                cudaGetErrorString(e));
+  }
+  *p = static_cast<float*>(q);
+  ctx->scratch_bytes += nfloats * sizeof(float);
+  return XPT_OK;
+}
+
+#define XPT_TRY(expr)            \
+  do {                           \
+    int rc_ = (expr);            \
+    if (rc_ != XPT_OK) return rc_; \
+  } while (0)
+
+size_t lvl_pix(const xpt_ctx* c, int l) { return (size_t)c->h[l] * c->w[l]; }
+
+int check_frames(const xpt_ctx* ctx, const xpt_frames* f, bool need_target) {
+  if (!f) return fail(XPT_BAD_ARGUMENT, "frames is NULL");
+  if (!f->source) return fail(XPT_BAD_ARGUMENT, "frames.source is NULL");
+  if (!f->intrinsic) return fail(XPT_BAD_ARGUMENT, "frames.intrinsic is NULL");
+  if (need_target && !f->target) return fail(XPT_BAD_ARGUMENT, "frames.target is NULL");
+  long long hw3 = (long long)ctx->H * ctx->W * 3;
+  if (f->source_frame_stride < hw3) return fail(XPT_BAD_SHAPE, "source_frame_stride %lld < H*W*3", (long long)f->source_frame_stride);
+  if (ctx->B > 1 && f->source_batch_stride < hw3) return fail(XPT_BAD_SHAPE, "source_batch_stride too small");
+  if (need_target && ctx->B > 1 && f->target_batch_stride < hw3) return fail(XPT_BAD_SHAPE, "target_batch_stride too small");
+  return XPT_OK;
+}
+
+int check_list(const xpt_ctx* ctx, const void* const* p, const char* name, bool all_required) {
+  if (!p) return fail(XPT_BAD_ARGUMENT, "%s is NULL", name);
+  if (all_required)
+    for (int l = 0; l < ctx->S; ++l)
+      if (!p[l]) return fail(XPT_BAD_ARGUMENT, "%s[%d] is NULL", name, l);
+  return XPT_OK;
+}
+
+// level table with the source / target pointers for this call
+LevelTable make_levels(const xpt_ctx* ctx, const xpt_frames* f, const float* const tgt_override[]) {
+  LevelTable lt;
+  memset(&lt, 0, sizeof(lt));
+  lt.S = ctx->S;
+  for (int l = 0; l < ctx->S; ++l) {
+    Level& L = lt.lv[l];
+    L.s = ctx->s[l]; L.H = ctx->h[l]; L.W = ctx->w[l];
+    L.tiles_x = ctx->tiles_x[l]; L.tiles_y = ctx->tiles_y[l];
+    L.slot_base = ctx->first_tile[l];
+    if (f) {
+      if (ctx->s[l] == 1) {
+        L.src = f->source; L.src_bs = f->source_batch_stride; L.src_fs = f->source_frame_stride;
+        L.tgt = f->target; L.tgt_bs = f->target_batch_stride;
+      } else {
+        L.src = ctx->src_pyr[l]; L.src_fs = (long long)lvl_pix(ctx, l) * 3; L.src_bs = L.src_fs * ctx->N;
+        L.tgt = ctx->tgt_pyr[l]; L.tgt_bs = (long long)lvl_pix(ctx, l) * 3;
+      }
+    }
+    if (tgt_override && tgt_override[l]) { L.tgt = tgt_override[l]; L.tgt_bs = (long long)lvl_pix(ctx, l) * 3; }
+  }
+  return lt;
+}
+
+int launch_geometry(xpt_ctx* ctx, const float* pose, const float* intrinsic, float* matr_out, cudaStream_t st) {
+  LevelTable lt = make_levels(ctx, nullptr, nullptr);
+  int n = ctx->B * (ctx->N > ctx->S ? ctx->N : ctx->S);
+  k_geometry<<<cdiv(n, 128), 128, 0, st>>>(pose, intrinsic, intrinsic ? ctx->geoK : nullptr,
+                                           pose ? ctx->geoT : nullptr, matr_out, ctx->B, ctx->N, lt);
+  XPT_LAUNCH_CHECK("k_geometry");
+  return XPT_OK;
+}
+
+// source pyramid into the ctx (+ target pyramid into ctx or user buffers)
+int launch_pyramids(xpt_ctx* ctx, const xpt_frames* f, float* const target_ms[], bool want_source,
+                    cudaStream_t st) {
+  PyramidArgs a;
+  memset(&a, 0, sizeof(a));
+  a.source = f->source; a.src_bs = f->source_batch_stride; a.src_fs = f->source_frame_stride;
+  a.target = f->target; a.tgt_bs = f->target_batch_stride;
+  a.B = ctx->B; a.N = ctx->N; a.H = ctx->H; a.W = ctx->W; a.S = ctx->S;
+  long long maxcount = 0;
+  for (int l = 0; l < ctx->S; ++l) {
+    a.s[l] = ctx->s[l];
+    bool work = false;
+    if (ctx->s[l] > 1) {
+      if (want_source) { a.src_out[l] = ctx->src_pyr[l]; work = true; }
+      if (f->target) { a.tgt_out[l] = ctx->tgt_pyr[l]; work = true; }
+    } else if (f->target && target_ms && target_ms[l]) {
+      a.tgt_out[l] = target_ms[l];      // level-0 copy for the caller
+      work = true;
+    }
+    if (work) {
+      long long c = (long long)ctx->B * (ctx->N + 1) * lvl_pix(ctx, l);
+      if (c > maxcount) maxcount = c;
+    }
+  }
+  if (maxcount == 0) return XPT_OK;
+  dim3 grid(cdiv(maxcount, 256), ctx->S);
+  k_pyramid<<<grid, 256, 0, st>>>(a);
+  XPT_LAUNCH_CHECK("k_pyramid");
+  // user copies of the target pyramid (augm_data["target_ms"])
+  if (target_ms && f->target)
+    for (int l = 0; l < ctx->S; ++l)
+      if (ctx->s[l] > 1 && target_ms[l])
+        XPT_CUDA(cudaMemcpyAsync(target_ms[l], ctx->tgt_pyr[l], (size_t)ctx->B * lvl_pix(ctx, l) * 3 * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, st));
+  return XPT_OK;
+}
+
+int launch_warp_fwd(xpt_ctx* ctx, const LevelTable& lt, const float* const depth_ms[], float* const synth_ms[],
+                    float* const mask_ms[], cudaStream_t st) {
+  WarpFwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.lt = lt; a.B = ctx->B; a.N = ctx->N; a.geoK = ctx->geoK; a.geoT = ctx->geoT;
+  for (int l = 0; l < ctx->S; ++l) {
+    a.depth[l] = depth_ms[l]; a.synth[l] = synth_ms[l]; a.mask[l] = mask_ms ? mask_ms[l] : nullptr;
+  }
+  dim3 grid(cdiv((long long)ctx->B * lvl_pix(ctx, 0), 256), ctx->S);
+  for (int l = 1; l < ctx->S; ++l) {
+    int g = cdiv((long long)ctx->B * lvl_pix(ctx, l), 256);
+    if ((unsigned)g > grid.x) grid.x = g;
+  }
+  k_warp_fwd<<<grid, 256, 0, st>>>(a);
+  XPT_LAUNCH_CHECK("k_warp_fwd");
+  return XPT_OK;
+}
+
+// prepares per-level dL/dsource buffers; level with s == 1 accumulates straight into d_source
+int prepare_dsource(xpt_ctx* ctx, float* d_source, float* d_src[], long long bs[], long long fs[], cudaStream_t st) {
+  for (int l = 0; l < ctx->S; ++l) { d_src[l] = nullptr; bs[l] = 0; fs[l] = 0; }
+  if (!d_source) return XPT_OK;
+  size_t full = (size_t)ctx->B * ctx->N * ctx->H * ctx->W * 3;
+  XPT_CUDA(cudaMemsetAsync(d_source, 0, full * sizeof(float), st));
+  for (int l = 0; l < ctx->S; ++l) {
+    size_t n = (size_t)ctx->B * ctx->N * lvl_pix(ctx, l) * 3;
+    if (ctx->s[l] == 1) {
+      d_src[l] = d_source;
+    } else {
+      XPT_TRY(dev_alloc(ctx, &ctx->dsrc_lvl[l], n));
+      XPT_CUDA(cudaMemsetAsync(ctx->dsrc_lvl[l], 0, n * sizeof(float), st));
+      d_src[l] = ctx->dsrc_lvl[l];
+    }
+    fs[l] = (long long)lvl_pix(ctx, l) * 3;
+    bs[l] = fs[l] * ctx->N;
+  }
+  return XPT_OK;
+}
+
+int finish_dsource(xpt_ctx* ctx, float* d_source, cudaStream_t st) {
+  if (!d_source) return XPT_OK;
+  PyramidAdjArgs a;
+  memset(&a, 0, sizeof(a));
+  a.d_source = d_source; a.BN = ctx->B * ctx->N; a.H = ctx->H; a.W = ctx->W; a.S = ctx->S;
+  bool any = false;
+  for (int l = 0; l < ctx->S; ++l) {
+    a.s[l] = ctx->s[l];
+    if (ctx->s[l] > 1) { a.d_level[l] = ctx->dsrc_lvl[l]; any = true; }
+  }
+  if (!any) return XPT_OK;
+  long long total = (long long)a.BN * a.H * a.W;
+  k_pyramid_adjoint<<<cdiv(total, 256), 256, 0, st>>>(a);
+  XPT_LAUNCH_CHECK("k_pyramid_adjoint");
+  return XPT_OK;
+}
+
+int launch_warp_bwd(xpt_ctx* ctx, const LevelTable& lt, const float* const depth_ms[], const float* const gsynth[],
+                    float* const d_depth_ms[], float* d_source, const float* pose, float* d_pose, float scale,
+                    cudaStream_t st) {
+  WarpBwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.lt = lt; a.B = ctx->B; a.N = ctx->N; a.geoK = ctx->geoK; a.geoT = ctx->geoT;
+  a.pose_part = ctx->pose_part; a.slots_per_b = ctx->slots_per_b;
+  XPT_TRY(prepare_dsource(ctx, d_source, a.d_src, a.d_src_bs, a.d_src_fs, st));
+  int maxchunks = 0;
+  for (int l = 0; l < ctx->S; ++l) {
+    a.depth[l] = depth_ms[l]; a.gsynth[l] = gsynth[l]; a.d_depth[l] = d_depth_ms ? d_depth_ms[l] : nullptr;
+    a.chunk_base[l] = ctx->first_chunk[l];
+    if (ctx->chunks[l] > maxchunks) maxchunks = ctx->chunks[l];
+  }
+  dim3 grid(maxchunks, ctx->B, ctx->S);
+  k_warp_bwd<<<grid, kWarpBwdThreads, 0, st>>>(a);
+  XPT_LAUNCH_CHECK("k_warp_bwd");
+  if (d_pose) {
+    k_pose_epilogue<<<ctx->B * ctx->N, 128, 0, st>>>(ctx->pose_part, ctx->slots_per_b, ctx->first_chunk[ctx->S],
+                                                     pose, d_pose, ctx->N, scale);
+    XPT_LAUNCH_CHECK("k_pose_epilogue");
+  }
+  XPT_TRY(finish_dsource(ctx, d_source, st));
+  return XPT_OK;
+}
+
+void fill_photo_norms(const xpt_ctx* ctx, PhotoArgs& a) {
+  a.B = ctx->B; a.N = ctx->N;
+  a.tiles_per_b = ctx->first_tile[ctx->S];
+  for (int l = 0; l <= ctx->S; ++l) a.first_tile[l] = ctx->first_tile[l];
+  a.slots_per_b = ctx->slots_per_b;
+  a.loss_part = ctx->loss_part;
+  a.pose_part = ctx->pose_part;
+  a.grad_factor = ctx->cfg.img_grad_factor;
+  for (int l = 0; l < ctx->S; ++l) {
+    double hw = (double)ctx->h[l] * ctx->w[l];
+    double sw = ctx->cfg.scale_weights[l];
+    a.norm_photo[l] = (float)(sw / ((double)ctx->N * hw * 3.0));
+    // losses.py:401-402: each scale's smoothness divided by scale = orig_width / width
+    double scale = (double)ctx->W / (double)ctx->w[l];
+    a.norm_sm_x[l] = (float)(sw * 0.5 / ((double)ctx->h[l] * (ctx->w[l] - 1)) / scale);
+    a.norm_sm_y[l] = (float)(sw * 0.5 / ((double)(ctx->h[l] - 1) * ctx->w[l]) / scale);
+  }
+}
+
+template <bool FUSED, bool GRAD>
+int launch_photo(xpt_ctx* ctx, const PhotoArgs& a, cudaStream_t st) {
+  static bool attr_set = false;
+  size_t smem = PhotoSmem<GRAD>::kBytes;
+  if (!attr_set) {
+    XPT_CUDA(cudaFuncSetAttribute(k_photo<FUSED, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid(a.tiles_per_b, ctx->B);
+  k_photo<FUSED, GRAD><<<grid, kPhotoThreads, smem, st>>>(a);
+  XPT_LAUNCH_CHECK(FUSED ? "k_photo<fused>" : "k_photo<tensor>");
+  return XPT_OK;
+}
+
+int launch_smooth(xpt_ctx* ctx, const float* const disp_ms[], const LevelTable& lt, const float* gbatch,
+                  float gcoef, float* const d_disp_ms[], int slot_offset, cudaStream_t st) {
+  SmoothArgs a;
+  memset(&a, 0, sizeof(a));
+  PhotoArgs nrm;
+  memset(&nrm, 0, sizeof(nrm));
+  fill_photo_norms(ctx, nrm);
+  a.S = ctx->S; a.B = ctx->B; a.grad_factor = ctx->cfg.img_grad_factor; a.gbatch = gbatch;
+  a.loss_part = ctx->loss_part; a.slots_per_b = ctx->slots_per_b;
+  int maxchunks = 0;
+  for (int l = 0; l < ctx->S; ++l) {
+    a.H[l] = ctx->h[l]; a.W[l] = ctx->w[l];
+    a.disp[l] = disp_ms[l]; a.tgt[l] = lt.lv[l].tgt; a.tgt_bs[l] = lt.lv[l].tgt_bs;
+    // gcoef folds dTotal/d(loss) into the per-level normaliser of the backward only
+    a.norm_x[l] = nrm.norm_sm_x[l]; a.norm_y[l] = nrm.norm_sm_y[l];
+    a.d_disp[l] = d_disp_ms ? d_disp_ms[l] : nullptr;
+    a.chunk_base[l] = slot_offset + ctx->first_sm_chunk[l];
+    if (ctx->sm_chunks[l] > maxchunks) maxchunks = ctx->sm_chunks[l];
+  }
+  (void)gcoef;
+  dim3 grid(maxchunks, ctx->B, ctx->S);
+  k_smooth<<<grid, 256, 0, st>>>(a);
+  XPT_LAUNCH_CHECK("k_smooth");
+  return XPT_OK;
+}
+
+int launch_loss_epilogue(xpt_ctx* ctx, int slots_used, float w0, float w1, float w2, float* losses,
+                         float* loss_batch, cudaStream_t st) {
+  int gb = ctx->cfg.global_batch > 0 ? ctx->cfg.global_batch : ctx->B;
+  k_loss_epilogue<<<1, 256, 0, st>>>(ctx->loss_part, ctx->slots_per_b, slots_used, ctx->B, 1.0f / (float)gb, w0, w1,
+                                     w2, losses, loss_batch);
+  XPT_LAUNCH_CHECK("k_loss_epilogue");
+  return XPT_OK;
+}
+
+}  // namespace
+
+// ===========================================================================
+// C-ABI
+// ===========================================================================
+extern "C" {
+
+int xpt_version(void) { return XPT_VERSION; }
+const char* xpt_last_error(void) { return g_err; }
+
+const char* xpt_status_string(int status) {
+  switch (status) {
+    case XPT_OK: return "XPT_OK";
+    case XPT_BAD_ARGUMENT: return "XPT_BAD_ARGUMENT";
+    case XPT_BAD_SHAPE: return "XPT_BAD_SHAPE";
+    case XPT_CUDA_ERROR: return "XPT_CUDA_ERROR";
+    case XPT_NO_DEVICE: return "XPT_NO_DEVICE";
+    case XPT_OUT_OF_MEMORY: return "XPT_OUT_OF_MEMORY";
+    default: return "XPT_UNKNOWN";
+  }
+}
+
+int xpt_create(xpt_ctx** out, const xpt_config* cfg) {
+  if (!out || !cfg) return fail(XPT_BAD_ARGUMENT, "xpt_create: NULL argument");
+  *out = nullptr;
+  if (cfg->batch < 1 || cfg->num_src < 1 || cfg->num_src > kMaxSrc)
+    return fail(XPT_BAD_SHAPE, "batch=%d num_src=%d out of range (num_src <= %d)", cfg->batch, cfg->num_src, kMaxSrc);
+  if (cfg->num_scales < 1 || cfg->num_scales > XPT_MAX_SCALES)
+    return fail(XPT_BAD_SHAPE, "num_scales=%d out of range", cfg->num_scales);
+  for (int l = 0; l < cfg->num_scales; ++l) {
+    int s = cfg->scales[l];
+    if (s < 1 || cfg->height % s || cfg->width % s)
+      return fail(XPT_BAD_SHAPE, "scale %d does not divide %dx%d", s, cfg->height, cfg->width);
+    if (cfg->height / s < 2 || cfg->width / s < 2)
+      return fail(XPT_BAD_SHAPE, "level %d (%dx%d) smaller than 2x2", l, cfg->height / s, cfg->width / s);
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    (void)cudaGetLastError();
+    return fail(XPT_NO_DEVICE, "no CUDA device visible (libxptwarp has no CPU fallback)");
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(XPT_NO_DEVICE, "device %d out of range (%d visible)", cfg->device, ndev);
+  cudaDeviceProp prop;
+  XPT_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10)
+    return fail(XPT_NO_DEVICE, "device %d is sm_%d%d; libxptwarp is built for sm_100a only", cfg->device, prop.major, prop.minor);
+  XPT_CUDA(cudaSetDevice(cfg->device));
+
+  xpt_ctx* ctx = new (std::nothrow) xpt_ctx;
+  if (!ctx) return fail(XPT_OUT_OF_MEMORY, "host allocation failed");
+  memset(ctx, 0, sizeof(*ctx));
+  ctx->cfg = *cfg;
+  if (ctx->cfg.global_batch <= 0) ctx->cfg.global_batch = cfg->batch;
+  ctx->S = cfg->num_scales; ctx->B = cfg->batch; ctx->N = cfg->num_src; ctx->H = cfg->height; ctx->W = cfg->width;
+  ctx->first_tile[0] = ctx->first_chunk[0] = ctx->first_sm_chunk[0] = 0;
+  for (int l = 0; l < ctx->S; ++l) {
+    ctx->s[l] = cfg->scales[l];
+    ctx->h[l] = ctx->H / ctx->s[l]; ctx->w[l] = ctx->W / ctx->s[l];
+    ctx->tiles_x[l] = cdiv(ctx->w[l], kTW); ctx->tiles_y[l] = cdiv(ctx->h[l], kTH);
+    ctx->first_tile[l + 1] = ctx->first_tile[l] + ctx->tiles_x[l] * ctx->tiles_y[l];
+    ctx->chunks[l] = cdiv((long long)ctx->h[l] * ctx->w[l], kWarpBwdChunk);
+    ctx->first_chunk[l + 1] = ctx->first_chunk[l] + ctx->chunks[l];
+    ctx->sm_chunks[l] = cdiv((long long)ctx->h[l] * ctx->w[l], 256);
+    ctx->first_sm_chunk[l + 1] = ctx->first_sm_chunk[l] + ctx->sm_chunks[l];
+  }
+  ctx->slots_per_b = ctx->first_tile[ctx->S] + ctx->first_sm_chunk[ctx->S];
+  if (ctx->first_chunk[ctx->S] > ctx->slots_per_b) ctx->slots_per_b = ctx->first_chunk[ctx->S];
+
+  int rc = XPT_OK;
+  auto A = [&](float** p, size_t n) { if (rc == XPT_OK) rc = dev_alloc(ctx, p, n); };
+  A(&ctx->geoK, (size_t)ctx->B * ctx->S * kGeoK);
+  A(&ctx->geoT, (size_t)ctx->B * ctx->N * kGeoT);
+  for (int l = 0; l < ctx->S; ++l)
+    if (ctx->s[l] > 1) {
+      A(&ctx->src_pyr[l], (size_t)ctx->B * ctx->N * lvl_pix(ctx, l) * 3);
+      A(&ctx->tgt_pyr[l], (size_t)ctx->B * lvl_pix(ctx, l) * 3);
+    }
+  A(&ctx->loss_part, (size_t)ctx->B * ctx->slots_per_b * 3);
+  A(&ctx->pose_part, (size_t)ctx->B * ctx->slots_per_b * ctx->N * 12);
+  if (rc != XPT_OK) { xpt_destroy(ctx); return rc; }
+  *out = ctx;
+  return XPT_OK;
+}
+
+void xpt_destroy(xpt_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->cfg.device);
+  auto F = [](float* p) { if (p) cudaFree(p); };
+  F(ctx->geoK); F(ctx->geoT); F(ctx->loss_part); F(ctx->pose_part); F(ctx->tgt0_copy);
+  F(ctx->st_frames); F(ctx->st_K); F(ctx->st_pose); F(ctx->st_losses); F(ctx->st_loss_batch); F(ctx->st_dpose);
+  F(ctx->st_dsource);
+  for (int l = 0; l < kMaxScales; ++l) {
+    F(ctx->src_pyr[l]); F(ctx->tgt_pyr[l]); F(ctx->synth_scr[l]); F(ctx->gsynth_scr[l]); F(ctx->dsrc_lvl[l]);
+    F(ctx->st_depth[l]); F(ctx->st_disp[l]); F(ctx->st_ddepth[l]); F(ctx->st_ddisp[l]);
+    F(ctx->st_synth[l]); F(ctx->st_mask[l]); F(ctx->st_target[l]);
+  }
+  delete ctx;
+}
+
+int xpt_get_config(const xpt_ctx* ctx, xpt_config* out) {
+  if (!ctx || !out) return fail(XPT_BAD_ARGUMENT, "xpt_get_config: NULL argument");
+  *out = ctx->cfg;
+  return XPT_OK;
+}
+
+size_t xpt_scratch_bytes(const xpt_ctx* ctx) { return ctx ? ctx->scratch_bytes : 0; }
+int xpt_last_launch_count(const xpt_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int xpt_pose_rvec2matr(xpt_ctx* ctx, const float* pose, float* matr, void* stream) {
+  if (!ctx || !pose || !matr) return fail(XPT_BAD_ARGUMENT, "xpt_pose_rvec2matr: NULL argument");
+  XPT_CUDA(cudaSetDevice(ctx->cfg.device));
+  ctx->launches = 0;
+  return launch_geometry(ctx, pose, nullptr, matr, (cudaStream_t)stream);
+}
+
+int xpt_build_pyramids(xpt_ctx* ctx, const xpt_frames* frames, float* const target_ms[], void* stream) {
+  if (!ctx) return fail(XPT_BAD_ARGUMENT, "ctx is NULL");
+  XPT_TRY(check_frames(ctx, frames, false));
+  XPT_CUDA(cudaSetDevice(ctx->cfg.device));
+  ctx->launches = 0;
+  return launch_pyramids(ctx, frames, target_ms, true, (cudaStream_t)stream);
+}
+
+int xpt_synthesize(xpt_ctx* ctx, const xpt_frames* frames, const float* const depth_ms[], const float* pose,
+                   float* const synth_ms[], float* const mask_ms[], void* stream) {
+  if (!ctx || !pose) return fail(XPT_BAD_ARGUMENT, "xpt_synthesize: NULL argument");
+  XPT_TRY(check_frames(ctx, frames, false));
+  XPT_TRY(check_list(ctx, (const void* const*)depth_ms, "depth_ms", true));
+  XPT_TRY(check_list(ctx, (const void* const*)synth_ms, "synth_ms", true));
+  cudaStream_t st = (cudaStream_t)stream;
+  XPT_CUDA(cudaSetDevice(ctx->cfg.device));
+  ctx->launches = 0;
+  xpt_frames f = *frames;
+  f.target = nullptr;                       // synthesis does not touch the target frame
+  XPT_TRY(launch_geometry(ctx, pose, f.intrinsic, nullptr, st));
+  XPT_TRY(launch_pyramids(ctx, &f, nullptr, true, st));
+  LevelTable lt = make_levels(ctx, &f, nullptr);
+  return launch_warp_fwd(ctx, lt, depth_ms, synth_ms, mask_ms, st);
+}
+
+int xpt_synthesize_backward(xpt_ctx* ctx, const xpt_frames* frames, const float* const depth_ms[], const float* pose,
+                            const float* const grad_synth_ms[], float* const d_depth_ms[], float* d_pose,
+                            float* d_source, void* stream) {
+  if (!ctx || !pose) return fail(XPT_BAD_ARGUMENT, "xpt_synthesize_backward: NULL argument");
+  XPT_TRY(check_frames(ctx, frames, false));
+  XPT_TRY(check_list(ctx, (const void* const*)depth_ms, "depth_ms", true));
+  XPT_TRY(check_list(ctx, (const void* const*)grad_synth_ms, "grad_synth_ms", true));
+  cudaStream_t st = (cudaStream_t)stream;
+  XPT_CUDA(cudaSetDevice(ctx->cfg.device));
+  ctx->launches = 0;
+  xpt_frames f = *frames;
+  f.target = nullptr;
+  XPT_TRY(launch_geometry(ctx, pose, f.intrinsic, nullptr, st));
+  XPT_TRY(launch_pyramids(ctx, &f, nullptr, true, st));
+  LevelTable lt = make_levels(ctx, &f, nullptr);
+  return launch_warp_bwd(ctx, lt, depth_ms, grad_synth_ms, d_depth_ms, d_source, pose, d_pose, 1.0f, st);
+}
+
+int xpt_photometric_loss(xpt_ctx* ctx, int method, const float* const synth_ms[], const float* const target_ms[],
+                         float* loss_batch, const float* grad_loss_batch, float* const d_synth_ms[], void* stream) {
+  if (!ctx || !loss_batch) return fail(XPT_BAD_ARGUMENT, "xpt_photometric_loss: NULL argument");
+  if (method != XPT_PHOTO_L1 && method != XPT_PHOTO_L2 && method != XPT_PHOTO_SSIM)
+    return fail(XPT_BAD_ARGUMENT, "unknown photometric method %d", method);
+  XPT_TRY(check_list(ctx, (const void* const*)synth_ms, "synth_ms", true));
+  XPT_TRY(check_list(ctx, (const void* const*)target_ms, "target_ms", true));
+  if (d_synth_ms) XPT_TRY(check_list(ctx, (const void* const*)d_synth_ms, "d_synth_ms", true));
+  cudaStream_t st = (cudaStream_t)stream;
+  XPT_CUDA(cudaSetDevice(ctx->cfg.device));
+  ctx->launches = 0;
+  PhotoArgs a;
+  memset(&a, 0, sizeof(a));
+  a.lt = make_levels(ctx, nullptr, target_ms);
+  fill_photo_norms(ctx, a);
+  a.l1_kind = method == XPT_PHOTO_L1 ? 1 : (method == XPT_PHOTO_L2 ? 2 : 0);
+  a.do_ssim = method == XPT_PHOTO_SSIM;
+  a.gcoef_l1 = 1.f; a.gcoef_ssim = 1.f; a.gbatch = grad_loss_batch;
+  for (int l = 0; l < ctx->S; ++l) { a.synth[l] = synth_ms[l]; a.gsynth[l] = d_synth_ms ? d_synth_ms[l] : nullptr; }
+  if (d_synth_ms) XPT_TRY((launch_photo<false, true>(ctx, a, st)));
+  else XPT_TRY((launch_photo<false, false>(ctx, a, st)));
+  // column 0 holds L1/L2, column 1 SSIM: select the requested one into loss_batch[B]
+  float* lb3 = nullptr;
+  XPT_TRY(dev_alloc(ctx, &ctx->st_loss_batch, (size_t)3 * ctx->B));
+  lb3 = ctx->st_loss_batch;
+  XPT_TRY(launch_loss_epilogue(ctx, ctx->first_tile[ctx->S], 0.f, 0.f, 0.f, nullptr, lb3, st));
+  int col = method == XPT_PHOTO_SSIM ? 1 : 0;
+  XPT_CUDA(cudaMemcpyAsync(loss_batch, lb3 + (size_t)col * ctx->B, ctx->B * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return XPT_OK;
+}
+
+int xpt_smoothness_loss(xpt_ctx* ctx, const float* const disp_ms[], const float* const target_ms[], float* loss_batch,
+                        const float* grad_loss_batch, float* const d_disp_ms[], void* stream) {
+  if (!ctx || !loss_batch) return fail(XPT_BAD_ARGUMENT, "xpt_smoothness_loss: NULL argument");
+  XPT_TRY(check_list(ctx, (const void* const*)disp_ms, "disp_ms", true));
+  XPT_TRY(check_list(ctx, (const void* const*)target_ms, "target_ms", true));
+  if (d_disp_ms) XPT_TRY(check_list(ctx, (const void* const*)d_disp_ms, "d_disp_ms", true));
+  cudaStream_t st = (cudaStream_t)stream;
+  XPT_CUDA(cudaSetDevice(ctx->cfg.device));
+  ctx->launches = 0;
+  LevelTable lt = make_levels(ctx, nullptr, target_ms);
+  XPT_TRY(launch_smooth(ctx, disp_ms, lt, grad_loss_batch, 1.f, d_disp_ms, 0, st));
+  XPT_TRY(dev_alloc(ctx, &ctx->st_loss_batch, (size_t)3 * ctx->B));
+  XPT_TRY(launch_loss_epilogue(ctx, ctx->first_sm_chunk[ctx->S], 0.f, 0.f, 0.f, nullptr, ctx->st_loss_batch, st));
+  XPT_CUDA(cudaMemcpyAsync(loss_batch, ctx->st_loss_batch + (size_t)2 * ctx->B, ctx->B * sizeof(float),
+                           cudaMemcpyDeviceToDevice, st));
+  return XPT_OK;
+}
+
+int xpt_total_loss(xpt_ctx* ctx, const xpt_frames* frames, const float* const depth_ms[],
+                   const float* const disp_ms[], const float* pose, const xpt_loss_outputs* out, void* stream) {
+  if (!ctx || !pose || !out) return fail(XPT_BAD_ARGUMENT, "xpt_total_loss: NULL argument");
+  if (!out->losses) return fail(XPT_BAD_ARGUMENT, "out->losses is NULL");
+  XPT_TRY(check_frames(ctx, frames, true));
+  XPT_TRY(check_list(ctx, (const void* const*)depth_ms, "depth_ms", true));
+  const xpt_config& c = ctx->cfg;
+  const bool do_smooth = c.w_smooth != 0.f;
+  if (do_smooth) XPT_TRY(check_list(ctx, (const void* const*)disp_ms, "disp_ms", true));
+  cudaStream_t st = (cudaStream_t)stream;
+  XPT_CUDA(cudaSetDevice(c.device));
+  ctx->launches = 0;
+
+  bool grad = out->d_pose || out->d_source;
+  for (int l = 0; l < ctx->S; ++l) grad = grad || out->d_depth_ms[l] || out->d_disp_ms[l];
+  const float gs = out->grad_scale;
+  const float inv_gb = 1.0f / (float)c.global_batch;
+
+  XPT_TRY(launch_geometry(ctx, pose, frames->intrinsic, nullptr, st));
+  XPT_TRY(launch_pyramids(ctx, frames, out->target_ms, true, st));
+  LevelTable lt = make_levels(ctx, frames, nullptr);
+
+  PhotoArgs a;
+  memset(&a, 0, sizeof(a));
+  a.lt = lt;
+  fill_photo_norms(ctx, a);
+  a.geoK = ctx->geoK; a.geoT = ctx->geoT;
+  a.l1_kind = c.w_l1 != 0.f ? 1 : 0;
+  a.do_ssim = c.w_ssim != 0.f;
+  a.do_smooth = do_smooth;
+  a.gcoef_l1 = c.w_l1 * inv_gb * gs;
+  a.gcoef_ssim = c.w_ssim * inv_gb * gs;
+  a.gcoef_smooth = c.w_smooth * inv_gb * gs;
+  float* d_src[kMaxScales]; long long dbs[kMaxScales], dfs[kMaxScales];
+  XPT_TRY(prepare_dsource(ctx, grad ? out->d_source : nullptr, d_src, dbs, dfs, st));
+  for (int l = 0; l < ctx->S; ++l) {
+    a.depth[l] = depth_ms[l];
+    a.disp[l] = do_smooth ? disp_ms[l] : nullptr;
+    a.synth_out[l] = out->synth_ms[l]; a.mask_out[l] = out->mask_ms[l];
+    a.d_depth[l] = out->d_depth_ms[l]; a.d_disp[l] = out->d_disp_ms[l];
+    a.d_src[l] = d_src[l]; a.d_src_bs[l] = dbs[l]; a.d_src_fs[l] = dfs[l];
+  }
+  const int tiles = ctx->first_tile[ctx->S];
+  if (!do_smooth)      // no smoothness term: its gradient is identically zero
+    for (int l = 0; l < ctx->S; ++l)
+      if (out->d_disp_ms[l])
+        XPT_CUDA(cudaMemsetAsync(out->d_disp_ms[l], 0, (size_t)ctx->B * lvl_pix(ctx, l) * sizeof(float), st));
+
+  if (!(c.flags & XPT_FLAG_UNFUSED)) {
+    // ---- fused path: warp + L1 + SSIM + smoothness (+ all gradients) in one kernel
+    if (grad) XPT_TRY((launch_photo<true, true>(ctx, a, st)));
+    else XPT_TRY((launch_photo<true, false>(ctx, a, st)));
+    if (grad && out->d_pose) {
+      k_pose_epilogue<<<ctx->B * ctx->N, 128, 0, st>>>(ctx->pose_part, ctx->slots_per_b, tiles, pose, out->d_pose,
+                                                       ctx->N, 1.0f);
+      XPT_LAUNCH_CHECK("k_pose_epilogue");
+    }
+    XPT_TRY(launch_loss_epilogue(ctx, tiles, c.w_l1, c.w_ssim, c.w_smooth, out->losses, out->loss_batch, st));
+  } else {
+    // ---- unfused path (flags bit 0): one kernel per reference stage, tensors through HBM
+    float* synth[kMaxScales]; float* gsyn[kMaxScales];
+    for (int l = 0; l < ctx->S; ++l) {
+      size_t n = (size_t)ctx->B * ctx->N * lvl_pix(ctx, l) * 3;
+      if (out->synth_ms[l]) synth[l] = out->synth_ms[l];
+      else { XPT_TRY(dev_alloc(ctx, &ctx->synth_scr[l], n)); synth[l] = ctx->synth_scr[l]; }
+      gsyn[l] = nullptr;
+      if (grad) { XPT_TRY(dev_alloc(ctx, &ctx->gsynth_scr[l], n)); gsyn[l] = ctx->gsynth_scr[l]; }
+      a.synth[l] = synth[l]; a.gsynth[l] = gsyn[l];
+    }
+    XPT_TRY(launch_warp_fwd(ctx, lt, depth_ms, synth, out->mask_ms, st));
+    a.do_smooth = 0;
+    if (grad) XPT_TRY((launch_photo<false, true>(ctx, a, st)));
+    else XPT_TRY((launch_photo<false, false>(ctx, a, st)));
+    int used = tiles;
+    if (do_smooth) {
+      // k_smooth applies gbatch * norm; fold dTotal/dloss in through a per-snippet vector
+      float* gvec = nullptr;
+      if (grad) {
+        XPT_TRY(dev_alloc(ctx, &ctx->st_dpose, (size_t)ctx->B * ctx->N * 6 + ctx->B));
+        gvec = ctx->st_dpose + (size_t)ctx->B * ctx->N * 6;
+        k_fill<<<cdiv(ctx->B, 128), 128, 0, st>>>(gvec, ctx->B, a.gcoef_smooth);
+        XPT_LAUNCH_CHECK("k_fill");
+      }
+      XPT_TRY(launch_smooth(ctx, disp_ms, lt, gvec, 1.f, grad ? out->d_disp_ms : nullptr, tiles, st));
+      used = tiles + ctx->first_sm_chunk[ctx->S];
+    }
+    XPT_TRY(launch_loss_epilogue(ctx, used, c.w_l1, c.w_ssim, c.w_smooth, out->losses, out->loss_batch, st));
+    if (grad) {
+      // reuse the standalone warp backward; d_source was prepared above, so pass NULL and finish here
+      WarpBwdArgs w;
+      memset(&w, 0, sizeof(w));
+      w.lt = lt; w.B = ctx->B; w.N = ctx->N; w.geoK = ctx->geoK; w.geoT = ctx->geoT;
+      w.pose_part = ctx->pose_part; w.slots_per_b = ctx->slots_per_b;
+      int maxchunks = 0;
+      for (int l = 0; l < ctx->S; ++l) {
+        w.depth[l] = depth_ms[l]; w.gsynth[l] = gsyn[l]; w.d_depth[l] = out->d_depth_ms[l];
+        w.d_src[l] = d_src[l]; w.d_src_bs[l] = dbs[l]; w.d_src_fs[l] = dfs[l];
+        w.chunk_base[l] = ctx->first_chunk[l];
+        if (ctx->chunks[l] > maxchunks) maxchunks = ctx->chunks[l];
+      }
+      dim3 grid(maxchunks, ctx->B, ctx->S);
+      k_warp_bwd<<<grid, kWarpBwdThreads, 0, st>>>(w);
+      XPT_LAUNCH_CHECK("k_warp_bwd");
+      if (out->d_pose) {
+        k_pose_epilogue<<<ctx->B * ctx->N, 128, 0, st>>>(ctx->pose_part, ctx->slots_per_b, ctx->first_chunk[ctx->S],
+                                                         pose, out->d_pose, ctx->N, 1.0f);
+        XPT_LAUNCH_CHECK("k_pose_epilogue");
+      }
+    }
+  }
+  if (grad) XPT_TRY(finish_dsource(ctx, out->d_source, st));
+  return XPT_OK;
+}
+
+int xpt_total_loss_host(xpt_ctx* ctx, const xpt_frames* frames, const float* const depth_ms[],
+                        const float* const disp_ms[], const float* pose, const xpt_loss_outputs* out, void* stream) {
+  if (!ctx || !pose || !out) return fail(XPT_BAD_ARGUMENT, "xpt_total_loss_host: NULL argument");
+  if (!out->losses) return fail(XPT_BAD_ARGUMENT, "out->losses is NULL");
+  XPT_TRY(check_frames(ctx, frames, true));
+  XPT_TRY(check_list(ctx, (const void* const*)depth_ms, "depth_ms", true));
+  const bool do_smooth = ctx->cfg.w_smooth != 0.f;
+  if (do_smooth) XPT_TRY(check_list(ctx, (const void* const*)disp_ms, "disp_ms", true));
+  const long long hw3 = (long long)ctx->H * ctx->W * 3;
+  if (frames->source_frame_stride != hw3)
+    return fail(XPT_BAD_SHAPE, "host entry point needs dense frames (source_frame_stride == H*W*3)");
+  cudaStream_t st = (cudaStream_t)stream;
+  XPT_CUDA(cudaSetDevice(ctx->cfg.device));
+  const int B = ctx->B, N = ctx->N, S = ctx->S;
+  const size_t fb = sizeof(float);
+
+  // ---- host -> device staging ------------------------------------------------
+  XPT_TRY(dev_alloc(ctx, &ctx->st_frames, (size_t)B * (N + 1) * hw3));
+  XPT_TRY(dev_alloc(ctx, &ctx->st_K, (size_t)B * 9));
+  XPT_TRY(dev_alloc(ctx, &ctx->st_pose, (size_t)B * N * 6));
+  XPT_TRY(dev_alloc(ctx, &ctx->st_losses, 4));
+  const long long snip = (long long)(N + 1) * hw3;
+  const bool one_block = frames->target == frames->source + (long long)N * hw3 &&
+                         frames->source_batch_stride == snip && frames->target_batch_stride == snip;
+  if (one_block) {
+    XPT_CUDA(cudaMemcpyAsync(ctx->st_frames, frames->source, (size_t)B * snip * fb, cudaMemcpyHostToDevice, st));
+  } else {
+    XPT_CUDA(cudaMemcpy2DAsync(ctx->st_frames, snip * fb, frames->source, frames->source_batch_stride * fb,
+                               (size_t)N * hw3 * fb, B, cudaMemcpyHostToDevice, st));
+    XPT_CUDA(cudaMemcpy2DAsync(ctx->st_frames + (long long)N * hw3, snip * fb, frames->target,
+                               frames->target_batch_stride * fb, (size_t)hw3 * fb, B, cudaMemcpyHostToDevice, st));
+  }
+  XPT_CUDA(cudaMemcpyAsync(ctx->st_K, frames->intrinsic, (size_t)B * 9 * fb, cudaMemcpyHostToDevice, st));
+  XPT_CUDA(cudaMemcpyAsync(ctx->st_pose, pose, (size_t)B * N * 6 * fb, cudaMemcpyHostToDevice, st));
+  const float* d_depth_in[kMaxScales]; const float* d_disp_in[kMaxScales];
+  for (int l = 0; l < S; ++l) {
+    size_t n = (size_t)B * lvl_pix(ctx, l);
+    XPT_TRY(dev_alloc(ctx, &ctx->st_depth[l], n));
+    XPT_CUDA(cudaMemcpyAsync(ctx->st_depth[l], depth_ms[l], n * fb, cudaMemcpyHostToDevice, st));
+    d_depth_in[l] = ctx->st_depth[l];
+    d_disp_in[l] = nullptr;
+    if (do_smooth) {
+      XPT_TRY(dev_alloc(ctx, &ctx->st_disp[l], n));
+      XPT_CUDA(cudaMemcpyAsync(ctx->st_disp[l], disp_ms[l], n * fb, cudaMemcpyHostToDevice, st));
+      d_disp_in[l] = ctx->st_disp[l];
+    }
+  }
+  xpt_frames df;
+  df.source = ctx->st_frames; df.source_batch_stride = snip; df.source_frame_stride = hw3;
+  df.target = ctx->st_frames + (long long)N * hw3; df.target_batch_stride = snip;
+  df.intrinsic = ctx->st_K;
+
+  // ---- device outputs mirroring the requested host outputs --------------------
+  xpt_loss_outputs dout;
+  memset(&dout, 0, sizeof(dout));
+  dout.grad_scale = out->grad_scale;
+  dout.losses = ctx->st_losses;
+  if (out->loss_batch) { XPT_TRY(dev_alloc(ctx, &ctx->st_loss_batch, (size_t)3 * B)); dout.loss_batch = ctx->st_loss_batch; }
+  if (out->d_pose) { XPT_TRY(dev_alloc(ctx, &ctx->st_dpose, (size_t)B * N * 6 + B)); dout.d_pose = ctx->st_dpose; }
+  if (out->d_source) { XPT_TRY(dev_alloc(ctx, &ctx->st_dsource, (size_t)B * N * hw3)); dout.d_source = ctx->st_dsource; }
+  for (int l = 0; l < S; ++l) {
+    size_t n = (size_t)B * lvl_pix(ctx, l);
+    if (out->d_depth_ms[l]) { XPT_TRY(dev_alloc(ctx, &ctx->st_ddepth[l], n)); dout.d_depth_ms[l] = ctx->st_ddepth[l]; }
+    if (out->d_disp_ms[l]) { XPT_TRY(dev_alloc(ctx, &ctx->st_ddisp[l], n)); dout.d_disp_ms[l] = ctx->st_ddisp[l]; }
+    if (out->synth_ms[l]) { XPT_TRY(dev_alloc(ctx, &ctx->st_synth[l], n * N * 3)); dout.synth_ms[l] = ctx->st_synth[l]; }
+    if (out->mask_ms[l]) { XPT_TRY(dev_alloc(ctx, &ctx->st_mask[l], n * N)); dout.mask_ms[l] = ctx->st_mask[l]; }
+    if (out->target_ms[l]) { XPT_TRY(dev_alloc(ctx, &ctx->st_target[l], n * 3)); dout.target_ms[l] = ctx->st_target[l]; }
+  }
+  XPT_TRY(xpt_total_loss(ctx, &df, d_depth_in, d_disp_in, ctx->st_pose, &dout, stream));
+
+  // ---- device -> host ----------------------------------------------------------
+  XPT_CUDA(cudaMemcpyAsync(out->losses, dout.losses, 4 * fb, cudaMemcpyDeviceToHost, st));
+  if (out->loss_batch) XPT_CUDA(cudaMemcpyAsync(out->loss_batch, dout.loss_batch, (size_t)3 * B * fb, cudaMemcpyDeviceToHost, st));
+  if (out->d_pose) XPT_CUDA(cudaMemcpyAsync(out->d_pose, dout.d_pose, (size_t)B * N * 6 * fb, cudaMemcpyDeviceToHost, st));
+  if (out->d_source) XPT_CUDA(cudaMemcpyAsync(out->d_source, dout.d_source, (size_t)B * N * hw3 * fb, cudaMemcpyDeviceToHost, st));
+  for (int l = 0; l < S; ++l) {
+    size_t n = (size_t)B * lvl_pix(ctx, l);
+    if (out->d_depth_ms[l]) XPT_CUDA(cudaMemcpyAsync(out->d_depth_ms[l], dout.d_depth_ms[l], n * fb, cudaMemcpyDeviceToHost, st));
+    if (out->d_disp_ms[l]) XPT_CUDA(cudaMemcpyAsync(out->d_disp_ms[l], dout.d_disp_ms[l], n * fb, cudaMemcpyDeviceToHost, st));
+    if (out->synth_ms[l]) XPT_CUDA(cudaMemcpyAsync(out->synth_ms[l], dout.synth_ms[l], n * N * 3 * fb, cudaMemcpyDeviceToHost, st));
+    if (out->mask_ms[l]) XPT_CUDA(cudaMemcpyAsync(out->mask_ms[l], dout.mask_ms[l], n * N * fb, cudaMemcpyDeviceToHost, st));
+    if (out->target_ms[l]) XPT_CUDA(cudaMemcpyAsync(out->target_ms[l], dout.target_ms[l], n * 3 * fb, cudaMemcpyDeviceToHost, st));
+  }
+  XPT_CUDA(cudaStreamSynchronize(st));
+  return XPT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,299 @@
+"""Host-side engine: plans (xpt_ctx handles), pointer marshalling, output allocation.
+
+PyTorch is used here for device memory, streams and autograd plumbing only; all
+arithmetic happens in libxptwarp.so.  Inputs may be torch CUDA tensors or any
+``__dlpack__`` producer (zero-copy, see dlpack.py)."""
+from __future__ import annotations
+
+import collections
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _cabi
+from ._cabi import XPT_MAX_SCALES, XptConfig, XptFrames, XptLossOutputs, ptr_array
+from .dlpack import kDLCUDA, view_of
+
+
+class WrongInputException(Exception):
+    """Same name and role as the reference's utils/util_class.py:11-13."""
+
+    def __init__(self, msg):
+        super().__init__(msg)
+
+
+def as_torch(x) -> torch.Tensor:
+    """torch tensor as-is; any other DLPack producer is imported zero-copy."""
+    if isinstance(x, torch.Tensor):
+        return x
+    if hasattr(x, "__dlpack__") or type(x).__name__ == "PyCapsule":
+        v = view_of(x)            # validates dtype and reads the device without consuming the capsule
+        if v.device_type != kDLCUDA:
+            raise WrongInputException("xptwarp needs CUDA tensors (DLPack device_type kDLCUDA); there is no CPU path")
+        return torch.from_dlpack(x)
+    raise WrongInputException(f"unsupported tensor type {type(x).__name__}: need torch.Tensor or __dlpack__")
+
+
+def _check_cuda_f32(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise WrongInputException(f"{name} must live on a CUDA device: xptwarp has no CPU fallback")
+    if t.dtype != torch.float32:
+        raise WrongInputException(f"{name} must be float32, got {t.dtype}")
+
+
+def _dense(t: torch.Tensor, name: str) -> torch.Tensor:
+    _check_cuda_f32(t, name)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _frame_view(t: torch.Tensor, name: str, lead: int) -> torch.Tensor:
+    """[...lead dims..., H, W, 3] with dense inner (H, W, 3): leading dims may be strided views."""
+    _check_cuda_f32(t, name)
+    H, W, Cn = t.shape[-3:]
+    if Cn != 3:
+        raise WrongInputException(f"{name}: channel-last RGB expected, got {tuple(t.shape)}")
+    if t.stride(-1) != 1 or t.stride(-2) != 3 or t.stride(-3) != W * 3:
+        t = t.contiguous()
+    return t
+
+
+class Plan:
+    """Owns one xpt_ctx (shapes, weights and device scratch bound at creation)."""
+
+    def __init__(self, device_index, B, N, H, W, scales, scale_weights, w_l1, w_ssim, w_smooth,
+                 global_batch, flags=0, img_grad_factor=4.0):
+        if len(scales) > XPT_MAX_SCALES:
+            raise WrongInputException(f"at most {XPT_MAX_SCALES} scales")
+        cfg = XptConfig()
+        cfg.batch, cfg.num_src, cfg.height, cfg.width = B, N, H, W
+        cfg.num_scales = len(scales)
+        for i, s in enumerate(scales):
+            cfg.scales[i] = int(s)
+            cfg.scale_weights[i] = float(scale_weights[i])
+        cfg.w_l1, cfg.w_ssim, cfg.w_smooth = float(w_l1), float(w_ssim), float(w_smooth)
+        cfg.img_grad_factor = float(img_grad_factor)
+        cfg.global_batch = int(global_batch)
+        cfg.device = int(device_index)
+        cfg.flags = int(flags)
+        self.cfg = cfg
+        self.B, self.N, self.H, self.W = B, N, H, W
+        self.scales = tuple(int(s) for s in scales)
+        self.S = len(scales)
+        self.device = torch.device("cuda", device_index)
+        self._lib = _cabi.lib()
+        h = C.c_void_p()
+        _cabi.check(self._lib.xpt_create(C.byref(h), C.byref(cfg)))
+        self.handle = h
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._lib.xpt_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- helpers ------------------------------------------------------------
+    def level_hw(self, l):
+        return self.H // self.scales[l], self.W // self.scales[l]
+
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def launches(self):
+        return self._lib.xpt_last_launch_count(self.handle)
+
+    def scratch_bytes(self):
+        return self._lib.xpt_scratch_bytes(self.handle)
+
+    def _frames(self, source, target, intrinsic):
+        f = XptFrames()
+        f.source = source.data_ptr()
+        f.source_batch_stride = source.stride(0)
+        f.source_frame_stride = source.stride(1)
+        if target is not None:
+            f.target = target.data_ptr()
+            f.target_batch_stride = target.stride(0)
+        f.intrinsic = intrinsic.data_ptr()
+        return f
+
+    def _level_list(self, ts: Sequence[torch.Tensor], name, last):
+        if len(ts) != self.S:
+            raise WrongInputException(f"{name}: expected {self.S} scales, got {len(ts)}")
+        out = []
+        for l, t in enumerate(ts):
+            h, w = self.level_hw(l)
+            t = _dense(t, f"{name}[{l}]")
+            if t.numel() != self.B * h * w * last:
+                raise WrongInputException(f"{name}[{l}]: expected {self.B}x..x{h}x{w} ({last} per pixel), got {tuple(t.shape)}")
+            out.append(t)
+        return out
+
+    def _empty_levels(self, *lead_last):
+        lead, last = lead_last
+        return [torch.empty((self.B, *lead, *self.level_hw(l), last), dtype=torch.float32, device=self.device)
+                for l in range(self.S)]
+
+    # ---- C-ABI calls ----------------------------------------------------------
+    def pose_rvec2matr(self, pose):
+        pose = _dense(pose, "pose")
+        out = torch.empty((self.B, self.N, 4, 4), dtype=torch.float32, device=self.device)
+        _cabi.check(self._lib.xpt_pose_rvec2matr(self.handle, pose.data_ptr(), out.data_ptr(), self.stream()))
+        return out
+
+    def build_pyramids(self, source, target, intrinsic=None):
+        source = _frame_view(source, "source", 2)
+        target = _frame_view(target, "target", 1)
+        K = intrinsic if intrinsic is not None else torch.zeros(self.B, 3, 3, device=self.device)
+        tgt = self._empty_levels((), 3)
+        f = self._frames(source, target, _dense(K, "intrinsic"))
+        arr = ptr_array([t.data_ptr() for t in tgt])
+        _cabi.check(self._lib.xpt_build_pyramids(self.handle, C.byref(f), C.byref(arr), self.stream()))
+        return tgt
+
+    def synthesize(self, source, intrinsic, depth_ms, pose, want_mask=False):
+        source = _frame_view(source, "source", 2)
+        intrinsic, pose = _dense(intrinsic, "intrinsic"), _dense(pose, "pose")
+        depth_ms = self._level_list(depth_ms, "depth_ms", 1)
+        synth = self._empty_levels((self.N,), 3)
+        mask = self._empty_levels((self.N,), 1) if want_mask else None
+        f = self._frames(source, None, intrinsic)
+        d = ptr_array([t.data_ptr() for t in depth_ms])
+        s = ptr_array([t.data_ptr() for t in synth])
+        m = ptr_array([t.data_ptr() for t in mask]) if want_mask else None
+        _cabi.check(self._lib.xpt_synthesize(self.handle, C.byref(f), C.byref(d), pose.data_ptr(), C.byref(s),
+                                             C.byref(m) if want_mask else None, self.stream()))
+        return synth, mask
+
+    def synthesize_backward(self, source, intrinsic, depth_ms, pose, grad_synth_ms, want_source_grad=False):
+        source = _frame_view(source, "source", 2)
+        intrinsic, pose = _dense(intrinsic, "intrinsic"), _dense(pose, "pose")
+        depth_ms = self._level_list(depth_ms, "depth_ms", 1)
+        grad_synth_ms = self._level_list(grad_synth_ms, "grad_synth_ms", self.N * 3)
+        d_depth = self._empty_levels((), 1)
+        d_pose = torch.empty((self.B, self.N, 6), dtype=torch.float32, device=self.device)
+        d_source = (torch.empty((self.B, self.N, self.H, self.W, 3), dtype=torch.float32, device=self.device)
+                    if want_source_grad else None)
+        f = self._frames(source, None, intrinsic)
+        _cabi.check(self._lib.xpt_synthesize_backward(
+            self.handle, C.byref(f), C.byref(ptr_array([t.data_ptr() for t in depth_ms])), pose.data_ptr(),
+            C.byref(ptr_array([t.data_ptr() for t in grad_synth_ms])),
+            C.byref(ptr_array([t.data_ptr() for t in d_depth])), d_pose.data_ptr(),
+            d_source.data_ptr() if want_source_grad else None, self.stream()))
+        return d_depth, d_pose, d_source
+
+    def photometric_loss(self, method, synth_ms, target_ms, grad_loss_batch=None, want_grad=False):
+        synth_ms = self._level_list(synth_ms, "synth_target_ms", self.N * 3)
+        target_ms = self._level_list(target_ms, "target_ms", 3)
+        loss = torch.empty((self.B,), dtype=torch.float32, device=self.device)
+        d_synth = self._empty_levels((self.N,), 3) if want_grad else None
+        g = _dense(grad_loss_batch, "grad_loss_batch") if grad_loss_batch is not None else None
+        _cabi.check(self._lib.xpt_photometric_loss(
+            self.handle, int(method), C.byref(ptr_array([t.data_ptr() for t in synth_ms])),
+            C.byref(ptr_array([t.data_ptr() for t in target_ms])), loss.data_ptr(),
+            g.data_ptr() if g is not None else None,
+            C.byref(ptr_array([t.data_ptr() for t in d_synth])) if want_grad else None, self.stream()))
+        return loss, d_synth
+
+    def smoothness_loss(self, disp_ms, target_ms, grad_loss_batch=None, want_grad=False):
+        disp_ms = self._level_list(disp_ms, "disp_ms", 1)
+        target_ms = self._level_list(target_ms, "target_ms", 3)
+        loss = torch.empty((self.B,), dtype=torch.float32, device=self.device)
+        d_disp = self._empty_levels((), 1) if want_grad else None
+        g = _dense(grad_loss_batch, "grad_loss_batch") if grad_loss_batch is not None else None
+        _cabi.check(self._lib.xpt_smoothness_loss(
+            self.handle, C.byref(ptr_array([t.data_ptr() for t in disp_ms])),
+            C.byref(ptr_array([t.data_ptr() for t in target_ms])), loss.data_ptr(),
+            g.data_ptr() if g is not None else None,
+            C.byref(ptr_array([t.data_ptr() for t in d_disp])) if want_grad else None, self.stream()))
+        return loss, d_disp
+
+    def total_loss(self, source, target, intrinsic, depth_ms, disp_ms, pose, want_grad=True, want_synth=False,
+                   want_mask=False, want_target_ms=False, want_source_grad=False, want_loss_batch=False,
+                   grad_scale=1.0, out: Optional[dict] = None):
+        """xpt_total_loss.  `out` may carry preallocated output tensors from a previous call
+        (same keys as the returned dict) so that steady-state steps allocate nothing."""
+        source = _frame_view(source, "source", 2)
+        target = _frame_view(target, "target", 1)
+        intrinsic, pose = _dense(intrinsic, "intrinsic"), _dense(pose, "pose")
+        depth_ms = self._level_list(depth_ms, "depth_ms", 1)
+        have_disp = disp_ms is not None
+        if have_disp:
+            disp_ms = self._level_list(disp_ms, "disp_ms", 1)
+        elif self.cfg.w_smooth != 0.0:
+            raise WrongInputException("disp_ms is required when the smoothe weight is non-zero")
+        r = out if out is not None else {}
+        dev, f32 = self.device, torch.float32
+
+        def need(key, make):
+            if key not in r or r[key] is None:
+                r[key] = make()
+            return r[key]
+        o = XptLossOutputs()
+        o.grad_scale = float(grad_scale)
+        o.losses = need("losses", lambda: torch.empty(4, dtype=f32, device=dev)).data_ptr()
+        if want_loss_batch:
+            o.loss_batch = need("loss_batch", lambda: torch.empty((3, self.B), dtype=f32, device=dev)).data_ptr()
+
+        def put(field, key, lead, last):
+            ts = need(key, lambda: self._empty_levels(lead, last))
+            for l, t in enumerate(ts):
+                getattr(o, field)[l] = t.data_ptr()
+        if want_synth:
+            put("synth_ms", "synth_ms", (self.N,), 3)
+        if want_mask:
+            put("mask_ms", "mask_ms", (self.N,), 1)
+        if want_target_ms:
+            put("target_ms", "target_ms", (), 3)
+        if want_grad:
+            put("d_depth_ms", "d_depth_ms", (), 1)
+            put("d_disp_ms", "d_disp_ms", (), 1)
+            o.d_pose = need("d_pose", lambda: torch.empty((self.B, self.N, 6), dtype=f32, device=dev)).data_ptr()
+            if want_source_grad:
+                o.d_source = need("d_source", lambda: torch.empty((self.B, self.N, self.H, self.W, 3), dtype=f32,
+                                                                  device=dev)).data_ptr()
+        f = self._frames(source, target, intrinsic)
+        d = ptr_array([t.data_ptr() for t in depth_ms])
+        dd = ptr_array([t.data_ptr() for t in disp_ms]) if have_disp else None
+        _cabi.check(self._lib.xpt_total_loss(self.handle, C.byref(f), C.byref(d),
+                                             C.byref(dd) if have_disp else None, pose.data_ptr(), C.byref(o),
+                                             self.stream()))
+        return r
+
+
+_PLANS: "collections.OrderedDict[tuple, Plan]" = collections.OrderedDict()
+_MAX_PLANS = 8
+
+
+def get_plan(device_index, B, N, H, W, scales, scale_weights=None, w_l1=0.0, w_ssim=0.0, w_smooth=0.0,
+             global_batch=0, flags=0, img_grad_factor=4.0) -> Plan:
+    scales = tuple(int(s) for s in scales)
+    sw = tuple(float(w) for w in (scale_weights if scale_weights is not None else [1.0] * len(scales)))
+    key = (device_index, B, N, H, W, scales, sw, float(w_l1), float(w_ssim), float(w_smooth),
+           int(global_batch) or B, int(flags), float(img_grad_factor))
+    p = _PLANS.get(key)
+    if p is None:
+        p = Plan(device_index, B, N, H, W, scales, sw, w_l1, w_ssim, w_smooth, int(global_batch) or B, flags,
+                 img_grad_factor)
+        _PLANS[key] = p
+        while len(_PLANS) > _MAX_PLANS:
+            _, old = _PLANS.popitem(last=False)
+            old.close()
+    else:
+        _PLANS.move_to_end(key)
+    return p
+
+
+def infer_scales(H: int, depth_ms: Sequence[torch.Tensor]) -> List[int]:
+    """scale = H // H_s, read from static shapes like synthesize_base.py:61-64."""
+    scales = []
+    for d in depth_ms:
+        hs = d.shape[1]
+        if hs <= 0 or H % hs:
+            raise WrongInputException(f"depth height {hs} does not divide the image height {H}")
+        scales.append(H // hs)
+    return scales
