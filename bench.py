@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- fwd+bwd warp+loss throughput (Gpixels/s) of the xpt-mde hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg5]
+
+A "step" is one pass of the hot path over one batch of synthetic snippets: pyramids, inverse
+warp of 4 sources at 4 scales, L1 + SSIM + edge-aware smoothness, and the backward to
+dL/ddepth_ms, dL/ddisp_ms, dL/dpose (reference model/loss_and_metric/losses.py:26-55 under
+train_val.py:78-92).  A pixel is one full-resolution target pixel of one snippet.
+Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "xpt-mde-2021_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+METRIC = "fwd+bwd warp+loss Gpixels/s"
+UNIT = "Gpixel/s"
+WORKLOADS = {
+    # name: (B per rank, H, W)   -- BASELINE.json configs[1], [2], [4]
+    "cfg2": (8, 128, 384),
+    "cfg3": (16, 256, 832),
+    "cfg5": (128, 384, 1280),
+}
+N_SRC, N_SCALES = 4, 4
+GAMMA = sum(1.0 / (4 ** s) for s in range(N_SCALES))          # 85/64
+# algorithmic bytes per full-res target pixel (DESIGN.md "Bytes model")
+BYTES_PREP = 48 + 48 * (GAMMA - 1) + 12 + 12 * (GAMMA - 1)     # read frames, write levels s>1: 79.7
+BYTES_FUSED = N_SRC * GAMMA * 12 + GAMMA * 12 + 4 * GAMMA * 4   # gather src_ms, tgt_ms, depth, disp, d_depth, d_disp: 100.9
+BYTES_SURVEY_STEP = 355.9                                      # unfused fwd + bwd + prep model of SURVEY 8d
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_input_sets(orc, B, H, W, n_sets, seed, device):
+    """n_sets distinct snippet batches resident in HBM (rotated so that no step finds its inputs in L2).
+    Two are generated from scratch; the rest are cheap perturbations of those (rolled images, scaled
+    depth, jittered pose) -- generating 20+ full batches on the CPU would dominate start-up."""
+    base = [orc.make_inputs(B, H, W, N=N_SRC, n_scales=N_SCALES, seed=seed + i) for i in range(2)]
+    sets = []
+    for i in range(n_sets):
+        bf, bp = base[i % 2]
+        if i < 2:
+            feats, preds = bf, bp
+        else:
+            g = torch.Generator().manual_seed(seed + i)
+            feats = {"image5d": torch.roll(bf["image5d"], shifts=(i, 3 * i), dims=(2, 3)), "intrinsic": bf["intrinsic"]}
+            preds = {"depth_ms": [d * (1 + 0.01 * i) for d in bp["depth_ms"]],
+                     "disp_ms": [d / (1 + 0.01 * i) for d in bp["disp_ms"]],
+                     "pose": bp["pose"] * (1 + 0.02 * torch.rand(bp["pose"].shape, generator=g))}
+        sets.append(({k: v.to(device) for k, v in feats.items()},
+                     {"depth_ms": [d.to(device) for d in preds["depth_ms"]],
+                      "disp_ms": [d.to(device) for d in preds["disp_ms"]], "pose": preds["pose"].to(device)}))
+    return sets, base
+
+
+def set_bytes(feats, preds):
+    n = feats["image5d"].numel() + feats["intrinsic"].numel() + preds["pose"].numel()
+    n += sum(d.numel() for d in preds["depth_ms"]) + sum(d.numel() for d in preds["disp_ms"])
+    return 4 * n
+
+
+def run_reference(args, B, H, W):
+    """--impl reference: the reference's CPU implementation of the path, i.e. the oracle restatement of
+    its TF op graph on torch-CPU with all host threads (TF 2.4.1 is not installable offline)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import xpt_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    feats, preds = orc.make_inputs(B, H, W, N=N_SRC, n_scales=N_SCALES, seed=20211 + 2000)
+    lw, sw = orc.LOSS_RIGID_T1, orc.SCALE_WEIGHT_T1
+
+    def step(fb, pb):
+        orc.loss_and_grads(fb, pb, lw, sw, global_batch=B)
+    # bound the run: size the per-step sample from one probe step on a single snippet
+    sub = lambda b: ({k: v[:b] for k, v in feats.items()},
+                     {"depth_ms": [d[:b] for d in preds["depth_ms"]], "disp_ms": [d[:b] for d in preds["disp_ms"]],
+                      "pose": preds["pose"][:b]})
+    f1, p1 = sub(1)
+    step(f1, p1)
+    t0 = time.perf_counter()
+    step(f1, p1)
+    t1 = time.perf_counter() - t0
+    budget = 150.0
+    sb = int(max(1, min(B, budget / max(1e-6, (args.steps + args.warmup) * t1))))
+    fb, pb = sub(sb)
+    for _ in range(args.warmup):
+        step(fb, pb)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(fb, pb)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = sb * H * W / dt / 1e9
+    sample = f"{sb} of {B} snippets per step ({H}x{W}, 4 sources, 4 scales, fwd+bwd), {args.steps} steps"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3 * (B / sb), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: B={B} {H}x{W} snippet=5 scales=4 LOSS_RIGID_T1",
+                   "note": "reference TF op graph restated on torch-CPU (TF 2.4.1 not installable offline)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA-graph replay")
+    ap.add_argument("--unfused", action="store_true", help="one kernel per reference stage (A/B)")
+    ap.add_argument("--source-grad", action="store_true", help="also produce dL/dsource (config 5's full backward)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=10)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    B, H, W = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, B, H, W)
+        return
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device: xptwarp has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+
+    import xptwarp
+    from xptwarp import _cabi
+    from oracle import xpt_oracle as orc     # input generator + cpu_baseline checker only
+
+    lw, sw = orc.LOSS_RIGID_T1, orc.SCALE_WEIGHT_T1
+    global_batch = B * world                # weak scaling: B snippets per rank (compute_average_loss divisor)
+    flags = (0 if args.no_graph else _cabi.XPT_FLAG_GRAPH) | (_cabi.XPT_FLAG_UNFUSED if args.unfused else 0)
+    plan = xptwarp.get_plan(local_rank, B, N_SRC, H, W, [1, 2, 4, 8], sw, lw["L1"], lw["SSIM"], lw["smoothe"],
+                            global_batch, flags)
+
+    # ---- inputs: enough distinct resident sets that a step never finds its inputs in the 126 MB L2
+    probe_f, probe_p = orc.make_inputs(1, H, W, N=N_SRC, n_scales=N_SCALES, seed=1)
+    per_set = set_bytes(probe_f, probe_p) * B
+    n_sets = int(min(24, max(3, -(-3 * 126e6 // per_set))))
+    sets, sets_cpu = make_input_sets(orc, B, H, W, n_sets, 20211 + 2000 + rank, device)
+    calls = []
+    for f, p in sets:
+        img = f["image5d"]
+        calls.append(plan.bind_total_loss(img[:, :-1], img[:, -1], f["intrinsic"], p["depth_ms"], p["disp_ms"],
+                                          p["pose"], want_grad=True, want_source_grad=args.source_grad))
+    # a real (non-NULL) stream: the legacy default stream cannot be captured into a CUDA graph
+    side = torch.cuda.Stream(device)
+    side.wait_stream(torch.cuda.current_stream(device))
+    torch.cuda.set_stream(side)
+    stream = plan.stream()
+
+    def step(i):
+        c = calls[i % n_sets]
+        c.run(stream)
+        if dist is not None:
+            # the path's only exchange: the 4 loss scalars (replaces distributer.py:93-110)
+            dist.all_reduce(c.out["losses"])
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 2 * n_sets)):        # warm-up also captures one graph per input set
+        step(i)
+    barrier()
+    launches_per_step = plan.launches()
+
+    # ---- timed region A: K steps, device-timed on the launching stream ------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    if ms_total < 400:      # keep the clock sampler meaningful on tiny workloads: same loop, untimed
+        t_end = time.time() + 0.6
+        i = 0
+        while time.time() < t_end:
+            step(i)
+            i += 1
+        torch.cuda.synchronize()
+    clocks = sampler.stop()
+    t = torch.tensor([ms_total], dtype=torch.float64, device=device)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    pixels_step = B * H * W * world
+    value = pixels_step / (ms_step * 1e-3) / 1e9
+
+    # ---- timed region B: the dominant kernel alone (events around each launch, eager launches) -----
+    peak, peak_src = load_peaks()
+    kern_ms = None
+    if not args.unfused:
+        eager = xptwarp.get_plan(local_rank, B, N_SRC, H, W, [1, 2, 4, 8], sw, lw["L1"], lw["SSIM"], lw["smoothe"],
+                                 global_batch, flags & ~_cabi.XPT_FLAG_GRAPH)
+        ecalls = []
+        for (f, p), c in zip(sets, calls):
+            img = f["image5d"]
+            ecalls.append(eager.bind_total_loss(img[:, :-1], img[:, -1], f["intrinsic"], p["depth_ms"], p["disp_ms"],
+                                                p["pose"], want_grad=True, want_source_grad=args.source_grad, out=c.out))
+        for i in range(n_sets):
+            ecalls[i].run(stream)
+        torch.cuda.synchronize()
+        nrec = min(args.steps, 200)
+        eager.profile_begin(nrec)
+        for i in range(nrec):
+            ecalls[i % n_sets].run(stream)
+        torch.cuda.synchronize()
+        durs = eager.profile_end(nrec)
+        kern_ms = sum(durs) / len(durs)
+    px_rank = B * H * W
+    roofline = None
+    if kern_ms:
+        fused_bytes = BYTES_FUSED + (N_SRC * GAMMA * 12 if args.source_grad else 0)
+        ach = px_rank * fused_bytes / (kern_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "k_photo<fused,grad>", "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": ach / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": kern_ms,
+                    "bytes_per_pixel": fused_bytes, "kernel_share_of_step": kern_ms / ms_step if world == 1 else None}
+    step_model = {"bytes_per_pixel": BYTES_SURVEY_STEP,
+                  "achieved_gbs": value / world * BYTES_SURVEY_STEP, "frac_of_peak": value / world * BYTES_SURVEY_STEP / peak,
+                  "note": "SURVEY 8d unfused fwd+bwd+prep bytes model at the measured pixel rate, per GPU"}
+
+    # ---- e2e: same step through the host-buffer C-ABI entry point (H2D + D2H inside) ---------------
+    import ctypes as C
+    fcpu, pcpu = sets_cpu[0]
+    himg = fcpu["image5d"].contiguous().pin_memory()
+    hK, hpose = fcpu["intrinsic"].contiguous().pin_memory(), pcpu["pose"].contiguous().pin_memory()
+    hdepth = [d.contiguous().pin_memory() for d in pcpu["depth_ms"]]
+    hdisp = [d.contiguous().pin_memory() for d in pcpu["disp_ms"]]
+    hlosses, hdpose = torch.zeros(4).pin_memory(), torch.zeros(B, N_SRC, 6).pin_memory()
+    hdd = [torch.zeros_like(d).pin_memory() for d in hdepth]
+    hds = [torch.zeros_like(d).pin_memory() for d in hdepth]
+    fr = _cabi.XptFrames()
+    fr.source, fr.source_batch_stride, fr.source_frame_stride = himg.data_ptr(), himg.stride(0), himg.stride(1)
+    fr.target, fr.target_batch_stride = himg.data_ptr() + N_SRC * himg.stride(1) * 4, himg.stride(0)
+    fr.intrinsic = hK.data_ptr()
+    o = _cabi.XptLossOutputs()
+    o.losses, o.d_pose, o.grad_scale = hlosses.data_ptr(), hdpose.data_ptr(), 1.0
+    for s_ in range(N_SCALES):
+        o.d_depth_ms[s_], o.d_disp_ms[s_] = hdd[s_].data_ptr(), hds[s_].data_ptr()
+    dptr, sptr = _cabi.ptr_array([d.data_ptr() for d in hdepth]), _cabi.ptr_array([d.data_ptr() for d in hdisp])
+    h2d = 4 * (himg.numel() + hK.numel() + hpose.numel() + sum(d.numel() for d in hdepth) + sum(d.numel() for d in hdisp))
+    d2h = 4 * (4 + hdpose.numel() + sum(d.numel() for d in hdd) + sum(d.numel() for d in hds))
+
+    def host_step():
+        rc = plan._lib.xpt_total_loss_host(plan.handle, C.byref(fr), C.byref(dptr), C.byref(sptr), hpose.data_ptr(),
+                                           C.byref(o), stream)
+        if rc != 0:
+            _cabi.check(rc)
+    for _ in range(5):
+        host_step()
+    barrier()
+    n_e2e = max(10, min(args.steps, 100))
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        host_step()                      # synchronous: returns after the D2H copies have landed
+    torch.cuda.synchronize()
+    t_e2e = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=device)
+    if dist is not None:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_val = pixels_step / float(t_e2e.item()) / 1e9
+
+    # ---- CPU baseline beside it (rank 0, N=1 only; bounded sample) ----------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        fb, pb = sets_cpu[0]
+        for _ in range(2):
+            ref = orc.loss_and_grads(fb, pb, lw, sw, global_batch=global_batch)
+        t0 = time.perf_counter()
+        for _ in range(args.cpu_steps):
+            orc.loss_and_grads(fb, pb, lw, sw, global_batch=global_batch)
+        dt = (time.perf_counter() - t0) / args.cpu_steps
+        cpu = {"value": B * H * W / dt / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_steps} steps of the full batch (B={B}, {H}x{W}) on torch-CPU fp32, 2 warm-up",
+               "ms_per_step": dt * 1e3}
+        # the same run also checks the GPU result of input set 0 against the oracle
+        got = calls[0].run(stream)
+        torch.cuda.synchronize()
+        rel = abs(float(got["losses"][0]) - float(ref["total"])) / abs(float(ref["total"]))
+        cpu["gpu_vs_oracle_total_loss_relerr"] = rel
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 2 * n_sets), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: B={B}/gpu {H}x{W} snippet=5 (4 sources) scales=4 LOSS_RIGID_T1 fwd+bwd"
+                                   + (" +dL/dsource" if args.source_grad else ""),
+                       "global_batch": global_batch, "parallelism": f"dp{world}",
+                       "l2": f"rotating {n_sets} resident input sets ({n_sets * per_set / 1e6:.0f} MB > 126 MB L2)",
+                       "launch": "eager" if args.no_graph else "cuda-graph replay", "fused": not args.unfused},
+            "roofline": roofline, "step_model": step_model, "cpu_baseline": cpu, "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches_per_step * args.steps,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -76,6 +76,10 @@ typedef struct {
  * (warp -> synth -> loss -> dL/dsynth -> warp adjoint) instead of the fused
  * tile kernel.  Same results; kept for A/B parity tests and profiling.        */
 #define XPT_FLAG_UNFUSED 1u
+/* xpt_total_loss captures its launches into a CUDA graph the first time it sees a
+ * given argument set (all pointers, strides, grad_scale, stream) and replays the
+ * instantiated graph afterwards (up to 64 cached argument sets per ctx).      */
+#define XPT_FLAG_GRAPH 2u
 
 /* The snippet frames + intrinsics (features of losses.py:26-37).              */
 typedef struct {
@@ -170,6 +174,13 @@ XPT_API int xpt_total_loss(xpt_ctx* ctx, const xpt_frames* frames,
 XPT_API int xpt_total_loss_host(xpt_ctx* ctx, const xpt_frames* frames,
                         const float* const depth_ms[], const float* const disp_ms[],
                         const float* pose, const xpt_loss_outputs* out, void* stream);
+
+/* Device timing of the dominant kernel (the fused photometric tile kernel): after
+ * xpt_profile_begin, each of the next `max_records` eager launches of that kernel is bracketed
+ * by CUDA events on its stream; xpt_profile_end waits for them and returns how many durations
+ * (milliseconds) it wrote to ms_out.  Not recorded inside graph replays.          */
+XPT_API int xpt_profile_begin(xpt_ctx* ctx, int max_records);
+XPT_API int xpt_profile_end(xpt_ctx* ctx, float* ms_out, int capacity);
 
 /* number of kernels the last call on this ctx launched (bench's gpu_launches) */
 XPT_API int xpt_last_launch_count(const xpt_ctx* ctx);

@@ -240,8 +240,8 @@ def test_full_size_properties(xw):
         assert relerr(ru["d_depth_ms"][s].cpu().numpy(), r1["d_depth_ms"][s].cpu().numpy()) < 1e-5
     # (b) gradients are linear in the upstream gradient
     r3 = _run_total(plan, f, p, want_grad=True, grad_scale=3.0)
-    assert relerr(r3["d_pose"].cpu().numpy(), 3.0 * r1["d_pose"].cpu().numpy()) < 1e-6
-    assert relerr(r3["d_depth_ms"][1].cpu().numpy(), 3.0 * r1["d_depth_ms"][1].cpu().numpy()) < 1e-6
+    assert relerr(r3["d_pose"].cpu().numpy(), 3.0 * r1["d_pose"].cpu().numpy()) < 1e-5
+    assert relerr(r3["d_depth_ms"][1].cpu().numpy(), 3.0 * r1["d_depth_ms"][1].cpu().numpy()) < 1e-5
     # (c) snippets are independent: permuting the batch permutes the per-snippet results
     perm = torch.tensor([3, 0, 7, 1, 6, 2, 5, 4])
     fp = {k: v[perm.cuda()] for k, v in f.items()}
@@ -326,3 +326,30 @@ def test_dlpack_only_producer_and_errors(xw):
         xw.SynthesizeMultiScale()(src, K, depth_ms, pose[:, :1])
     with pytest.raises(xw.WrongInputException):
         xw.SynthesizeMultiScale()(src.double(), K, depth_ms, pose)
+
+
+def test_cuda_graph_replay_matches_eager(xw):
+    """XPT_FLAG_GRAPH: the captured-and-replayed step gives bit-identical results, also when the
+    same ctx alternates between argument sets."""
+    from oracle import xpt_oracle as orc
+    from xptwarp import _cabi
+    lw, sw = orc.LOSS_RIGID_T1, orc.SCALE_WEIGHT_T1
+    sets = []
+    for seed in (1, 2):
+        feats, preds = orc.make_inputs(2, 32, 64, seed=seed)
+        sets.append(_to_cuda(feats, preds))
+    eager = _plan_for(xw, *sets[0], lw, sw, 2)
+    graph = _plan_for(xw, *sets[0], lw, sw, 2, flags=_cabi.XPT_FLAG_GRAPH)
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        want = [{k: ([t.clone() for t in v] if isinstance(v, list) else v.clone())
+                 for k, v in _run_total(eager, f, p, want_grad=True).items()} for f, p in sets]
+        calls = [graph.bind_total_loss(f["image5d"][:, :-1], f["image5d"][:, -1], f["intrinsic"], p["depth_ms"],
+                                       p["disp_ms"], p["pose"], want_grad=True) for f, p in sets]
+        for rep in range(3):                 # 1st: eager warm call, 2nd: capture, 3rd: replay
+            for i, c in enumerate(calls):
+                got = c.run()
+                torch.cuda.synchronize()
+                assert torch.equal(got["losses"], want[i]["losses"])
+                assert torch.equal(got["d_pose"], want[i]["d_pose"])
+                assert all(torch.equal(a, b) for a, b in zip(got["d_depth_ms"], want[i]["d_depth_ms"]))

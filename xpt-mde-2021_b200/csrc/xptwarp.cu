@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "xpt_kernels.cuh"
 
@@ -75,6 +76,14 @@ struct xpt_ctx {
   float* st_depth[kMaxScales]; float* st_disp[kMaxScales];
   float* st_ddepth[kMaxScales]; float* st_ddisp[kMaxScales];
   float* st_synth[kMaxScales]; float* st_mask[kMaxScales]; float* st_target[kMaxScales];
+  // CUDA-graph cache of whole xpt_total_loss calls (XPT_FLAG_GRAPH), keyed by every argument
+  struct GraphEntry { std::vector<uint64_t> key; cudaGraphExec_t exec; int launches; };
+  std::vector<GraphEntry>* graphs;
+  bool warm;                    // one eager call has run (all lazy scratch exists)
+  // per-launch device timing of the dominant kernel (xpt_profile_*)
+  std::vector<cudaEvent_t>* prof_events;
+  int prof_count;
+  int prof_on;                  // records still allowed
 };
 
 namespace {
@@ -301,7 +310,10 @@ int launch_photo(xpt_ctx* ctx, const PhotoArgs& a, cudaStream_t st) {
     attr_set = true;
   }
   dim3 grid(a.tiles_per_b, ctx->B);
+  const bool prof = FUSED && ctx->prof_on > 0 && ctx->prof_count < ctx->prof_on;
+  if (prof) XPT_CUDA(cudaEventRecord((*ctx->prof_events)[2 * ctx->prof_count], st));
   k_photo<FUSED, GRAD><<<grid, kPhotoThreads, smem, st>>>(a);
+  if (prof) { XPT_CUDA(cudaEventRecord((*ctx->prof_events)[2 * ctx->prof_count + 1], st)); ++ctx->prof_count; }
   XPT_LAUNCH_CHECK(FUSED ? "k_photo<fused>" : "k_photo<tensor>");
   return XPT_OK;
 }
@@ -437,6 +449,14 @@ void xpt_destroy(xpt_ctx* ctx) {
     F(ctx->st_depth[l]); F(ctx->st_disp[l]); F(ctx->st_ddepth[l]); F(ctx->st_ddisp[l]);
     F(ctx->st_synth[l]); F(ctx->st_mask[l]); F(ctx->st_target[l]);
   }
+  if (ctx->graphs) {
+    for (auto& e : *ctx->graphs) cudaGraphExecDestroy(e.exec);
+    delete ctx->graphs;
+  }
+  if (ctx->prof_events) {
+    for (auto e : *ctx->prof_events) cudaEventDestroy(e);
+    delete ctx->prof_events;
+  }
   delete ctx;
 }
 
@@ -548,8 +568,9 @@ int xpt_smoothness_loss(xpt_ctx* ctx, const float* const disp_ms[], const float*
   return XPT_OK;
 }
 
-int xpt_total_loss(xpt_ctx* ctx, const xpt_frames* frames, const float* const depth_ms[],
-                   const float* const disp_ms[], const float* pose, const xpt_loss_outputs* out, void* stream) {
+static int total_loss_impl(xpt_ctx* ctx, const xpt_frames* frames, const float* const depth_ms[],
+                           const float* const disp_ms[], const float* pose, const xpt_loss_outputs* out,
+                           void* stream) {
   if (!ctx || !pose || !out) return fail(XPT_BAD_ARGUMENT, "xpt_total_loss: NULL argument");
   if (!out->losses) return fail(XPT_BAD_ARGUMENT, "out->losses is NULL");
   XPT_TRY(check_frames(ctx, frames, true));
@@ -660,6 +681,85 @@ int xpt_total_loss(xpt_ctx* ctx, const xpt_frames* frames, const float* const de
   }
   if (grad) XPT_TRY(finish_dsource(ctx, out->d_source, st));
   return XPT_OK;
+}
+
+int xpt_total_loss(xpt_ctx* ctx, const xpt_frames* frames, const float* const depth_ms[],
+                   const float* const disp_ms[], const float* pose, const xpt_loss_outputs* out, void* stream) {
+  if (!ctx || !frames || !pose || !out || !depth_ms) return fail(XPT_BAD_ARGUMENT, "xpt_total_loss: NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!(ctx->cfg.flags & XPT_FLAG_GRAPH)) return total_loss_impl(ctx, frames, depth_ms, disp_ms, pose, out, stream);
+  XPT_CUDA(cudaSetDevice(ctx->cfg.device));
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  XPT_CUDA(cudaStreamIsCapturing(st, &cs));
+  const bool legacy = st == nullptr || st == cudaStreamLegacy;       // the NULL stream cannot be captured
+  if (cs != cudaStreamCaptureStatusNone || !ctx->warm || legacy) {
+    // already inside someone else's capture, or first call (lazy scratch is allocated eagerly once)
+    int rc = total_loss_impl(ctx, frames, depth_ms, disp_ms, pose, out, stream);
+    if (rc == XPT_OK && cs == cudaStreamCaptureStatusNone) ctx->warm = true;
+    return rc;
+  }
+  // key = every argument that ends up in a kernel parameter
+  std::vector<uint64_t> key;
+  key.reserve(16 + 7 * kMaxScales);
+  auto K = [&](const void* p) { key.push_back((uint64_t)(uintptr_t)p); };
+  K(frames->source); key.push_back((uint64_t)frames->source_batch_stride); key.push_back((uint64_t)frames->source_frame_stride);
+  K(frames->target); key.push_back((uint64_t)frames->target_batch_stride); K(frames->intrinsic);
+  K(pose); K(stream); K(out->losses); K(out->loss_batch); K(out->d_pose); K(out->d_source);
+  uint32_t gsbits; memcpy(&gsbits, &out->grad_scale, 4); key.push_back(gsbits);
+  for (int l = 0; l < ctx->S; ++l) {
+    K(depth_ms[l]); K(disp_ms ? disp_ms[l] : nullptr); K(out->synth_ms[l]); K(out->mask_ms[l]);
+    K(out->target_ms[l]); K(out->d_depth_ms[l]); K(out->d_disp_ms[l]);
+  }
+  if (!ctx->graphs) ctx->graphs = new std::vector<xpt_ctx::GraphEntry>();
+  for (auto& e : *ctx->graphs)
+    if (e.key == key) {
+      XPT_CUDA(cudaGraphLaunch(e.exec, st));
+      ctx->launches = e.launches;
+      return XPT_OK;
+    }
+  XPT_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+  int rc = total_loss_impl(ctx, frames, depth_ms, disp_ms, pose, out, stream);
+  cudaGraph_t graph = nullptr;
+  cudaError_t ce = cudaStreamEndCapture(st, &graph);
+  if (rc != XPT_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+  if (ce != cudaSuccess) return fail(XPT_CUDA_ERROR, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
+  cudaGraphExec_t exec = nullptr;
+  ce = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess) return fail(XPT_CUDA_ERROR, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+  if (ctx->graphs->size() >= 64) {           // bounded cache: drop the oldest
+    cudaGraphExecDestroy(ctx->graphs->front().exec);
+    ctx->graphs->erase(ctx->graphs->begin());
+  }
+  ctx->graphs->push_back({key, exec, ctx->launches});
+  XPT_CUDA(cudaGraphLaunch(exec, st));
+  return XPT_OK;
+}
+
+int xpt_profile_begin(xpt_ctx* ctx, int max_records) {
+  if (!ctx || max_records < 0) return fail(XPT_BAD_ARGUMENT, "xpt_profile_begin: bad argument");
+  XPT_CUDA(cudaSetDevice(ctx->cfg.device));
+  if (!ctx->prof_events) ctx->prof_events = new std::vector<cudaEvent_t>();
+  while ((int)ctx->prof_events->size() < 2 * max_records) {
+    cudaEvent_t e;
+    XPT_CUDA(cudaEventCreate(&e));
+    ctx->prof_events->push_back(e);
+  }
+  ctx->prof_count = 0;
+  ctx->prof_on = max_records;
+  return XPT_OK;
+}
+
+int xpt_profile_end(xpt_ctx* ctx, float* ms_out, int capacity) {
+  if (!ctx) return fail(XPT_BAD_ARGUMENT, "xpt_profile_end: NULL ctx");
+  int n = ctx->prof_count;
+  ctx->prof_on = 0;
+  if (n > capacity) n = capacity;
+  for (int i = 0; i < n; ++i) {
+    XPT_CUDA(cudaEventSynchronize((*ctx->prof_events)[2 * i + 1]));
+    XPT_CUDA(cudaEventElapsedTime(ms_out + i, (*ctx->prof_events)[2 * i], (*ctx->prof_events)[2 * i + 1]));
+  }
+  return n;
 }
 
 int xpt_total_loss_host(xpt_ctx* ctx, const xpt_frames* frames, const float* const depth_ms[],

@@ -8,6 +8,7 @@ import os
 
 XPT_MAX_SCALES = 8
 XPT_FLAG_UNFUSED = 1
+XPT_FLAG_GRAPH = 2
 XPT_PHOTO_L1, XPT_PHOTO_L2, XPT_PHOTO_SSIM = 0, 1, 2
 
 _FP = C.POINTER(C.c_float)
@@ -68,6 +69,8 @@ SYMBOLS = {
                                  C.c_void_p, C.POINTER(XptLossOutputs), C.c_void_p]),
     "xpt_total_loss_host": (C.c_int, [C.c_void_p, C.POINTER(XptFrames), C.POINTER(PtrArray), C.POINTER(PtrArray),
                                       C.c_void_p, C.POINTER(XptLossOutputs), C.c_void_p]),
+    "xpt_profile_begin": (C.c_int, [C.c_void_p, C.c_int]),
+    "xpt_profile_end": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "xpt_last_launch_count": (C.c_int, [C.c_void_p]),
 }
 

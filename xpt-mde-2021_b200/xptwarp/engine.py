@@ -212,11 +212,11 @@ class Plan:
             C.byref(ptr_array([t.data_ptr() for t in d_disp])) if want_grad else None, self.stream()))
         return loss, d_disp
 
-    def total_loss(self, source, target, intrinsic, depth_ms, disp_ms, pose, want_grad=True, want_synth=False,
-                   want_mask=False, want_target_ms=False, want_source_grad=False, want_loss_batch=False,
-                   grad_scale=1.0, out: Optional[dict] = None):
-        """xpt_total_loss.  `out` may carry preallocated output tensors from a previous call
-        (same keys as the returned dict) so that steady-state steps allocate nothing."""
+    def bind_total_loss(self, source, target, intrinsic, depth_ms, disp_ms, pose, want_grad=True,
+                        want_synth=False, want_mask=False, want_target_ms=False, want_source_grad=False,
+                        want_loss_batch=False, grad_scale=1.0, out: Optional[dict] = None) -> "BoundTotalLoss":
+        """Marshal one xpt_total_loss call once; .run() then only crosses the C-ABI.  `out` may carry
+        preallocated output tensors (same keys as the result dict) to be reused."""
         source = _frame_view(source, "source", 2)
         target = _frame_view(target, "target", 1)
         intrinsic, pose = _dense(intrinsic, "intrinsic"), _dense(pose, "pose")
@@ -259,10 +259,40 @@ class Plan:
         f = self._frames(source, target, intrinsic)
         d = ptr_array([t.data_ptr() for t in depth_ms])
         dd = ptr_array([t.data_ptr() for t in disp_ms]) if have_disp else None
-        _cabi.check(self._lib.xpt_total_loss(self.handle, C.byref(f), C.byref(d),
-                                             C.byref(dd) if have_disp else None, pose.data_ptr(), C.byref(o),
-                                             self.stream()))
-        return r
+        keep = (source, target, intrinsic, pose, depth_ms, disp_ms)
+        return BoundTotalLoss(self, f, d, dd, pose.data_ptr(), o, r, keep)
+
+    def total_loss(self, *args, **kwargs):
+        """xpt_total_loss (see bind_total_loss for the arguments); returns the dict of outputs."""
+        return self.bind_total_loss(*args, **kwargs).run()
+
+    def profile_begin(self, max_records):
+        _cabi.check(self._lib.xpt_profile_begin(self.handle, int(max_records)))
+
+    def profile_end(self, capacity):
+        buf = (C.c_float * capacity)()
+        n = self._lib.xpt_profile_end(self.handle, buf, capacity)
+        if n < 0:
+            _cabi.check(n)
+        return [buf[i] for i in range(n)]
+
+
+class BoundTotalLoss:
+    """A fully marshalled xpt_total_loss call (ctypes structs prebuilt, tensors kept alive)."""
+    __slots__ = ("plan", "_f", "_d", "_dd", "_pose", "_o", "out", "_keep", "_fn", "_h")
+
+    def __init__(self, plan, f, d, dd, pose_ptr, o, out, keep):
+        self.plan, self._f, self._d, self._dd, self._pose, self._o = plan, f, d, dd, pose_ptr, o
+        self.out, self._keep = out, keep
+        self._fn, self._h = plan._lib.xpt_total_loss, plan.handle
+
+    def run(self, stream=None):
+        st = self.plan.stream() if stream is None else stream
+        rc = self._fn(self._h, C.byref(self._f), C.byref(self._d), C.byref(self._dd) if self._dd is not None else None,
+                      self._pose, C.byref(self._o), st)
+        if rc != 0:
+            _cabi.check(rc)
+        return self.out
 
 
 _PLANS: "collections.OrderedDict[tuple, Plan]" = collections.OrderedDict()
