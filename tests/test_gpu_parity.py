@@ -237,7 +237,7 @@ def test_full_size_properties(xw):
     assert relerr(ru["losses"].cpu().numpy(), r1["losses"].cpu().numpy()) < 1e-6
     assert relerr(ru["d_pose"].cpu().numpy(), r1["d_pose"].cpu().numpy()) < 1e-5
     for s in range(4):
-        assert relerr(ru["d_depth_ms"][s].cpu().numpy(), r1["d_depth_ms"][s].cpu().numpy()) < 1e-5
+        assert relerr(ru["d_depth_ms"][s].cpu().numpy(), r1["d_depth_ms"][s].cpu().numpy()) < 1e-4
     # (b) gradients are linear in the upstream gradient
     r3 = _run_total(plan, f, p, want_grad=True, grad_scale=3.0)
     assert relerr(r3["d_pose"].cpu().numpy(), 3.0 * r1["d_pose"].cpu().numpy()) < 1e-5

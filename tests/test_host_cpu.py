@@ -1,0 +1,164 @@
+"""CPU-side tests (no GPU): the C-ABI library loads and exports every symbol include/xptwarp.h
+declares, the ctypes structs match the header, DLPack unwrapping is zero-copy, the host logic
+mirrors the reference's factory/validation behaviour, and the product path refuses to run without
+a CUDA device (no fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "xptwarp.h")
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as g
+    g.build()
+    from xptwarp import _cabi
+    return _cabi
+
+
+def test_library_exports_every_declared_symbol(built):
+    text = open(HEADER).read()
+    declared = set(re.findall(r"XPT_API\s+[\w\s\*]+?\b(xpt_\w+)\s*\(", text))
+    assert len(declared) >= 16
+    assert declared == set(built.SYMBOLS), declared ^ set(built.SYMBOLS)
+    lib = built.lib()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.xpt_version() == int(re.search(r"#define XPT_VERSION (\d+)", text).group(1))
+    assert lib.xpt_status_string(-2) == b"XPT_BAD_SHAPE"
+
+
+def test_struct_layouts_match_the_header(built, tmp_path):
+    """sizeof/offsetof of the ctypes mirrors equal the C compiler's view of include/xptwarp.h."""
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "xptwarp.h"\nint main(){'
+                   'printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(xpt_config), offsetof(xpt_config, scale_weights),'
+                   'offsetof(xpt_config, flags), sizeof(xpt_frames), sizeof(xpt_loss_outputs),'
+                   'offsetof(xpt_loss_outputs, d_pose), offsetof(xpt_loss_outputs, grad_scale));return 0;}')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    vals = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    assert vals == [C.sizeof(built.XptConfig), built.XptConfig.scale_weights.offset, built.XptConfig.flags.offset,
+                    C.sizeof(built.XptFrames), C.sizeof(built.XptLossOutputs), built.XptLossOutputs.d_pose.offset,
+                    built.XptLossOutputs.grad_scale.offset]
+
+
+def test_no_cpu_fallback(built):
+    """Without a CUDA device the library refuses (XPT_NO_DEVICE); with CPU tensors the host raises."""
+    import xptwarp
+    if not torch.cuda.is_available():
+        with pytest.raises(built.XptError) as e:
+            xptwarp.get_plan(0, 2, 4, 32, 64, [1, 2, 4, 8])
+        assert e.value.status == -4
+    img = torch.zeros(1, 2, 16, 16, 3)
+    with pytest.raises(xptwarp.WrongInputException):
+        xptwarp.SynthesizeMultiScale()(img, torch.eye(3)[None], [torch.ones(1, 16, 16, 1)], torch.zeros(1, 2, 6))
+
+
+def test_create_rejects_bad_shapes(built):
+    lib = built.lib()
+    cfg = built.XptConfig()
+    cfg.batch, cfg.num_src, cfg.height, cfg.width, cfg.num_scales = 1, 4, 30, 64, 2
+    cfg.scales[0], cfg.scales[1] = 1, 4                   # 30 % 4 != 0
+    h = C.c_void_p()
+    assert lib.xpt_create(C.byref(h), C.byref(cfg)) == -2
+    assert b"does not divide" in lib.xpt_last_error()
+    cfg.num_src = 99
+    assert lib.xpt_create(C.byref(h), C.byref(cfg)) == -2
+    assert lib.xpt_create(None, C.byref(cfg)) == -1
+
+
+def test_dlpack_view_is_zero_copy():
+    from xptwarp.dlpack import kDLCPU, view_of
+    t = torch.arange(2 * 3 * 4, dtype=torch.float32).reshape(2, 3, 4)
+    v = view_of(t[:, 1:])                     # strided view with an offset
+    assert v.ptr == t[:, 1:].data_ptr() and v.shape == (2, 2, 4) and v.strides == (12, 4, 1)
+    assert v.device_type == kDLCPU and v.is_dense_from(1) and not v.is_dense_from(0)
+    with pytest.raises(TypeError):
+        view_of(torch.zeros(3, dtype=torch.float64))
+    with pytest.raises(TypeError):
+        view_of(object())
+
+
+def test_loss_factory_mirrors_reference_filtering():
+    import xptwarp
+    from xptwarp.loss_factory import check_loss_dependency
+    weights = {"L1": 0.5, "L1_R": 0.5, "SSIM": 0.5, "SSIM_R": 0.5, "smoothe": 1.0, "smoothe_R": 1.0,
+               "stereoL1": 0.01, "stereoSSIM": 0.01, "stereoPose": 1.0, "md2L1": 0.0}
+    tl = xptwarp.loss_factory({"image": 1, "intrinsic": 1}, weights, np.array([1, 1, 1, 1.0]), batch_size=4)
+    assert list(tl.loss_objects) == ["L1", "SSIM", "smoothe"] and tl.batch_size == 4
+    assert tl.loss_weights == {"L1": 0.5, "SSIM": 0.5, "smoothe": 1.0}
+    assert check_loss_dependency("stereoL1", {"image", "intrinsic", "image_R", "intrinsic_R", "stereo_T_LR"})
+    assert not check_loss_dependency("L1_R", {"image", "intrinsic"})
+    with pytest.raises(xptwarp.WrongInputException):
+        xptwarp.losses.PhotometricLossMultiScale("L3", None)
+    # a loss outside the hot path is constructible (like in the reference's pool) but refuses to run
+    tl2 = xptwarp.loss_factory({"image": 1, "intrinsic": 1}, {"md2L1": 1.0}, np.ones(4))
+    with pytest.raises(xptwarp.WrongInputException):
+        tl2.loss_objects["md2L1"](None, None, None)
+
+
+def test_infer_scales_and_shard_bounds():
+    from xptwarp.distributed import shard_bounds
+    from xptwarp.engine import WrongInputException, infer_scales
+    assert infer_scales(128, [torch.zeros(1, 128 // s, 4, 1) for s in (1, 2, 4, 8)]) == [1, 2, 4, 8]
+    with pytest.raises(WrongInputException):
+        infer_scales(128, [torch.zeros(1, 50, 4, 1)])
+    spans = [shard_bounds(64, r, 8) for r in range(8)]
+    assert spans[0] == (0, 8) and spans[-1] == (56, 64)
+    spans = [shard_bounds(10, r, 4) for r in range(4)]
+    assert [hi - lo for lo, hi in spans] == [3, 3, 2, 2] and spans[-1][1] == 10
+    with pytest.raises(ValueError):
+        shard_bounds(8, 4, 4)
+
+
+def _gloo_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "xpt-mde-2021_b200"))
+    from oracle import xpt_oracle as orc
+    from xptwarp.distributed import allreduce_gradient_buckets, allreduce_losses, shard_batch
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    feats, preds = orc.make_inputs(4, 16, 24, N=2, seed=77)
+    f, p = shard_batch(feats, preds, rank, world)
+    # per-rank losses normalised by the GLOBAL batch (the oracle stands in for the kernels on CPU)
+    total, by_type = orc.total_loss(p, f, orc.LOSS_RIGID_T1, orc.SCALE_WEIGHT_T1, global_batch=4)
+    vec = torch.stack([total, by_type["L1"], by_type["SSIM"], by_type["smoothe"]]).detach()
+    allreduce_losses(vec)
+    bucket = torch.full((1000,), float(rank + 1))
+    for w in allreduce_gradient_buckets([bucket]):
+        w.wait()
+    q.put((rank, vec.tolist(), float(bucket[0])))
+    dist.destroy_process_group()
+
+
+def test_sharded_losses_allreduce_to_the_global_batch_mean_gloo():
+    """world_size 2 over gloo: shard + all-reduce(sum) of per-rank losses == single-process loss."""
+    import torch.multiprocessing as mp
+    from oracle import xpt_oracle as orc
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    feats, preds = orc.make_inputs(4, 16, 24, N=2, seed=77)
+    total, by_type = orc.total_loss(preds, feats, orc.LOSS_RIGID_T1, orc.SCALE_WEIGHT_T1, global_batch=4)
+    want = [float(total), float(by_type["L1"]), float(by_type["SSIM"]), float(by_type["smoothe"])]
+    for rank, vec, b0 in res:
+        assert np.allclose(vec, want, rtol=1e-5), (rank, vec, want)
+        assert b0 == 3.0

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "xpt_kernels.cuh"
+#include "xpt_fused.cuh"
 
 using namespace xpt;
 
@@ -53,6 +54,7 @@ struct xpt_ctx {
   int S, B, N, H, W;
   int h[kMaxScales], w[kMaxScales], s[kMaxScales];
   int tiles_x[kMaxScales], tiles_y[kMaxScales], first_tile[kMaxScales + 1];
+  int ftiles_x[kMaxScales], ftiles_y[kMaxScales], ffirst_tile[kMaxScales + 1];   // 64x13 tiles (k_fused)
   int chunks[kMaxScales], first_chunk[kMaxScales + 1];       // 1024-pixel chunks (k_warp_bwd)
   int sm_chunks[kMaxScales], first_sm_chunk[kMaxScales + 1]; // 256-pixel chunks (k_smooth)
   int slots_per_b;
@@ -310,11 +312,25 @@ int launch_photo(xpt_ctx* ctx, const PhotoArgs& a, cudaStream_t st) {
     attr_set = true;
   }
   dim3 grid(a.tiles_per_b, ctx->B);
-  const bool prof = FUSED && ctx->prof_on > 0 && ctx->prof_count < ctx->prof_on;
-  if (prof) XPT_CUDA(cudaEventRecord((*ctx->prof_events)[2 * ctx->prof_count], st));
   k_photo<FUSED, GRAD><<<grid, kPhotoThreads, smem, st>>>(a);
-  if (prof) { XPT_CUDA(cudaEventRecord((*ctx->prof_events)[2 * ctx->prof_count + 1], st)); ++ctx->prof_count; }
   XPT_LAUNCH_CHECK(FUSED ? "k_photo<fused>" : "k_photo<tensor>");
+  return XPT_OK;
+}
+
+template <bool GRAD>
+int launch_fused(xpt_ctx* ctx, const FusedArgs& a, cudaStream_t st) {
+  static bool attr_set = false;
+  const size_t smem = FusedSmem<GRAD>::kBytes;
+  if (!attr_set) {
+    XPT_CUDA(cudaFuncSetAttribute(k_fused<GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid(a.tiles_per_b, ctx->B);
+  const bool prof = ctx->prof_on > 0 && ctx->prof_count < ctx->prof_on;
+  if (prof) XPT_CUDA(cudaEventRecord((*ctx->prof_events)[2 * ctx->prof_count], st));
+  k_fused<GRAD><<<grid, kFThreads, smem, st>>>(a);
+  if (prof) { XPT_CUDA(cudaEventRecord((*ctx->prof_events)[2 * ctx->prof_count + 1], st)); ++ctx->prof_count; }
+  XPT_LAUNCH_CHECK("k_fused");
   return XPT_OK;
 }
 
@@ -407,12 +423,14 @@ int xpt_create(xpt_ctx** out, const xpt_config* cfg) {
   ctx->cfg = *cfg;
   if (ctx->cfg.global_batch <= 0) ctx->cfg.global_batch = cfg->batch;
   ctx->S = cfg->num_scales; ctx->B = cfg->batch; ctx->N = cfg->num_src; ctx->H = cfg->height; ctx->W = cfg->width;
-  ctx->first_tile[0] = ctx->first_chunk[0] = ctx->first_sm_chunk[0] = 0;
+  ctx->first_tile[0] = ctx->first_chunk[0] = ctx->first_sm_chunk[0] = ctx->ffirst_tile[0] = 0;
   for (int l = 0; l < ctx->S; ++l) {
     ctx->s[l] = cfg->scales[l];
     ctx->h[l] = ctx->H / ctx->s[l]; ctx->w[l] = ctx->W / ctx->s[l];
     ctx->tiles_x[l] = cdiv(ctx->w[l], kTW); ctx->tiles_y[l] = cdiv(ctx->h[l], kTH);
     ctx->first_tile[l + 1] = ctx->first_tile[l] + ctx->tiles_x[l] * ctx->tiles_y[l];
+    ctx->ftiles_x[l] = cdiv(ctx->w[l], kFCW); ctx->ftiles_y[l] = cdiv(ctx->h[l], kFCH);
+    ctx->ffirst_tile[l + 1] = ctx->ffirst_tile[l] + ctx->ftiles_x[l] * ctx->ftiles_y[l];
     ctx->chunks[l] = cdiv((long long)ctx->h[l] * ctx->w[l], kWarpBwdChunk);
     ctx->first_chunk[l + 1] = ctx->first_chunk[l] + ctx->chunks[l];
     ctx->sm_chunks[l] = cdiv((long long)ctx->h[l] * ctx->w[l], 256);
@@ -420,6 +438,7 @@ int xpt_create(xpt_ctx** out, const xpt_config* cfg) {
   }
   ctx->slots_per_b = ctx->first_tile[ctx->S] + ctx->first_sm_chunk[ctx->S];
   if (ctx->first_chunk[ctx->S] > ctx->slots_per_b) ctx->slots_per_b = ctx->first_chunk[ctx->S];
+  if (ctx->ffirst_tile[ctx->S] > ctx->slots_per_b) ctx->slots_per_b = ctx->ffirst_tile[ctx->S];
 
   int rc = XPT_OK;
   auto A = [&](float** p, size_t n) { if (rc == XPT_OK) rc = dev_alloc(ctx, p, n); };
@@ -619,14 +638,35 @@ static int total_loss_impl(xpt_ctx* ctx, const xpt_frames* frames, const float* 
 
   if (!(c.flags & XPT_FLAG_UNFUSED)) {
     // ---- fused path: warp + L1 + SSIM + smoothness (+ all gradients) in one kernel
-    if (grad) XPT_TRY((launch_photo<true, true>(ctx, a, st)));
-    else XPT_TRY((launch_photo<true, false>(ctx, a, st)));
+    FusedArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.lt = lt;
+    for (int l = 0; l < ctx->S; ++l) {
+      fa.lt.lv[l].tiles_x = ctx->ftiles_x[l]; fa.lt.lv[l].tiles_y = ctx->ftiles_y[l];
+      fa.lt.lv[l].slot_base = ctx->ffirst_tile[l];
+      fa.first_tile[l] = ctx->ffirst_tile[l];
+      fa.depth[l] = a.depth[l]; fa.disp[l] = a.disp[l];
+      fa.norm_photo[l] = a.norm_photo[l]; fa.norm_sm_x[l] = a.norm_sm_x[l]; fa.norm_sm_y[l] = a.norm_sm_y[l];
+      fa.synth_out[l] = a.synth_out[l]; fa.mask_out[l] = a.mask_out[l];
+      fa.d_depth[l] = a.d_depth[l]; fa.d_disp[l] = a.d_disp[l];
+      fa.d_src[l] = a.d_src[l]; fa.d_src_bs[l] = a.d_src_bs[l]; fa.d_src_fs[l] = a.d_src_fs[l];
+    }
+    const int ftiles = ctx->ffirst_tile[ctx->S];
+    fa.first_tile[ctx->S] = ftiles;
+    fa.tiles_per_b = ftiles;
+    fa.B = ctx->B; fa.N = ctx->N; fa.geoK = ctx->geoK; fa.geoT = ctx->geoT;
+    fa.do_l1 = a.l1_kind != 0; fa.do_ssim = a.do_ssim; fa.do_smooth = a.do_smooth;
+    fa.grad_factor = a.grad_factor;
+    fa.gcoef_l1 = a.gcoef_l1; fa.gcoef_ssim = a.gcoef_ssim; fa.gcoef_smooth = a.gcoef_smooth;
+    fa.loss_part = ctx->loss_part; fa.slots_per_b = ctx->slots_per_b; fa.pose_part = ctx->pose_part;
+    if (grad) XPT_TRY((launch_fused<true>(ctx, fa, st)));
+    else XPT_TRY((launch_fused<false>(ctx, fa, st)));
     if (grad && out->d_pose) {
-      k_pose_epilogue<<<ctx->B * ctx->N, 128, 0, st>>>(ctx->pose_part, ctx->slots_per_b, tiles, pose, out->d_pose,
+      k_pose_epilogue<<<ctx->B * ctx->N, 128, 0, st>>>(ctx->pose_part, ctx->slots_per_b, ftiles, pose, out->d_pose,
                                                        ctx->N, 1.0f);
       XPT_LAUNCH_CHECK("k_pose_epilogue");
     }
-    XPT_TRY(launch_loss_epilogue(ctx, tiles, c.w_l1, c.w_ssim, c.w_smooth, out->losses, out->loss_batch, st));
+    XPT_TRY(launch_loss_epilogue(ctx, ftiles, c.w_l1, c.w_ssim, c.w_smooth, out->losses, out->loss_batch, st));
   } else {
     // ---- unfused path (flags bit 0): one kernel per reference stage, tensors through HBM
     float* synth[kMaxScales]; float* gsyn[kMaxScales];

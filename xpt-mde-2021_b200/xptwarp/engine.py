@@ -42,6 +42,13 @@ def _check_cuda_f32(t: torch.Tensor, name: str):
         raise WrongInputException(f"{name} must be float32, got {t.dtype}")
 
 
+def require_cuda_f32(**named):
+    """Entry-point guard: every tensor must already live on a CUDA device as float32."""
+    for name, t in named.items():
+        for i, x in enumerate(t if isinstance(t, (list, tuple)) else [t]):
+            _check_cuda_f32(x, name if not isinstance(t, (list, tuple)) else f"{name}[{i}]")
+
+
 def _dense(t: torch.Tensor, name: str) -> torch.Tensor:
     _check_cuda_f32(t, name)
     return t if t.is_contiguous() else t.contiguous()

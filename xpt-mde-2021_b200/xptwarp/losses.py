@@ -6,7 +6,7 @@ from __future__ import annotations
 import torch
 
 from . import _cabi
-from .engine import WrongInputException, as_torch, get_plan, infer_scales
+from .engine import WrongInputException, as_torch, get_plan, infer_scales, require_cuda_f32
 from .synthesize import SynthesizeMultiScale
 from .util_funcs import multi_scale_like_depth
 
@@ -111,6 +111,7 @@ class PhotometricLossMultiScale(PhotometricLoss):
     def __call__(self, features, predictions, augm_data):
         target_ms = [as_torch(t) for t in augm_data["target_ms" + self.key_suffix]]
         synth_ms = [as_torch(t) for t in augm_data["synth_target_ms" + self.key_suffix]]
+        require_cuda_f32(synth_target_ms=synth_ms, target_ms=target_ms)
         B, N, H, W, _ = synth_ms[0].shape
         scales = [H // s.shape[2] for s in synth_ms]
         plan = get_plan(synth_ms[0].device.index or 0, B, N, H, W, scales, _scale_weights_list(self.scale_weights))
@@ -127,6 +128,7 @@ class SmoothenessLossMultiScale(LossBase):
     def __call__(self, features, predictions, augm_data):
         disp_ms = [as_torch(t) for t in predictions["disp_ms" + self.key_suffix]]
         target_ms = [as_torch(t) for t in augm_data["target_ms" + self.key_suffix]]
+        require_cuda_f32(disp_ms=disp_ms, target_ms=target_ms)
         B, H, W, _ = target_ms[0].shape
         scales = [H // t.shape[1] for t in target_ms]
         plan = get_plan(target_ms[0].device.index or 0, B, 1, H, W, scales, _scale_weights_list(self.scale_weights))
@@ -186,6 +188,7 @@ class TotalLoss:
         intrinsic = as_torch(features["intrinsic"])
         depth_ms = [as_torch(d) for d in predictions["depth_ms"]]
         pose = as_torch(predictions["pose"])
+        require_cuda_f32(image5d=image5d, intrinsic=intrinsic, pose=pose, depth_ms=depth_ms)
         B, F, H, W, _ = image5d.shape
         w = {k: float(self.loss_weights[k]) for k in self.loss_objects}
         sw = _scale_weights_list(next(iter(self.loss_objects.values())).scale_weights)

@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import torch
 
-from .engine import WrongInputException, as_torch, get_plan, infer_scales
+from .engine import WrongInputException, as_torch, get_plan, infer_scales, require_cuda_f32
 
 
 class _SynthesizeFn(torch.autograd.Function):
@@ -54,6 +54,7 @@ class SynthesizeMultiScale:
         pred_depth_ms = [as_torch(d) for d in pred_depth_ms]
         if source_image.dim() != 5 or source_image.shape[-1] != 3:
             raise WrongInputException(f"source_image must be [batch, numsrc, height, width, 3], got {tuple(source_image.shape)}")
+        require_cuda_f32(source_image=source_image, intrinsic=intrinsic, pred_pose=pred_pose, pred_depth_ms=pred_depth_ms)
         B, N, H, W, _ = source_image.shape
         if tuple(pred_pose.shape) != (B, N, 6):
             raise WrongInputException(f"pred_pose must be [{B}, {N}, 6], got {tuple(pred_pose.shape)}")

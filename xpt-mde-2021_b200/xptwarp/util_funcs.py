@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import torch
 
-from .engine import as_torch, get_plan, infer_scales
+from .engine import as_torch, get_plan, require_cuda_f32, infer_scales
 
 
 def multi_scale_like_depth(image, depth_ms):
@@ -11,6 +11,7 @@ def multi_scale_like_depth(image, depth_ms):
     half-pixel centres) sized like each depth map.  image [B,H,W,3] -> list of [B,H_s,W_s,3]."""
     image = as_torch(image)
     depth_ms = [as_torch(d) for d in depth_ms]
+    require_cuda_f32(image=image)
     B, H, W, _ = image.shape
     plan = get_plan(image.device.index or 0, B, 1, H, W, infer_scales(H, depth_ms))
     # the pyramid kernel wants a source tensor too: pass the target as a 1-frame source view
