@@ -3,15 +3,17 @@
 // -> bilinear + projection adjoint, one launch for all scales, all sources, forward AND backward.
 //
 // Design (DESIGN.md "k_fused"):
-//   * one CTA = one 64x13 centre tile of (level, snippet); all N sources are looped inside so the
-//     target tile and its window statistics are loaded / computed once;
-//   * the 3x3 SSIM windows and their adjoint are evaluated on 4-pixel strips per thread from
-//     16-byte aligned shared-memory rows (LDS.128 + LDS.64), vertical sums first, so each input is
-//     loaded once per strip instead of nine times per pixel;
+//   * one CTA (512 threads, 2 CTAs/SM = 32 warps/SM) = one 64x13 centre tile of (level, snippet);
+//     all N sources are looped inside so the target tile and its statistics are loaded once;
+//   * camera geometry (K_s, inv K_s, [R|t]) sits in the constant bank: the compiler keeps it in
+//     UNIFORM registers (LDCU -> FFMA R, R, UR, R), so the projection costs no vector registers;
+//   * the 3x3 SSIM windows and their adjoint are evaluated on 2-pixel strips per thread from 8-byte
+//     aligned shared-memory rows (LDS.64), vertical sums first, with Blackwell's packed FP32 pipe
+//     (FFMA2 / FADD2 / FMUL2 on float2) doing both pixels of the strip per instruction;
 //   * the bilinear Jacobian (dS/du, dS/dv per channel) and (u, v, 1/den) of the centre samples are
 //     cached in shared memory by the forward phase, so the backward phase gathers nothing again;
-//   * region widths are multiples of 4 floats and the centre width is 64 so that 384/832/1280-wide
-//     images (and every 2^k-scaled level down to 64) tile without waste.
+//   * region pitch is 68 floats and the centre width is 64 so that 384/832/1280-wide images (and
+//     every 2^k-scaled level down to 64) tile without waste.
 #pragma once
 #include "xpt_kernels.cuh"
 
@@ -21,25 +23,30 @@ constexpr int kFCW = 64, kFCH = 13;            // centre tile
 constexpr int kFSW = 66, kFSH = 15;            // statistics region (halo 1)
 constexpr int kFRW = 68, kFRH = 17;            // warped / target region (halo 2)
 constexpr int kFP = 68;                        // row pitch (floats) of region and statistics arrays
-constexpr int kFStrips = 17;                   // 4-pixel strips per statistics row
-constexpr int kFThreads = 256;
+constexpr int kFSStrips = 33;                  // 2-pixel strips per statistics row
+constexpr int kFGStrips = 32;                  // 2-pixel strips per centre row
+constexpr int kFThreads = 512;
 constexpr int kFRegion = kFRH * kFP;           // 1156 floats per channel
 constexpr int kFStats = kFSH * kFP;            // 1020
 constexpr int kFCP = 64;                       // pitch of the centre arrays
 constexpr int kFCentre = kFCH * kFCP;          // 832
-constexpr int kFYIters = (kFRegion + kFThreads - 1) / kFThreads;   // 5
+constexpr int kFYIters = (kFRegion + kFThreads - 1) / kFThreads;   // 3
+
+// camera geometry in the constant bank: [Bc][S][18] (K_s, inv K_s) then [Bc][N][12] ([R|t])
+constexpr int kGeoConstFloats = 15360;         // 60 KB
+__constant__ float c_geo[kGeoConstFloats];
 
 template <bool GRAD>
 struct FusedSmem {
   // offsets in floats
   static constexpr int sy = 0;                                  // [3][17][68] warped tile
-  static constexpr int sx = sy + 3 * kFRegion + 8;              // [3][17][68] target tile (+8: strip over-read)
-  static constexpr int sD = sx + 3 * kFRegion + 8;              // [17][68] depth
-  static constexpr int red = sD + kFRegion + 4;                 // 128 floats of reduction scratch
-  static constexpr int sA = red + 128;                          // GRAD: [3][15][68] x3
-  static constexpr int sB = sA + (GRAD ? 3 * kFStats + 8 : 0);
-  static constexpr int sC = sB + (GRAD ? 3 * kFStats + 8 : 0);
-  static constexpr int sGU = sC + (GRAD ? 3 * kFStats + 8 : 0); // GRAD: [3][13][64] dS_c/du
+  static constexpr int sx = sy + 3 * kFRegion + 4;              // [3][17][68] target tile
+  static constexpr int sD = sx + 3 * kFRegion + 4;              // [17][68] depth
+  static constexpr int red = sD + kFRegion + 4;                 // 256 floats of reduction scratch
+  static constexpr int sA = red + 256;                          // GRAD: [3][15][68] x3
+  static constexpr int sB = sA + (GRAD ? 3 * kFStats + 4 : 0);
+  static constexpr int sC = sB + (GRAD ? 3 * kFStats + 4 : 0);
+  static constexpr int sGU = sC + (GRAD ? 3 * kFStats + 4 : 0); // GRAD: [3][13][64] dS_c/du
   static constexpr int sGV = sGU + (GRAD ? 3 * kFCentre : 0);
   static constexpr int sU = sGV + (GRAD ? 3 * kFCentre : 0);    // GRAD: [13][64] u, v, 1/den
   static constexpr int sV = sU + (GRAD ? kFCentre : 0);
@@ -48,27 +55,31 @@ struct FusedSmem {
   static constexpr size_t kBytes = sizeof(float) * kFloats;
 };
 
-__device__ __forceinline__ void lds6(const float* p, float v[6]) {
-  const float4 a = *reinterpret_cast<const float4*>(p);
-  const float2 b = *reinterpret_cast<const float2*>(p + 4);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y;
-}
+// ---- packed FP32 (Blackwell FFMA2 / FADD2 / FMUL2) -----------------------------------------------
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 f2s(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 f2neg(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 lds2(const float* p) { return *reinterpret_cast<const float2*>(p); }
 
-__device__ __forceinline__ void lds4u(const float* p, float v[4]) {   // 8-byte aligned
-  const float2 a = *reinterpret_cast<const float2*>(p);
-  const float2 b = *reinterpret_cast<const float2*>(p + 2);
-  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+// 1/x: MUFU.RCP + one Newton step (<= 1 ulp); used where the reference divides but a 1-ulp
+// difference cannot move a mask (SSIM ratio, cached 1/den of the backward)
+__device__ __forceinline__ float rcp_nr(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return fmaf(fmaf(-x, r, 1.f), r, r);
 }
 
 __device__ __forceinline__ float box_inv(int cnt) {   // 1 / #in-image taps of a 3x3 window
   return cnt == 9 ? (1.f / 9.f) : (cnt == 6 ? (1.f / 6.f) : (cnt == 4 ? 0.25f : 1.f / (float)cnt));
 }
 
-// sum of 12 per-thread accumulators over a warp in 16 shuffles: at each butterfly step a lane keeps
-// half of the values and hands the other half to its partner.  Result k lands in lane (k*2) % 32 ... we
-// only need the totals somewhere deterministic: afterwards lane L holds total[index_of(L)] in v[0].
+// sum of 16 per-thread accumulators over a warp in 16 shuffles: at each butterfly step a lane keeps
+// half of the values and hands the other half to its partner.  Afterwards lane L holds the total of
+// value index ((L>>4)&1)*8 + ((L>>3)&1)*4 + ((L>>2)&1)*2 + ((L>>1)&1).
 __device__ __forceinline__ float warp_reduce16(float v[16], int lane) {
-  // step 1: exchange 8 values with lane^16
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const bool hi = lane & 16;
@@ -97,16 +108,16 @@ __device__ __forceinline__ float warp_reduce16(float v[16], int lane) {
     v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
   }
   v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-  // lane L now holds the total of value index ((L>>4)&1)*8 + ((L>>3)&1)*4 + ((L>>2)&1)*2 + ((L>>1)&1)
   return v[0];
 }
 
 struct FusedArgs {
   LevelTable lt;                       // Level.tiles_x/y/slot_base describe the 64x13 tiling
   int B, N;
+  int b_off;                           // first snippet of this launch (constant-bank chunking)
+  int geo_t_off;                       // float offset of the [R|t] block inside c_geo
   int tiles_per_b;
   int first_tile[kMaxScales + 1];
-  const float* geoK; const float* geoT;
   const float* depth[kMaxScales];
   const float* disp[kMaxScales];
   int do_l1, do_ssim, do_smooth;
@@ -126,7 +137,7 @@ struct FusedArgs {
 };
 
 template <bool GRAD>
-__global__ void __launch_bounds__(kFThreads, 2) k_fused(FusedArgs a) {
+__global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ FusedArgs a) {
   using SM = FusedSmem<GRAD>;
   extern __shared__ __align__(16) float smem[];
   float* const sy = smem + SM::sy;
@@ -144,7 +155,8 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(FusedArgs a) {
 
   // ---- which tile -------------------------------------------------------------
   int t = blockIdx.x;
-  const int b = blockIdx.y;
+  const int bl = blockIdx.y;               // snippet inside this launch's constant-bank chunk
+  const int b = a.b_off + bl;
   int l = 0;
   while (l + 1 < a.lt.S && t >= a.first_tile[l + 1]) ++l;
   t -= a.first_tile[l];
@@ -153,13 +165,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(FusedArgs a) {
   const int ty0 = (t / L.tiles_x) * kFCH, tx0 = (t % L.tiles_x) * kFCW;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int slot = L.slot_base + t;
-
-  float K[9], Ki[9];
-  {
-    const float* gk = a.geoK + ((size_t)b * a.lt.S + l) * kGeoK;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) { K[k] = __ldg(gk + k); Ki[k] = __ldg(gk + 9 + k); }
-  }
+  const float* const gk = c_geo + (bl * a.lt.S + l) * kGeoK;     // K_s (9), inv K_s (9): uniform registers
 
   // ---- target tile and depth tile (halo 2), zero outside the image --------------------
   {
@@ -167,10 +173,10 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(FusedArgs a) {
     const float* dep = a.depth[l] + (long long)b * P;
 #pragma unroll
     for (int it = 0; it < kFYIters; ++it) {
-      int i = tid + it * kFThreads;
+      const int i = tid + it * kFThreads;
       if (i < kFRegion) {
-        int ry = i / kFP, rx = i - ry * kFP;
-        int gy = ty0 - 2 + ry, gx = tx0 - 2 + rx;
+        const int ry = i / kFP, rx = i - ry * kFP;
+        const int gy = ty0 - 2 + ry, gx = tx0 - 2 + rx;
         float v0 = 0.f, v1 = 0.f, v2 = 0.f, d = 0.f;
         if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
           const float* p = tgt + ((long long)gy * W + gx) * 3;
@@ -185,11 +191,11 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(FusedArgs a) {
   __syncthreads();
 
   // ---- strip coordinates ----------------------------------------------------------------
-  // S phase: statistics row qy (0..14), columns q0..q0+3
-  const int qy = tid / kFStrips, q0 = (tid - qy * kFStrips) * 4;
-  const bool s_active = tid < kFSH * kFStrips;
-  // G phase: centre row cyy (0..12), columns c0..c0+3
-  const int cyy = tid >> 4, c0 = (tid & 15) * 4;
+  // S phase: statistics row qy (0..14), columns q0, q0+1
+  const int qy = tid / kFSStrips, q0 = (tid - qy * kFSStrips) * 2;
+  const bool s_active = tid < kFSH * kFSStrips;
+  // G phase: centre row cyy (0..12), columns c0, c0+1
+  const int cyy = tid >> 5, c0 = (tid & 31) * 2;
   const bool g_active = cyy < kFCH;
 
   float lsum_l1 = 0.f, lsum_ssim = 0.f, lsum_sm = 0.f;
@@ -202,7 +208,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(FusedArgs a) {
     const float k3 = a.grad_factor;
     const int gy = ty0 + cyy;
 #pragma unroll
-    for (int o = 0; o < 4; ++o) {
+    for (int o = 0; o < 2; ++o) {
       const int gx = tx0 + c0 + o;
       if (gy < H && gx < W) {
         const int ri = (cyy + 2) * kFP + (c0 + o + 2);
@@ -212,8 +218,8 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(FusedArgs a) {
           float e = 0.f;
 #pragma unroll
           for (int c = 0; c < 3; ++c) e += fabsf((sx[c * kFRegion + ri] - sx[c * kFRegion + ri + 1]) * k3);
-          float w = expf(-(e / 3.f));
-          float sd = (d - __ldg(dsp + (long long)gy * W + gx + 1)) * w;
+          const float w = expf(-(e / 3.f));
+          const float sd = (d - __ldg(dsp + (long long)gy * W + gx + 1)) * w;
           lsum_sm += fabsf(sd) * nx;
           gd += gcx * sgnf(sd) * w;
         }
@@ -221,8 +227,8 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(FusedArgs a) {
           float e = 0.f;
 #pragma unroll
           for (int c = 0; c < 3; ++c) e += fabsf((sx[c * kFRegion + ri] - sx[c * kFRegion + ri + kFP]) * k3);
-          float w = expf(-(e / 3.f));
-          float sd = (d - __ldg(dsp + (long long)(gy + 1) * W + gx)) * w;
+          const float w = expf(-(e / 3.f));
+          const float sd = (d - __ldg(dsp + (long long)(gy + 1) * W + gx)) * w;
           lsum_sm += fabsf(sd) * ny;
           gd += gcy * sgnf(sd) * w;
         }
@@ -231,16 +237,16 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(FusedArgs a) {
             float e = 0.f;
 #pragma unroll
             for (int c = 0; c < 3; ++c) e += fabsf((sx[c * kFRegion + ri - 1] - sx[c * kFRegion + ri]) * k3);
-            float w = expf(-(e / 3.f));
-            float sd = (__ldg(dsp + (long long)gy * W + gx - 1) - d) * w;
+            const float w = expf(-(e / 3.f));
+            const float sd = (__ldg(dsp + (long long)gy * W + gx - 1) - d) * w;
             gd -= gcx * sgnf(sd) * w;
           }
           if (gy >= 1) {
             float e = 0.f;
 #pragma unroll
             for (int c = 0; c < 3; ++c) e += fabsf((sx[c * kFRegion + ri - kFP] - sx[c * kFRegion + ri]) * k3);
-            float w = expf(-(e / 3.f));
-            float sd = (__ldg(dsp + (long long)(gy - 1) * W + gx) - d) * w;
+            const float w = expf(-(e / 3.f));
+            const float sd = (__ldg(dsp + (long long)(gy - 1) * W + gx) - d) * w;
             gd -= gcy * sgnf(sd) * w;
           }
           if (a.d_disp[l]) a.d_disp[l][(long long)b * P + gy * W + gx] = gd;
@@ -250,55 +256,50 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(FusedArgs a) {
   }
 
   // ---- per-strip invariants of the S phase ------------------------------------------------------
-  float inv_cnt[4];
-  bool s_in[4], s_centre[4];
+  float2 inv_cnt, s_in, s_centre;          // per pixel of the strip: 1/#taps, in-image (0/1), counted in the loss (0/1)
   {
     const int gy = ty0 - 1 + qy;
     const bool row_in = s_active && gy >= 0 && gy < H;
     const int cy = min(gy + 1, H - 1) - max(gy - 1, 0) + 1;
+    float iv[2], in[2], ce[2];
 #pragma unroll
-    for (int o = 0; o < 4; ++o) {
+    for (int o = 0; o < 2; ++o) {
       const int q = q0 + o, gx = tx0 - 1 + q;
-      s_in[o] = row_in && q < kFSW && gx >= 0 && gx < W;
+      const bool inb = row_in && q < kFSW && gx >= 0 && gx < W;
       const int cx = min(gx + 1, W - 1) - max(gx - 1, 0) + 1;
-      inv_cnt[o] = s_in[o] ? box_inv(cy * cx) : 0.f;
-      s_centre[o] = s_in[o] && qy >= 1 && qy <= kFCH && q >= 1 && q <= kFCW;
+      iv[o] = inb ? box_inv(cy * cx) : 0.f;
+      in[o] = inb ? 1.f : 0.f;
+      ce[o] = (inb && qy >= 1 && qy <= kFCH && q >= 1 && q <= kFCW) ? 1.f : 0.f;
     }
+    inv_cnt = f2(iv[0], iv[1]); s_in = f2(in[0], in[1]); s_centre = f2(ce[0], ce[1]);
   }
   // window statistics of the target (x) for this strip: evaluated once, kept across the N sources
-  float MUX[3][4], SGX[3][4];
+  // (premixed with the SSIM constants: mux, 2*mux, mux^2 + c1, sigma_x + c2)
+  float2 MUX[3], MUX2C[3], SGXC[3];
   if (a.do_ssim && s_active) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float* px = sx + c * kFRegion + qy * kFP + q0;
-      float X0[6], X1[6], X2[6], v1[6], v2[6];
-      lds6(px, X0); lds6(px + kFP, X1); lds6(px + 2 * kFP, X2);
-#pragma unroll
-      for (int j = 0; j < 6; ++j) {
-        v1[j] = X0[j] + X1[j] + X2[j];
-        v2[j] = fmaf(X2[j], X2[j], fmaf(X1[j], X1[j], X0[j] * X0[j]));
-      }
-#pragma unroll
-      for (int o = 0; o < 4; ++o) {
-        float mu = (v1[o] + v1[o + 1] + v1[o + 2]) * inv_cnt[o];
-        MUX[c][o] = mu;
-        SGX[c][o] = (v2[o] + v2[o + 1] + v2[o + 2]) * inv_cnt[o] - mu * mu;
-      }
+      const float2 a0 = lds2(px), b0 = lds2(px + 2), a1 = lds2(px + kFP), b1 = lds2(px + kFP + 2);
+      const float2 a2 = lds2(px + 2 * kFP), b2 = lds2(px + 2 * kFP + 2);
+      const float2 v1a = f2add(f2add(a0, a1), a2), v1b = f2add(f2add(b0, b1), b2);
+      const float2 v2a = f2fma(a2, a2, f2fma(a1, a1, f2mul(a0, a0))), v2b = f2fma(b2, b2, f2fma(b1, b1, f2mul(b0, b0)));
+      const float2 s1 = f2((v1a.x + v1a.y) + v1b.x, (v1a.y + v1b.x) + v1b.y);
+      const float2 s2 = f2((v2a.x + v2a.y) + v2b.x, (v2a.y + v2b.x) + v2b.y);
+      const float2 mu = f2mul(s1, inv_cnt);
+      const float2 mu2 = f2mul(mu, mu);
+      MUX[c] = mu;
+      MUX2C[c] = f2add(mu2, f2s(kC1));
+      SGXC[c] = f2add(f2fma(s2, inv_cnt, f2neg(mu2)), f2s(kC2));
     }
   }
 
-  // ---- per-strip invariants of the G phase ------------------------------------------------------
-  float gD[4] = {0.f, 0.f, 0.f, 0.f};
+  float gD[2] = {0.f, 0.f};
   const float cl1 = a.gcoef_l1 * a.norm_photo[l];
   const float hss = -0.5f * a.gcoef_ssim * a.norm_photo[l];     // dTotal/d ssim at a contributing pixel
 
   for (int n = 0; n < a.N; ++n) {
-    float T[12];
-    {
-      const float* gt = a.geoT + ((size_t)b * a.N + n) * kGeoT;
-#pragma unroll
-      for (int k = 0; k < 12; ++k) T[k] = __ldg(gt + k);
-    }
+    const float* const gt = c_geo + a.geo_t_off + (bl * a.N + n) * kGeoT;   // [R|t]: uniform registers
     const float* img = L.src + b * L.src_bs + n * L.src_fs;
 
     // ---- phase Y: inverse warp of the region into shared memory ---------------------------------
@@ -317,8 +318,8 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(FusedArgs a) {
         if (inimg) {
           const float D = sD[i];
           float r0, r1, r2;
-          ray_of_pixel(Ki, (float)gx, (float)gy, r0, r1, r2);
-          const Proj pr = project(K, T, r0, r1, r2, D);
+          ray_of_pixel(gk + 9, (float)gx, (float)gy, r0, r1, r2);
+          const Proj pr = project(gk, gt, r0, r1, r2, D);
           const Taps tp = make_taps(pr.u, pr.v, D, W, H);
           valid = tp.valid;
           if (valid) {
@@ -326,14 +327,15 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(FusedArgs a) {
             gather_taps(img, W, tp, I0, I1, I2, I3);
             const float w0 = tp.w_uf * tp.w_vf, w1 = tp.w_uf * tp.w_vc, w2 = tp.w_uc * tp.w_vf, w3 = tp.w_uc * tp.w_vc;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              yv[c] = ((I0[c] * w0 + I1[c] * w1) + I2[c] * w2) + I3[c] * w3;
-              if (GRAD) {
+            for (int c = 0; c < 3; ++c) yv[c] = ((I0[c] * w0 + I1[c] * w1) + I2[c] * w2) + I3[c] * w3;
+            if (GRAD && centre) {
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
                 gu[c] = tp.w_vf * (I2[c] - I0[c]) + tp.w_vc * (I3[c] - I1[c]);
                 gv[c] = tp.w_uf * (I1[c] - I0[c]) + tp.w_uc * (I3[c] - I2[c]);
               }
+              su = pr.u; sv = pr.v; si = rcp_nr(pr.den);
             }
-            su = pr.u; sv = pr.v; si = 1.f / pr.den;
           }
         }
         sy[i] = yv[0]; sy[kFRegion + i] = yv[1]; sy[2 * kFRegion + i] = yv[2];
@@ -354,68 +356,74 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(FusedArgs a) {
     }
     __syncthreads();
 
-    // ---- phase S: L1 + SSIM (and the SSIM adjoint coefficients) on a 4-pixel strip ----------------
+    // ---- phase S: L1 + SSIM (and the SSIM adjoint coefficients) on a 2-pixel strip ----------------
     if (s_active) {
-      bool masked[4];
+      // the strip's pixels sit at region (qy+1, q0+1) and (qy+1, q0+2)
+      const int mid = (qy + 1) * kFP + q0;
+      float2 live, cnt_w;       // live: in-image and not black; cnt_w: counted in the loss and not black
       {
-        // mean_c(synth) == 0 (loss_util.py:15-16): the pixel itself sits at region (qy+1, q0+o+1)
-        float m0[6], m1[6], m2[6];
-        lds6(sy + (qy + 1) * kFP + q0, m0);
-        lds6(sy + kFRegion + (qy + 1) * kFP + q0, m1);
-        lds6(sy + 2 * kFRegion + (qy + 1) * kFP + q0, m2);
-#pragma unroll
-        for (int o = 0; o < 4; ++o) masked[o] = ((m0[o + 1] + m1[o + 1]) + m2[o + 1]) == 0.f;
+        // mean_c(synth) == 0 (loss_util.py:15-16)
+        const float2 m0a = lds2(sy + mid), m0b = lds2(sy + mid + 2);
+        const float2 m1a = lds2(sy + kFRegion + mid), m1b = lds2(sy + kFRegion + mid + 2);
+        const float2 m2a = lds2(sy + 2 * kFRegion + mid), m2b = lds2(sy + 2 * kFRegion + mid + 2);
+        const float nb0 = (((m0a.y + m1a.y) + m2a.y) == 0.f) ? 0.f : 1.f;
+        const float nb1 = (((m0b.x + m1b.x) + m2b.x) == 0.f) ? 0.f : 1.f;
+        live = f2(s_in.x * nb0, s_in.y * nb1);
+        cnt_w = f2(s_centre.x * nb0, s_centre.y * nb1);
       }
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const float* py = sy + c * kFRegion + qy * kFP + q0;
         const float* px = sx + c * kFRegion + qy * kFP + q0;
-        float Y0[6], Y1[6], Y2[6], X0[6], X1[6], X2[6];
-        lds6(py, Y0); lds6(py + kFP, Y1); lds6(py + 2 * kFP, Y2);
-        lds6(px, X0); lds6(px + kFP, X1); lds6(px + 2 * kFP, X2);
+        const float2 ya0 = lds2(py), yb0 = lds2(py + 2), ya1 = lds2(py + kFP), yb1 = lds2(py + kFP + 2);
+        const float2 ya2 = lds2(py + 2 * kFP), yb2 = lds2(py + 2 * kFP + 2);
+        const float2 xa0 = lds2(px), xb0 = lds2(px + 2), xa1 = lds2(px + kFP), xb1 = lds2(px + kFP + 2);
+        const float2 xa2 = lds2(px + 2 * kFP), xb2 = lds2(px + 2 * kFP + 2);
         if (a.do_l1) {
-#pragma unroll
-          for (int o = 0; o < 4; ++o)
-            if (s_centre[o] && !masked[o]) lsum_l1 += fabsf(Y1[o + 1] - X1[o + 1]);
+          lsum_l1 = fmaf(cnt_w.x, fabsf(ya1.y - xa1.y), lsum_l1);
+          lsum_l1 = fmaf(cnt_w.y, fabsf(yb1.x - xb1.x), lsum_l1);
         }
         if (a.do_ssim) {
-          float v1[6], v2[6], v3[6];
-#pragma unroll
-          for (int j = 0; j < 6; ++j) {
-            v1[j] = Y0[j] + Y1[j] + Y2[j];
-            v2[j] = fmaf(Y2[j], Y2[j], fmaf(Y1[j], Y1[j], Y0[j] * Y0[j]));
-            v3[j] = fmaf(X2[j], Y2[j], fmaf(X1[j], Y1[j], X0[j] * Y0[j]));
-          }
-          float Ao[4], Bo[4], Co[4];
-#pragma unroll
-          for (int o = 0; o < 4; ++o) {
-            const float inv = inv_cnt[o];
-            const float mux = MUX[c][o], sgx = SGX[c][o];
-            const float muy = (v1[o] + v1[o + 1] + v1[o + 2]) * inv;
-            const float sgy = (v2[o] + v2[o + 1] + v2[o + 2]) * inv - muy * muy;
-            const float sgxy = (v3[o] + v3[o + 1] + v3[o + 2]) * inv - mux * muy;
-            const float a1 = 2.f * mux * muy + kC1, a2 = 2.f * sgxy + kC2;
-            const float b1 = mux * mux + muy * muy + kC1, b2 = sgx + sgy + kC2;
-            const float r12 = 1.f / (b1 * b2);
-            const float ssim = (a1 * a2) * r12;
-            const float lv = (1.f - ssim) * 0.5f;
-            const bool live = s_in[o] && !masked[o];
-            if (s_centre[o] && !masked[o]) lsum_ssim += fminf(fmaxf(lv, 0.f), 1.f);
-            float A = 0.f, Bq = 0.f, Cq = 0.f;
-            if (GRAD && live && lv >= 0.f && lv <= 1.f) {        // clip_by_value passes the gradient inside [0,1]
-              const float rb1 = r12 * b2, rb2 = r12 * b1;        // 1/b1, 1/b2
-              const float hi = hss * inv;
-              A = hi * ((2.f * mux * (a2 - a1)) * r12 - ssim * (2.f * muy) * (rb1 - rb2));
-              Bq = hi * (-ssim * rb2);
-              Cq = hi * (2.f * a1 * r12);
-            }
-            Ao[o] = A; Bo[o] = Bq; Co[o] = Cq;
-          }
+          const float2 v1a = f2add(f2add(ya0, ya1), ya2), v1b = f2add(f2add(yb0, yb1), yb2);
+          const float2 v2a = f2fma(ya2, ya2, f2fma(ya1, ya1, f2mul(ya0, ya0)));
+          const float2 v2b = f2fma(yb2, yb2, f2fma(yb1, yb1, f2mul(yb0, yb0)));
+          const float2 v3a = f2fma(xa2, ya2, f2fma(xa1, ya1, f2mul(xa0, ya0)));
+          const float2 v3b = f2fma(xb2, yb2, f2fma(xb1, yb1, f2mul(xb0, yb0)));
+          const float2 s1 = f2((v1a.x + v1a.y) + v1b.x, (v1a.y + v1b.x) + v1b.y);
+          const float2 s2 = f2((v2a.x + v2a.y) + v2b.x, (v2a.y + v2b.x) + v2b.y);
+          const float2 s3 = f2((v3a.x + v3a.y) + v3b.x, (v3a.y + v3b.x) + v3b.y);
+          const float2 mux = MUX[c];
+          const float2 muy = f2mul(s1, inv_cnt);
+          const float2 muy2 = f2mul(muy, muy);
+          const float2 mxy = f2mul(mux, muy);
+          const float2 sgy = f2fma(s2, inv_cnt, f2neg(muy2));
+          const float2 sgxy = f2fma(s3, inv_cnt, f2neg(mxy));
+          const float2 a1 = f2fma(f2s(2.f), mxy, f2s(kC1));
+          const float2 a2 = f2fma(f2s(2.f), sgxy, f2s(kC2));
+          const float2 b1 = f2add(MUX2C[c], muy2);
+          const float2 b2 = f2add(SGXC[c], sgy);
+          const float2 den = f2mul(b1, b2);
+          const float2 r12 = f2(rcp_nr(den.x), rcp_nr(den.y));
+          const float2 ssim = f2mul(f2mul(a1, a2), r12);
+          const float2 lv = f2fma(f2s(-0.5f), ssim, f2s(0.5f));
+          lsum_ssim = fmaf(cnt_w.x, fminf(fmaxf(lv.x, 0.f), 1.f), lsum_ssim);
+          lsum_ssim = fmaf(cnt_w.y, fminf(fmaxf(lv.y, 0.f), 1.f), lsum_ssim);
           if (GRAD) {
+            // clip_by_value passes the gradient inside [0,1]; h = dTotal/d ssim / #taps, 0 where dead
+            const float2 pass = f2((lv.x >= 0.f && lv.x <= 1.f) ? live.x : 0.f, (lv.y >= 0.f && lv.y <= 1.f) ? live.y : 0.f);
+            const float2 hi = f2mul(f2mul(pass, inv_cnt), f2s(hss));
+            const float2 rb1 = f2mul(r12, b2), rb2 = f2mul(r12, b1);        // 1/b1, 1/b2
+            const float2 hr = f2mul(hi, r12);
+            // A = hi * ( 2 mux (a2 - a1) r12 - ssim * 2 muy (1/b1 - 1/b2) )
+            const float2 t1 = f2mul(f2add(mux, mux), f2add(a2, f2neg(a1)));
+            const float2 t2 = f2mul(f2mul(ssim, f2add(muy, muy)), f2add(rb1, f2neg(rb2)));
+            const float2 Av = f2fma(hr, t1, f2neg(f2mul(hi, t2)));
+            const float2 Bv = f2neg(f2mul(f2mul(hi, ssim), rb2));
+            const float2 Cv = f2mul(hr, f2add(a1, a1));
             const int so = c * kFStats + qy * kFP + q0;
-            *reinterpret_cast<float4*>(sA + so) = make_float4(Ao[0], Ao[1], Ao[2], Ao[3]);
-            *reinterpret_cast<float4*>(sB + so) = make_float4(Bo[0], Bo[1], Bo[2], Bo[3]);
-            *reinterpret_cast<float4*>(sC + so) = make_float4(Co[0], Co[1], Co[2], Co[3]);
+            *reinterpret_cast<float2*>(sA + so) = Av;
+            *reinterpret_cast<float2*>(sB + so) = Bv;
+            *reinterpret_cast<float2*>(sC + so) = Cv;
           }
         }
       }
@@ -430,97 +438,81 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(FusedArgs a) {
       if (g_active) {
         const int gy = ty0 + cyy;
         const int rrow = (cyy + 2) * kFP + c0 + 2;      // centre pixel in region coordinates
-        float yv[3][4], xv[3][4], g[3][4];
-        bool masked[4];
+        float2 yv[3], xv[3], g[3];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) { lds4u(sy + c * kFRegion + rrow, yv[c]); lds4u(sx + c * kFRegion + rrow, xv[c]); }
-#pragma unroll
-        for (int o = 0; o < 4; ++o) masked[o] = ((yv[0][o] + yv[1][o]) + yv[2][o]) == 0.f;
+        for (int c = 0; c < 3; ++c) { yv[c] = lds2(sy + c * kFRegion + rrow); xv[c] = lds2(sx + c * kFRegion + rrow); }
+        const float2 nb = f2((((yv[0].x + yv[1].x) + yv[2].x) == 0.f) ? 0.f : 1.f,
+                             (((yv[0].y + yv[1].y) + yv[2].y) == 0.f) ? 0.f : 1.f);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          float sa[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f}, sc[4] = {0.f, 0.f, 0.f, 0.f};
+          float2 gc = f2s(0.f);
           if (a.do_ssim) {
-            // centre (cyy, c0+o) = statistics (cyy+1, c0+o+1): its window is statistics rows cyy..cyy+2,
-            // columns c0+o..c0+o+2
+            // centre (cyy, c0+o) = statistics (cyy+1, c0+o+1): window = statistics rows cyy..cyy+2, cols c0+o..c0+o+2
             const int so = c * kFStats + cyy * kFP + c0;
-            float R0[6], R1[6], R2[6], v[6];
-            lds6(sA + so, R0); lds6(sA + so + kFP, R1); lds6(sA + so + 2 * kFP, R2);
-#pragma unroll
-            for (int j = 0; j < 6; ++j) v[j] = R0[j] + R1[j] + R2[j];
-#pragma unroll
-            for (int o = 0; o < 4; ++o) sa[o] = v[o] + v[o + 1] + v[o + 2];
-            lds6(sB + so, R0); lds6(sB + so + kFP, R1); lds6(sB + so + 2 * kFP, R2);
-#pragma unroll
-            for (int j = 0; j < 6; ++j) v[j] = R0[j] + R1[j] + R2[j];
-#pragma unroll
-            for (int o = 0; o < 4; ++o) sb[o] = v[o] + v[o + 1] + v[o + 2];
-            lds6(sC + so, R0); lds6(sC + so + kFP, R1); lds6(sC + so + 2 * kFP, R2);
-#pragma unroll
-            for (int j = 0; j < 6; ++j) v[j] = R0[j] + R1[j] + R2[j];
-#pragma unroll
-            for (int o = 0; o < 4; ++o) sc[o] = v[o] + v[o + 1] + v[o + 2];
+            float2 va, vb;
+            va = f2add(f2add(lds2(sA + so), lds2(sA + so + kFP)), lds2(sA + so + 2 * kFP));
+            vb = f2add(f2add(lds2(sA + so + 2), lds2(sA + so + kFP + 2)), lds2(sA + so + 2 * kFP + 2));
+            const float2 sa = f2((va.x + va.y) + vb.x, (va.y + vb.x) + vb.y);
+            va = f2add(f2add(lds2(sB + so), lds2(sB + so + kFP)), lds2(sB + so + 2 * kFP));
+            vb = f2add(f2add(lds2(sB + so + 2), lds2(sB + so + kFP + 2)), lds2(sB + so + 2 * kFP + 2));
+            const float2 sb = f2((va.x + va.y) + vb.x, (va.y + vb.x) + vb.y);
+            va = f2add(f2add(lds2(sC + so), lds2(sC + so + kFP)), lds2(sC + so + 2 * kFP));
+            vb = f2add(f2add(lds2(sC + so + 2), lds2(sC + so + kFP + 2)), lds2(sC + so + 2 * kFP + 2));
+            const float2 sc = f2((va.x + va.y) + vb.x, (va.y + vb.x) + vb.y);
+            gc = f2fma(f2add(yv[c], yv[c]), sb, f2fma(xv[c], sc, sa));
           }
-#pragma unroll
-          for (int o = 0; o < 4; ++o) {
-            float gc = sa[o] + 2.f * yv[c][o] * sb[o] + xv[c][o] * sc[o];
-            if (a.do_l1 && !masked[o]) gc += cl1 * sgnf(yv[c][o] - xv[c][o]);
-            g[c][o] = gc;
+          if (a.do_l1) {
+            const float2 sg = f2(sgnf(yv[c].x - xv[c].x), sgnf(yv[c].y - xv[c].y));
+            gc = f2fma(f2mul(nb, f2s(cl1)), sg, gc);
           }
+          g[c] = gc;
         }
         const int ci = cyy * kFCP + c0;
-        float GUv[3][4], GVv[3][4], U[4], V[4], IV[4];
+        float2 gu2 = f2s(0.f), gv2 = f2s(0.f);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const float4 p = *reinterpret_cast<const float4*>(sGU + c * kFCentre + ci);
-          const float4 q = *reinterpret_cast<const float4*>(sGV + c * kFCentre + ci);
-          GUv[c][0] = p.x; GUv[c][1] = p.y; GUv[c][2] = p.z; GUv[c][3] = p.w;
-          GVv[c][0] = q.x; GVv[c][1] = q.y; GVv[c][2] = q.z; GVv[c][3] = q.w;
+          gu2 = f2fma(g[c], lds2(sGU + c * kFCentre + ci), gu2);
+          gv2 = f2fma(g[c], lds2(sGV + c * kFCentre + ci), gv2);
         }
-        {
-          const float4 p = *reinterpret_cast<const float4*>(sU + ci);
-          const float4 q = *reinterpret_cast<const float4*>(sV + ci);
-          const float4 r = *reinterpret_cast<const float4*>(sI + ci);
-          U[0] = p.x; U[1] = p.y; U[2] = p.z; U[3] = p.w;
-          V[0] = q.x; V[1] = q.y; V[2] = q.z; V[3] = q.w;
-          IV[0] = r.x; IV[1] = r.y; IV[2] = r.z; IV[3] = r.w;
-        }
+        const float2 U2 = lds2(sU + ci), V2 = lds2(sV + ci), I2v = lds2(sI + ci);
+        const float2 D2 = lds2(sD + rrow);
+        const float gus[2] = {gu2.x, gu2.y}, gvs[2] = {gv2.x, gv2.y};
+        const float Us[2] = {U2.x, U2.y}, Vs[2] = {V2.x, V2.y}, Is[2] = {I2v.x, I2v.y}, Ds[2] = {D2.x, D2.y};
 #pragma unroll
-        for (int o = 0; o < 4; ++o) {
+        for (int o = 0; o < 2; ++o) {
           const int gx = tx0 + c0 + o;
           if (gy < H && gx < W) {
-            const float gu = g[0][o] * GUv[0][o] + g[1][o] * GUv[1][o] + g[2][o] * GUv[2][o];
-            const float gv = g[0][o] * GVv[0][o] + g[1][o] * GVv[1][o] + g[2][o] * GVv[2][o];
-            const float D = sD[rrow + o];
+            const float gu = gus[o], gv = gvs[o], D = Ds[o], inv = Is[o];
             float r0, r1, r2;
-            ray_of_pixel(Ki, (float)gx, (float)gy, r0, r1, r2);
+            ray_of_pixel(gk + 9, (float)gx, (float)gy, r0, r1, r2);
             const float X0 = r0 * D, X1 = r1 * D, X2 = r2 * D;
-            const float inv = IV[o];
-            const float gp0 = gu * inv, gp1 = gv * inv, gp2 = -(gu * U[o] + gv * V[o]) * inv;
-            const float gY0 = K[0] * gp0 + K[3] * gp1 + K[6] * gp2;
-            const float gY1 = K[1] * gp0 + K[4] * gp1 + K[7] * gp2;
-            const float gY2 = K[2] * gp0 + K[5] * gp1 + K[8] * gp2;
+            const float gp0 = gu * inv, gp1 = gv * inv, gp2 = -(gu * Us[o] + gv * Vs[o]) * inv;
+            const float gY0 = gk[0] * gp0 + gk[3] * gp1 + gk[6] * gp2;
+            const float gY1 = gk[1] * gp0 + gk[4] * gp1 + gk[7] * gp2;
+            const float gY2 = gk[2] * gp0 + gk[5] * gp1 + gk[8] * gp2;
             acc[0] += gY0 * X0; acc[1] += gY0 * X1; acc[2] += gY0 * X2;
             acc[3] += gY1 * X0; acc[4] += gY1 * X1; acc[5] += gY1 * X2;
             acc[6] += gY2 * X0; acc[7] += gY2 * X1; acc[8] += gY2 * X2;
             acc[9] += gY0; acc[10] += gY1; acc[11] += gY2;
-            const float gX0 = T[0] * gY0 + T[3] * gY1 + T[6] * gY2;
-            const float gX1 = T[1] * gY0 + T[4] * gY1 + T[7] * gY2;
-            const float gX2 = T[2] * gY0 + T[5] * gY1 + T[8] * gY2;
+            const float gX0 = gt[0] * gY0 + gt[3] * gY1 + gt[6] * gY2;
+            const float gX1 = gt[1] * gY0 + gt[4] * gY1 + gt[7] * gY2;
+            const float gX2 = gt[2] * gY0 + gt[5] * gY1 + gt[8] * gY2;
             gD[o] += gX0 * r0 + gX1 * r1 + gX2 * r2;
             if (a.d_src[l]) {
               // dL/dsource: re-derive the taps from the cached coordinates (bit-identical to the forward)
-              const Taps tp = make_taps(U[o], V[o], D, W, H);
+              const Taps tp = make_taps(Us[o], Vs[o], D, W, H);
               if (tp.valid && inv != 0.f) {
                 float* dimg = a.d_src[l] + b * a.d_src_bs[l] + n * a.d_src_fs[l];
                 const float w0 = tp.w_uf * tp.w_vf, w1 = tp.w_uf * tp.w_vc, w2 = tp.w_uc * tp.w_vf, w3 = tp.w_uc * tp.w_vc;
                 float* p = dimg + ((long long)tp.iv * W + tp.iu) * 3;
                 float* q = p + (long long)W * 3;
+                const float gs[3] = {o ? g[0].y : g[0].x, o ? g[1].y : g[1].x, o ? g[2].y : g[2].x};
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                  atomicAdd(p + c, w0 * g[c][o]);
-                  atomicAdd(p + 3 + c, w2 * g[c][o]);
-                  atomicAdd(q + c, w1 * g[c][o]);
-                  atomicAdd(q + 3 + c, w3 * g[c][o]);
+                  atomicAdd(p + c, w0 * gs[c]);
+                  atomicAdd(p + 3 + c, w2 * gs[c]);
+                  atomicAdd(q + c, w1 * gs[c]);
+                  atomicAdd(q + 3 + c, w3 * gs[c]);
                 }
               }
             }
@@ -529,7 +521,8 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(FusedArgs a) {
       }
       // 12 pose accumulators: warp reduction in 16 shuffles, then one deterministic cross-warp sum
       const float tot = warp_reduce16(acc, lane);
-      if ((lane & 1) == 0) red[wid * 16 + (((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1))] = tot;
+      if ((lane & 1) == 0)
+        red[wid * 16 + (((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1))] = tot;
       __syncthreads();
       if (tid < 12) {
         float v = 0.f;
@@ -544,7 +537,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(FusedArgs a) {
   if (GRAD && g_active && a.d_depth[l]) {
     const int gy = ty0 + cyy;
 #pragma unroll
-    for (int o = 0; o < 4; ++o) {
+    for (int o = 0; o < 2; ++o) {
       const int gx = tx0 + c0 + o;
       if (gy < H && gx < W) a.d_depth[l][(long long)b * P + gy * W + gx] = gD[o];
     }

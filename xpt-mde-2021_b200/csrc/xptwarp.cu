@@ -318,19 +318,31 @@ int launch_photo(xpt_ctx* ctx, const PhotoArgs& a, cudaStream_t st) {
 }
 
 template <bool GRAD>
-int launch_fused(xpt_ctx* ctx, const FusedArgs& a, cudaStream_t st) {
+int launch_fused(xpt_ctx* ctx, FusedArgs& a, cudaStream_t st) {
   static bool attr_set = false;
   const size_t smem = FusedSmem<GRAD>::kBytes;
   if (!attr_set) {
     XPT_CUDA(cudaFuncSetAttribute(k_fused<GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  dim3 grid(a.tiles_per_b, ctx->B);
+  // camera geometry goes to the constant bank (uniform registers in the kernel); 60 KB hold
+  // kGeoConstFloats / (S*18 + N*12) snippets, larger batches are launched in chunks
+  const int per_b = ctx->S * kGeoK + ctx->N * kGeoT;
+  const int cap = kGeoConstFloats / per_b;
   const bool prof = ctx->prof_on > 0 && ctx->prof_count < ctx->prof_on;
   if (prof) XPT_CUDA(cudaEventRecord((*ctx->prof_events)[2 * ctx->prof_count], st));
-  k_fused<GRAD><<<grid, kFThreads, smem, st>>>(a);
+  for (int b0 = 0; b0 < ctx->B; b0 += cap) {
+    const int bc = ctx->B - b0 < cap ? ctx->B - b0 : cap;
+    const size_t kbytes = (size_t)bc * ctx->S * kGeoK * sizeof(float), tbytes = (size_t)bc * ctx->N * kGeoT * sizeof(float);
+    XPT_CUDA(cudaMemcpyToSymbolAsync(c_geo, ctx->geoK + (size_t)b0 * ctx->S * kGeoK, kbytes, 0, cudaMemcpyDeviceToDevice, st));
+    XPT_CUDA(cudaMemcpyToSymbolAsync(c_geo, ctx->geoT + (size_t)b0 * ctx->N * kGeoT, tbytes, kbytes, cudaMemcpyDeviceToDevice, st));
+    a.b_off = b0;
+    a.geo_t_off = bc * ctx->S * kGeoK;
+    dim3 grid(a.tiles_per_b, bc);
+    k_fused<GRAD><<<grid, kFThreads, smem, st>>>(a);
+    XPT_LAUNCH_CHECK("k_fused");
+  }
   if (prof) { XPT_CUDA(cudaEventRecord((*ctx->prof_events)[2 * ctx->prof_count + 1], st)); ++ctx->prof_count; }
-  XPT_LAUNCH_CHECK("k_fused");
   return XPT_OK;
 }
 
@@ -654,7 +666,7 @@ static int total_loss_impl(xpt_ctx* ctx, const xpt_frames* frames, const float* 
     const int ftiles = ctx->ffirst_tile[ctx->S];
     fa.first_tile[ctx->S] = ftiles;
     fa.tiles_per_b = ftiles;
-    fa.B = ctx->B; fa.N = ctx->N; fa.geoK = ctx->geoK; fa.geoT = ctx->geoT;
+    fa.B = ctx->B; fa.N = ctx->N;
     fa.do_l1 = a.l1_kind != 0; fa.do_ssim = a.do_ssim; fa.do_smooth = a.do_smooth;
     fa.grad_factor = a.grad_factor;
     fa.gcoef_l1 = a.gcoef_l1; fa.gcoef_ssim = a.gcoef_ssim; fa.gcoef_smooth = a.gcoef_smooth;
