@@ -154,8 +154,10 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
   float* const sI = smem + SM::sI;
 
   // ---- which tile -------------------------------------------------------------
-  int t = blockIdx.x;
-  const int bl = blockIdx.y;               // snippet inside this launch's constant-bank chunk
+  // grid = (snippets, tiles): all snippets' tile 0 first, ... the cheap small-level tiles last, so that the
+  // final partial wave is filled with short CTAs
+  int t = blockIdx.y;
+  const int bl = blockIdx.x;               // snippet inside this launch's constant-bank chunk
   const int b = a.b_off + bl;
   int l = 0;
   while (l + 1 < a.lt.S && t >= a.first_tile[l + 1]) ++l;

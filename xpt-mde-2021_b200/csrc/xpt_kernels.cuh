@@ -54,11 +54,21 @@ __device__ __forceinline__ float warp_sum(float v) {
 // (synthesize_base.py:66-71) with their inverses (synthesize_base.py:138).
 // Evaluated in fp64 and rounded once: B*N + B*S tiny problems.
 // ---------------------------------------------------------------------------
-__global__ void k_geometry(const float* __restrict__ pose, const float* __restrict__ intrinsic,
-                           float* __restrict__ geoK, float* __restrict__ geoT,
-                           float* __restrict__ matr_out, int B, int N, LevelTable lt) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < B * N) {
+struct GeoArgs {
+  const float* pose; const float* intrinsic;
+  float* geoK; float* geoT; float* matr_out;
+  int B, N, S;
+  int s[kMaxScales];
+};
+
+__device__ __forceinline__ void geometry_item(const GeoArgs& ga, int i) {
+  const float* __restrict__ pose = ga.pose;
+  const float* __restrict__ intrinsic = ga.intrinsic;
+  float* __restrict__ geoK = ga.geoK;
+  float* __restrict__ geoT = ga.geoT;
+  float* __restrict__ matr_out = ga.matr_out;
+  const int B = ga.B, N = ga.N;
+  if (pose && i < B * N) {
     const float* p = pose + (size_t)i * 6;
     double w1 = p[3], w2 = p[4], w3 = p[5];
     float thf = sqrtf(p[3] * p[3] + p[4] * p[4] + p[5] * p[5]);
@@ -89,10 +99,10 @@ __global__ void k_geometry(const float* __restrict__ pose, const float* __restri
       m[12] = 0.f; m[13] = 0.f; m[14] = 0.f; m[15] = 1.f;
     }
   }
-  if (geoK && i < B * lt.S) {
-    int b = i / lt.S, l = i % lt.S;
+  if (geoK && intrinsic && i < B * ga.S) {
+    int b = i / ga.S, l = i % ga.S;
     const float* K = intrinsic + (size_t)b * 9;
-    float sc = (float)lt.lv[l].s;
+    float sc = (float)ga.s[l];
     float Ks[9];
     for (int k = 0; k < 6; ++k) Ks[k] = K[k] / sc;      // rows 0-1 divided, fp32 like the reference
     Ks[6] = 0.f; Ks[7] = 0.f; Ks[8] = 1.f;
@@ -105,6 +115,8 @@ __global__ void k_geometry(const float* __restrict__ pose, const float* __restri
     for (int k = 0; k < 9; ++k) { o[k] = Ks[k]; o[9 + k] = (float)inv[k]; }
   }
 }
+
+__global__ void k_geometry(GeoArgs ga) { geometry_item(ga, blockIdx.x * blockDim.x + threadIdx.x); }
 
 // ---------------------------------------------------------------------------
 // pyramids: tf.image.resize(bilinear), TF2 half-pixel centres, no antialias
@@ -121,9 +133,15 @@ struct PyramidArgs {
   int s[kMaxScales];
   float* src_out[kMaxScales];  // [B,N,h,w,3] (NULL for s == 1)
   float* tgt_out[kMaxScales];  // [B,h,w,3]   (NULL = not wanted)
+  int with_geometry;           // grid row S carries the camera geometry (overlaps with the pyramid rows)
+  GeoArgs geo;
 };
 
 __global__ void k_pyramid(PyramidArgs a) {
+  if (a.with_geometry && (int)blockIdx.y == a.S) {
+    geometry_item(a.geo, blockIdx.x * blockDim.x + threadIdx.x);
+    return;
+  }
   const int l = blockIdx.y;
   const int s = a.s[l];
   const int h = a.H / s, w = a.W / s;
@@ -476,11 +494,10 @@ __global__ void __launch_bounds__(kWarpBwdThreads) k_warp_bwd(WarpBwdArgs a) {
 // adjoint of Rodrigues' formula: with S = -[w]x, a = sin(th)/th, b = (1-cos th)/th^2,
 // R = I + a S + b S^2  =>  dR/dw_k = a E_k + a'(w_k/th) S + b (E_k S + S E_k) + b'(w_k/th) S^2.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_pose_epilogue(const float* __restrict__ pose_part, int slots_per_b,
-                                                       int slots_used, const float* __restrict__ pose,
-                                                       float* __restrict__ d_pose, int N, float scale) {
+__device__ void pose_block(const float* __restrict__ pose_part, int slots_per_b, int slots_used,
+                           const float* __restrict__ pose, float* __restrict__ d_pose, int N, int bn) {
   __shared__ double red[4][12];
-  const int bn = blockIdx.x;
+  const float scale = 1.0f;
   const int b = bn / N, n = bn % N;
   double acc[12];
   for (int k = 0; k < 12; ++k) acc[k] = 0.0;
@@ -1004,6 +1021,12 @@ __global__ void __launch_bounds__(256) k_smooth(SmoothArgs a) {
 //   mean_k = sum_b loss_batch[k][b] / global_batch        (compute_average_loss, losses.py:49)
 //   total  = sum_k w_k * mean_k                            (losses.py:50-54)
 // ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_pose_epilogue(const float* __restrict__ pose_part, int slots_per_b,
+                                                       int slots_used, const float* __restrict__ pose,
+                                                       float* __restrict__ d_pose, int N, float /*scale*/) {
+  pose_block(pose_part, slots_per_b, slots_used, pose, d_pose, N, blockIdx.x);
+}
+
 __global__ void __launch_bounds__(256) k_loss_epilogue(const float* __restrict__ loss_part, int slots_per_b,
                                                        int slots_used, int B, float inv_global_batch, float w0,
                                                        float w1, float w2, float* __restrict__ losses,
@@ -1036,6 +1059,62 @@ __global__ void __launch_bounds__(256) k_loss_epilogue(const float* __restrict__
     double m0 = tot[0] * inv_global_batch, m1 = tot[1] * inv_global_batch, m2 = tot[2] * inv_global_batch;
     losses[0] = (float)(w0 * m0 + w1 * m1 + w2 * m2);
     losses[1] = (float)m0; losses[2] = (float)m1; losses[3] = (float)m2;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// merged epilogue of the fused path: blocks [0, B*N) reduce the pose partials and apply the Rodrigues
+// adjoint (same code as k_pose_epilogue); blocks [B*N, B*N+B) reduce one snippet's loss partials; the
+// last of those to finish (atomic ticket) sums the snippets in fixed order -> losses[4].
+// ---------------------------------------------------------------------------
+struct EpilogueArgs {
+  const float* pose_part; const float* loss_part;
+  int slots_per_b, slots_used, B, N;
+  const float* pose; float* d_pose;            // d_pose may be NULL (forward only)
+  float inv_global_batch, w0, w1, w2;
+  float* losses; float* loss_batch;            // loss_batch may be NULL
+  double* loss_sum_b;                          // [B][3] scratch
+  unsigned int* ticket;                        // zero before the first launch; self-resetting
+};
+
+__global__ void __launch_bounds__(128) k_epilogue(EpilogueArgs a) {
+  __shared__ double red[4][3];
+  __shared__ bool last;
+  const int nb_pose = a.d_pose ? a.B * a.N : 0;
+  if ((int)blockIdx.x < nb_pose) {
+    pose_block(a.pose_part, a.slots_per_b, a.slots_used, a.pose, a.d_pose, a.N, blockIdx.x);
+    return;
+  }
+  const int b = blockIdx.x - nb_pose;
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (int sl = threadIdx.x; sl < a.slots_used; sl += blockDim.x) {
+    const float* p = a.loss_part + ((size_t)b * a.slots_per_b + sl) * 3;
+    acc[0] += p[0]; acc[1] += p[1]; acc[2] += p[2];
+  }
+  for (int k = 0; k < 3; ++k) {
+    double v = acc[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double v = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+    a.loss_sum_b[b * 3 + threadIdx.x] = v;
+    if (a.loss_batch) a.loss_batch[threadIdx.x * a.B + b] = (float)v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(a.ticket, 1u) == (unsigned)(a.B - 1);
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double tot[3] = {0.0, 0.0, 0.0};
+    for (int bb = 0; bb < a.B; ++bb)
+      for (int k = 0; k < 3; ++k) tot[k] += ((volatile double*)a.loss_sum_b)[bb * 3 + k];
+    const double m0 = tot[0] * a.inv_global_batch, m1 = tot[1] * a.inv_global_batch, m2 = tot[2] * a.inv_global_batch;
+    a.losses[0] = (float)(a.w0 * m0 + a.w1 * m1 + a.w2 * m2);
+    a.losses[1] = (float)m0; a.losses[2] = (float)m1; a.losses[3] = (float)m2;
+    *a.ticket = 0u;
   }
 }
 

@@ -67,6 +67,8 @@ struct xpt_ctx {
   float* tgt_pyr[kMaxScales];   // s > 1
   float* loss_part;
   float* pose_part;
+  double* loss_sum_b;           // [B][3] (k_epilogue)
+  unsigned int* ticket;         // k_epilogue's last-block ticket (self-resetting)
   // lazily allocated
   float* synth_scr[kMaxScales];
   float* gsynth_scr[kMaxScales];
@@ -156,20 +158,29 @@ LevelTable make_levels(const xpt_ctx* ctx, const xpt_frames* f, const float* con
   return lt;
 }
 
+GeoArgs make_geo(xpt_ctx* ctx, const float* pose, const float* intrinsic, float* matr_out) {
+  GeoArgs g;
+  memset(&g, 0, sizeof(g));
+  g.pose = pose; g.intrinsic = intrinsic;
+  g.geoK = intrinsic ? ctx->geoK : nullptr; g.geoT = pose ? ctx->geoT : nullptr; g.matr_out = matr_out;
+  g.B = ctx->B; g.N = ctx->N; g.S = ctx->S;
+  for (int l = 0; l < ctx->S; ++l) g.s[l] = ctx->s[l];
+  return g;
+}
+
 int launch_geometry(xpt_ctx* ctx, const float* pose, const float* intrinsic, float* matr_out, cudaStream_t st) {
-  LevelTable lt = make_levels(ctx, nullptr, nullptr);
   int n = ctx->B * (ctx->N > ctx->S ? ctx->N : ctx->S);
-  k_geometry<<<cdiv(n, 128), 128, 0, st>>>(pose, intrinsic, intrinsic ? ctx->geoK : nullptr,
-                                           pose ? ctx->geoT : nullptr, matr_out, ctx->B, ctx->N, lt);
+  k_geometry<<<cdiv(n, 128), 128, 0, st>>>(make_geo(ctx, pose, intrinsic, matr_out));
   XPT_LAUNCH_CHECK("k_geometry");
   return XPT_OK;
 }
 
 // source pyramid into the ctx (+ target pyramid into ctx or user buffers)
 int launch_pyramids(xpt_ctx* ctx, const xpt_frames* f, float* const target_ms[], bool want_source,
-                    cudaStream_t st) {
+                    cudaStream_t st, const float* geo_pose = nullptr) {
   PyramidArgs a;
   memset(&a, 0, sizeof(a));
+  if (geo_pose) { a.with_geometry = 1; a.geo = make_geo(ctx, geo_pose, f->intrinsic, nullptr); }
   a.source = f->source; a.src_bs = f->source_batch_stride; a.src_fs = f->source_frame_stride;
   a.target = f->target; a.tgt_bs = f->target_batch_stride;
   a.B = ctx->B; a.N = ctx->N; a.H = ctx->H; a.W = ctx->W; a.S = ctx->S;
@@ -189,8 +200,12 @@ int launch_pyramids(xpt_ctx* ctx, const xpt_frames* f, float* const target_ms[],
       if (c > maxcount) maxcount = c;
     }
   }
+  if (a.with_geometry) {
+    long long g = (long long)ctx->B * (ctx->N > ctx->S ? ctx->N : ctx->S);
+    if (g > maxcount) maxcount = g;
+  }
   if (maxcount == 0) return XPT_OK;
-  dim3 grid(cdiv(maxcount, 256), ctx->S);
+  dim3 grid(cdiv(maxcount, 256), ctx->S + (a.with_geometry ? 1 : 0));
   k_pyramid<<<grid, 256, 0, st>>>(a);
   XPT_LAUNCH_CHECK("k_pyramid");
   // user copies of the target pyramid (augm_data["target_ms"])
@@ -334,11 +349,15 @@ int launch_fused(xpt_ctx* ctx, FusedArgs& a, cudaStream_t st) {
   for (int b0 = 0; b0 < ctx->B; b0 += cap) {
     const int bc = ctx->B - b0 < cap ? ctx->B - b0 : cap;
     const size_t kbytes = (size_t)bc * ctx->S * kGeoK * sizeof(float), tbytes = (size_t)bc * ctx->N * kGeoT * sizeof(float);
-    XPT_CUDA(cudaMemcpyToSymbolAsync(c_geo, ctx->geoK + (size_t)b0 * ctx->S * kGeoK, kbytes, 0, cudaMemcpyDeviceToDevice, st));
-    XPT_CUDA(cudaMemcpyToSymbolAsync(c_geo, ctx->geoT + (size_t)b0 * ctx->N * kGeoT, tbytes, kbytes, cudaMemcpyDeviceToDevice, st));
+    if (bc == ctx->B) {       // K block and [R|t] block are adjacent in the scratch: one copy
+      XPT_CUDA(cudaMemcpyToSymbolAsync(c_geo, ctx->geoK, kbytes + tbytes, 0, cudaMemcpyDeviceToDevice, st));
+    } else {
+      XPT_CUDA(cudaMemcpyToSymbolAsync(c_geo, ctx->geoK + (size_t)b0 * ctx->S * kGeoK, kbytes, 0, cudaMemcpyDeviceToDevice, st));
+      XPT_CUDA(cudaMemcpyToSymbolAsync(c_geo, ctx->geoT + (size_t)b0 * ctx->N * kGeoT, tbytes, kbytes, cudaMemcpyDeviceToDevice, st));
+    }
     a.b_off = b0;
     a.geo_t_off = bc * ctx->S * kGeoK;
-    dim3 grid(a.tiles_per_b, bc);
+    dim3 grid(bc, a.tiles_per_b);
     k_fused<GRAD><<<grid, kFThreads, smem, st>>>(a);
     XPT_LAUNCH_CHECK("k_fused");
   }
@@ -454,8 +473,17 @@ int xpt_create(xpt_ctx** out, const xpt_config* cfg) {
 
   int rc = XPT_OK;
   auto A = [&](float** p, size_t n) { if (rc == XPT_OK) rc = dev_alloc(ctx, p, n); };
-  A(&ctx->geoK, (size_t)ctx->B * ctx->S * kGeoK);
-  A(&ctx->geoT, (size_t)ctx->B * ctx->N * kGeoT);
+  A(&ctx->geoK, (size_t)ctx->B * ctx->S * kGeoK + (size_t)ctx->B * ctx->N * kGeoT);   // K block, then [R|t] block
+  if (rc == XPT_OK) ctx->geoT = ctx->geoK + (size_t)ctx->B * ctx->S * kGeoK;
+  {
+    float* tmp = nullptr;
+    A(&tmp, (size_t)ctx->B * 6 + 2);          // [B][3] doubles + ticket
+    if (rc == XPT_OK) {
+      ctx->loss_sum_b = reinterpret_cast<double*>(tmp);
+      ctx->ticket = reinterpret_cast<unsigned int*>(tmp + (size_t)ctx->B * 6);
+      if (cudaMemset(ctx->ticket, 0, sizeof(unsigned int)) != cudaSuccess) rc = fail(XPT_CUDA_ERROR, "cudaMemset failed");
+    }
+  }
   for (int l = 0; l < ctx->S; ++l)
     if (ctx->s[l] > 1) {
       A(&ctx->src_pyr[l], (size_t)ctx->B * ctx->N * lvl_pix(ctx, l) * 3);
@@ -472,7 +500,7 @@ void xpt_destroy(xpt_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->cfg.device);
   auto F = [](float* p) { if (p) cudaFree(p); };
-  F(ctx->geoK); F(ctx->geoT); F(ctx->loss_part); F(ctx->pose_part); F(ctx->tgt0_copy);
+  F(ctx->geoK); F(reinterpret_cast<float*>(ctx->loss_sum_b)); F(ctx->loss_part); F(ctx->pose_part); F(ctx->tgt0_copy);
   F(ctx->st_frames); F(ctx->st_K); F(ctx->st_pose); F(ctx->st_losses); F(ctx->st_loss_batch); F(ctx->st_dpose);
   F(ctx->st_dsource);
   for (int l = 0; l < kMaxScales; ++l) {
@@ -618,8 +646,7 @@ static int total_loss_impl(xpt_ctx* ctx, const xpt_frames* frames, const float* 
   const float gs = out->grad_scale;
   const float inv_gb = 1.0f / (float)c.global_batch;
 
-  XPT_TRY(launch_geometry(ctx, pose, frames->intrinsic, nullptr, st));
-  XPT_TRY(launch_pyramids(ctx, frames, out->target_ms, true, st));
+  XPT_TRY(launch_pyramids(ctx, frames, out->target_ms, true, st, pose));   // + camera geometry in the same launch
   LevelTable lt = make_levels(ctx, frames, nullptr);
 
   PhotoArgs a;
@@ -673,12 +700,16 @@ static int total_loss_impl(xpt_ctx* ctx, const xpt_frames* frames, const float* 
     fa.loss_part = ctx->loss_part; fa.slots_per_b = ctx->slots_per_b; fa.pose_part = ctx->pose_part;
     if (grad) XPT_TRY((launch_fused<true>(ctx, fa, st)));
     else XPT_TRY((launch_fused<false>(ctx, fa, st)));
-    if (grad && out->d_pose) {
-      k_pose_epilogue<<<ctx->B * ctx->N, 128, 0, st>>>(ctx->pose_part, ctx->slots_per_b, ftiles, pose, out->d_pose,
-                                                       ctx->N, 1.0f);
-      XPT_LAUNCH_CHECK("k_pose_epilogue");
-    }
-    XPT_TRY(launch_loss_epilogue(ctx, ftiles, c.w_l1, c.w_ssim, c.w_smooth, out->losses, out->loss_batch, st));
+    EpilogueArgs ea;
+    memset(&ea, 0, sizeof(ea));
+    ea.pose_part = ctx->pose_part; ea.loss_part = ctx->loss_part;
+    ea.slots_per_b = ctx->slots_per_b; ea.slots_used = ftiles; ea.B = ctx->B; ea.N = ctx->N;
+    ea.pose = pose; ea.d_pose = grad ? out->d_pose : nullptr;
+    ea.inv_global_batch = inv_gb; ea.w0 = c.w_l1; ea.w1 = c.w_ssim; ea.w2 = c.w_smooth;
+    ea.losses = out->losses; ea.loss_batch = out->loss_batch;
+    ea.loss_sum_b = ctx->loss_sum_b; ea.ticket = ctx->ticket;
+    k_epilogue<<<(ea.d_pose ? ctx->B * ctx->N : 0) + ctx->B, 128, 0, st>>>(ea);
+    XPT_LAUNCH_CHECK("k_epilogue");
   } else {
     // ---- unfused path (flags bit 0): one kernel per reference stage, tensors through HBM
     float* synth[kMaxScales]; float* gsyn[kMaxScales];
