@@ -64,14 +64,6 @@ __device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) { return _
 __device__ __forceinline__ float2 f2neg(float2 a) { return make_float2(-a.x, -a.y); }
 __device__ __forceinline__ float2 lds2(const float* p) { return *reinterpret_cast<const float2*>(p); }
 
-// 1/x: MUFU.RCP + one Newton step (<= 1 ulp); used where the reference divides but a 1-ulp
-// difference cannot move a mask (SSIM ratio, cached 1/den of the backward)
-__device__ __forceinline__ float rcp_nr(float x) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return fmaf(fmaf(-x, r, 1.f), r, r);
-}
-
 __device__ __forceinline__ float box_inv(int cnt) {   // 1 / #in-image taps of a 3x3 window
   return cnt == 9 ? (1.f / 9.f) : (cnt == 6 ? (1.f / 6.f) : (cnt == 4 ? 0.25f : 1.f / (float)cnt));
 }
@@ -321,7 +313,9 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
           const float D = sD[i];
           float r0, r1, r2;
           ray_of_pixel(gk + 9, (float)gx, (float)gy, r0, r1, r2);
-          const Proj pr = project(gk, gt, r0, r1, r2, D);
+          // IEEE division like the reference: floor(u) decides taps and validity, so the perspective
+          // divide is not approximated (measured: the reciprocal form costs parity at floor crossings)
+          const Proj pr = project<false>(gk, gt, r0, r1, r2, D);
           const Taps tp = make_taps(pr.u, pr.v, D, W, H);
           valid = tp.valid;
           if (valid) {

@@ -185,6 +185,63 @@ __global__ void k_pyramid(PyramidArgs a) {
   }
 }
 
+// Fast path for scales within {1,2,4,8}: ONE pass over the full-resolution frames.  A CTA stages an
+// 8-row x 128-pixel tile in shared memory with 16-byte loads and emits the s=2, 4, 8 outputs of
+// that tile (centre 2x2 of each s x s block, TF's nested lerps), so every input byte is read from
+// HBM once instead of once per level.  Extra z-slice: the camera geometry (overlaps with the copy).
+constexpr int kPyrTW = 128, kPyrTH = 8, kPyrThreads = 256;
+
+struct PyramidTiledArgs {
+  const float* source; long long src_bs, src_fs;
+  const float* target; long long tgt_bs;       // target may be NULL
+  int B, N, H, W;
+  float* src_out[4];   // index = log2(s): [1] s=2, [2] s=4, [3] s=8 (NULL = level absent)
+  float* tgt_out[4];
+  int with_geometry;
+  GeoArgs geo;
+};
+
+__global__ void __launch_bounds__(kPyrThreads) k_pyramid_tiled(PyramidTiledArgs a) {
+  __shared__ __align__(16) float tile[kPyrTH][kPyrTW * 3];
+  const int nfr = a.N + 1;
+  if ((int)blockIdx.z == a.B * nfr) {           // geometry slice
+    if (a.with_geometry && blockIdx.y == 0) geometry_item(a.geo, blockIdx.x * blockDim.x + threadIdx.x);
+    return;
+  }
+  const int b = blockIdx.z / nfr, f = blockIdx.z % nfr;
+  const bool is_tgt = f == a.N;
+  if (is_tgt && a.target == nullptr) return;
+  const float* in = is_tgt ? a.target + b * a.tgt_bs : a.source + b * a.src_bs + f * a.src_fs;
+  const int x0 = blockIdx.x * kPyrTW, y0 = blockIdx.y * kPyrTH;
+  const int tw = min(kPyrTW, a.W - x0);         // multiple of 8
+  const int row_f4 = tw * 3 / 4;                // float4 per tile row
+  for (int i = threadIdx.x; i < kPyrTH * row_f4; i += kPyrThreads) {
+    const int r = i / row_f4, c4 = i - r * row_f4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(in + ((long long)(y0 + r) * a.W + x0) * 3) + c4);
+    *reinterpret_cast<float4*>(&tile[r][c4 * 4]) = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int lg = 1; lg <= 3; ++lg) {
+    float* outp = is_tgt ? a.tgt_out[lg] : a.src_out[lg];
+    if (outp == nullptr) continue;
+    const int s = 1 << lg;
+    const int oh = kPyrTH / s, ow = tw / s;      // outputs of this tile
+    const int Hs = a.H / s, Ws = a.W / s;
+    const long long frame = is_tgt ? (long long)b : (long long)(b * a.N + f);
+    float* o = outp + frame * Hs * Ws * 3;
+    for (int e = threadIdx.x; e < oh * ow * 3; e += kPyrThreads) {
+      const int oy = e / (ow * 3), rem = e - oy * (ow * 3);
+      const int ox = rem / 3, c = rem - ox * 3;
+      const int ry = oy * s + s / 2 - 1, rx = (ox * s + s / 2 - 1) * 3 + c;
+      const float tl = tile[ry][rx], tr = tile[ry][rx + 3], bl = tile[ry + 1][rx], br = tile[ry + 1][rx + 3];
+      const float top = tl + (tr - tl) * 0.5f;
+      const float bot = bl + (br - bl) * 0.5f;
+      o[((long long)(y0 / s + oy) * Ws + (x0 / s + ox)) * 3 + c] = top + (bot - top) * 0.5f;
+    }
+  }
+}
+
 // adjoint of the source pyramid: d_source[full] += resize^T(d_source_level) for s > 1
 // (each level pixel spreads 1/4 to its centre 2x2 / 1 to the centre pixel).
 struct PyramidAdjArgs {
@@ -245,8 +302,18 @@ __device__ __forceinline__ void ray_of_pixel(const float* __restrict__ Ki, float
   r2 = Ki[6] * uu + Ki[7] * vv + Ki[8];
 }
 
+// 1/x: MUFU.RCP + one Newton step (<= 1 ulp of the correctly rounded reciprocal)
+__device__ __forceinline__ float rcp_nr(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return fmaf(fmaf(-x, r, 1.f), r, r);
+}
+
+// FAST = false: IEEE division like the reference's `pixel_coords / (z + 1e-10)`;
+// FAST = true : one reciprocal + two multiplies (<= 2 ulp on u, v), `inv` returned for the backward.
+template <bool FAST = false>
 __device__ __forceinline__ Proj project(const float* __restrict__ K, const float* __restrict__ T,
-                                        float r0, float r1, float r2, float D) {
+                                        float r0, float r1, float r2, float D, float* inv_out = nullptr) {
   Proj o;
   o.X0 = r0 * D; o.X1 = r1 * D; o.X2 = r2 * D;
   float Y0 = T[0] * o.X0 + T[1] * o.X1 + T[2] * o.X2 + T[9];
@@ -256,8 +323,15 @@ __device__ __forceinline__ Proj project(const float* __restrict__ K, const float
   float p1 = K[3] * Y0 + K[4] * Y1 + K[5] * Y2;
   float p2 = K[6] * Y0 + K[7] * Y1 + K[8] * Y2;
   o.den = p2 + 1e-10f;
-  o.u = p0 / o.den;
-  o.v = p1 / o.den;
+  if (FAST) {
+    const float inv = rcp_nr(o.den);
+    o.u = p0 * inv;
+    o.v = p1 * inv;
+    if (inv_out) *inv_out = inv;
+  } else {
+    o.u = p0 / o.den;
+    o.v = p1 / o.den;
+  }
   return o;
 }
 

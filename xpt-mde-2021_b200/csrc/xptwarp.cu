@@ -8,6 +8,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdint>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -178,6 +179,51 @@ int launch_geometry(xpt_ctx* ctx, const float* pose, const float* intrinsic, flo
 // source pyramid into the ctx (+ target pyramid into ctx or user buffers)
 int launch_pyramids(xpt_ctx* ctx, const xpt_frames* f, float* const target_ms[], bool want_source,
                     cudaStream_t st, const float* geo_pose = nullptr) {
+  // ---- fast path: scales within {1,2,4,8}, 16-byte aligned rows -> one tiled pass over the frames
+  {
+    bool ok = ctx->W % 8 == 0 && ctx->H % 8 == 0 && want_source;
+    for (int l = 0; l < ctx->S; ++l) ok = ok && (ctx->s[l] == 1 || ctx->s[l] == 2 || ctx->s[l] == 4 || ctx->s[l] == 8);
+    auto al16 = [](const void* p) { return ((uintptr_t)p & 15u) == 0; };
+    ok = ok && al16(f->source) && f->source_batch_stride % 4 == 0 && f->source_frame_stride % 4 == 0;
+    if (f->target) ok = ok && al16(f->target) && f->target_batch_stride % 4 == 0;
+    if (ok) {
+      PyramidTiledArgs t;
+      memset(&t, 0, sizeof(t));
+      t.source = f->source; t.src_bs = f->source_batch_stride; t.src_fs = f->source_frame_stride;
+      t.target = f->target; t.tgt_bs = f->target_batch_stride;
+      t.B = ctx->B; t.N = ctx->N; t.H = ctx->H; t.W = ctx->W;
+      bool any = false;
+      for (int l = 0; l < ctx->S; ++l) {
+        const int sc = ctx->s[l];
+        if (sc == 1) continue;
+        const int lg = sc == 2 ? 1 : (sc == 4 ? 2 : 3);
+        t.src_out[lg] = ctx->src_pyr[l];
+        if (f->target) t.tgt_out[lg] = ctx->tgt_pyr[l];
+        any = true;
+      }
+      if (geo_pose) { t.with_geometry = 1; t.geo = make_geo(ctx, geo_pose, f->intrinsic, nullptr); }
+      if (any || geo_pose) {
+        int gx = cdiv(ctx->W, kPyrTW);
+        const int need = cdiv((long long)ctx->B * (ctx->N > ctx->S ? ctx->N : ctx->S), kPyrThreads);
+        if (geo_pose && need > gx) gx = need;
+        dim3 grid(gx, ctx->H / kPyrTH, ctx->B * (ctx->N + 1) + 1);
+        if (!any) grid = dim3(need, 1, ctx->B * (ctx->N + 1) + 1);
+        k_pyramid_tiled<<<grid, kPyrThreads, 0, st>>>(t);
+        XPT_LAUNCH_CHECK("k_pyramid_tiled");
+      }
+      if (target_ms && f->target)
+        for (int l = 0; l < ctx->S; ++l) {
+          if (!target_ms[l]) continue;
+          const size_t row = lvl_pix(ctx, l) * 3 * sizeof(float);
+          if (ctx->s[l] > 1)
+            XPT_CUDA(cudaMemcpyAsync(target_ms[l], ctx->tgt_pyr[l], (size_t)ctx->B * row, cudaMemcpyDeviceToDevice, st));
+          else
+            XPT_CUDA(cudaMemcpy2DAsync(target_ms[l], row, f->target, f->target_batch_stride * sizeof(float), row, ctx->B,
+                                       cudaMemcpyDeviceToDevice, st));
+        }
+      return XPT_OK;
+    }
+  }
   PyramidArgs a;
   memset(&a, 0, sizeof(a));
   if (geo_pose) { a.with_geometry = 1; a.geo = make_geo(ctx, geo_pose, f->intrinsic, nullptr); }
