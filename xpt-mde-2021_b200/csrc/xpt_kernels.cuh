@@ -214,30 +214,47 @@ __global__ void __launch_bounds__(kPyrThreads) k_pyramid_tiled(PyramidTiledArgs 
   const float* in = is_tgt ? a.target + b * a.tgt_bs : a.source + b * a.src_bs + f * a.src_fs;
   const int x0 = blockIdx.x * kPyrTW, y0 = blockIdx.y * kPyrTH;
   const int tw = min(kPyrTW, a.W - x0);         // multiple of 8
-  const int row_f4 = tw * 3 / 4;                // float4 per tile row
-  for (int i = threadIdx.x; i < kPyrTH * row_f4; i += kPyrThreads) {
-    const int r = i / row_f4, c4 = i - r * row_f4;
-    const float4 v = __ldg(reinterpret_cast<const float4*>(in + ((long long)(y0 + r) * a.W + x0) * 3) + c4);
-    *reinterpret_cast<float4*>(&tile[r][c4 * 4]) = v;
+  const float* in0 = in + ((long long)y0 * a.W + x0) * 3;
+  const long long rowst = (long long)a.W * 3;
+  if (tw == kPyrTW) {
+    constexpr int kRowF4 = kPyrTW * 3 / 4;      // 96 float4 per tile row: all index math is compile-time
+#pragma unroll
+    for (int k = 0; k < kPyrTH * kRowF4 / kPyrThreads; ++k) {
+      const int i = threadIdx.x + k * kPyrThreads;
+      const int r = i / kRowF4, c4 = i - r * kRowF4;
+      *reinterpret_cast<float4*>(&tile[r][c4 * 4]) = __ldg(reinterpret_cast<const float4*>(in0 + r * rowst) + c4);
+    }
+  } else {
+    const int row_f4 = tw * 3 / 4;
+    for (int i = threadIdx.x; i < kPyrTH * row_f4; i += kPyrThreads) {
+      const int r = i / row_f4, c4 = i - r * row_f4;
+      *reinterpret_cast<float4*>(&tile[r][c4 * 4]) = __ldg(reinterpret_cast<const float4*>(in0 + r * rowst) + c4);
+    }
   }
   __syncthreads();
+  const long long frame = is_tgt ? (long long)b : (long long)(b * a.N + f);
 #pragma unroll
   for (int lg = 1; lg <= 3; ++lg) {
     float* outp = is_tgt ? a.tgt_out[lg] : a.src_out[lg];
     if (outp == nullptr) continue;
     const int s = 1 << lg;
-    const int oh = kPyrTH / s, ow = tw / s;      // outputs of this tile
-    const int Hs = a.H / s, Ws = a.W / s;
-    const long long frame = is_tgt ? (long long)b : (long long)(b * a.N + f);
-    float* o = outp + frame * Hs * Ws * 3;
-    for (int e = threadIdx.x; e < oh * ow * 3; e += kPyrThreads) {
-      const int oy = e / (ow * 3), rem = e - oy * (ow * 3);
+    const int oh = kPyrTH >> lg;                 // output rows of this tile
+    const int Hs = a.H >> lg, Ws = a.W >> lg;
+    float* o = outp + (frame * Hs + (y0 >> lg)) * Ws * 3 + (x0 >> lg) * 3;
+    auto emit = [&](int oy, int rem) {           // rem = 3*ox + c inside the tile's output row
       const int ox = rem / 3, c = rem - ox * 3;
       const int ry = oy * s + s / 2 - 1, rx = (ox * s + s / 2 - 1) * 3 + c;
       const float tl = tile[ry][rx], tr = tile[ry][rx + 3], bl = tile[ry + 1][rx], br = tile[ry + 1][rx + 3];
       const float top = tl + (tr - tl) * 0.5f;
       const float bot = bl + (br - bl) * 0.5f;
-      o[((long long)(y0 / s + oy) * Ws + (x0 / s + ox)) * 3 + c] = top + (bot - top) * 0.5f;
+      o[(long long)oy * Ws * 3 + rem] = top + (bot - top) * 0.5f;
+    };
+    if (tw == kPyrTW) {
+      const int roww = (kPyrTW >> lg) * 3;       // 192 / 96 / 48: compile-time after unrolling
+      for (int e = threadIdx.x; e < oh * roww; e += kPyrThreads) emit(e / roww, e % roww);
+    } else {
+      const int roww = (tw >> lg) * 3;
+      for (int e = threadIdx.x; e < oh * roww; e += kPyrThreads) emit(e / roww, e % roww);
     }
   }
 }
