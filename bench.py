@@ -225,14 +225,28 @@ def main():
     torch.cuda.set_stream(side)
     stream = plan.stream()
 
+    pending = [None] * n_sets
+
     def step(i):
-        c = calls[i % n_sets]
+        k = i % n_sets
+        if pending[k] is not None:            # this set's loss buffer is about to be rewritten
+            pending[k].wait()
+            pending[k] = None
+        c = calls[k]
         c.run(stream)
         if dist is not None:
-            # the path's only exchange: the 4 loss scalars (replaces distributer.py:93-110)
-            dist.all_reduce(c.out["losses"])
+            # the path's only exchange: the 4 loss scalars (replaces distributer.py:93-110); asynchronous, so
+            # the NCCL kernel overlaps with the next step's launches instead of serialising the stream
+            pending[k] = dist.all_reduce(c.out["losses"], async_op=True)
+
+    def drain():
+        for k in range(n_sets):
+            if pending[k] is not None:
+                pending[k].wait()             # current stream waits for the collective
+                pending[k] = None
 
     def barrier():
+        drain()
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
@@ -251,6 +265,7 @@ def main():
     e0.record()
     for i in range(args.steps):
         step(i)
+    drain()
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -295,8 +310,16 @@ def main():
     if kern_ms:
         fused_bytes = BYTES_FUSED + (N_SRC * GAMMA * 12 if args.source_grad else 0)
         ach = px_rank * fused_bytes / (kern_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "k_photo<fused,grad>", "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": ach / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": kern_ms,
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath) and not args.source_grad:
+            with open(tpath) as tf_:
+                rec = json.load(tf_).get(args.workload)
+            if rec:
+                traffic = rec["dram_bytes_per_launch"]        # bytes per launch, from the committed ncu --set full capture
+        roofline = {"bound": "hbm", "kernel": "k_fused<grad>", "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": ach / peak, "traffic": traffic, "algorithmic_bytes_per_launch": px_rank * fused_bytes,
+                    "peak_source": peak_src, "kernel_ms": kern_ms,
                     "bytes_per_pixel": fused_bytes, "kernel_share_of_step": kern_ms / ms_step if world == 1 else None}
     step_model = {"bytes_per_pixel": BYTES_SURVEY_STEP,
                   "achieved_gbs": value / world * BYTES_SURVEY_STEP, "frac_of_peak": value / world * BYTES_SURVEY_STEP / peak,
