@@ -128,7 +128,19 @@ struct FusedArgs {
   long long d_src_bs[kMaxScales], d_src_fs[kMaxScales];
 };
 
-template <bool GRAD>
+// Perspective divide of both coordinates with ONE reciprocal: r = 1/den refined once, then each
+// quotient gets the remainder correction q' = q + (p - den*q)*r (Markstein), which reproduces the
+// correctly rounded IEEE quotient the reference computes for normal-range operands.
+__device__ __forceinline__ void div_pair(float p0, float p1, float den, float& u, float& v, float& r) {
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(den));
+  r = fmaf(fmaf(-den, r, 1.f), r, r);
+  const float q0 = p0 * r, q1 = p1 * r;
+  u = fmaf(fmaf(-den, q0, p0), r, q0);
+  v = fmaf(fmaf(-den, q1, p1), r, q1);
+}
+
+// GRAD: backward in the same launch.  OUT: synth_ms / mask_ms are written.  DSRC: dL/dsource scatter.
+template <bool GRAD, bool OUT, bool DSRC>
 __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ FusedArgs a) {
   using SM = FusedSmem<GRAD>;
   extern __shared__ __align__(16) float smem[];
@@ -212,7 +224,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
           float e = 0.f;
 #pragma unroll
           for (int c = 0; c < 3; ++c) e += fabsf((sx[c * kFRegion + ri] - sx[c * kFRegion + ri + 1]) * k3);
-          const float w = expf(-(e / 3.f));
+          const float w = expf(-(e * (1.f / 3.f)));
           const float sd = (d - __ldg(dsp + (long long)gy * W + gx + 1)) * w;
           lsum_sm += fabsf(sd) * nx;
           gd += gcx * sgnf(sd) * w;
@@ -221,7 +233,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
           float e = 0.f;
 #pragma unroll
           for (int c = 0; c < 3; ++c) e += fabsf((sx[c * kFRegion + ri] - sx[c * kFRegion + ri + kFP]) * k3);
-          const float w = expf(-(e / 3.f));
+          const float w = expf(-(e * (1.f / 3.f)));
           const float sd = (d - __ldg(dsp + (long long)(gy + 1) * W + gx)) * w;
           lsum_sm += fabsf(sd) * ny;
           gd += gcy * sgnf(sd) * w;
@@ -231,7 +243,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
             float e = 0.f;
 #pragma unroll
             for (int c = 0; c < 3; ++c) e += fabsf((sx[c * kFRegion + ri - 1] - sx[c * kFRegion + ri]) * k3);
-            const float w = expf(-(e / 3.f));
+            const float w = expf(-(e * (1.f / 3.f)));
             const float sd = (__ldg(dsp + (long long)gy * W + gx - 1) - d) * w;
             gd -= gcx * sgnf(sd) * w;
           }
@@ -239,7 +251,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
             float e = 0.f;
 #pragma unroll
             for (int c = 0; c < 3; ++c) e += fabsf((sx[c * kFRegion + ri - kFP] - sx[c * kFRegion + ri]) * k3);
-            const float w = expf(-(e / 3.f));
+            const float w = expf(-(e * (1.f / 3.f)));
             const float sd = (__ldg(dsp + (long long)(gy - 1) * W + gx) - d) * w;
             gd -= gcy * sgnf(sd) * w;
           }
@@ -311,11 +323,21 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
         const bool inimg = gy >= 0 && gy < H && gx >= 0 && gx < W;
         if (inimg) {
           const float D = sD[i];
-          float r0, r1, r2;
-          ray_of_pixel(gk + 9, (float)gx, (float)gy, r0, r1, r2);
-          // IEEE division like the reference: floor(u) decides taps and validity, so the perspective
-          // divide is not approximated (measured: the reciprocal form costs parity at floor crossings)
-          const Proj pr = project<false>(gk, gt, r0, r1, r2, D);
+          // reference order.  The last rows of K_s and inv(K_s) are exactly (0,0,1)
+          // (synthesize_base.py:66-71), so ray.z = 1 and p.z = Y.z hold bit-exactly and are not recomputed.
+          const float fx = (float)gx, fy = (float)gy;
+          const float r0 = gk[9] * fx + gk[10] * fy + gk[11];
+          const float r1 = gk[12] * fx + gk[13] * fy + gk[14];
+          const float X0 = r0 * D, X1 = r1 * D, X2 = D;
+          const float Y0 = gt[0] * X0 + gt[1] * X1 + gt[2] * X2 + gt[9];
+          const float Y1 = gt[3] * X0 + gt[4] * X1 + gt[5] * X2 + gt[10];
+          const float Y2 = gt[6] * X0 + gt[7] * X1 + gt[8] * X2 + gt[11];
+          const float p0 = gk[0] * Y0 + gk[1] * Y1 + gk[2] * Y2;
+          const float p1 = gk[3] * Y0 + gk[4] * Y1 + gk[5] * Y2;
+          Proj pr;
+          pr.den = Y2 + 1e-10f;
+          float inv_den;
+          div_pair(p0, p1, pr.den, pr.u, pr.v, inv_den);
           const Taps tp = make_taps(pr.u, pr.v, D, W, H);
           valid = tp.valid;
           if (valid) {
@@ -330,7 +352,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
                 gu[c] = tp.w_vf * (I2[c] - I0[c]) + tp.w_vc * (I3[c] - I1[c]);
                 gv[c] = tp.w_uf * (I1[c] - I0[c]) + tp.w_uc * (I3[c] - I2[c]);
               }
-              su = pr.u; sv = pr.v; si = rcp_nr(pr.den);
+              su = pr.u; sv = pr.v; si = inv_den;
             }
           }
         }
@@ -342,7 +364,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
             sGV[ci] = gv[0]; sGV[kFCentre + ci] = gv[1]; sGV[2 * kFCentre + ci] = gv[2];
             sU[ci] = su; sV[ci] = sv; sI[ci] = si;
           }
-          if (inimg) {
+          if (OUT && inimg) {
             const long long o = (long long)(b * a.N + n) * P + gy * W + gx;
             if (a.synth_out[l]) { float* so = a.synth_out[l] + o * 3; so[0] = yv[0]; so[1] = yv[1]; so[2] = yv[2]; }
             if (a.mask_out[l]) a.mask_out[l][o] = valid ? 1.f : 0.f;
@@ -479,13 +501,14 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
           const int gx = tx0 + c0 + o;
           if (gy < H && gx < W) {
             const float gu = gus[o], gv = gvs[o], D = Ds[o], inv = Is[o];
-            float r0, r1, r2;
-            ray_of_pixel(gk + 9, (float)gx, (float)gy, r0, r1, r2);
-            const float X0 = r0 * D, X1 = r1 * D, X2 = r2 * D;
+            const float fx = (float)gx, fy = (float)gy;
+            const float r0 = gk[9] * fx + gk[10] * fy + gk[11];
+            const float r1 = gk[12] * fx + gk[13] * fy + gk[14];
+            const float X0 = r0 * D, X1 = r1 * D, X2 = D;
             const float gp0 = gu * inv, gp1 = gv * inv, gp2 = -(gu * Us[o] + gv * Vs[o]) * inv;
-            const float gY0 = gk[0] * gp0 + gk[3] * gp1 + gk[6] * gp2;
-            const float gY1 = gk[1] * gp0 + gk[4] * gp1 + gk[7] * gp2;
-            const float gY2 = gk[2] * gp0 + gk[5] * gp1 + gk[8] * gp2;
+            const float gY0 = gk[0] * gp0 + gk[3] * gp1;          // K_s^T with last row (0,0,1)
+            const float gY1 = gk[1] * gp0 + gk[4] * gp1;
+            const float gY2 = gk[2] * gp0 + gk[5] * gp1 + gp2;
             acc[0] += gY0 * X0; acc[1] += gY0 * X1; acc[2] += gY0 * X2;
             acc[3] += gY1 * X0; acc[4] += gY1 * X1; acc[5] += gY1 * X2;
             acc[6] += gY2 * X0; acc[7] += gY2 * X1; acc[8] += gY2 * X2;
@@ -493,8 +516,8 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
             const float gX0 = gt[0] * gY0 + gt[3] * gY1 + gt[6] * gY2;
             const float gX1 = gt[1] * gY0 + gt[4] * gY1 + gt[7] * gY2;
             const float gX2 = gt[2] * gY0 + gt[5] * gY1 + gt[8] * gY2;
-            gD[o] += gX0 * r0 + gX1 * r1 + gX2 * r2;
-            if (a.d_src[l]) {
+            gD[o] += gX0 * r0 + gX1 * r1 + gX2;
+            if (DSRC && a.d_src[l]) {
               // dL/dsource: re-derive the taps from the cached coordinates (bit-identical to the forward)
               const Taps tp = make_taps(Us[o], Vs[o], D, W, H);
               if (tp.valid && inv != 0.f) {

@@ -378,12 +378,12 @@ int launch_photo(xpt_ctx* ctx, const PhotoArgs& a, cudaStream_t st) {
   return XPT_OK;
 }
 
-template <bool GRAD>
+template <bool GRAD, bool OUT, bool DSRC>
 int launch_fused(xpt_ctx* ctx, FusedArgs& a, cudaStream_t st) {
   static bool attr_set = false;
   const size_t smem = FusedSmem<GRAD>::kBytes;
   if (!attr_set) {
-    XPT_CUDA(cudaFuncSetAttribute(k_fused<GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    XPT_CUDA(cudaFuncSetAttribute(k_fused<GRAD, OUT, DSRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   // camera geometry goes to the constant bank (uniform registers in the kernel); 60 KB hold
@@ -404,7 +404,7 @@ int launch_fused(xpt_ctx* ctx, FusedArgs& a, cudaStream_t st) {
     a.b_off = b0;
     a.geo_t_off = bc * ctx->S * kGeoK;
     dim3 grid(bc, a.tiles_per_b);
-    k_fused<GRAD><<<grid, kFThreads, smem, st>>>(a);
+    k_fused<GRAD, OUT, DSRC><<<grid, kFThreads, smem, st>>>(a);
     XPT_LAUNCH_CHECK("k_fused");
   }
   if (prof) { XPT_CUDA(cudaEventRecord((*ctx->prof_events)[2 * ctx->prof_count + 1], st)); ++ctx->prof_count; }
@@ -744,8 +744,15 @@ static int total_loss_impl(xpt_ctx* ctx, const xpt_frames* frames, const float* 
     fa.grad_factor = a.grad_factor;
     fa.gcoef_l1 = a.gcoef_l1; fa.gcoef_ssim = a.gcoef_ssim; fa.gcoef_smooth = a.gcoef_smooth;
     fa.loss_part = ctx->loss_part; fa.slots_per_b = ctx->slots_per_b; fa.pose_part = ctx->pose_part;
-    if (grad) XPT_TRY((launch_fused<true>(ctx, fa, st)));
-    else XPT_TRY((launch_fused<false>(ctx, fa, st)));
+    bool want_out = false;
+    for (int l = 0; l < ctx->S; ++l) want_out = want_out || out->synth_ms[l] || out->mask_ms[l];
+    const bool dsrc = grad && out->d_source;
+    if (grad) {
+      if (dsrc) { if (want_out) XPT_TRY((launch_fused<true, true, true>(ctx, fa, st))); else XPT_TRY((launch_fused<true, false, true>(ctx, fa, st))); }
+      else { if (want_out) XPT_TRY((launch_fused<true, true, false>(ctx, fa, st))); else XPT_TRY((launch_fused<true, false, false>(ctx, fa, st))); }
+    } else {
+      if (want_out) XPT_TRY((launch_fused<false, true, false>(ctx, fa, st))); else XPT_TRY((launch_fused<false, false, false>(ctx, fa, st)));
+    }
     EpilogueArgs ea;
     memset(&ea, 0, sizeof(ea));
     ea.pose_part = ctx->pose_part; ea.loss_part = ctx->loss_part;
