@@ -80,6 +80,8 @@ typedef struct {
  * given argument set (all pointers, strides, grad_scale, stream) and replays the
  * instantiated graph afterwards (up to 64 cached argument sets per ctx).      */
 #define XPT_FLAG_GRAPH 2u
+/* xpt_total_loss_host runs the batch as ONE chunk (no copy/compute pipelining).                */
+#define XPT_FLAG_NO_PIPELINE 4u
 
 /* The snippet frames + intrinsics (features of losses.py:26-37).              */
 typedef struct {
@@ -169,8 +171,12 @@ XPT_API int xpt_total_loss(xpt_ctx* ctx, const xpt_frames* frames,
 
 /* The same call with HOST buffers (pinned or pageable): copies inputs to
  * device staging owned by the ctx, runs xpt_total_loss, copies back the
- * outputs that are non-NULL, and synchronises the stream before returning.
- * `frames` and all pointers in `out` are host pointers here.                  */
+ * outputs that are non-NULL, and synchronises before returning.  The batch is
+ * cut into up to 4 chunks so that host->device copies, compute and
+ * device->host copies of consecutive chunks overlap (copy streams inside the
+ * ctx; compute on `stream`).  `frames` and all pointers in `out` are host
+ * pointers here; losses of a pipelined call are the sum of the chunk losses
+ * (same value up to fp32 rounding of the 4 partial sums).                     */
 XPT_API int xpt_total_loss_host(xpt_ctx* ctx, const xpt_frames* frames,
                         const float* const depth_ms[], const float* const disp_ms[],
                         const float* pose, const xpt_loss_outputs* out, void* stream);

@@ -296,7 +296,8 @@ def test_host_buffer_entry_point(xw):
     _cabi.check(plan._lib.xpt_total_loss_host(
         plan.handle, C.byref(fr), C.byref(_cabi.ptr_array([d.data_ptr() for d in preds["depth_ms"]])),
         C.byref(_cabi.ptr_array([d.data_ptr() for d in preds["disp_ms"]])), pose.data_ptr(), C.byref(out), None))
-    assert torch.equal(losses, r["losses"].cpu())
+    # the host entry point pipelines the batch in chunks: losses are sums of chunk losses
+    assert relerr(losses.numpy(), r["losses"].cpu().numpy()) < 1e-6
     assert torch.equal(d_pose, r["d_pose"].cpu())
     for s in range(4):
         assert torch.equal(d_depth[s], r["d_depth_ms"][s].cpu().reshape(d_depth[s].shape))

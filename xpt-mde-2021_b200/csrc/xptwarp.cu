@@ -85,6 +85,12 @@ struct xpt_ctx {
   struct GraphEntry { std::vector<uint64_t> key; cudaGraphExec_t exec; int launches; };
   std::vector<GraphEntry>* graphs;
   bool warm;                    // one eager call has run (all lazy scratch exists)
+  // pipelined host entry point: a child ctx for one batch chunk, copy streams, events
+  xpt_ctx* child;
+  cudaStream_t s_in, s_in2, s_out;
+  cudaEvent_t ev_small;
+  cudaEvent_t ev_in[4], ev_done[4];
+  float* h_losses;              // pinned [4][4]: a pageable destination would block the host per chunk
   // per-launch device timing of the dominant kernel (xpt_profile_*)
   std::vector<cudaEvent_t>* prof_events;
   int prof_count;
@@ -554,6 +560,12 @@ void xpt_destroy(xpt_ctx* ctx) {
     F(ctx->st_depth[l]); F(ctx->st_disp[l]); F(ctx->st_ddepth[l]); F(ctx->st_ddisp[l]);
     F(ctx->st_synth[l]); F(ctx->st_mask[l]); F(ctx->st_target[l]);
   }
+  if (ctx->child) xpt_destroy(ctx->child);
+  if (ctx->h_losses) cudaFreeHost(ctx->h_losses);
+  if (ctx->s_in) {
+    cudaStreamDestroy(ctx->s_in); cudaStreamDestroy(ctx->s_out); cudaStreamDestroy(ctx->s_in2); cudaEventDestroy(ctx->ev_small);
+    for (int k = 0; k < 4; ++k) { cudaEventDestroy(ctx->ev_in[k]); cudaEventDestroy(ctx->ev_done[k]); }
+  }
   if (ctx->graphs) {
     for (auto& e : *ctx->graphs) cudaGraphExecDestroy(e.exec);
     delete ctx->graphs;
@@ -914,74 +926,152 @@ int xpt_total_loss_host(xpt_ctx* ctx, const xpt_frames* frames, const float* con
   const int B = ctx->B, N = ctx->N, S = ctx->S;
   const size_t fb = sizeof(float);
 
-  // ---- host -> device staging ------------------------------------------------
-  XPT_TRY(dev_alloc(ctx, &ctx->st_frames, (size_t)B * (N + 1) * hw3));
-  XPT_TRY(dev_alloc(ctx, &ctx->st_K, (size_t)B * 9));
-  XPT_TRY(dev_alloc(ctx, &ctx->st_pose, (size_t)B * N * 6));
-  XPT_TRY(dev_alloc(ctx, &ctx->st_losses, 4));
-  const long long snip = (long long)(N + 1) * hw3;
-  const bool one_block = frames->target == frames->source + (long long)N * hw3 &&
-                         frames->source_batch_stride == snip && frames->target_batch_stride == snip;
-  if (one_block) {
-    XPT_CUDA(cudaMemcpyAsync(ctx->st_frames, frames->source, (size_t)B * snip * fb, cudaMemcpyHostToDevice, st));
-  } else {
-    XPT_CUDA(cudaMemcpy2DAsync(ctx->st_frames, snip * fb, frames->source, frames->source_batch_stride * fb,
-                               (size_t)N * hw3 * fb, B, cudaMemcpyHostToDevice, st));
-    XPT_CUDA(cudaMemcpy2DAsync(ctx->st_frames + (long long)N * hw3, snip * fb, frames->target,
-                               frames->target_batch_stride * fb, (size_t)hw3 * fb, B, cudaMemcpyHostToDevice, st));
-  }
-  XPT_CUDA(cudaMemcpyAsync(ctx->st_K, frames->intrinsic, (size_t)B * 9 * fb, cudaMemcpyHostToDevice, st));
-  XPT_CUDA(cudaMemcpyAsync(ctx->st_pose, pose, (size_t)B * N * 6 * fb, cudaMemcpyHostToDevice, st));
-  const float* d_depth_in[kMaxScales]; const float* d_disp_in[kMaxScales];
-  for (int l = 0; l < S; ++l) {
-    size_t n = (size_t)B * lvl_pix(ctx, l);
-    XPT_TRY(dev_alloc(ctx, &ctx->st_depth[l], n));
-    XPT_CUDA(cudaMemcpyAsync(ctx->st_depth[l], depth_ms[l], n * fb, cudaMemcpyHostToDevice, st));
-    d_depth_in[l] = ctx->st_depth[l];
-    d_disp_in[l] = nullptr;
-    if (do_smooth) {
-      XPT_TRY(dev_alloc(ctx, &ctx->st_disp[l], n));
-      XPT_CUDA(cudaMemcpyAsync(ctx->st_disp[l], disp_ms[l], n * fb, cudaMemcpyHostToDevice, st));
-      d_disp_in[l] = ctx->st_disp[l];
+  // ---- pipeline: the batch is cut into chunks; chunk k+1's host->device copies run on a copy-in
+  // stream while chunk k computes on the caller's stream and chunk k-1's results drain on a copy-out
+  // stream (snippets are independent; every chunk normalises by the global batch, so chunk losses add).
+  int nc = 1;
+  if (!(ctx->cfg.flags & XPT_FLAG_NO_PIPELINE))
+    for (int c = 4; c >= 2; --c)
+      if (B % c == 0) { nc = c; break; }
+  const int Bc = B / nc;
+  xpt_ctx* child = ctx;
+  if (nc > 1) {
+    if (!ctx->child) {
+      xpt_config cc = ctx->cfg;
+      cc.batch = Bc;
+      cc.flags |= XPT_FLAG_NO_PIPELINE;
+      XPT_TRY(xpt_create(&ctx->child, &cc));
+    }
+    child = ctx->child;
+    if (!ctx->s_in) {
+      XPT_CUDA(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+      XPT_CUDA(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+      XPT_CUDA(cudaStreamCreateWithFlags(&ctx->s_in2, cudaStreamNonBlocking));
+      XPT_CUDA(cudaEventCreateWithFlags(&ctx->ev_small, cudaEventDisableTiming));
+      for (int k = 0; k < 4; ++k) {
+        XPT_CUDA(cudaEventCreateWithFlags(&ctx->ev_in[k], cudaEventDisableTiming));
+        XPT_CUDA(cudaEventCreateWithFlags(&ctx->ev_done[k], cudaEventDisableTiming));
+      }
     }
   }
-  xpt_frames df;
-  df.source = ctx->st_frames; df.source_batch_stride = snip; df.source_frame_stride = hw3;
-  df.target = ctx->st_frames + (long long)N * hw3; df.target_batch_stride = snip;
-  df.intrinsic = ctx->st_K;
+  cudaStream_t s_in = nc > 1 ? ctx->s_in : st, s_in2 = nc > 1 ? ctx->s_in2 : st, s_out = nc > 1 ? ctx->s_out : st;
 
-  // ---- device outputs mirroring the requested host outputs --------------------
-  xpt_loss_outputs dout;
-  memset(&dout, 0, sizeof(dout));
-  dout.grad_scale = out->grad_scale;
-  dout.losses = ctx->st_losses;
-  if (out->loss_batch) { XPT_TRY(dev_alloc(ctx, &ctx->st_loss_batch, (size_t)3 * B)); dout.loss_batch = ctx->st_loss_batch; }
-  if (out->d_pose) { XPT_TRY(dev_alloc(ctx, &ctx->st_dpose, (size_t)B * N * 6 + B)); dout.d_pose = ctx->st_dpose; }
-  if (out->d_source) { XPT_TRY(dev_alloc(ctx, &ctx->st_dsource, (size_t)B * N * hw3)); dout.d_source = ctx->st_dsource; }
+  // ---- device staging (sized for the whole batch, owned by the parent ctx) ---------------------------
+  const long long snip = (long long)(N + 1) * hw3;
+  XPT_TRY(dev_alloc(ctx, &ctx->st_frames, (size_t)B * snip));
+  XPT_TRY(dev_alloc(ctx, &ctx->st_K, (size_t)B * 9));
+  XPT_TRY(dev_alloc(ctx, &ctx->st_pose, (size_t)B * N * 6));
+  XPT_TRY(dev_alloc(ctx, &ctx->st_losses, 4 * 4));
+  if (out->loss_batch) XPT_TRY(dev_alloc(ctx, &ctx->st_loss_batch, (size_t)3 * B));
+  if (out->d_pose) XPT_TRY(dev_alloc(ctx, &ctx->st_dpose, (size_t)B * N * 6 + B));
+  if (out->d_source) XPT_TRY(dev_alloc(ctx, &ctx->st_dsource, (size_t)B * N * hw3));
   for (int l = 0; l < S; ++l) {
-    size_t n = (size_t)B * lvl_pix(ctx, l);
-    if (out->d_depth_ms[l]) { XPT_TRY(dev_alloc(ctx, &ctx->st_ddepth[l], n)); dout.d_depth_ms[l] = ctx->st_ddepth[l]; }
-    if (out->d_disp_ms[l]) { XPT_TRY(dev_alloc(ctx, &ctx->st_ddisp[l], n)); dout.d_disp_ms[l] = ctx->st_ddisp[l]; }
-    if (out->synth_ms[l]) { XPT_TRY(dev_alloc(ctx, &ctx->st_synth[l], n * N * 3)); dout.synth_ms[l] = ctx->st_synth[l]; }
-    if (out->mask_ms[l]) { XPT_TRY(dev_alloc(ctx, &ctx->st_mask[l], n * N)); dout.mask_ms[l] = ctx->st_mask[l]; }
-    if (out->target_ms[l]) { XPT_TRY(dev_alloc(ctx, &ctx->st_target[l], n * 3)); dout.target_ms[l] = ctx->st_target[l]; }
+    const size_t n = (size_t)B * lvl_pix(ctx, l);
+    XPT_TRY(dev_alloc(ctx, &ctx->st_depth[l], n));
+    if (do_smooth) XPT_TRY(dev_alloc(ctx, &ctx->st_disp[l], n));
+    if (out->d_depth_ms[l]) XPT_TRY(dev_alloc(ctx, &ctx->st_ddepth[l], n));
+    if (out->d_disp_ms[l]) XPT_TRY(dev_alloc(ctx, &ctx->st_ddisp[l], n));
+    if (out->synth_ms[l]) XPT_TRY(dev_alloc(ctx, &ctx->st_synth[l], n * N * 3));
+    if (out->mask_ms[l]) XPT_TRY(dev_alloc(ctx, &ctx->st_mask[l], n * N));
+    if (out->target_ms[l]) XPT_TRY(dev_alloc(ctx, &ctx->st_target[l], n * 3));
   }
-  XPT_TRY(xpt_total_loss(ctx, &df, d_depth_in, d_disp_in, ctx->st_pose, &dout, stream));
+  const bool one_block = frames->target == frames->source + (long long)N * hw3 &&
+                         frames->source_batch_stride == snip && frames->target_batch_stride == snip;
+  if (!ctx->h_losses) XPT_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_losses), 16 * sizeof(float)));
+  float (*h_losses)[4] = reinterpret_cast<float (*)[4]>(ctx->h_losses);
 
-  // ---- device -> host ----------------------------------------------------------
-  XPT_CUDA(cudaMemcpyAsync(out->losses, dout.losses, 4 * fb, cudaMemcpyDeviceToHost, st));
-  if (out->loss_batch) XPT_CUDA(cudaMemcpyAsync(out->loss_batch, dout.loss_batch, (size_t)3 * B * fb, cudaMemcpyDeviceToHost, st));
-  if (out->d_pose) XPT_CUDA(cudaMemcpyAsync(out->d_pose, dout.d_pose, (size_t)B * N * 6 * fb, cudaMemcpyDeviceToHost, st));
-  if (out->d_source) XPT_CUDA(cudaMemcpyAsync(out->d_source, dout.d_source, (size_t)B * N * hw3 * fb, cudaMemcpyDeviceToHost, st));
+  // small inputs (K, pose, depth_ms, disp_ms: ~7 % of the bytes, 10 copies of ~5 us latency each): whole
+  // batch at once on their own stream, concurrently with the first frame chunk
+  XPT_CUDA(cudaMemcpyAsync(ctx->st_K, frames->intrinsic, (size_t)B * 9 * fb, cudaMemcpyHostToDevice, s_in2));
+  XPT_CUDA(cudaMemcpyAsync(ctx->st_pose, pose, (size_t)B * N * 6 * fb, cudaMemcpyHostToDevice, s_in2));
   for (int l = 0; l < S; ++l) {
-    size_t n = (size_t)B * lvl_pix(ctx, l);
-    if (out->d_depth_ms[l]) XPT_CUDA(cudaMemcpyAsync(out->d_depth_ms[l], dout.d_depth_ms[l], n * fb, cudaMemcpyDeviceToHost, st));
-    if (out->d_disp_ms[l]) XPT_CUDA(cudaMemcpyAsync(out->d_disp_ms[l], dout.d_disp_ms[l], n * fb, cudaMemcpyDeviceToHost, st));
-    if (out->synth_ms[l]) XPT_CUDA(cudaMemcpyAsync(out->synth_ms[l], dout.synth_ms[l], n * N * 3 * fb, cudaMemcpyDeviceToHost, st));
-    if (out->mask_ms[l]) XPT_CUDA(cudaMemcpyAsync(out->mask_ms[l], dout.mask_ms[l], n * N * fb, cudaMemcpyDeviceToHost, st));
-    if (out->target_ms[l]) XPT_CUDA(cudaMemcpyAsync(out->target_ms[l], dout.target_ms[l], n * 3 * fb, cudaMemcpyDeviceToHost, st));
+    const size_t n = (size_t)B * lvl_pix(ctx, l);
+    XPT_CUDA(cudaMemcpyAsync(ctx->st_depth[l], depth_ms[l], n * fb, cudaMemcpyHostToDevice, s_in2));
+    if (do_smooth) XPT_CUDA(cudaMemcpyAsync(ctx->st_disp[l], disp_ms[l], n * fb, cudaMemcpyHostToDevice, s_in2));
   }
+  if (nc > 1) {
+    XPT_CUDA(cudaEventRecord(ctx->ev_small, s_in2));
+    XPT_CUDA(cudaStreamWaitEvent(st, ctx->ev_small, 0));
+  }
+
+  for (int k = 0; k < nc; ++k) {
+    const int b0 = k * Bc;
+    // -- host -> device, chunk k: the frames
+    float* dfr = ctx->st_frames + (long long)b0 * snip;
+    if (one_block) {
+      XPT_CUDA(cudaMemcpyAsync(dfr, frames->source + (long long)b0 * snip, (size_t)Bc * snip * fb, cudaMemcpyHostToDevice, s_in));
+    } else {
+      XPT_CUDA(cudaMemcpy2DAsync(dfr, snip * fb, frames->source + (long long)b0 * frames->source_batch_stride,
+                                 frames->source_batch_stride * fb, (size_t)N * hw3 * fb, Bc, cudaMemcpyHostToDevice, s_in));
+      XPT_CUDA(cudaMemcpy2DAsync(dfr + (long long)N * hw3, snip * fb, frames->target + (long long)b0 * frames->target_batch_stride,
+                                 frames->target_batch_stride * fb, (size_t)hw3 * fb, Bc, cudaMemcpyHostToDevice, s_in));
+    }
+    const float* cdepth[kMaxScales]; const float* cdisp[kMaxScales];
+    for (int l = 0; l < S; ++l) {
+      const size_t off = (size_t)b0 * lvl_pix(ctx, l);
+      cdepth[l] = ctx->st_depth[l] + off;
+      cdisp[l] = do_smooth ? ctx->st_disp[l] + off : nullptr;
+    }
+    if (nc > 1) {
+      XPT_CUDA(cudaEventRecord(ctx->ev_in[k], s_in));
+      XPT_CUDA(cudaStreamWaitEvent(st, ctx->ev_in[k], 0));
+    }
+    // -- compute, chunk k (caller's stream)
+    xpt_frames df;
+    df.source = dfr; df.source_batch_stride = snip; df.source_frame_stride = hw3;
+    df.target = dfr + (long long)N * hw3; df.target_batch_stride = snip;
+    df.intrinsic = ctx->st_K + (size_t)b0 * 9;
+    xpt_loss_outputs dout;
+    memset(&dout, 0, sizeof(dout));
+    dout.grad_scale = out->grad_scale;
+    dout.losses = ctx->st_losses + 4 * k;
+    if (out->loss_batch) dout.loss_batch = ctx->st_loss_batch + (size_t)3 * b0;     // chunk-major [k][3][Bc]
+    if (out->d_pose) dout.d_pose = ctx->st_dpose + (size_t)b0 * N * 6;
+    if (out->d_source) dout.d_source = ctx->st_dsource + (size_t)b0 * N * hw3;
+    for (int l = 0; l < S; ++l) {
+      const size_t off = (size_t)b0 * lvl_pix(ctx, l);
+      if (out->d_depth_ms[l]) dout.d_depth_ms[l] = ctx->st_ddepth[l] + off;
+      if (out->d_disp_ms[l]) dout.d_disp_ms[l] = ctx->st_ddisp[l] + off;
+      if (out->synth_ms[l]) dout.synth_ms[l] = ctx->st_synth[l] + off * N * 3;
+      if (out->mask_ms[l]) dout.mask_ms[l] = ctx->st_mask[l] + off * N;
+      if (out->target_ms[l]) dout.target_ms[l] = ctx->st_target[l] + off * 3;
+    }
+    XPT_TRY(xpt_total_loss(child, &df, cdepth, cdisp, ctx->st_pose + (size_t)b0 * N * 6, &dout, stream));
+    if (nc > 1) {
+      XPT_CUDA(cudaEventRecord(ctx->ev_done[k], st));
+      XPT_CUDA(cudaStreamWaitEvent(s_out, ctx->ev_done[k], 0));
+    }
+    // -- device -> host, chunk k: the large per-chunk outputs; small ones leave once at the end
+    if (out->d_source) XPT_CUDA(cudaMemcpyAsync(out->d_source + (size_t)b0 * N * hw3, dout.d_source, (size_t)Bc * N * hw3 * fb, cudaMemcpyDeviceToHost, s_out));
+    for (int l = 0; l < S; ++l) {
+      const size_t off = (size_t)b0 * lvl_pix(ctx, l), n = (size_t)Bc * lvl_pix(ctx, l);
+      if (l == 0 && out->d_depth_ms[l]) XPT_CUDA(cudaMemcpyAsync(out->d_depth_ms[l] + off, dout.d_depth_ms[l], n * fb, cudaMemcpyDeviceToHost, s_out));
+      if (l == 0 && out->d_disp_ms[l]) XPT_CUDA(cudaMemcpyAsync(out->d_disp_ms[l] + off, dout.d_disp_ms[l], n * fb, cudaMemcpyDeviceToHost, s_out));
+      if (out->synth_ms[l]) XPT_CUDA(cudaMemcpyAsync(out->synth_ms[l] + off * N * 3, dout.synth_ms[l], n * N * 3 * fb, cudaMemcpyDeviceToHost, s_out));
+      if (out->mask_ms[l]) XPT_CUDA(cudaMemcpyAsync(out->mask_ms[l] + off * N, dout.mask_ms[l], n * N * fb, cudaMemcpyDeviceToHost, s_out));
+      if (out->target_ms[l]) XPT_CUDA(cudaMemcpyAsync(out->target_ms[l] + off * 3, dout.target_ms[l], n * 3 * fb, cudaMemcpyDeviceToHost, s_out));
+    }
+  }
+  // small outputs, whole batch (s_out already waits for the last chunk's compute)
+  XPT_CUDA(cudaMemcpyAsync(ctx->h_losses, ctx->st_losses, (size_t)4 * nc * fb, cudaMemcpyDeviceToHost, s_out));
+  if (out->loss_batch)
+    for (int k = 0; k < nc; ++k)
+      for (int r = 0; r < 3; ++r)
+        XPT_CUDA(cudaMemcpyAsync(out->loss_batch + (size_t)r * B + (size_t)k * Bc, ctx->st_loss_batch + (size_t)3 * k * Bc + (size_t)r * Bc,
+                                 Bc * fb, cudaMemcpyDeviceToHost, s_out));
+  if (out->d_pose) XPT_CUDA(cudaMemcpyAsync(out->d_pose, ctx->st_dpose, (size_t)B * N * 6 * fb, cudaMemcpyDeviceToHost, s_out));
+  for (int l = 1; l < S; ++l) {
+    const size_t n = (size_t)B * lvl_pix(ctx, l);
+    if (out->d_depth_ms[l]) XPT_CUDA(cudaMemcpyAsync(out->d_depth_ms[l], ctx->st_ddepth[l], n * fb, cudaMemcpyDeviceToHost, s_out));
+    if (out->d_disp_ms[l]) XPT_CUDA(cudaMemcpyAsync(out->d_disp_ms[l], ctx->st_ddisp[l], n * fb, cudaMemcpyDeviceToHost, s_out));
+  }
+  if (nc > 1) XPT_CUDA(cudaStreamSynchronize(s_out));
   XPT_CUDA(cudaStreamSynchronize(st));
+  for (int j = 0; j < 4; ++j) {
+    double v = 0.0;
+    for (int k = 0; k < nc; ++k) v += (double)h_losses[k][j];
+    out->losses[j] = (float)v;
+  }
   return XPT_OK;
 }
 
