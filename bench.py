@@ -198,6 +198,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
+        # torchrun exports OMP_NUM_THREADS=1; the synthetic inputs are generated on the host
+        torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))
 
     import xptwarp
     from xptwarp import _cabi
@@ -269,11 +271,12 @@ def main():
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
-    if ms_total < 400:      # keep the clock sampler meaningful on tiny workloads: same loop, untimed
+    if ms_total < 400:      # keep the clock sampler meaningful on tiny workloads: same kernels, untimed.
+        # No collective in here: ranks run different numbers of filler steps, and unmatched all-reduces deadlock.
         t_end = time.time() + 0.6
         i = 0
         while time.time() < t_end:
-            step(i)
+            calls[i % n_sets].run(stream)
             i += 1
         torch.cuda.synchronize()
     clocks = sampler.stop()

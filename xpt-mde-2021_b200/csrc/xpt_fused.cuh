@@ -31,6 +31,8 @@ constexpr int kFStats = kFSH * kFP;            // 1020
 constexpr int kFCP = 64;                       // pitch of the centre arrays
 constexpr int kFCentre = kFCH * kFCP;          // 832
 constexpr int kFYIters = (kFRegion + kFThreads - 1) / kFThreads;   // 3
+constexpr int kFRedSrc = 4;                    // sources whose pose partials are buffered before the cross-warp sum
+constexpr int kFRedFloats = kFRedSrc * kFCH * 16;                  // 832 (>= 48 floats of loss scratch)
 
 // camera geometry in the constant bank: [Bc][S][18] (K_s, inv K_s) then [Bc][N][12] ([R|t])
 constexpr int kGeoConstFloats = 15360;         // 60 KB
@@ -41,9 +43,11 @@ struct FusedSmem {
   // offsets in floats
   static constexpr int sy = 0;                                  // [3][17][68] warped tile
   static constexpr int sx = sy + 3 * kFRegion + 4;              // [3][17][68] target tile
-  static constexpr int sD = sx + 3 * kFRegion + 4;              // [17][68] depth
-  static constexpr int red = sD + kFRegion + 4;                 // 256 floats of reduction scratch
-  static constexpr int sA = red + 256;                          // GRAD: [3][15][68] x3
+  static constexpr int sD = sx + 3 * kFRegion + 4;              // [17][68] depth (0 outside the image)
+  static constexpr int sR0 = sD + kFRegion + 4;                 // [17][68] x2: ray = inv(K_s) (u,v,1), xy components
+  static constexpr int sR1 = sR0 + kFRegion + 4;
+  static constexpr int red = sR1 + kFRegion + 4;                // pose partials [kFRedSrc][13 warps][16] / loss scratch
+  static constexpr int sA = red + kFRedFloats;                  // GRAD: [3][15][68] x3
   static constexpr int sB = sA + (GRAD ? 3 * kFStats + 4 : 0);
   static constexpr int sC = sB + (GRAD ? 3 * kFStats + 4 : 0);
   static constexpr int sGU = sC + (GRAD ? 3 * kFStats + 4 : 0); // GRAD: [3][13][64] dS_c/du
@@ -139,6 +143,12 @@ __device__ __forceinline__ void div_pair(float p0, float p1, float den, float& u
   v = fmaf(fmaf(-den, q1, p1), r, q1);
 }
 
+// horizontal 3-sums of a 4-column vertical sum (a.x a.y b.x b.y) for the strip's two pixels
+__device__ __forceinline__ float2 hsum3(float2 a, float2 b) {
+  const float m = a.y + b.x;
+  return make_float2(a.x + m, m + b.y);
+}
+
 // GRAD: backward in the same launch.  OUT: synth_ms / mask_ms are written.  DSRC: dL/dsource scatter.
 template <bool GRAD, bool OUT, bool DSRC>
 __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ FusedArgs a) {
@@ -147,6 +157,8 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
   float* const sy = smem + SM::sy;
   float* const sx = smem + SM::sx;
   float* const sD = smem + SM::sD;
+  float* const sR0 = smem + SM::sR0;
+  float* const sR1 = smem + SM::sR1;
   float* const red = smem + SM::red;
   float* const sA = smem + SM::sA;
   float* const sB = smem + SM::sB;
@@ -173,7 +185,9 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
   const int slot = L.slot_base + t;
   const float* const gk = c_geo + (bl * a.lt.S + l) * kGeoK;     // K_s (9), inv K_s (9): uniform registers
 
-  // ---- target tile and depth tile (halo 2), zero outside the image --------------------
+  // ---- target tile, depth tile and pixel rays (halo 2); zero outside the image ---------------------
+  // depth 0 marks "no sample": the reference's D != 0 validity test (bilinear_interp.py:53-76) then also
+  // rejects the out-of-image halo, so the warp phase needs no bounds test of its own.
   {
     const float* tgt = L.tgt + b * L.tgt_bs;
     const float* dep = a.depth[l] + (long long)b * P;
@@ -183,14 +197,19 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
       if (i < kFRegion) {
         const int ry = i / kFP, rx = i - ry * kFP;
         const int gy = ty0 - 2 + ry, gx = tx0 - 2 + rx;
-        float v0 = 0.f, v1 = 0.f, v2 = 0.f, d = 0.f;
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f, d = 0.f, r0 = 0.f, r1 = 0.f;
         if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
           const float* p = tgt + ((long long)gy * W + gx) * 3;
           v0 = __ldg(p); v1 = __ldg(p + 1); v2 = __ldg(p + 2);
           d = __ldg(dep + (long long)gy * W + gx);
+          // reference order (SURVEY A.2).  The last rows of K_s and inv(K_s) are exactly (0,0,1)
+          // (synthesize_base.py:66-71), so ray.z = 1 and p.z = Y.z hold bit-exactly and are not recomputed.
+          const float fx = (float)gx, fy = (float)gy;
+          r0 = gk[9] * fx + gk[10] * fy + gk[11];
+          r1 = gk[12] * fx + gk[13] * fy + gk[14];
         }
         sx[i] = v0; sx[kFRegion + i] = v1; sx[2 * kFRegion + i] = v2;
-        sD[i] = d;
+        sD[i] = d; sR0[i] = r0; sR1[i] = r1;
       }
     }
   }
@@ -262,25 +281,27 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
   }
 
   // ---- per-strip invariants of the S phase ------------------------------------------------------
-  float2 inv_cnt, s_in, s_centre;          // per pixel of the strip: 1/#taps, in-image (0/1), counted in the loss (0/1)
+  const float cl1 = a.gcoef_l1 * a.norm_photo[l];
+  const float hss2 = -a.gcoef_ssim * a.norm_photo[l];           // 2 * dTotal/d ssim at a contributing pixel
+  float2 inv_cnt, s_hc, s_centre;          // per pixel of the strip: 1/#taps, in-image * hss2/#taps, counted in the loss (0/1)
   {
     const int gy = ty0 - 1 + qy;
     const bool row_in = s_active && gy >= 0 && gy < H;
     const int cy = min(gy + 1, H - 1) - max(gy - 1, 0) + 1;
-    float iv[2], in[2], ce[2];
+    float iv[2], ce[2];
 #pragma unroll
     for (int o = 0; o < 2; ++o) {
       const int q = q0 + o, gx = tx0 - 1 + q;
       const bool inb = row_in && q < kFSW && gx >= 0 && gx < W;
       const int cx = min(gx + 1, W - 1) - max(gx - 1, 0) + 1;
       iv[o] = inb ? box_inv(cy * cx) : 0.f;
-      in[o] = inb ? 1.f : 0.f;
       ce[o] = (inb && qy >= 1 && qy <= kFCH && q >= 1 && q <= kFCW) ? 1.f : 0.f;
     }
-    inv_cnt = f2(iv[0], iv[1]); s_in = f2(in[0], in[1]); s_centre = f2(ce[0], ce[1]);
+    inv_cnt = f2(iv[0], iv[1]); s_centre = f2(ce[0], ce[1]);
+    s_hc = f2(iv[0] * hss2, iv[1] * hss2);                       // 0 outside the image (iv = 0)
   }
   // window statistics of the target (x) for this strip: evaluated once, kept across the N sources
-  // (premixed with the SSIM constants: mux, 2*mux, mux^2 + c1, sigma_x + c2)
+  // (premixed with the SSIM constants: mux, mux^2 + c1, sigma_x + c2)
   float2 MUX[3], MUX2C[3], SGXC[3];
   if (a.do_ssim && s_active) {
 #pragma unroll
@@ -290,8 +311,8 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
       const float2 a2 = lds2(px + 2 * kFP), b2 = lds2(px + 2 * kFP + 2);
       const float2 v1a = f2add(f2add(a0, a1), a2), v1b = f2add(f2add(b0, b1), b2);
       const float2 v2a = f2fma(a2, a2, f2fma(a1, a1, f2mul(a0, a0))), v2b = f2fma(b2, b2, f2fma(b1, b1, f2mul(b0, b0)));
-      const float2 s1 = f2((v1a.x + v1a.y) + v1b.x, (v1a.y + v1b.x) + v1b.y);
-      const float2 s2 = f2((v2a.x + v2a.y) + v2b.x, (v2a.y + v2b.x) + v2b.y);
+      const float2 s1 = hsum3(v1a, v1b);
+      const float2 s2 = hsum3(v2a, v2b);
       const float2 mu = f2mul(s1, inv_cnt);
       const float2 mu2 = f2mul(mu, mu);
       MUX[c] = mu;
@@ -301,8 +322,6 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
   }
 
   float gD[2] = {0.f, 0.f};
-  const float cl1 = a.gcoef_l1 * a.norm_photo[l];
-  const float hss = -0.5f * a.gcoef_ssim * a.norm_photo[l];     // dTotal/d ssim at a contributing pixel
 
   for (int n = 0; n < a.N; ++n) {
     const float* const gt = c_geo + a.geo_t_off + (bl * a.N + n) * kGeoT;   // [R|t]: uniform registers
@@ -314,60 +333,51 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
       const int i = tid + it * kFThreads;
       if (i < kFRegion) {
         const int ry = i / kFP, rx = i - ry * kFP;
-        const int gy = ty0 - 2 + ry, gx = tx0 - 2 + rx;
-        const bool centre = ry >= 2 && ry < 2 + kFCH && rx >= 2 && rx < 2 + kFCW;
+        const bool centre = (unsigned)(ry - 2) < (unsigned)kFCH && (unsigned)(rx - 2) < (unsigned)kFCW;
         float yv[3] = {0.f, 0.f, 0.f};
         float gu[3] = {0.f, 0.f, 0.f}, gv[3] = {0.f, 0.f, 0.f};
         float su = 0.f, sv = 0.f, si = 0.f;
-        bool valid = false;
-        const bool inimg = gy >= 0 && gy < H && gx >= 0 && gx < W;
-        if (inimg) {
-          const float D = sD[i];
-          // reference order (SURVEY A.2).  The last rows of K_s and inv(K_s) are exactly (0,0,1)
-          // (synthesize_base.py:66-71), so ray.z = 1 and p.z = Y.z hold bit-exactly and are not recomputed.
-          const float fx = (float)gx, fy = (float)gy;
-          const float r0 = gk[9] * fx + gk[10] * fy + gk[11];
-          const float r1 = gk[12] * fx + gk[13] * fy + gk[14];
-          const float X0 = r0 * D, X1 = r1 * D, X2 = D;
-          const float Y0 = gt[0] * X0 + gt[1] * X1 + gt[2] * X2 + gt[9];
-          const float Y1 = gt[3] * X0 + gt[4] * X1 + gt[5] * X2 + gt[10];
-          const float Y2 = gt[6] * X0 + gt[7] * X1 + gt[8] * X2 + gt[11];
-          const float p0 = gk[0] * Y0 + gk[1] * Y1 + gk[2] * Y2;
-          const float p1 = gk[3] * Y0 + gk[4] * Y1 + gk[5] * Y2;
-          Proj pr;
-          pr.den = Y2 + 1e-10f;
-          float inv_den;
-          div_pair(p0, p1, pr.den, pr.u, pr.v, inv_den);
-          const Taps tp = make_taps(pr.u, pr.v, D, W, H);
-          valid = tp.valid;
-          if (valid) {
-            float I0[3], I1[3], I2[3], I3[3];
-            gather_taps(img, W, tp, I0, I1, I2, I3);
-            const float w0 = tp.w_uf * tp.w_vf, w1 = tp.w_uf * tp.w_vc, w2 = tp.w_uc * tp.w_vf, w3 = tp.w_uc * tp.w_vc;
+        const float D = sD[i];
+        const float X0 = sR0[i] * D, X1 = sR1[i] * D, X2 = D;
+        const float Y0 = gt[0] * X0 + gt[1] * X1 + gt[2] * X2 + gt[9];
+        const float Y1 = gt[3] * X0 + gt[4] * X1 + gt[5] * X2 + gt[10];
+        const float Y2 = gt[6] * X0 + gt[7] * X1 + gt[8] * X2 + gt[11];
+        const float p0 = gk[0] * Y0 + gk[1] * Y1 + gk[2] * Y2;
+        const float p1 = gk[3] * Y0 + gk[4] * Y1 + gk[5] * Y2;
+        const float den = Y2 + 1e-10f;
+        float pu, pv, inv_den;
+        div_pair(p0, p1, den, pu, pv, inv_den);
+        const Taps tp = make_taps(pu, pv, D, W, H);
+        if (tp.valid) {
+          float I0[3], I1[3], I2[3], I3[3];
+          gather_taps(img, W, tp, I0, I1, I2, I3);
+          const float w0 = tp.w_uf * tp.w_vf, w1 = tp.w_uf * tp.w_vc, w2 = tp.w_uc * tp.w_vf, w3 = tp.w_uc * tp.w_vc;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) yv[c] = ((I0[c] * w0 + I1[c] * w1) + I2[c] * w2) + I3[c] * w3;
-            if (GRAD && centre) {
+          for (int c = 0; c < 3; ++c) yv[c] = ((I0[c] * w0 + I1[c] * w1) + I2[c] * w2) + I3[c] * w3;
+          if (GRAD && centre) {
 #pragma unroll
-              for (int c = 0; c < 3; ++c) {
-                gu[c] = tp.w_vf * (I2[c] - I0[c]) + tp.w_vc * (I3[c] - I1[c]);
-                gv[c] = tp.w_uf * (I1[c] - I0[c]) + tp.w_uc * (I3[c] - I2[c]);
-              }
-              su = pr.u; sv = pr.v; si = inv_den;
+            for (int c = 0; c < 3; ++c) {
+              gu[c] = tp.w_vf * (I2[c] - I0[c]) + tp.w_vc * (I3[c] - I1[c]);
+              gv[c] = tp.w_uf * (I1[c] - I0[c]) + tp.w_uc * (I3[c] - I2[c]);
             }
+            su = pu; sv = pv; si = inv_den;
           }
         }
         sy[i] = yv[0]; sy[kFRegion + i] = yv[1]; sy[2 * kFRegion + i] = yv[2];
         if (centre) {
           if (GRAD) {
-            const int ci = (ry - 2) * kFCP + (rx - 2);
+            const int ci = i - (2 * kFP + 2) - (ry - 2) * (kFP - kFCP);
             sGU[ci] = gu[0]; sGU[kFCentre + ci] = gu[1]; sGU[2 * kFCentre + ci] = gu[2];
             sGV[ci] = gv[0]; sGV[kFCentre + ci] = gv[1]; sGV[2 * kFCentre + ci] = gv[2];
             sU[ci] = su; sV[ci] = sv; sI[ci] = si;
           }
-          if (OUT && inimg) {
-            const long long o = (long long)(b * a.N + n) * P + gy * W + gx;
-            if (a.synth_out[l]) { float* so = a.synth_out[l] + o * 3; so[0] = yv[0]; so[1] = yv[1]; so[2] = yv[2]; }
-            if (a.mask_out[l]) a.mask_out[l][o] = valid ? 1.f : 0.f;
+          if (OUT) {
+            const int gy = ty0 - 2 + ry, gx = tx0 - 2 + rx;
+            if (gy < H && gx < W) {
+              const long long o = (long long)(b * a.N + n) * P + gy * W + gx;
+              if (a.synth_out[l]) { float* so = a.synth_out[l] + o * 3; so[0] = yv[0]; so[1] = yv[1]; so[2] = yv[2]; }
+              if (a.mask_out[l]) a.mask_out[l][o] = tp.valid ? 1.f : 0.f;
+            }
           }
         }
       }
@@ -378,16 +388,16 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
     if (s_active) {
       // the strip's pixels sit at region (qy+1, q0+1) and (qy+1, q0+2)
       const int mid = (qy + 1) * kFP + q0;
-      float2 live, cnt_w;       // live: in-image and not black; cnt_w: counted in the loss and not black
+      float2 hlive, cnt_w;      // hlive: hss2/#taps where in-image and not black; cnt_w: counted in the loss and not black
       {
         // mean_c(synth) == 0 (loss_util.py:15-16)
         const float2 m0a = lds2(sy + mid), m0b = lds2(sy + mid + 2);
         const float2 m1a = lds2(sy + kFRegion + mid), m1b = lds2(sy + kFRegion + mid + 2);
         const float2 m2a = lds2(sy + 2 * kFRegion + mid), m2b = lds2(sy + 2 * kFRegion + mid + 2);
-        const float nb0 = (((m0a.y + m1a.y) + m2a.y) == 0.f) ? 0.f : 1.f;
-        const float nb1 = (((m0b.x + m1b.x) + m2b.x) == 0.f) ? 0.f : 1.f;
-        live = f2(s_in.x * nb0, s_in.y * nb1);
-        cnt_w = f2(s_centre.x * nb0, s_centre.y * nb1);
+        const bool bk0 = ((m0a.y + m1a.y) + m2a.y) == 0.f;
+        const bool bk1 = ((m0b.x + m1b.x) + m2b.x) == 0.f;
+        hlive = f2(bk0 ? 0.f : s_hc.x, bk1 ? 0.f : s_hc.y);
+        cnt_w = f2(bk0 ? 0.f : s_centre.x, bk1 ? 0.f : s_centre.y);
       }
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
@@ -407,9 +417,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
           const float2 v2b = f2fma(yb2, yb2, f2fma(yb1, yb1, f2mul(yb0, yb0)));
           const float2 v3a = f2fma(xa2, ya2, f2fma(xa1, ya1, f2mul(xa0, ya0)));
           const float2 v3b = f2fma(xb2, yb2, f2fma(xb1, yb1, f2mul(xb0, yb0)));
-          const float2 s1 = f2((v1a.x + v1a.y) + v1b.x, (v1a.y + v1b.x) + v1b.y);
-          const float2 s2 = f2((v2a.x + v2a.y) + v2b.x, (v2a.y + v2b.x) + v2b.y);
-          const float2 s3 = f2((v3a.x + v3a.y) + v3b.x, (v3a.y + v3b.x) + v3b.y);
+          const float2 s1 = hsum3(v1a, v1b), s2 = hsum3(v2a, v2b), s3 = hsum3(v3a, v3b);
           const float2 mux = MUX[c];
           const float2 muy = f2mul(s1, inv_cnt);
           const float2 muy2 = f2mul(muy, muy);
@@ -424,20 +432,21 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
           const float2 r12 = f2(rcp_nr(den.x), rcp_nr(den.y));
           const float2 ssim = f2mul(f2mul(a1, a2), r12);
           const float2 lv = f2fma(f2s(-0.5f), ssim, f2s(0.5f));
-          lsum_ssim = fmaf(cnt_w.x, fminf(fmaxf(lv.x, 0.f), 1.f), lsum_ssim);
-          lsum_ssim = fmaf(cnt_w.y, fminf(fmaxf(lv.y, 0.f), 1.f), lsum_ssim);
+          const float lc0 = fminf(fmaxf(lv.x, 0.f), 1.f), lc1 = fminf(fmaxf(lv.y, 0.f), 1.f);
+          lsum_ssim = fmaf(cnt_w.x, lc0, lsum_ssim);
+          lsum_ssim = fmaf(cnt_w.y, lc1, lsum_ssim);
           if (GRAD) {
-            // clip_by_value passes the gradient inside [0,1]; h = dTotal/d ssim / #taps, 0 where dead
-            const float2 pass = f2((lv.x >= 0.f && lv.x <= 1.f) ? live.x : 0.f, (lv.y >= 0.f && lv.y <= 1.f) ? live.y : 0.f);
-            const float2 hi = f2mul(f2mul(pass, inv_cnt), f2s(hss));
-            const float2 rb1 = f2mul(r12, b2), rb2 = f2mul(r12, b1);        // 1/b1, 1/b2
-            const float2 hr = f2mul(hi, r12);
-            // A = hi * ( 2 mux (a2 - a1) r12 - ssim * 2 muy (1/b1 - 1/b2) )
-            const float2 t1 = f2mul(f2add(mux, mux), f2add(a2, f2neg(a1)));
-            const float2 t2 = f2mul(f2mul(ssim, f2add(muy, muy)), f2add(rb1, f2neg(rb2)));
-            const float2 Av = f2fma(hr, t1, f2neg(f2mul(hi, t2)));
-            const float2 Bv = f2neg(f2mul(f2mul(hi, ssim), rb2));
-            const float2 Cv = f2mul(hr, f2add(a1, a1));
+            // clip_by_value passes the gradient inside [0,1] (there the clamp is the identity).
+            // With Hh = 2 h / (#taps b1 b2), h = dTotal/d ssim:
+            //   dL/dP(xy) = Hh a1,  2 dL/dP(y^2) = -Hh ssim b1,
+            //   dL/dmu_y  = Hh [ mux (a2 - a1) - ssim muy (b2 - b1) ]
+            const float2 Hh = f2mul(f2(lc0 == lv.x ? hlive.x : 0.f, lc1 == lv.y ? hlive.y : 0.f), r12);
+            const float2 Hs = f2mul(Hh, ssim);
+            const float2 t1 = f2mul(mux, f2add(a2, f2neg(a1)));
+            const float2 t2 = f2mul(muy, f2add(b2, f2neg(b1)));
+            const float2 Av = f2fma(Hh, t1, f2neg(f2mul(Hs, t2)));
+            const float2 Bv = f2mul(f2neg(Hs), b1);
+            const float2 Cv = f2mul(Hh, a1);
             const int so = c * kFStats + qy * kFP + q0;
             *reinterpret_cast<float2*>(sA + so) = Av;
             *reinterpret_cast<float2*>(sB + so) = Bv;
@@ -450,40 +459,43 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
     // ---- phase G: dL/dS on the centre strip, pushed through the bilinear + projection adjoint ------
     if (GRAD) {
       __syncthreads();
-      float acc[16];
+      if (g_active) {                       // warp-uniform: warps 0..12 own one centre row each
+        float acc[16];
 #pragma unroll
-      for (int k = 0; k < 16; ++k) acc[k] = 0.f;
-      if (g_active) {
-        const int gy = ty0 + cyy;
+        for (int k = 0; k < 16; ++k) acc[k] = 0.f;
         const int rrow = (cyy + 2) * kFP + c0 + 2;      // centre pixel in region coordinates
-        float2 yv[3], xv[3], g[3];
+        float2 g[3];
+        {
+          float2 yv[3], xv[3];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) { yv[c] = lds2(sy + c * kFRegion + rrow); xv[c] = lds2(sx + c * kFRegion + rrow); }
-        const float2 nb = f2((((yv[0].x + yv[1].x) + yv[2].x) == 0.f) ? 0.f : 1.f,
-                             (((yv[0].y + yv[1].y) + yv[2].y) == 0.f) ? 0.f : 1.f);
+          for (int c = 0; c < 3; ++c) { yv[c] = lds2(sy + c * kFRegion + rrow); xv[c] = lds2(sx + c * kFRegion + rrow); }
+          // L1 term: cl1 * sign(y - x), 0 where the synthesised pixel is black
+          const float2 nbc = f2((((yv[0].x + yv[1].x) + yv[2].x) == 0.f) ? 0.f : cl1,
+                                (((yv[0].y + yv[1].y) + yv[2].y) == 0.f) ? 0.f : cl1);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          float2 gc = f2s(0.f);
-          if (a.do_ssim) {
-            // centre (cyy, c0+o) = statistics (cyy+1, c0+o+1): window = statistics rows cyy..cyy+2, cols c0+o..c0+o+2
-            const int so = c * kFStats + cyy * kFP + c0;
-            float2 va, vb;
-            va = f2add(f2add(lds2(sA + so), lds2(sA + so + kFP)), lds2(sA + so + 2 * kFP));
-            vb = f2add(f2add(lds2(sA + so + 2), lds2(sA + so + kFP + 2)), lds2(sA + so + 2 * kFP + 2));
-            const float2 sa = f2((va.x + va.y) + vb.x, (va.y + vb.x) + vb.y);
-            va = f2add(f2add(lds2(sB + so), lds2(sB + so + kFP)), lds2(sB + so + 2 * kFP));
-            vb = f2add(f2add(lds2(sB + so + 2), lds2(sB + so + kFP + 2)), lds2(sB + so + 2 * kFP + 2));
-            const float2 sb = f2((va.x + va.y) + vb.x, (va.y + vb.x) + vb.y);
-            va = f2add(f2add(lds2(sC + so), lds2(sC + so + kFP)), lds2(sC + so + 2 * kFP));
-            vb = f2add(f2add(lds2(sC + so + 2), lds2(sC + so + kFP + 2)), lds2(sC + so + 2 * kFP + 2));
-            const float2 sc = f2((va.x + va.y) + vb.x, (va.y + vb.x) + vb.y);
-            gc = f2fma(f2add(yv[c], yv[c]), sb, f2fma(xv[c], sc, sa));
+          for (int c = 0; c < 3; ++c) {
+            float2 gc = f2s(0.f);
+            if (a.do_ssim) {
+              // centre (cyy, c0+o) = statistics (cyy+1, c0+o+1): window = statistics rows cyy..cyy+2, cols c0+o..c0+o+2
+              const int so = c * kFStats + cyy * kFP + c0;
+              float2 va, vb;
+              va = f2add(f2add(lds2(sA + so), lds2(sA + so + kFP)), lds2(sA + so + 2 * kFP));
+              vb = f2add(f2add(lds2(sA + so + 2), lds2(sA + so + kFP + 2)), lds2(sA + so + 2 * kFP + 2));
+              const float2 sa = hsum3(va, vb);
+              va = f2add(f2add(lds2(sB + so), lds2(sB + so + kFP)), lds2(sB + so + 2 * kFP));
+              vb = f2add(f2add(lds2(sB + so + 2), lds2(sB + so + kFP + 2)), lds2(sB + so + 2 * kFP + 2));
+              const float2 sb = hsum3(va, vb);
+              va = f2add(f2add(lds2(sC + so), lds2(sC + so + kFP)), lds2(sC + so + 2 * kFP));
+              vb = f2add(f2add(lds2(sC + so + 2), lds2(sC + so + kFP + 2)), lds2(sC + so + 2 * kFP + 2));
+              const float2 sc = hsum3(va, vb);
+              gc = f2fma(yv[c], sb, f2fma(xv[c], sc, sa));       // sB holds 2 dL/dP(y^2)
+            }
+            if (a.do_l1) {
+              const float2 d = f2add(yv[c], f2neg(xv[c]));
+              gc = f2add(gc, f2(d.x == 0.f ? 0.f : copysignf(nbc.x, d.x), d.y == 0.f ? 0.f : copysignf(nbc.y, d.y)));
+            }
+            g[c] = gc;
           }
-          if (a.do_l1) {
-            const float2 sg = f2(sgnf(yv[c].x - xv[c].x), sgnf(yv[c].y - xv[c].y));
-            gc = f2fma(f2mul(nb, f2s(cl1)), sg, gc);
-          }
-          g[c] = gc;
         }
         const int ci = cyy * kFCP + c0;
         float2 gu2 = f2s(0.f), gv2 = f2s(0.f);
@@ -493,64 +505,69 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
           gv2 = f2fma(g[c], lds2(sGV + c * kFCentre + ci), gv2);
         }
         const float2 U2 = lds2(sU + ci), V2 = lds2(sV + ci), I2v = lds2(sI + ci);
-        const float2 D2 = lds2(sD + rrow);
-        const float gus[2] = {gu2.x, gu2.y}, gvs[2] = {gv2.x, gv2.y};
-        const float Us[2] = {U2.x, U2.y}, Vs[2] = {V2.x, V2.y}, Is[2] = {I2v.x, I2v.y}, Ds[2] = {D2.x, D2.y};
+        const float2 D2 = lds2(sD + rrow), R02 = lds2(sR0 + rrow), R12 = lds2(sR1 + rrow);
+        // samples without a valid warp (incl. everything outside the image) cached zero Jacobians and 1/den = 0:
+        // their contributions below are exact zeros, so no bounds test is needed
+        const float2 gp0 = f2mul(gu2, I2v), gp1 = f2mul(gv2, I2v);
+        const float2 gp2 = f2mul(f2neg(f2fma(gv2, V2, f2mul(gu2, U2))), I2v);
+        const float2 X02 = f2mul(R02, D2), X12 = f2mul(R12, D2);
+        const float gp0s[2] = {gp0.x, gp0.y}, gp1s[2] = {gp1.x, gp1.y}, gp2s[2] = {gp2.x, gp2.y};
+        const float X0s[2] = {X02.x, X02.y}, X1s[2] = {X12.x, X12.y}, Ds[2] = {D2.x, D2.y};
+        const float r0s[2] = {R02.x, R02.y}, r1s[2] = {R12.x, R12.y};
 #pragma unroll
         for (int o = 0; o < 2; ++o) {
-          const int gx = tx0 + c0 + o;
-          if (gy < H && gx < W) {
-            const float gu = gus[o], gv = gvs[o], D = Ds[o], inv = Is[o];
-            const float fx = (float)gx, fy = (float)gy;
-            const float r0 = gk[9] * fx + gk[10] * fy + gk[11];
-            const float r1 = gk[12] * fx + gk[13] * fy + gk[14];
-            const float X0 = r0 * D, X1 = r1 * D, X2 = D;
-            const float gp0 = gu * inv, gp1 = gv * inv, gp2 = -(gu * Us[o] + gv * Vs[o]) * inv;
-            const float gY0 = gk[0] * gp0 + gk[3] * gp1;          // K_s^T with last row (0,0,1)
-            const float gY1 = gk[1] * gp0 + gk[4] * gp1;
-            const float gY2 = gk[2] * gp0 + gk[5] * gp1 + gp2;
-            acc[0] += gY0 * X0; acc[1] += gY0 * X1; acc[2] += gY0 * X2;
-            acc[3] += gY1 * X0; acc[4] += gY1 * X1; acc[5] += gY1 * X2;
-            acc[6] += gY2 * X0; acc[7] += gY2 * X1; acc[8] += gY2 * X2;
-            acc[9] += gY0; acc[10] += gY1; acc[11] += gY2;
-            const float gX0 = gt[0] * gY0 + gt[3] * gY1 + gt[6] * gY2;
-            const float gX1 = gt[1] * gY0 + gt[4] * gY1 + gt[7] * gY2;
-            const float gX2 = gt[2] * gY0 + gt[5] * gY1 + gt[8] * gY2;
-            gD[o] += gX0 * r0 + gX1 * r1 + gX2;
-            if (DSRC && a.d_src[l]) {
-              // dL/dsource: re-derive the taps from the cached coordinates (bit-identical to the forward)
-              const Taps tp = make_taps(Us[o], Vs[o], D, W, H);
-              if (tp.valid && inv != 0.f) {
-                float* dimg = a.d_src[l] + b * a.d_src_bs[l] + n * a.d_src_fs[l];
-                const float w0 = tp.w_uf * tp.w_vf, w1 = tp.w_uf * tp.w_vc, w2 = tp.w_uc * tp.w_vf, w3 = tp.w_uc * tp.w_vc;
-                float* p = dimg + ((long long)tp.iv * W + tp.iu) * 3;
-                float* q = p + (long long)W * 3;
-                const float gs[3] = {o ? g[0].y : g[0].x, o ? g[1].y : g[1].x, o ? g[2].y : g[2].x};
+          const float X0 = X0s[o], X1 = X1s[o], X2 = Ds[o];
+          const float gY0 = gk[0] * gp0s[o] + gk[3] * gp1s[o];          // K_s^T with last row (0,0,1)
+          const float gY1 = gk[1] * gp0s[o] + gk[4] * gp1s[o];
+          const float gY2 = gk[2] * gp0s[o] + gk[5] * gp1s[o] + gp2s[o];
+          acc[0] += gY0 * X0; acc[1] += gY0 * X1; acc[2] += gY0 * X2;
+          acc[3] += gY1 * X0; acc[4] += gY1 * X1; acc[5] += gY1 * X2;
+          acc[6] += gY2 * X0; acc[7] += gY2 * X1; acc[8] += gY2 * X2;
+          acc[9] += gY0; acc[10] += gY1; acc[11] += gY2;
+          const float gX0 = gt[0] * gY0 + gt[3] * gY1 + gt[6] * gY2;
+          const float gX1 = gt[1] * gY0 + gt[4] * gY1 + gt[7] * gY2;
+          const float gX2 = gt[2] * gY0 + gt[5] * gY1 + gt[8] * gY2;
+          gD[o] += gX0 * r0s[o] + gX1 * r1s[o] + gX2;
+          if (DSRC && a.d_src[l]) {
+            // dL/dsource: re-derive the taps from the cached coordinates (bit-identical to the forward)
+            const float Us = o ? U2.y : U2.x, Vs = o ? V2.y : V2.x, inv = o ? I2v.y : I2v.x;
+            const Taps tp = make_taps(Us, Vs, Ds[o], W, H);
+            if (tp.valid && inv != 0.f) {
+              float* dimg = a.d_src[l] + b * a.d_src_bs[l] + n * a.d_src_fs[l];
+              const float w0 = tp.w_uf * tp.w_vf, w1 = tp.w_uf * tp.w_vc, w2 = tp.w_uc * tp.w_vf, w3 = tp.w_uc * tp.w_vc;
+              float* p = dimg + ((long long)tp.iv * W + tp.iu) * 3;
+              float* q = p + (long long)W * 3;
+              const float gs[3] = {o ? g[0].y : g[0].x, o ? g[1].y : g[1].x, o ? g[2].y : g[2].x};
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                  atomicAdd(p + c, w0 * gs[c]);
-                  atomicAdd(p + 3 + c, w2 * gs[c]);
-                  atomicAdd(q + c, w1 * gs[c]);
-                  atomicAdd(q + 3 + c, w3 * gs[c]);
-                }
+              for (int c = 0; c < 3; ++c) {
+                atomicAdd(p + c, w0 * gs[c]);
+                atomicAdd(p + 3 + c, w2 * gs[c]);
+                atomicAdd(q + c, w1 * gs[c]);
+                atomicAdd(q + 3 + c, w3 * gs[c]);
               }
             }
           }
         }
-      }
-      // 12 pose accumulators: warp reduction in 16 shuffles, then one deterministic cross-warp sum
-      const float tot = warp_reduce16(acc, lane);
-      if ((lane & 1) == 0)
-        red[wid * 16 + (((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1))] = tot;
-      __syncthreads();
-      if (tid < 12) {
-        float v = 0.f;
-#pragma unroll
-        for (int w = 0; w < kFThreads / 32; ++w) v += red[w * 16 + tid];
-        a.pose_part[(((size_t)b * a.slots_per_b + slot) * a.N + n) * 12 + tid] = v;
+        // 12 pose accumulators: warp reduction in 16 shuffles; the cross-warp sum is deferred (below)
+        const float tot = warp_reduce16(acc, lane);
+        if ((lane & 1) == 0)
+          red[((n & (kFRedSrc - 1)) * kFCH + wid) * 16 +
+              (((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1))] = tot;
       }
     }
-    __syncthreads();      // sy / sA.. / sGU.. / red are rewritten by the next source
+    __syncthreads();      // sy / sA.. / sGU.. are rewritten by the next source; pose partials are complete
+    if (GRAD && ((n & (kFRedSrc - 1)) == kFRedSrc - 1 || n == a.N - 1)) {
+      // deterministic cross-warp sum of the buffered sources.  The buffer is next written in a later G phase,
+      // i.e. behind two more barriers that these threads also have to pass.
+      const int n0 = n & ~(kFRedSrc - 1);
+      const int k = tid >> 4, j = tid & 15;
+      if (k <= n - n0 && j < 12) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < kFCH; ++w) v += red[(k * kFCH + w) * 16 + j];
+        a.pose_part[(((size_t)b * a.slots_per_b + slot) * a.N + (n0 + k)) * 12 + j] = v;
+      }
+    }
   }
 
   if (GRAD && g_active && a.d_depth[l]) {
@@ -565,6 +582,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
   // ---- loss sums -> one partial record per tile -----------------------------------------------------
   {
     const float v0 = warp_sum(lsum_l1), v1 = warp_sum(lsum_ssim), v2 = warp_sum(lsum_sm);
+    __syncthreads();      // the last pose sum has read the scratch
     if (lane == 0) { red[wid * 3] = v0; red[wid * 3 + 1] = v1; red[wid * 3 + 2] = v2; }
     __syncthreads();
     if (tid < 3) {
