@@ -116,6 +116,7 @@ struct FusedArgs {
   int first_tile[kMaxScales + 1];
   const float* depth[kMaxScales];
   const float* disp[kMaxScales];
+  const float4* src4[kMaxScales];      // RGBx texels of the source levels [B,N,h,w] (written by the pyramid kernels)
   int do_l1, do_ssim, do_smooth;
   float norm_photo[kMaxScales];        // sw_s / (N*h*w*3)
   float norm_sm_x[kMaxScales];
@@ -217,8 +218,10 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
 
   // ---- strip coordinates ----------------------------------------------------------------
   // S phase: statistics row qy (0..14), columns q0, q0+1
-  const int qy = tid / kFSStrips, q0 = (tid - qy * kFSStrips) * 2;
-  const bool s_active = tid < kFSH * kFSStrips;
+  // warps 0..14 own one statistics row each (lane = strip: conflict-free 8-byte rows); the 33rd strip of
+  // every row goes to lanes 0..14 of warp 15
+  const int qy = wid < kFSH ? wid : lane, q0 = wid < kFSH ? lane * 2 : 2 * (kFSStrips - 1);
+  const bool s_active = wid < kFSH || lane < kFSH;
   // G phase: centre row cyy (0..12), columns c0, c0+1
   const int cyy = tid >> 5, c0 = (tid & 31) * 2;
   const bool g_active = cyy < kFCH;
@@ -299,6 +302,8 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
     }
     inv_cnt = f2(iv[0], iv[1]); s_centre = f2(ce[0], ce[1]);
     s_hc = f2(iv[0] * hss2, iv[1] * hss2);                       // 0 outside the image (iv = 0)
+    // keep the six values in registers: the compiler would otherwise re-derive them for every source
+    asm volatile("" : "+f"(inv_cnt.x), "+f"(inv_cnt.y), "+f"(s_hc.x), "+f"(s_hc.y), "+f"(s_centre.x), "+f"(s_centre.y));
   }
   // window statistics of the target (x) for this strip: evaluated once, kept across the N sources
   // (premixed with the SSIM constants: mux, mux^2 + c1, sigma_x + c2)
@@ -325,7 +330,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
 
   for (int n = 0; n < a.N; ++n) {
     const float* const gt = c_geo + a.geo_t_off + (bl * a.N + n) * kGeoT;   // [R|t]: uniform registers
-    const float* img = L.src + b * L.src_bs + n * L.src_fs;
+    const float4* const img4 = a.src4[l] + (size_t)(b * a.N + n) * P;
 
     // ---- phase Y: inverse warp of the region into shared memory ---------------------------------
 #pragma unroll
@@ -349,8 +354,10 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
         div_pair(p0, p1, den, pu, pv, inv_den);
         const Taps tp = make_taps(pu, pv, D, W, H);
         if (tp.valid) {
-          float I0[3], I1[3], I2[3], I3[3];
-          gather_taps(img, W, tp, I0, I1, I2, I3);
+          // four 16-byte texel loads: I0 = (vf,uf), I1 = (vc,uf), I2 = (vf,uc), I3 = (vc,uc)   (bilinear_interp.py:125-128)
+          const float4* tp0 = img4 + (tp.iv * W + tp.iu);
+          const float4 t0 = __ldg(tp0), t2 = __ldg(tp0 + 1), t1 = __ldg(tp0 + W), t3 = __ldg(tp0 + W + 1);
+          const float I0[3] = {t0.x, t0.y, t0.z}, I1[3] = {t1.x, t1.y, t1.z}, I2[3] = {t2.x, t2.y, t2.z}, I3[3] = {t3.x, t3.y, t3.z};
           const float w0 = tp.w_uf * tp.w_vf, w1 = tp.w_uf * tp.w_vc, w2 = tp.w_uc * tp.w_vf, w3 = tp.w_uc * tp.w_vc;
 #pragma unroll
           for (int c = 0; c < 3; ++c) yv[c] = ((I0[c] * w0 + I1[c] * w1) + I2[c] * w2) + I3[c] * w3;
@@ -390,7 +397,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
       const int mid = (qy + 1) * kFP + q0;
       float2 hlive, cnt_w;      // hlive: hss2/#taps where in-image and not black; cnt_w: counted in the loss and not black
       {
-        // mean_c(synth) == 0 (loss_util.py:15-16)
+        // mean_c(synth) == 0 (loss_util.py:15-16); the compiler merges these loads with the window rows below
         const float2 m0a = lds2(sy + mid), m0b = lds2(sy + mid + 2);
         const float2 m1a = lds2(sy + kFRegion + mid), m1b = lds2(sy + kFRegion + mid + 2);
         const float2 m2a = lds2(sy + 2 * kFRegion + mid), m2b = lds2(sy + 2 * kFRegion + mid + 2);

@@ -132,6 +132,7 @@ struct PyramidArgs {
   int S;                       // number of levels
   int s[kMaxScales];
   float* src_out[kMaxScales];  // [B,N,h,w,3] (NULL for s == 1)
+  float4* src4_out[kMaxScales];// [B,N,h,w] RGBx texels for the fused kernel's 16-byte gathers (all levels; NULL = not wanted)
   float* tgt_out[kMaxScales];  // [B,h,w,3]   (NULL = not wanted)
   int with_geometry;           // grid row S carries the camera geometry (overlaps with the pyramid rows)
   GeoArgs geo;
@@ -155,23 +156,27 @@ __global__ void k_pyramid(PyramidArgs a) {
   int f = (int)(r % nfr);
   int b = (int)(r / nfr);
   const float* in;
-  float* out;
+  float* out = nullptr;
+  float4* out4 = nullptr;
   if (f < a.N) {
-    if (a.src_out[l] == nullptr) return;
+    if (a.src_out[l] == nullptr && a.src4_out[l] == nullptr) return;
     in = a.source + b * a.src_bs + f * a.src_fs;
-    out = a.src_out[l] + (((long long)(b * a.N + f) * h + y) * w + x) * 3;
+    const long long o = ((long long)(b * a.N + f) * h + y) * w + x;
+    if (a.src_out[l]) out = a.src_out[l] + o * 3;
+    if (a.src4_out[l]) out4 = a.src4_out[l] + o;
   } else {
     if (a.tgt_out[l] == nullptr || a.target == nullptr) return;
     in = a.target + b * a.tgt_bs;
     out = a.tgt_out[l] + (((long long)b * h + y) * w + x) * 3;
   }
   const long long rowst = (long long)a.W * 3;
+  float v[3];
   if (s == 1) {
     const float* p = in + y * rowst + x * 3;
-    out[0] = p[0]; out[1] = p[1]; out[2] = p[2];
+    v[0] = p[0]; v[1] = p[1]; v[2] = p[2];
   } else if (s & 1) {
     const float* p = in + (long long)(y * s + s / 2) * rowst + (x * s + s / 2) * 3;
-    out[0] = p[0]; out[1] = p[1]; out[2] = p[2];
+    v[0] = p[0]; v[1] = p[1]; v[2] = p[2];
   } else {
     const float* p0 = in + (long long)(y * s + s / 2 - 1) * rowst + (x * s + s / 2 - 1) * 3;
     const float* p1 = p0 + rowst;
@@ -180,9 +185,11 @@ __global__ void k_pyramid(PyramidArgs a) {
       float tl = __ldg(p0 + c), tr = __ldg(p0 + 3 + c), bl = __ldg(p1 + c), br = __ldg(p1 + 3 + c);
       float top = tl + (tr - tl) * 0.5f;
       float bot = bl + (br - bl) * 0.5f;
-      out[c] = top + (bot - top) * 0.5f;
+      v[c] = top + (bot - top) * 0.5f;
     }
   }
+  if (out) { out[0] = v[0]; out[1] = v[1]; out[2] = v[2]; }
+  if (out4) *out4 = make_float4(v[0], v[1], v[2], 0.f);
 }
 
 // Fast path for scales within {1,2,4,8}: ONE pass over the full-resolution frames.  A CTA stages an
@@ -196,6 +203,7 @@ struct PyramidTiledArgs {
   const float* target; long long tgt_bs;       // target may be NULL
   int B, N, H, W;
   float* src_out[4];   // index = log2(s): [1] s=2, [2] s=4, [3] s=8 (NULL = level absent)
+  float4* src4_out[4]; // RGBx texels of the source levels, index = log2(s) incl. [0] = full resolution (NULL = not wanted)
   float* tgt_out[4];
   int with_geometry;
   GeoArgs geo;
@@ -233,6 +241,36 @@ __global__ void __launch_bounds__(kPyrThreads) k_pyramid_tiled(PyramidTiledArgs 
   }
   __syncthreads();
   const long long frame = is_tgt ? (long long)b : (long long)(b * a.N + f);
+  if (!is_tgt) {
+    // RGBx texels (16 bytes) of every source level for the fused kernel's 128-bit gathers
+#pragma unroll
+    for (int lg = 0; lg <= 3; ++lg) {
+      float4* o4 = a.src4_out[lg];
+      if (o4 == nullptr) continue;
+      const int s = 1 << lg;
+      const int oh = kPyrTH >> lg, ow = tw >> lg;
+      const int Hs = a.H >> lg, Ws = a.W >> lg;
+      o4 += (frame * Hs + (y0 >> lg)) * Ws + (x0 >> lg);
+      for (int e = threadIdx.x; e < oh * ow; e += kPyrThreads) {
+        const int oy = e / ow, ox = e - oy * ow;
+        float v[3];
+        if (lg == 0) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) v[c] = tile[oy][ox * 3 + c];
+        } else {
+          const int ry = oy * s + s / 2 - 1, rx = (ox * s + s / 2 - 1) * 3;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float tl = tile[ry][rx + c], tr = tile[ry][rx + 3 + c], bl = tile[ry + 1][rx + c], br = tile[ry + 1][rx + 3 + c];
+            const float top = tl + (tr - tl) * 0.5f;
+            const float bot = bl + (br - bl) * 0.5f;
+            v[c] = top + (bot - top) * 0.5f;
+          }
+        }
+        o4[(long long)oy * Ws + ox] = make_float4(v[0], v[1], v[2], 0.f);
+      }
+    }
+  }
 #pragma unroll
   for (int lg = 1; lg <= 3; ++lg) {
     float* outp = is_tgt ? a.tgt_out[lg] : a.src_out[lg];

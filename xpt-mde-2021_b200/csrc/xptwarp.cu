@@ -65,6 +65,7 @@ struct xpt_ctx {
   float* geoK;
   float* geoT;
   float* src_pyr[kMaxScales];   // s > 1
+  float* src4_pyr[kMaxScales];  // RGBx (16-byte) texels of every source level for k_fused's gathers; lazily allocated
   float* tgt_pyr[kMaxScales];   // s > 1
   float* loss_part;
   float* pose_part;
@@ -183,8 +184,12 @@ int launch_geometry(xpt_ctx* ctx, const float* pose, const float* intrinsic, flo
 }
 
 // source pyramid into the ctx (+ target pyramid into ctx or user buffers)
+// rgba: write the source levels (incl. full resolution) as RGBx texels for the fused kernel INSTEAD of the 3-channel levels
 int launch_pyramids(xpt_ctx* ctx, const xpt_frames* f, float* const target_ms[], bool want_source,
-                    cudaStream_t st, const float* geo_pose = nullptr) {
+                    cudaStream_t st, const float* geo_pose = nullptr, bool rgba = false) {
+  if (rgba)
+    for (int l = 0; l < ctx->S; ++l)
+      XPT_TRY(dev_alloc(ctx, &ctx->src4_pyr[l], (size_t)ctx->B * ctx->N * lvl_pix(ctx, l) * 4));
   // ---- fast path: scales within {1,2,4,8}, 16-byte aligned rows -> one tiled pass over the frames
   {
     bool ok = ctx->W % 8 == 0 && ctx->H % 8 == 0 && want_source;
@@ -201,9 +206,10 @@ int launch_pyramids(xpt_ctx* ctx, const xpt_frames* f, float* const target_ms[],
       bool any = false;
       for (int l = 0; l < ctx->S; ++l) {
         const int sc = ctx->s[l];
+        const int lg = sc == 1 ? 0 : (sc == 2 ? 1 : (sc == 4 ? 2 : 3));
+        if (rgba) { t.src4_out[lg] = reinterpret_cast<float4*>(ctx->src4_pyr[l]); any = true; }
         if (sc == 1) continue;
-        const int lg = sc == 2 ? 1 : (sc == 4 ? 2 : 3);
-        t.src_out[lg] = ctx->src_pyr[l];
+        if (!rgba) t.src_out[lg] = ctx->src_pyr[l];
         if (f->target) t.tgt_out[lg] = ctx->tgt_pyr[l];
         any = true;
       }
@@ -240,8 +246,9 @@ int launch_pyramids(xpt_ctx* ctx, const xpt_frames* f, float* const target_ms[],
   for (int l = 0; l < ctx->S; ++l) {
     a.s[l] = ctx->s[l];
     bool work = false;
+    if (rgba && want_source) { a.src4_out[l] = reinterpret_cast<float4*>(ctx->src4_pyr[l]); work = true; }
     if (ctx->s[l] > 1) {
-      if (want_source) { a.src_out[l] = ctx->src_pyr[l]; work = true; }
+      if (want_source && !rgba) { a.src_out[l] = ctx->src_pyr[l]; work = true; }
       if (f->target) { a.tgt_out[l] = ctx->tgt_pyr[l]; work = true; }
     } else if (f->target && target_ms && target_ms[l]) {
       a.tgt_out[l] = target_ms[l];      // level-0 copy for the caller
@@ -556,7 +563,7 @@ void xpt_destroy(xpt_ctx* ctx) {
   F(ctx->st_frames); F(ctx->st_K); F(ctx->st_pose); F(ctx->st_losses); F(ctx->st_loss_batch); F(ctx->st_dpose);
   F(ctx->st_dsource);
   for (int l = 0; l < kMaxScales; ++l) {
-    F(ctx->src_pyr[l]); F(ctx->tgt_pyr[l]); F(ctx->synth_scr[l]); F(ctx->gsynth_scr[l]); F(ctx->dsrc_lvl[l]);
+    F(ctx->src_pyr[l]); F(ctx->src4_pyr[l]); F(ctx->tgt_pyr[l]); F(ctx->synth_scr[l]); F(ctx->gsynth_scr[l]); F(ctx->dsrc_lvl[l]);
     F(ctx->st_depth[l]); F(ctx->st_disp[l]); F(ctx->st_ddepth[l]); F(ctx->st_ddisp[l]);
     F(ctx->st_synth[l]); F(ctx->st_mask[l]); F(ctx->st_target[l]);
   }
@@ -704,7 +711,8 @@ static int total_loss_impl(xpt_ctx* ctx, const xpt_frames* frames, const float* 
   const float gs = out->grad_scale;
   const float inv_gb = 1.0f / (float)c.global_batch;
 
-  XPT_TRY(launch_pyramids(ctx, frames, out->target_ms, true, st, pose));   // + camera geometry in the same launch
+  const bool fused = !(c.flags & XPT_FLAG_UNFUSED);
+  XPT_TRY(launch_pyramids(ctx, frames, out->target_ms, true, st, pose, fused));   // + camera geometry in the same launch
   LevelTable lt = make_levels(ctx, frames, nullptr);
 
   PhotoArgs a;
@@ -743,6 +751,7 @@ static int total_loss_impl(xpt_ctx* ctx, const xpt_frames* frames, const float* 
       fa.lt.lv[l].slot_base = ctx->ffirst_tile[l];
       fa.first_tile[l] = ctx->ffirst_tile[l];
       fa.depth[l] = a.depth[l]; fa.disp[l] = a.disp[l];
+      fa.src4[l] = reinterpret_cast<const float4*>(ctx->src4_pyr[l]);
       fa.norm_photo[l] = a.norm_photo[l]; fa.norm_sm_x[l] = a.norm_sm_x[l]; fa.norm_sm_y[l] = a.norm_sm_y[l];
       fa.synth_out[l] = a.synth_out[l]; fa.mask_out[l] = a.mask_out[l];
       fa.d_depth[l] = a.d_depth[l]; fa.d_disp[l] = a.d_disp[l];
