@@ -172,11 +172,11 @@ XPT_API int xpt_total_loss(xpt_ctx* ctx, const xpt_frames* frames,
 /* The same call with HOST buffers (pinned or pageable): copies inputs to
  * device staging owned by the ctx, runs xpt_total_loss, copies back the
  * outputs that are non-NULL, and synchronises before returning.  The batch is
- * cut into up to 4 chunks so that host->device copies, compute and
+ * cut into up to 8 chunks so that host->device copies, compute and
  * device->host copies of consecutive chunks overlap (copy streams inside the
  * ctx; compute on `stream`).  `frames` and all pointers in `out` are host
  * pointers here; losses of a pipelined call are the sum of the chunk losses
- * (same value up to fp32 rounding of the 4 partial sums).                     */
+ * (same value up to fp32 rounding of the partial sums).                     */
 XPT_API int xpt_total_loss_host(xpt_ctx* ctx, const xpt_frames* frames,
                         const float* const depth_ms[], const float* const disp_ms[],
                         const float* pose, const xpt_loss_outputs* out, void* stream);

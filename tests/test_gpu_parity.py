@@ -268,8 +268,11 @@ def test_full_size_properties(xw):
     assert np.abs(r1["synth_ms"][0][2:3].cpu().numpy() - ref["synth_ms"][0].numpy()).max() < IMG_TOL
 
 
-def test_host_buffer_entry_point(xw):
-    """xpt_total_loss_host (host pointers, copies inside) equals the device entry point."""
+@pytest.mark.parametrize("pinned", [False, True], ids=["pageable", "pinned"])
+def test_host_buffer_entry_point(xw, pinned):
+    """xpt_total_loss_host (host pointers, copies inside) equals the device entry point.  Pageable buffers
+    take the staged copies on the legacy stream; pinned ones are written through the device mapping and the
+    whole call is replayed as one CUDA graph from the third call on (all three calls are compared)."""
     import ctypes as C
     from xptwarp import _cabi
     g = load_case("case_small_t1")
@@ -277,30 +280,81 @@ def test_host_buffer_entry_point(xw):
     f, p = _to_cuda(feats, preds)
     plan = _plan_for(xw, f, p, lw, sw, gb)
     r = _run_total(plan, f, p, want_grad=True)
-    img = feats["image5d"].contiguous().pin_memory()
+    hold = (lambda t: t.contiguous().pin_memory()) if pinned else (lambda t: t.contiguous())
+    img = hold(feats["image5d"])
     B, F, H, W, _ = img.shape
     fr = _cabi.XptFrames()
     fr.source = img.data_ptr()
     fr.source_batch_stride, fr.source_frame_stride = img.stride(0), img.stride(1)
     fr.target = img.data_ptr() + (F - 1) * img.stride(1) * 4
     fr.target_batch_stride = img.stride(0)
-    K = feats["intrinsic"].contiguous()
+    K = hold(feats["intrinsic"])
     fr.intrinsic = K.data_ptr()
     out = _cabi.XptLossOutputs()
-    losses, d_pose = torch.zeros(4), torch.zeros(B, F - 1, 6)
-    d_depth = [torch.zeros_like(d) for d in preds["depth_ms"]]
+    losses, d_pose = hold(torch.zeros(4)), hold(torch.zeros(B, F - 1, 6))
+    d_depth = [hold(torch.zeros_like(d)) for d in preds["depth_ms"]]
+    d_disp = [hold(torch.zeros_like(d)) for d in preds["disp_ms"]]
     out.losses, out.d_pose, out.grad_scale = losses.data_ptr(), d_pose.data_ptr(), 1.0
     for s, t in enumerate(d_depth):
         out.d_depth_ms[s] = t.data_ptr()
-    pose = preds["pose"].contiguous()
-    _cabi.check(plan._lib.xpt_total_loss_host(
-        plan.handle, C.byref(fr), C.byref(_cabi.ptr_array([d.data_ptr() for d in preds["depth_ms"]])),
-        C.byref(_cabi.ptr_array([d.data_ptr() for d in preds["disp_ms"]])), pose.data_ptr(), C.byref(out), None))
-    # the host entry point pipelines the batch in chunks: losses are sums of chunk losses
-    assert relerr(losses.numpy(), r["losses"].cpu().numpy()) < 1e-6
-    assert torch.equal(d_pose, r["d_pose"].cpu())
+        out.d_disp_ms[s] = d_disp[s].data_ptr()
+    pose = hold(preds["pose"])
+    depth_h, disp_h = [hold(d) for d in preds["depth_ms"]], [hold(d) for d in preds["disp_ms"]]
+    side = torch.cuda.Stream()
+    stream = C.c_void_p(side.cuda_stream) if pinned else None
+    for call in range(3):
+        for t in (losses, d_pose, *d_depth, *d_disp):
+            t.zero_()
+        _cabi.check(plan._lib.xpt_total_loss_host(
+            plan.handle, C.byref(fr), C.byref(_cabi.ptr_array([d.data_ptr() for d in depth_h])),
+            C.byref(_cabi.ptr_array([d.data_ptr() for d in disp_h])), pose.data_ptr(), C.byref(out), stream))
+        # the host entry point pipelines the batch in chunks: losses are sums of chunk losses
+        assert relerr(losses.numpy(), r["losses"].cpu().numpy()) < 1e-6, call
+        assert torch.equal(d_pose, r["d_pose"].cpu()), call
+        for s in range(4):
+            assert torch.equal(d_depth[s], r["d_depth_ms"][s].cpu().reshape(d_depth[s].shape)), (call, s)
+            assert torch.equal(d_disp[s], r["d_disp_ms"][s].cpu().reshape(d_disp[s].shape)), (call, s)
+
+
+def test_host_pipeline_full_size(xw):
+    """BASELINE config 2 through the pipelined host entry point (8 chunks, two copy-in streams, results written
+    through the pinned mapping, whole call replayed as a graph): bit-identical per-snippet gradients."""
+    import ctypes as C
+    from xptwarp import _cabi
+    from oracle import xpt_oracle as orc
+    feats, preds = orc.make_inputs(8, 128, 384, seed=77)
+    lw, sw = orc.LOSS_RIGID_T1, orc.SCALE_WEIGHT_T1
+    f, p = _to_cuda(feats, preds)
+    plan = _plan_for(xw, f, p, lw, sw, 8)
+    r = _run_total(plan, f, p, want_grad=True)
+    pin = lambda t: t.contiguous().pin_memory()
+    img, K, pose = pin(feats["image5d"]), pin(feats["intrinsic"]), pin(preds["pose"])
+    depth_h, disp_h = [pin(d) for d in preds["depth_ms"]], [pin(d) for d in preds["disp_ms"]]
+    B, F, H, W, _ = img.shape
+    fr = _cabi.XptFrames()
+    fr.source, fr.source_batch_stride, fr.source_frame_stride = img.data_ptr(), img.stride(0), img.stride(1)
+    fr.target, fr.target_batch_stride = img.data_ptr() + (F - 1) * img.stride(1) * 4, img.stride(0)
+    fr.intrinsic = K.data_ptr()
+    out = _cabi.XptLossOutputs()
+    losses, d_pose = pin(torch.zeros(4)), pin(torch.zeros(B, F - 1, 6))
+    d_depth = [pin(torch.zeros_like(d)) for d in preds["depth_ms"]]
+    d_disp = [pin(torch.zeros_like(d)) for d in preds["disp_ms"]]
+    out.losses, out.d_pose, out.grad_scale = losses.data_ptr(), d_pose.data_ptr(), 1.0
     for s in range(4):
-        assert torch.equal(d_depth[s], r["d_depth_ms"][s].cpu().reshape(d_depth[s].shape))
+        out.d_depth_ms[s], out.d_disp_ms[s] = d_depth[s].data_ptr(), d_disp[s].data_ptr()
+    side = torch.cuda.Stream()
+    for call in range(3):
+        for t in (losses, d_pose, *d_depth, *d_disp):
+            t.zero_()
+        _cabi.check(plan._lib.xpt_total_loss_host(
+            plan.handle, C.byref(fr), C.byref(_cabi.ptr_array([d.data_ptr() for d in depth_h])),
+            C.byref(_cabi.ptr_array([d.data_ptr() for d in disp_h])), pose.data_ptr(), C.byref(out),
+            C.c_void_p(side.cuda_stream)))
+        assert relerr(losses.numpy(), r["losses"].cpu().numpy()) < 1e-6, call
+        assert torch.equal(d_pose, r["d_pose"].cpu()), call
+        for s in range(4):
+            assert torch.equal(d_depth[s], r["d_depth_ms"][s].cpu().reshape(d_depth[s].shape)), (call, s)
+            assert torch.equal(d_disp[s], r["d_disp_ms"][s].cpu().reshape(d_disp[s].shape)), (call, s)
 
 
 def test_dlpack_only_producer_and_errors(xw):

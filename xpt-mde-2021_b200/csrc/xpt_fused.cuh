@@ -17,6 +17,17 @@
 #pragma once
 #include "xpt_kernels.cuh"
 
+// XPT_EXP: timing ablations for profiles/ablate_variants.sh ONLY (results are wrong when non-zero):
+//   1 = no CTA barriers inside the source loop, 2 = skip phase Y, 4 = skip phase S, 8 = skip phase G
+#ifndef XPT_EXP
+#define XPT_EXP 0
+#endif
+#if XPT_EXP & 1
+#define XPT_SYNC() ((void)0)
+#else
+#define XPT_SYNC() __syncthreads()
+#endif
+
 namespace xpt {
 
 constexpr int kFCW = 64, kFCH = 13;            // centre tile
@@ -336,7 +347,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
 #pragma unroll
     for (int it = 0; it < kFYIters; ++it) {
       const int i = tid + it * kFThreads;
-      if (i < kFRegion) {
+      if (i < kFRegion && !(XPT_EXP & 2)) {
         const int ry = i / kFP, rx = i - ry * kFP;
         const bool centre = (unsigned)(ry - 2) < (unsigned)kFCH && (unsigned)(rx - 2) < (unsigned)kFCW;
         float yv[3] = {0.f, 0.f, 0.f};
@@ -389,10 +400,10 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
         }
       }
     }
-    __syncthreads();
+    XPT_SYNC();
 
     // ---- phase S: L1 + SSIM (and the SSIM adjoint coefficients) on a 2-pixel strip ----------------
-    if (s_active) {
+    if (s_active && !(XPT_EXP & 4)) {
       // the strip's pixels sit at region (qy+1, q0+1) and (qy+1, q0+2)
       const int mid = (qy + 1) * kFP + q0;
       float2 hlive, cnt_w;      // hlive: hss2/#taps where in-image and not black; cnt_w: counted in the loss and not black
@@ -465,8 +476,8 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
 
     // ---- phase G: dL/dS on the centre strip, pushed through the bilinear + projection adjoint ------
     if (GRAD) {
-      __syncthreads();
-      if (g_active) {                       // warp-uniform: warps 0..12 own one centre row each
+      XPT_SYNC();
+      if (g_active && !(XPT_EXP & 8)) {     // warp-uniform: warps 0..12 own one centre row each
         float acc[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) acc[k] = 0.f;
@@ -562,7 +573,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
               (((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1))] = tot;
       }
     }
-    __syncthreads();      // sy / sA.. / sGU.. are rewritten by the next source; pose partials are complete
+    XPT_SYNC();           // sy / sA.. / sGU.. are rewritten by the next source; pose partials are complete
     if (GRAD && ((n & (kFRedSrc - 1)) == kFRedSrc - 1 || n == a.N - 1)) {
       // deterministic cross-warp sum of the buffered sources.  The buffer is next written in a later G phase,
       // i.e. behind two more barriers that these threads also have to pass.

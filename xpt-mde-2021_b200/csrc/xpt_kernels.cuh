@@ -1247,6 +1247,31 @@ __global__ void __launch_bounds__(128) k_epilogue(EpilogueArgs a) {
   }
 }
 
+// device staging -> pinned host memory THROUGH its device mapping, 16 bytes per thread and fully coalesced
+// (each warp emits 512 contiguous bytes): the small outputs of the host-buffer entry point leave in one launch
+struct DrainArgs {
+  int n;
+  const float* src[16];
+  float* dst[16];
+  long long count[16];
+};
+
+__global__ void __launch_bounds__(256) k_drain(DrainArgs a) {
+  const int seg = blockIdx.y;
+  const float* __restrict__ src = a.src[seg];
+  float* __restrict__ dst = a.dst[seg];
+  const long long n = a.count[seg];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((((uintptr_t)src | (uintptr_t)dst) & 15u) == 0) {
+    const long long n4 = n >> 2;
+    for (long long i = t; i < n4; i += stride) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
+    for (long long i = (n4 << 2) + t; i < n; i += stride) dst[i] = src[i];
+  } else {
+    for (long long i = t; i < n; i += stride) dst[i] = src[i];
+  }
+}
+
 __global__ void k_fill(float* __restrict__ p, long long n, float v) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;

@@ -50,6 +50,8 @@ inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 }  // namespace
 
+constexpr int kMaxChunks = 8;   // pipeline depth of the host-buffer entry point
+
 struct xpt_ctx {
   xpt_config cfg;
   int S, B, N, H, W;
@@ -89,8 +91,10 @@ struct xpt_ctx {
   // pipelined host entry point: a child ctx for one batch chunk, copy streams, events
   xpt_ctx* child;
   cudaStream_t s_in, s_in2, s_out;
-  cudaEvent_t ev_small;
-  cudaEvent_t ev_in[4], ev_done[4];
+  cudaEvent_t ev_small, ev_fork, ev_join;
+  std::vector<GraphEntry>* host_graphs;   // whole xpt_total_loss_host calls (copies + compute), keyed by every pointer
+  bool host_warm;
+  cudaEvent_t ev_in[kMaxChunks], ev_done[kMaxChunks];
   float* h_losses;              // pinned [4][4]: a pageable destination would block the host per chunk
   // per-launch device timing of the dominant kernel (xpt_profile_*)
   std::vector<cudaEvent_t>* prof_events;
@@ -571,11 +575,16 @@ void xpt_destroy(xpt_ctx* ctx) {
   if (ctx->h_losses) cudaFreeHost(ctx->h_losses);
   if (ctx->s_in) {
     cudaStreamDestroy(ctx->s_in); cudaStreamDestroy(ctx->s_out); cudaStreamDestroy(ctx->s_in2); cudaEventDestroy(ctx->ev_small);
-    for (int k = 0; k < 4; ++k) { cudaEventDestroy(ctx->ev_in[k]); cudaEventDestroy(ctx->ev_done[k]); }
+    cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
+    for (int k = 0; k < kMaxChunks; ++k) { cudaEventDestroy(ctx->ev_in[k]); cudaEventDestroy(ctx->ev_done[k]); }
   }
   if (ctx->graphs) {
     for (auto& e : *ctx->graphs) cudaGraphExecDestroy(e.exec);
     delete ctx->graphs;
+  }
+  if (ctx->host_graphs) {
+    for (auto& e : *ctx->host_graphs) cudaGraphExecDestroy(e.exec);
+    delete ctx->host_graphs;
   }
   if (ctx->prof_events) {
     for (auto e : *ctx->prof_events) cudaEventDestroy(e);
@@ -919,8 +928,28 @@ int xpt_profile_end(xpt_ctx* ctx, float* ms_out, int capacity) {
   return n;
 }
 
-int xpt_total_loss_host(xpt_ctx* ctx, const xpt_frames* frames, const float* const depth_ms[],
-                        const float* const disp_ms[], const float* pose, const xpt_loss_outputs* out, void* stream) {
+// Enqueues one whole host-buffer call (copies in, chunked compute, copies out) on `stream` and the ctx's copy
+// streams; every side stream is forked from and joined back into `stream`, so the sequence can be captured
+// into ONE CUDA graph.  Returns the number of chunks in *nc_out.  No synchronisation in here.
+// XPT_HOST_TRACE=1: per-stage device timestamps of the (eager) host-buffer pipeline, printed to stderr
+struct HostTrace { bool on; cudaEvent_t t0, small_in, in[kMaxChunks], done[kMaxChunks], out_end; };
+static HostTrace g_trace = {};
+static bool host_trace_on() {
+  static int state = -1;
+  if (state < 0) {
+    const char* e = getenv("XPT_HOST_TRACE");
+    state = (e && e[0] == '1') ? 1 : 0;
+    if (state) {
+      cudaEventCreate(&g_trace.t0); cudaEventCreate(&g_trace.small_in); cudaEventCreate(&g_trace.out_end);
+      for (int k = 0; k < kMaxChunks; ++k) { cudaEventCreate(&g_trace.in[k]); cudaEventCreate(&g_trace.done[k]); }
+    }
+  }
+  return state == 1;
+}
+
+static int host_enqueue(xpt_ctx* ctx, const xpt_frames* frames, const float* const depth_ms[],
+                        const float* const disp_ms[], const float* pose, const xpt_loss_outputs* out, void* stream,
+                        int* nc_out) {
   if (!ctx || !pose || !out) return fail(XPT_BAD_ARGUMENT, "xpt_total_loss_host: NULL argument");
   if (!out->losses) return fail(XPT_BAD_ARGUMENT, "out->losses is NULL");
   XPT_TRY(check_frames(ctx, frames, true));
@@ -938,17 +967,20 @@ int xpt_total_loss_host(xpt_ctx* ctx, const xpt_frames* frames, const float* con
   // ---- pipeline: the batch is cut into chunks; chunk k+1's host->device copies run on a copy-in
   // stream while chunk k computes on the caller's stream and chunk k-1's results drain on a copy-out
   // stream (snippets are independent; every chunk normalises by the global batch, so chunk losses add).
+  // The link is the bottleneck (the frames are ~70 B per pixel), so what is exposed is the LAST chunk's compute
+  // and drain: use the deepest pipeline whose chunks still hold >= 64 Ki pixels (a smaller chunk no longer fills the GPU: its compute takes as long as its copy and the pipeline turns compute-bound).  Chunk arguments are stable
+  // (ctx-owned staging), so the child replays one captured CUDA graph per chunk.
   int nc = 1;
   if (!(ctx->cfg.flags & XPT_FLAG_NO_PIPELINE))
-    for (int c = 4; c >= 2; --c)
-      if (B % c == 0) { nc = c; break; }
+    for (int c = kMaxChunks; c >= 2; --c)
+      if (B % c == 0 && (long long)(B / c) * ctx->H * ctx->W >= 65536) { nc = c; break; }
   const int Bc = B / nc;
   xpt_ctx* child = ctx;
   if (nc > 1) {
     if (!ctx->child) {
       xpt_config cc = ctx->cfg;
       cc.batch = Bc;
-      cc.flags |= XPT_FLAG_NO_PIPELINE;
+      cc.flags |= XPT_FLAG_NO_PIPELINE | XPT_FLAG_GRAPH;
       XPT_TRY(xpt_create(&ctx->child, &cc));
     }
     child = ctx->child;
@@ -957,20 +989,23 @@ int xpt_total_loss_host(xpt_ctx* ctx, const xpt_frames* frames, const float* con
       XPT_CUDA(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
       XPT_CUDA(cudaStreamCreateWithFlags(&ctx->s_in2, cudaStreamNonBlocking));
       XPT_CUDA(cudaEventCreateWithFlags(&ctx->ev_small, cudaEventDisableTiming));
-      for (int k = 0; k < 4; ++k) {
+      XPT_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+      XPT_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+      for (int k = 0; k < kMaxChunks; ++k) {
         XPT_CUDA(cudaEventCreateWithFlags(&ctx->ev_in[k], cudaEventDisableTiming));
         XPT_CUDA(cudaEventCreateWithFlags(&ctx->ev_done[k], cudaEventDisableTiming));
       }
     }
   }
-  cudaStream_t s_in = nc > 1 ? ctx->s_in : st, s_in2 = nc > 1 ? ctx->s_in2 : st, s_out = nc > 1 ? ctx->s_out : st;
+  cudaStream_t s_in = nc > 1 ? ctx->s_in : st, s_out = nc > 1 ? ctx->s_out : st;
+  cudaStream_t s_in2 = s_in;          // small inputs first, then the frame chunks: one FIFO keeps the link saturated
 
   // ---- device staging (sized for the whole batch, owned by the parent ctx) ---------------------------
   const long long snip = (long long)(N + 1) * hw3;
   XPT_TRY(dev_alloc(ctx, &ctx->st_frames, (size_t)B * snip));
   XPT_TRY(dev_alloc(ctx, &ctx->st_K, (size_t)B * 9));
   XPT_TRY(dev_alloc(ctx, &ctx->st_pose, (size_t)B * N * 6));
-  XPT_TRY(dev_alloc(ctx, &ctx->st_losses, 4 * 4));
+  XPT_TRY(dev_alloc(ctx, &ctx->st_losses, 4 * kMaxChunks));
   if (out->loss_batch) XPT_TRY(dev_alloc(ctx, &ctx->st_loss_batch, (size_t)3 * B));
   if (out->d_pose) XPT_TRY(dev_alloc(ctx, &ctx->st_dpose, (size_t)B * N * 6 + B));
   if (out->d_source) XPT_TRY(dev_alloc(ctx, &ctx->st_dsource, (size_t)B * N * hw3));
@@ -986,11 +1021,30 @@ int xpt_total_loss_host(xpt_ctx* ctx, const xpt_frames* frames, const float* con
   }
   const bool one_block = frames->target == frames->source + (long long)N * hw3 &&
                          frames->source_batch_stride == snip && frames->target_batch_stride == snip;
-  if (!ctx->h_losses) XPT_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_losses), 16 * sizeof(float)));
-  float (*h_losses)[4] = reinterpret_cast<float (*)[4]>(ctx->h_losses);
+  if (!ctx->h_losses) XPT_CUDA(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_losses), 4 * kMaxChunks * sizeof(float)));
 
-  // small inputs (K, pose, depth_ms, disp_ms: ~7 % of the bytes, 10 copies of ~5 us latency each): whole
-  // batch at once on their own stream, concurrently with the first frame chunk
+  // Small outputs whose host buffer is pinned (device-mapped) are written by the epilogue kernel THROUGH the
+  // mapping -- no staging and no copy-out latency; pageable buffers take the staged device->host copies.
+  auto mapped = [](float* host) -> float* {
+    if (!host) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    return at.type == cudaMemoryTypeHost ? static_cast<float*>(at.devicePointer) : nullptr;
+  };
+  float* m_dpose = mapped(out->d_pose);
+  float* m_losses = mapped(ctx->h_losses);
+  float* m_ddepth[kMaxScales]; float* m_ddisp[kMaxScales];
+  // Only the tiny outputs go this way: the fused kernel's 8-byte gradient stores would become one PCIe
+  // transaction each (measured: chunk compute 50 -> 150 us), so the gradient maps stay staged.
+  for (int l = 0; l < S; ++l) { m_ddepth[l] = nullptr; m_ddisp[l] = nullptr; }
+  const bool trace = host_trace_on() && nc > 1;
+  if (trace) cudaEventRecord(g_trace.t0, st);
+  if (nc > 1) {      // fork the copy streams from the caller's stream
+    XPT_CUDA(cudaEventRecord(ctx->ev_fork, st));
+    XPT_CUDA(cudaStreamWaitEvent(s_in, ctx->ev_fork, 0));
+    XPT_CUDA(cudaStreamWaitEvent(s_out, ctx->ev_fork, 0));
+  }
+  // small inputs (K, pose, depth_ms, disp_ms: ~15 % of the bytes): whole batch at once, ahead of the first frame chunk
   XPT_CUDA(cudaMemcpyAsync(ctx->st_K, frames->intrinsic, (size_t)B * 9 * fb, cudaMemcpyHostToDevice, s_in2));
   XPT_CUDA(cudaMemcpyAsync(ctx->st_pose, pose, (size_t)B * N * 6 * fb, cudaMemcpyHostToDevice, s_in2));
   for (int l = 0; l < S; ++l) {
@@ -1002,10 +1056,12 @@ int xpt_total_loss_host(xpt_ctx* ctx, const xpt_frames* frames, const float* con
     XPT_CUDA(cudaEventRecord(ctx->ev_small, s_in2));
     XPT_CUDA(cudaStreamWaitEvent(st, ctx->ev_small, 0));
   }
+  if (trace) cudaEventRecord(g_trace.small_in, s_in2);
 
   for (int k = 0; k < nc; ++k) {
     const int b0 = k * Bc;
     // -- host -> device, chunk k: the frames
+    // ONE copy-in stream: a second one only splits the link and delays every chunk (profiles/microbench/h2d_pipe.cu)
     float* dfr = ctx->st_frames + (long long)b0 * snip;
     if (one_block) {
       XPT_CUDA(cudaMemcpyAsync(dfr, frames->source + (long long)b0 * snip, (size_t)Bc * snip * fb, cudaMemcpyHostToDevice, s_in));
@@ -1025,6 +1081,7 @@ int xpt_total_loss_host(xpt_ctx* ctx, const xpt_frames* frames, const float* con
       XPT_CUDA(cudaEventRecord(ctx->ev_in[k], s_in));
       XPT_CUDA(cudaStreamWaitEvent(st, ctx->ev_in[k], 0));
     }
+    if (trace) cudaEventRecord(g_trace.in[k], s_in);
     // -- compute, chunk k (caller's stream)
     xpt_frames df;
     df.source = dfr; df.source_batch_stride = snip; df.source_frame_stride = hw3;
@@ -1033,14 +1090,14 @@ int xpt_total_loss_host(xpt_ctx* ctx, const xpt_frames* frames, const float* con
     xpt_loss_outputs dout;
     memset(&dout, 0, sizeof(dout));
     dout.grad_scale = out->grad_scale;
-    dout.losses = ctx->st_losses + 4 * k;
+    dout.losses = m_losses ? m_losses + 4 * k : ctx->st_losses + 4 * k;
     if (out->loss_batch) dout.loss_batch = ctx->st_loss_batch + (size_t)3 * b0;     // chunk-major [k][3][Bc]
-    if (out->d_pose) dout.d_pose = ctx->st_dpose + (size_t)b0 * N * 6;
+    if (out->d_pose) dout.d_pose = m_dpose ? m_dpose + (size_t)b0 * N * 6 : ctx->st_dpose + (size_t)b0 * N * 6;
     if (out->d_source) dout.d_source = ctx->st_dsource + (size_t)b0 * N * hw3;
     for (int l = 0; l < S; ++l) {
       const size_t off = (size_t)b0 * lvl_pix(ctx, l);
-      if (out->d_depth_ms[l]) dout.d_depth_ms[l] = ctx->st_ddepth[l] + off;
-      if (out->d_disp_ms[l]) dout.d_disp_ms[l] = ctx->st_ddisp[l] + off;
+      if (out->d_depth_ms[l]) dout.d_depth_ms[l] = m_ddepth[l] ? m_ddepth[l] + off : ctx->st_ddepth[l] + off;
+      if (out->d_disp_ms[l]) dout.d_disp_ms[l] = m_ddisp[l] ? m_ddisp[l] + off : ctx->st_ddisp[l] + off;
       if (out->synth_ms[l]) dout.synth_ms[l] = ctx->st_synth[l] + off * N * 3;
       if (out->mask_ms[l]) dout.mask_ms[l] = ctx->st_mask[l] + off * N;
       if (out->target_ms[l]) dout.target_ms[l] = ctx->st_target[l] + off * 3;
@@ -1050,32 +1107,129 @@ int xpt_total_loss_host(xpt_ctx* ctx, const xpt_frames* frames, const float* con
       XPT_CUDA(cudaEventRecord(ctx->ev_done[k], st));
       XPT_CUDA(cudaStreamWaitEvent(s_out, ctx->ev_done[k], 0));
     }
+    if (trace) cudaEventRecord(g_trace.done[k], st);
     // -- device -> host, chunk k: the large per-chunk outputs; small ones leave once at the end
     if (out->d_source) XPT_CUDA(cudaMemcpyAsync(out->d_source + (size_t)b0 * N * hw3, dout.d_source, (size_t)Bc * N * hw3 * fb, cudaMemcpyDeviceToHost, s_out));
     for (int l = 0; l < S; ++l) {
       const size_t off = (size_t)b0 * lvl_pix(ctx, l), n = (size_t)Bc * lvl_pix(ctx, l);
-      if (l == 0 && out->d_depth_ms[l]) XPT_CUDA(cudaMemcpyAsync(out->d_depth_ms[l] + off, dout.d_depth_ms[l], n * fb, cudaMemcpyDeviceToHost, s_out));
-      if (l == 0 && out->d_disp_ms[l]) XPT_CUDA(cudaMemcpyAsync(out->d_disp_ms[l] + off, dout.d_disp_ms[l], n * fb, cudaMemcpyDeviceToHost, s_out));
+      if (l == 0 && out->d_depth_ms[l] && !m_ddepth[l]) XPT_CUDA(cudaMemcpyAsync(out->d_depth_ms[l] + off, dout.d_depth_ms[l], n * fb, cudaMemcpyDeviceToHost, s_out));
+      if (l == 0 && out->d_disp_ms[l] && !m_ddisp[l]) XPT_CUDA(cudaMemcpyAsync(out->d_disp_ms[l] + off, dout.d_disp_ms[l], n * fb, cudaMemcpyDeviceToHost, s_out));
       if (out->synth_ms[l]) XPT_CUDA(cudaMemcpyAsync(out->synth_ms[l] + off * N * 3, dout.synth_ms[l], n * N * 3 * fb, cudaMemcpyDeviceToHost, s_out));
       if (out->mask_ms[l]) XPT_CUDA(cudaMemcpyAsync(out->mask_ms[l] + off * N, dout.mask_ms[l], n * N * fb, cudaMemcpyDeviceToHost, s_out));
       if (out->target_ms[l]) XPT_CUDA(cudaMemcpyAsync(out->target_ms[l] + off * 3, dout.target_ms[l], n * 3 * fb, cudaMemcpyDeviceToHost, s_out));
     }
   }
   // small outputs, whole batch (s_out already waits for the last chunk's compute)
-  XPT_CUDA(cudaMemcpyAsync(ctx->h_losses, ctx->st_losses, (size_t)4 * nc * fb, cudaMemcpyDeviceToHost, s_out));
+  if (!m_losses) XPT_CUDA(cudaMemcpyAsync(ctx->h_losses, ctx->st_losses, (size_t)4 * nc * fb, cudaMemcpyDeviceToHost, s_out));
   if (out->loss_batch)
     for (int k = 0; k < nc; ++k)
       for (int r = 0; r < 3; ++r)
         XPT_CUDA(cudaMemcpyAsync(out->loss_batch + (size_t)r * B + (size_t)k * Bc, ctx->st_loss_batch + (size_t)3 * k * Bc + (size_t)r * Bc,
                                  Bc * fb, cudaMemcpyDeviceToHost, s_out));
-  if (out->d_pose) XPT_CUDA(cudaMemcpyAsync(out->d_pose, ctx->st_dpose, (size_t)B * N * 6 * fb, cudaMemcpyDeviceToHost, s_out));
+  if (out->d_pose && !m_dpose) XPT_CUDA(cudaMemcpyAsync(out->d_pose, ctx->st_dpose, (size_t)B * N * 6 * fb, cudaMemcpyDeviceToHost, s_out));
+  // levels >= 1 of the gradient maps: one kernel with wide coalesced stores through the pinned mapping instead of
+  // six copies of ~7 us latency each in the tail of the call; pageable destinations take the copies
+  {
+    DrainArgs da;
+    memset(&da, 0, sizeof(da));
+    for (int l = 1; l < S; ++l) {
+      const long long n = (long long)B * lvl_pix(ctx, l);
+      float* md = mapped(out->d_depth_ms[l]);
+      float* ms = mapped(out->d_disp_ms[l]);
+      if (md && da.n < 16) { da.src[da.n] = ctx->st_ddepth[l]; da.dst[da.n] = md; da.count[da.n] = n; ++da.n; m_ddepth[l] = md; }
+      if (ms && da.n < 16) { da.src[da.n] = ctx->st_ddisp[l]; da.dst[da.n] = ms; da.count[da.n] = n; ++da.n; m_ddisp[l] = ms; }
+    }
+    if (da.n > 0) {
+      k_drain<<<dim3(32, da.n), 256, 0, s_out>>>(da);
+      XPT_LAUNCH_CHECK("k_drain");
+    }
+  }
   for (int l = 1; l < S; ++l) {
     const size_t n = (size_t)B * lvl_pix(ctx, l);
-    if (out->d_depth_ms[l]) XPT_CUDA(cudaMemcpyAsync(out->d_depth_ms[l], ctx->st_ddepth[l], n * fb, cudaMemcpyDeviceToHost, s_out));
-    if (out->d_disp_ms[l]) XPT_CUDA(cudaMemcpyAsync(out->d_disp_ms[l], ctx->st_ddisp[l], n * fb, cudaMemcpyDeviceToHost, s_out));
+    if (out->d_depth_ms[l] && !m_ddepth[l]) XPT_CUDA(cudaMemcpyAsync(out->d_depth_ms[l], ctx->st_ddepth[l], n * fb, cudaMemcpyDeviceToHost, s_out));
+    if (out->d_disp_ms[l] && !m_ddisp[l]) XPT_CUDA(cudaMemcpyAsync(out->d_disp_ms[l], ctx->st_ddisp[l], n * fb, cudaMemcpyDeviceToHost, s_out));
   }
-  if (nc > 1) XPT_CUDA(cudaStreamSynchronize(s_out));
-  XPT_CUDA(cudaStreamSynchronize(st));
+  if (trace) cudaEventRecord(g_trace.out_end, s_out);
+  if (nc > 1) {      // join: the caller's stream completes when the last copy-out has landed
+    XPT_CUDA(cudaEventRecord(ctx->ev_join, s_out));
+    XPT_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+  }
+  *nc_out = nc;
+  return XPT_OK;
+}
+
+static bool is_pinned(const void* p) {
+  if (!p) return true;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+
+int xpt_total_loss_host(xpt_ctx* ctx, const xpt_frames* frames, const float* const depth_ms[],
+                        const float* const disp_ms[], const float* pose, const xpt_loss_outputs* out, void* stream) {
+  if (!ctx || !frames || !pose || !out || !depth_ms) return fail(XPT_BAD_ARGUMENT, "xpt_total_loss_host: NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  XPT_CUDA(cudaSetDevice(ctx->cfg.device));
+  int nc = 1, rc = XPT_OK;
+  // Replay path: once the ctx is warm, a call whose buffers are all pinned and whose stream can be captured is
+  // recorded ONCE (copies + chunked compute + copies out, ~100 API calls) and replayed as one graph launch.
+  bool can_graph = ctx->host_warm && !(ctx->cfg.flags & XPT_FLAG_NO_PIPELINE) && st != nullptr && st != cudaStreamLegacy &&
+                   !host_trace_on();
+  if (can_graph) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    XPT_CUDA(cudaStreamIsCapturing(st, &cs));
+    can_graph = cs == cudaStreamCaptureStatusNone;
+  }
+  std::vector<uint64_t> key;
+  if (can_graph) {
+    auto K = [&](const void* p) { key.push_back((uint64_t)(uintptr_t)p); can_graph = can_graph && is_pinned(p); };
+    K(frames->source); K(frames->target); K(frames->intrinsic); K(pose);
+    key.push_back((uint64_t)frames->source_batch_stride); key.push_back((uint64_t)frames->source_frame_stride);
+    key.push_back((uint64_t)frames->target_batch_stride); key.push_back((uint64_t)(uintptr_t)stream);
+    K(out->losses); K(out->loss_batch); K(out->d_pose); K(out->d_source);
+    uint32_t gsbits; memcpy(&gsbits, &out->grad_scale, 4); key.push_back(gsbits);
+    for (int l = 0; l < ctx->S; ++l) {
+      K(depth_ms[l]); K(disp_ms ? disp_ms[l] : nullptr); K(out->synth_ms[l]); K(out->mask_ms[l]);
+      K(out->target_ms[l]); K(out->d_depth_ms[l]); K(out->d_disp_ms[l]);
+    }
+  }
+  if (!can_graph) {
+    rc = host_enqueue(ctx, frames, depth_ms, disp_ms, pose, out, stream, &nc);
+    if (rc != XPT_OK) return rc;
+    XPT_CUDA(cudaStreamSynchronize(st));
+    if (host_trace_on() && nc > 1 && ctx->host_warm) {
+      float ms;
+      auto T = [&](cudaEvent_t e) { cudaEventElapsedTime(&ms, g_trace.t0, e); return ms * 1e3f; };
+      fprintf(stderr, "[xpt host trace] small-in %.0f us |", T(g_trace.small_in));
+      for (int k = 0; k < nc; ++k) { fprintf(stderr, " in%d %.0f", k, T(g_trace.in[k])); fprintf(stderr, " done%d %.0f |", k, T(g_trace.done[k])); }
+      fprintf(stderr, " out-end %.0f us\n", T(g_trace.out_end));
+    }
+    ctx->host_warm = true;
+  } else {
+    if (!ctx->host_graphs) ctx->host_graphs = new std::vector<xpt_ctx::GraphEntry>();
+    cudaGraphExec_t exec = nullptr;
+    for (auto& e : *ctx->host_graphs)
+      if (e.key == key) { exec = e.exec; nc = e.launches; break; }
+    if (!exec) {
+      XPT_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+      rc = host_enqueue(ctx, frames, depth_ms, disp_ms, pose, out, stream, &nc);
+      cudaGraph_t graph = nullptr;
+      cudaError_t ce = cudaStreamEndCapture(st, &graph);
+      if (rc != XPT_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+      if (ce != cudaSuccess) return fail(XPT_CUDA_ERROR, "cudaStreamEndCapture (host call) failed: %s", cudaGetErrorString(ce));
+      ce = cudaGraphInstantiate(&exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ce != cudaSuccess) return fail(XPT_CUDA_ERROR, "cudaGraphInstantiate (host call) failed: %s", cudaGetErrorString(ce));
+      if (ctx->host_graphs->size() >= 16) {
+        cudaGraphExecDestroy(ctx->host_graphs->front().exec);
+        ctx->host_graphs->erase(ctx->host_graphs->begin());
+      }
+      ctx->host_graphs->push_back({key, exec, nc});      // `launches` carries the chunk count here
+    }
+    XPT_CUDA(cudaGraphLaunch(exec, st));
+    XPT_CUDA(cudaStreamSynchronize(st));
+  }
+  float (*h_losses)[4] = reinterpret_cast<float (*)[4]>(ctx->h_losses);
   for (int j = 0; j < 4; ++j) {
     double v = 0.0;
     for (int k = 0; k < nc; ++k) v += (double)h_losses[k][j];

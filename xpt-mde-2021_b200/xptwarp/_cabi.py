@@ -75,7 +75,8 @@ SYMBOLS = {
     "xpt_last_launch_count": (C.c_int, [C.c_void_p]),
 }
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libxptwarp.so")
+# XPTWARP_LIB: explicit path of another BUILD of the same library (profiling ablations); never a fallback
+LIB_PATH = os.environ.get("XPTWARP_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libxptwarp.so")
 _lib = None
 
 
