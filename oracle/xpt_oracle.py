@@ -69,6 +69,17 @@ def pose_rvec2matr_batch(poses: torch.Tensor) -> torch.Tensor:
 # --------------------------------------------------------------------------
 # pyramids  (reference synthesize_base.py:74-85, util_funcs.py:163-175)
 # --------------------------------------------------------------------------
+def pose_matr2rvec_batch(poses: torch.Tensor) -> torch.Tensor:
+    """utils/convert_pose.py:151-168: [B,N,4,4] -> [B,N,6] = (t, rvec).  theta = acos((tr R - 1)/2);
+    axis from the antisymmetric part (same flipped sign convention as rvec2matr); |theta| < 1e-5 -> axis/2."""
+    R = poses[:, :, :3, :3]
+    theta = torch.acos((R[:, :, 0, 0] + R[:, :, 1, 1] + R[:, :, 2, 2] - 1.0) / 2.0).unsqueeze(-1)
+    axis = torch.stack([R[:, :, 1, 2] - R[:, :, 2, 1], R[:, :, 2, 0] - R[:, :, 0, 2],
+                        R[:, :, 0, 1] - R[:, :, 1, 0]], dim=-1)
+    rvec = torch.where(theta.abs() < 0.00001, axis / 2.0, axis / (2 * torch.sin(theta)) * theta)
+    return torch.cat([poses[:, :, :3, 3], rvec], dim=-1)
+
+
 def resize_bilinear_tf(img_nhwc: torch.Tensor, size_hw: Tuple[int, int]) -> torch.Tensor:
     """tf.image.resize(method="bilinear") of TF2: half-pixel centres, no antialias.
     img [M,H,W,C] -> [M,h,w,C].  Identity when the size is unchanged."""
@@ -365,42 +376,104 @@ def monodepth2_loss_multi_scale(method, synth_target_ms, target, scale_weights):
 # --------------------------------------------------------------------------
 # TotalLoss  (reference losses.py:14-103)
 # --------------------------------------------------------------------------
-def append_data(features: Dict, predictions: Dict) -> Dict:
+def append_data(features: Dict, predictions: Dict, suffix: str = "") -> Dict:
     """losses.py:57-103 (target frame is the LAST one of the snippet, :77-78)."""
-    image5d = features["image5d"]
+    image5d = features["image5d" + suffix]
     source, target = image5d[:, :-1], image5d[:, -1]
-    augm = {"source": source, "target": target}
-    if "depth_ms" in predictions and "pose" in predictions:
-        augm["target_ms"] = multi_scale_like_depth(target, predictions["depth_ms"])
-        augm["synth_target_ms"] = synthesize_multi_scale(source, features["intrinsic"],
-                                                         predictions["depth_ms"], predictions["pose"])
-    if "flow_ms" in predictions:
-        augm["flow_target_ms"] = [resize_bilinear_tf(target, (f.shape[2], f.shape[3]))
-                                  for f in predictions["flow_ms"]]
-        augm["warped_target_ms"] = flow_warp_multi_scale(source, predictions["flow_ms"])
+    augm = {"source" + suffix: source, "target" + suffix: target}
+    if "depth_ms" + suffix in predictions and "pose" + suffix in predictions:
+        augm["target_ms" + suffix] = multi_scale_like_depth(target, predictions["depth_ms" + suffix])
+        augm["synth_target_ms" + suffix] = synthesize_multi_scale(source, features["intrinsic" + suffix],
+                                                                  predictions["depth_ms" + suffix],
+                                                                  predictions["pose" + suffix])
+    if "flow_ms" + suffix in predictions:
+        augm["flow_target_ms" + suffix] = [resize_bilinear_tf(target, (f.shape[2], f.shape[3]))
+                                           for f in predictions["flow_ms" + suffix]]
+        augm["warped_target_ms" + suffix] = flow_warp_multi_scale(source, predictions["flow_ms" + suffix])
     return augm
+
+
+def synthesize_stereo(features: Dict, predictions: Dict, augm: Dict) -> Dict:
+    """losses.py:105-140: left target from the right frame with T_RL = inv(T_LR), right target from the left
+    frame with T_LR; both through the rvec round trip of convert_pose.py:151-168 and -- as the reference
+    does -- both with the LEFT intrinsics."""
+    out = {}
+    if "stereo_T_LR" not in features or "depth_ms" not in predictions:
+        return out
+    T_LR = features["stereo_T_LR"]
+    pose_RL = pose_matr2rvec_batch(torch.linalg.inv(T_LR).unsqueeze(1))
+    out["stereo_synth_ms"] = synthesize_multi_scale(augm["target_R"].unsqueeze(1), features["intrinsic"],
+                                                    predictions["depth_ms"], pose_RL)
+    pose_LR = pose_matr2rvec_batch(T_LR.unsqueeze(1))
+    out["stereo_synth_ms_R"] = synthesize_multi_scale(augm["target"].unsqueeze(1), features["intrinsic"],
+                                                      predictions["depth_ms_R"], pose_LR)
+    return out
+
+
+def stereo_depth_loss(method, augm: Dict, scale_weights) -> torch.Tensor:
+    """losses.py:443-478: per-scale photometric loss of both stereo syntheses, summed, then merged."""
+    fn = _PHOTO[method]
+    left = [fn(s, t) for s, t in zip(augm["stereo_synth_ms"], augm["target_ms"])]
+    right = [fn(s, t) for s, t in zip(augm["stereo_synth_ms_R"], augm["target_ms_R"])]
+    return merge_multi_scale_losses([l + r for l, r in zip(left, right)], scale_weights)
+
+
+def stereo_pose_loss(features: Dict, predictions: Dict) -> torch.Tensor:
+    """losses.py:481-495: MSE over the 6 twist components of both directions, mean over numsrc -> [B]."""
+    T = features["stereo_T_LR"].unsqueeze(1)
+    lr_true, rl_true = pose_matr2rvec_batch(T), pose_matr2rvec_batch(torch.linalg.inv(T))
+    loss = ((lr_true - predictions["pose_LR"]) ** 2).mean(dim=-1) + ((rl_true - predictions["pose_RL"]) ** 2).mean(dim=-1)
+    return loss.mean(dim=1)
+
+
+def moa_loss_multi_scale(method, temp_synth_ms, stereo_synth_ms, target, scale_weights):
+    """losses.py:282-321: per-pixel min over the N temporal and the stereo synthesis, at full resolution."""
+    fn = _PHOTO[method]
+    Ho, Wo = target.shape[1:3]
+
+    def up(x):
+        B, N, h, w, C = x.shape
+        return resize_bilinear_tf(x.reshape(B * N, h, w, C), (Ho, Wo)).reshape(B, N, Ho, Wo, C)
+    losses = []
+    for temp, stro in zip(temp_synth_ms, stereo_synth_ms):
+        both = torch.cat([fn(up(temp), target, False), fn(up(stro), target, False)], dim=1)
+        losses.append(torch.amin(both, dim=1).mean(dim=(1, 2, 3)))
+    return merge_multi_scale_losses(losses, scale_weights)
 
 
 def total_loss(predictions: Dict, features: Dict, loss_weights: Dict[str, float],
                scale_weights: Sequence[float], global_batch: Optional[int] = None,
-               return_augm: bool = False):
+               return_augm: bool = False, stereo: bool = False):
     """losses.py:26-55: per-type [B] loss -> sum/global_batch -> weighted sum.
     Returns (total, {name: unweighted mean}[, augm_data])."""
     augm = append_data(features, predictions)
+    if stereo and "image5d_R" in features:             # losses.py:38-42
+        augm.update(append_data(features, predictions, "_R"))
+        augm.update(synthesize_stereo(features, predictions, augm))
     B = features["image5d"].shape[0]
     gb = B if global_batch is None else global_batch
     by_type, weighted = {}, []
     for name, w in loss_weights.items():
         if w == 0.0:
             continue                                   # loss_factory.py:41-43
-        if name in ("L1", "SSIM"):
-            lb = photometric_loss_multi_scale(name, augm["synth_target_ms"], augm["target_ms"], scale_weights)
-        elif name == "smoothe":
-            lb = smootheness_loss_multi_scale(predictions["disp_ms"], augm["target_ms"], scale_weights)
-        elif name in ("md2L1", "md2SSIM"):
-            lb = monodepth2_loss_multi_scale(name[3:], augm["synth_target_ms"], augm["target"], scale_weights)
-        elif name == "flowL2":
-            lb = photometric_loss_multi_scale("L2", augm["warped_target_ms"], augm["flow_target_ms"],
+        sfx = "_R" if name.endswith("_R") else ""
+        base = name[:-2] if sfx else name
+        if base in ("L1", "SSIM"):
+            lb = photometric_loss_multi_scale(base, augm["synth_target_ms" + sfx], augm["target_ms" + sfx], scale_weights)
+        elif base == "smoothe":
+            lb = smootheness_loss_multi_scale(predictions["disp_ms" + sfx], augm["target_ms" + sfx], scale_weights)
+        elif base in ("md2L1", "md2SSIM"):
+            lb = monodepth2_loss_multi_scale(base[3:], augm["synth_target_ms" + sfx], augm["target" + sfx], scale_weights)
+        elif base in ("moaL1", "moaSSIM"):
+            # losses.py:293-295: the stereo synthesis is ALWAYS the left one ("stereo_synth_ms"), also for "_R"
+            lb = moa_loss_multi_scale(base[3:], augm["synth_target_ms" + sfx], augm["stereo_synth_ms"],
+                                      augm["target" + sfx], scale_weights)
+        elif base in ("stereoL1", "stereoSSIM"):
+            lb = stereo_depth_loss(base[6:], augm, scale_weights)
+        elif base == "stereoPose":
+            lb = stereo_pose_loss(features, predictions)
+        elif base == "flowL2":
+            lb = photometric_loss_multi_scale("L2", augm["warped_target_ms" + sfx], augm["flow_target_ms" + sfx],
                                               scale_weights)
         else:
             raise ValueError(f"oracle: loss {name!r} is outside the hot path")
@@ -470,6 +543,52 @@ def make_inputs(B: int, H: int, W: int, N: int = 4, n_scales: int = 4, seed: int
     predictions = {"depth_ms": depth_ms, "disp_ms": disp_ms,
                    "pose": pose.to(dtype)}
     return features, predictions
+
+
+def make_stereo_inputs(B: int, H: int, W: int, N: int = 4, n_scales: int = 4, seed: int = 20211,
+                       dtype=torch.float32) -> Tuple[Dict, Dict]:
+    """make_inputs for a stereo rig: left + right snippets, the rig transform T_LR (baseline ~0.5 m along x, a
+    slight toe-in) and the two rig-pose predictions the reference's StereoPoseLoss consumes."""
+    fl, pl = make_inputs(B, H, W, N, n_scales, seed, dtype)
+    fr, pr = make_inputs(B, H, W, N, n_scales, seed + 7919, dtype)
+    g = torch.Generator().manual_seed(seed + 1)
+    rig = torch.zeros(B, 1, 6, dtype=torch.float64)
+    rig[:, 0, 0] = 0.5 + 0.05 * (torch.rand(B, generator=g, dtype=torch.float64) - 0.5)
+    rig[:, 0, 1:3] = 0.02 * (torch.rand(B, 2, generator=g, dtype=torch.float64) - 0.5)
+    rig[:, 0, 3:] = 0.02 * (torch.rand(B, 3, generator=g, dtype=torch.float64) - 0.5) + 0.004
+    T_LR = pose_rvec2matr_batch(rig)[:, 0]
+    features = {"image5d": fl["image5d"], "intrinsic": fl["intrinsic"], "image5d_R": fr["image5d"],
+                "intrinsic_R": (fl["intrinsic"].double() * (1 + 0.01 * torch.rand(B, 1, 1, generator=g, dtype=torch.float64))
+                                ).to(dtype).clone(),
+                "stereo_T_LR": T_LR.to(dtype)}
+    features["intrinsic_R"][:, 2, :] = fl["intrinsic"][:, 2, :]
+    noise = lambda: 0.01 * (torch.rand(B, 1, 6, generator=g, dtype=torch.float64) - 0.5)
+    predictions = dict(pl)
+    predictions.update({"depth_ms_R": pr["depth_ms"], "disp_ms_R": pr["disp_ms"], "pose_R": pr["pose"],
+                        "pose_LR": (rig + noise()).to(dtype),
+                        "pose_RL": (pose_matr2rvec_batch(torch.linalg.inv(T_LR).unsqueeze(1)) + noise()).to(dtype)})
+    return features, predictions
+
+
+_GRAD_KEYS = ("depth_ms", "disp_ms", "pose", "depth_ms_R", "disp_ms_R", "pose_R", "pose_LR", "pose_RL")
+
+
+def stereo_loss_and_grads(features: Dict, predictions: Dict, loss_weights, scale_weights,
+                          global_batch: Optional[int] = None):
+    """total_loss(stereo=True) + autograd w.r.t. every prediction.  Returns dict(total, by_type, grads{key})."""
+    preds = {}
+    for k in _GRAD_KEYS:
+        if k not in predictions:
+            continue
+        v = predictions[k]
+        preds[k] = ([t.detach().clone().requires_grad_(True) for t in v] if isinstance(v, (list, tuple))
+                    else v.detach().clone().requires_grad_(True))
+    total, by_type, augm = total_loss(preds, features, loss_weights, scale_weights, global_batch, True, stereo=True)
+    total.backward()
+    gz = lambda t: torch.zeros_like(t) if t.grad is None else t.grad
+    grads = {k: ([gz(t) for t in v] if isinstance(v, list) else gz(v)) for k, v in preds.items()}
+    return {"total": total.detach(), "by_type": {k: v.detach() for k, v in by_type.items()}, "grads": grads,
+            "augm": {k: ([t.detach() for t in v] if isinstance(v, list) else v.detach()) for k, v in augm.items()}}
 
 
 def loss_and_grads(features: Dict, predictions: Dict, loss_weights, scale_weights,

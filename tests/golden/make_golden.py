@@ -102,6 +102,61 @@ def run_case(name, B, H, W, N, loss_set, seed, adversarial=False, global_batch=N
     print("wrote", path, {k: float(v) for k, v in by_type.items()}, float(total))
 
 
+STEREO_SETS = {
+    # reference config-example.py:76-121 as written (stereo rigs: STEREO=True, config-example.py:20)
+    "T1": LOSS_SETS["T1"][0], "T2": LOSS_SETS["T2"][0],
+    "MOA_WST": {"moaL1": 5.0, "moaL1_R": 5.0, "moaSSIM": 0.5, "moaSSIM_R": 0.5, "smoothe": 20.0, "smoothe_R": 20.0,
+                "stereoL1": 0.5, "stereoSSIM": 0.5, "stereoPose": 1.0},
+    "MD2": {"md2L1": 0.5, "md2L1_R": 0.5, "md2SSIM": 0.5, "md2SSIM_R": 0.5, "smoothe": 1.0, "smoothe_R": 1.0,
+            "stereoL1": 0.5, "stereoSSIM": 0.5, "stereoPose": 1.0},
+}
+_PRED_KEYS = ("depth_ms", "disp_ms", "pose", "depth_ms_R", "disp_ms_R", "pose_R", "pose_LR", "pose_RL")
+
+
+def run_stereo_case(name, B, H, W, N, loss_set, scale_weights, seed, global_batch=None):
+    """TotalLoss(stereo=True) of the reference on a stereo rig: temporal losses of both eyes, the two stereo
+    syntheses (losses.py:105-140), StereoDepthLoss / StereoPoseLoss / MoA / MonoDepth2 as configured."""
+    feats, preds = orc.make_stereo_inputs(B, H, W, N=N, seed=seed, dtype=torch.float32)
+    cv = lambda t: t.to(DT)
+    feats = {k: cv(v) for k, v in feats.items()}
+    preds = {k: ([cv(t).clone().requires_grad_(True) for t in v] if isinstance(v, list)
+                 else cv(v).clone().requires_grad_(True)) for k, v in preds.items()}
+    feats["image_R"] = feats["image5d_R"]             # losses.py:38 tests this key
+    gb = B if global_batch is None else global_batch
+    cfg = {"image": 1, "intrinsic": 1, "image_R": 1, "intrinsic_R": 1, "stereo_T_LR": 1}
+    total_obj = loss_factory(cfg, STEREO_SETS[loss_set], np.asarray(scale_weights, dtype=np.float64), stereo=True, batch_size=gb)
+    total, by_type = total_obj(preds, feats)
+    total.backward()
+    out = {"B": B, "H": H, "W": W, "N": N, "global_batch": gb, "loss_set": loss_set,
+           "loss_names": np.array(list(total_obj.loss_objects.keys())),
+           "loss_weights": np.array([total_obj.loss_weights[k] for k in total_obj.loss_objects]),
+           "scale_weights": np.asarray(scale_weights, dtype=np.float64), "total": np_(total)}
+    for k, v in by_type.items():
+        out["loss_" + k] = np_(v)
+    gz = lambda t: np_(torch.zeros_like(t) if t.grad is None else t.grad)
+    for k in _PRED_KEYS:
+        v = preds[k]
+        if isinstance(v, list):
+            for s_, t in enumerate(v):
+                out[f"d_{k}_{s_}"] = gz(t)
+        else:
+            out["d_" + k] = gz(v)
+    if not F64:
+        for k, v in feats.items():
+            if k != "image_R":
+                out["in_" + k] = np_(v)
+        for k in _PRED_KEYS:
+            v = preds[k]
+            if isinstance(v, list):
+                for s_, t in enumerate(v):
+                    out[f"in_{k}_{s_}"] = np_(t)
+            else:
+                out["in_" + k] = np_(v)
+    path = os.path.join(HERE, f"{name}_{'f64' if F64 else 'f32'}.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, {k: float(v) for k, v in by_type.items()}, float(total))
+
+
 def run_pieces():
     """Per-function vectors: pose conversion (tf and numpy twins), per-pixel
     photometric terms, safe reciprocal, SynthesizeMultiScale alone."""
@@ -144,3 +199,7 @@ if __name__ == "__main__":
     run_case("case_small_t1", B=2, H=32, W=64, N=4, loss_set="T1", seed=101)
     run_case("case_n2_t2", B=3, H=48, W=40, N=2, loss_set="T2", seed=202, global_batch=6)
     run_case("case_adv_t1", B=2, H=32, W=48, N=4, loss_set="T1", seed=303, adversarial=True)
+    run_stereo_case("stereo_t1", B=2, H=32, W=64, N=2, loss_set="T1", scale_weights=[1, 1, 1, 1], seed=404)
+    run_stereo_case("stereo_t2", B=2, H=32, W=40, N=3, loss_set="T2", scale_weights=[0.4, 0.8, 1.2, 1.6], seed=505, global_batch=4)
+    run_stereo_case("stereo_moa", B=2, H=32, W=64, N=2, loss_set="MOA_WST", scale_weights=[1, 1, 1, 1], seed=606)
+    run_stereo_case("stereo_md2", B=2, H=32, W=48, N=3, loss_set="MD2", scale_weights=[1, 1, 1, 1], seed=707)

@@ -56,6 +56,9 @@ def _t(x, dtype=None):
         return x if dtype is None else x.to(_dt(dtype))
     if isinstance(x, (list, tuple)) and len(x) and isinstance(x[0], torch.Tensor):
         return torch.stack([_t(v) for v in x], dim=0)
+    if isinstance(x, (list, tuple)) and len(x) and isinstance(x[0], (list, tuple)) and len(x[0]) \
+            and isinstance(x[0][0], torch.Tensor):
+        return torch.stack([_t(v) for v in x], dim=0)      # nested lists of tensors (tf auto-packing)
     a = np.asarray(x)
     if dtype is not None:
         return torch.as_tensor(a).to(_dt(dtype))
@@ -323,6 +326,22 @@ def random_uniform(shape, minval=0, maxval=1, **_):
     return torch.rand(tuple(shape), dtype=FLOAT) * (maxval - minval) + minval
 
 
+def linalg_trace(x, **_):
+    """tf.linalg.trace: sum of the main diagonal of the innermost matrices."""
+    x = _t(x)
+    return torch.einsum("...ii->...", x)
+
+
+def acos(x, **_):
+    return torch.arccos(_t(x))
+
+
+def keras_mse(y_true, y_pred):
+    """tf.keras.losses.MSE: mean of squared differences over the LAST axis."""
+    d = _t(y_pred) - _t(y_true)
+    return (d * d).sum(dim=-1) / d.shape[-1]
+
+
 def _unsupported(name):
     def f(*a, **k):
         raise NotImplementedError(f"tf_shim: {name} is outside the hot path")
@@ -345,9 +364,9 @@ def install(opts_overrides=None):
         norm=norm, matmul=matmul, tensordot=tensordot, gather_nd=gather_nd,
     ).items():
         setattr(tf, name, fn)
-    tf.linalg = types.SimpleNamespace(inv=linalg_inv, trace=_unsupported("linalg.trace"))
+    tf.linalg = types.SimpleNamespace(inv=linalg_inv, trace=linalg_trace)
     tf.math = types.SimpleNamespace(not_equal=not_equal, equal=equal, sin=sin, cos=cos,
-                                    acos=_unsupported("math.acos"), is_nan=torch.isnan,
+                                    acos=acos, is_nan=torch.isnan,
                                     count_nonzero=_unsupported("math.count_nonzero"))
     tf.image = types.SimpleNamespace(resize=image_resize,
                                      convert_image_dtype=_unsupported("image.convert_image_dtype"))
@@ -360,7 +379,7 @@ def install(opts_overrides=None):
     layers.Lambda = Lambda
     layers.AveragePooling3D = AveragePooling3D
     keras.layers = layers
-    keras.losses = types.SimpleNamespace(MSE=_unsupported("keras.losses.MSE"))
+    keras.losses = types.SimpleNamespace(MSE=keras_mse)
     tf.keras = keras
     sys.modules["tensorflow"] = tf
     sys.modules["tensorflow.keras"] = keras

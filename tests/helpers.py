@@ -1,5 +1,6 @@
 """Shared test helpers (CPU and GPU tests)."""
 import os
+import re
 
 import numpy as np
 import torch
@@ -21,6 +22,34 @@ def case_inputs(g, device="cpu", dtype=torch.float32):
     lw = dict(zip(g["loss_names"].tolist(), [float(w) for w in g["loss_weights"]]))
     sw = [float(w) for w in g["scale_weights"]]
     return feats, preds, lw, sw, int(g["global_batch"])
+
+
+STEREO_CASES = ["stereo_t1", "stereo_t2", "stereo_moa", "stereo_md2"]
+PRED_KEYS = ("depth_ms", "disp_ms", "pose", "depth_ms_R", "disp_ms_R", "pose_R", "pose_LR", "pose_RL")
+
+
+def stereo_case_inputs(g, device="cpu", dtype=torch.float32):
+    """features / predictions of a stereo golden case (tests/golden/make_golden.py:run_stereo_case)."""
+    cv = lambda a: torch.tensor(a, dtype=dtype, device=device)
+    feats = {k: cv(g["in_" + k]) for k in ("image5d", "intrinsic", "image5d_R", "intrinsic_R", "stereo_T_LR")}
+    preds = {}
+    for k in PRED_KEYS:
+        if "in_" + k in g.files:
+            preds[k] = cv(g["in_" + k])
+        else:
+            S = sum(1 for n in g.files if re.fullmatch(rf"in_{k}_\d+", n))
+            preds[k] = [cv(g[f"in_{k}_{s}"]) for s in range(S)]
+    lw = dict(zip(g["loss_names"].tolist(), [float(w) for w in g["loss_weights"]]))
+    sw = [float(w) for w in g["scale_weights"]]
+    return feats, preds, lw, sw, int(g["global_batch"])
+
+
+def golden_grad(g, key):
+    """gradient entry of a stereo golden case: tensor or per-scale list"""
+    if "d_" + key in g.files:
+        return g["d_" + key]
+    S = sum(1 for n in g.files if re.fullmatch(rf"d_{key}_\d+", n))
+    return [g[f"d_{key}_{s}"] for s in range(S)]
 
 
 def relerr(a, b):

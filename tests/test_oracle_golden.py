@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import xpt_oracle as orc
-from helpers import CASES, case_inputs, load_case, relerr
+from helpers import CASES, PRED_KEYS, STEREO_CASES, case_inputs, golden_grad, load_case, relerr, stereo_case_inputs
 
 
 def test_pieces_pose_and_photometric_maps():
@@ -63,6 +63,36 @@ def test_total_loss_and_gradients_fp64(name):
     for s in range(len(preds["depth_ms"])):
         assert relerr(r["d_depth_ms"][s].numpy(), g64[f"d_depth_{s}"]) < 1e-9
         assert relerr(r["d_disp_ms"][s].numpy(), g64[f"d_disp_{s}"]) < 1e-9
+
+
+@pytest.mark.parametrize("name", STEREO_CASES)
+@pytest.mark.parametrize("kind", ["f32", "f64"])
+def test_stereo_total_loss_and_gradients(name, kind):
+    """TotalLoss(stereo=True): both eyes' temporal losses, the two stereo syntheses, StereoDepthLoss,
+    StereoPoseLoss, MoA and MonoDepth2 min-over-sources -- against the reference's own source."""
+    g32, g = load_case(name), load_case(name, kind)
+    dt = torch.float64 if kind == "f64" else torch.float32
+    feats, preds, lw, sw, gb = stereo_case_inputs(g32, dtype=dt)
+    r = orc.stereo_loss_and_grads(feats, preds, lw, sw, gb)
+    ltol, gtol = (1e-12, 1e-9) if kind == "f64" else (1e-5, 1e-4)
+    assert relerr(r["total"].numpy(), g["total"]) < ltol
+    for k in lw:
+        assert relerr(r["by_type"][k].numpy(), g["loss_" + k]) < max(ltol, 2e-5 if kind == "f32" else 0), k
+    for k in PRED_KEYS:
+        ref = golden_grad(g, k)
+        got = r["grads"][k]
+        if isinstance(ref, list):
+            for s in range(len(ref)):
+                assert relerr(got[s].numpy(), ref[s]) < gtol, (k, s)
+        else:
+            assert relerr(got.numpy(), ref) < gtol, k
+
+
+def test_pose_matr2rvec_round_trip():
+    """reference test_pose_matr2rvec_batch (convert_pose.py:256-271): rvec -> matrix -> rvec for U(-1,1)."""
+    g = torch.Generator().manual_seed(3)
+    p = torch.rand(8, 5, 6, generator=g, dtype=torch.float64) * 2 - 1
+    assert float((orc.pose_matr2rvec_batch(orc.pose_rvec2matr_batch(p)) - p).abs().max()) < 1e-9
 
 
 def test_gradients_match_finite_differences_fp64():
