@@ -126,6 +126,18 @@ XPT_API size_t xpt_scratch_bytes(const xpt_ctx* ctx);
 /* utils/convert_pose.py:32-71  pose_rvec2matr_batch_tf: [B,N,6] -> [B,N,4,4] */
 XPT_API int xpt_pose_rvec2matr(xpt_ctx* ctx, const float* pose, float* matr, void* stream);
 
+/* utils/convert_pose.py:151-168 pose_matr2rvec_batch: `count` 4x4 matrices -> [count,6] = (t, rvec).
+ * invert != 0 first applies tf.linalg.inv (losses.py:120 turns stereo_T_LR into T_RL this way).
+ * Needs no ctx: `device` is the CUDA ordinal the pointers live on.                                    */
+XPT_API int xpt_pose_matr2rvec(int device, const float* matr, int count, int invert, float* rvec, void* stream);
+
+/* losses.py:481-495 StereoPoseLoss.__call__: stereo_T_LR [B,4,4], pose_lr / pose_rl [B,num,6] ->
+ * loss_batch [B] (may be NULL).  d_pose_lr / d_pose_rl (may be NULL) receive
+ * d(sum_b grad_loss_batch[b] * loss_batch[b]) / d pose_* (grad_loss_batch NULL = all ones).            */
+XPT_API int xpt_stereo_pose_loss(int device, const float* stereo_T_LR, const float* pose_lr, const float* pose_rl,
+                                 int batch, int num, float* loss_batch, const float* grad_loss_batch,
+                                 float* d_pose_lr, float* d_pose_rl, void* stream);
+
 /* utils/util_funcs.py:163-175 multi_scale_like_depth (target pyramid) and
  * synthesize_base.py:74-85 resize_source_images (source pyramid, kept inside
  * the ctx).  target_ms[s] may be NULL (level not wanted); level 0 is a copy.  */

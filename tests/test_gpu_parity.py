@@ -408,3 +408,55 @@ def test_cuda_graph_replay_matches_eager(xw):
                 assert torch.equal(got["losses"], want[i]["losses"])
                 assert torch.equal(got["d_pose"], want[i]["d_pose"])
                 assert all(torch.equal(a, b) for a, b in zip(got["d_depth_ms"], want[i]["d_depth_ms"]))
+
+
+# ---- stereo rig: TotalLoss(stereo=True) as configured in LOSS_RIGID_T1 / T2 -------------------
+def _stereo_cuda(feats, preds):
+    f = {k: v.cuda() for k, v in feats.items()}
+    p = {k: ([t.cuda().requires_grad_(True) for t in v] if isinstance(v, list) else v.cuda().requires_grad_(True))
+         for k, v in preds.items()}
+    return f, p
+
+
+@pytest.mark.parametrize("path", ["fused", "objects"])
+@pytest.mark.parametrize("name", ["stereo_t1", "stereo_t2"])
+def test_stereo_total_loss_against_golden(xw, name, path, monkeypatch):
+    """Both eyes' temporal losses, the two stereo syntheses (losses.py:105-140), StereoDepthLoss and
+    StereoPoseLoss through loss_factory -> TotalLoss(stereo=True) against the reference's own source; once as
+    four fused launches and once loss object by loss object (SynthesizeMultiScale + per-loss kernels)."""
+    from helpers import PRED_KEYS, golden_grad, stereo_case_inputs
+    g, g64 = load_case(name), load_case(name, "f64")
+    feats, preds, lw, sw, gb = stereo_case_inputs(g)
+    f, p = _stereo_cuda(feats, preds)
+    cfg = {"image": 1, "intrinsic": 1, "image_R": 1, "intrinsic_R": 1, "stereo_T_LR": 1}
+    total_obj = xw.loss_factory(cfg, lw, np.array(sw), stereo=True, batch_size=gb)
+    if path == "objects":
+        monkeypatch.setattr(type(total_obj), "_fused_ok", lambda self, pr, ft: False)
+    total, by_type = total_obj(p, f)
+    total.backward()
+    torch.cuda.synchronize()
+    assert relerr(total.item(), g["total"]) < LOSS_TOL and relerr(total.item(), g64["total"]) < LOSS_TOL
+    for k in lw:
+        assert relerr(by_type[k].item(), g["loss_" + k]) < 2 * LOSS_TOL, k
+    for k in PRED_KEYS:
+        ref, ref64, got = golden_grad(g, k), golden_grad(g64, k), p[k]
+        if isinstance(ref, list):
+            for s in range(len(ref)):
+                ok, msg = grad_close(got[s].grad.cpu().numpy(), ref[s], ref64[s], GRAD_TOL)
+                assert ok, (k, s, msg)
+        else:
+            tol = max(GRAD_TOL, 3 * relerr(ref, ref64))
+            assert relerr(got.grad.cpu().numpy(), ref64) < tol, k
+
+
+def test_pose_matr2rvec_against_oracle(xw):
+    from oracle import xpt_oracle as orc
+    g = torch.Generator().manual_seed(9)
+    pose = torch.rand(6, 3, 6, generator=g) - 0.5
+    pose[0, 0, 3:] = torch.tensor([0.004, -0.003, 0.002])          # a rig-sized rotation (acos is ill-conditioned there)
+    T = orc.pose_rvec2matr_batch(pose.double()).float()
+    got = xw.pose_matr2rvec_batch(T.cuda()).cpu()
+    assert relerr(got.numpy(), orc.pose_matr2rvec_batch(T).numpy()) < 1e-5
+    got_inv = xw.pose_matr2rvec_batch(T.cuda(), invert=True).cpu()
+    ref_inv = orc.pose_matr2rvec_batch(torch.linalg.inv(T.double())).float()
+    assert relerr(got_inv[1:].numpy(), ref_inv[1:].numpy()) < 1e-4

@@ -1272,6 +1272,83 @@ __global__ void __launch_bounds__(256) k_drain(DrainArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// stereo rig poses (losses.py:105-140, :481-495; utils/convert_pose.py:151-168)
+// ---------------------------------------------------------------------------
+// general 4x4 inverse (tf.linalg.inv): Gauss-Jordan with partial pivoting in fp64, rounded once
+__device__ inline void invert4x4(const float* __restrict__ m, float* __restrict__ out) {
+  double a[4][8];
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) { a[r][c] = m[r * 4 + c]; a[r][4 + c] = r == c ? 1.0 : 0.0; }
+  for (int col = 0; col < 4; ++col) {
+    int piv = col;
+    for (int r = col + 1; r < 4; ++r)
+      if (fabs(a[r][col]) > fabs(a[piv][col])) piv = r;
+    if (piv != col)
+      for (int c = 0; c < 8; ++c) { double t = a[col][c]; a[col][c] = a[piv][c]; a[piv][c] = t; }
+    const double inv = 1.0 / a[col][col];
+    for (int c = 0; c < 8; ++c) a[col][c] *= inv;
+    for (int r = 0; r < 4; ++r) {
+      if (r == col) continue;
+      const double f = a[r][col];
+      for (int c = 0; c < 8; ++c) a[r][c] -= f * a[col][c];
+    }
+  }
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) out[r * 4 + c] = (float)a[r][4 + c];
+}
+
+// pose_matr2rvec_batch: fp32, the reference's operation order (theta = acos((tr R - 1)/2) is ill-conditioned
+// for the small rig rotations, so the SAME roundings as the reference matter more than extra precision)
+__device__ inline void matr2rvec(const float* __restrict__ m, float* __restrict__ out) {
+  const float tr = (m[0] + m[5]) + m[10];
+  const float theta = acosf((tr - 1.f) / 2.f);
+  const float ax[3] = {m[6] - m[9], m[8] - m[2], m[1] - m[4]};
+  out[0] = m[3]; out[1] = m[7]; out[2] = m[11];
+  if (fabsf(theta) < 0.00001f) {
+    for (int k = 0; k < 3; ++k) out[3 + k] = ax[k] / 2.f;
+  } else {
+    const float den = 2.f * sinf(theta);
+    for (int k = 0; k < 3; ++k) out[3 + k] = ax[k] / den * theta;
+  }
+}
+
+__global__ void k_pose_matr2rvec(const float* __restrict__ matr, int count, int invert, float* __restrict__ rvec) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float m[16];
+  if (invert) invert4x4(matr + (size_t)i * 16, m);
+  else for (int k = 0; k < 16; ++k) m[k] = matr[(size_t)i * 16 + k];
+  matr2rvec(m, rvec + (size_t)i * 6);
+}
+
+// StereoPoseLoss: loss[b] = mean_n [ MSE6(rvec(T_LR), pose_lr[b,n]) + MSE6(rvec(inv T_LR), pose_rl[b,n]) ]
+// and its gradient w.r.t. both predictions scaled by gscale[b] (NULL = 1).  One thread per snippet.
+__global__ void k_stereo_pose_loss(const float* __restrict__ T_LR, const float* __restrict__ pose_lr,
+                                   const float* __restrict__ pose_rl, int B, int n, float* __restrict__ loss_batch,
+                                   const float* __restrict__ gscale, float* __restrict__ d_lr, float* __restrict__ d_rl) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float inv[16], lr[6], rl[6];
+  matr2rvec(T_LR + (size_t)b * 16, lr);
+  invert4x4(T_LR + (size_t)b * 16, inv);
+  matr2rvec(inv, rl);
+  const float g = (gscale ? gscale[b] : 1.f) * (2.f / (6.f * (float)n));
+  float acc = 0.f;
+  for (int j = 0; j < n; ++j) {
+    float s0 = 0.f, s1 = 0.f;
+    for (int k = 0; k < 6; ++k) {
+      const size_t o = ((size_t)b * n + j) * 6 + k;
+      const float e0 = lr[k] - pose_lr[o], e1 = rl[k] - pose_rl[o];
+      s0 += e0 * e0; s1 += e1 * e1;
+      if (d_lr) d_lr[o] = -g * e0;
+      if (d_rl) d_rl[o] = -g * e1;
+    }
+    acc += s0 / 6.f + s1 / 6.f;
+  }
+  if (loss_batch) loss_batch[b] = acc / (float)n;
+}
+
 __global__ void k_fill(float* __restrict__ p, long long n, float v) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;

@@ -602,6 +602,29 @@ int xpt_get_config(const xpt_ctx* ctx, xpt_config* out) {
 size_t xpt_scratch_bytes(const xpt_ctx* ctx) { return ctx ? ctx->scratch_bytes : 0; }
 int xpt_last_launch_count(const xpt_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int xpt_pose_matr2rvec(int device, const float* matr, int count, int invert, float* rvec, void* stream) {
+  if (!matr || !rvec || count < 0) return fail(XPT_BAD_ARGUMENT, "xpt_pose_matr2rvec: bad argument");
+  XPT_CUDA(cudaSetDevice(device));
+  if (count == 0) return XPT_OK;
+  k_pose_matr2rvec<<<cdiv(count, 128), 128, 0, (cudaStream_t)stream>>>(matr, count, invert, rvec);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(XPT_CUDA_ERROR, "launch of k_pose_matr2rvec failed: %s", cudaGetErrorString(e));
+  return XPT_OK;
+}
+
+int xpt_stereo_pose_loss(int device, const float* stereo_T_LR, const float* pose_lr, const float* pose_rl, int batch,
+                         int num, float* loss_batch, const float* grad_loss_batch, float* d_pose_lr, float* d_pose_rl,
+                         void* stream) {
+  if (!stereo_T_LR || !pose_lr || !pose_rl || batch <= 0 || num <= 0)
+    return fail(XPT_BAD_ARGUMENT, "xpt_stereo_pose_loss: bad argument");
+  XPT_CUDA(cudaSetDevice(device));
+  k_stereo_pose_loss<<<cdiv(batch, 64), 64, 0, (cudaStream_t)stream>>>(stereo_T_LR, pose_lr, pose_rl, batch, num, loss_batch,
+                                                                        grad_loss_batch, d_pose_lr, d_pose_rl);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(XPT_CUDA_ERROR, "launch of k_stereo_pose_loss failed: %s", cudaGetErrorString(e));
+  return XPT_OK;
+}
+
 int xpt_pose_rvec2matr(xpt_ctx* ctx, const float* pose, float* matr, void* stream) {
   if (!ctx || !pose || !matr) return fail(XPT_BAD_ARGUMENT, "xpt_pose_rvec2matr: NULL argument");
   XPT_CUDA(cudaSetDevice(ctx->cfg.device));

@@ -9,11 +9,13 @@ include/xptwarp.h); this package mirrors the reference's Python call surface:
     model/loss_and_metric/losses.*LossMultiScale          xptwarp.losses.*
     model/loss_and_metric/loss_factory.loss_factory       xptwarp.loss_factory
     utils/convert_pose.pose_rvec2matr_batch_tf            xptwarp.pose_rvec2matr_batch_tf
+    utils/convert_pose.pose_matr2rvec_batch               xptwarp.pose_matr2rvec_batch
     utils/util_funcs.multi_scale_like_depth               xptwarp.multi_scale_like_depth
 """
 from .engine import Plan, WrongInputException, get_plan  # noqa: F401
 from .synthesize import SynthesizeMultiScale  # noqa: F401
-from .losses import (TotalLoss, PhotometricLossMultiScale, SmoothenessLossMultiScale)  # noqa: F401
+from .losses import (TotalLoss, PhotometricLossMultiScale, SmoothenessLossMultiScale, StereoDepthLoss,  # noqa: F401
+                     StereoPoseLoss)
 from .loss_factory import loss_factory, check_loss_dependency  # noqa: F401
-from .convert_pose import pose_rvec2matr_batch_tf  # noqa: F401
+from .convert_pose import pose_rvec2matr_batch_tf, pose_matr2rvec_batch  # noqa: F401
 from .util_funcs import multi_scale_like_depth, safe_reciprocal_number, safe_reciprocal_number_ms  # noqa: F401

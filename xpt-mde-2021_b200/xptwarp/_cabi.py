@@ -56,6 +56,9 @@ SYMBOLS = {
     "xpt_get_config": (C.c_int, [C.c_void_p, C.POINTER(XptConfig)]),
     "xpt_scratch_bytes": (C.c_size_t, [C.c_void_p]),
     "xpt_pose_rvec2matr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "xpt_pose_matr2rvec": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "xpt_stereo_pose_loss": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xpt_build_pyramids": (C.c_int, [C.c_void_p, C.POINTER(XptFrames), C.POINTER(PtrArray), C.c_void_p]),
     "xpt_synthesize": (C.c_int, [C.c_void_p, C.POINTER(XptFrames), C.POINTER(PtrArray), C.c_void_p,
                                  C.POINTER(PtrArray), C.POINTER(PtrArray), C.c_void_p]),

@@ -6,8 +6,7 @@ import numpy as np
 from . import losses as lm
 
 _OUTSIDE = ["md2L1", "md2L1_R", "md2SSIM", "md2SSIM_R", "cmbL1", "cmbL1_R", "cmbSSIM", "cmbSSIM_R",
-            "moaL1", "moaL1_R", "moaSSIM", "moaSSIM_R", "stereoL1", "stereoSSIM", "stereoPose",
-            "flowL2", "flowL2_R", "flow_reg"]
+            "moaL1", "moaL1_R", "moaSSIM", "moaSSIM_R", "flowL2", "flowL2_R", "flow_reg"]
 
 
 def loss_factory(dataset_cfg, loss_weights, scale_weights, stereo=False, weights_to_regularize=None, batch_size=1):
@@ -21,6 +20,9 @@ def loss_factory(dataset_cfg, loss_weights, scale_weights, stereo=False, weights
         "SSIM_R": lm.PhotometricLossMultiScale("SSIM", scale_weights, key_suffix="_R"),
         "smoothe": lm.SmoothenessLossMultiScale(scale_weights),
         "smoothe_R": lm.SmoothenessLossMultiScale(scale_weights, key_suffix="_R"),
+        "stereoL1": lm.StereoDepthLoss("L1", scale_weights),
+        "stereoSSIM": lm.StereoDepthLoss("SSIM", scale_weights),
+        "stereoPose": lm.StereoPoseLoss(),
     }
     for name in _OUTSIDE:
         loss_pool[name] = lm._OutsideHotPath(name)

@@ -3,14 +3,20 @@ TotalLoss, PhotometricLossMultiScale, SmoothenessLossMultiScale (+ the per-scale
 loss_util.py through the same kernels)."""
 from __future__ import annotations
 
+import ctypes as C
+
 import torch
 
 from . import _cabi
+from .convert_pose import pose_matr2rvec_batch
 from .engine import WrongInputException, as_torch, get_plan, infer_scales, require_cuda_f32
 from .synthesize import SynthesizeMultiScale
 from .util_funcs import multi_scale_like_depth
 
-_FUSED_SET = ("L1", "SSIM", "smoothe")
+# losses the fused tile kernel evaluates (one launch per group): the temporal set of each eye, the two stereo
+# syntheses of StereoDepthLoss; StereoPoseLoss is a tiny kernel of its own
+_TEMPORAL = ("L1", "SSIM", "smoothe")
+_FUSED_SET = _TEMPORAL + tuple(n + "_R" for n in _TEMPORAL) + ("stereoL1", "stereoSSIM", "stereoPose")
 
 
 def _scale_weights_list(scale_weights):
@@ -26,10 +32,9 @@ class _TotalLossFn(torch.autograd.Function):
     (the loss is linear in its upstream gradient)."""
 
     @staticmethod
-    def forward(ctx, plan, want_grad, image5d, intrinsic, pose, *maps):
+    def forward(ctx, plan, want_grad, source, target, intrinsic, pose, *maps):
         S = plan.S
         depth_ms, disp_ms = maps[:S], (maps[S:] if len(maps) > S else None)
-        source, target = image5d[:, :-1], image5d[:, -1]
         r = plan.total_loss(source, target, intrinsic, depth_ms, disp_ms, pose, want_grad=want_grad)
         losses = r["losses"]
         if want_grad:
@@ -47,7 +52,30 @@ class _TotalLossFn(torch.autograd.Function):
             raise RuntimeError("TotalLoss was evaluated without gradients")
         d_pose, *d_maps = ctx.saved_tensors
         outs = [g_total * d.reshape(s) for d, s in zip(d_maps, ctx.shapes)]
-        return (None, None, None, None, g_total * d_pose, *outs)
+        return (None, None, None, None, None, g_total * d_pose, *outs)
+
+
+class _StereoPoseFn(torch.autograd.Function):
+    """StereoPoseLoss forward + both gradients in one tiny launch (xpt_stereo_pose_loss)."""
+
+    @staticmethod
+    def forward(ctx, T_LR, pose_lr, pose_rl):
+        T_LR, pose_lr, pose_rl = T_LR.contiguous(), pose_lr.contiguous(), pose_rl.contiguous()
+        B, n = pose_lr.shape[:2]
+        loss = torch.empty((B,), dtype=torch.float32, device=pose_lr.device)
+        d_lr, d_rl = torch.empty_like(pose_lr), torch.empty_like(pose_rl)
+        st = C.c_void_p(torch.cuda.current_stream(pose_lr.device).cuda_stream)
+        _cabi.check(_cabi.lib().xpt_stereo_pose_loss(pose_lr.device.index or 0, T_LR.data_ptr(), pose_lr.data_ptr(),
+                                                     pose_rl.data_ptr(), B, n, loss.data_ptr(), None,
+                                                     d_lr.data_ptr(), d_rl.data_ptr(), st))
+        ctx.save_for_backward(d_lr, d_rl)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        d_lr, d_rl = ctx.saved_tensors
+        g = g.reshape(-1, 1, 1)
+        return None, g * d_lr, g * d_rl
 
 
 class _PhotoFn(torch.autograd.Function):
@@ -135,6 +163,31 @@ class SmoothenessLossMultiScale(LossBase):
         return _SmoothFn.apply(plan, plan.S, *disp_ms, *target_ms)
 
 
+class StereoDepthLoss(PhotometricLoss):
+    """reference losses.py:443-478: photometric loss of the left view synthesised from the right frame plus
+    that of the right view synthesised from the left frame (both N = 1), summed per scale, then merged."""
+
+    def __init__(self, method, scale_weights):
+        super().__init__(method, scale_weights)
+
+    def __call__(self, features, predictions, augm_data):
+        left = PhotometricLossMultiScale(self.method, self.scale_weights)(
+            features, predictions, {"synth_target_ms": augm_data["stereo_synth_ms"], "target_ms": augm_data["target_ms"]})
+        right = PhotometricLossMultiScale(self.method, self.scale_weights)(
+            features, predictions, {"synth_target_ms": augm_data["stereo_synth_ms_R"], "target_ms": augm_data["target_ms_R"]})
+        return left + right
+
+
+class StereoPoseLoss(LossBase):
+    """reference losses.py:481-495."""
+
+    def __call__(self, features, predictions, augm_data):
+        T = as_torch(features["stereo_T_LR"])
+        lr, rl = as_torch(predictions["pose_LR"]), as_torch(predictions["pose_RL"])
+        require_cuda_f32(stereo_T_LR=T, pose_LR=lr, pose_RL=rl)
+        return _StereoPoseFn.apply(T, lr, rl)
+
+
 class _OutsideHotPath(LossBase):
     def __init__(self, name):
         self.name = name
@@ -153,28 +206,38 @@ class TotalLoss:
         self.stereo = stereo
         self.batch_size = batch_size
 
+    def _stereo_on(self, features):
+        """losses.py:38: the right eye and the stereo syntheses are used when the rig flag is set and the
+        dataset carries right frames (the reference tests the key "image_R" and then reads "image5d_R")."""
+        return bool(self.stereo) and ("image_R" in features or "image5d_R" in features)
+
     def _fused_ok(self, predictions, features):
         if not self.loss_objects or any(k not in _FUSED_SET for k in self.loss_objects):
-            return False
-        if self.stereo and ("image5d_R" in features):
             return False
         sw = None
         for obj in self.loss_objects.values():
             w = _scale_weights_list(getattr(obj, "scale_weights", None))
+            if w is None:
+                continue
             if sw is not None and w != sw:
                 return False
             sw = w
-        return "depth_ms" in predictions and "pose" in predictions and "flow_ms" not in predictions
+        return sw is not None and "depth_ms" in predictions and "pose" in predictions and "flow_ms" not in predictions
 
     def __call__(self, predictions, features):
         """
         :param predictions: {"depth_ms": [...], "disp_ms": [...], "pose": [batch, numsrc, 6]}
+                            (+ the same keys with "_R", "pose_LR", "pose_RL" on a stereo rig)
         :param features: {"image5d": [batch, snippet, height, width, 3], "intrinsic": [batch, 3, 3]}
+                         (+ "image5d_R", "intrinsic_R", "stereo_T_LR" [batch, 4, 4] on a stereo rig)
         :return: total_loss (scalar), loss_by_type {name: unweighted mean}
         """
         if self._fused_ok(predictions, features):
             return self._call_fused(predictions, features)
         augm_data = self.append_data(features, predictions)
+        if self._stereo_on(features):
+            augm_data.update(self.append_data(features, predictions, "_R"))
+            augm_data.update(self.synethesize_stereo(features, predictions, augm_data))
         losses, loss_by_type = [], dict()
         for loss_name in self.loss_objects:
             loss_batch = self.loss_objects[loss_name](features, predictions, augm_data)
@@ -183,24 +246,80 @@ class TotalLoss:
             loss_by_type[loss_name] = loss_mean
         return torch.stack(losses).sum(), loss_by_type
 
-    def _call_fused(self, predictions, features):
-        image5d = as_torch(features["image5d"])
-        intrinsic = as_torch(features["intrinsic"])
-        depth_ms = [as_torch(d) for d in predictions["depth_ms"]]
-        pose = as_torch(predictions["pose"])
-        require_cuda_f32(image5d=image5d, intrinsic=intrinsic, pose=pose, depth_ms=depth_ms)
-        B, F, H, W, _ = image5d.shape
-        w = {k: float(self.loss_weights[k]) for k in self.loss_objects}
-        sw = _scale_weights_list(next(iter(self.loss_objects.values())).scale_weights)
-        plan = get_plan(image5d.device.index or 0, B, F - 1, H, W, infer_scales(H, depth_ms), sw,
-                        w.get("L1", 0.0), w.get("SSIM", 0.0), w.get("smoothe", 0.0), self.batch_size)
-        maps = list(depth_ms)
-        if "smoothe" in w:
-            maps += [as_torch(d) for d in predictions["disp_ms"]]
+    def _fused_group(self, source, target, intrinsic, depth_ms, disp_ms, pose, w_l1, w_ssim, w_smooth, sw):
+        """one fused launch: (total contribution, [L1, SSIM, smoothe] unweighted means)"""
+        B, N, H, W, _ = source.shape
+        plan = get_plan(source.device.index or 0, B, N, H, W, infer_scales(H, depth_ms), sw, w_l1, w_ssim, w_smooth,
+                        self.batch_size)
+        maps = list(depth_ms) + (list(disp_ms) if w_smooth != 0.0 else [])
         want_grad = torch.is_grad_enabled() and any(t.requires_grad for t in [pose, *maps])
-        total, by_type = _TotalLossFn.apply(plan, want_grad, image5d, intrinsic, pose, *maps)
-        names = ("L1", "SSIM", "smoothe")
-        return total, {k: by_type[names.index(k)] for k in self.loss_objects}
+        return _TotalLossFn.apply(plan, want_grad, source, target, intrinsic, pose, *maps)
+
+    def _call_fused(self, predictions, features):
+        w = {k: float(self.loss_weights[k]) for k in self.loss_objects}
+        sw = next(v for v in (_scale_weights_list(getattr(o, "scale_weights", None)) for o in self.loss_objects.values())
+                  if v is not None)
+        stereo = self._stereo_on(features)
+        totals, by = [], {}
+        eyes = {}
+        for sfx in ("", "_R"):
+            names = [n + sfx for n in _TEMPORAL if n + sfx in w]
+            need = names or (stereo and ("stereoL1" in w or "stereoSSIM" in w))
+            if not need:
+                continue
+            if sfx and not stereo:
+                raise WrongInputException(f"losses {names} need a stereo rig: TotalLoss(stereo=True) and image5d_R in features")
+            image5d, K = as_torch(features["image5d" + sfx]), as_torch(features["intrinsic" + sfx])
+            depth_ms = [as_torch(d) for d in predictions["depth_ms" + sfx]]
+            require_cuda_f32(**{"image5d" + sfx: image5d, "intrinsic" + sfx: K, "depth_ms" + sfx: depth_ms})
+            eyes[sfx] = (image5d, K, depth_ms)
+            if not names:
+                continue
+            pose = as_torch(predictions["pose" + sfx])
+            disp_ms = [as_torch(d) for d in predictions["disp_ms" + sfx]] if "smoothe" + sfx in w else None
+            total, by_type = self._fused_group(image5d[:, :-1], image5d[:, -1], K, depth_ms, disp_ms, pose,
+                                               w.get("L1" + sfx, 0.0), w.get("SSIM" + sfx, 0.0), w.get("smoothe" + sfx, 0.0), sw)
+            totals.append(total)
+            for i, n in enumerate(_TEMPORAL):
+                if n + sfx in w:
+                    by[n + sfx] = by_type[i]
+        if "stereoL1" in w or "stereoSSIM" in w:
+            # StereoDepthLoss (losses.py:443-478) over the two syntheses of losses.py:105-140: the fused kernel with
+            # ONE source frame (the other eye's target), the rig transform as the pose and -- like the reference --
+            # the LEFT intrinsics for both directions
+            if not stereo or "stereo_T_LR" not in features:
+                raise WrongInputException("stereoL1 / stereoSSIM need TotalLoss(stereo=True), image5d_R and stereo_T_LR")
+            T = as_torch(features["stereo_T_LR"])
+            require_cuda_f32(stereo_T_LR=T)
+            (img_l, K_l, depth_l), (img_r, _, depth_r) = eyes[""], eyes["_R"]
+            parts = []
+            for src_img, tgt_img, depth_ms, inv in ((img_r, img_l, depth_l, True), (img_l, img_r, depth_r, False)):
+                rig = pose_matr2rvec_batch(T.unsqueeze(1), invert=inv)
+                parts.append(self._fused_group(src_img[:, -1:], tgt_img[:, -1], K_l, depth_ms, None, rig,
+                                               w.get("stereoL1", 0.0), w.get("stereoSSIM", 0.0), 0.0, sw))
+            totals += [parts[0][0], parts[1][0]]
+            if "stereoL1" in w:
+                by["stereoL1"] = parts[0][1][0] + parts[1][1][0]
+            if "stereoSSIM" in w:
+                by["stereoSSIM"] = parts[0][1][1] + parts[1][1][1]
+        if "stereoPose" in w:
+            mean = self.loss_objects["stereoPose"](features, predictions, None).sum() / self.batch_size
+            by["stereoPose"] = mean
+            totals.append(mean * w["stereoPose"])
+        return torch.stack(totals).sum(), {k: by[k] for k in self.loss_objects}
+
+    def synethesize_stereo(self, features, predictions, augm_data):
+        """reference losses.py:105-140 (the method name is the reference's)."""
+        synth_stereo = dict()
+        if ("stereo_T_LR" not in features) or ("depth_ms" not in predictions):
+            return synth_stereo
+        T = as_torch(features["stereo_T_LR"])
+        K = as_torch(features["intrinsic"])
+        synth_stereo["stereo_synth_ms"] = SynthesizeMultiScale()(
+            augm_data["target_R"].unsqueeze(1), K, predictions["depth_ms"], pose_matr2rvec_batch(T.unsqueeze(1), invert=True))
+        synth_stereo["stereo_synth_ms_R"] = SynthesizeMultiScale()(
+            augm_data["target"].unsqueeze(1), K, predictions["depth_ms_R"], pose_matr2rvec_batch(T.unsqueeze(1)))
+        return synth_stereo
 
     def append_data(self, features, predictions, suffix=""):
         """reference losses.py:57-103 (the target frame is the LAST one of the snippet)."""
