@@ -168,6 +168,19 @@ XPT_API int xpt_photometric_loss(xpt_ctx* ctx, int method,
                          float* loss_batch, const float* grad_loss_batch,
                          float* const d_synth_ms[], void* stream);
 
+/* losses.py:198-232 MonoDepth2LossMultiScale(method).__call__ and, with stereo_synth_ms != NULL,
+ * losses.py:282-321 MoALossMultiScale(method).__call__: every scale's synthesis [B,N,h,w,3] (and the
+ * stereo synthesis [B,1,h,w,3]) is bilinearly up-sampled to H x W (losses.py:377-383), compared with
+ * the FULL-RESOLUTION target [B,H,W,3] per pixel and channel, the minimum over the N (+1) sources is
+ * taken and averaged -> loss_batch [B] (scale-merged, losses.py:147-154).
+ * If d_synth_ms != NULL also writes d(sum_b grad_loss_batch[b]*loss_batch[b]) / d synth_ms[s]
+ * (and / d stereo_synth_ms[s] into d_stereo_synth_ms[s]); tf.reduce_min's rule: ties share equally.  */
+XPT_API int xpt_photometric_min_loss(xpt_ctx* ctx, int method,
+                             const float* const synth_ms[], const float* const stereo_synth_ms[],
+                             const float* target, int64_t target_batch_stride, float* loss_batch,
+                             const float* grad_loss_batch, float* const d_synth_ms[],
+                             float* const d_stereo_synth_ms[], void* stream);
+
 /* losses.py:386-440 SmoothenessLossMultiScale.__call__ -> loss_batch [B];
  * optional backward to d_disp_ms as above.                                    */
 XPT_API int xpt_smoothness_loss(xpt_ctx* ctx, const float* const disp_ms[],

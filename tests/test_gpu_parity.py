@@ -419,12 +419,14 @@ def _stereo_cuda(feats, preds):
 
 
 @pytest.mark.parametrize("path", ["fused", "objects"])
-@pytest.mark.parametrize("name", ["stereo_t1", "stereo_t2"])
+@pytest.mark.parametrize("name", ["stereo_t1", "stereo_t2", "stereo_moa", "stereo_md2"])
 def test_stereo_total_loss_against_golden(xw, name, path, monkeypatch):
     """Both eyes' temporal losses, the two stereo syntheses (losses.py:105-140), StereoDepthLoss and
     StereoPoseLoss through loss_factory -> TotalLoss(stereo=True) against the reference's own source; once as
     four fused launches and once loss object by loss object (SynthesizeMultiScale + per-loss kernels)."""
     from helpers import PRED_KEYS, golden_grad, stereo_case_inputs
+    if path == "fused" and name in ("stereo_moa", "stereo_md2"):
+        pytest.skip("the min-over-sources losses (MoA / MonoDepth2) run loss object by loss object")
     g, g64 = load_case(name), load_case(name, "f64")
     feats, preds, lw, sw, gb = stereo_case_inputs(g)
     f, p = _stereo_cuda(feats, preds)

@@ -15,6 +15,7 @@
 
 #include "xpt_kernels.cuh"
 #include "xpt_fused.cuh"
+#include "xpt_minloss.cuh"
 
 using namespace xpt;
 
@@ -78,6 +79,7 @@ struct xpt_ctx {
   float* gsynth_scr[kMaxScales];
   float* dsrc_lvl[kMaxScales];  // s > 1
   float* tgt0_copy;             // unused unless a level-0 copy is wanted without a user buffer
+  float* min_part;              // [B][S * full-res tiles] partial sums of xpt_photometric_min_loss
   // staging for the host-buffer entry point
   float* st_frames; float* st_K; float* st_pose; float* st_losses; float* st_loss_batch; float* st_dpose;
   float* st_dsource;
@@ -563,7 +565,7 @@ void xpt_destroy(xpt_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->cfg.device);
   auto F = [](float* p) { if (p) cudaFree(p); };
-  F(ctx->geoK); F(reinterpret_cast<float*>(ctx->loss_sum_b)); F(ctx->loss_part); F(ctx->pose_part); F(ctx->tgt0_copy);
+  F(ctx->geoK); F(reinterpret_cast<float*>(ctx->loss_sum_b)); F(ctx->loss_part); F(ctx->pose_part); F(ctx->tgt0_copy); F(ctx->min_part);
   F(ctx->st_frames); F(ctx->st_K); F(ctx->st_pose); F(ctx->st_losses); F(ctx->st_loss_batch); F(ctx->st_dpose);
   F(ctx->st_dsource);
   for (int l = 0; l < kMaxScales; ++l) {
@@ -703,6 +705,62 @@ int xpt_photometric_loss(xpt_ctx* ctx, int method, const float* const synth_ms[]
   XPT_TRY(launch_loss_epilogue(ctx, ctx->first_tile[ctx->S], 0.f, 0.f, 0.f, nullptr, lb3, st));
   int col = method == XPT_PHOTO_SSIM ? 1 : 0;
   XPT_CUDA(cudaMemcpyAsync(loss_batch, lb3 + (size_t)col * ctx->B, ctx->B * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return XPT_OK;
+}
+
+int xpt_photometric_min_loss(xpt_ctx* ctx, int method, const float* const synth_ms[], const float* const stereo_synth_ms[],
+                             const float* target, int64_t target_batch_stride, float* loss_batch,
+                             const float* grad_loss_batch, float* const d_synth_ms[], float* const d_stereo_synth_ms[],
+                             void* stream) {
+  if (!ctx || !loss_batch || !target) return fail(XPT_BAD_ARGUMENT, "xpt_photometric_min_loss: NULL argument");
+  if (method != XPT_PHOTO_L1 && method != XPT_PHOTO_L2 && method != XPT_PHOTO_SSIM)
+    return fail(XPT_BAD_ARGUMENT, "unknown photometric method %d", method);
+  XPT_TRY(check_list(ctx, (const void* const*)synth_ms, "synth_ms", true));
+  if (stereo_synth_ms) XPT_TRY(check_list(ctx, (const void* const*)stereo_synth_ms, "stereo_synth_ms", true));
+  if (d_synth_ms) XPT_TRY(check_list(ctx, (const void* const*)d_synth_ms, "d_synth_ms", true));
+  if (d_synth_ms && stereo_synth_ms) XPT_TRY(check_list(ctx, (const void* const*)d_stereo_synth_ms, "d_stereo_synth_ms", true));
+  if (ctx->B > 1 && target_batch_stride < (int64_t)ctx->H * ctx->W * 3) return fail(XPT_BAD_SHAPE, "target_batch_stride too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  XPT_CUDA(cudaSetDevice(ctx->cfg.device));
+  ctx->launches = 0;
+  MinLossArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = ctx->B; a.N = ctx->N; a.NS = stereo_synth_ms ? 1 : 0; a.H = ctx->H; a.W = ctx->W; a.S = ctx->S;
+  a.target = target; a.tgt_bs = target_batch_stride;
+  a.method = method == XPT_PHOTO_L1 ? 0 : (method == XPT_PHOTO_L2 ? 1 : 2);
+  a.gbatch = grad_loss_batch;
+  a.tiles_x = cdiv(ctx->W, kTW);
+  a.tiles = a.tiles_x * cdiv(ctx->H, kTH);
+  XPT_TRY(dev_alloc(ctx, &ctx->min_part, (size_t)ctx->B * ctx->S * a.tiles));
+  a.loss_part = ctx->min_part;
+  for (int l = 0; l < ctx->S; ++l) {
+    a.h[l] = ctx->h[l]; a.w[l] = ctx->w[l];
+    a.synth[l] = synth_ms[l]; a.stereo[l] = stereo_synth_ms ? stereo_synth_ms[l] : nullptr;
+    a.norm[l] = (float)((double)ctx->cfg.scale_weights[l] / ((double)ctx->H * ctx->W * 3.0));
+    if (d_synth_ms) {
+      a.gsynth[l] = d_synth_ms[l];
+      XPT_CUDA(cudaMemsetAsync(d_synth_ms[l], 0, (size_t)ctx->B * ctx->N * lvl_pix(ctx, l) * 3 * sizeof(float), st));
+      if (stereo_synth_ms) {
+        a.gstereo[l] = d_stereo_synth_ms[l];
+        XPT_CUDA(cudaMemsetAsync(d_stereo_synth_ms[l], 0, (size_t)ctx->B * lvl_pix(ctx, l) * 3 * sizeof(float), st));
+      }
+    }
+  }
+  dim3 grid(ctx->S * a.tiles, ctx->B);
+  if (d_synth_ms) {
+    static bool attr = false;
+    const size_t smem = MinLossSmem<true>::kBytes;
+    if (!attr) { XPT_CUDA(cudaFuncSetAttribute(k_photo_min<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    k_photo_min<true><<<grid, kPhotoThreads, smem, st>>>(a);
+  } else {
+    static bool attr = false;
+    const size_t smem = MinLossSmem<false>::kBytes;
+    if (!attr) { XPT_CUDA(cudaFuncSetAttribute(k_photo_min<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    k_photo_min<false><<<grid, kPhotoThreads, smem, st>>>(a);
+  }
+  XPT_LAUNCH_CHECK("k_photo_min");
+  k_sum_slots<<<ctx->B, 128, 0, st>>>(ctx->min_part, ctx->S * a.tiles, loss_batch);
+  XPT_LAUNCH_CHECK("k_sum_slots");
   return XPT_OK;
 }
 

@@ -15,7 +15,7 @@ include/xptwarp.h); this package mirrors the reference's Python call surface:
 from .engine import Plan, WrongInputException, get_plan  # noqa: F401
 from .synthesize import SynthesizeMultiScale  # noqa: F401
 from .losses import (TotalLoss, PhotometricLossMultiScale, SmoothenessLossMultiScale, StereoDepthLoss,  # noqa: F401
-                     StereoPoseLoss)
+                     StereoPoseLoss, MonoDepth2LossMultiScale, MoALossMultiScale)
 from .loss_factory import loss_factory, check_loss_dependency  # noqa: F401
 from .convert_pose import pose_rvec2matr_batch_tf, pose_matr2rvec_batch  # noqa: F401
 from .util_funcs import multi_scale_like_depth, safe_reciprocal_number, safe_reciprocal_number_ms  # noqa: F401

@@ -67,6 +67,9 @@ SYMBOLS = {
                                           C.c_void_p]),
     "xpt_photometric_loss": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(PtrArray), C.POINTER(PtrArray), C.c_void_p,
                                        C.c_void_p, C.POINTER(PtrArray), C.c_void_p]),
+    "xpt_photometric_min_loss": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(PtrArray), C.POINTER(PtrArray), C.c_void_p,
+                                           C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(PtrArray), C.POINTER(PtrArray),
+                                           C.c_void_p]),
     "xpt_smoothness_loss": (C.c_int, [C.c_void_p, C.POINTER(PtrArray), C.POINTER(PtrArray), C.c_void_p,
                                       C.c_void_p, C.POINTER(PtrArray), C.c_void_p]),
     "xpt_total_loss": (C.c_int, [C.c_void_p, C.POINTER(XptFrames), C.POINTER(PtrArray), C.POINTER(PtrArray),

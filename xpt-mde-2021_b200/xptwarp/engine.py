@@ -206,6 +206,25 @@ class Plan:
             C.byref(ptr_array([t.data_ptr() for t in d_synth])) if want_grad else None, self.stream()))
         return loss, d_synth
 
+    def photometric_min_loss(self, method, synth_ms, stereo_synth_ms, target, grad_loss_batch=None, want_grad=False):
+        """xpt_photometric_min_loss: per-pixel min over the N (+1 stereo) sources at full resolution."""
+        synth_ms = self._level_list(synth_ms, "synth_target_ms", self.N * 3)
+        have_st = stereo_synth_ms is not None
+        if have_st:
+            stereo_synth_ms = self._level_list(stereo_synth_ms, "stereo_synth_ms", 3)
+        target = _frame_view(target, "target", 1)
+        loss = torch.empty((self.B,), dtype=torch.float32, device=self.device)
+        d_synth = self._empty_levels((self.N,), 3) if want_grad else None
+        d_stereo = self._empty_levels((1,), 3) if (want_grad and have_st) else None
+        g = _dense(grad_loss_batch, "grad_loss_batch") if grad_loss_batch is not None else None
+        _cabi.check(self._lib.xpt_photometric_min_loss(
+            self.handle, int(method), C.byref(ptr_array([t.data_ptr() for t in synth_ms])),
+            C.byref(ptr_array([t.data_ptr() for t in stereo_synth_ms])) if have_st else None,
+            target.data_ptr(), target.stride(0), loss.data_ptr(), g.data_ptr() if g is not None else None,
+            C.byref(ptr_array([t.data_ptr() for t in d_synth])) if want_grad else None,
+            C.byref(ptr_array([t.data_ptr() for t in d_stereo])) if d_stereo is not None else None, self.stream()))
+        return loss, d_synth, d_stereo, (target, synth_ms, stereo_synth_ms)
+
     def smoothness_loss(self, disp_ms, target_ms, grad_loss_batch=None, want_grad=False):
         disp_ms = self._level_list(disp_ms, "disp_ms", 1)
         target_ms = self._level_list(target_ms, "target_ms", 3)

@@ -5,8 +5,7 @@ import numpy as np
 
 from . import losses as lm
 
-_OUTSIDE = ["md2L1", "md2L1_R", "md2SSIM", "md2SSIM_R", "cmbL1", "cmbL1_R", "cmbSSIM", "cmbSSIM_R",
-            "moaL1", "moaL1_R", "moaSSIM", "moaSSIM_R", "flowL2", "flowL2_R", "flow_reg"]
+_OUTSIDE = ["cmbL1", "cmbL1_R", "cmbSSIM", "cmbSSIM_R", "flowL2", "flowL2_R", "flow_reg"]   # need FlowNet outputs
 
 
 def loss_factory(dataset_cfg, loss_weights, scale_weights, stereo=False, weights_to_regularize=None, batch_size=1):
@@ -20,6 +19,14 @@ def loss_factory(dataset_cfg, loss_weights, scale_weights, stereo=False, weights
         "SSIM_R": lm.PhotometricLossMultiScale("SSIM", scale_weights, key_suffix="_R"),
         "smoothe": lm.SmoothenessLossMultiScale(scale_weights),
         "smoothe_R": lm.SmoothenessLossMultiScale(scale_weights, key_suffix="_R"),
+        "md2L1": lm.MonoDepth2LossMultiScale("L1", scale_weights),
+        "md2L1_R": lm.MonoDepth2LossMultiScale("L1", scale_weights, key_suffix="_R"),
+        "md2SSIM": lm.MonoDepth2LossMultiScale("SSIM", scale_weights),
+        "md2SSIM_R": lm.MonoDepth2LossMultiScale("SSIM", scale_weights, key_suffix="_R"),
+        "moaL1": lm.MoALossMultiScale("L1", scale_weights),
+        "moaL1_R": lm.MoALossMultiScale("L1", scale_weights, key_suffix="_R"),
+        "moaSSIM": lm.MoALossMultiScale("SSIM", scale_weights),
+        "moaSSIM_R": lm.MoALossMultiScale("SSIM", scale_weights, key_suffix="_R"),
         "stereoL1": lm.StereoDepthLoss("L1", scale_weights),
         "stereoSSIM": lm.StereoDepthLoss("SSIM", scale_weights),
         "stereoPose": lm.StereoPoseLoss(),

@@ -96,6 +96,28 @@ class _PhotoFn(torch.autograd.Function):
         return (None, None, None, *d_synth, *([None] * S))
 
 
+class _PhotoMinFn(torch.autograd.Function):
+    """MonoDepth2 / MoA: min over sources per pixel and channel at full resolution (xpt_photometric_min_loss)."""
+
+    @staticmethod
+    def forward(ctx, plan, method, S, have_stereo, target, *ts):
+        synth_ms = ts[:S]
+        stereo_ms = ts[S:] if have_stereo else None
+        loss, _, _, _ = plan.photometric_min_loss(method, synth_ms, stereo_ms, target)
+        ctx.plan, ctx.method, ctx.S, ctx.have_stereo = plan, method, S, have_stereo
+        ctx.save_for_backward(target, *ts)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        target, *ts = ctx.saved_tensors
+        S = ctx.S
+        _, d_synth, d_stereo, _ = ctx.plan.photometric_min_loss(
+            ctx.method, ts[:S], ts[S:] if ctx.have_stereo else None, target,
+            grad_loss_batch=g.reshape(-1).contiguous(), want_grad=True)
+        return (None, None, None, None, None, *d_synth, *(d_stereo if ctx.have_stereo else ()))
+
+
 class _SmoothFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, plan, S, *ts):
@@ -144,6 +166,33 @@ class PhotometricLossMultiScale(PhotometricLoss):
         scales = [H // s.shape[2] for s in synth_ms]
         plan = get_plan(synth_ms[0].device.index or 0, B, N, H, W, scales, _scale_weights_list(self.scale_weights))
         return _PhotoFn.apply(plan, self._METHODS[self.method], plan.S, *synth_ms, *target_ms)
+
+
+class MonoDepth2LossMultiScale(PhotometricLoss):
+    """reference losses.py:198-232: every scale's synthesis is up-sampled to the original size, the per-pixel
+    photometric term is taken against the full-resolution target and the minimum over the sources is averaged."""
+
+    def _call(self, augm_data, stereo_key):
+        synth_ms = [as_torch(t) for t in augm_data["synth_target_ms" + self.key_suffix]]
+        stereo_ms = [as_torch(t) for t in augm_data[stereo_key]] if stereo_key else None
+        target = as_torch(augm_data["target" + self.key_suffix])
+        require_cuda_f32(synth_target_ms=synth_ms, target=target)
+        B, N, H, W = synth_ms[0].shape[0], synth_ms[0].shape[1], target.shape[1], target.shape[2]
+        scales = [H // s.shape[2] for s in synth_ms]
+        plan = get_plan(target.device.index or 0, B, N, H, W, scales, _scale_weights_list(self.scale_weights))
+        return _PhotoMinFn.apply(plan, self._METHODS[self.method], plan.S, stereo_ms is not None, target,
+                                 *synth_ms, *(stereo_ms or ()))
+
+    def __call__(self, features, predictions, augm_data):
+        return self._call(augm_data, None)
+
+
+class MoALossMultiScale(MonoDepth2LossMultiScale):
+    """reference losses.py:282-321: minimum over the temporal syntheses AND the stereo synthesis.  As in the
+    reference the stereo entry is always augm_data["stereo_synth_ms"] (the left one), also for key_suffix "_R"."""
+
+    def __call__(self, features, predictions, augm_data):
+        return self._call(augm_data, "stereo_synth_ms")
 
 
 class SmoothenessLossMultiScale(LossBase):
