@@ -222,6 +222,59 @@ def test_edge_cases(xw):
     assert np.allclose(T[0, 0, :3, :3], np.eye(3))
 
 
+@pytest.mark.parametrize("B,H,W,N,S", [(1, 24, 40, 1, 2), (2, 16, 136, 6, 3), (1, 72, 88, 8, 4), (5, 8, 8, 3, 1)])
+def test_ragged_shapes_and_source_counts(xw, B, H, W, N, S):
+    """Tile-ragged sizes (partial 64x13 tiles, widths that are no multiple of 8 -> generic pyramid path), one
+    source, more than four sources (the fused kernel buffers pose partials four sources at a time), one to
+    four levels -- all against the oracle, fused and unfused."""
+    from oracle import xpt_oracle as orc
+    feats, preds = orc.make_inputs(B, H, W, N=N, n_scales=S, seed=1000 + H + N)
+    lw, sw = orc.LOSS_RIGID_T1, [1.0, 0.5, 2.0, 1.5][:S]
+    ref = orc.loss_and_grads(feats, preds, lw, sw)
+    f64 = {k: v.double() for k, v in feats.items()}
+    p64 = {"depth_ms": [d.double() for d in preds["depth_ms"]], "disp_ms": [d.double() for d in preds["disp_ms"]],
+           "pose": preds["pose"].double()}
+    ref64 = orc.loss_and_grads(f64, p64, lw, sw)
+    f, p = _to_cuda(feats, preds)
+    for flags in (0, 1):
+        plan = _plan_for(xw, f, p, lw, sw, B, flags)
+        r = _run_total(plan, f, p, want_grad=True)
+        losses = r["losses"].cpu().numpy()
+        assert relerr(losses[0], ref64["total"].numpy()) < LOSS_TOL, flags
+        pose_tol = max(GRAD_TOL, 3 * relerr(ref["d_pose"].numpy(), ref64["d_pose"].numpy()))
+        assert relerr(r["d_pose"].cpu().numpy(), ref64["d_pose"].numpy()) < pose_tol, flags
+        for s in range(S):
+            ok, msg = grad_close(r["d_depth_ms"][s].cpu().numpy(), ref["d_depth_ms"][s].numpy(),
+                                 ref64["d_depth_ms"][s].numpy(), GRAD_TOL)
+            assert ok, (flags, s, msg)
+            assert relerr(r["d_disp_ms"][s].cpu().numpy(), ref64["d_disp_ms"][s].numpy()) < GRAD_TOL, (flags, s)
+
+
+def test_config3_size_properties(xw):
+    """BASELINE config 3 (B=16, 256x832): fused == unfused, per-snippet losses add up, one snippet vs the oracle."""
+    from oracle import xpt_oracle as orc
+    feats, preds = orc.make_inputs(16, 256, 832, seed=20211 + 3000)
+    lw, sw = orc.LOSS_RIGID_T2, orc.SCALE_WEIGHT_T2
+    f, p = _to_cuda(feats, preds)
+    r1 = _run_total(_plan_for(xw, f, p, lw, sw, 16), f, p, want_grad=True, want_loss_batch=True)
+    r1 = {k: ([t.clone() for t in v] if isinstance(v, list) else v.clone()) for k, v in r1.items()}
+    ru = _run_total(_plan_for(xw, f, p, lw, sw, 16, flags=1), f, p, want_grad=True)
+    assert relerr(ru["losses"].cpu().numpy(), r1["losses"].cpu().numpy()) < 1e-6
+    assert relerr(ru["d_pose"].cpu().numpy(), r1["d_pose"].cpu().numpy()) < 1e-5
+    for s in range(4):
+        assert relerr(ru["d_depth_ms"][s].cpu().numpy(), r1["d_depth_ms"][s].cpu().numpy()) < 1e-4
+        assert relerr(ru["d_disp_ms"][s].cpu().numpy(), r1["d_disp_ms"][s].cpu().numpy()) < 1e-5
+    losses = r1["losses"].cpu().numpy()
+    assert np.allclose(r1["loss_batch"].cpu().numpy().sum(axis=1) / 16, losses[1:4], rtol=1e-5)
+    f1 = {k: v[5:6] for k, v in feats.items()}
+    p1 = {"depth_ms": [d[5:6] for d in preds["depth_ms"]], "disp_ms": [d[5:6] for d in preds["disp_ms"]],
+          "pose": preds["pose"][5:6]}
+    ref = orc.loss_and_grads(f1, p1, lw, sw, global_batch=16)
+    lb = r1["loss_batch"].cpu().numpy()[:, 5] / 16
+    for i, k in enumerate(("L1", "SSIM", "smoothe")):
+        assert relerr(lb[i], ref["by_type"][k].numpy()) < LOSS_TOL, k
+
+
 def test_full_size_properties(xw):
     """BASELINE config 2 (B=8, 128x384): size-independent properties instead of the slow oracle."""
     from oracle import xpt_oracle as orc
