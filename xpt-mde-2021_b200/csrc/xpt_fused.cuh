@@ -232,10 +232,16 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
   // warps 0..14 own one statistics row each (lane = strip: conflict-free 8-byte rows); the 33rd strip of
   // every row goes to lanes 0..14 of warp 15
   const int qy = wid < kFSH ? wid : lane, q0 = wid < kFSH ? lane * 2 : 2 * (kFSStrips - 1);
-  const bool s_active = wid < kFSH || lane < kFSH;
+  // rows below the image (ragged last tile row, the small pyramid levels) are skipped altogether: the
+  // statistics slots of a ragged tile are zeroed once, the skipped centre rows contribute nothing
+  const bool s_active = (wid < kFSH || lane < kFSH) && (unsigned)(ty0 - 1 + qy) < (unsigned)H;
   // G phase: centre row cyy (0..12), columns c0, c0+1
   const int cyy = tid >> 5, c0 = (tid & 31) * 2;
-  const bool g_active = cyy < kFCH;
+  const bool g_active = cyy < kFCH && ty0 + cyy < H;
+  if (GRAD && (ty0 == 0 || ty0 + kFCH + 1 > H)) {          // block-uniform: some statistics row lies outside the image
+    for (int i = tid; i < SM::sGU - SM::sA; i += kFThreads) sA[i] = 0.f;
+    __syncthreads();
+  }
 
   float lsum_l1 = 0.f, lsum_ssim = 0.f, lsum_sm = 0.f;
 
@@ -582,7 +588,8 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
       if (k <= n - n0 && j < 12) {
         float v = 0.f;
 #pragma unroll
-        for (int w = 0; w < kFCH; ++w) v += red[(k * kFCH + w) * 16 + j];
+        for (int w = 0; w < kFCH; ++w)
+          if (ty0 + w < H) v += red[(k * kFCH + w) * 16 + j];       // rows below the image were skipped
         a.pose_part[(((size_t)b * a.slots_per_b + slot) * a.N + (n0 + k)) * 12 + j] = v;
       }
     }
