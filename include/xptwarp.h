@@ -189,7 +189,11 @@ XPT_API int xpt_smoothness_loss(xpt_ctx* ctx, const float* const disp_ms[],
 
 /* losses.py:26-55 TotalLoss.__call__ for the loss set {L1, SSIM, smoothe}
  * (config LOSS_RIGID_T1/T2), forward and -- when any gradient output is
- * non-NULL -- backward in the same call: pyramids, warp, losses, gradients.   */
+ * non-NULL -- backward in the same call: pyramids, warp, losses, gradients.
+ * disp_ms == NULL with a smoothness weight: the disparity is what model/model_wrappers.py:47-48
+ * feeds in, safe_reciprocal_number(depth_ms) (utils/util_funcs.py:146-160), formed inside the fused
+ * kernel; its gradient is folded into d_depth_ms and d_disp_ms (if given) is zero-filled.  Needs the
+ * fused path (not XPT_FLAG_UNFUSED).                                           */
 XPT_API int xpt_total_loss(xpt_ctx* ctx, const xpt_frames* frames,
                    const float* const depth_ms[], const float* const disp_ms[],
                    const float* pose, const xpt_loss_outputs* out, void* stream);

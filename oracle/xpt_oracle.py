@@ -461,7 +461,12 @@ def total_loss(predictions: Dict, features: Dict, loss_weights: Dict[str, float]
         if base in ("L1", "SSIM"):
             lb = photometric_loss_multi_scale(base, augm["synth_target_ms" + sfx], augm["target_ms" + sfx], scale_weights)
         elif base == "smoothe":
-            lb = smootheness_loss_multi_scale(predictions["disp_ms" + sfx], augm["target_ms" + sfx], scale_weights)
+            # no disp_ms: what model_wrappers.py:47-48 derives from depth_ms (value 0, not the reference's NaN, at depth 0)
+            disp = predictions.get("disp_ms" + sfx)
+            if disp is None:
+                disp = [torch.where(d > 0.00001, 1.0 / torch.where(d > 0.00001, d, torch.ones_like(d)), torch.zeros_like(d))
+                        for d in predictions["depth_ms" + sfx]]
+            lb = smootheness_loss_multi_scale(disp, augm["target_ms" + sfx], scale_weights)
         elif base in ("md2L1", "md2SSIM"):
             lb = monodepth2_loss_multi_scale(base[3:], augm["synth_target_ms" + sfx], augm["target" + sfx], scale_weights)
         elif base in ("moaL1", "moaSSIM"):

@@ -250,6 +250,41 @@ def test_ragged_shapes_and_source_counts(xw, B, H, W, N, S):
             assert relerr(r["d_disp_ms"][s].cpu().numpy(), ref64["d_disp_ms"][s].numpy()) < GRAD_TOL, (flags, s)
 
 
+def test_disparity_derived_from_depth(xw):
+    """without predictions["disp_ms"] the fused kernel forms disp = safe_reciprocal_number(depth)
+    itself (utils/util_funcs.py:146-160, model_wrappers.py:47-48) and returns the whole gradient on depth_ms."""
+    from oracle import xpt_oracle as orc
+    feats, preds = orc.make_inputs(2, 64, 96, seed=4711)
+    lw, sw = orc.LOSS_RIGID_T2, orc.SCALE_WEIGHT_T2
+    # oracle: depth -> disp inside the graph
+    depth = [d.clone().requires_grad_(True) for d in preds["depth_ms"]]
+    pose = preds["pose"].clone().requires_grad_(True)
+    total, by_type = orc.total_loss({"depth_ms": depth, "pose": pose}, feats, lw, sw)
+    total.backward()
+    d64 = [d.double().clone().requires_grad_(True) for d in preds["depth_ms"]]
+    t64, _ = orc.total_loss({"depth_ms": d64, "pose": preds["pose"].double()}, {k: v.double() for k, v in feats.items()}, lw, sw)
+    t64.backward()
+    f = {k: v.cuda() for k, v in feats.items()}
+    cdepth = [d.cuda().requires_grad_(True) for d in preds["depth_ms"]]
+    cpose = preds["pose"].cuda().requires_grad_(True)
+    tot = xw.loss_factory({"image": 1, "intrinsic": 1}, lw, np.array(sw), batch_size=2)
+    ctotal, cby = tot({"depth_ms": cdepth, "pose": cpose}, f)
+    ctotal.backward()
+    assert relerr(ctotal.item(), t64.item()) < LOSS_TOL
+    assert relerr(cby["smoothe"].item(), by_type["smoothe"].item()) < LOSS_TOL
+    for s in range(4):
+        ok, msg = grad_close(cdepth[s].grad.cpu().numpy(), depth[s].grad.numpy(), d64[s].grad.numpy(), GRAD_TOL)
+        assert ok, (s, msg)
+    # and it is the explicit-tensor result with the reciprocal's chain rule applied
+    p_exp = {"depth_ms": [d.cuda() for d in preds["depth_ms"]], "disp_ms": [d.cuda() for d in preds["disp_ms"]],
+             "pose": preds["pose"].cuda()}
+    r = _run_total(_plan_for(xw, f, p_exp, lw, sw, 2), f, p_exp, want_grad=True)
+    for s in range(4):
+        disp = p_exp["disp_ms"][s]
+        chained = r["d_depth_ms"][s] - r["d_disp_ms"][s] * disp * disp
+        assert relerr(cdepth[s].grad.cpu().numpy(), chained.cpu().numpy().reshape(cdepth[s].shape)) < 1e-5, s
+
+
 def test_config3_size_properties(xw):
     """BASELINE config 3 (B=16, 256x832): fused == unfused, per-snippet losses add up, one snippet vs the oracle."""
     from oracle import xpt_oracle as orc

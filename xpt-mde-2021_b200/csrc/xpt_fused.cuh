@@ -162,7 +162,8 @@ __device__ __forceinline__ float2 hsum3(float2 a, float2 b) {
 }
 
 // GRAD: backward in the same launch.  OUT: synth_ms / mask_ms are written.  DSRC: dL/dsource scatter.
-template <bool GRAD, bool OUT, bool DSRC>
+// DERIVE: the disparity of the smoothness term is safe_reciprocal_number(depth) formed in the kernel.
+template <bool GRAD, bool OUT, bool DSRC, bool DERIVE>
 __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ FusedArgs a) {
   using SM = FusedSmem<GRAD>;
   extern __shared__ __align__(16) float smem[];
@@ -246,25 +247,34 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
   float lsum_l1 = 0.f, lsum_ssim = 0.f, lsum_sm = 0.f;
 
   // ---- smoothness on the centre strip (losses.py:409-440) ------------------------------------
+  // a.disp[l] == NULL: the disparity is safe_reciprocal_number(depth) (utils/util_funcs.py:157-160, what
+  // model_wrappers.py:47-48 feeds in), taken from the depth tile already in shared memory; its gradient is
+  // folded into d_depth (d disp / d depth = -disp^2), so neither disp_ms nor d_disp_ms touches HBM.
+  float gD[2] = {0.f, 0.f};
   if (a.do_smooth && g_active) {
-    const float* dsp = a.disp[l] + (long long)b * P;
+    const float* dsp = DERIVE ? nullptr : a.disp[l] + (long long)b * P;
     const float nx = a.norm_sm_x[l], ny = a.norm_sm_y[l];
     const float gcx = a.gcoef_smooth * nx, gcy = a.gcoef_smooth * ny;
     const float k3 = a.grad_factor;
     const int gy = ty0 + cyy;
+    auto disp_at = [&](int ri, int yy, int xx) -> float {       // region index / image coordinates of the same pixel
+      if (!DERIVE) return __ldg(dsp + (long long)yy * W + xx);
+      const float D = sD[ri];
+      return D > 0.00001f ? __frcp_rn(D) : 0.f;
+    };
 #pragma unroll
     for (int o = 0; o < 2; ++o) {
       const int gx = tx0 + c0 + o;
       if (gy < H && gx < W) {
         const int ri = (cyy + 2) * kFP + (c0 + o + 2);
-        const float d = __ldg(dsp + (long long)gy * W + gx);
+        const float d = disp_at(ri, gy, gx);
         float gd = 0.f;
         if (gx + 1 < W) {
           float e = 0.f;
 #pragma unroll
           for (int c = 0; c < 3; ++c) e += fabsf((sx[c * kFRegion + ri] - sx[c * kFRegion + ri + 1]) * k3);
           const float w = expf(-(e * (1.f / 3.f)));
-          const float sd = (d - __ldg(dsp + (long long)gy * W + gx + 1)) * w;
+          const float sd = (d - disp_at(ri + 1, gy, gx + 1)) * w;
           lsum_sm += fabsf(sd) * nx;
           gd += gcx * sgnf(sd) * w;
         }
@@ -273,7 +283,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
 #pragma unroll
           for (int c = 0; c < 3; ++c) e += fabsf((sx[c * kFRegion + ri] - sx[c * kFRegion + ri + kFP]) * k3);
           const float w = expf(-(e * (1.f / 3.f)));
-          const float sd = (d - __ldg(dsp + (long long)(gy + 1) * W + gx)) * w;
+          const float sd = (d - disp_at(ri + kFP, gy + 1, gx)) * w;
           lsum_sm += fabsf(sd) * ny;
           gd += gcy * sgnf(sd) * w;
         }
@@ -283,7 +293,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
 #pragma unroll
             for (int c = 0; c < 3; ++c) e += fabsf((sx[c * kFRegion + ri - 1] - sx[c * kFRegion + ri]) * k3);
             const float w = expf(-(e * (1.f / 3.f)));
-            const float sd = (__ldg(dsp + (long long)gy * W + gx - 1) - d) * w;
+            const float sd = (disp_at(ri - 1, gy, gx - 1) - d) * w;
             gd -= gcx * sgnf(sd) * w;
           }
           if (gy >= 1) {
@@ -291,10 +301,11 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
 #pragma unroll
             for (int c = 0; c < 3; ++c) e += fabsf((sx[c * kFRegion + ri - kFP] - sx[c * kFRegion + ri]) * k3);
             const float w = expf(-(e * (1.f / 3.f)));
-            const float sd = (__ldg(dsp + (long long)(gy - 1) * W + gx) - d) * w;
+            const float sd = (disp_at(ri - kFP, gy - 1, gx) - d) * w;
             gd -= gcy * sgnf(sd) * w;
           }
-          if (a.d_disp[l]) a.d_disp[l][(long long)b * P + gy * W + gx] = gd;
+          if (DERIVE) gD[o] = -(gd * d) * d;
+          else if (a.d_disp[l]) a.d_disp[l][(long long)b * P + gy * W + gx] = gd;
         }
       }
     }
@@ -342,8 +353,6 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
       SGXC[c] = f2add(f2fma(s2, inv_cnt, f2neg(mu2)), f2s(kC2));
     }
   }
-
-  float gD[2] = {0.f, 0.f};
 
   for (int n = 0; n < a.N; ++n) {
     const float* const gt = c_geo + a.geo_t_off + (bl * a.N + n) * kGeoT;   // [R|t]: uniform registers

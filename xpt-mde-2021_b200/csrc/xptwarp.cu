@@ -397,12 +397,12 @@ int launch_photo(xpt_ctx* ctx, const PhotoArgs& a, cudaStream_t st) {
   return XPT_OK;
 }
 
-template <bool GRAD, bool OUT, bool DSRC>
+template <bool GRAD, bool OUT, bool DSRC, bool DERIVE>
 int launch_fused(xpt_ctx* ctx, FusedArgs& a, cudaStream_t st) {
   static bool attr_set = false;
   const size_t smem = FusedSmem<GRAD>::kBytes;
   if (!attr_set) {
-    XPT_CUDA(cudaFuncSetAttribute(k_fused<GRAD, OUT, DSRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    XPT_CUDA(cudaFuncSetAttribute(k_fused<GRAD, OUT, DSRC, DERIVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   // camera geometry goes to the constant bank (uniform registers in the kernel); 60 KB hold
@@ -423,7 +423,7 @@ int launch_fused(xpt_ctx* ctx, FusedArgs& a, cudaStream_t st) {
     a.b_off = b0;
     a.geo_t_off = bc * ctx->S * kGeoK;
     dim3 grid(bc, a.tiles_per_b);
-    k_fused<GRAD, OUT, DSRC><<<grid, kFThreads, smem, st>>>(a);
+    k_fused<GRAD, OUT, DSRC, DERIVE><<<grid, kFThreads, smem, st>>>(a);
     XPT_LAUNCH_CHECK("k_fused");
   }
   if (prof) { XPT_CUDA(cudaEventRecord((*ctx->prof_events)[2 * ctx->prof_count + 1], st)); ++ctx->prof_count; }
@@ -791,7 +791,12 @@ static int total_loss_impl(xpt_ctx* ctx, const xpt_frames* frames, const float* 
   XPT_TRY(check_list(ctx, (const void* const*)depth_ms, "depth_ms", true));
   const xpt_config& c = ctx->cfg;
   const bool do_smooth = c.w_smooth != 0.f;
-  if (do_smooth) XPT_TRY(check_list(ctx, (const void* const*)disp_ms, "disp_ms", true));
+  // disp_ms == NULL with a smoothness weight: the disparity is safe_reciprocal_number(depth_ms), evaluated in the
+  // fused kernel (utils/util_funcs.py:146-160 + model_wrappers.py:47-48); its gradient lands in d_depth_ms
+  const bool derive_disp = do_smooth && disp_ms == nullptr;
+  if (do_smooth && !derive_disp) XPT_TRY(check_list(ctx, (const void* const*)disp_ms, "disp_ms", true));
+  if (derive_disp && (c.flags & XPT_FLAG_UNFUSED))
+    return fail(XPT_BAD_ARGUMENT, "disp_ms == NULL (disparity derived from depth) needs the fused path");
   cudaStream_t st = (cudaStream_t)stream;
   XPT_CUDA(cudaSetDevice(c.device));
   ctx->launches = 0;
@@ -820,13 +825,13 @@ static int total_loss_impl(xpt_ctx* ctx, const xpt_frames* frames, const float* 
   XPT_TRY(prepare_dsource(ctx, grad ? out->d_source : nullptr, d_src, dbs, dfs, st));
   for (int l = 0; l < ctx->S; ++l) {
     a.depth[l] = depth_ms[l];
-    a.disp[l] = do_smooth ? disp_ms[l] : nullptr;
+    a.disp[l] = (do_smooth && !derive_disp) ? disp_ms[l] : nullptr;
     a.synth_out[l] = out->synth_ms[l]; a.mask_out[l] = out->mask_ms[l];
     a.d_depth[l] = out->d_depth_ms[l]; a.d_disp[l] = out->d_disp_ms[l];
     a.d_src[l] = d_src[l]; a.d_src_bs[l] = dbs[l]; a.d_src_fs[l] = dfs[l];
   }
   const int tiles = ctx->first_tile[ctx->S];
-  if (!do_smooth)      // no smoothness term: its gradient is identically zero
+  if (!do_smooth || derive_disp)      // no smoothness term / no disparity tensor: that gradient is identically zero
     for (int l = 0; l < ctx->S; ++l)
       if (out->d_disp_ms[l])
         XPT_CUDA(cudaMemsetAsync(out->d_disp_ms[l], 0, (size_t)ctx->B * lvl_pix(ctx, l) * sizeof(float), st));
@@ -858,11 +863,21 @@ static int total_loss_impl(xpt_ctx* ctx, const xpt_frames* frames, const float* 
     bool want_out = false;
     for (int l = 0; l < ctx->S; ++l) want_out = want_out || out->synth_ms[l] || out->mask_ms[l];
     const bool dsrc = grad && out->d_source;
-    if (grad) {
-      if (dsrc) { if (want_out) XPT_TRY((launch_fused<true, true, true>(ctx, fa, st))); else XPT_TRY((launch_fused<true, false, true>(ctx, fa, st))); }
-      else { if (want_out) XPT_TRY((launch_fused<true, true, false>(ctx, fa, st))); else XPT_TRY((launch_fused<true, false, false>(ctx, fa, st))); }
-    } else {
-      if (want_out) XPT_TRY((launch_fused<false, true, false>(ctx, fa, st))); else XPT_TRY((launch_fused<false, false, false>(ctx, fa, st)));
+    // template dispatch: (GRAD, OUT, DSRC, DERIVE)
+    const int sel = (grad ? 8 : 0) | (want_out ? 4 : 0) | (dsrc ? 2 : 0) | (derive_disp ? 1 : 0);
+    switch (sel) {
+      case 0: XPT_TRY((launch_fused<false, false, false, false>(ctx, fa, st))); break;
+      case 1: XPT_TRY((launch_fused<false, false, false, true>(ctx, fa, st))); break;
+      case 4: XPT_TRY((launch_fused<false, true, false, false>(ctx, fa, st))); break;
+      case 5: XPT_TRY((launch_fused<false, true, false, true>(ctx, fa, st))); break;
+      case 8: XPT_TRY((launch_fused<true, false, false, false>(ctx, fa, st))); break;
+      case 9: XPT_TRY((launch_fused<true, false, false, true>(ctx, fa, st))); break;
+      case 10: XPT_TRY((launch_fused<true, false, true, false>(ctx, fa, st))); break;
+      case 11: XPT_TRY((launch_fused<true, false, true, true>(ctx, fa, st))); break;
+      case 12: XPT_TRY((launch_fused<true, true, false, false>(ctx, fa, st))); break;
+      case 13: XPT_TRY((launch_fused<true, true, false, true>(ctx, fa, st))); break;
+      case 14: XPT_TRY((launch_fused<true, true, true, false>(ctx, fa, st))); break;
+      default: XPT_TRY((launch_fused<true, true, true, true>(ctx, fa, st))); break;
     }
     EpilogueArgs ea;
     memset(&ea, 0, sizeof(ea));
@@ -1035,7 +1050,7 @@ static int host_enqueue(xpt_ctx* ctx, const xpt_frames* frames, const float* con
   if (!out->losses) return fail(XPT_BAD_ARGUMENT, "out->losses is NULL");
   XPT_TRY(check_frames(ctx, frames, true));
   XPT_TRY(check_list(ctx, (const void* const*)depth_ms, "depth_ms", true));
-  const bool do_smooth = ctx->cfg.w_smooth != 0.f;
+  const bool do_smooth = ctx->cfg.w_smooth != 0.f && disp_ms != nullptr;     // NULL: derived from depth in the kernel
   if (do_smooth) XPT_TRY(check_list(ctx, (const void* const*)disp_ms, "disp_ms", true));
   const long long hw3 = (long long)ctx->H * ctx->W * 3;
   if (frames->source_frame_stride != hw3)
@@ -1183,7 +1198,7 @@ static int host_enqueue(xpt_ctx* ctx, const xpt_frames* frames, const float* con
       if (out->mask_ms[l]) dout.mask_ms[l] = ctx->st_mask[l] + off * N;
       if (out->target_ms[l]) dout.target_ms[l] = ctx->st_target[l] + off * 3;
     }
-    XPT_TRY(xpt_total_loss(child, &df, cdepth, cdisp, ctx->st_pose + (size_t)b0 * N * 6, &dout, stream));
+    XPT_TRY(xpt_total_loss(child, &df, cdepth, do_smooth ? cdisp : nullptr, ctx->st_pose + (size_t)b0 * N * 6, &dout, stream));
     if (nc > 1) {
       XPT_CUDA(cudaEventRecord(ctx->ev_done[k], st));
       XPT_CUDA(cudaStreamWaitEvent(s_out, ctx->ev_done[k], 0));

@@ -250,8 +250,8 @@ class Plan:
         have_disp = disp_ms is not None
         if have_disp:
             disp_ms = self._level_list(disp_ms, "disp_ms", 1)
-        elif self.cfg.w_smooth != 0.0:
-            raise WrongInputException("disp_ms is required when the smoothe weight is non-zero")
+        # disp_ms None with a smoothe weight: the kernel derives disp = safe_reciprocal_number(depth)
+        # (utils/util_funcs.py:146-160) and folds d_disp into d_depth
         r = out if out is not None else {}
         dev, f32 = self.device, torch.float32
 
@@ -277,7 +277,8 @@ class Plan:
             put("target_ms", "target_ms", (), 3)
         if want_grad:
             put("d_depth_ms", "d_depth_ms", (), 1)
-            put("d_disp_ms", "d_disp_ms", (), 1)
+            if have_disp or self.cfg.w_smooth == 0.0:
+                put("d_disp_ms", "d_disp_ms", (), 1)
             o.d_pose = need("d_pose", lambda: torch.empty((self.B, self.N, 6), dtype=f32, device=dev)).data_ptr()
             if want_source_grad:
                 o.d_source = need("d_source", lambda: torch.empty((self.B, self.N, self.H, self.W, 3), dtype=f32,

@@ -300,7 +300,7 @@ class TotalLoss:
         B, N, H, W, _ = source.shape
         plan = get_plan(source.device.index or 0, B, N, H, W, infer_scales(H, depth_ms), sw, w_l1, w_ssim, w_smooth,
                         self.batch_size)
-        maps = list(depth_ms) + (list(disp_ms) if w_smooth != 0.0 else [])
+        maps = list(depth_ms) + (list(disp_ms) if (w_smooth != 0.0 and disp_ms is not None) else [])
         want_grad = torch.is_grad_enabled() and any(t.requires_grad for t in [pose, *maps])
         return _TotalLossFn.apply(plan, want_grad, source, target, intrinsic, pose, *maps)
 
@@ -325,7 +325,10 @@ class TotalLoss:
             if not names:
                 continue
             pose = as_torch(predictions["pose" + sfx])
-            disp_ms = [as_torch(d) for d in predictions["disp_ms" + sfx]] if "smoothe" + sfx in w else None
+            # no "disp_ms" in predictions: the kernel derives it from depth_ms (what model_wrappers.py:47-48 computes
+            # with safe_reciprocal_number_ms) and returns the whole gradient on depth_ms
+            disp_ms = ([as_torch(d) for d in predictions["disp_ms" + sfx]]
+                       if ("smoothe" + sfx in w and "disp_ms" + sfx in predictions) else None)
             total, by_type = self._fused_group(image5d[:, :-1], image5d[:, -1], K, depth_ms, disp_ms, pose,
                                                w.get("L1" + sfx, 0.0), w.get("SSIM" + sfx, 0.0), w.get("smoothe" + sfx, 0.0), sw)
             totals.append(total)
