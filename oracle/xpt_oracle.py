@@ -441,9 +441,35 @@ def moa_loss_multi_scale(method, temp_synth_ms, stereo_synth_ms, target, scale_w
     return merge_multi_scale_losses(losses, scale_weights)
 
 
+def combined_loss_multi_scale(method, synth_target_ms, warped_target_ms, target, scale_weights):
+    """losses.py:235-279 CombinedLossMultiScale: per pixel/channel/source, the static (depth+pose) loss of every
+    scale counts only where it is smaller than the optical-flow loss of flow level 0; both compared at full
+    resolution.  The mask is a constant of the graph (tf.cast of a comparison): no gradient reaches the flow."""
+    fn = _PHOTO[method]
+    Ho, Wo = target.shape[1:3]
+
+    def up(x):
+        B, N, h, w, C = x.shape
+        return resize_bilinear_tf(x.reshape(B * N, h, w, C), (Ho, Wo)).reshape(B, N, Ho, Wo, C)
+    flow_loss = fn(up(warped_target_ms[0]), target, False)
+    losses = []
+    for synt in synth_target_ms:
+        static = fn(up(synt), target, False)
+        mask = (static < flow_loss).to(static.dtype)
+        losses.append((static * mask).mean(dim=(1, 2, 3, 4)))
+    return merge_multi_scale_losses(losses, scale_weights)
+
+
+def l2_regularizer(weights: Sequence[torch.Tensor], batch: int) -> torch.Tensor:
+    """losses.py:522-534 L2Regularizer: sum_w tf.nn.l2_loss(w) = sum(w^2)/2, tiled to [batch]."""
+    loss = sum((w ** 2).sum() / 2 for w in weights)
+    return loss.reshape(1).repeat(batch)
+
+
 def total_loss(predictions: Dict, features: Dict, loss_weights: Dict[str, float],
                scale_weights: Sequence[float], global_batch: Optional[int] = None,
-               return_augm: bool = False, stereo: bool = False):
+               return_augm: bool = False, stereo: bool = False,
+               weights_to_regularize: Optional[Sequence[torch.Tensor]] = None):
     """losses.py:26-55: per-type [B] loss -> sum/global_batch -> weighted sum.
     Returns (total, {name: unweighted mean}[, augm_data])."""
     augm = append_data(features, predictions)
@@ -480,6 +506,11 @@ def total_loss(predictions: Dict, features: Dict, loss_weights: Dict[str, float]
         elif base == "flowL2":
             lb = photometric_loss_multi_scale("L2", augm["warped_target_ms" + sfx], augm["flow_target_ms" + sfx],
                                               scale_weights)
+        elif base in ("cmbL1", "cmbSSIM"):
+            lb = combined_loss_multi_scale(base[3:], augm["synth_target_ms" + sfx], augm["warped_target_ms" + sfx],
+                                           augm["target" + sfx], scale_weights)
+        elif name == "flow_reg":
+            lb = l2_regularizer(weights_to_regularize, B)
         else:
             raise ValueError(f"oracle: loss {name!r} is outside the hot path")
         mean = lb.sum() / gb                           # tf.nn.compute_average_loss
@@ -575,11 +606,34 @@ def make_stereo_inputs(B: int, H: int, W: int, N: int = 4, n_scales: int = 4, se
     return features, predictions
 
 
-_GRAD_KEYS = ("depth_ms", "disp_ms", "pose", "depth_ms_R", "disp_ms_R", "pose_R", "pose_LR", "pose_RL")
+def make_flow(B: int, H: int, W: int, N: int = 4, n_scales: int = 4, seed: int = 20211, dtype=torch.float32,
+              first_scale: int = 4, magnitude: float = 3.0) -> List[torch.Tensor]:
+    """Seeded optical-flow pyramid shaped like PWC-Net's output (flow_net.py:44-48, :349-350): list of
+    [B,N,H/s,W/s,2], s = first_scale * 2^k; a smooth field of a few pixels plus per-pixel noise, so that some
+    samples leave the image (invalid) and some land exactly on integer coordinates (flow 0 at ~1 % of pixels)."""
+    g = torch.Generator().manual_seed(seed + 4242)
+
+    def U(*shape, lo=-1.0, hi=1.0):
+        return torch.rand(*shape, generator=g, dtype=torch.float64) * (hi - lo) + lo
+    out = []
+    for k in range(n_scales):
+        s = first_scale * 2 ** k
+        h, w = H // s, W // s
+        low = U(B * N, 2, max(h // 4, 1), max(w // 4, 1))
+        fld = F.interpolate(low, size=(h, w), mode="bilinear", align_corners=False) * magnitude
+        fld = fld + 0.2 * U(B * N, 2, h, w)
+        zero = U(B * N, 1, h, w, lo=0.0, hi=1.0) < 0.01
+        fld = torch.where(zero, torch.zeros((), dtype=torch.float64), fld)
+        out.append(fld.reshape(B, N, 2, h, w).permute(0, 1, 3, 4, 2).contiguous().to(dtype))
+    return out
+
+
+_GRAD_KEYS = ("depth_ms", "disp_ms", "pose", "depth_ms_R", "disp_ms_R", "pose_R", "pose_LR", "pose_RL",
+              "flow_ms", "flow_ms_R")
 
 
 def stereo_loss_and_grads(features: Dict, predictions: Dict, loss_weights, scale_weights,
-                          global_batch: Optional[int] = None):
+                          global_batch: Optional[int] = None, weights_to_regularize=None):
     """total_loss(stereo=True) + autograd w.r.t. every prediction.  Returns dict(total, by_type, grads{key})."""
     preds = {}
     for k in _GRAD_KEYS:
@@ -588,10 +642,14 @@ def stereo_loss_and_grads(features: Dict, predictions: Dict, loss_weights, scale
         v = predictions[k]
         preds[k] = ([t.detach().clone().requires_grad_(True) for t in v] if isinstance(v, (list, tuple))
                     else v.detach().clone().requires_grad_(True))
-    total, by_type, augm = total_loss(preds, features, loss_weights, scale_weights, global_batch, True, stereo=True)
+    wreg = None if weights_to_regularize is None else [w.detach().clone().requires_grad_(True) for w in weights_to_regularize]
+    total, by_type, augm = total_loss(preds, features, loss_weights, scale_weights, global_batch, True, stereo=True,
+                                      weights_to_regularize=wreg)
     total.backward()
     gz = lambda t: torch.zeros_like(t) if t.grad is None else t.grad
     grads = {k: ([gz(t) for t in v] if isinstance(v, list) else gz(v)) for k, v in preds.items()}
+    if wreg is not None:
+        grads["weights_to_regularize"] = [gz(w) for w in wreg]
     return {"total": total.detach(), "by_type": {k: v.detach() for k, v in by_type.items()}, "grads": grads,
             "augm": {k: ([t.detach() for t in v] if isinstance(v, list) else v.detach()) for k, v in augm.items()}}
 

@@ -109,14 +109,28 @@ STEREO_SETS = {
                 "stereoL1": 0.5, "stereoSSIM": 0.5, "stereoPose": 1.0},
     "MD2": {"md2L1": 0.5, "md2L1_R": 0.5, "md2SSIM": 0.5, "md2SSIM_R": 0.5, "smoothe": 1.0, "smoothe_R": 1.0,
             "stereoL1": 0.5, "stereoSSIM": 0.5, "stereoPose": 1.0},
+    # config-example.py:90-95 LOSS_RIGID_COMB and :108-111 LOSS_FLOW
+    "COMB": {"cmbL1": 5.0, "cmbL1_R": 5.0, "cmbSSIM": 0.5, "cmbSSIM_R": 0.5, "smoothe": 20.0, "smoothe_R": 20.0,
+             "stereoL1": 0.5, "stereoSSIM": 0.5, "stereoPose": 1.0},
+    "FLOW": {"flowL2": 1.0, "flowL2_R": 1.0, "flow_reg": 4e-7},
 }
-_PRED_KEYS = ("depth_ms", "disp_ms", "pose", "depth_ms_R", "disp_ms_R", "pose_R", "pose_LR", "pose_RL")
+_PRED_KEYS = ("depth_ms", "disp_ms", "pose", "depth_ms_R", "disp_ms_R", "pose_R", "pose_LR", "pose_RL",
+              "flow_ms", "flow_ms_R")
 
 
-def run_stereo_case(name, B, H, W, N, loss_set, scale_weights, seed, global_batch=None):
+def run_stereo_case(name, B, H, W, N, loss_set, scale_weights, seed, global_batch=None, flow=None):
     """TotalLoss(stereo=True) of the reference on a stereo rig: temporal losses of both eyes, the two stereo
     syntheses (losses.py:105-140), StereoDepthLoss / StereoPoseLoss / MoA / MonoDepth2 as configured."""
     feats, preds = orc.make_stereo_inputs(B, H, W, N=N, seed=seed, dtype=torch.float32)
+    wreg = None
+    if flow:      # "with": rigid predictions + PWC-shaped flows (LOSS_RIGID_COMB); "only": FlowNet training (LOSS_FLOW)
+        if flow == "only":
+            preds = {}
+            g = torch.Generator().manual_seed(seed + 99)
+            wreg = [(torch.randn(*shp, generator=g, dtype=torch.float64) * 3).float().to(DT).requires_grad_(True)
+                    for shp in ((3, 3, 8, 16), (16,), (5, 7))]
+        preds["flow_ms"] = orc.make_flow(B, H, W, N=N, seed=seed, dtype=torch.float32)
+        preds["flow_ms_R"] = orc.make_flow(B, H, W, N=N, seed=seed + 13, dtype=torch.float32)
     cv = lambda t: t.to(DT)
     feats = {k: cv(v) for k, v in feats.items()}
     preds = {k: ([cv(t).clone().requires_grad_(True) for t in v] if isinstance(v, list)
@@ -124,7 +138,8 @@ def run_stereo_case(name, B, H, W, N, loss_set, scale_weights, seed, global_batc
     feats["image_R"] = feats["image5d_R"]             # losses.py:38 tests this key
     gb = B if global_batch is None else global_batch
     cfg = {"image": 1, "intrinsic": 1, "image_R": 1, "intrinsic_R": 1, "stereo_T_LR": 1}
-    total_obj = loss_factory(cfg, STEREO_SETS[loss_set], np.asarray(scale_weights, dtype=np.float64), stereo=True, batch_size=gb)
+    total_obj = loss_factory(cfg, STEREO_SETS[loss_set], np.asarray(scale_weights, dtype=np.float64), stereo=True,
+                             weights_to_regularize=wreg, batch_size=gb)
     total, by_type = total_obj(preds, feats)
     total.backward()
     out = {"B": B, "H": H, "W": W, "N": N, "global_batch": gb, "loss_set": loss_set,
@@ -135,17 +150,31 @@ def run_stereo_case(name, B, H, W, N, loss_set, scale_weights, seed, global_batc
         out["loss_" + k] = np_(v)
     gz = lambda t: np_(torch.zeros_like(t) if t.grad is None else t.grad)
     for k in _PRED_KEYS:
+        if k not in preds:
+            continue
         v = preds[k]
         if isinstance(v, list):
             for s_, t in enumerate(v):
                 out[f"d_{k}_{s_}"] = gz(t)
         else:
             out["d_" + k] = gz(v)
+    if wreg is not None:
+        for i, w_ in enumerate(wreg):
+            out[f"d_wreg_{i}"] = gz(w_)
+            if not F64:
+                out[f"in_wreg_{i}"] = np_(w_)
+    if flow:      # the flow-warped views and their targets (augm_data of losses.py:95-101)
+        augm = total_obj.append_data(feats, preds)
+        for s_, (wt, ft) in enumerate(zip(augm["warped_target_ms"], augm["flow_target_ms"])):
+            out[f"warped_{s_}"] = np_(wt)
+            out[f"flow_target_{s_}"] = np_(ft)
     if not F64:
         for k, v in feats.items():
             if k != "image_R":
                 out["in_" + k] = np_(v)
         for k in _PRED_KEYS:
+            if k not in preds:
+                continue
             v = preds[k]
             if isinstance(v, list):
                 for s_, t in enumerate(v):
@@ -203,3 +232,7 @@ if __name__ == "__main__":
     run_stereo_case("stereo_t2", B=2, H=32, W=40, N=3, loss_set="T2", scale_weights=[0.4, 0.8, 1.2, 1.6], seed=505, global_batch=4)
     run_stereo_case("stereo_moa", B=2, H=32, W=64, N=2, loss_set="MOA_WST", scale_weights=[1, 1, 1, 1], seed=606)
     run_stereo_case("stereo_md2", B=2, H=32, W=48, N=3, loss_set="MD2", scale_weights=[1, 1, 1, 1], seed=707)
+    run_stereo_case("stereo_comb", B=2, H=64, W=96, N=2, loss_set="COMB", scale_weights=[0.4, 0.8, 1.2, 1.6], seed=808,
+                    flow="with")
+    run_stereo_case("stereo_flow", B=2, H=64, W=96, N=3, loss_set="FLOW", scale_weights=[1, 1, 1, 1], seed=909,
+                    global_batch=4, flow="only")

@@ -342,6 +342,12 @@ def keras_mse(y_true, y_pred):
     return (d * d).sum(dim=-1) / d.shape[-1]
 
 
+def l2_loss(t, **_):
+    """tf.nn.l2_loss: sum(t ** 2) / 2 (TF op definition)."""
+    t = _t(t)
+    return (t * t).sum() / 2
+
+
 def _unsupported(name):
     def f(*a, **k):
         raise NotImplementedError(f"tf_shim: {name} is outside the hot path")
@@ -371,7 +377,7 @@ def install(opts_overrides=None):
     tf.image = types.SimpleNamespace(resize=image_resize,
                                      convert_image_dtype=_unsupported("image.convert_image_dtype"))
     tf.nn = types.SimpleNamespace(compute_average_loss=compute_average_loss,
-                                  l2_loss=_unsupported("nn.l2_loss"), avg_pool=_unsupported("nn.avg_pool"))
+                                  l2_loss=l2_loss, avg_pool=_unsupported("nn.avg_pool"))
     tf.random = types.SimpleNamespace(uniform=random_uniform, normal=_unsupported("random.normal"))
 
     keras = types.ModuleType("tensorflow.keras")

@@ -26,6 +26,9 @@ def case_inputs(g, device="cpu", dtype=torch.float32):
 
 STEREO_CASES = ["stereo_t1", "stereo_t2", "stereo_moa", "stereo_md2"]
 PRED_KEYS = ("depth_ms", "disp_ms", "pose", "depth_ms_R", "disp_ms_R", "pose_R", "pose_LR", "pose_RL")
+# optical-flow rows: LOSS_RIGID_COMB with PWC-shaped flows, LOSS_FLOW with flows only
+FLOW_CASES = ["stereo_comb", "stereo_flow"]
+FLOW_KEYS = ("flow_ms", "flow_ms_R")
 
 
 def stereo_case_inputs(g, device="cpu", dtype=torch.float32):
@@ -33,7 +36,9 @@ def stereo_case_inputs(g, device="cpu", dtype=torch.float32):
     cv = lambda a: torch.tensor(a, dtype=dtype, device=device)
     feats = {k: cv(g["in_" + k]) for k in ("image5d", "intrinsic", "image5d_R", "intrinsic_R", "stereo_T_LR")}
     preds = {}
-    for k in PRED_KEYS:
+    for k in PRED_KEYS + FLOW_KEYS:
+        if "in_" + k not in g.files and f"in_{k}_0" not in g.files:
+            continue
         if "in_" + k in g.files:
             preds[k] = cv(g["in_" + k])
         else:
@@ -42,6 +47,12 @@ def stereo_case_inputs(g, device="cpu", dtype=torch.float32):
     lw = dict(zip(g["loss_names"].tolist(), [float(w) for w in g["loss_weights"]]))
     sw = [float(w) for w in g["scale_weights"]]
     return feats, preds, lw, sw, int(g["global_batch"])
+
+
+def case_reg_weights(g, device="cpu", dtype=torch.float32):
+    """weights_to_regularize of a flow golden case (None when the case has none)"""
+    n = sum(1 for k in g.files if re.fullmatch(r"in_wreg_\d+", k))
+    return [torch.tensor(g[f"in_wreg_{i}"], dtype=dtype, device=device) for i in range(n)] or None
 
 
 def golden_grad(g, key):

@@ -5,7 +5,8 @@ import pytest
 import torch
 
 from oracle import xpt_oracle as orc
-from helpers import CASES, PRED_KEYS, STEREO_CASES, case_inputs, golden_grad, load_case, relerr, stereo_case_inputs
+from helpers import (CASES, FLOW_CASES, FLOW_KEYS, PRED_KEYS, STEREO_CASES, case_inputs, case_reg_weights, golden_grad,
+                     load_case, relerr, stereo_case_inputs)
 
 
 def test_pieces_pose_and_photometric_maps():
@@ -86,6 +87,37 @@ def test_stereo_total_loss_and_gradients(name, kind):
                 assert relerr(got[s].numpy(), ref[s]) < gtol, (k, s)
         else:
             assert relerr(got.numpy(), ref) < gtol, k
+
+
+@pytest.mark.parametrize("name", FLOW_CASES)
+@pytest.mark.parametrize("kind", ["f32", "f64"])
+def test_flow_total_loss_and_gradients(name, kind):
+    """FlowWarpMultiScale + flowL2 + flow_reg (LOSS_FLOW) and CombinedLossMultiScale (LOSS_RIGID_COMB) on a stereo
+    rig -- against the reference's own source (flow_warping.py, losses.py:235-279,497-534)."""
+    g32, g = load_case(name), load_case(name, kind)
+    dt = torch.float64 if kind == "f64" else torch.float32
+    feats, preds, lw, sw, gb = stereo_case_inputs(g32, dtype=dt)
+    wreg = case_reg_weights(g32, dtype=dt)
+    r = orc.stereo_loss_and_grads(feats, preds, lw, sw, gb, weights_to_regularize=wreg)
+    ltol, gtol = (1e-12, 1e-9) if kind == "f64" else (1e-5, 1e-4)
+    assert relerr(r["total"].numpy(), g["total"]) < ltol
+    for k in lw:
+        assert relerr(r["by_type"][k].numpy(), g["loss_" + k]) < max(ltol, 2e-5 if kind == "f32" else 0), k
+    for s in range(len(preds["flow_ms"])):
+        assert np.abs(r["augm"]["warped_target_ms"][s].numpy() - g[f"warped_{s}"]).max() < (1e-5 if kind == "f32" else 1e-12)
+        assert np.abs(r["augm"]["flow_target_ms"][s].numpy() - g[f"flow_target_{s}"]).max() < (1e-6 if kind == "f32" else 1e-12)
+    for k in PRED_KEYS + FLOW_KEYS:
+        if k not in preds:
+            continue
+        ref, got = golden_grad(g, k), r["grads"][k]
+        if isinstance(ref, list):
+            for s in range(len(ref)):
+                assert relerr(got[s].numpy(), ref[s]) < gtol, (k, s)
+        else:
+            assert relerr(got.numpy(), ref) < gtol, k
+    if wreg is not None:
+        for i, w in enumerate(r["grads"]["weights_to_regularize"]):
+            assert relerr(w.numpy(), g[f"d_wreg_{i}"]) < gtol
 
 
 def test_pose_matr2rvec_round_trip():
