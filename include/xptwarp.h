@@ -40,7 +40,7 @@ extern "C" {
 #define XPT_API
 #endif
 
-#define XPT_VERSION 100        /* 0.1.0 */
+#define XPT_VERSION 101        /* 0.1.1 */
 #define XPT_MAX_SCALES 8
 
 typedef enum {
@@ -180,6 +180,37 @@ XPT_API int xpt_photometric_min_loss(xpt_ctx* ctx, int method,
                              const float* target, int64_t target_batch_stride, float* loss_batch,
                              const float* grad_loss_batch, float* const d_synth_ms[],
                              float* const d_stereo_synth_ms[], void* stream);
+
+/* losses.py:235-279 CombinedLossMultiScale(method).__call__: every scale's synthesis [B,N,h,w,3] and the
+ * flow-warped view `warped` = warped_target_ms[0] [B,N,warped_height,warped_width,3] are bilinearly up-sampled to
+ * H x W (losses.py:377-383); per pixel, channel and source the static term counts only where it is SMALLER than
+ * the optical-flow term (the mask is a constant: no gradient reaches `warped`); mean over [N,H,W,3] ->
+ * loss_batch [B] (scale-merged).  d_synth_ms as for xpt_photometric_min_loss.                                  */
+XPT_API int xpt_photometric_cmb_loss(xpt_ctx* ctx, int method, const float* const synth_ms[], const float* warped,
+                             int warped_height, int warped_width, const float* target,
+                             int64_t target_batch_stride, float* loss_batch, const float* grad_loss_batch,
+                             float* const d_synth_ms[], void* stream);
+
+/* model/synthesize/flow_warping.py:11-49 FlowWarpMultiScale.__call__: flow_ms[s] [B,N,H_s,W_s,2] (the ctx's
+ * scales are the FLOW scales, e.g. 4,8,16,32 for PWC-Net, flow_net.py:44-48) -> warped_ms[s] [B,N,H_s,W_s,3]:
+ * the source frames resized to the flow's size (flow_warping.py:36-49) and sampled at grid - flow (:51-71) by
+ * BilinearInterpolation (bilinear_interp.py:7-147).  mask_ms (may be NULL) receives the validity mask.
+ * frames->target and frames->intrinsic are not read.                                                           */
+XPT_API int xpt_flow_warp(xpt_ctx* ctx, const xpt_frames* frames, const float* const flow_ms[],
+                  float* const warped_ms[], float* const mask_ms[], void* stream);
+
+/* Backward of xpt_flow_warp for an upstream gradient grad_warped_ms[s] = dL/d warped_ms[s]:
+ * d_flow_ms[s] [B,N,H_s,W_s,2] (may be NULL) and d_source [B,N,H,W,3] dense (may be NULL; fp32 atomics).       */
+XPT_API int xpt_flow_warp_backward(xpt_ctx* ctx, const xpt_frames* frames, const float* const flow_ms[],
+                           const float* const grad_warped_ms[], float* const d_flow_ms[], float* d_source,
+                           void* stream);
+
+/* losses.py:522-534 L2Regularizer.__call__ ("flow_reg"): loss[0] = sum_i tf.nn.l2_loss(weights[i]) =
+ * sum_i sum(weights[i]^2)/2 over `num` dense fp32 device tensors of counts[i] elements (the caller tiles the
+ * scalar to [batch]).  With d_weights != NULL also writes d_weights[i] = grad_loss[0] * weights[i]
+ * (grad_loss: device pointer to the upstream dL/d loss scalar).                                               */
+XPT_API int xpt_l2_regularizer(xpt_ctx* ctx, const float* const weights[], const int64_t counts[], int num,
+                       float* loss, const float* grad_loss, float* const d_weights[], void* stream);
 
 /* losses.py:386-440 SmoothenessLossMultiScale.__call__ -> loss_batch [B];
  * optional backward to d_disp_ms as above.                                    */

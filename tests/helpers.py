@@ -70,7 +70,7 @@ def relerr(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
 
 
-def grad_close(cuda, ref32, ref64, tol=1e-4, outlier_frac=1e-4):
+def grad_close(cuda, ref32, ref64, tol=1e-4, outlier_frac=1e-4, self_factor=0):
     """Gradient parity at BASELINE.json's 1e-4 relative (max-norm) tolerance, made robust to the
     path's genuine discontinuities: d(bilinear)/du jumps where floor(u) changes, clip and |.| have
     kinks.  At such pixels the fp32 and fp64 ORACLES already disagree with each other (measured:
@@ -80,6 +80,8 @@ def grad_close(cuda, ref32, ref64, tol=1e-4, outlier_frac=1e-4):
     twice the fp32 oracle's own (+ tol).  (Outliers are excluded from the L2 term because one
     floor() flip moves a whole tap set: e.g. golden case stereo_moa has u = 53.999996 (fp32) /
     53.9999985 (fp64) at one pixel whose gradient then differs by 1.3e-2 of the max norm.)
+    self_factor > 0 (losses built on a comparison mask, e.g. CombinedLossMultiScale's static < flow): the budget
+    is at least self_factor x the number of elements on which the two ORACLES disagree by more than `tol`.
     Returns (ok, message)."""
     c = np.asarray(cuda, dtype=np.float64)
     a = np.asarray(ref32, dtype=np.float64)
@@ -87,7 +89,7 @@ def grad_close(cuda, ref32, ref64, tol=1e-4, outlier_frac=1e-4):
     m = max(np.abs(b).max(), 1e-30)
     near = (np.abs(c - b) <= tol * m) | (np.abs(c - a) <= tol * m)
     n_out = int((~near).sum())
-    budget = max(4, int(outlier_frac * c.size))
+    budget = max(4, int(outlier_frac * c.size), int(self_factor * (np.abs(a - b) > tol * m).sum()))
     nb = max(np.linalg.norm(b), 1e-30)
     l2_c, l2_a = np.linalg.norm((c - b)[near]) / nb, np.linalg.norm(a - b) / nb
     ok = n_out <= budget and l2_c <= 2 * l2_a + tol

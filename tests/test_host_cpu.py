@@ -100,12 +100,15 @@ def test_loss_factory_mirrors_reference_filtering():
     assert not check_loss_dependency("L1_R", {"image", "intrinsic"})
     with pytest.raises(xptwarp.WrongInputException):
         xptwarp.losses.PhotometricLossMultiScale("L3", None)
-    # a loss outside the hot path (the flow losses need FlowNet outputs) is constructible, like in the
-    # reference's pool, but refuses to run
-    tl2 = xptwarp.loss_factory({"image": 1, "intrinsic": 1}, {"flowL2": 1.0, "md2L1": 0.5}, np.ones(4))
+    # the optical-flow rows of the pool (loss_factory.py:27-29): flowL2 is the "L2" photometric term; flow_reg
+    # without weights_to_regularize refuses to run
+    tl2 = xptwarp.loss_factory({"image": 1, "intrinsic": 1}, {"flowL2": 1.0, "md2L1": 0.5, "flow_reg": 4e-7, "cmbSSIM": 0.5},
+                               np.ones(4))
     assert isinstance(tl2.loss_objects["md2L1"], xptwarp.MonoDepth2LossMultiScale)
+    assert isinstance(tl2.loss_objects["flowL2"], xptwarp.FlowWarpLossMultiScale) and tl2.loss_objects["flowL2"].method == "L2"
+    assert isinstance(tl2.loss_objects["cmbSSIM"], xptwarp.CombinedLossMultiScale)
     with pytest.raises(xptwarp.WrongInputException):
-        tl2.loss_objects["flowL2"](None, None, None)
+        tl2.loss_objects["flow_reg"]({"image5d": None}, None, None)
     # the whole stereo pool of config-example.py:76-121 is served on a rig dataset
     rig = {"image": 1, "intrinsic": 1, "image_R": 1, "intrinsic_R": 1, "stereo_T_LR": 1}
     tl3 = xptwarp.loss_factory(rig, dict(weights, moaL1=5.0, moaSSIM_R=0.5), np.ones(4), stereo=True, batch_size=4)

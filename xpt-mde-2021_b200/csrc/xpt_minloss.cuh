@@ -33,6 +33,10 @@ struct MinLossArgs {
   float* loss_part;                    // [B][S*tiles]
   float* gsynth[kMaxScales];           // GRAD: [B,N,h,w,3], zeroed by the host, accumulated atomically
   float* gstereo[kMaxScales];          // GRAD: [B,NS,h,w,3]
+  // CombinedLossMultiScale (losses.py:235-279): instead of the minimum over sources, every source's term counts
+  // where it is smaller than the term of the flow-warped view `cmb_flow` [B,N,cmb_h,cmb_w,3] (level 0 of
+  // warped_target_ms), both up-sampled to H x W; norm[] then carries 1/(N*H*W*3).  NULL = min-over-sources mode.
+  const float* cmb_flow; int cmb_h, cmb_w;
 };
 
 template <bool GRAD>
@@ -117,10 +121,9 @@ __global__ void __launch_bounds__(kPhotoThreads) k_photo_min(MinLossArgs a) {
   const float coef = gb * a.norm[l];
   const int nsrc = a.N + a.NS;
 
-  // up-sampled region of source m into sy (zero outside the image)
-  auto load_region = [&](int m) {
-    const float* low = m < a.N ? a.synth[l] + ((size_t)b * a.N + m) * h * w * 3
-                               : a.stereo[l] + ((size_t)b * a.NS + (m - a.N)) * h * w * 3;
+  // up-sampled region of a low-resolution view [h,w,3] into sy (zero outside the image)
+  auto load_low = [&](const float* low, int h, int w) {
+    const float sc_y = (float)h / (float)H, sc_x = (float)w / (float)W;
     for (int i = tid; i < SM::kRegion; i += kPhotoThreads) {
       const int ry = i / RW, rx = i % RW;
       const int gy = ty0 + ry - HL, gx = tx0 + rx - HL;
@@ -142,6 +145,10 @@ __global__ void __launch_bounds__(kPhotoThreads) k_photo_min(MinLossArgs a) {
       }
       sy[i] = yv[0]; sy[SM::kRegion + i] = yv[1]; sy[2 * SM::kRegion + i] = yv[2];
     }
+  };
+  auto load_region = [&](int m) {
+    load_low(m < a.N ? a.synth[l] + ((size_t)b * a.N + m) * h * w * 3
+                     : a.stereo[l] + ((size_t)b * a.NS + (m - a.N)) * h * w * 3, h, w);
   };
 
   // per-pixel, per-channel loss of the source currently in sy at stats position i (in-image positions only);
@@ -187,6 +194,113 @@ __global__ void __launch_bounds__(kPhotoThreads) k_photo_min(MinLossArgs a) {
     }
     return r;
   };
+
+  // dL/dS of the source in sy from the coefficient planes sA/sB/sC (SSIM: box-summed over the 3x3 window), pushed
+  // through the adjoint of the up-sampling into the low-resolution gradient (fp32 atomics)
+  auto scatter = [&](int m) {
+    float* glow = m < a.N ? a.gsynth[l] + ((size_t)b * a.N + m) * h * w * 3
+                          : a.gstereo[l] + ((size_t)b * a.NS + (m - a.N)) * h * w * 3;
+    for (int i = tid; i < kTW * kTH; i += kPhotoThreads) {
+      const int cy_ = i / kTW, cx_ = i % kTW;
+      const int gy = ty0 + cy_, gx = tx0 + cx_;
+      if (gy >= H || gx >= W) continue;
+      const int ri = (cy_ + HL) * RW + (cx_ + HL);
+      const int si = (cy_ + HS) * SW + (cx_ + HS);
+      float g[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        if (ssim) {
+          const float yv = sy[c * SM::kRegion + ri], xv = sx[c * SM::kRegion + ri];
+          float gc = 0.f;
+#pragma unroll
+          for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+              const int k = c * SM::kStats + si + dy * SW + dx;
+              gc += sA[k] + 2.f * yv * sB[k] + xv * sC[k];
+            }
+          g[c] = gc;
+        } else {
+          g[c] = sA[c * SM::kStats + si];
+        }
+      }
+      if (g[0] == 0.f && g[1] == 0.f && g[2] == 0.f) continue;
+      // adjoint of the up-sampling: top = tl + (tr - tl) fx, out = top + (bot - top) fy
+      int y0, y1, x0, x1; float fy, fx;
+      up_taps(gy, h, sc_y, y0, y1, fy);
+      up_taps(gx, w, sc_x, x0, x1, fx);
+      const float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx, w10 = fy * (1.f - fx), w11 = fy * fx;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        atomicAdd(glow + ((size_t)y0 * w + x0) * 3 + c, w00 * g[c]);
+        atomicAdd(glow + ((size_t)y0 * w + x1) * 3 + c, w01 * g[c]);
+        atomicAdd(glow + ((size_t)y1 * w + x0) * 3 + c, w10 * g[c]);
+        atomicAdd(glow + ((size_t)y1 * w + x1) * 3 + c, w11 * g[c]);
+      }
+    }
+  };
+
+  // ---- CombinedLossMultiScale: per source, the static term where it beats the flow term ----------------------
+  if (a.cmb_flow) {
+    float lsum = 0.f;
+    for (int m = 0; m < a.N; ++m) {
+      __syncthreads();
+      load_low(a.cmb_flow + ((size_t)b * a.N + m) * a.cmb_h * a.cmb_w * 3, a.cmb_h, a.cmb_w);
+      __syncthreads();
+      for (int i = tid; i < SM::kStats; i += kPhotoThreads) {       // flow term of this source -> smin
+        const int qy = i / SW, qx = i % SW;
+        const int gy = ty0 + qy - HS, gx = tx0 + qx - HS;
+        if (!(gy >= 0 && gy < H && gx >= 0 && gx < W)) continue;
+        const int ri = (qy + 1) * RW + (qx + 1);
+        const bool masked = ((sy[ri] + sy[SM::kRegion + ri]) + sy[2 * SM::kRegion + ri]) == 0.f;
+        const int cy = min(gy + 1, H - 1) - max(gy - 1, 0) + 1, cx = min(gx + 1, W - 1) - max(gx - 1, 0) + 1;
+        const float inv = 1.f / (float)(cy * cx);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) smin[c * SM::kStats + i] = term(i, c, masked, inv).val;
+      }
+      __syncthreads();
+      load_region(m);
+      __syncthreads();
+      for (int i = tid; i < SM::kStats; i += kPhotoThreads) {
+        const int qy = i / SW, qx = i % SW;
+        const int gy = ty0 + qy - HS, gx = tx0 + qx - HS;
+        const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
+        const bool centre = in && qy >= HS && qy < HS + kTH && qx >= HS && qx < HS + kTW;
+        const int ri = (qy + 1) * RW + (qx + 1);
+        const bool masked = ((sy[ri] + sy[SM::kRegion + ri]) + sy[2 * SM::kRegion + ri]) == 0.f;
+        const int cy = min(gy + 1, H - 1) - max(gy - 1, 0) + 1, cx = min(gx + 1, W - 1) - max(gx - 1, 0) + 1;
+        const float inv = in ? 1.f / (float)(cy * cx) : 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float A = 0.f, Bq = 0.f, Cq = 0.f;
+          if (in) {
+            const Term r = term(i, c, masked, inv);
+            const bool keep = r.val < smin[c * SM::kStats + i];     // tf.cast(static_loss < flow_loss): a constant
+            if (keep && centre) lsum += r.val;
+            if (GRAD && keep && r.pass && !masked) {
+              if (ssim) { const float hh = -0.5f * coef; A = hh * r.dm * inv; Bq = hh * r.dq * inv; Cq = hh * r.dr * inv; }
+              else A = a.method == 0 ? coef * sgnf(r.dm) : coef * 2.f * r.dm;
+            }
+          }
+          if (GRAD) { sA[c * SM::kStats + i] = A; sB[c * SM::kStats + i] = Bq; sC[c * SM::kStats + i] = Cq; }
+        }
+      }
+      if constexpr (GRAD) {
+        __syncthreads();
+        scatter(m);
+      }
+    }
+    lsum = warp_sum(lsum);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = lsum;
+    __syncthreads();
+    if (tid == 0) {
+      float v = 0.f;
+      for (int k = 0; k < kPhotoThreads / 32; ++k) v += red[k];
+      a.loss_part[(size_t)b * a.S * a.tiles + blockIdx.x] = v * a.norm[l];
+    }
+    return;
+  }
 
   // ---- sweep 1: minimum and tie count per (pixel, channel) over the stats region -------------------------
   for (int m = 0; m < nsrc; ++m) {
@@ -259,46 +373,7 @@ __global__ void __launch_bounds__(kPhotoThreads) k_photo_min(MinLossArgs a) {
       }
     }
     __syncthreads();
-    float* glow = m < a.N ? a.gsynth[l] + ((size_t)b * a.N + m) * h * w * 3
-                          : a.gstereo[l] + ((size_t)b * a.NS + (m - a.N)) * h * w * 3;
-    for (int i = tid; i < kTW * kTH; i += kPhotoThreads) {
-      const int cy_ = i / kTW, cx_ = i % kTW;
-      const int gy = ty0 + cy_, gx = tx0 + cx_;
-      if (gy >= H || gx >= W) continue;
-      const int ri = (cy_ + HL) * RW + (cx_ + HL);
-      const int si = (cy_ + HS) * SW + (cx_ + HS);
-      float g[3];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        if (ssim) {
-          const float yv = sy[c * SM::kRegion + ri], xv = sx[c * SM::kRegion + ri];
-          float gc = 0.f;
-#pragma unroll
-          for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-            for (int dx = -1; dx <= 1; ++dx) {
-              const int k = c * SM::kStats + si + dy * SW + dx;
-              gc += sA[k] + 2.f * yv * sB[k] + xv * sC[k];
-            }
-          g[c] = gc;
-        } else {
-          g[c] = sA[c * SM::kStats + si];
-        }
-      }
-      if (g[0] == 0.f && g[1] == 0.f && g[2] == 0.f) continue;
-      // adjoint of the up-sampling: top = tl + (tr - tl) fx, out = top + (bot - top) fy
-      int y0, y1, x0, x1; float fy, fx;
-      up_taps(gy, h, sc_y, y0, y1, fy);
-      up_taps(gx, w, sc_x, x0, x1, fx);
-      const float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx, w10 = fy * (1.f - fx), w11 = fy * fx;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        atomicAdd(glow + ((size_t)y0 * w + x0) * 3 + c, w00 * g[c]);
-        atomicAdd(glow + ((size_t)y0 * w + x1) * 3 + c, w01 * g[c]);
-        atomicAdd(glow + ((size_t)y1 * w + x0) * 3 + c, w10 * g[c]);
-        atomicAdd(glow + ((size_t)y1 * w + x1) * 3 + c, w11 * g[c]);
-      }
-    }
+    scatter(m);
   }
 }
 

@@ -15,6 +15,7 @@
 
 #include "xpt_kernels.cuh"
 #include "xpt_fused.cuh"
+#include "xpt_flow.cuh"
 #include "xpt_minloss.cuh"
 
 using namespace xpt;
@@ -80,6 +81,7 @@ struct xpt_ctx {
   float* dsrc_lvl[kMaxScales];  // s > 1
   float* tgt0_copy;             // unused unless a level-0 copy is wanted without a user buffer
   float* min_part;              // [B][S * full-res tiles] partial sums of xpt_photometric_min_loss
+  float* l2_part;               // block partials (doubles) of xpt_l2_regularizer
   // staging for the host-buffer entry point
   float* st_frames; float* st_K; float* st_pose; float* st_losses; float* st_loss_batch; float* st_dpose;
   float* st_dsource;
@@ -565,7 +567,7 @@ void xpt_destroy(xpt_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->cfg.device);
   auto F = [](float* p) { if (p) cudaFree(p); };
-  F(ctx->geoK); F(reinterpret_cast<float*>(ctx->loss_sum_b)); F(ctx->loss_part); F(ctx->pose_part); F(ctx->tgt0_copy); F(ctx->min_part);
+  F(ctx->geoK); F(reinterpret_cast<float*>(ctx->loss_sum_b)); F(ctx->loss_part); F(ctx->pose_part); F(ctx->tgt0_copy); F(ctx->min_part); F(ctx->l2_part);
   F(ctx->st_frames); F(ctx->st_K); F(ctx->st_pose); F(ctx->st_losses); F(ctx->st_loss_batch); F(ctx->st_dpose);
   F(ctx->st_dsource);
   for (int l = 0; l < kMaxScales; ++l) {
@@ -708,10 +710,11 @@ int xpt_photometric_loss(xpt_ctx* ctx, int method, const float* const synth_ms[]
   return XPT_OK;
 }
 
-int xpt_photometric_min_loss(xpt_ctx* ctx, int method, const float* const synth_ms[], const float* const stereo_synth_ms[],
-                             const float* target, int64_t target_batch_stride, float* loss_batch,
-                             const float* grad_loss_batch, float* const d_synth_ms[], float* const d_stereo_synth_ms[],
-                             void* stream) {
+static int min_loss_impl(xpt_ctx* ctx, int method, const float* const synth_ms[], const float* const stereo_synth_ms[],
+                         const float* cmb_flow, int cmb_h, int cmb_w,
+                         const float* target, int64_t target_batch_stride, float* loss_batch,
+                         const float* grad_loss_batch, float* const d_synth_ms[], float* const d_stereo_synth_ms[],
+                         void* stream) {
   if (!ctx || !loss_batch || !target) return fail(XPT_BAD_ARGUMENT, "xpt_photometric_min_loss: NULL argument");
   if (method != XPT_PHOTO_L1 && method != XPT_PHOTO_L2 && method != XPT_PHOTO_SSIM)
     return fail(XPT_BAD_ARGUMENT, "unknown photometric method %d", method);
@@ -729,6 +732,7 @@ int xpt_photometric_min_loss(xpt_ctx* ctx, int method, const float* const synth_
   a.target = target; a.tgt_bs = target_batch_stride;
   a.method = method == XPT_PHOTO_L1 ? 0 : (method == XPT_PHOTO_L2 ? 1 : 2);
   a.gbatch = grad_loss_batch;
+  a.cmb_flow = cmb_flow; a.cmb_h = cmb_h; a.cmb_w = cmb_w;
   a.tiles_x = cdiv(ctx->W, kTW);
   a.tiles = a.tiles_x * cdiv(ctx->H, kTH);
   XPT_TRY(dev_alloc(ctx, &ctx->min_part, (size_t)ctx->B * ctx->S * a.tiles));
@@ -736,7 +740,8 @@ int xpt_photometric_min_loss(xpt_ctx* ctx, int method, const float* const synth_
   for (int l = 0; l < ctx->S; ++l) {
     a.h[l] = ctx->h[l]; a.w[l] = ctx->w[l];
     a.synth[l] = synth_ms[l]; a.stereo[l] = stereo_synth_ms ? stereo_synth_ms[l] : nullptr;
-    a.norm[l] = (float)((double)ctx->cfg.scale_weights[l] / ((double)ctx->H * ctx->W * 3.0));
+    // min over sources: mean over [H,W,3]; combined loss: mean over [N,H,W,3] (losses.py:273)
+    a.norm[l] = (float)((double)ctx->cfg.scale_weights[l] / ((double)ctx->H * ctx->W * 3.0 * (cmb_flow ? ctx->N : 1)));
     if (d_synth_ms) {
       a.gsynth[l] = d_synth_ms[l];
       XPT_CUDA(cudaMemsetAsync(d_synth_ms[l], 0, (size_t)ctx->B * ctx->N * lvl_pix(ctx, l) * 3 * sizeof(float), st));
@@ -761,6 +766,104 @@ int xpt_photometric_min_loss(xpt_ctx* ctx, int method, const float* const synth_
   XPT_LAUNCH_CHECK("k_photo_min");
   k_sum_slots<<<ctx->B, 128, 0, st>>>(ctx->min_part, ctx->S * a.tiles, loss_batch);
   XPT_LAUNCH_CHECK("k_sum_slots");
+  return XPT_OK;
+}
+
+int xpt_photometric_min_loss(xpt_ctx* ctx, int method, const float* const synth_ms[], const float* const stereo_synth_ms[],
+                             const float* target, int64_t target_batch_stride, float* loss_batch,
+                             const float* grad_loss_batch, float* const d_synth_ms[], float* const d_stereo_synth_ms[],
+                             void* stream) {
+  return min_loss_impl(ctx, method, synth_ms, stereo_synth_ms, nullptr, 0, 0, target, target_batch_stride, loss_batch,
+                       grad_loss_batch, d_synth_ms, d_stereo_synth_ms, stream);
+}
+
+int xpt_photometric_cmb_loss(xpt_ctx* ctx, int method, const float* const synth_ms[], const float* warped,
+                             int warped_height, int warped_width, const float* target, int64_t target_batch_stride,
+                             float* loss_batch, const float* grad_loss_batch, float* const d_synth_ms[], void* stream) {
+  if (!warped) return fail(XPT_BAD_ARGUMENT, "xpt_photometric_cmb_loss: warped is NULL");
+  if (warped_height < 1 || warped_width < 1) return fail(XPT_BAD_SHAPE, "warped view %dx%d", warped_height, warped_width);
+  return min_loss_impl(ctx, method, synth_ms, nullptr, warped, warped_height, warped_width, target, target_batch_stride,
+                       loss_batch, grad_loss_batch, d_synth_ms, nullptr, stream);
+}
+
+// ---- optical-flow warping (flow_warping.py) -------------------------------------------------------------
+static int flow_warp_impl(xpt_ctx* ctx, const xpt_frames* frames, const float* const flow_ms[], float* const warped_ms[],
+                          float* const mask_ms[], const float* const grad_warped_ms[], float* const d_flow_ms[],
+                          float* d_source, void* stream) {
+  const bool bwd = grad_warped_ms != nullptr;
+  if (!ctx) return fail(XPT_BAD_ARGUMENT, "xpt_flow_warp: ctx is NULL");
+  if (!frames || !frames->source) return fail(XPT_BAD_ARGUMENT, "frames.source is NULL");
+  const long long hw3 = (long long)ctx->H * ctx->W * 3;
+  if (frames->source_frame_stride < hw3) return fail(XPT_BAD_SHAPE, "source_frame_stride %lld < H*W*3", (long long)frames->source_frame_stride);
+  if (ctx->B > 1 && frames->source_batch_stride < hw3) return fail(XPT_BAD_SHAPE, "source_batch_stride too small");
+  XPT_TRY(check_list(ctx, (const void* const*)flow_ms, "flow_ms", true));
+  if (bwd) {
+    XPT_TRY(check_list(ctx, (const void* const*)grad_warped_ms, "grad_warped_ms", true));
+    if (!d_flow_ms && !d_source) return fail(XPT_BAD_ARGUMENT, "xpt_flow_warp_backward: no gradient output requested");
+  } else {
+    XPT_TRY(check_list(ctx, (const void* const*)warped_ms, "warped_ms", true));
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  XPT_CUDA(cudaSetDevice(ctx->cfg.device));
+  ctx->launches = 0;
+  xpt_frames f = *frames;
+  f.target = nullptr;                       // the flow warp reads the source frames only
+  XPT_TRY(launch_pyramids(ctx, &f, nullptr, true, st));
+  FlowWarpArgs a;
+  memset(&a, 0, sizeof(a));
+  a.lt = make_levels(ctx, &f, nullptr);
+  a.B = ctx->B; a.N = ctx->N;
+  if (bwd) XPT_TRY(prepare_dsource(ctx, d_source, a.d_src, a.d_src_bs, a.d_src_fs, st));
+  unsigned gx = 1;
+  for (int l = 0; l < ctx->S; ++l) {
+    a.flow[l] = flow_ms[l];
+    if (bwd) { a.gwarped[l] = grad_warped_ms[l]; a.d_flow[l] = d_flow_ms ? d_flow_ms[l] : nullptr; }
+    else { a.warped[l] = warped_ms[l]; a.mask[l] = mask_ms ? mask_ms[l] : nullptr; }
+    const unsigned g = (unsigned)cdiv((long long)ctx->B * ctx->N * lvl_pix(ctx, l), 256);
+    if (g > gx) gx = g;
+  }
+  dim3 grid(gx, ctx->S);
+  if (bwd) k_flow_warp<true><<<grid, 256, 0, st>>>(a);
+  else k_flow_warp<false><<<grid, 256, 0, st>>>(a);
+  XPT_LAUNCH_CHECK("k_flow_warp");
+  if (bwd) XPT_TRY(finish_dsource(ctx, d_source, st));
+  return XPT_OK;
+}
+
+int xpt_flow_warp(xpt_ctx* ctx, const xpt_frames* frames, const float* const flow_ms[], float* const warped_ms[],
+                  float* const mask_ms[], void* stream) {
+  return flow_warp_impl(ctx, frames, flow_ms, warped_ms, mask_ms, nullptr, nullptr, nullptr, stream);
+}
+
+int xpt_flow_warp_backward(xpt_ctx* ctx, const xpt_frames* frames, const float* const flow_ms[],
+                           const float* const grad_warped_ms[], float* const d_flow_ms[], float* d_source, void* stream) {
+  if (!grad_warped_ms) return fail(XPT_BAD_ARGUMENT, "grad_warped_ms is NULL");
+  return flow_warp_impl(ctx, frames, flow_ms, nullptr, nullptr, grad_warped_ms, d_flow_ms, d_source, stream);
+}
+
+int xpt_l2_regularizer(xpt_ctx* ctx, const float* const weights[], const int64_t counts[], int num, float* loss,
+                       const float* grad_loss, float* const d_weights[], void* stream) {
+  if (!ctx || !loss || (num > 0 && (!weights || !counts))) return fail(XPT_BAD_ARGUMENT, "xpt_l2_regularizer: NULL argument");
+  if (d_weights && !grad_loss) return fail(XPT_BAD_ARGUMENT, "xpt_l2_regularizer: d_weights needs grad_loss");
+  cudaStream_t st = (cudaStream_t)stream;
+  XPT_CUDA(cudaSetDevice(ctx->cfg.device));
+  ctx->launches = 0;
+  constexpr int kBlocks = 296;
+  XPT_TRY(dev_alloc(ctx, &ctx->l2_part, 2 * kBlocks));
+  XPT_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
+  for (int i = 0; i < num; ++i) {
+    if (!weights[i] || counts[i] < 0) return fail(XPT_BAD_ARGUMENT, "weights[%d] is NULL or has a negative count", i);
+    if (counts[i] == 0) continue;
+    const int blocks = (int)(counts[i] < (int64_t)kBlocks * 256 ? cdiv(counts[i], 256) : kBlocks);
+    k_l2_partial<<<blocks, 256, 0, st>>>(weights[i], counts[i], reinterpret_cast<double*>(ctx->l2_part));
+    XPT_LAUNCH_CHECK("k_l2_partial");
+    k_l2_finish<<<1, 32, 0, st>>>(reinterpret_cast<const double*>(ctx->l2_part), blocks, loss, 1);
+    XPT_LAUNCH_CHECK("k_l2_finish");
+    if (d_weights && d_weights[i]) {
+      k_scale_by<<<blocks, 256, 0, st>>>(weights[i], counts[i], grad_loss, d_weights[i]);
+      XPT_LAUNCH_CHECK("k_scale_by");
+    }
+  }
   return XPT_OK;
 }
 

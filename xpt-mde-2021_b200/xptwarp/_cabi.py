@@ -70,6 +70,15 @@ SYMBOLS = {
     "xpt_photometric_min_loss": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(PtrArray), C.POINTER(PtrArray), C.c_void_p,
                                            C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(PtrArray), C.POINTER(PtrArray),
                                            C.c_void_p]),
+    "xpt_photometric_cmb_loss": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(PtrArray), C.c_void_p, C.c_int, C.c_int,
+                                           C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(PtrArray),
+                                           C.c_void_p]),
+    "xpt_flow_warp": (C.c_int, [C.c_void_p, C.POINTER(XptFrames), C.POINTER(PtrArray), C.POINTER(PtrArray),
+                                C.POINTER(PtrArray), C.c_void_p]),
+    "xpt_flow_warp_backward": (C.c_int, [C.c_void_p, C.POINTER(XptFrames), C.POINTER(PtrArray), C.POINTER(PtrArray),
+                                         C.POINTER(PtrArray), C.c_void_p, C.c_void_p]),
+    "xpt_l2_regularizer": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int, C.c_void_p,
+                                     C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]),
     "xpt_smoothness_loss": (C.c_int, [C.c_void_p, C.POINTER(PtrArray), C.POINTER(PtrArray), C.c_void_p,
                                       C.c_void_p, C.POINTER(PtrArray), C.c_void_p]),
     "xpt_total_loss": (C.c_int, [C.c_void_p, C.POINTER(XptFrames), C.POINTER(PtrArray), C.POINTER(PtrArray),

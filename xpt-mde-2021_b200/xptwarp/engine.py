@@ -225,6 +225,67 @@ class Plan:
             C.byref(ptr_array([t.data_ptr() for t in d_stereo])) if d_stereo is not None else None, self.stream()))
         return loss, d_synth, d_stereo, (target, synth_ms, stereo_synth_ms)
 
+    def photometric_cmb_loss(self, method, synth_ms, warped, target, grad_loss_batch=None, want_grad=False):
+        """xpt_photometric_cmb_loss: static term where it beats the optical-flow term (CombinedLossMultiScale)."""
+        synth_ms = self._level_list(synth_ms, "synth_target_ms", self.N * 3)
+        warped = _dense(warped, "warped_target_ms[0]")
+        if warped.dim() != 5 or warped.shape[0] != self.B or warped.shape[1] != self.N or warped.shape[4] != 3:
+            raise WrongInputException(f"warped_target_ms[0]: expected [{self.B},{self.N},h,w,3], got {tuple(warped.shape)}")
+        target = _frame_view(target, "target", 1)
+        loss = torch.empty((self.B,), dtype=torch.float32, device=self.device)
+        d_synth = self._empty_levels((self.N,), 3) if want_grad else None
+        g = _dense(grad_loss_batch, "grad_loss_batch") if grad_loss_batch is not None else None
+        _cabi.check(self._lib.xpt_photometric_cmb_loss(
+            self.handle, int(method), C.byref(ptr_array([t.data_ptr() for t in synth_ms])), warped.data_ptr(),
+            int(warped.shape[2]), int(warped.shape[3]), target.data_ptr(), target.stride(0), loss.data_ptr(),
+            g.data_ptr() if g is not None else None,
+            C.byref(ptr_array([t.data_ptr() for t in d_synth])) if want_grad else None, self.stream()))
+        return loss, d_synth, (target, synth_ms, warped)
+
+    def flow_warp(self, source, flow_ms, want_mask=False):
+        """xpt_flow_warp (FlowWarpMultiScale.__call__); the plan's scales are the flow scales."""
+        source = _frame_view(source, "source", 2)
+        flow_ms = self._level_list(flow_ms, "flow_ms", self.N * 2)
+        warped = self._empty_levels((self.N,), 3)
+        mask = self._empty_levels((self.N,), 1) if want_mask else None
+        f = XptFrames()
+        f.source, f.source_batch_stride, f.source_frame_stride = source.data_ptr(), source.stride(0), source.stride(1)
+        _cabi.check(self._lib.xpt_flow_warp(
+            self.handle, C.byref(f), C.byref(ptr_array([t.data_ptr() for t in flow_ms])),
+            C.byref(ptr_array([t.data_ptr() for t in warped])),
+            C.byref(ptr_array([t.data_ptr() for t in mask])) if want_mask else None, self.stream()))
+        return warped, mask
+
+    def flow_warp_backward(self, source, flow_ms, grad_warped_ms, want_flow_grad=True, want_source_grad=False):
+        source = _frame_view(source, "source", 2)
+        flow_ms = self._level_list(flow_ms, "flow_ms", self.N * 2)
+        grad_warped_ms = self._level_list(grad_warped_ms, "grad_warped_ms", self.N * 3)
+        d_flow = self._empty_levels((self.N,), 2) if want_flow_grad else None
+        d_source = (torch.empty((self.B, self.N, self.H, self.W, 3), dtype=torch.float32, device=self.device)
+                    if want_source_grad else None)
+        f = XptFrames()
+        f.source, f.source_batch_stride, f.source_frame_stride = source.data_ptr(), source.stride(0), source.stride(1)
+        _cabi.check(self._lib.xpt_flow_warp_backward(
+            self.handle, C.byref(f), C.byref(ptr_array([t.data_ptr() for t in flow_ms])),
+            C.byref(ptr_array([t.data_ptr() for t in grad_warped_ms])),
+            C.byref(ptr_array([t.data_ptr() for t in d_flow])) if want_flow_grad else None,
+            d_source.data_ptr() if want_source_grad else None, self.stream()))
+        return d_flow, d_source
+
+    def l2_regularizer(self, weights, grad_loss=None, want_grad=False):
+        """xpt_l2_regularizer: sum_i sum(w_i^2)/2 -> [1]; with want_grad also grad_loss * w_i per tensor."""
+        ws = [_dense(w, f"weights[{i}]") for i, w in enumerate(weights)]
+        n = len(ws)
+        wp = (C.c_void_p * max(n, 1))(*[w.data_ptr() for w in ws])
+        cnt = (C.c_int64 * max(n, 1))(*[w.numel() for w in ws])
+        loss = torch.empty((1,), dtype=torch.float32, device=self.device)
+        d_w = [torch.empty_like(w) for w in ws] if want_grad else None
+        dp = (C.c_void_p * max(n, 1))(*[d.data_ptr() for d in d_w]) if want_grad else None
+        g = _dense(grad_loss, "grad_loss") if grad_loss is not None else None
+        _cabi.check(self._lib.xpt_l2_regularizer(self.handle, wp, cnt, n, loss.data_ptr(),
+                                                 g.data_ptr() if g is not None else None, dp, self.stream()))
+        return loss, d_w
+
     def smoothness_loss(self, disp_ms, target_ms, grad_loss_batch=None, want_grad=False):
         disp_ms = self._level_list(disp_ms, "disp_ms", 1)
         target_ms = self._level_list(target_ms, "target_ms", 3)

@@ -5,8 +5,6 @@ import numpy as np
 
 from . import losses as lm
 
-_OUTSIDE = ["cmbL1", "cmbL1_R", "cmbSSIM", "cmbSSIM_R", "flowL2", "flowL2_R", "flow_reg"]   # need FlowNet outputs
-
 
 def loss_factory(dataset_cfg, loss_weights, scale_weights, stereo=False, weights_to_regularize=None, batch_size=1):
     """reference loss_factory.py:6-52.  `stereo` / `batch_size` are explicit here: the reference
@@ -30,9 +28,14 @@ def loss_factory(dataset_cfg, loss_weights, scale_weights, stereo=False, weights
         "stereoL1": lm.StereoDepthLoss("L1", scale_weights),
         "stereoSSIM": lm.StereoDepthLoss("SSIM", scale_weights),
         "stereoPose": lm.StereoPoseLoss(),
+        "cmbL1": lm.CombinedLossMultiScale("L1", scale_weights),
+        "cmbL1_R": lm.CombinedLossMultiScale("L1", scale_weights, key_suffix="_R"),
+        "cmbSSIM": lm.CombinedLossMultiScale("SSIM", scale_weights),
+        "cmbSSIM_R": lm.CombinedLossMultiScale("SSIM", scale_weights, key_suffix="_R"),
+        "flowL2": lm.FlowWarpLossMultiScale("L2", scale_weights),
+        "flowL2_R": lm.FlowWarpLossMultiScale("L2", scale_weights, key_suffix="_R"),
+        "flow_reg": lm.L2Regularizer(weights_to_regularize),
     }
-    for name in _OUTSIDE:
-        loss_pool[name] = lm._OutsideHotPath(name)
     losses, weights = dict(), dict()
     for name, weight in loss_weights.items():
         if weight == 0.:

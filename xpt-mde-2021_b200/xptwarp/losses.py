@@ -10,8 +10,9 @@ import torch
 from . import _cabi
 from .convert_pose import pose_matr2rvec_batch
 from .engine import WrongInputException, as_torch, get_plan, infer_scales, require_cuda_f32
+from .flow_warping import FlowWarpMultiScale, infer_flow_scales
 from .synthesize import SynthesizeMultiScale
-from .util_funcs import multi_scale_like_depth
+from .util_funcs import multi_scale_like_depth, multi_scale_like_flow
 
 # losses the fused tile kernel evaluates (one launch per group): the temporal set of each eye, the two stereo
 # syntheses of StereoDepthLoss; StereoPoseLoss is a tiny kernel of its own
@@ -118,6 +119,39 @@ class _PhotoMinFn(torch.autograd.Function):
         return (None, None, None, None, None, *d_synth, *(d_stereo if ctx.have_stereo else ()))
 
 
+class _PhotoCmbFn(torch.autograd.Function):
+    """CombinedLossMultiScale: static term where it beats the flow term (xpt_photometric_cmb_loss).  The flow-warped
+    view only enters through a comparison, so it receives no gradient (as in the reference's graph)."""
+
+    @staticmethod
+    def forward(ctx, plan, method, target, warped, *synth_ms):
+        loss, _, _ = plan.photometric_cmb_loss(method, synth_ms, warped, target)
+        ctx.plan, ctx.method = plan, method
+        ctx.save_for_backward(target, warped, *synth_ms)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        target, warped, *synth_ms = ctx.saved_tensors
+        _, d_synth, _ = ctx.plan.photometric_cmb_loss(ctx.method, synth_ms, warped, target,
+                                                      grad_loss_batch=g.reshape(-1).contiguous(), want_grad=True)
+        return (None, None, None, None, *d_synth)
+
+
+class _L2RegFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan, *weights):
+        loss, _ = plan.l2_regularizer(weights)
+        ctx.plan = plan
+        ctx.save_for_backward(*weights)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        _, d_w = ctx.plan.l2_regularizer(ctx.saved_tensors, grad_loss=g.reshape(1).contiguous(), want_grad=True)
+        return (None, *d_w)
+
+
 class _SmoothFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, plan, S, *ts):
@@ -195,6 +229,53 @@ class MoALossMultiScale(MonoDepth2LossMultiScale):
         return self._call(augm_data, "stereo_synth_ms")
 
 
+class CombinedLossMultiScale(PhotometricLoss):
+    """reference losses.py:235-279: the static (depth + pose) photometric term of every scale, kept only where it
+    is smaller than the optical-flow term of warped_target_ms[0]; both compared at the original resolution."""
+
+    def __call__(self, features, predictions, augm_data):
+        synth_ms = [as_torch(t) for t in augm_data["synth_target_ms" + self.key_suffix]]
+        warped = as_torch(augm_data["warped_target_ms" + self.key_suffix][0])
+        target = as_torch(augm_data["target" + self.key_suffix])
+        require_cuda_f32(synth_target_ms=synth_ms, warped_target_ms=warped, target=target)
+        B, N, H, W = synth_ms[0].shape[0], synth_ms[0].shape[1], target.shape[1], target.shape[2]
+        scales = [H // s.shape[2] for s in synth_ms]
+        plan = get_plan(target.device.index or 0, B, N, H, W, scales, _scale_weights_list(self.scale_weights))
+        return _PhotoCmbFn.apply(plan, self._METHODS[self.method], target, warped.detach(), *synth_ms)
+
+
+class FlowWarpLossMultiScale(PhotometricLoss):
+    """reference losses.py:497-519: photometric term ("L2" in the pool) between every flow-warped view and the
+    target resized like the flow, mean over sources, weighted sum over the flow scales."""
+
+    def __call__(self, features, predictions, augm_data):
+        flow_target_ms = [as_torch(t) for t in augm_data["flow_target_ms" + self.key_suffix]]
+        warped_ms = [as_torch(t) for t in augm_data["warped_target_ms" + self.key_suffix]]
+        require_cuda_f32(warped_target_ms=warped_ms, flow_target_ms=flow_target_ms)
+        B, N = warped_ms[0].shape[:2]
+        # the plan's "full resolution" is the first flow level: only the level sizes matter to the loss kernel
+        H, W = warped_ms[0].shape[2], warped_ms[0].shape[3]
+        scales = [H // t.shape[2] for t in warped_ms]
+        plan = get_plan(warped_ms[0].device.index or 0, B, N, H, W, scales, _scale_weights_list(self.scale_weights))
+        return _PhotoFn.apply(plan, self._METHODS[self.method], plan.S, *warped_ms, *flow_target_ms)
+
+
+class L2Regularizer(LossBase):
+    """reference losses.py:522-534 ("flow_reg"): sum of tf.nn.l2_loss over the given weights, tiled to [batch]."""
+
+    def __init__(self, weights_to_regularize):
+        self.weights = weights_to_regularize
+
+    def __call__(self, features, predictions, augm_data):
+        if not self.weights:
+            raise WrongInputException("flow_reg needs weights_to_regularize (loss_factory(..., weights_to_regularize=...))")
+        ws = [as_torch(w) for w in self.weights]
+        require_cuda_f32(weights_to_regularize=ws)
+        batch = as_torch(features["image5d"]).shape[0]
+        plan = get_plan(ws[0].device.index or 0, 1, 1, 8, 8, [1])
+        return _L2RegFn.apply(plan, *ws).expand(batch)
+
+
 class SmoothenessLossMultiScale(LossBase):
     """reference losses.py:386-440."""
 
@@ -235,15 +316,6 @@ class StereoPoseLoss(LossBase):
         lr, rl = as_torch(predictions["pose_LR"]), as_torch(predictions["pose_RL"])
         require_cuda_f32(stereo_T_LR=T, pose_LR=lr, pose_RL=rl)
         return _StereoPoseFn.apply(T, lr, rl)
-
-
-class _OutsideHotPath(LossBase):
-    def __init__(self, name):
-        self.name = name
-
-    def __call__(self, features, predictions, augm_data):
-        raise WrongInputException(f"loss {self.name!r} is outside the B200 hot path of this build "
-                                  "(SURVEY.md section 8f lists it as a next row)")
 
 
 class TotalLoss:
@@ -386,5 +458,8 @@ class TotalLoss:
             augm_data["synth_target_ms" + suffix] = SynthesizeMultiScale()(source_image, intrinsic, pred_depth_ms,
                                                                            predictions["pose" + suffix])
         if "flow_ms" + suffix in predictions:
-            raise WrongInputException("flow_ms: FlowWarpMultiScale is outside the B200 hot path of this build")
+            pred_flow_ms = predictions["flow_ms" + suffix]
+            # flows have lower resolution than depths, so "target_ms" is not appropriate for flows (losses.py:97)
+            augm_data["flow_target_ms" + suffix] = multi_scale_like_flow(target_image, pred_flow_ms)
+            augm_data["warped_target_ms" + suffix] = FlowWarpMultiScale()(source_image, pred_flow_ms)
         return augm_data

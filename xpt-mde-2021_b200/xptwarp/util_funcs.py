@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import torch
 
-from .engine import as_torch, get_plan, require_cuda_f32, infer_scales
+from .engine import WrongInputException, as_torch, get_plan, require_cuda_f32, infer_scales
 
 
 def multi_scale_like_depth(image, depth_ms):
@@ -15,6 +15,22 @@ def multi_scale_like_depth(image, depth_ms):
     B, H, W, _ = image.shape
     plan = get_plan(image.device.index or 0, B, 1, H, W, infer_scales(H, depth_ms))
     # the pyramid kernel wants a source tensor too: pass the target as a 1-frame source view
+    return plan.build_pyramids(image.unsqueeze(1), image)
+
+
+def multi_scale_like_flow(image, flow_ms):
+    """reference utils/util_funcs.py:178-190: the target resized to each flow level's size.
+    image [B,H,W,3], flow_ms list of [B,N,H_s,W_s,2] -> list of [B,H_s,W_s,3]."""
+    image = as_torch(image)
+    flow_ms = [as_torch(f) for f in flow_ms]
+    require_cuda_f32(image=image)
+    B, H, W, _ = image.shape
+    scales = []
+    for f in flow_ms:
+        if f.shape[2] <= 0 or H % f.shape[2]:
+            raise WrongInputException(f"flow height {f.shape[2]} does not divide the image height {H}")
+        scales.append(H // f.shape[2])
+    plan = get_plan(image.device.index or 0, B, 1, H, W, scales)
     return plan.build_pyramids(image.unsqueeze(1), image)
 
 
