@@ -41,7 +41,14 @@ constexpr int kFRegion = kFRH * kFP;           // 1156 floats per channel
 constexpr int kFStats = kFSH * kFP;            // 1020
 constexpr int kFCP = 64;                       // pitch of the centre arrays
 constexpr int kFCentre = kFCH * kFCP;          // 832
-constexpr int kFYIters = (kFRegion + kFThreads - 1) / kFThreads;   // 3
+constexpr int kFYIters = (kFRegion + kFThreads - 1) / kFThreads;   // 3 (tile load)
+// warp phase: every thread takes two region samples (1024); the remaining 132 -- the last two halo rows, never
+// centre samples -- are computed ONE SOURCE AHEAD by the three warps that idle in the adjoint phase (13..15),
+// so the phase is two balanced iterations.
+constexpr int kFYMain = 2 * kFThreads;         // 1024
+constexpr int kFYTail = kFRegion - kFYMain;    // 132
+constexpr int kFTailThreads = kFThreads - kFCH * 32;   // 96
+static_assert(kFYTail <= 2 * kFTailThreads && kFYMain >= (kFCH + 2) * kFP, "tail samples must be halo samples of warps 13..15");
 constexpr int kFRedSrc = 4;                    // sources whose pose partials are buffered before the cross-warp sum
 constexpr int kFRedFloats = kFRedSrc * kFCH * 16;                  // 832 (>= 48 floats of loss scratch)
 
@@ -161,6 +168,31 @@ __device__ __forceinline__ float2 hsum3(float2 a, float2 b) {
   return make_float2(a.x + m, m + b.y);
 }
 
+// value of one warped region sample (no Jacobian): the same operation order as the main warp phase
+__device__ __forceinline__ void halo_sample(const float* __restrict__ gk, const float* __restrict__ gt,
+                                            const float4* __restrict__ img4, float D, float r0, float r1, int W, int H,
+                                            float yv[3]) {
+  const float X0 = r0 * D, X1 = r1 * D, X2 = D;
+  const float Y0 = gt[0] * X0 + gt[1] * X1 + gt[2] * X2 + gt[9];
+  const float Y1 = gt[3] * X0 + gt[4] * X1 + gt[5] * X2 + gt[10];
+  const float Y2 = gt[6] * X0 + gt[7] * X1 + gt[8] * X2 + gt[11];
+  const float p0 = gk[0] * Y0 + gk[1] * Y1 + gk[2] * Y2;
+  const float p1 = gk[3] * Y0 + gk[4] * Y1 + gk[5] * Y2;
+  const float den = Y2 + 1e-10f;
+  float pu, pv, inv_den;
+  div_pair(p0, p1, den, pu, pv, inv_den);
+  const Taps tp = make_taps(pu, pv, D, W, H);
+  yv[0] = yv[1] = yv[2] = 0.f;
+  if (tp.valid) {
+    const float4* tp0 = img4 + (tp.iv * W + tp.iu);
+    const float4 t0 = __ldg(tp0), t2 = __ldg(tp0 + 1), t1 = __ldg(tp0 + W), t3 = __ldg(tp0 + W + 1);
+    const float w0 = tp.w_uf * tp.w_vf, w1 = tp.w_uf * tp.w_vc, w2 = tp.w_uc * tp.w_vf, w3 = tp.w_uc * tp.w_vc;
+    yv[0] = ((t0.x * w0 + t1.x * w1) + t2.x * w2) + t3.x * w3;
+    yv[1] = ((t0.y * w0 + t1.y * w1) + t2.y * w2) + t3.y * w3;
+    yv[2] = ((t0.z * w0 + t1.z * w1) + t2.z * w2) + t3.z * w3;
+  }
+}
+
 // GRAD: backward in the same launch.  OUT: synth_ms / mask_ms are written.  DSRC: dL/dsource scatter.
 // DERIVE: the disparity of the smoothness term is safe_reciprocal_number(depth) formed in the kernel.
 template <bool GRAD, bool OUT, bool DSRC, bool DERIVE>
@@ -245,6 +277,27 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
   }
 
   float lsum_l1 = 0.f, lsum_ssim = 0.f, lsum_sm = 0.f;
+
+  // the 132 tail samples of the region (see kFYTail) for source n, written straight into the warped tile: region
+  // rows 15..16 are read by the statistics phase only, so warps 13..15 may fill them for source n+1 while the
+  // other warps run the adjoint phase of source n
+  const bool tail_warp = wid >= kFCH;
+  const int tj = tid - kFCH * 32;
+  auto tail_compute = [&](int n) {
+    const float* const gtn = c_geo + a.geo_t_off + (bl * a.N + n) * kGeoT;
+    const float4* const imgn = a.src4[l] + (size_t)(b * a.N + n) * P;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int i = kFYMain + tj + k * kFTailThreads;
+      if (k == 0 || tj < kFYTail - kFTailThreads) {
+        float yv[3];
+        halo_sample(gk, gtn, imgn, sD[i], sR0[i], sR1[i], W, H, yv);
+        sy[i] = yv[0]; sy[kFRegion + i] = yv[1]; sy[2 * kFRegion + i] = yv[2];
+      }
+    }
+  };
+  if (GRAD && tail_warp && !(XPT_EXP & 2)) tail_compute(0);      // overlaps with the smoothness rows of warps 0..12
+
 
   // ---- smoothness on the centre strip (losses.py:409-440) ------------------------------------
   // a.disp[l] == NULL: the disparity is safe_reciprocal_number(depth) (utils/util_funcs.py:157-160, what
@@ -359,10 +412,12 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
     const float4* const img4 = a.src4[l] + (size_t)(b * a.N + n) * P;
 
     // ---- phase Y: inverse warp of the region into shared memory ---------------------------------
+    // GRAD: two balanced iterations, the tail comes from warps 13..15 (above / adjoint phase); forward only: no idle
+    // phase to hide the tail in, so a third, partly filled iteration takes it
 #pragma unroll
-    for (int it = 0; it < kFYIters; ++it) {
+    for (int it = 0; it < (GRAD ? kFYMain / kFThreads : kFYIters); ++it) {
       const int i = tid + it * kFThreads;
-      if (i < kFRegion && !(XPT_EXP & 2)) {
+      if ((GRAD || i < kFRegion) && !(XPT_EXP & 2)) {
         const int ry = i / kFP, rx = i - ry * kFP;
         const bool centre = (unsigned)(ry - 2) < (unsigned)kFCH && (unsigned)(rx - 2) < (unsigned)kFCW;
         float yv[3] = {0.f, 0.f, 0.f};
@@ -492,6 +547,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
     // ---- phase G: dL/dS on the centre strip, pushed through the bilinear + projection adjoint ------
     if (GRAD) {
       XPT_SYNC();
+      if (tail_warp && n + 1 < a.N && !(XPT_EXP & 2)) tail_compute(n + 1);   // warps 13..15 have no adjoint rows
       if (g_active && !(XPT_EXP & 8)) {     // warp-uniform: warps 0..12 own one centre row each
         float acc[16];
 #pragma unroll
