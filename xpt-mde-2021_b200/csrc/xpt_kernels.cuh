@@ -209,38 +209,11 @@ struct PyramidTiledArgs {
   GeoArgs geo;
 };
 
-__global__ void __launch_bounds__(kPyrThreads) k_pyramid_tiled(PyramidTiledArgs a) {
-  __shared__ __align__(16) float tile[kPyrTH][kPyrTW * 3];
-  const int nfr = a.N + 1;
-  if ((int)blockIdx.z == a.B * nfr) {           // geometry slice
-    if (a.with_geometry && blockIdx.y == 0) geometry_item(a.geo, blockIdx.x * blockDim.x + threadIdx.x);
-    return;
-  }
-  const int b = blockIdx.z / nfr, f = blockIdx.z % nfr;
-  const bool is_tgt = f == a.N;
-  if (is_tgt && a.target == nullptr) return;
-  const float* in = is_tgt ? a.target + b * a.tgt_bs : a.source + b * a.src_bs + f * a.src_fs;
-  const int x0 = blockIdx.x * kPyrTW, y0 = blockIdx.y * kPyrTH;
-  const int tw = min(kPyrTW, a.W - x0);         // multiple of 8
-  const float* in0 = in + ((long long)y0 * a.W + x0) * 3;
-  const long long rowst = (long long)a.W * 3;
-  if (tw == kPyrTW) {
-    constexpr int kRowF4 = kPyrTW * 3 / 4;      // 96 float4 per tile row: all index math is compile-time
-#pragma unroll
-    for (int k = 0; k < kPyrTH * kRowF4 / kPyrThreads; ++k) {
-      const int i = threadIdx.x + k * kPyrThreads;
-      const int r = i / kRowF4, c4 = i - r * kRowF4;
-      *reinterpret_cast<float4*>(&tile[r][c4 * 4]) = __ldg(reinterpret_cast<const float4*>(in0 + r * rowst) + c4);
-    }
-  } else {
-    const int row_f4 = tw * 3 / 4;
-    for (int i = threadIdx.x; i < kPyrTH * row_f4; i += kPyrThreads) {
-      const int r = i / row_f4, c4 = i - r * row_f4;
-      *reinterpret_cast<float4*>(&tile[r][c4 * 4]) = __ldg(reinterpret_cast<const float4*>(in0 + r * rowst) + c4);
-    }
-  }
-  __syncthreads();
-  const long long frame = is_tgt ? (long long)b : (long long)(b * a.N + f);
+// tile -> outputs.  FULL: the tile is kPyrTW wide, so every division below has a compile-time divisor.
+template <bool FULL>
+__device__ __forceinline__ void pyramid_emit(const PyramidTiledArgs& a, const float (*tile)[kPyrTW * 3], int tw_rt,
+                                             bool is_tgt, long long frame, int x0, int y0) {
+  const int tw = FULL ? kPyrTW : tw_rt;
   if (!is_tgt) {
     // RGBx texels (16 bytes) of every source level for the fused kernel's 128-bit gathers
 #pragma unroll
@@ -279,21 +252,56 @@ __global__ void __launch_bounds__(kPyrThreads) k_pyramid_tiled(PyramidTiledArgs 
     const int oh = kPyrTH >> lg;                 // output rows of this tile
     const int Hs = a.H >> lg, Ws = a.W >> lg;
     float* o = outp + (frame * Hs + (y0 >> lg)) * Ws * 3 + (x0 >> lg) * 3;
-    auto emit = [&](int oy, int rem) {           // rem = 3*ox + c inside the tile's output row
+    const int roww = (tw >> lg) * 3;             // FULL: 192 / 96 / 48
+    for (int e = threadIdx.x; e < oh * roww; e += kPyrThreads) {
+      const int oy = e / roww, rem = e - oy * roww;      // rem = 3*ox + c inside the tile's output row
       const int ox = rem / 3, c = rem - ox * 3;
       const int ry = oy * s + s / 2 - 1, rx = (ox * s + s / 2 - 1) * 3 + c;
       const float tl = tile[ry][rx], tr = tile[ry][rx + 3], bl = tile[ry + 1][rx], br = tile[ry + 1][rx + 3];
       const float top = tl + (tr - tl) * 0.5f;
       const float bot = bl + (br - bl) * 0.5f;
       o[(long long)oy * Ws * 3 + rem] = top + (bot - top) * 0.5f;
-    };
-    if (tw == kPyrTW) {
-      const int roww = (kPyrTW >> lg) * 3;       // 192 / 96 / 48: compile-time after unrolling
-      for (int e = threadIdx.x; e < oh * roww; e += kPyrThreads) emit(e / roww, e % roww);
-    } else {
-      const int roww = (tw >> lg) * 3;
-      for (int e = threadIdx.x; e < oh * roww; e += kPyrThreads) emit(e / roww, e % roww);
     }
+  }
+}
+
+#ifndef XPT_PYR_MINB
+#define XPT_PYR_MINB 6
+#endif
+__global__ void __launch_bounds__(kPyrThreads, XPT_PYR_MINB) k_pyramid_tiled(const __grid_constant__ PyramidTiledArgs a) {
+  __shared__ __align__(16) float tile[kPyrTH][kPyrTW * 3];
+  const int nfr = a.N + 1;
+  if ((int)blockIdx.z == a.B * nfr) {           // geometry slice
+    if (a.with_geometry && blockIdx.y == 0) geometry_item(a.geo, blockIdx.x * blockDim.x + threadIdx.x);
+    return;
+  }
+  const int b = blockIdx.z / nfr, f = blockIdx.z % nfr;
+  const bool is_tgt = f == a.N;
+  if (is_tgt && a.target == nullptr) return;
+  const float* in = is_tgt ? a.target + b * a.tgt_bs : a.source + b * a.src_bs + f * a.src_fs;
+  const int x0 = blockIdx.x * kPyrTW, y0 = blockIdx.y * kPyrTH;
+  const int tw = min(kPyrTW, a.W - x0);         // multiple of 8
+  const float* in0 = in + ((long long)y0 * a.W + x0) * 3;
+  const long long rowst = (long long)a.W * 3;
+  const long long frame = is_tgt ? (long long)b : (long long)(b * a.N + f);
+  if (tw == kPyrTW) {
+    constexpr int kRowF4 = kPyrTW * 3 / 4;      // 96 float4 per tile row: all index math is compile-time
+#pragma unroll
+    for (int k = 0; k < kPyrTH * kRowF4 / kPyrThreads; ++k) {
+      const int i = threadIdx.x + k * kPyrThreads;
+      const int r = i / kRowF4, c4 = i - r * kRowF4;
+      *reinterpret_cast<float4*>(&tile[r][c4 * 4]) = __ldg(reinterpret_cast<const float4*>(in0 + r * rowst) + c4);
+    }
+    __syncthreads();
+    pyramid_emit<true>(a, tile, tw, is_tgt, frame, x0, y0);
+  } else {
+    const int row_f4 = tw * 3 / 4;
+    for (int i = threadIdx.x; i < kPyrTH * row_f4; i += kPyrThreads) {
+      const int r = i / row_f4, c4 = i - r * row_f4;
+      *reinterpret_cast<float4*>(&tile[r][c4 * 4]) = __ldg(reinterpret_cast<const float4*>(in0 + r * rowst) + c4);
+    }
+    __syncthreads();
+    pyramid_emit<false>(a, tile, tw, is_tgt, frame, x0, y0);
   }
 }
 
