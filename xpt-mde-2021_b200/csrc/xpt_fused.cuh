@@ -147,8 +147,7 @@ struct FusedArgs {
   float* mask_out[kMaxScales];
   float* d_depth[kMaxScales];
   float* d_disp[kMaxScales];
-  float* d_src[kMaxScales];
-  long long d_src_bs[kMaxScales], d_src_fs[kMaxScales];
+  float4* d_src4[kMaxScales];          // DSRC: RGBx gradient texels of every source level [B,N,h,w], zeroed by the host
 };
 
 // Perspective divide of both coordinates with ONE reciprocal: r = 1/den refined once, then each
@@ -160,6 +159,11 @@ __device__ __forceinline__ void div_pair(float p0, float p1, float den, float& u
   const float q0 = p0 * r, q1 = p1 * r;
   u = fmaf(fmaf(-den, q0, p0), r, q0);
   v = fmaf(fmaf(-den, q1, p1), r, q1);
+}
+
+// 16-byte vector reduction into an RGBx gradient texel (sm_90+: red.global.add.v4.f32)
+__device__ __forceinline__ void red_add_rgbx(float4* p, float x, float y, float z) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(0.f) : "memory");
 }
 
 // horizontal 3-sums of a 4-column vertical sum (a.x a.y b.x b.y) for the strip's two pixels
@@ -617,23 +621,19 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
           const float gX1 = gt[1] * gY0 + gt[4] * gY1 + gt[7] * gY2;
           const float gX2 = gt[2] * gY0 + gt[5] * gY1 + gt[8] * gY2;
           gD[o] += gX0 * r0s[o] + gX1 * r1s[o] + gX2;
-          if (DSRC && a.d_src[l]) {
-            // dL/dsource: re-derive the taps from the cached coordinates (bit-identical to the forward)
+          if (DSRC && a.d_src4[l]) {
+            // dL/dsource: re-derive the taps from the cached coordinates (bit-identical to the forward) and add the
+            // four weighted texels with ONE 16-byte vector reduction each (REDG.E.ADD.F32x4) into the RGBx gradient level
             const float Us = o ? U2.y : U2.x, Vs = o ? V2.y : V2.x, inv = o ? I2v.y : I2v.x;
             const Taps tp = make_taps(Us, Vs, Ds[o], W, H);
             if (tp.valid && inv != 0.f) {
-              float* dimg = a.d_src[l] + b * a.d_src_bs[l] + n * a.d_src_fs[l];
+              float4* p = a.d_src4[l] + (size_t)(b * a.N + n) * P + (tp.iv * W + tp.iu);
               const float w0 = tp.w_uf * tp.w_vf, w1 = tp.w_uf * tp.w_vc, w2 = tp.w_uc * tp.w_vf, w3 = tp.w_uc * tp.w_vc;
-              float* p = dimg + ((long long)tp.iv * W + tp.iu) * 3;
-              float* q = p + (long long)W * 3;
               const float gs[3] = {o ? g[0].y : g[0].x, o ? g[1].y : g[1].x, o ? g[2].y : g[2].x};
-#pragma unroll
-              for (int c = 0; c < 3; ++c) {
-                atomicAdd(p + c, w0 * gs[c]);
-                atomicAdd(p + 3 + c, w2 * gs[c]);
-                atomicAdd(q + c, w1 * gs[c]);
-                atomicAdd(q + 3 + c, w3 * gs[c]);
-              }
+              red_add_rgbx(p, w0 * gs[0], w0 * gs[1], w0 * gs[2]);
+              red_add_rgbx(p + 1, w2 * gs[0], w2 * gs[1], w2 * gs[2]);
+              red_add_rgbx(p + W, w1 * gs[0], w1 * gs[1], w1 * gs[2]);
+              red_add_rgbx(p + W + 1, w3 * gs[0], w3 * gs[1], w3 * gs[2]);
             }
           }
         }

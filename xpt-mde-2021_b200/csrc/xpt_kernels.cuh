@@ -344,6 +344,47 @@ __global__ void k_pyramid_adjoint(PyramidAdjArgs a) {
   o[0] += acc[0]; o[1] += acc[1]; o[2] += acc[2];
 }
 
+// dL/dsource of the fused path: the kernel scatters into RGBx gradient levels (one 16-byte reduction per tap);
+// this pass folds them -- level 0 plus the adjoint of the source pyramid for s > 1 (each level pixel spreads 1/4 to
+// its centre 2x2, 1 to the centre pixel for odd s) -- into the dense 3-channel d_source, which it WRITES (no memset
+// and no read-modify-write of d_source).  One thread per full-resolution pixel of one frame.
+struct DsourceFinishArgs {
+  float* d_source;             // [B*N,H,W,3] dense
+  int BN, H, W, S;
+  int s[kMaxScales];
+  const float4* d_level4[kMaxScales];   // [B*N,h,w] RGBx
+};
+
+__global__ void __launch_bounds__(256) k_dsource_finish(DsourceFinishArgs a) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)a.BN * a.H * a.W;
+  if (idx >= total) return;
+  const int x = (int)(idx % a.W);
+  const long long r = idx / a.W;
+  const int y = (int)(r % a.H);
+  const int f = (int)(r / a.H);
+  float acc[3] = {0.f, 0.f, 0.f};
+  for (int l = 0; l < a.S; ++l) {
+    const int s = a.s[l];
+    if (a.d_level4[l] == nullptr) continue;
+    const int h = a.H / s, w = a.W / s;
+    const int ys = y / s, xs = x / s, ry = y % s, rx = x % s;
+    float wt = 1.f;
+    if (s > 1) {
+      if (s & 1) {
+        if (ry != s / 2 || rx != s / 2) continue;
+      } else {
+        if ((ry != s / 2 - 1 && ry != s / 2) || (rx != s / 2 - 1 && rx != s / 2)) continue;
+        wt = 0.25f;
+      }
+    }
+    const float4 g = __ldg(a.d_level4[l] + ((long long)f * h + ys) * w + xs);
+    acc[0] += wt * g.x; acc[1] += wt * g.y; acc[2] += wt * g.z;
+  }
+  float* o = a.d_source + idx * 3;
+  o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2];
+}
+
 // ---------------------------------------------------------------------------
 // inverse warp of one target pixel into one source frame.
 // Order of operations follows the reference:

@@ -79,6 +79,7 @@ struct xpt_ctx {
   float* synth_scr[kMaxScales];
   float* gsynth_scr[kMaxScales];
   float* dsrc_lvl[kMaxScales];  // s > 1
+  float* dsrc4_lvl[kMaxScales]; // RGBx gradient levels of the fused path (all levels)
   float* tgt0_copy;             // unused unless a level-0 copy is wanted without a user buffer
   float* min_part;              // [B][S * full-res tiles] partial sums of xpt_photometric_min_loss
   float* l2_part;               // block partials (doubles) of xpt_l2_regularizer
@@ -340,6 +341,34 @@ int finish_dsource(xpt_ctx* ctx, float* d_source, cudaStream_t st) {
   return XPT_OK;
 }
 
+// fused path: RGBx gradient levels (zeroed), folded into the dense d_source by k_dsource_finish
+int prepare_dsource4(xpt_ctx* ctx, float4* d_src4[], cudaStream_t st) {
+  for (int l = 0; l < ctx->S; ++l) {
+    const size_t n = (size_t)ctx->B * ctx->N * lvl_pix(ctx, l) * 4;
+    XPT_TRY(dev_alloc(ctx, &ctx->dsrc4_lvl[l], n));
+    XPT_CUDA(cudaMemsetAsync(ctx->dsrc4_lvl[l], 0, n * sizeof(float), st));
+    d_src4[l] = reinterpret_cast<float4*>(ctx->dsrc4_lvl[l]);
+  }
+  return XPT_OK;
+}
+
+int finish_dsource4(xpt_ctx* ctx, float* d_source, cudaStream_t st) {
+  DsourceFinishArgs a;
+  memset(&a, 0, sizeof(a));
+  a.d_source = d_source; a.BN = ctx->B * ctx->N; a.H = ctx->H; a.W = ctx->W; a.S = ctx->S;
+  bool have0 = false;
+  for (int l = 0; l < ctx->S; ++l) {
+    a.s[l] = ctx->s[l];
+    a.d_level4[l] = reinterpret_cast<const float4*>(ctx->dsrc4_lvl[l]);
+    have0 = have0 || ctx->s[l] == 1;
+  }
+  (void)have0;       // without a level-0 scale the pass still writes every element (zeros where no level touches it)
+  const long long total = (long long)a.BN * a.H * a.W;
+  k_dsource_finish<<<cdiv(total, 256), 256, 0, st>>>(a);
+  XPT_LAUNCH_CHECK("k_dsource_finish");
+  return XPT_OK;
+}
+
 int launch_warp_bwd(xpt_ctx* ctx, const LevelTable& lt, const float* const depth_ms[], const float* const gsynth[],
                     float* const d_depth_ms[], float* d_source, const float* pose, float* d_pose, float scale,
                     cudaStream_t st) {
@@ -571,7 +600,7 @@ void xpt_destroy(xpt_ctx* ctx) {
   F(ctx->st_frames); F(ctx->st_K); F(ctx->st_pose); F(ctx->st_losses); F(ctx->st_loss_batch); F(ctx->st_dpose);
   F(ctx->st_dsource);
   for (int l = 0; l < kMaxScales; ++l) {
-    F(ctx->src_pyr[l]); F(ctx->src4_pyr[l]); F(ctx->tgt_pyr[l]); F(ctx->synth_scr[l]); F(ctx->gsynth_scr[l]); F(ctx->dsrc_lvl[l]);
+    F(ctx->src_pyr[l]); F(ctx->src4_pyr[l]); F(ctx->tgt_pyr[l]); F(ctx->synth_scr[l]); F(ctx->gsynth_scr[l]); F(ctx->dsrc_lvl[l]); F(ctx->dsrc4_lvl[l]);
     F(ctx->st_depth[l]); F(ctx->st_disp[l]); F(ctx->st_ddepth[l]); F(ctx->st_ddisp[l]);
     F(ctx->st_synth[l]); F(ctx->st_mask[l]); F(ctx->st_target[l]);
   }
@@ -924,8 +953,9 @@ static int total_loss_impl(xpt_ctx* ctx, const xpt_frames* frames, const float* 
   a.gcoef_l1 = c.w_l1 * inv_gb * gs;
   a.gcoef_ssim = c.w_ssim * inv_gb * gs;
   a.gcoef_smooth = c.w_smooth * inv_gb * gs;
+  const bool fused_path = !(c.flags & XPT_FLAG_UNFUSED);
   float* d_src[kMaxScales]; long long dbs[kMaxScales], dfs[kMaxScales];
-  XPT_TRY(prepare_dsource(ctx, grad ? out->d_source : nullptr, d_src, dbs, dfs, st));
+  XPT_TRY(prepare_dsource(ctx, (grad && !fused_path) ? out->d_source : nullptr, d_src, dbs, dfs, st));
   for (int l = 0; l < ctx->S; ++l) {
     a.depth[l] = depth_ms[l];
     a.disp[l] = (do_smooth && !derive_disp) ? disp_ms[l] : nullptr;
@@ -953,8 +983,9 @@ static int total_loss_impl(xpt_ctx* ctx, const xpt_frames* frames, const float* 
       fa.norm_photo[l] = a.norm_photo[l]; fa.norm_sm_x[l] = a.norm_sm_x[l]; fa.norm_sm_y[l] = a.norm_sm_y[l];
       fa.synth_out[l] = a.synth_out[l]; fa.mask_out[l] = a.mask_out[l];
       fa.d_depth[l] = a.d_depth[l]; fa.d_disp[l] = a.d_disp[l];
-      fa.d_src[l] = a.d_src[l]; fa.d_src_bs[l] = a.d_src_bs[l]; fa.d_src_fs[l] = a.d_src_fs[l];
     }
+    const bool dsrc = grad && out->d_source;
+    if (dsrc) XPT_TRY(prepare_dsource4(ctx, fa.d_src4, st));
     const int ftiles = ctx->ffirst_tile[ctx->S];
     fa.first_tile[ctx->S] = ftiles;
     fa.tiles_per_b = ftiles;
@@ -965,7 +996,6 @@ static int total_loss_impl(xpt_ctx* ctx, const xpt_frames* frames, const float* 
     fa.loss_part = ctx->loss_part; fa.slots_per_b = ctx->slots_per_b; fa.pose_part = ctx->pose_part;
     bool want_out = false;
     for (int l = 0; l < ctx->S; ++l) want_out = want_out || out->synth_ms[l] || out->mask_ms[l];
-    const bool dsrc = grad && out->d_source;
     // template dispatch: (GRAD, OUT, DSRC, DERIVE)
     const int sel = (grad ? 8 : 0) | (want_out ? 4 : 0) | (dsrc ? 2 : 0) | (derive_disp ? 1 : 0);
     switch (sel) {
@@ -992,6 +1022,7 @@ static int total_loss_impl(xpt_ctx* ctx, const xpt_frames* frames, const float* 
     ea.loss_sum_b = ctx->loss_sum_b; ea.ticket = ctx->ticket;
     k_epilogue<<<(ea.d_pose ? ctx->B * ctx->N : 0) + ctx->B, 128, 0, st>>>(ea);
     XPT_LAUNCH_CHECK("k_epilogue");
+    if (dsrc) XPT_TRY(finish_dsource4(ctx, out->d_source, st));
   } else {
     // ---- unfused path (flags bit 0): one kernel per reference stage, tensors through HBM
     float* synth[kMaxScales]; float* gsyn[kMaxScales];
@@ -1044,7 +1075,7 @@ static int total_loss_impl(xpt_ctx* ctx, const xpt_frames* frames, const float* 
       }
     }
   }
-  if (grad) XPT_TRY(finish_dsource(ctx, out->d_source, st));
+  if (grad && !fused_path) XPT_TRY(finish_dsource(ctx, out->d_source, st));
   return XPT_OK;
 }
 
