@@ -356,19 +356,22 @@ struct DsourceFinishArgs {
 };
 
 __global__ void __launch_bounds__(256) k_dsource_finish(DsourceFinishArgs a) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)a.BN * a.H * a.W;
-  if (idx >= total) return;
-  const int x = (int)(idx % a.W);
-  const long long r = idx / a.W;
-  const int y = (int)(r % a.H);
-  const int f = (int)(r / a.H);
+  // grid = (ceil(W / 256), H, B*N): no integer division by runtime image sizes
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= a.W) return;
+  const int y = blockIdx.y, f = blockIdx.z;
+  const long long idx = ((long long)f * a.H + y) * a.W + x;
   float acc[3] = {0.f, 0.f, 0.f};
   for (int l = 0; l < a.S; ++l) {
     const int s = a.s[l];
     if (a.d_level4[l] == nullptr) continue;
-    const int h = a.H / s, w = a.W / s;
-    const int ys = y / s, xs = x / s, ry = y % s, rx = x % s;
+    int h, w, ys, xs, ry, rx;
+    if ((s & (s - 1)) == 0) {                  // power of two (the usual 1, 2, 4, 8): shifts and masks
+      const int lg = 31 - __clz(s);
+      h = a.H >> lg; w = a.W >> lg; ys = y >> lg; xs = x >> lg; ry = y & (s - 1); rx = x & (s - 1);
+    } else {
+      h = a.H / s; w = a.W / s; ys = y / s; xs = x / s; ry = y % s; rx = x % s;
+    }
     float wt = 1.f;
     if (s > 1) {
       if (s & 1) {

@@ -363,8 +363,8 @@ int finish_dsource4(xpt_ctx* ctx, float* d_source, cudaStream_t st) {
     have0 = have0 || ctx->s[l] == 1;
   }
   (void)have0;       // without a level-0 scale the pass still writes every element (zeros where no level touches it)
-  const long long total = (long long)a.BN * a.H * a.W;
-  k_dsource_finish<<<cdiv(total, 256), 256, 0, st>>>(a);
+  if (a.H > 65535 || a.BN > 65535) return fail(XPT_BAD_SHAPE, "d_source: H or B*N exceeds the grid limit 65535");
+  k_dsource_finish<<<dim3(cdiv(a.W, 256), a.H, a.BN), 256, 0, st>>>(a);
   XPT_LAUNCH_CHECK("k_dsource_finish");
   return XPT_OK;
 }
