@@ -16,7 +16,7 @@ st = torch.cuda.Stream(); torch.cuda.set_stream(st)
 for name, (w1, ws, wm, grad, synth) in {
     "full fwd+bwd": (0.5, 0.5, 1.0, True, False), "forward only": (0.5, 0.5, 1.0, False, False),
     "L1 only fwd+bwd": (0.5, 0.0, 0.0, True, False), "SSIM only fwd+bwd": (0.0, 0.5, 0.0, True, False),
-    "smooth only fwd+bwd": (0.0, 0.0, 1.0, True, False), "full + synth/mask out": (0.5, 0.5, 1.0, True, True),
+    "smooth only fwd+bwd": (0.0, 0.0, 1.0, True, False), "L1+SSIM (no smooth) fwd+bwd": (0.5, 0.5, 0.0, True, False), "full + synth/mask out": (0.5, 0.5, 1.0, True, True),
     "full + dL/dsource": (0.5, 0.5, 1.0, True, "src"),
 }.items():
     plan = xptwarp.get_plan(0, B, 4, H, W, [1, 2, 4, 8], [1, 1, 1, 1], w1, ws, wm, B)

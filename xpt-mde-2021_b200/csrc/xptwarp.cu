@@ -414,14 +414,22 @@ void fill_photo_norms(const xpt_ctx* ctx, PhotoArgs& a) {
   }
 }
 
+// opt a kernel in to its dynamic shared-memory size once per DEVICE (the attribute is per context; `done` is the
+// call site's bit mask over device ordinals, so several ranks / devices in one process each get it)
+template <typename F>
+int ensure_dyn_smem(F* func, size_t bytes, int device, unsigned long long* done) {
+  const unsigned long long bit = 1ull << (device & 63);
+  if (__atomic_load_n(done, __ATOMIC_ACQUIRE) & bit) return XPT_OK;
+  XPT_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  __atomic_fetch_or(done, bit, __ATOMIC_RELEASE);
+  return XPT_OK;
+}
+
 template <bool FUSED, bool GRAD>
 int launch_photo(xpt_ctx* ctx, const PhotoArgs& a, cudaStream_t st) {
-  static bool attr_set = false;
+  static unsigned long long attr_done = 0;
   size_t smem = PhotoSmem<GRAD>::kBytes;
-  if (!attr_set) {
-    XPT_CUDA(cudaFuncSetAttribute(k_photo<FUSED, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  XPT_TRY(ensure_dyn_smem(k_photo<FUSED, GRAD>, smem, ctx->cfg.device, &attr_done));
   dim3 grid(a.tiles_per_b, ctx->B);
   k_photo<FUSED, GRAD><<<grid, kPhotoThreads, smem, st>>>(a);
   XPT_LAUNCH_CHECK(FUSED ? "k_photo<fused>" : "k_photo<tensor>");
@@ -430,12 +438,9 @@ int launch_photo(xpt_ctx* ctx, const PhotoArgs& a, cudaStream_t st) {
 
 template <bool GRAD, bool OUT, bool DSRC, bool DERIVE>
 int launch_fused(xpt_ctx* ctx, FusedArgs& a, cudaStream_t st) {
-  static bool attr_set = false;
+  static unsigned long long attr_done = 0;
   const size_t smem = FusedSmem<GRAD>::kBytes;
-  if (!attr_set) {
-    XPT_CUDA(cudaFuncSetAttribute(k_fused<GRAD, OUT, DSRC, DERIVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  XPT_TRY(ensure_dyn_smem(k_fused<GRAD, OUT, DSRC, DERIVE>, smem, ctx->cfg.device, &attr_done));
   // camera geometry goes to the constant bank (uniform registers in the kernel); 60 KB hold
   // kGeoConstFloats / (S*18 + N*12) snippets, larger batches are launched in chunks
   const int per_b = ctx->S * kGeoK + ctx->N * kGeoT;
@@ -782,14 +787,14 @@ static int min_loss_impl(xpt_ctx* ctx, int method, const float* const synth_ms[]
   }
   dim3 grid(ctx->S * a.tiles, ctx->B);
   if (d_synth_ms) {
-    static bool attr = false;
+    static unsigned long long attr_done = 0;
     const size_t smem = MinLossSmem<true>::kBytes;
-    if (!attr) { XPT_CUDA(cudaFuncSetAttribute(k_photo_min<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    XPT_TRY(ensure_dyn_smem(k_photo_min<true>, smem, ctx->cfg.device, &attr_done));
     k_photo_min<true><<<grid, kPhotoThreads, smem, st>>>(a);
   } else {
-    static bool attr = false;
+    static unsigned long long attr_done = 0;
     const size_t smem = MinLossSmem<false>::kBytes;
-    if (!attr) { XPT_CUDA(cudaFuncSetAttribute(k_photo_min<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    XPT_TRY(ensure_dyn_smem(k_photo_min<false>, smem, ctx->cfg.device, &attr_done));
     k_photo_min<false><<<grid, kPhotoThreads, smem, st>>>(a);
   }
   XPT_LAUNCH_CHECK("k_photo_min");

@@ -399,8 +399,9 @@ def get_plan(device_index, B, N, H, W, scales, scale_weights=None, w_l1=0.0, w_s
                  img_grad_factor)
         _PLANS[key] = p
         while len(_PLANS) > _MAX_PLANS:
-            _, old = _PLANS.popitem(last=False)
-            old.close()
+            # only drop the cache's reference: an autograd graph may still hold the plan for its backward;
+            # Plan.__del__ destroys the xpt_ctx when the last reference goes
+            _PLANS.popitem(last=False)
     else:
         _PLANS.move_to_end(key)
     return p
