@@ -667,3 +667,84 @@ def test_combined_loss_against_oracle_full_size(xw):
             ok, msg = grad_close(csy[s].grad.cpu().numpy(), res[torch.float32][1][s].numpy(), res[torch.float64][1][s].numpy(),
                                  GRAD_TOL, self_factor=2)
             assert ok, (method, s, msg)
+
+
+def _safe_disp(d):
+    """safe_reciprocal_number with value 0 (not the reference's inf * 0 = NaN) at depth <= 1e-5 or NaN"""
+    d = torch.nan_to_num(d, nan=0.0)
+    return torch.where(d > 1e-5, 1.0 / torch.where(d > 1e-5, d, torch.ones_like(d)), torch.zeros_like(d))
+
+
+def test_adversarial_geometry(xw):
+    """Cases the reference does not guard against: points BEHIND the camera (negative depth: no z > 0
+    test in cam2pixel, synthesize_base.py:161-178), skewed intrinsics, NaN depth, poses that throw half of the samples
+    out of the image -- masks bit-compared, images / losses / gradients at the usual tolerances."""
+    from oracle import xpt_oracle as orc
+    B, H, W, N = 2, 48, 80, 3
+    feats, preds = orc.make_inputs(B, H, W, N=N, seed=4242, adversarial=True)
+    K = feats["intrinsic"].clone()
+    K[:, 0, 1] = 0.7                                         # skew
+    feats["intrinsic"] = K
+    d0 = preds["depth_ms"][0]
+    d0[0, 5:9, 10:30, 0] = -3.0                              # behind the camera
+    d0[1, 20, 40, 0] = float("nan")
+    d0[1, 21:23, 41:44, 0] = 1e-12                           # den ~ t_z + 1e-10
+    preds["disp_ms"] = [_safe_disp(d) for d in preds["depth_ms"]]
+    src, K_, pose = feats["image5d"][:, :-1], feats["intrinsic"], preds["pose"]
+    ref_synth, ref_mask = orc.synthesize_multi_scale(src, K_, preds["depth_ms"], pose, return_mask=True)
+    got_synth, got_mask = xw.SynthesizeMultiScale()(src.cuda(), K_.cuda(), [d.cuda() for d in preds["depth_ms"]],
+                                                    pose.cuda(), return_mask=True)
+    plan = xw.get_plan(0, B, N, H, W, [1, 2, 4, 8], [1, 1, 1, 1], 0.5, 0.5, 1.0, B)
+    f, p = _to_cuda(feats, preds)
+    r = _run_total(plan, f, p, want_grad=True, want_synth=True, want_mask=True)
+    for s in range(4):
+        m_ref = ref_mask[s].numpy().reshape(-1)
+        for name, m in (("synthesize", got_mask[s]), ("fused", r["mask_ms"][s])):
+            m = m.cpu().numpy().reshape(-1)
+            # a sample whose floor(u) sits within one ulp of an integer may flip between fp32 implementations
+            assert (m != m_ref).sum() <= 2, (name, s, int((m != m_ref).sum()))
+        same = (got_mask[s].cpu() == ref_mask[s].reshape(got_mask[s].shape)).expand_as(ref_synth[s])
+        diff = (got_synth[s].cpu() - ref_synth[s]).abs()
+        assert float(diff[same].max()) < IMG_TOL, s
+        assert float((r["synth_ms"][s].cpu() - got_synth[s].cpu()).abs().max()) == 0.0, s     # fused == standalone kernel
+    # losses and gradients with the NaN pixel removed (NaN depth poisons the reference's own sums)
+    preds["depth_ms"][0][1, 20, 40, 0] = 0.0
+    preds["disp_ms"][0][1, 20, 40, 0] = 0.0
+    lw, sw = orc.LOSS_RIGID_T2, orc.SCALE_WEIGHT_T2
+    ref, ref64 = orc.loss_and_grads(feats, preds, lw, sw), None
+    f64 = {k: v.double() for k, v in feats.items()}
+    p64 = {"depth_ms": [d.double() for d in preds["depth_ms"]], "disp_ms": [d.double() for d in preds["disp_ms"]],
+           "pose": preds["pose"].double()}
+    ref64 = orc.loss_and_grads(f64, p64, lw, sw)
+    f, p = _to_cuda(feats, preds)
+    r = _run_total(_plan_for(xw, f, p, lw, sw, B), f, p, want_grad=True)
+    assert min(relerr(r["losses"].cpu().numpy()[0], ref64["total"].numpy()),
+               relerr(r["losses"].cpu().numpy()[0], ref["total"].numpy())) < LOSS_TOL
+    pose_tol = max(GRAD_TOL, 3 * relerr(ref["d_pose"].numpy(), ref64["d_pose"].numpy()))
+    assert relerr(r["d_pose"].cpu().numpy(), ref64["d_pose"].numpy()) < pose_tol
+    for s in range(4):
+        ok, msg = grad_close(r["d_depth_ms"][s].cpu().numpy(), ref["d_depth_ms"][s].numpy(), ref64["d_depth_ms"][s].numpy(),
+                             GRAD_TOL, self_factor=2)
+        assert ok, (s, msg)
+
+
+def test_odd_and_sparse_scale_sets(xw):
+    """Scale sets outside the 1/2/4/8 fast path: an odd factor (tf.image.resize then samples the centre pixel of each
+    3x3 block) and a sparse set (1, 4) -- generic pyramid kernel, fused and unfused, against the oracle."""
+    from oracle import xpt_oracle as orc
+    for H, W, scales in ((24, 48, (1, 3)), (32, 64, (1, 4)), (48, 96, (2, 6))):
+        feats, base = orc.make_inputs(2, H, W, N=2, n_scales=1, seed=H)
+        d0 = base["depth_ms"][0]
+        depth_ms = [d0[:, ::s, ::s, :].contiguous() * (1.0 + 0.01 * k) for k, s in enumerate(scales)]
+        preds = {"depth_ms": depth_ms, "disp_ms": [_safe_disp(d) for d in depth_ms], "pose": base["pose"]}
+        lw, sw = orc.LOSS_RIGID_T1, [1.0, 0.7]
+        ref = orc.loss_and_grads(feats, preds, lw, sw)
+        f, p = _to_cuda(feats, preds)
+        for flags in (0, 1):
+            plan = xw.get_plan(0, 2, 2, H, W, list(scales), sw, 0.5, 0.5, 1.0, 2, flags)
+            r = _run_total(plan, f, p, want_grad=True, want_synth=True)
+            assert relerr(r["losses"].cpu().numpy()[0], ref["total"].numpy()) < LOSS_TOL, (scales, flags)
+            for s in range(2):
+                assert float((r["synth_ms"][s].cpu() - ref["synth_ms"][s]).abs().max()) < IMG_TOL, (scales, flags, s)
+                assert relerr(r["d_depth_ms"][s].cpu().numpy(), ref["d_depth_ms"][s].numpy()) < 5 * GRAD_TOL, (scales, flags, s)
+            assert relerr(r["d_pose"].cpu().numpy(), ref["d_pose"].numpy()) < 5 * GRAD_TOL, (scales, flags)

@@ -408,7 +408,7 @@ void fill_photo_norms(const xpt_ctx* ctx, PhotoArgs& a) {
     double sw = ctx->cfg.scale_weights[l];
     a.norm_photo[l] = (float)(sw / ((double)ctx->N * hw * 3.0));
     // losses.py:401-402: each scale's smoothness divided by scale = orig_width / width
-    double scale = (double)ctx->W / (double)ctx->w[l];
+    double scale = (double)ctx->w[0] / (double)ctx->w[l];   // orig_width = width of target_ms[0] (the FIRST level, losses.py:399)
     a.norm_sm_x[l] = (float)(sw * 0.5 / ((double)ctx->h[l] * (ctx->w[l] - 1)) / scale);
     a.norm_sm_y[l] = (float)(sw * 0.5 / ((double)(ctx->h[l] - 1) * ctx->w[l]) / scale);
   }
