@@ -748,3 +748,56 @@ def test_odd_and_sparse_scale_sets(xw):
                 assert float((r["synth_ms"][s].cpu() - ref["synth_ms"][s]).abs().max()) < IMG_TOL, (scales, flags, s)
                 assert relerr(r["d_depth_ms"][s].cpu().numpy(), ref["d_depth_ms"][s].numpy()) < 5 * GRAD_TOL, (scales, flags, s)
             assert relerr(r["d_pose"].cpu().numpy(), ref["d_pose"].numpy()) < 5 * GRAD_TOL, (scales, flags)
+
+
+@pytest.mark.parametrize("B,H,W,N", [(2, 40, 72, 3), (1, 24, 104, 1), (3, 16, 32, 5)])
+@pytest.mark.parametrize("method", ["L1", "SSIM"])
+def test_min_and_combined_losses_on_ragged_tiles(xw, B, H, W, N, method):
+    """MonoDepth2 / MoA / Combined losses (full-resolution 32x16 tiles, on-the-fly up-sampling) at sizes that leave
+    partial tiles, 1..5 sources, with black (invalid) pixels in the syntheses -- loss and dL/dsynth vs the oracle."""
+    from oracle import xpt_oracle as orc
+    g = torch.Generator().manual_seed(H * 1000 + W + N)
+    U = lambda *shape: torch.rand(*shape, generator=g, dtype=torch.float64).float() * 2 - 1
+    target = U(B, H, W, 3)
+    synth, stereo = [], []
+    for s in (1, 2, 4, 8):
+        t = U(B, N, H // s, W // s, 3)
+        t[:, :, : max(1, H // s // 5), :, :] = 0                      # a black band (invalid warp): loss 0 there
+        t[:, 0, :, : max(1, W // s // 7), :] = 0
+        st = U(B, 1, H // s, W // s, 3)
+        st[:, :, -1, :, :] = 0
+        synth.append(t); stereo.append(st)
+    warped0 = U(B, N, H // 4, W // 4, 3)
+    sw = [0.4, 0.8, 1.2, 1.6]
+    cases = {
+        "md2": (lambda sy, st: orc.monodepth2_loss_multi_scale(method, sy, target.to(sy[0].dtype), sw), False,
+                lambda: xw.MonoDepth2LossMultiScale(method, np.array(sw))),
+        "moa": (lambda sy, st: orc.moa_loss_multi_scale(method, sy, st, target.to(sy[0].dtype), sw), True,
+                lambda: xw.MoALossMultiScale(method, np.array(sw))),
+        "cmb": (lambda sy, st: orc.combined_loss_multi_scale(method, sy, [warped0.to(sy[0].dtype)], target.to(sy[0].dtype), sw), False,
+                lambda: xw.CombinedLossMultiScale(method, np.array(sw))),
+    }
+    for name, (ofn, uses_stereo, mk) in cases.items():
+        res = {}
+        for dt in (torch.float32, torch.float64):
+            sy = [t.to(dt).clone().requires_grad_(True) for t in synth]
+            st = [t.to(dt).clone().requires_grad_(True) for t in stereo]
+            lb = ofn(sy, st)
+            lb.sum().backward()
+            res[dt] = (lb.detach().reshape(-1), [t.grad for t in sy], [t.grad for t in st] if uses_stereo else None)
+        csy = [t.cuda().requires_grad_(True) for t in synth]
+        cst = [t.cuda().requires_grad_(True) for t in stereo]
+        augm = {"synth_target_ms": csy, "stereo_synth_ms": cst, "warped_target_ms": [warped0.cuda()], "target": target.cuda()}
+        got = mk()(None, None, augm)
+        got.sum().backward()
+        torch.cuda.synchronize()
+        l64 = res[torch.float64][0].numpy()
+        assert relerr(got.detach().cpu().numpy().reshape(-1), l64) < max(2 * LOSS_TOL, 3 * relerr(res[torch.float32][0].numpy(), l64)), name
+        for s in range(4):
+            ok, msg = grad_close(csy[s].grad.cpu().numpy(), res[torch.float32][1][s].numpy(), res[torch.float64][1][s].numpy(),
+                                 GRAD_TOL, self_factor=2)
+            assert ok, (name, s, msg)
+            if uses_stereo:
+                ok, msg = grad_close(cst[s].grad.cpu().numpy(), res[torch.float32][2][s].numpy(), res[torch.float64][2][s].numpy(),
+                                     GRAD_TOL, self_factor=2)
+                assert ok, (name, "stereo", s, msg)
