@@ -801,3 +801,63 @@ def test_min_and_combined_losses_on_ragged_tiles(xw, B, H, W, N, method):
                 ok, msg = grad_close(cst[s].grad.cpu().numpy(), res[torch.float32][2][s].numpy(), res[torch.float64][2][s].numpy(),
                                      GRAD_TOL, self_factor=2)
                 assert ok, (name, "stereo", s, msg)
+
+
+@pytest.mark.parametrize("derive", [False, True], ids=["disp_given", "disp_from_depth"])
+def test_host_entry_point_all_outputs(xw, derive):
+    """xpt_total_loss_host with EVERY optional output (synth_ms, mask_ms, target_ms, loss_batch, d_source) and with
+    disp_ms == NULL (disparity derived from depth in the kernel): equals the device entry point on the same inputs."""
+    import ctypes as C
+    from xptwarp import _cabi
+    from oracle import xpt_oracle as orc
+    B, H, W, N = 5, 64, 128, 3
+    feats, preds = orc.make_inputs(B, H, W, N=N, seed=2718)
+    lw, sw = orc.LOSS_RIGID_T2, orc.SCALE_WEIGHT_T2
+    f, p = _to_cuda(feats, preds)
+    plan = _plan_for(xw, f, p, lw, sw, B)
+    img_d = f["image5d"]
+    r = plan.total_loss(img_d[:, :-1], img_d[:, -1], f["intrinsic"], p["depth_ms"], None if derive else p["disp_ms"], p["pose"],
+                        want_grad=True, want_synth=True, want_mask=True, want_target_ms=True, want_source_grad=True,
+                        want_loss_batch=True)
+    torch.cuda.synchronize()
+    pin = lambda t: t.contiguous().pin_memory()
+    img, K, pose = pin(feats["image5d"]), pin(feats["intrinsic"]), pin(preds["pose"])
+    depth_h, disp_h = [pin(d) for d in preds["depth_ms"]], [pin(d) for d in preds["disp_ms"]]
+    fr = _cabi.XptFrames()
+    fr.source, fr.source_batch_stride, fr.source_frame_stride = img.data_ptr(), img.stride(0), img.stride(1)
+    fr.target, fr.target_batch_stride = img.data_ptr() + N * img.stride(1) * 4, img.stride(0)
+    fr.intrinsic = K.data_ptr()
+    out = _cabi.XptLossOutputs()
+    Z = lambda *shape: pin(torch.full(shape, -7.0))
+    losses, loss_batch, d_pose, d_source = Z(4), Z(3, B), Z(B, N, 6), Z(B, N, H, W, 3)
+    hw = [(H >> s, W >> s) for s in range(4)]
+    synth = [Z(B, N, h, w, 3) for h, w in hw]
+    mask = [Z(B, N, h, w, 1) for h, w in hw]
+    tgt = [Z(B, h, w, 3) for h, w in hw]
+    d_depth = [Z(B, h, w, 1) for h, w in hw]
+    d_disp = [Z(B, h, w, 1) for h, w in hw]
+    out.losses, out.loss_batch, out.d_pose, out.d_source, out.grad_scale = (losses.data_ptr(), loss_batch.data_ptr(),
+                                                                            d_pose.data_ptr(), d_source.data_ptr(), 1.0)
+    for s in range(4):
+        out.synth_ms[s], out.mask_ms[s], out.target_ms[s] = synth[s].data_ptr(), mask[s].data_ptr(), tgt[s].data_ptr()
+        out.d_depth_ms[s] = d_depth[s].data_ptr()
+        if not derive:
+            out.d_disp_ms[s] = d_disp[s].data_ptr()
+    side = torch.cuda.Stream()
+    for call in range(3):
+        _cabi.check(plan._lib.xpt_total_loss_host(
+            plan.handle, C.byref(fr), C.byref(_cabi.ptr_array([d.data_ptr() for d in depth_h])),
+            None if derive else C.byref(_cabi.ptr_array([d.data_ptr() for d in disp_h])), pose.data_ptr(), C.byref(out),
+            C.c_void_p(side.cuda_stream)))
+        assert relerr(losses.numpy(), r["losses"].cpu().numpy()) < 1e-6, call
+        assert relerr(loss_batch.numpy(), r["loss_batch"].cpu().numpy()) < 1e-6, call
+        assert torch.equal(d_pose, r["d_pose"].cpu()), call
+        # dL/dsource is an atomic scatter: same values up to the summation order
+        assert relerr(d_source.numpy(), r["d_source"].cpu().numpy()) < 1e-5, call
+        for s in range(4):
+            assert torch.equal(synth[s], r["synth_ms"][s].cpu()), (call, s)
+            assert torch.equal(mask[s], r["mask_ms"][s].cpu()), (call, s)
+            assert torch.equal(tgt[s], r["target_ms"][s].cpu()), (call, s)
+            assert torch.equal(d_depth[s], r["d_depth_ms"][s].cpu().reshape(d_depth[s].shape)), (call, s)
+            if not derive:
+                assert torch.equal(d_disp[s], r["d_disp_ms"][s].cpu().reshape(d_disp[s].shape)), (call, s)
