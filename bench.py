@@ -178,6 +178,10 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA-graph replay")
     ap.add_argument("--unfused", action="store_true", help="one kernel per reference stage (A/B)")
     ap.add_argument("--source-grad", action="store_true", help="also produce dL/dsource (config 5's full backward)")
+    ap.add_argument("--net-grad-mb", type=float, default=0.0,
+                    help="N > 1 only: also all-reduce a stand-in fp32 net-gradient bucket of this many MB every step "
+                         "(SURVEY 8e: the depth/pose nets are out of scope; ~120 MB is EfficientNet-B5 + PoseNet), "
+                         "asynchronously, overlapped with the next step's kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=10)
     args = ap.parse_args()
@@ -228,6 +232,11 @@ def main():
     stream = plan.stream()
 
     pending = [None] * n_sets
+    net_grad = None
+    net_pending = [None]
+    if dist is not None and args.net_grad_mb > 0:
+        from xptwarp.distributed import allreduce_gradient_buckets
+        net_grad = torch.zeros(int(args.net_grad_mb * 1e6 / 4), dtype=torch.float32, device=device)
 
     def step(i):
         k = i % n_sets
@@ -240,12 +249,19 @@ def main():
             # the path's only exchange: the 4 loss scalars (replaces distributer.py:93-110); asynchronous, so
             # the NCCL kernel overlaps with the next step's launches instead of serialising the stream
             pending[k] = dist.all_reduce(c.out["losses"], async_op=True)
+            if net_grad is not None:          # stand-in for the nets' gradient buckets (one bucket in flight)
+                if net_pending[0] is not None:
+                    net_pending[0].wait()
+                net_pending[0] = allreduce_gradient_buckets([net_grad])[0]
 
     def drain():
         for k in range(n_sets):
             if pending[k] is not None:
                 pending[k].wait()             # current stream waits for the collective
                 pending[k] = None
+        if net_pending[0] is not None:
+            net_pending[0].wait()
+            net_pending[0] = None
 
     def barrier():
         drain()
@@ -398,7 +414,10 @@ def main():
                                    + (" +dL/dsource" if args.source_grad else ""),
                        "global_batch": global_batch, "parallelism": f"dp{world}",
                        "l2": f"rotating {n_sets} resident input sets ({n_sets * per_set / 1e6:.0f} MB > 126 MB L2)",
-                       "launch": "eager" if args.no_graph else "cuda-graph replay", "fused": not args.unfused},
+                       "launch": "eager" if args.no_graph else "cuda-graph replay", "fused": not args.unfused,
+                       "collectives": ("none (1 GPU)" if world == 1 else
+                                       "all-reduce of the 4 loss scalars per step" +
+                                       (f" + a {args.net_grad_mb:g} MB stand-in net-gradient bucket" if args.net_grad_mb > 0 else ""))},
             "roofline": roofline, "step_model": step_model, "cpu_baseline": cpu, "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches_per_step * args.steps,
