@@ -33,17 +33,25 @@ class _TotalLossFn(torch.autograd.Function):
     (the loss is linear in its upstream gradient)."""
 
     @staticmethod
-    def forward(ctx, plan, want_grad, source, target, intrinsic, pose, *maps):
+    def forward(ctx, plan, want_grad, split, source, target, intrinsic, pose, *maps):
+        """split > 0: the batch holds two groups of snippets (first `split`, rest) -- both eyes of a rig in one
+        launch -- and the by-type means come back per group, [2, 3], from the per-snippet losses."""
         S = plan.S
         depth_ms, disp_ms = maps[:S], (maps[S:] if len(maps) > S else None)
-        r = plan.total_loss(source, target, intrinsic, depth_ms, disp_ms, pose, want_grad=want_grad)
+        r = plan.total_loss(source, target, intrinsic, depth_ms, disp_ms, pose, want_grad=want_grad,
+                            want_loss_batch=split > 0)
         losses = r["losses"]
         if want_grad:
             ctx.shapes = [t.shape for t in maps]
             ctx.have_disp = disp_ms is not None
             ctx.save_for_backward(r["d_pose"], *r["d_depth_ms"], *(r["d_disp_ms"] if disp_ms is not None else ()))
         ctx.want_grad = want_grad
-        by_type = losses[1:4].clone()
+        if split > 0:
+            lb = r["loss_batch"].reshape(3, plan.B)
+            inv_gb = 1.0 / float(plan.cfg.global_batch)
+            by_type = torch.stack([lb[:, :split].sum(dim=1), lb[:, split:].sum(dim=1)]) * inv_gb
+        else:
+            by_type = losses[1:4].clone()
         ctx.mark_non_differentiable(by_type)
         return losses[0].clone(), by_type
 
@@ -53,7 +61,7 @@ class _TotalLossFn(torch.autograd.Function):
             raise RuntimeError("TotalLoss was evaluated without gradients")
         d_pose, *d_maps = ctx.saved_tensors
         outs = [g_total * d.reshape(s) for d, s in zip(d_maps, ctx.shapes)]
-        return (None, None, None, None, None, g_total * d_pose, *outs)
+        return (None, None, None, None, None, None, g_total * d_pose, *outs)
 
 
 class _StereoPoseFn(torch.autograd.Function):
@@ -367,14 +375,25 @@ class TotalLoss:
             loss_by_type[loss_name] = loss_mean
         return torch.stack(losses).sum(), loss_by_type
 
-    def _fused_group(self, source, target, intrinsic, depth_ms, disp_ms, pose, w_l1, w_ssim, w_smooth, sw):
-        """one fused launch: (total contribution, [L1, SSIM, smoothe] unweighted means)"""
+    def _fused_group(self, source, target, intrinsic, depth_ms, disp_ms, pose, w_l1, w_ssim, w_smooth, sw, split=0):
+        """one fused launch: (total contribution, [L1, SSIM, smoothe] unweighted means -- [2, 3] per group of
+        snippets when split > 0)"""
         B, N, H, W, _ = source.shape
         plan = get_plan(source.device.index or 0, B, N, H, W, infer_scales(H, depth_ms), sw, w_l1, w_ssim, w_smooth,
                         self.batch_size)
         maps = list(depth_ms) + (list(disp_ms) if (w_smooth != 0.0 and disp_ms is not None) else [])
         want_grad = torch.is_grad_enabled() and any(t.requires_grad for t in [pose, *maps])
-        return _TotalLossFn.apply(plan, want_grad, source, target, intrinsic, pose, *maps)
+        return _TotalLossFn.apply(plan, want_grad, int(split), source, target, intrinsic, pose, *maps)
+
+    @staticmethod
+    def _same_launch(groups):
+        """both eyes can share a launch: same weights, same shapes, disparities given for both or for neither"""
+        if len(groups) != 2:
+            return False
+        (img_l, K_l, dep_l, dsp_l, pose_l, w_l), (img_r, K_r, dep_r, dsp_r, pose_r, w_r) = groups[""], groups["_R"]
+        return (w_l == w_r and img_l.shape == img_r.shape and pose_l.shape == pose_r.shape
+                and (dsp_l is None) == (dsp_r is None) and img_l.device == img_r.device
+                and all(a.shape == b.shape for a, b in zip(dep_l, dep_r)))
 
     def _call_fused(self, predictions, features):
         w = {k: float(self.loss_weights[k]) for k in self.loss_objects}
@@ -382,7 +401,7 @@ class TotalLoss:
                   if v is not None)
         stereo = self._stereo_on(features)
         totals, by = [], {}
-        eyes = {}
+        eyes, groups = {}, {}
         for sfx in ("", "_R"):
             names = [n + sfx for n in _TEMPORAL if n + sfx in w]
             need = names or (stereo and ("stereoL1" in w or "stereoSSIM" in w))
@@ -401,31 +420,59 @@ class TotalLoss:
             # with safe_reciprocal_number_ms) and returns the whole gradient on depth_ms
             disp_ms = ([as_torch(d) for d in predictions["disp_ms" + sfx]]
                        if ("smoothe" + sfx in w and "disp_ms" + sfx in predictions) else None)
-            total, by_type = self._fused_group(image5d[:, :-1], image5d[:, -1], K, depth_ms, disp_ms, pose,
-                                               w.get("L1" + sfx, 0.0), w.get("SSIM" + sfx, 0.0), w.get("smoothe" + sfx, 0.0), sw)
+            groups[sfx] = (image5d, K, depth_ms, disp_ms, pose,
+                           (w.get("L1" + sfx, 0.0), w.get("SSIM" + sfx, 0.0), w.get("smoothe" + sfx, 0.0)))
+        if self._same_launch(groups):
+            # both eyes of the rig in ONE fused launch (twice the batch): same kernels, half the launches and a
+            # better filled last wave; the by-type means come back per eye from the per-snippet losses
+            (img_l, K_l, dep_l, dsp_l, pose_l, wts), (img_r, K_r, dep_r, dsp_r, pose_r, _) = groups[""], groups["_R"]
+            B = img_l.shape[0]
+            cat = lambda a, b: torch.cat([a, b], dim=0)
+            disp = None if dsp_l is None else [cat(a, b) for a, b in zip(dsp_l, dsp_r)]
+            total, by_eye = self._fused_group(cat(img_l[:, :-1], img_r[:, :-1]), cat(img_l[:, -1], img_r[:, -1]), cat(K_l, K_r),
+                                              [cat(a, b) for a, b in zip(dep_l, dep_r)], disp, cat(pose_l, pose_r),
+                                              *wts, sw, split=B)
             totals.append(total)
-            for i, n in enumerate(_TEMPORAL):
-                if n + sfx in w:
-                    by[n + sfx] = by_type[i]
+            for e, sfx in enumerate(("", "_R")):
+                for i, n in enumerate(_TEMPORAL):
+                    if n + sfx in w:
+                        by[n + sfx] = by_eye[e, i]
+        else:
+            for sfx, (image5d, K, depth_ms, disp_ms, pose, wts) in groups.items():
+                total, by_type = self._fused_group(image5d[:, :-1], image5d[:, -1], K, depth_ms, disp_ms, pose, *wts, sw)
+                totals.append(total)
+                for i, n in enumerate(_TEMPORAL):
+                    if n + sfx in w:
+                        by[n + sfx] = by_type[i]
         if "stereoL1" in w or "stereoSSIM" in w:
             # StereoDepthLoss (losses.py:443-478) over the two syntheses of losses.py:105-140: the fused kernel with
             # ONE source frame (the other eye's target), the rig transform as the pose and -- like the reference --
-            # the LEFT intrinsics for both directions
+            # the LEFT intrinsics for both directions.  Both directions share one launch (the loss is their sum).
             if not stereo or "stereo_T_LR" not in features:
                 raise WrongInputException("stereoL1 / stereoSSIM need TotalLoss(stereo=True), image5d_R and stereo_T_LR")
             T = as_torch(features["stereo_T_LR"])
             require_cuda_f32(stereo_T_LR=T)
             (img_l, K_l, depth_l), (img_r, _, depth_r) = eyes[""], eyes["_R"]
-            parts = []
-            for src_img, tgt_img, depth_ms, inv in ((img_r, img_l, depth_l, True), (img_l, img_r, depth_r, False)):
-                rig = pose_matr2rvec_batch(T.unsqueeze(1), invert=inv)
-                parts.append(self._fused_group(src_img[:, -1:], tgt_img[:, -1], K_l, depth_ms, None, rig,
-                                               w.get("stereoL1", 0.0), w.get("stereoSSIM", 0.0), 0.0, sw))
-            totals += [parts[0][0], parts[1][0]]
+            ws = (w.get("stereoL1", 0.0), w.get("stereoSSIM", 0.0), 0.0)
+            if img_l.shape == img_r.shape and all(a.shape == b.shape for a, b in zip(depth_l, depth_r)):
+                rig = torch.cat([pose_matr2rvec_batch(T.unsqueeze(1), invert=True), pose_matr2rvec_batch(T.unsqueeze(1))], dim=0)
+                tgt = torch.cat([img_l[:, -1], img_r[:, -1]], dim=0)         # [2B,H,W,3]: left targets, then right targets
+                src = torch.cat([img_r[:, -1:], img_l[:, -1:]], dim=0)       # the other eye's frame as the single source
+                total, by_type = self._fused_group(src, tgt, torch.cat([K_l, K_l], dim=0),
+                                                   [torch.cat([a, b], dim=0) for a, b in zip(depth_l, depth_r)], None, rig, *ws, sw)
+                totals.append(total)
+                st_l1, st_ssim = by_type[0], by_type[1]
+            else:
+                parts = []
+                for src_img, tgt_img, depth_ms, inv in ((img_r, img_l, depth_l, True), (img_l, img_r, depth_r, False)):
+                    rig = pose_matr2rvec_batch(T.unsqueeze(1), invert=inv)
+                    parts.append(self._fused_group(src_img[:, -1:], tgt_img[:, -1], K_l, depth_ms, None, rig, *ws, sw))
+                totals += [parts[0][0], parts[1][0]]
+                st_l1, st_ssim = parts[0][1][0] + parts[1][1][0], parts[0][1][1] + parts[1][1][1]
             if "stereoL1" in w:
-                by["stereoL1"] = parts[0][1][0] + parts[1][1][0]
+                by["stereoL1"] = st_l1
             if "stereoSSIM" in w:
-                by["stereoSSIM"] = parts[0][1][1] + parts[1][1][1]
+                by["stereoSSIM"] = st_ssim
         if "stereoPose" in w:
             mean = self.loss_objects["stereoPose"](features, predictions, None).sum() / self.batch_size
             by["stereoPose"] = mean
