@@ -83,6 +83,8 @@ struct xpt_ctx {
   float* tgt0_copy;             // unused unless a level-0 copy is wanted without a user buffer
   float* min_part;              // [B][S * full-res tiles] partial sums of xpt_photometric_min_loss
   float* l2_part;               // block partials (doubles) of xpt_l2_regularizer
+  float* c_geo_dev;             // device address of the constant-bank geometry block (c_geo)
+  bool geo_direct;              // this call's geometry is produced straight into c_geo (no staging copy)
   // staging for the host-buffer entry point
   float* st_frames; float* st_K; float* st_pose; float* st_losses; float* st_loss_batch; float* st_dpose;
   float* st_dsource;
@@ -180,6 +182,10 @@ GeoArgs make_geo(xpt_ctx* ctx, const float* pose, const float* intrinsic, float*
   memset(&g, 0, sizeof(g));
   g.pose = pose; g.intrinsic = intrinsic;
   g.geoK = intrinsic ? ctx->geoK : nullptr; g.geoT = pose ? ctx->geoT : nullptr; g.matr_out = matr_out;
+  if (ctx->geo_direct && intrinsic && pose) {      // same [K block | [R|t] block] layout, inside the constant bank
+    g.geoK = ctx->c_geo_dev;
+    g.geoT = ctx->c_geo_dev + (size_t)ctx->B * ctx->S * kGeoK;
+  }
   g.B = ctx->B; g.N = ctx->N; g.S = ctx->S;
   for (int l = 0; l < ctx->S; ++l) g.s[l] = ctx->s[l];
   return g;
@@ -450,7 +456,9 @@ int launch_fused(xpt_ctx* ctx, FusedArgs& a, cudaStream_t st) {
   for (int b0 = 0; b0 < ctx->B; b0 += cap) {
     const int bc = ctx->B - b0 < cap ? ctx->B - b0 : cap;
     const size_t kbytes = (size_t)bc * ctx->S * kGeoK * sizeof(float), tbytes = (size_t)bc * ctx->N * kGeoT * sizeof(float);
-    if (bc == ctx->B) {       // K block and [R|t] block are adjacent in the scratch: one copy
+    if (ctx->geo_direct) {
+      // the pyramid launch wrote the geometry of the whole batch straight into the constant bank
+    } else if (bc == ctx->B) {       // K block and [R|t] block are adjacent in the scratch: one copy
       XPT_CUDA(cudaMemcpyToSymbolAsync(c_geo, ctx->geoK, kbytes + tbytes, 0, cudaMemcpyDeviceToDevice, st));
     } else {
       XPT_CUDA(cudaMemcpyToSymbolAsync(c_geo, ctx->geoK + (size_t)b0 * ctx->S * kGeoK, kbytes, 0, cudaMemcpyDeviceToDevice, st));
@@ -572,6 +580,11 @@ int xpt_create(xpt_ctx** out, const xpt_config* cfg) {
   if (ctx->first_chunk[ctx->S] > ctx->slots_per_b) ctx->slots_per_b = ctx->first_chunk[ctx->S];
   if (ctx->ffirst_tile[ctx->S] > ctx->slots_per_b) ctx->slots_per_b = ctx->ffirst_tile[ctx->S];
 
+  {
+    void* cg = nullptr;
+    if (cudaGetSymbolAddress(&cg, c_geo) == cudaSuccess) ctx->c_geo_dev = static_cast<float*>(cg);
+    else (void)cudaGetLastError();
+  }
   int rc = XPT_OK;
   auto A = [&](float** p, size_t n) { if (rc == XPT_OK) rc = dev_alloc(ctx, p, n); };
   A(&ctx->geoK, (size_t)ctx->B * ctx->S * kGeoK + (size_t)ctx->B * ctx->N * kGeoT);   // K block, then [R|t] block
@@ -919,7 +932,7 @@ int xpt_smoothness_loss(xpt_ctx* ctx, const float* const disp_ms[], const float*
   return XPT_OK;
 }
 
-static int total_loss_impl(xpt_ctx* ctx, const xpt_frames* frames, const float* const depth_ms[],
+static int total_loss_body(xpt_ctx* ctx, const xpt_frames* frames, const float* const depth_ms[],
                            const float* const disp_ms[], const float* pose, const xpt_loss_outputs* out,
                            void* stream) {
   if (!ctx || !pose || !out) return fail(XPT_BAD_ARGUMENT, "xpt_total_loss: NULL argument");
@@ -944,7 +957,14 @@ static int total_loss_impl(xpt_ctx* ctx, const xpt_frames* frames, const float* 
   const float inv_gb = 1.0f / (float)c.global_batch;
 
   const bool fused = !(c.flags & XPT_FLAG_UNFUSED);
-  XPT_TRY(launch_pyramids(ctx, frames, out->target_ms, true, st, pose, fused));   // + camera geometry in the same launch
+#ifdef XPT_GEO_DIRECT
+  // fused path, whole batch in one constant-bank chunk: the geometry slice of the pyramid launch writes c_geo itself
+  // (a kernel may write a __constant__ variable through its device address; later LAUNCHES on the stream see it)
+  ctx->geo_direct = fused && ctx->c_geo_dev != nullptr &&
+                    ctx->B * (ctx->S * kGeoK + ctx->N * kGeoT) <= kGeoConstFloats;
+#endif
+  const int rc_pyr = launch_pyramids(ctx, frames, out->target_ms, true, st, pose, fused);   // + camera geometry in the same launch
+  if (rc_pyr != XPT_OK) { ctx->geo_direct = false; return rc_pyr; }
   LevelTable lt = make_levels(ctx, frames, nullptr);
 
   PhotoArgs a;
@@ -1082,6 +1102,13 @@ static int total_loss_impl(xpt_ctx* ctx, const xpt_frames* frames, const float* 
   }
   if (grad && !fused_path) XPT_TRY(finish_dsource(ctx, out->d_source, st));
   return XPT_OK;
+}
+
+static int total_loss_impl(xpt_ctx* ctx, const xpt_frames* frames, const float* const depth_ms[],
+                           const float* const disp_ms[], const float* pose, const xpt_loss_outputs* out, void* stream) {
+  const int rc = total_loss_body(ctx, frames, depth_ms, disp_ms, pose, out, stream);
+  if (ctx) ctx->geo_direct = false;      // per-call state of the fused path
+  return rc;
 }
 
 int xpt_total_loss(xpt_ctx* ctx, const xpt_frames* frames, const float* const depth_ms[],
