@@ -37,7 +37,7 @@ for name, lw in SETS.items():
         total.backward()
     for _ in range(3): step()
     torch.cuda.synchronize()
-    n = 10
+    n = int(os.environ.get("XPT_LS_STEPS", "10"))
     t0 = time.perf_counter()
     for _ in range(n): step()
     torch.cuda.synchronize()

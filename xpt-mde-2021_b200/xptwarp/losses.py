@@ -105,45 +105,49 @@ class _PhotoFn(torch.autograd.Function):
         return (None, None, None, *d_synth, *([None] * S))
 
 
+def _scale_by_snippet(g, grads):
+    """upstream dL/d loss_batch [B] applied to per-snippet gradients computed for an all-ones upstream"""
+    g = g.reshape(-1)
+    return [d * g.view(-1, *([1] * (d.dim() - 1))) for d in grads]
+
+
 class _PhotoMinFn(torch.autograd.Function):
-    """MonoDepth2 / MoA: min over sources per pixel and channel at full resolution (xpt_photometric_min_loss)."""
+    """MonoDepth2 / MoA: min over sources per pixel and channel at full resolution (xpt_photometric_min_loss).
+    When a gradient is wanted the forward call already runs the gradient kernel (for an all-ones upstream: the loss is
+    linear in it), so the backward is a per-snippet rescale instead of a second pass over every scale."""
 
     @staticmethod
     def forward(ctx, plan, method, S, have_stereo, target, *ts):
         synth_ms = ts[:S]
         stereo_ms = ts[S:] if have_stereo else None
-        loss, _, _, _ = plan.photometric_min_loss(method, synth_ms, stereo_ms, target)
-        ctx.plan, ctx.method, ctx.S, ctx.have_stereo = plan, method, S, have_stereo
-        ctx.save_for_backward(target, *ts)
+        want = any(ctx.needs_input_grad[5:])
+        loss, d_synth, d_stereo, _ = plan.photometric_min_loss(method, synth_ms, stereo_ms, target, want_grad=want)
+        ctx.S, ctx.have_stereo, ctx.want = S, have_stereo, want
+        if want:
+            ctx.save_for_backward(*d_synth, *(d_stereo if have_stereo else ()))
         return loss
 
     @staticmethod
     def backward(ctx, g):
-        target, *ts = ctx.saved_tensors
-        S = ctx.S
-        _, d_synth, d_stereo, _ = ctx.plan.photometric_min_loss(
-            ctx.method, ts[:S], ts[S:] if ctx.have_stereo else None, target,
-            grad_loss_batch=g.reshape(-1).contiguous(), want_grad=True)
-        return (None, None, None, None, None, *d_synth, *(d_stereo if ctx.have_stereo else ()))
+        return (None, None, None, None, None, *_scale_by_snippet(g, ctx.saved_tensors))
 
 
 class _PhotoCmbFn(torch.autograd.Function):
     """CombinedLossMultiScale: static term where it beats the flow term (xpt_photometric_cmb_loss).  The flow-warped
-    view only enters through a comparison, so it receives no gradient (as in the reference's graph)."""
+    view only enters through a comparison, so it receives no gradient (as in the reference's graph).  Forward and
+    gradient share one launch, like _PhotoMinFn."""
 
     @staticmethod
     def forward(ctx, plan, method, target, warped, *synth_ms):
-        loss, _, _ = plan.photometric_cmb_loss(method, synth_ms, warped, target)
-        ctx.plan, ctx.method = plan, method
-        ctx.save_for_backward(target, warped, *synth_ms)
+        want = any(ctx.needs_input_grad[4:])
+        loss, d_synth, _ = plan.photometric_cmb_loss(method, synth_ms, warped, target, want_grad=want)
+        if want:
+            ctx.save_for_backward(*d_synth)
         return loss
 
     @staticmethod
     def backward(ctx, g):
-        target, warped, *synth_ms = ctx.saved_tensors
-        _, d_synth, _ = ctx.plan.photometric_cmb_loss(ctx.method, synth_ms, warped, target,
-                                                      grad_loss_batch=g.reshape(-1).contiguous(), want_grad=True)
-        return (None, None, None, None, *d_synth)
+        return (None, None, None, None, *_scale_by_snippet(g, ctx.saved_tensors))
 
 
 class _L2RegFn(torch.autograd.Function):
