@@ -58,7 +58,7 @@ __device__ __forceinline__ void up_taps(int o, int in_size, float scale, int& lo
 }
 
 template <bool GRAD>
-__global__ void __launch_bounds__(kPhotoThreads) k_photo_min(MinLossArgs a) {
+__global__ void __launch_bounds__(kPhotoThreads, 3) k_photo_min(MinLossArgs a) {
   using SM = PhotoSmem<GRAD>;
   constexpr int HL = SM::HL, RW = SM::RW, SW = SM::SW;
   constexpr int HS = HL - 1;
@@ -196,7 +196,11 @@ __global__ void __launch_bounds__(kPhotoThreads) k_photo_min(MinLossArgs a) {
   };
 
   // dL/dS of the source in sy from the coefficient planes sA/sB/sC (SSIM: box-summed over the 3x3 window), pushed
-  // through the adjoint of the up-sampling into the low-resolution gradient (fp32 atomics)
+  // through the adjoint of the up-sampling into the low-resolution gradient (fp32 atomics in L2; zero-weight taps are
+  // skipped).  A level at full resolution (identity up-sampling) owns its pixels: plain stores.
+  // (Staging the tile's contributions in shared memory first was measured and is slower: fp32 shared-memory atomics
+  // serialise on the few low-resolution values a coarse level's tile maps to -- 394 vs 307 us at config 2.)
+  const bool identity = (h == H) && (w == W);
   auto scatter = [&](int m) {
     float* glow = m < a.N ? a.gsynth[l] + ((size_t)b * a.N + m) * h * w * 3
                           : a.gstereo[l] + ((size_t)b * a.NS + (m - a.N)) * h * w * 3;
@@ -225,17 +229,23 @@ __global__ void __launch_bounds__(kPhotoThreads) k_photo_min(MinLossArgs a) {
         }
       }
       if (g[0] == 0.f && g[1] == 0.f && g[2] == 0.f) continue;
+      if (identity) {
+        float* o = glow + ((size_t)gy * w + gx) * 3;
+        o[0] = g[0]; o[1] = g[1]; o[2] = g[2];
+        continue;
+      }
       // adjoint of the up-sampling: top = tl + (tr - tl) fx, out = top + (bot - top) fy
       int y0, y1, x0, x1; float fy, fx;
       up_taps(gy, h, sc_y, y0, y1, fy);
       up_taps(gx, w, sc_x, x0, x1, fx);
-      const float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx, w10 = fy * (1.f - fx), w11 = fy * fx;
+      const float wt[4] = {(1.f - fy) * (1.f - fx), (1.f - fy) * fx, fy * (1.f - fx), fy * fx};
+      const int ys[4] = {y0, y0, y1, y1}, xs[4] = {x0, x1, x0, x1};
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        atomicAdd(glow + ((size_t)y0 * w + x0) * 3 + c, w00 * g[c]);
-        atomicAdd(glow + ((size_t)y0 * w + x1) * 3 + c, w01 * g[c]);
-        atomicAdd(glow + ((size_t)y1 * w + x0) * 3 + c, w10 * g[c]);
-        atomicAdd(glow + ((size_t)y1 * w + x1) * 3 + c, w11 * g[c]);
+      for (int k = 0; k < 4; ++k) {
+        if (wt[k] == 0.f) continue;
+        float* o = glow + ((size_t)ys[k] * w + xs[k]) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) atomicAdd(o + c, wt[k] * g[c]);
       }
     }
   };
