@@ -93,11 +93,11 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_input_sets(orc, B, H, W, n_sets, seed, device):
+def make_input_sets(orc, B, H, W, n_sets, seed, device, adversarial=False):
     """n_sets distinct snippet batches resident in HBM (rotated so that no step finds its inputs in L2).
     Two are generated from scratch; the rest are cheap perturbations of those (rolled images, scaled
     depth, jittered pose) -- generating 20+ full batches on the CPU would dominate start-up."""
-    base = [orc.make_inputs(B, H, W, N=N_SRC, n_scales=N_SCALES, seed=seed + i) for i in range(2)]
+    base = [orc.make_inputs(B, H, W, N=N_SRC, n_scales=N_SCALES, seed=seed + i, adversarial=adversarial) for i in range(2)]
     sets = []
     for i in range(n_sets):
         bf, bp = base[i % 2]
@@ -182,6 +182,9 @@ def main():
                     help="N > 1 only: also all-reduce a stand-in fp32 net-gradient bucket of this many MB every step "
                          "(SURVEY 8e: the depth/pose nets are out of scope; ~120 MB is EfficientNet-B5 + PoseNet), "
                          "asynchronously, overlapped with the next step's kernels")
+    ap.add_argument("--adversarial", action="store_true",
+                    help="SURVEY 8d's adversarial inputs: iid depth U(1,80) per pixel (worst-case gather locality) and "
+                         "large poses (about half of the samples leave the image)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=10)
     args = ap.parse_args()
@@ -219,7 +222,7 @@ def main():
     probe_f, probe_p = orc.make_inputs(1, H, W, N=N_SRC, n_scales=N_SCALES, seed=1)
     per_set = set_bytes(probe_f, probe_p) * B
     n_sets = int(min(24, max(3, -(-3 * 126e6 // per_set))))
-    sets, sets_cpu = make_input_sets(orc, B, H, W, n_sets, 20211 + 2000 + rank, device)
+    sets, sets_cpu = make_input_sets(orc, B, H, W, n_sets, 20211 + 2000 + rank, device, args.adversarial)
     calls = []
     for f, p in sets:
         img = f["image5d"]
@@ -324,6 +327,8 @@ def main():
         torch.cuda.synchronize()
         durs = eager.profile_end(nrec)
         kern_ms = sum(durs) / len(durs)
+        sd = sorted(durs)
+        kern_pct = {"p10": sd[len(sd) // 10], "p50": sd[len(sd) // 2], "p90": sd[(9 * len(sd)) // 10], "n": len(sd)}
     px_rank = B * H * W
     roofline = None
     if kern_ms:
@@ -338,7 +343,7 @@ def main():
                 traffic = rec["dram_bytes_per_launch"]        # bytes per launch, from the committed ncu --set full capture
         roofline = {"bound": "hbm", "kernel": "k_fused<grad>", "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": ach / peak, "traffic": traffic, "algorithmic_bytes_per_launch": px_rank * fused_bytes,
-                    "peak_source": peak_src, "kernel_ms": kern_ms,
+                    "peak_source": peak_src, "kernel_ms": kern_ms, "kernel_ms_percentiles": kern_pct,
                     "bytes_per_pixel": fused_bytes, "kernel_share_of_step": kern_ms / ms_step if world == 1 else None}
     step_model = {"bytes_per_pixel": BYTES_SURVEY_STEP,
                   "achieved_gbs": value / world * BYTES_SURVEY_STEP, "frac_of_peak": value / world * BYTES_SURVEY_STEP / peak,
@@ -411,7 +416,8 @@ def main():
             "warmup": max(args.warmup, 2 * n_sets), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: B={B}/gpu {H}x{W} snippet=5 (4 sources) scales=4 LOSS_RIGID_T1 fwd+bwd"
-                                   + (" +dL/dsource" if args.source_grad else ""),
+                                   + (" +dL/dsource" if args.source_grad else "")
+                                   + (" ADVERSARIAL inputs (iid depth, large poses)" if args.adversarial else ""),
                        "global_batch": global_batch, "parallelism": f"dp{world}",
                        "l2": f"rotating {n_sets} resident input sets ({n_sets * per_set / 1e6:.0f} MB > 126 MB L2)",
                        "launch": "eager" if args.no_graph else "cuda-graph replay", "fused": not args.unfused,
