@@ -693,48 +693,49 @@ __device__ void pose_block(const float* __restrict__ pose_part, int slots_per_b,
     if (lane == 0) red[wid][k] = v;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 3) {
+    // threads 0..2 each take one rotation component k (the serial fp64 chain is the epilogue's latency);
+    // thread 0 also writes the translation part
+    const int k = threadIdx.x;
     double G[12];
-    for (int k = 0; k < 12; ++k) G[k] = (red[0][k] + red[1][k] + red[2][k] + red[3][k]) * (double)scale;
+    for (int j = 0; j < 12; ++j) G[j] = (red[0][j] + red[1][j] + red[2][j] + red[3][j]) * (double)scale;
     const float* p = pose + (size_t)bn * 6;
     double w[3] = {p[3], p[4], p[5]};
     double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
     double th = sqrt(th2);
     float* o = d_pose + (size_t)bn * 6;
-    o[0] = (float)G[9]; o[1] = (float)G[10]; o[2] = (float)G[11];
+    if (k == 0) { o[0] = (float)G[9]; o[1] = (float)G[10]; o[2] = (float)G[11]; }
     if (th < 1e-8) {
       // the reference's gradient is NaN here: propagate that, do not invent a value
-      o[3] = o[4] = o[5] = __int_as_float(0x7fc00000);
+      o[3 + k] = __int_as_float(0x7fc00000);
     } else {
       double Sm[9] = {0, w[2], -w[1], -w[2], 0, w[0], w[1], -w[0], 0};
       double S2[9];
       for (int r = 0; r < 3; ++r)
         for (int c = 0; c < 3; ++c) {
           double v = 0;
-          for (int k = 0; k < 3; ++k) v += Sm[r * 3 + k] * Sm[k * 3 + c];
+          for (int j = 0; j < 3; ++j) v += Sm[r * 3 + j] * Sm[j * 3 + c];
           S2[r * 3 + c] = v;
         }
       double sn = sin(th), cs = cos(th);
       double ca = sn / th, cb = (1.0 - cs) / th2;
       double da = (th * cs - sn) / th2;                    // d(sin th / th)/d th
       double db = (th * sn - 2.0 * (1.0 - cs)) / (th2 * th);   // d((1-cos th)/th^2)/d th
-      for (int k = 0; k < 3; ++k) {
-        double E[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        // E_k = d S / d w_k
-        if (k == 0) { E[5] = 1; E[7] = -1; }
-        if (k == 1) { E[2] = -1; E[6] = 1; }
-        if (k == 2) { E[1] = 1; E[3] = -1; }
-        double dth = w[k] / th;
-        double s = 0;
-        for (int r = 0; r < 3; ++r)
-          for (int c = 0; c < 3; ++c) {
-            double es = 0;
-            for (int j = 0; j < 3; ++j) es += E[r * 3 + j] * Sm[j * 3 + c] + Sm[r * 3 + j] * E[j * 3 + c];
-            double dR = ca * E[r * 3 + c] + da * dth * Sm[r * 3 + c] + cb * es + db * dth * S2[r * 3 + c];
-            s += G[r * 3 + c] * dR;
-          }
-        o[3 + k] = (float)s;
-      }
+      double E[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      // E_k = d S / d w_k
+      if (k == 0) { E[5] = 1; E[7] = -1; }
+      if (k == 1) { E[2] = -1; E[6] = 1; }
+      if (k == 2) { E[1] = 1; E[3] = -1; }
+      double dth = w[k] / th;
+      double sacc = 0;
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) {
+          double es = 0;
+          for (int j = 0; j < 3; ++j) es += E[r * 3 + j] * Sm[j * 3 + c] + Sm[r * 3 + j] * E[j * 3 + c];
+          double dR = ca * E[r * 3 + c] + da * dth * Sm[r * 3 + c] + cb * es + db * dth * S2[r * 3 + c];
+          sacc += G[r * 3 + c] * dR;
+        }
+      o[3 + k] = (float)sacc;
     }
   }
 }
