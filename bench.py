@@ -50,6 +50,41 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank to the CPUs next to its GPU (sysfs local_cpulist of the GPU's PCI function) BEFORE any pinned
+    host buffer is allocated, so that the buffers of the end-to-end leg are first-touched on the GPU's NUMA node.
+    Returns a short description for the JSON line; silently a no-op when the topology cannot be read."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        path = f"/sys/bus/pci/devices/{dom[-4:].lower()}:{rest.lower()}"
+        with open(path + "/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        node = None
+        try:
+            with open(path + "/numa_node") as f:
+                node = int(f.read().strip())
+        except OSError:
+            pass
+        return f"numa node {node}, {len(cpus)} cpus"
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -200,6 +235,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl ours needs a CUDA device: xptwarp has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local_rank) if os.environ.get("XPT_NO_NUMA_BIND") is None else None
     device = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
@@ -392,6 +429,7 @@ def main():
     # ---- CPU baseline beside it (rank 0, N=1 only; bounded sample) ----------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)         # the CPU baseline gets every host core back
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
         fb, pb = sets_cpu[0]
@@ -421,6 +459,7 @@ def main():
                        "global_batch": global_batch, "parallelism": f"dp{world}",
                        "l2": f"rotating {n_sets} resident input sets ({n_sets * per_set / 1e6:.0f} MB > 126 MB L2)",
                        "launch": "eager" if args.no_graph else "cuda-graph replay", "fused": not args.unfused,
+                       "host_affinity": numa or "unbound",
                        "collectives": ("none (1 GPU)" if world == 1 else
                                        "all-reduce of the 4 loss scalars per step" +
                                        (f" + a {args.net_grad_mb:g} MB stand-in net-gradient bucket" if args.net_grad_mb > 0 else ""))},
