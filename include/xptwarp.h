@@ -23,6 +23,11 @@
  *    the thread-local message.  There is no CPU fallback.
  *  - one xpt_ctx per (device, host thread); calls on one ctx must be serialised
  *    by the caller (stream order is enough when one stream is used).
+ *  - the fused kernel reads the camera geometry from ONE __constant__ block per
+ *    device, uploaded in stream order right before each launch: xpt_total_loss
+ *    calls of DIFFERENT contexts on the same device must therefore also be ordered
+ *    with respect to each other (issue them on one stream, as the Python host does,
+ *    or synchronise between them).
  */
 #ifndef XPTWARP_H_
 #define XPTWARP_H_
