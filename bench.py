@@ -346,6 +346,7 @@ def main():
     # ---- timed region B: the dominant kernel alone (events around each launch, eager launches) -----
     peak, peak_src = load_peaks()
     kern_ms = None
+    pyr_ms = None
     if not args.unfused:
         eager = xptwarp.get_plan(local_rank, B, N_SRC, H, W, [1, 2, 4, 8], sw, lw["L1"], lw["SSIM"], lw["smoothe"],
                                  global_batch, flags & ~_cabi.XPT_FLAG_GRAPH)
@@ -366,6 +367,13 @@ def main():
         kern_ms = sum(durs) / len(durs)
         sd = sorted(durs)
         kern_pct = {"p10": sd[len(sd) // 10], "p50": sd[len(sd) // 2], "p90": sd[(9 * len(sd)) // 10], "n": len(sd)}
+        # the step's one HBM-bound kernel, timed the same way: pyramids (+ camera geometry)
+        eager.profile_begin(nrec, kernel=1)
+        for i in range(nrec):
+            ecalls[i % n_sets].run(stream)
+        torch.cuda.synchronize()
+        pdurs = eager.profile_end(nrec)
+        pyr_ms = sum(pdurs) / len(pdurs) if pdurs else None
     px_rank = B * H * W
     roofline = None
     if kern_ms:
@@ -382,6 +390,14 @@ def main():
                     "frac": ach / peak, "traffic": traffic, "algorithmic_bytes_per_launch": px_rank * fused_bytes,
                     "peak_source": peak_src, "kernel_ms": kern_ms, "kernel_ms_percentiles": kern_pct,
                     "bytes_per_pixel": fused_bytes, "kernel_share_of_step": kern_ms / ms_step if world == 1 else None}
+    if roofline is not None and pyr_ms:
+        # k_pyramid_tiled: read 60 B (5 frames x 12), write the RGBx source levels (4 x gamma x 16) and the target
+        # levels s > 1 ((gamma - 1) x 12) per full-resolution target pixel
+        pyr_bytes = 60 + N_SRC * GAMMA * 16 + (GAMMA - 1) * 12
+        pach = px_rank * pyr_bytes / (pyr_ms * 1e-3) / 1e9
+        roofline["secondary"] = {"bound": "hbm", "kernel": "k_pyramid_tiled", "achieved": pach, "peak": peak, "unit": "GB/s",
+                                 "frac": pach / peak, "kernel_ms": pyr_ms, "bytes_per_pixel": pyr_bytes,
+                                 "algorithmic_bytes_per_launch": px_rank * pyr_bytes}
     step_model = {"bytes_per_pixel": BYTES_SURVEY_STEP,
                   "achieved_gbs": value / world * BYTES_SURVEY_STEP, "frac_of_peak": value / world * BYTES_SURVEY_STEP / peak,
                   "note": "SURVEY 8d unfused fwd+bwd+prep bytes model at the measured pixel rate, per GPU"}

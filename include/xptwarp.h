@@ -251,6 +251,10 @@ XPT_API int xpt_total_loss_host(xpt_ctx* ctx, const xpt_frames* frames,
  * by CUDA events on its stream; xpt_profile_end waits for them and returns how many durations
  * (milliseconds) it wrote to ms_out.  Not recorded inside graph replays.          */
 XPT_API int xpt_profile_begin(xpt_ctx* ctx, int max_records);
+/* which kernel of xpt_total_loss the events bracket (default: the fused tile kernel) */
+#define XPT_PROFILE_FUSED 0
+#define XPT_PROFILE_PYRAMID 1      /* the single-pass tiled pyramid + geometry kernel (scales within 1,2,4,8) */
+XPT_API int xpt_profile_select(xpt_ctx* ctx, int kernel);
 XPT_API int xpt_profile_end(xpt_ctx* ctx, float* ms_out, int capacity);
 
 /* number of kernels the last call on this ctx launched (bench's gpu_launches) */

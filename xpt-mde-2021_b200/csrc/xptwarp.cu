@@ -107,6 +107,7 @@ struct xpt_ctx {
   std::vector<cudaEvent_t>* prof_events;
   int prof_count;
   int prof_on;                  // records still allowed
+  int prof_kind;                // which kernel xpt_profile_* brackets: XPT_PROFILE_FUSED / XPT_PROFILE_PYRAMID
 };
 
 namespace {
@@ -235,8 +236,11 @@ int launch_pyramids(xpt_ctx* ctx, const xpt_frames* f, float* const target_ms[],
         if (geo_pose && need > gx) gx = need;
         dim3 grid(gx, ctx->H / kPyrTH, ctx->B * (ctx->N + 1) + 1);
         if (!any) grid = dim3(need, 1, ctx->B * (ctx->N + 1) + 1);
+        const bool prof = ctx->prof_on > 0 && ctx->prof_count < ctx->prof_on && ctx->prof_kind == XPT_PROFILE_PYRAMID;
+        if (prof) XPT_CUDA(cudaEventRecord((*ctx->prof_events)[2 * ctx->prof_count], st));
         k_pyramid_tiled<<<grid, kPyrThreads, 0, st>>>(t);
         XPT_LAUNCH_CHECK("k_pyramid_tiled");
+        if (prof) { XPT_CUDA(cudaEventRecord((*ctx->prof_events)[2 * ctx->prof_count + 1], st)); ++ctx->prof_count; }
       }
       if (target_ms && f->target)
         for (int l = 0; l < ctx->S; ++l) {
@@ -451,7 +455,7 @@ int launch_fused(xpt_ctx* ctx, FusedArgs& a, cudaStream_t st) {
   // kGeoConstFloats / (S*18 + N*12) snippets, larger batches are launched in chunks
   const int per_b = ctx->S * kGeoK + ctx->N * kGeoT;
   const int cap = kGeoConstFloats / per_b;
-  const bool prof = ctx->prof_on > 0 && ctx->prof_count < ctx->prof_on;
+  const bool prof = ctx->prof_on > 0 && ctx->prof_count < ctx->prof_on && ctx->prof_kind == XPT_PROFILE_FUSED;
   if (prof) XPT_CUDA(cudaEventRecord((*ctx->prof_events)[2 * ctx->prof_count], st));
   for (int b0 = 0; b0 < ctx->B; b0 += cap) {
     const int bc = ctx->B - b0 < cap ? ctx->B - b0 : cap;
@@ -1161,6 +1165,13 @@ int xpt_total_loss(xpt_ctx* ctx, const xpt_frames* frames, const float* const de
   }
   ctx->graphs->push_back({key, exec, ctx->launches});
   XPT_CUDA(cudaGraphLaunch(exec, st));
+  return XPT_OK;
+}
+
+int xpt_profile_select(xpt_ctx* ctx, int kernel) {
+  if (!ctx || (kernel != XPT_PROFILE_FUSED && kernel != XPT_PROFILE_PYRAMID))
+    return fail(XPT_BAD_ARGUMENT, "xpt_profile_select: bad argument");
+  ctx->prof_kind = kernel;
   return XPT_OK;
 }
 

@@ -354,7 +354,9 @@ class Plan:
         """xpt_total_loss (see bind_total_loss for the arguments); returns the dict of outputs."""
         return self.bind_total_loss(*args, **kwargs).run()
 
-    def profile_begin(self, max_records):
+    def profile_begin(self, max_records, kernel=0):
+        """kernel: 0 = the fused tile kernel, 1 = the tiled pyramid kernel (XPT_PROFILE_*)"""
+        _cabi.check(self._lib.xpt_profile_select(self.handle, int(kernel)))
         _cabi.check(self._lib.xpt_profile_begin(self.handle, int(max_records)))
 
     def profile_end(self, capacity):
