@@ -235,8 +235,9 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl ours needs a CUDA device: xptwarp has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    all_cpus = os.sched_getaffinity(0)
-    numa = bind_to_gpu_numa_node(local_rank) if os.environ.get("XPT_NO_NUMA_BIND") is None else None
+    # only multi-rank runs bind (several ranks competing for the host side of PCIe); the 1-GPU run also times the
+    # CPU baseline, whose worker threads must keep every host core
+    numa = bind_to_gpu_numa_node(local_rank) if (world > 1 and os.environ.get("XPT_NO_NUMA_BIND") is None) else None
     device = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
@@ -445,7 +446,6 @@ def main():
     # ---- CPU baseline beside it (rank 0, N=1 only; bounded sample) ----------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        os.sched_setaffinity(0, all_cpus)         # the CPU baseline gets every host core back
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
         fb, pb = sets_cpu[0]
