@@ -42,4 +42,32 @@ for name, lw in SETS.items():
     for _ in range(n): step()
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / n
-    print(f"{name:20s} {dt*1e3:8.2f} ms/step   {2*B*H*W/dt/1e9:6.3f} Gpixel/s (both eyes)   plans cached {len(engine._PLANS)}")
+    # the same step captured once with torch.cuda.graph and replayed (no Python on the path)
+    gdt = float("nan")
+    try:
+        for v in p.values():
+            for t in (v if isinstance(v, list) else [v]):
+                t.grad = None
+        side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                step()
+            for v in p.values():
+                for t in (v if isinstance(v, list) else [v]):
+                    t.grad = None
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            total, _ = tot(p, f)
+            total.backward()
+        for _ in range(3): graph.replay()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n): graph.replay()
+        torch.cuda.synchronize()
+        gdt = (time.perf_counter() - t0) / n
+    except Exception as e:      # a set whose objects cannot be captured is reported, not fatal
+        print("   graph capture failed:", type(e).__name__, str(e)[:120])
+        torch.cuda.synchronize()
+    print(f"{name:20s} eager {dt*1e3:7.2f} ms/step ({2*B*H*W/dt/1e9:6.3f} Gpixel/s both eyes)   "
+          f"torch.cuda.graph replay {gdt*1e3:7.2f} ms/step ({2*B*H*W/gdt/1e9:6.3f} Gpixel/s)   plans cached {len(engine._PLANS)}")

@@ -861,3 +861,55 @@ def test_host_entry_point_all_outputs(xw, derive):
             assert torch.equal(d_depth[s], r["d_depth_ms"][s].cpu().reshape(d_depth[s].shape)), (call, s)
             if not derive:
                 assert torch.equal(d_disp[s], r["d_disp_ms"][s].cpu().reshape(d_disp[s].shape)), (call, s)
+
+
+def test_whole_step_under_torch_cuda_graph(xw):
+    """The public-API step (TotalLoss forward + autograd backward) captured ONCE with torch.cuda.graph and replayed on
+    new input values: the library's launches are capturable after one warm-up call (lazy scratch exists), so a
+    trainer can remove the Python overhead of the call surface."""
+    from oracle import xpt_oracle as orc
+    B, H, W = 2, 64, 96
+    lw, sw = orc.LOSS_RIGID_T2, orc.SCALE_WEIGHT_T2
+    feats, preds = orc.make_inputs(B, H, W, seed=901)
+    feats2, preds2 = orc.make_inputs(B, H, W, seed=902)
+    f = {k: v.cuda() for k, v in feats.items()}
+    p = {"depth_ms": [d.cuda().requires_grad_(True) for d in preds["depth_ms"]],
+         "disp_ms": [d.cuda().requires_grad_(True) for d in preds["disp_ms"]], "pose": preds["pose"].cuda().requires_grad_(True)}
+    tot = xw.loss_factory({"image": 1, "intrinsic": 1}, lw, np.array(sw), batch_size=B)
+    leaves = [*p["depth_ms"], *p["disp_ms"], p["pose"]]
+
+    def step():
+        total, _ = tot(p, f)
+        total.backward()
+        return total
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step()
+            for t in leaves:
+                t.grad = None
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        static_total = step()
+    # new values into the captured (static) input tensors, then replay
+    with torch.no_grad():
+        f["image5d"].copy_(feats2["image5d"]); f["intrinsic"].copy_(feats2["intrinsic"])
+        p["pose"].copy_(preds2["pose"])
+        for s in range(4):
+            p["depth_ms"][s].copy_(preds2["depth_ms"][s]); p["disp_ms"][s].copy_(preds2["disp_ms"][s])
+    graph.replay()
+    torch.cuda.synchronize()
+    got_total = static_total.item()
+    got = [t.grad.clone() for t in leaves]
+    # eager evaluation of the same inputs
+    for t in leaves:
+        t.grad = None
+    ref_total = step()
+    torch.cuda.synchronize()
+    assert got_total == ref_total.item()
+    for a_, t in zip(got, leaves):
+        assert torch.equal(a_, t.grad)
+    ref = orc.loss_and_grads(feats2, preds2, lw, sw)
+    assert relerr(got_total, ref["total"].numpy()) < LOSS_TOL
