@@ -131,6 +131,28 @@ def test_infer_scales_and_shard_bounds():
         shard_bounds(8, 4, 4)
 
 
+def test_flow_call_surface_rejects_bad_inputs():
+    """FlowWarpMultiScale / multi_scale_like_flow / the flow losses refuse CPU tensors (no CPU path), wrong ranks and
+    flow sizes that do not divide the image -- with the reference's WrongInputException, before any kernel runs."""
+    import xptwarp
+    from xptwarp.flow_warping import infer_flow_scales
+    src = torch.zeros(2, 3, 32, 64, 3)
+    flows = [torch.zeros(2, 3, 32 // s, 64 // s, 2) for s in (4, 8)]
+    assert infer_flow_scales(32, flows) == [4, 8]
+    with pytest.raises(xptwarp.WrongInputException):
+        infer_flow_scales(32, [torch.zeros(2, 3, 5, 8, 2)])
+    with pytest.raises(xptwarp.WrongInputException):
+        xptwarp.FlowWarpMultiScale()(src, flows)                          # CPU tensors
+    with pytest.raises(xptwarp.WrongInputException):
+        xptwarp.FlowWarpMultiScale()(src[:, :, :, :, :2], flows)          # not RGB
+    with pytest.raises(xptwarp.WrongInputException):
+        xptwarp.multi_scale_like_flow(src[:, 0], flows)                   # CPU tensor
+    with pytest.raises(xptwarp.WrongInputException):
+        xptwarp.L2Regularizer(None)({"image5d": src}, None, None)          # no weights given
+    with pytest.raises(xptwarp.WrongInputException):
+        xptwarp.L2Regularizer([torch.zeros(3)])({"image5d": src}, None, None)   # CPU weights
+
+
 def _gloo_worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import torch.distributed as dist
