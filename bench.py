@@ -310,9 +310,25 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 2 * n_sets)):        # warm-up also captures one graph per input set
+    n_warm = max(args.warmup, 2 * n_sets)                # warm-up also captures one graph per input set
+    for i in range(n_warm):
         step(i)
     barrier()
+    # at least ~0.3 s of the same steps before the clock starts: a step is ~0.1 ms at config 2, and a device coming out
+    # of idle measured up to 8 % slow over the first few hundred of them.  The count is fixed from one timing on rank 0
+    # and broadcast, so every rank issues the same number of collectives.
+    t0 = time.perf_counter()
+    for i in range(20):
+        step(n_warm + i)
+    barrier()
+    per = max((time.perf_counter() - t0) / 20, 1e-6)
+    extra = torch.tensor([min(5000, int(0.3 / per))], dtype=torch.int64, device=device)
+    if dist is not None:
+        dist.broadcast(extra, src=0)
+    for i in range(int(extra.item())):
+        step(n_warm + 20 + i)
+    barrier()
+    n_warm += 20 + int(extra.item())
     launches_per_step = plan.launches()
 
     # ---- timed region A: K steps, device-timed on the launching stream ------------------------
@@ -467,7 +483,7 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 2 * n_sets), "ms_per_step": ms_step, "higher_is_better": True,
+            "warmup": n_warm, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: B={B}/gpu {H}x{W} snippet=5 (4 sources) scales=4 LOSS_RIGID_T1 fwd+bwd"
                                    + (" +dL/dsource" if args.source_grad else "")
