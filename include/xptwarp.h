@@ -87,6 +87,9 @@ typedef struct {
 #define XPT_FLAG_GRAPH 2u
 /* xpt_total_loss_host runs the batch as ONE chunk (no copy/compute pipelining).                */
 #define XPT_FLAG_NO_PIPELINE 4u
+/* xpt_total_loss uses the round-1 tile kernel (k_fused, one CTA per 64x13 tile) instead of the streaming strip
+ * kernel (k_strip) for training steps.  Same results; kept for A/B parity tests and profiling.               */
+#define XPT_FLAG_TILES 8u
 
 /* The snippet frames + intrinsics (features of losses.py:26-37).              */
 typedef struct {

@@ -1,0 +1,666 @@
+// xpt_strip.cuh -- the streaming strip kernel of the total-loss path (north-star kernels 1+2+3+4), round 2.
+//
+// Same arithmetic per sample as k_fused (xpt_fused.cuh), different machine mapping:
+//
+//   * work item ("piece") = rows [ya, yb) of one 64-column strip (60 centre columns + halo 2) of one
+//     (snippet, level).  A CTA owns a static, equal-cost list of pieces and MARCHES DOWN their rows; nothing is
+//     warped twice vertically (k_fused re-warped 39 % halo samples per 64x13 tile) and the list is cut so that every
+//     CTA of the grid carries the same number of row chunks (no partial last wave);
+//   * the CTA is a software pipeline of warp ROLES, one 32-lane warp per role instance, lane = 2 adjacent columns:
+//       L  loader      target rows (3 planes) + depth row -> shared-memory ring
+//       Y  warp        one per source: projection in packed FP32 (FFMA2, both columns per instruction), 2 x 4
+//                      16-byte gathers, bilinear value + Jacobian -> rings
+//       S  statistics  one per (source, channel): 3x3 window sums through warp shuffles (horizontal) and register
+//                      windows (vertical) -- no overlapping shared-memory re-reads --, SSIM + L1, the adjoint
+//                      coefficients, THEIR 3x3 box sums the same way, and dL/dS of one channel
+//       G  adjoint     one per source: contracts dL/dS with the cached Jacobian, projection adjoint, pose sums kept
+//                      in registers for the whole piece (one warp reduction per piece instead of one per tile row)
+//       O  output      sums dL/ddepth over the sources in a fixed order, edge-aware smoothness forward + backward
+//     role k works on row chunk (tick - lag_k); one CTA barrier per tick of 2 rows separates producers from
+//     consumers, every ring is indexed by the global row number, so the schedule is static and deadlock-free;
+//   * camera geometry comes from the ctx's own global buffers (geoK / geoT written by the pyramid launch), staged
+//     per piece into a few shared-memory words: no process-wide __constant__ block, no upload, no batch chunking.
+//
+// Citations: SURVEY.md Appendix A (reference synthesize_base.py:66-178, bilinear_interp.py:34-147,
+// loss_util.py:6-96, losses.py:147-154,386-440).
+#pragma once
+#include "xpt_fused.cuh"
+
+namespace xpt {
+
+constexpr int kSW = 64;                 // region columns of a strip (32 lanes x 2)
+constexpr int kSCWMax = 60;             // centre columns (halo 2 on both sides)
+constexpr int kSTRows = 8;              // ring rows: target/depth (L -> Y, S)
+constexpr int kSYRows = 4;              //            warped value (Y -> S)
+constexpr int kSJRows = 8;              //            Jacobian     (Y -> G)
+constexpr int kSGRows = 4;              //            dL/dS        (S -> G)
+constexpr int kSDRows = 4;              //            dL/ddepth    (G -> O)
+constexpr int kSJPlanes = 10;           // gu[3], gv[3], u, v, 1/den, D
+constexpr int kSLagY = 1, kSLagS = 2, kSLagG = 3, kSLagO = 4;   // ticks behind the loader
+
+struct StripPiece { int b, l, x0, cw, ya, yb, slot, nch; };     // nch = ceil((yb - ya + 4) / 2) row chunks
+struct StripCta { int first, count, chunks, pad; };
+
+struct StripArgs {
+  LevelTable lt;
+  int B, N, S;
+  const StripPiece* pieces;
+  const StripCta* ctas;
+  const float* geoK;                   // [B][S][18]
+  const float* geoT;                   // [B][N][12]
+  const float* depth[kMaxScales];
+  const float* disp[kMaxScales];
+  const float4* src4[kMaxScales];      // RGBx source levels [B,N,h,w]
+  int do_l1, do_ssim, do_smooth;
+  float norm_photo[kMaxScales];
+  float norm_sm_x[kMaxScales];
+  float norm_sm_y[kMaxScales];
+  float grad_factor;
+  float gcoef_l1, gcoef_ssim, gcoef_smooth;
+  float* loss_part; int slots_per_b;   // [B][slots][3]
+  float* pose_part;                    // [B][slots][N][12]
+  float* d_depth[kMaxScales];
+  float* d_disp[kMaxScales];
+};
+
+template <int NS>
+struct StripSmem {
+  static constexpr int T = 0;                                    // [4][8][64]: x0 x1 x2 depth
+  static constexpr int kY = 0;                                   // per source: [4][4][64] y0 y1 y2 notblack
+  static constexpr int kJ = kY + 4 * kSYRows * kSW;              //             [10][8][64]
+  static constexpr int kG = kJ + kSJPlanes * kSJRows * kSW;      //             [3][4][64]
+  static constexpr int kD = kG + 3 * kSGRows * kSW;              //             [4][64]
+  static constexpr int kSrc = kD + kSDRows * kSW;                // floats per source
+  static constexpr int src0 = T + 4 * kSTRows * kSW;
+  static constexpr int geo = src0 + NS * kSrc;                   // [NS][32]: K rows 0-1, inv K rows 0-1, [R|t]
+  static constexpr int loss = geo + NS * 32;                     // [2][3 NS][2]
+  static constexpr int kFloats = loss + 2 * 3 * NS * 2;
+  static constexpr size_t kBytes = sizeof(float) * kFloats;
+  static constexpr int kWarps = 1 + NS + 3 * NS + NS;
+  static constexpr int kThreads = 32 * kWarps;
+};
+
+__device__ __forceinline__ void strip_bar() { asm volatile("bar.sync 0;" ::: "memory"); }
+__device__ __forceinline__ void sts2(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float2 f2sub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+
+__device__ __forceinline__ StripPiece load_piece(const StripPiece* __restrict__ tab, int i) {
+  const int4* q = reinterpret_cast<const int4*>(tab + i);
+  const int4 a = __ldg(q), b = __ldg(q + 1);
+  StripPiece p;
+  p.b = a.x; p.l = a.y; p.x0 = a.z; p.cw = a.w; p.ya = b.x; p.yb = b.y; p.slot = b.z; p.nch = b.w;
+  return p;
+}
+
+// pixel rays of a column pair, the operation order of k_fused: fma(k0, x, k1*y) + k2
+__device__ __forceinline__ float2 ray_pair(float k0, float k1, float k2, float2 fx, float fy) {
+  return f2add(f2fma(f2s(k0), fx, f2s(k1 * fy)), f2s(k2));
+}
+
+// 1 / #in-image taps of the 3x3 window of a pixel whose row has cy and whose column has cx in-image neighbours
+__device__ __forceinline__ float strip_box_inv(int cy, int cx) { return (cy > 0 && cx > 0) ? box_inv(cy * cx) : 0.f; }
+__device__ __forceinline__ int strip_cnt(int g, int n) {      // in-image members of {g-1, g, g+1}; 0 when g is outside
+  return ((unsigned)g < (unsigned)n) ? (min(g + 1, n - 1) - max(g - 1, 0) + 1) : 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// L + O: loader of the target / depth rows, and the output stage (dL/ddepth over sources, smoothness)
+// ---------------------------------------------------------------------------------------------------------
+template <int NS, bool DERIVE>
+__device__ __forceinline__ void strip_role_lo(const StripArgs& a, float* smem, const int lane, const StripCta cta) {
+  using SM = StripSmem<NS>;
+  float* const T = smem + SM::T;
+  const int total = cta.chunks, pend = cta.first + cta.count;
+  int lpi = cta.first, lci = 0, opi = cta.first, oci = 0;
+  StripPiece lp = load_piece(a.pieces, lpi), op = lp;
+
+  // smoothness state of the output stage: the current row (the row whose outputs are due) and the vertical terms of
+  // the row above it
+  float tc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};      // target of the current row: (A.c0, A.c1, A.c2, B.c0, B.c1, B.c2)
+  float dc[2] = {0.f, 0.f};                          // disparity of the current row
+  float zc[2] = {0.f, 0.f};                          // DERIVE: its depth is not needed again (d disp/d depth = -disp^2)
+  float ty_up[2] = {0.f, 0.f};                       // gcy * sgn * w of the pair (row above, current row)
+  bool cur_in = false;                               // the current row lies inside the image
+  float lsum_sm = 0.f;
+  (void)zc;
+
+  for (int t = 0; t < total + kSLagO; ++t) {
+    // ---- L: rows of chunk t ------------------------------------------------------------------------------
+    if (t < total) {
+      const Level& L = a.lt.lv[lp.l];
+      const int H = L.H, W = L.W;
+      const float* const tg = L.tgt + (long long)lp.b * L.tgt_bs;
+      const float* const dp = a.depth[lp.l] + (long long)lp.b * H * W;
+      const int gx = lp.x0 - 2 + 2 * lane;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int s = 2 * t + r, gy = lp.ya - 2 + 2 * lci + r;
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f, v5 = 0.f, d0 = 0.f, d1 = 0.f;
+        if ((unsigned)gy < (unsigned)H) {
+          const long long o = (long long)gy * W + gx;
+          if ((unsigned)gx < (unsigned)W) { v0 = __ldg(tg + o * 3); v1 = __ldg(tg + o * 3 + 1); v2 = __ldg(tg + o * 3 + 2); d0 = __ldg(dp + o); }
+          if ((unsigned)(gx + 1) < (unsigned)W) { v3 = __ldg(tg + o * 3 + 3); v4 = __ldg(tg + o * 3 + 4); v5 = __ldg(tg + o * 3 + 5); d1 = __ldg(dp + o + 1); }
+        }
+        float* const q = T + (s & (kSTRows - 1)) * kSW + 2 * lane;
+        sts2(q, f2(v0, v3)); sts2(q + kSTRows * kSW, f2(v1, v4)); sts2(q + 2 * kSTRows * kSW, f2(v2, v5));
+        sts2(q + 3 * kSTRows * kSW, f2(d0, d1));
+      }
+      if (++lci == lp.nch) { lci = 0; if (++lpi < pend) lp = load_piece(a.pieces, lpi); }
+    }
+    // ---- O: rows of chunk t - 4 ---------------------------------------------------------------------------
+    const int co = t - kSLagO;
+    if (co >= 0) {
+      const Level& L = a.lt.lv[op.l];
+      const int H = L.H, W = L.W, Lr = op.yb - op.ya;
+      const float* const tg = L.tgt + (long long)op.b * L.tgt_bs;
+      const float* const dsrc = (DERIVE ? a.depth[op.l] : a.disp[op.l]);
+      const float* const dp = dsrc ? dsrc + (long long)op.b * H * W : nullptr;
+      const int gx = op.x0 - 2 + 2 * lane;
+      const float k3 = a.grad_factor;
+      const float nx = a.norm_sm_x[op.l], ny = a.norm_sm_y[op.l];
+      const float gcx = a.gcoef_smooth * nx, gcy = a.gcoef_smooth * ny;
+      const bool cen0 = 2 * lane >= 2 && 2 * lane < 2 + op.cw && gx < W;
+      const bool cen1 = 2 * lane + 1 >= 2 && 2 * lane + 1 < 2 + op.cw && gx + 1 < W;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int s = 2 * co + r, sg = 2 * oci + r;
+        const int gy = op.ya + sg - 4;                       // row whose outputs are due at this step
+        const bool out_row = sg >= 4 && sg < Lr + 4;
+        float gd0 = 0.f, gd1 = 0.f;                          // dL/ddisp of the smoothness term
+        if (a.do_smooth && sg >= 2 && sg < Lr + 4) {
+          // next row gy + 1
+          const int gn = gy + 1;
+          float tn[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dn[2] = {0.f, 0.f};
+          const bool nxt_in = (unsigned)gn < (unsigned)H;
+          if (nxt_in) {
+            const long long o = (long long)gn * W + gx;
+            if ((unsigned)gx < (unsigned)W) { tn[0] = __ldg(tg + o * 3); tn[1] = __ldg(tg + o * 3 + 1); tn[2] = __ldg(tg + o * 3 + 2); dn[0] = __ldg(dp + o); }
+            if ((unsigned)(gx + 1) < (unsigned)W) { tn[3] = __ldg(tg + o * 3 + 3); tn[4] = __ldg(tg + o * 3 + 4); tn[5] = __ldg(tg + o * 3 + 5); dn[1] = __ldg(dp + o + 1); }
+            if (DERIVE) {
+#pragma unroll
+              for (int k = 0; k < 2; ++k) dn[k] = dn[k] > 0.00001f ? __frcp_rn(dn[k]) : 0.f;   // safe_reciprocal_number
+            }
+          }
+          if (sg >= 3) {
+            // vertical pairs (current row, next row) of both columns
+            float ty[2] = {0.f, 0.f}, sdy[2] = {0.f, 0.f};
+            if (cur_in && nxt_in) {
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                float e = 0.f;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) e += fabsf((tc[3 * k + c] - tn[3 * k + c]) * k3);
+                const float w = expf(-(e * (1.f / 3.f)));
+                const float sd = (dc[k] - dn[k]) * w;
+                sdy[k] = sd;
+                ty[k] = gcy * sgnf(sd) * w;
+              }
+            }
+            // horizontal pairs of the current row: (A, B) inside the lane, (B, right lane's A) across lanes
+            float rt[3], rd;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) rt[c] = __shfl_down_sync(0xffffffffu, tc[c], 1);
+            rd = __shfl_down_sync(0xffffffffu, dc[0], 1);
+            float txA = 0.f, txB = 0.f, sdxA = 0.f, sdxB = 0.f;
+            if (cur_in) {
+              if ((unsigned)gx < (unsigned)W && gx + 1 < W) {
+                float e = 0.f;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) e += fabsf((tc[c] - tc[3 + c]) * k3);
+                const float w = expf(-(e * (1.f / 3.f)));
+                sdxA = (dc[0] - dc[1]) * w;
+                txA = gcx * sgnf(sdxA) * w;
+              }
+              if (gx + 1 >= 0 && gx + 2 < W && lane < 31) {
+                float e = 0.f;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) e += fabsf((tc[3 + c] - rt[c]) * k3);
+                const float w = expf(-(e * (1.f / 3.f)));
+                sdxB = (dc[1] - rd) * w;
+                txB = gcx * sgnf(sdxB) * w;
+              }
+            }
+            const float txL = __shfl_up_sync(0xffffffffu, txB, 1);       // pair (left lane's B, A)
+            if (out_row) {
+              // losses.py:409-440: forward terms of the pairs a pixel starts, gradient of all four pairs it is part of
+              if (cen0) lsum_sm += fabsf(sdxA) * nx + fabsf(sdy[0]) * ny;
+              if (cen1) lsum_sm += fabsf(sdxB) * nx + fabsf(sdy[1]) * ny;
+              gd0 = txA; gd0 += ty[0]; gd0 -= (lane > 0 ? txL : 0.f); gd0 -= ty_up[0];
+              gd1 = txB; gd1 += ty[1]; gd1 -= txA; gd1 -= ty_up[1];
+            }
+            ty_up[0] = ty[0]; ty_up[1] = ty[1];
+          }
+          if (out_row) { zc[0] = dc[0]; zc[1] = dc[1]; }
+          // advance: next -> current (after the outputs of this row used dc)
+          if (!out_row || true) {
+            // dc of the output row is still needed below for DERIVE: keep it in zc
+          }
+#pragma unroll
+          for (int k = 0; k < 6; ++k) tc[k] = tn[k];
+          dc[0] = dn[0]; dc[1] = dn[1];
+          cur_in = nxt_in;
+        }
+        if (out_row) {
+          float g0 = 0.f, g1 = 0.f;
+          if (DERIVE && a.do_smooth) { g0 = -(gd0 * zc[0]) * zc[0]; g1 = -(gd1 * zc[1]) * zc[1]; }
+#pragma unroll
+          for (int n = 0; n < NS; ++n)
+            if (n < a.N) {
+              const float2 v = lds2(smem + SM::src0 + n * SM::kSrc + SM::kD + ((s - 2) & (kSDRows - 1)) * kSW + 2 * lane);
+              g0 += v.x; g1 += v.y;
+            }
+          const long long o = (long long)op.b * H * W + (long long)gy * W + gx;
+          if (a.d_depth[op.l]) {
+            if (cen0) a.d_depth[op.l][o] = g0;
+            if (cen1) a.d_depth[op.l][o + 1] = g1;
+          }
+          if (!DERIVE && a.do_smooth && a.d_disp[op.l]) {
+            if (cen0) a.d_disp[op.l][o] = gd0;
+            if (cen1) a.d_disp[op.l][o + 1] = gd1;
+          }
+        }
+      }
+      if (++oci == op.nch) {
+        // ---- piece done: loss partial record (S warps left their sums two ticks ago) -------------------------
+        const float sm = warp_sum(lsum_sm);
+        if (lane == 0) {
+          const float* lb = smem + SM::loss + (opi & 1) * (3 * NS * 2);
+          float l1 = 0.f, ss = 0.f;
+          for (int k = 0; k < 3 * NS; ++k)
+            if (k < 3 * a.N) { l1 += lb[2 * k]; ss += lb[2 * k + 1]; }
+          float* out = a.loss_part + ((size_t)op.b * a.slots_per_b + op.slot) * 3;
+          out[0] = l1 * a.norm_photo[op.l]; out[1] = ss * a.norm_photo[op.l]; out[2] = sm;
+        }
+        lsum_sm = 0.f; oci = 0;
+        ty_up[0] = ty_up[1] = 0.f; cur_in = false;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) tc[k] = 0.f;
+        dc[0] = dc[1] = 0.f;
+        if (++opi < pend) op = load_piece(a.pieces, opi);
+      }
+    }
+    strip_bar();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Y: inverse warp of one source, one region row per step, two adjacent columns per lane
+// ---------------------------------------------------------------------------------------------------------
+struct StripSample {
+  float2 yxy; float yz;          // warped value
+  float2 guxy; float guz;        // dS/du
+  float2 gvxy; float gvz;        // dS/dv
+  float su, sv, si;              // u, v, 1/den (0 when invalid)
+};
+
+template <int NS>
+__device__ __forceinline__ void strip_role_y(const StripArgs& a, float* smem, const int lane, const int n,
+                                             const StripCta cta) {
+  using SM = StripSmem<NS>;
+  const float* const T = smem + SM::T;
+  float* const Yr = smem + SM::src0 + n * SM::kSrc + SM::kY;
+  float* const Jr = smem + SM::src0 + n * SM::kSrc + SM::kJ;
+  float* const geo = smem + SM::geo + n * 32;
+  const int total = cta.chunks, pend = cta.first + cta.count;
+  const bool live = n < a.N;
+  int pi = cta.first, ci = 0;
+  StripPiece p = load_piece(a.pieces, pi);
+  bool fresh = true;
+
+  for (int t = 0; t < total + kSLagO; ++t) {
+    const int c = t - kSLagY;
+    if (live && c >= 0 && c < total) {
+      const Level& L = a.lt.lv[p.l];
+      const int H = L.H, W = L.W;
+      if (fresh) {
+        // camera geometry of this piece -> 24 shared-memory words of this warp (K rows 0-1, inv K rows 0-1, [R|t])
+        __syncwarp();
+        if (lane < 6) geo[lane] = __ldg(a.geoK + (size_t)(p.b * a.S + p.l) * kGeoK + lane);
+        else if (lane < 12) geo[lane] = __ldg(a.geoK + (size_t)(p.b * a.S + p.l) * kGeoK + 9 + (lane - 6));
+        else if (lane < 24) geo[lane] = __ldg(a.geoT + (size_t)(p.b * a.N + n) * kGeoT + (lane - 12));
+        __syncwarp();
+        fresh = false;
+      }
+      const float4* const img4 = a.src4[p.l] + (size_t)(p.b * a.N + n) * H * W;
+      const float fx0 = (float)(p.x0 - 2 + 2 * lane);
+      const float2 fx = f2(fx0, fx0 + 1.f);
+      const float wlim = (float)(W - 2), hlim = (float)(H - 2);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int s = 2 * c + r, sg = 2 * ci + r;
+        const float fy = (float)(p.ya - 2 + sg);
+        const float2 D = lds2(T + (3 * kSTRows + (s & (kSTRows - 1))) * kSW + 2 * lane);
+        // ---- projection, both columns per instruction (reference order) -------------------------
+        float2 pu, pv, inv;
+        {
+          const float4 gA = lds4(geo), gB = lds4(geo + 4), gC = lds4(geo + 8);      // K0..K5 | Ki0..Ki5
+          const float4 tA = lds4(geo + 12), tB = lds4(geo + 16), tC = lds4(geo + 20); // R (9), t (3)
+          const float2 r0 = ray_pair(gB.z, gB.w, gC.x, fx, fy);
+          const float2 r1 = ray_pair(gC.y, gC.z, gC.w, fx, fy);
+          const float2 X0 = f2mul(r0, D), X1 = f2mul(r1, D);
+          const float2 Y0 = f2add(f2fma(f2s(tA.z), D, f2fma(f2s(tA.x), X0, f2mul(f2s(tA.y), X1))), f2s(tC.y));
+          const float2 Y1 = f2add(f2fma(f2s(tB.y), D, f2fma(f2s(tA.w), X0, f2mul(f2s(tB.x), X1))), f2s(tC.z));
+          const float2 Y2 = f2add(f2fma(f2s(tC.x), D, f2fma(f2s(tB.z), X0, f2mul(f2s(tB.w), X1))), f2s(tC.w));
+          const float2 p0 = f2fma(f2s(gA.z), Y2, f2fma(f2s(gA.x), Y0, f2mul(f2s(gA.y), Y1)));
+          const float2 p1 = f2fma(f2s(gB.y), Y2, f2fma(f2s(gA.w), Y0, f2mul(f2s(gB.x), Y1)));
+          const float2 den = f2add(Y2, f2s(1e-10f));
+          // perspective divide: one reciprocal per column, refined once, Markstein correction of both quotients
+          float ra, rb;
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(den.x));
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rb) : "f"(den.y));
+          const float2 nden = f2neg(den);
+          float2 rr = f2(ra, rb);
+          rr = f2fma(f2fma(nden, rr, f2s(1.f)), rr, rr);
+          const float2 q0 = f2mul(p0, rr), q1 = f2mul(p1, rr);
+          pu = f2fma(f2fma(nden, q0, p0), rr, q0);
+          pv = f2fma(f2fma(nden, q1, p1), rr, q1);
+          inv = rr;
+        }
+        // ---- taps of both columns, then all eight 16-byte gathers, then the bilinear value + Jacobian ---------
+        const float us[2] = {pu.x, pu.y}, vs[2] = {pv.x, pv.y}, Ds[2] = {D.x, D.y}, is[2] = {inv.x, inv.y};
+        float wuf[2], wuc[2], wvf[2], wvc[2];
+        bool val[2];
+        float4 t0[2], t1[2], t2[2], t3[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const float uf = floorf(us[k]), vf = floorf(vs[k]);
+          // valid <=> 0 <= floor(u) <= W-2 and 0 <= floor(v) <= H-2 and D != 0 (bilinear_interp.py:53-76); NaN -> false
+          val[k] = (uf >= 0.f) && (uf <= wlim) && (vf >= 0.f) && (vf <= hlim) && (Ds[k] != 0.f);
+          const int iu = val[k] ? (int)uf : 0, iv = val[k] ? (int)vf : 0;
+          // weights * valid_mask (bilinear_interp.py:100): an invalid sample gathers texel (0,0) with zero weights
+          wuf[k] = val[k] ? (uf + 1.f) - us[k] : 0.f;
+          wuc[k] = val[k] ? us[k] - uf : 0.f;
+          wvf[k] = val[k] ? (vf + 1.f) - vs[k] : 0.f;
+          wvc[k] = val[k] ? vs[k] - vf : 0.f;
+          const float4* tp = img4 + (iv * W + iu);
+          t0[k] = __ldg(tp); t2[k] = __ldg(tp + 1); t1[k] = __ldg(tp + W); t3[k] = __ldg(tp + W + 1);
+        }
+        StripSample o[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          // I0 = (vf,uf), I1 = (vc,uf), I2 = (vf,uc), I3 = (vc,uc)   (bilinear_interp.py:125-128)
+          const float w0 = wuf[k] * wvf[k], w1 = wuf[k] * wvc[k], w2 = wuc[k] * wvf[k], w3 = wuc[k] * wvc[k];
+          const float2 a0 = f2(t0[k].x, t0[k].y), a1 = f2(t1[k].x, t1[k].y), a2 = f2(t2[k].x, t2[k].y), a3 = f2(t3[k].x, t3[k].y);
+          o[k].yxy = f2fma(a3, f2s(w3), f2fma(a2, f2s(w2), f2fma(a0, f2s(w0), f2mul(a1, f2s(w1)))));
+          o[k].yz = fmaf(t3[k].z, w3, fmaf(t2[k].z, w2, fmaf(t0[k].z, w0, t1[k].z * w1)));
+          const float2 d20 = f2sub(a2, a0), d31 = f2sub(a3, a1), d10 = f2sub(a1, a0), d32 = f2sub(a3, a2);
+          o[k].guxy = f2fma(f2s(wvf[k]), d20, f2mul(f2s(wvc[k]), d31));
+          o[k].gvxy = f2fma(f2s(wuf[k]), d10, f2mul(f2s(wuc[k]), d32));
+          o[k].guz = fmaf(wvf[k], t2[k].z - t0[k].z, wvc[k] * (t3[k].z - t1[k].z));
+          o[k].gvz = fmaf(wuf[k], t1[k].z - t0[k].z, wuc[k] * (t3[k].z - t2[k].z));
+          o[k].su = val[k] ? us[k] : 0.f; o[k].sv = val[k] ? vs[k] : 0.f; o[k].si = val[k] ? is[k] : 0.f;
+        }
+        // ---- rings ------------------------------------------------------------------------------------------
+        {
+          float* const q = Yr + (s & (kSYRows - 1)) * kSW + 2 * lane;
+          sts2(q, f2(o[0].yxy.x, o[1].yxy.x));
+          sts2(q + kSYRows * kSW, f2(o[0].yxy.y, o[1].yxy.y));
+          sts2(q + 2 * kSYRows * kSW, f2(o[0].yz, o[1].yz));
+          // mean_c(synth) == 0 marks an invalid pixel for the losses (loss_util.py:15-16)
+          const float nb0 = (((o[0].yxy.x + o[0].yxy.y) + o[0].yz) == 0.f) ? 0.f : 1.f;
+          const float nb1 = (((o[1].yxy.x + o[1].yxy.y) + o[1].yz) == 0.f) ? 0.f : 1.f;
+          sts2(q + 3 * kSYRows * kSW, f2(nb0, nb1));
+          float* const j = Jr + (s & (kSJRows - 1)) * kSW + 2 * lane;
+          constexpr int JP = kSJRows * kSW;
+          sts2(j, f2(o[0].guxy.x, o[1].guxy.x));
+          sts2(j + JP, f2(o[0].guxy.y, o[1].guxy.y));
+          sts2(j + 2 * JP, f2(o[0].guz, o[1].guz));
+          sts2(j + 3 * JP, f2(o[0].gvxy.x, o[1].gvxy.x));
+          sts2(j + 4 * JP, f2(o[0].gvxy.y, o[1].gvxy.y));
+          sts2(j + 5 * JP, f2(o[0].gvz, o[1].gvz));
+          sts2(j + 6 * JP, f2(o[0].su, o[1].su));
+          sts2(j + 7 * JP, f2(o[0].sv, o[1].sv));
+          sts2(j + 8 * JP, f2(o[0].si, o[1].si));
+          sts2(j + 9 * JP, D);
+        }
+      }
+      if (++ci == p.nch) { ci = 0; fresh = true; if (++pi < pend) p = load_piece(a.pieces, pi); }
+    }
+    strip_bar();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// S: window statistics, SSIM + L1, adjoint coefficients and their box sums for one (source, channel)
+// ---------------------------------------------------------------------------------------------------------
+struct Win2 {        // sliding 3-row window of a row quantity h: sum(h[r-2], h[r-1], h[r]) in the order ((a + b) + c)
+  float2 p1, p2;     // p1 = h[r-1], p2 = h[r-2] + h[r-1]
+  __device__ __forceinline__ float2 push(float2 h) {
+    const float2 v = f2add(p2, h);
+    p2 = f2add(p1, h); p1 = h;
+    return v;
+  }
+  __device__ __forceinline__ void clear() { p1 = f2s(0.f); p2 = f2s(0.f); }
+};
+
+// horizontal 3-sums of a row quantity held as one column pair per lane: (left + q.x + q.y, q.x + q.y + right)
+__device__ __forceinline__ float2 hsum_nb(float2 q, float2 lr) { return f2add(lr, f2s(q.x + q.y)); }
+__device__ __forceinline__ float2 shfl_lr(float2 q) {   // (right column of the left lane, left column of the right lane)
+  return f2(__shfl_up_sync(0xffffffffu, q.y, 1), __shfl_down_sync(0xffffffffu, q.x, 1));
+}
+
+template <int NS>
+__device__ __forceinline__ void strip_role_s(const StripArgs& a, float* smem, const int lane, const int n, const int ch,
+                                             const StripCta cta) {
+  using SM = StripSmem<NS>;
+  const float* const Tx = smem + SM::T + ch * kSTRows * kSW;
+  const float* const Yc = smem + SM::src0 + n * SM::kSrc + SM::kY + ch * kSYRows * kSW;
+  const float* const Ynb = smem + SM::src0 + n * SM::kSrc + SM::kY + 3 * kSYRows * kSW;
+  float* const Gc = smem + SM::src0 + n * SM::kSrc + SM::kG + ch * kSGRows * kSW;
+  const int total = cta.chunks, pend = cta.first + cta.count;
+  const bool live = n < a.N;
+  int pi = cta.first, ci = 0;
+  StripPiece p = load_piece(a.pieces, pi);
+
+  Win2 wy, wyy, wxy, wx, wxx, wA, wB, wC;
+  wy.clear(); wyy.clear(); wxy.clear(); wx.clear(); wxx.clear(); wA.clear(); wB.clear(); wC.clear();
+  float2 y1 = f2s(0.f), x1 = f2s(0.f), nb1 = f2s(0.f);       // row sg-1
+  float2 y2 = f2s(0.f), x2 = f2s(0.f), l1t2 = f2s(0.f);      // row sg-2
+  float2 ls_l1 = f2s(0.f), ls_ss = f2s(0.f);
+
+  for (int t = 0; t < total + kSLagO; ++t) {
+    const int c = t - kSLagS;
+    if (live && c >= 0 && c < total) {
+      const Level& L = a.lt.lv[p.l];
+      const int H = L.H, W = L.W, Lr = p.yb - p.ya;
+      const int gx = p.x0 - 2 + 2 * lane;
+      // per-lane column constants of this piece
+      const int cx0 = strip_cnt(gx, W), cx1 = strip_cnt(gx + 1, W);
+      const float2 ic3 = f2(strip_box_inv(3, cx0), strip_box_inv(3, cx1));
+      const float2 ic2 = f2(strip_box_inv(2, cx0), strip_box_inv(2, cx1));
+      const float2 cen = f2((2 * lane >= 2 && 2 * lane < 2 + p.cw && gx < W) ? 1.f : 0.f,
+                            (2 * lane + 1 >= 2 && 2 * lane + 1 < 2 + p.cw && gx + 1 < W) ? 1.f : 0.f);
+      const float cl1 = a.gcoef_l1 * a.norm_photo[p.l];
+      const float hss2 = -a.gcoef_ssim * a.norm_photo[p.l];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int s = 2 * c + r, sg = 2 * ci + r;
+        const float2 y = lds2(Yc + (s & (kSYRows - 1)) * kSW + 2 * lane);
+        const float2 nb = lds2(Ynb + (s & (kSYRows - 1)) * kSW + 2 * lane);
+        const float2 x = lds2(Tx + (s & (kSTRows - 1)) * kSW + 2 * lane);
+        float2 g = f2s(0.f);
+        if (a.do_ssim) {
+          // ---- row sums of y, y^2, xy, x, x^2 over columns (c-1, c, c+1) -------------------------------------
+          const float2 yn = shfl_lr(y), xn = shfl_lr(x);
+          const float2 hy = hsum_nb(y, yn), hx = hsum_nb(x, xn);
+          const float2 hyy = hsum_nb(f2mul(y, y), f2mul(yn, yn));
+          const float2 hxy = hsum_nb(f2mul(x, y), f2mul(xn, yn));
+          const float2 hxx = hsum_nb(f2mul(x, x), f2mul(xn, xn));
+          const float2 Vy = wy.push(hy), Vyy = wyy.push(hyy), Vxy = wxy.push(hxy), Vx = wx.push(hx), Vxx = wxx.push(hxx);
+          // ---- statistics row sg-1 (image row gy1): SSIM, loss, adjoint coefficients (loss_util.py:52-96) ---------
+          const int gy1 = p.ya - 2 + sg - 1;
+          const int cy = strip_cnt(gy1, H);
+          const float2 ic = cy == 3 ? ic3 : (cy == 2 ? ic2 : f2s(0.f));
+          const bool row_c = sg - 1 >= 2 && sg - 1 < Lr + 2;            // a centre row of this piece
+          const float2 mux = f2mul(Vx, ic), mux2 = f2mul(mux, mux);
+          const float2 MUX2C = f2add(mux2, f2s(kC1));
+          const float2 SGXC = f2add(f2fma(Vxx, ic, f2neg(mux2)), f2s(kC2));
+          const float2 muy = f2mul(Vy, ic), muy2 = f2mul(muy, muy), mxy = f2mul(mux, muy);
+          const float2 sgy = f2fma(Vyy, ic, f2neg(muy2));
+          const float2 sgxy = f2fma(Vxy, ic, f2neg(mxy));
+          const float2 a1 = f2fma(f2s(2.f), mxy, f2s(kC1));
+          const float2 a2 = f2fma(f2s(2.f), sgxy, f2s(kC2));
+          const float2 b1 = f2add(MUX2C, muy2);
+          const float2 b2 = f2add(SGXC, sgy);
+          const float2 den = f2mul(b1, b2);
+          const float2 r12 = f2(rcp_nr(den.x), rcp_nr(den.y));
+          const float2 ssim = f2mul(f2mul(a1, a2), r12);
+          const float2 lv = f2fma(f2s(-0.5f), ssim, f2s(0.5f));
+          const float lc0 = fminf(fmaxf(lv.x, 0.f), 1.f), lc1 = fminf(fmaxf(lv.y, 0.f), 1.f);
+          const float2 cnt_w = row_c ? f2mul(cen, nb1) : f2s(0.f);
+          ls_ss = f2fma(cnt_w, f2(lc0, lc1), ls_ss);
+          // clip_by_value passes the gradient inside [0,1]; Hh = 2 h / (#taps b1 b2), h = dTotal/d ssim
+          const float2 hlive = f2mul(f2mul(ic, f2s(hss2)), nb1);
+          const float2 Hh = f2mul(f2(lc0 == lv.x ? hlive.x : 0.f, lc1 == lv.y ? hlive.y : 0.f), r12);
+          const float2 Hs = f2mul(Hh, ssim);
+          const float2 t1 = f2mul(mux, f2add(a2, f2neg(a1)));
+          const float2 t2 = f2mul(muy, f2add(b2, f2neg(b1)));
+          const float2 Av = f2fma(Hh, t1, f2neg(f2mul(Hs, t2)));
+          const float2 Bv = f2mul(f2neg(Hs), b1);              // 2 dL/dP(y^2)
+          const float2 Cv = f2mul(Hh, a1);
+          // ---- 3x3 box sums of the coefficients (adjoint of the SAME-padded mean) -> dL/dS of row sg-2 -----------
+          const float2 sa = wA.push(hsum_nb(Av, shfl_lr(Av)));
+          const float2 sb = wB.push(hsum_nb(Bv, shfl_lr(Bv)));
+          const float2 sc = wC.push(hsum_nb(Cv, shfl_lr(Cv)));
+          g = f2fma(y2, sb, f2fma(x2, sc, sa));
+        }
+        // ---- L1 (loss_util.py:6-25): loss of row sg-1, gradient term of row sg-2 ------------------------------
+        if (a.do_l1) {
+          const bool row_c = sg - 1 >= 2 && sg - 1 < Lr + 2;
+          const float2 cnt_w = row_c ? f2mul(cen, nb1) : f2s(0.f);
+          const float2 d1 = f2sub(y1, x1);
+          ls_l1 = f2fma(cnt_w, f2(fabsf(d1.x), fabsf(d1.y)), ls_l1);
+          g = f2add(g, l1t2);
+          const float2 nbc = f2mul(nb1, f2s(cl1));
+          l1t2 = f2(d1.x == 0.f ? 0.f : copysignf(nbc.x, d1.x), d1.y == 0.f ? 0.f : copysignf(nbc.y, d1.y));
+        }
+        sts2(Gc + ((s - 2) & (kSGRows - 1)) * kSW + 2 * lane, g);
+        y2 = y1; x2 = x1; y1 = y; x1 = x; nb1 = nb;
+      }
+      if (++ci == p.nch) {
+        // piece done: loss sums of this (source, channel) -> scratch of the output stage; windows restart
+        const float v0 = warp_sum(ls_l1.x + ls_l1.y), v1 = warp_sum(ls_ss.x + ls_ss.y);
+        if (lane == 0) {
+          float* lb = smem + SM::loss + (pi & 1) * (3 * NS * 2) + (n * 3 + ch) * 2;
+          lb[0] = v0; lb[1] = v1;
+        }
+        ls_l1 = f2s(0.f); ls_ss = f2s(0.f);
+        wy.clear(); wyy.clear(); wxy.clear(); wx.clear(); wxx.clear(); wA.clear(); wB.clear(); wC.clear();
+        y1 = x1 = nb1 = y2 = x2 = l1t2 = f2s(0.f);
+        ci = 0;
+        if (++pi < pend) p = load_piece(a.pieces, pi);
+      }
+    }
+    strip_bar();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// G: dL/dS x Jacobian -> projection adjoint: dL/ddepth per pixel, dL/dR, dL/dt sums per piece
+// ---------------------------------------------------------------------------------------------------------
+template <int NS>
+__device__ __forceinline__ void strip_role_g(const StripArgs& a, float* smem, const int lane, const int n,
+                                             const StripCta cta) {
+  using SM = StripSmem<NS>;
+  const float* const Jr = smem + SM::src0 + n * SM::kSrc + SM::kJ;
+  const float* const Gr = smem + SM::src0 + n * SM::kSrc + SM::kG;
+  float* const Dr = smem + SM::src0 + n * SM::kSrc + SM::kD;
+  const int total = cta.chunks, pend = cta.first + cta.count;
+  const bool live = n < a.N;
+  int pi = cta.first, ci = 0;
+  StripPiece p = load_piece(a.pieces, pi);
+  bool fresh = true;
+  float gk[6], ki[6], gt[9];
+  float2 acc[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) acc[k] = f2s(0.f);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { gk[k] = 0.f; ki[k] = 0.f; }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) gt[k] = 0.f;
+
+  for (int t = 0; t < total + kSLagO; ++t) {
+    const int c = t - kSLagG;
+    if (live && c >= 0 && c < total) {
+      const Level& L = a.lt.lv[p.l];
+      const int W = L.W, Lr = p.yb - p.ya;
+      if (fresh) {
+        const float* K = a.geoK + (size_t)(p.b * a.S + p.l) * kGeoK;
+        const float* Tt = a.geoT + (size_t)(p.b * a.N + n) * kGeoT;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { gk[k] = __ldg(K + k); ki[k] = __ldg(K + 9 + k); }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) gt[k] = __ldg(Tt + k);
+        fresh = false;
+      }
+      const int gx = p.x0 - 2 + 2 * lane;
+      const float fx0 = (float)gx;
+      const float2 fx = f2(fx0, fx0 + 1.f);
+      const float2 cen = f2((2 * lane >= 2 && 2 * lane < 2 + p.cw && gx < W) ? 1.f : 0.f,
+                            (2 * lane + 1 >= 2 && 2 * lane + 1 < 2 + p.cw && gx + 1 < W) ? 1.f : 0.f);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int s = 2 * c + r, sg = 2 * ci + r;
+        if (sg >= 4 && sg < Lr + 4) {                 // centre row sg-4 of the piece = region row sg-2
+          const int kg = ((s - 2) & (kSGRows - 1)) * kSW + 2 * lane;
+          const int kj = ((s - 2) & (kSJRows - 1)) * kSW + 2 * lane;
+          constexpr int GP = kSGRows * kSW, JP = kSJRows * kSW;
+          const float2 g0 = f2mul(lds2(Gr + kg), cen), g1 = f2mul(lds2(Gr + GP + kg), cen), g2 = f2mul(lds2(Gr + 2 * GP + kg), cen);
+          const float2 gu2 = f2fma(g2, lds2(Jr + 2 * JP + kj), f2fma(g1, lds2(Jr + JP + kj), f2mul(g0, lds2(Jr + kj))));
+          const float2 gv2 = f2fma(g2, lds2(Jr + 5 * JP + kj), f2fma(g1, lds2(Jr + 4 * JP + kj), f2mul(g0, lds2(Jr + 3 * JP + kj))));
+          const float2 U = lds2(Jr + 6 * JP + kj), V = lds2(Jr + 7 * JP + kj), I = lds2(Jr + 8 * JP + kj), D = lds2(Jr + 9 * JP + kj);
+          // samples without a valid warp cached zero Jacobians and 1/den = 0: exact zeros below
+          const float2 gp0 = f2mul(gu2, I), gp1 = f2mul(gv2, I);
+          const float2 gp2 = f2mul(f2neg(f2fma(gv2, V, f2mul(gu2, U))), I);
+          const float fy = (float)(p.ya + sg - 4);
+          const float2 r0 = ray_pair(ki[0], ki[1], ki[2], fx, fy);
+          const float2 r1 = ray_pair(ki[3], ki[4], ki[5], fx, fy);
+          const float2 X0 = f2mul(r0, D), X1 = f2mul(r1, D);
+          // dL/dY = K_s^T dL/dp (last row of K_s is (0,0,1))
+          const float2 gY0 = f2fma(f2s(gk[0]), gp0, f2mul(f2s(gk[3]), gp1));
+          const float2 gY1 = f2fma(f2s(gk[1]), gp0, f2mul(f2s(gk[4]), gp1));
+          const float2 gY2 = f2add(f2fma(f2s(gk[2]), gp0, f2mul(f2s(gk[5]), gp1)), gp2);
+          acc[0] = f2fma(gY0, X0, acc[0]); acc[1] = f2fma(gY0, X1, acc[1]); acc[2] = f2fma(gY0, D, acc[2]);
+          acc[3] = f2fma(gY1, X0, acc[3]); acc[4] = f2fma(gY1, X1, acc[4]); acc[5] = f2fma(gY1, D, acc[5]);
+          acc[6] = f2fma(gY2, X0, acc[6]); acc[7] = f2fma(gY2, X1, acc[7]); acc[8] = f2fma(gY2, D, acc[8]);
+          acc[9] = f2add(acc[9], gY0); acc[10] = f2add(acc[10], gY1); acc[11] = f2add(acc[11], gY2);
+          // dL/dX = R^T dL/dY, dL/dD = ray . dL/dX
+          const float2 gX0 = f2fma(f2s(gt[6]), gY2, f2fma(f2s(gt[0]), gY0, f2mul(f2s(gt[3]), gY1)));
+          const float2 gX1 = f2fma(f2s(gt[7]), gY2, f2fma(f2s(gt[1]), gY0, f2mul(f2s(gt[4]), gY1)));
+          const float2 gX2 = f2fma(f2s(gt[8]), gY2, f2fma(f2s(gt[2]), gY0, f2mul(f2s(gt[5]), gY1)));
+          const float2 gD = f2add(f2fma(gX0, r0, f2mul(gX1, r1)), gX2);
+          sts2(Dr + ((s - 2) & (kSDRows - 1)) * kSW + 2 * lane, gD);
+        }
+      }
+      if (++ci == p.nch) {
+        // piece done: 12 pose sums of (b, n) -> one partial record
+        float v[16];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) { v[k] = acc[k].x + acc[k].y; acc[k] = f2s(0.f); }
+        v[12] = v[13] = v[14] = v[15] = 0.f;
+        const float tot = warp_reduce16(v, lane);
+        const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+        if ((lane & 1) == 0 && idx < 12)
+          a.pose_part[(((size_t)p.b * a.slots_per_b + p.slot) * a.N + n) * 12 + idx] = tot;
+        ci = 0; fresh = true;
+        if (++pi < pend) p = load_piece(a.pieces, pi);
+      }
+    }
+    strip_bar();
+  }
+}
+
+template <int NS, bool DERIVE>
+__global__ void __launch_bounds__(StripSmem<NS>::kThreads, NS == 1 ? 3 : 1) k_strip(const __grid_constant__ StripArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const StripCta cta = a.ctas[blockIdx.x];
+  if (cta.count == 0) return;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (wid == 0) strip_role_lo<NS, DERIVE>(a, smem, lane, cta);
+  else if (wid <= NS) strip_role_y<NS>(a, smem, lane, wid - 1, cta);
+  else if (wid <= 4 * NS) strip_role_s<NS>(a, smem, lane, (wid - NS - 1) / 3, (wid - NS - 1) % 3, cta);
+  else strip_role_g<NS>(a, smem, lane, wid - 4 * NS - 1, cta);
+}
+
+}  // namespace xpt

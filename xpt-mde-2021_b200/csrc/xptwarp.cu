@@ -15,6 +15,7 @@
 
 #include "xpt_kernels.cuh"
 #include "xpt_fused.cuh"
+#include "xpt_strip.cuh"
 #include "xpt_flow.cuh"
 #include "xpt_minloss.cuh"
 
@@ -83,6 +84,10 @@ struct xpt_ctx {
   float* tgt0_copy;             // unused unless a level-0 copy is wanted without a user buffer
   float* min_part;              // [B][S * full-res tiles] partial sums of xpt_photometric_min_loss
   float* l2_part;               // block partials (doubles) of xpt_l2_regularizer
+  // streaming strip kernel (k_strip): static equal-cost partition of the (snippet, level, strip) rows over the grid
+  StripPiece* strip_pieces; StripCta* strip_ctas;
+  int strip_nctas, strip_slots, strip_ns; bool strip_ready;
+  float* strip_loss_part; float* strip_pose_part;
   float* c_geo_dev;             // device address of the constant-bank geometry block (c_geo)
   bool geo_direct;              // this call's geometry is produced straight into c_geo (no staging copy)
   // staging for the host-buffer entry point
@@ -476,6 +481,119 @@ int launch_fused(xpt_ctx* ctx, FusedArgs& a, cudaStream_t st) {
   }
   if (prof) { XPT_CUDA(cudaEventRecord((*ctx->prof_events)[2 * ctx->prof_count + 1], st)); ++ctx->prof_count; }
   return XPT_OK;
+}
+
+// ---- streaming strip kernel ---------------------------------------------------------------------------------
+// Static partition: the rows of every (level, snippet, strip) are laid end to end (large levels first) and cut into
+// `nctas` runs of equal cost, cost = row chunks of 2 rows incl. the 4 halo rows a piece re-warps.  A cut inside a
+// strip makes two pieces.  Partial-sum slots are numbered per snippet; unused slots stay zero for the ctx's life.
+template <int NS, bool DERIVE>
+int strip_grid(int device, int* ctas_per_sm) {
+  static unsigned long long attr_done = 0;
+  XPT_TRY(ensure_dyn_smem(k_strip<NS, DERIVE>, StripSmem<NS>::kBytes, device, &attr_done));
+  int n = 0;
+  XPT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_strip<NS, DERIVE>, StripSmem<NS>::kThreads, StripSmem<NS>::kBytes));
+  if (n < 1) return fail(XPT_CUDA_ERROR, "k_strip<%d> does not fit an SM", NS);
+  *ctas_per_sm = n;
+  return XPT_OK;
+}
+
+int prepare_strip(xpt_ctx* ctx) {
+  if (ctx->strip_ready) return XPT_OK;
+  const int NS = ctx->N == 1 ? 1 : (ctx->N == 2 ? 2 : 4);
+  int per_sm = 1;
+  if (NS == 1) XPT_TRY((strip_grid<1, false>(ctx->cfg.device, &per_sm)));
+  else if (NS == 2) XPT_TRY((strip_grid<2, false>(ctx->cfg.device, &per_sm)));
+  else XPT_TRY((strip_grid<4, false>(ctx->cfg.device, &per_sm)));
+  cudaDeviceProp prop;
+  XPT_CUDA(cudaGetDeviceProperties(&prop, ctx->cfg.device));
+  int nctas = prop.multiProcessorCount * per_sm;
+  if (const char* e = getenv("XPT_STRIP_CTAS")) { const int v = atoi(e); if (v > 0) nctas = v; }
+  // strips of every level
+  struct Unit { int b, l, x0, cw, rows; };
+  std::vector<Unit> units;
+  long long total = 0;
+  for (int l = 0; l < ctx->S; ++l) {
+    const int W = ctx->w[l], ns = cdiv(W, kSCWMax);
+    int cw = 2 * cdiv(W, 2 * ns);
+    if (cw > kSCWMax) cw = kSCWMax;
+    for (int b = 0; b < ctx->B; ++b)
+      for (int k = 0; k < ns; ++k) {
+        const int x0 = k * cw;
+        if (x0 >= W) break;
+        units.push_back({b, l, x0, (W - x0 < cw ? W - x0 : cw), ctx->h[l]});
+        total += (ctx->h[l] + 4 + 1) / 2;
+      }
+  }
+  const int kMinRows = 8;
+  long long target = (total + 2LL * nctas + nctas - 1) / nctas;      // every cut adds two chunks of halo
+  if (target < 8) target = 8;
+  std::vector<StripPiece> pieces;
+  std::vector<StripCta> ctas(nctas, StripCta{0, 0, 0, 0});
+  std::vector<int> slot_of_b(ctx->B, 0);
+  int cur = 0;
+  for (const Unit& u : units) {
+    int ya = 0;
+    while (ya < u.rows) {
+      long long left = target - ctas[cur].chunks;
+      if (cur < nctas - 1 && left < (kMinRows + 4) / 2) { ++cur; ctas[cur].first = (int)pieces.size(); continue; }
+      int take = u.rows - ya;
+      if (cur < nctas - 1) {
+        const long long max_rows = 2 * left - 4;
+        if (take > max_rows) take = (int)max_rows;
+        if (u.rows - ya - take > 0 && u.rows - ya - take < kMinRows) take = u.rows - ya;     // no sliver pieces
+      }
+      StripPiece p;
+      p.b = u.b; p.l = u.l; p.x0 = u.x0; p.cw = u.cw; p.ya = ya; p.yb = ya + take;
+      p.slot = slot_of_b[u.b]++; p.nch = (take + 4 + 1) / 2;
+      if (ctas[cur].count == 0) ctas[cur].first = (int)pieces.size();
+      pieces.push_back(p);
+      ctas[cur].count += 1; ctas[cur].chunks += p.nch;
+      ya += take;
+    }
+  }
+  int slots = 1;
+  for (int b = 0; b < ctx->B; ++b) if (slot_of_b[b] > slots) slots = slot_of_b[b];
+  ctx->strip_nctas = nctas; ctx->strip_slots = slots; ctx->strip_ns = NS;
+  {
+    float* tmp = nullptr;
+    XPT_TRY(dev_alloc(ctx, &tmp, pieces.size() * sizeof(StripPiece) / sizeof(float)));
+    ctx->strip_pieces = reinterpret_cast<StripPiece*>(tmp);
+    tmp = nullptr;
+    XPT_TRY(dev_alloc(ctx, &tmp, ctas.size() * sizeof(StripCta) / sizeof(float)));
+    ctx->strip_ctas = reinterpret_cast<StripCta*>(tmp);
+  }
+  XPT_CUDA(cudaMemcpy(ctx->strip_pieces, pieces.data(), pieces.size() * sizeof(StripPiece), cudaMemcpyHostToDevice));
+  XPT_CUDA(cudaMemcpy(ctx->strip_ctas, ctas.data(), ctas.size() * sizeof(StripCta), cudaMemcpyHostToDevice));
+  XPT_TRY(dev_alloc(ctx, &ctx->strip_loss_part, (size_t)ctx->B * slots * 3));
+  XPT_TRY(dev_alloc(ctx, &ctx->strip_pose_part, (size_t)ctx->B * slots * ctx->N * 12));
+  XPT_CUDA(cudaMemset(ctx->strip_loss_part, 0, (size_t)ctx->B * slots * 3 * sizeof(float)));
+  XPT_CUDA(cudaMemset(ctx->strip_pose_part, 0, (size_t)ctx->B * slots * ctx->N * 12 * sizeof(float)));
+  ctx->strip_ready = true;
+  return XPT_OK;
+}
+
+template <int NS, bool DERIVE>
+int launch_strip_t(xpt_ctx* ctx, const StripArgs& a, cudaStream_t st) {
+  int per_sm = 0;
+  XPT_TRY((strip_grid<NS, DERIVE>(ctx->cfg.device, &per_sm)));       // sets the dynamic shared-memory attribute once
+  const bool prof = ctx->prof_on > 0 && ctx->prof_count < ctx->prof_on && ctx->prof_kind == XPT_PROFILE_FUSED;
+  if (prof) XPT_CUDA(cudaEventRecord((*ctx->prof_events)[2 * ctx->prof_count], st));
+  k_strip<NS, DERIVE><<<ctx->strip_nctas, StripSmem<NS>::kThreads, StripSmem<NS>::kBytes, st>>>(a);
+  XPT_LAUNCH_CHECK("k_strip");
+  if (prof) { XPT_CUDA(cudaEventRecord((*ctx->prof_events)[2 * ctx->prof_count + 1], st)); ++ctx->prof_count; }
+  return XPT_OK;
+}
+
+int launch_strip(xpt_ctx* ctx, const StripArgs& a, bool derive, cudaStream_t st) {
+  switch (ctx->strip_ns * 2 + (derive ? 1 : 0)) {
+    case 2: return launch_strip_t<1, false>(ctx, a, st);
+    case 3: return launch_strip_t<1, true>(ctx, a, st);
+    case 4: return launch_strip_t<2, false>(ctx, a, st);
+    case 5: return launch_strip_t<2, true>(ctx, a, st);
+    case 8: return launch_strip_t<4, false>(ctx, a, st);
+    default: return launch_strip_t<4, true>(ctx, a, st);
+  }
 }
 
 int launch_smooth(xpt_ctx* ctx, const float* const disp_ms[], const LevelTable& lt, const float* gbatch,
@@ -1014,6 +1132,41 @@ static int total_loss_body(xpt_ctx* ctx, const xpt_frames* frames, const float* 
       fa.d_depth[l] = a.d_depth[l]; fa.d_disp[l] = a.d_disp[l];
     }
     const bool dsrc = grad && out->d_source;
+    bool want_out0 = false;
+    for (int l = 0; l < ctx->S; ++l) want_out0 = want_out0 || out->synth_ms[l] || out->mask_ms[l];
+    // training step (gradients, no synthesis tensors, no dL/dsource, N <= 4): the streaming strip kernel
+    const bool use_strip = grad && !dsrc && !want_out0 && ctx->N <= 4 && !(c.flags & XPT_FLAG_TILES);
+    if (use_strip) {
+      XPT_TRY(prepare_strip(ctx));
+      StripArgs sa;
+      memset(&sa, 0, sizeof(sa));
+      sa.lt = lt;
+      sa.B = ctx->B; sa.N = ctx->N; sa.S = ctx->S;
+      sa.pieces = ctx->strip_pieces; sa.ctas = ctx->strip_ctas;
+      sa.geoK = ctx->geoK; sa.geoT = ctx->geoT;
+      for (int l = 0; l < ctx->S; ++l) {
+        sa.depth[l] = a.depth[l]; sa.disp[l] = a.disp[l];
+        sa.src4[l] = reinterpret_cast<const float4*>(ctx->src4_pyr[l]);
+        sa.norm_photo[l] = a.norm_photo[l]; sa.norm_sm_x[l] = a.norm_sm_x[l]; sa.norm_sm_y[l] = a.norm_sm_y[l];
+        sa.d_depth[l] = a.d_depth[l]; sa.d_disp[l] = a.d_disp[l];
+      }
+      sa.do_l1 = a.l1_kind != 0; sa.do_ssim = a.do_ssim; sa.do_smooth = a.do_smooth;
+      sa.grad_factor = a.grad_factor;
+      sa.gcoef_l1 = a.gcoef_l1; sa.gcoef_ssim = a.gcoef_ssim; sa.gcoef_smooth = a.gcoef_smooth;
+      sa.loss_part = ctx->strip_loss_part; sa.slots_per_b = ctx->strip_slots; sa.pose_part = ctx->strip_pose_part;
+      XPT_TRY(launch_strip(ctx, sa, derive_disp, st));
+      EpilogueArgs ea;
+      memset(&ea, 0, sizeof(ea));
+      ea.pose_part = ctx->strip_pose_part; ea.loss_part = ctx->strip_loss_part;
+      ea.slots_per_b = ctx->strip_slots; ea.slots_used = ctx->strip_slots; ea.B = ctx->B; ea.N = ctx->N;
+      ea.pose = pose; ea.d_pose = out->d_pose;
+      ea.inv_global_batch = inv_gb; ea.w0 = c.w_l1; ea.w1 = c.w_ssim; ea.w2 = c.w_smooth;
+      ea.losses = out->losses; ea.loss_batch = out->loss_batch;
+      ea.loss_sum_b = ctx->loss_sum_b; ea.ticket = ctx->ticket;
+      k_epilogue<<<(ea.d_pose ? ctx->B * ctx->N : 0) + ctx->B, 128, 0, st>>>(ea);
+      XPT_LAUNCH_CHECK("k_epilogue");
+      return XPT_OK;
+    }
     if (dsrc) XPT_TRY(prepare_dsource4(ctx, fa.d_src4, st));
     const int ftiles = ctx->ffirst_tile[ctx->S];
     fa.first_tile[ctx->S] = ftiles;
