@@ -73,10 +73,12 @@ struct StripSmem {
   static constexpr int kSrc = kD + kSDRows * kSW;                // floats per source
   static constexpr int src0 = T + 4 * kSTRows * kSW;
   static constexpr int geo = src0 + NS * kSrc;                   // [NS][32]: K rows 0-1, inv K rows 0-1, [R|t]
-  static constexpr int loss = geo + NS * 32;                     // [2][3 NS][2]
-  static constexpr int kFloats = loss + 2 * 3 * NS * 2;
+  static constexpr int geoG = geo + NS * 32;                     // [(NS+1)/2][32]: [R|t] of a G warp's sources
+  static constexpr int loss = geoG + ((NS + 1) / 2) * 32;        // [2][3 NS][2]
+  static constexpr int stage = (loss + 2 * 3 * NS * 2 + 3) & ~3; // [NS][16 taps][32 lanes] float4: Y's gathers (cp.async)
+  static constexpr int kFloats = stage + NS * 16 * 32 * 4;
   static constexpr size_t kBytes = sizeof(float) * kFloats;
-  static constexpr int kWarps = 1 + NS + 3 * NS + NS;
+  static constexpr int kWarps = 2 + NS + 3 * NS + (NS + 1) / 2;
   static constexpr int kThreads = 32 * kWarps;
 };
 
@@ -105,61 +107,102 @@ __device__ __forceinline__ int strip_cnt(int g, int n) {      // in-image member
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// L + O: loader of the target / depth rows, and the output stage (dL/ddepth over sources, smoothness)
+// L: loader of the target / depth rows.  The rows of chunk t+1 are requested while chunk t is being stored, so the
+// HBM latency of a row sits behind one whole tick.
 // ---------------------------------------------------------------------------------------------------------
-template <int NS, bool DERIVE>
-__device__ __forceinline__ void strip_role_lo(const StripArgs& a, float* smem, const int lane, const StripCta cta) {
+struct StripRow { float v[6]; float d[2]; };     // two adjacent pixels: (A.c0 A.c1 A.c2 B.c0 B.c1 B.c2), depth or disparity
+
+__device__ __forceinline__ StripRow strip_load_row(const float* __restrict__ tg, const float* __restrict__ dp, int H, int W,
+                                                   int gy, int gx) {
+  StripRow r;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) r.v[k] = 0.f;
+  r.d[0] = r.d[1] = 0.f;
+  if ((unsigned)gy < (unsigned)H) {
+    const long long o = (long long)gy * W + gx;
+    if ((unsigned)gx < (unsigned)W) {
+      r.v[0] = __ldg(tg + o * 3); r.v[1] = __ldg(tg + o * 3 + 1); r.v[2] = __ldg(tg + o * 3 + 2);
+      if (dp) r.d[0] = __ldg(dp + o);
+    }
+    if ((unsigned)(gx + 1) < (unsigned)W) {
+      r.v[3] = __ldg(tg + o * 3 + 3); r.v[4] = __ldg(tg + o * 3 + 4); r.v[5] = __ldg(tg + o * 3 + 5);
+      if (dp) r.d[1] = __ldg(dp + o + 1);
+    }
+  }
+  return r;
+}
+
+template <int NS>
+__device__ __forceinline__ void strip_role_l(const StripArgs& a, float* smem, const int lane, const StripCta cta) {
   using SM = StripSmem<NS>;
   float* const T = smem + SM::T;
   const int total = cta.chunks, pend = cta.first + cta.count;
-  int lpi = cta.first, lci = 0, opi = cta.first, oci = 0;
-  StripPiece lp = load_piece(a.pieces, lpi), op = lp;
-
-  // smoothness state of the output stage: the current row (the row whose outputs are due) and the vertical terms of
-  // the row above it
-  float tc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};      // target of the current row: (A.c0, A.c1, A.c2, B.c0, B.c1, B.c2)
-  float dc[2] = {0.f, 0.f};                          // disparity of the current row
-  float zc[2] = {0.f, 0.f};                          // DERIVE: its depth is not needed again (d disp/d depth = -disp^2)
-  float ty_up[2] = {0.f, 0.f};                       // gcy * sgn * w of the pair (row above, current row)
-  bool cur_in = false;                               // the current row lies inside the image
-  float lsum_sm = 0.f;
-  (void)zc;
-
+  int pi = cta.first, ci = 0;
+  StripPiece p = load_piece(a.pieces, pi);
+  StripRow nx[2];
+  auto fetch = [&]() {            // rows of chunk (pi, ci)
+    const Level& L = a.lt.lv[p.l];
+    const float* const tg = L.tgt + (long long)p.b * L.tgt_bs;
+    const float* const dp = a.depth[p.l] + (long long)p.b * L.H * L.W;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) nx[r] = strip_load_row(tg, dp, L.H, L.W, p.ya - 2 + 2 * ci + r, p.x0 - 2 + 2 * lane);
+    if (++ci == p.nch) { ci = 0; if (++pi < pend) p = load_piece(a.pieces, pi); }
+  };
+  fetch();
   for (int t = 0; t < total + kSLagO; ++t) {
-    // ---- L: rows of chunk t ------------------------------------------------------------------------------
     if (t < total) {
-      const Level& L = a.lt.lv[lp.l];
-      const int H = L.H, W = L.W;
-      const float* const tg = L.tgt + (long long)lp.b * L.tgt_bs;
-      const float* const dp = a.depth[lp.l] + (long long)lp.b * H * W;
-      const int gx = lp.x0 - 2 + 2 * lane;
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
-        const int s = 2 * t + r, gy = lp.ya - 2 + 2 * lci + r;
-        float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f, v5 = 0.f, d0 = 0.f, d1 = 0.f;
-        if ((unsigned)gy < (unsigned)H) {
-          const long long o = (long long)gy * W + gx;
-          if ((unsigned)gx < (unsigned)W) { v0 = __ldg(tg + o * 3); v1 = __ldg(tg + o * 3 + 1); v2 = __ldg(tg + o * 3 + 2); d0 = __ldg(dp + o); }
-          if ((unsigned)(gx + 1) < (unsigned)W) { v3 = __ldg(tg + o * 3 + 3); v4 = __ldg(tg + o * 3 + 4); v5 = __ldg(tg + o * 3 + 5); d1 = __ldg(dp + o + 1); }
-        }
-        float* const q = T + (s & (kSTRows - 1)) * kSW + 2 * lane;
-        sts2(q, f2(v0, v3)); sts2(q + kSTRows * kSW, f2(v1, v4)); sts2(q + 2 * kSTRows * kSW, f2(v2, v5));
-        sts2(q + 3 * kSTRows * kSW, f2(d0, d1));
+        float* const q = T + ((2 * t + r) & (kSTRows - 1)) * kSW + 2 * lane;
+        sts2(q, f2(nx[r].v[0], nx[r].v[3])); sts2(q + kSTRows * kSW, f2(nx[r].v[1], nx[r].v[4]));
+        sts2(q + 2 * kSTRows * kSW, f2(nx[r].v[2], nx[r].v[5])); sts2(q + 3 * kSTRows * kSW, f2(nx[r].d[0], nx[r].d[1]));
       }
-      if (++lci == lp.nch) { lci = 0; if (++lpi < pend) lp = load_piece(a.pieces, lpi); }
+      if (t + 1 < total) fetch();
     }
-    // ---- O: rows of chunk t - 4 ---------------------------------------------------------------------------
+    strip_bar();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// O: output stage -- dL/ddepth summed over the sources in a fixed order, edge-aware smoothness (losses.py:409-440)
+// forward + backward on rows walked top to bottom, loss record of the piece.  Rows are requested one tick ahead.
+// ---------------------------------------------------------------------------------------------------------
+template <int NS, bool DERIVE>
+__device__ __forceinline__ void strip_role_o(const StripArgs& a, float* smem, const int lane, const StripCta cta) {
+  using SM = StripSmem<NS>;
+  const int total = cta.chunks, pend = cta.first + cta.count;
+  int opi = cta.first, oci = 0, qpi = cta.first, qci = 0;
+  StripPiece op = load_piece(a.pieces, opi), qp = op;
+  StripRow nx[2], cu[2];
+  auto fetch = [&]() {            // the "next rows" of chunk (qpi, qci): row ya + sg - 3 for step sg >= 2
+    const Level& L = a.lt.lv[qp.l];
+    const float* const tg = L.tgt + (long long)qp.b * L.tgt_bs;
+    const float* const ds = DERIVE ? a.depth[qp.l] : a.disp[qp.l];
+    const float* const dp = ds ? ds + (long long)qp.b * L.H * L.W : nullptr;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int sg = 2 * qci + r;
+      nx[r] = strip_load_row(tg, dp, (a.do_smooth && sg >= 2 && sg < qp.yb - qp.ya + 4) ? L.H : 0, L.W, qp.ya + sg - 3,
+                             qp.x0 - 2 + 2 * lane);
+    }
+    if (++qci == qp.nch) { qci = 0; if (++qpi < pend) qp = load_piece(a.pieces, qpi); }
+  };
+  // smoothness state: the current row (the row whose outputs are due) and the vertical terms of the pair above it
+  float tc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dc[2] = {0.f, 0.f}, ty_up[2] = {0.f, 0.f};
+  bool cur_in = false;
+  float lsum_sm = 0.f;
+  fetch();
+  for (int t = 0; t < total + kSLagO; ++t) {
     const int co = t - kSLagO;
     if (co >= 0) {
+      cu[0] = nx[0]; cu[1] = nx[1];
+      if (co + 1 < total) fetch();                 // one tick ahead of its use
       const Level& L = a.lt.lv[op.l];
       const int H = L.H, W = L.W, Lr = op.yb - op.ya;
-      const float* const tg = L.tgt + (long long)op.b * L.tgt_bs;
-      const float* const dsrc = (DERIVE ? a.depth[op.l] : a.disp[op.l]);
-      const float* const dp = dsrc ? dsrc + (long long)op.b * H * W : nullptr;
       const int gx = op.x0 - 2 + 2 * lane;
       const float k3 = a.grad_factor;
-      const float nx = a.norm_sm_x[op.l], ny = a.norm_sm_y[op.l];
-      const float gcx = a.gcoef_smooth * nx, gcy = a.gcoef_smooth * ny;
+      const float nx_ = a.norm_sm_x[op.l], ny_ = a.norm_sm_y[op.l];
+      const float gcx = a.gcoef_smooth * nx_, gcy = a.gcoef_smooth * ny_;
       const bool cen0 = 2 * lane >= 2 && 2 * lane < 2 + op.cw && gx < W;
       const bool cen1 = 2 * lane + 1 >= 2 && 2 * lane + 1 < 2 + op.cw && gx + 1 < W;
 #pragma unroll
@@ -167,20 +210,16 @@ __device__ __forceinline__ void strip_role_lo(const StripArgs& a, float* smem, c
         const int s = 2 * co + r, sg = 2 * oci + r;
         const int gy = op.ya + sg - 4;                       // row whose outputs are due at this step
         const bool out_row = sg >= 4 && sg < Lr + 4;
-        float gd0 = 0.f, gd1 = 0.f;                          // dL/ddisp of the smoothness term
+        float gd0 = 0.f, gd1 = 0.f, z0 = 0.f, z1 = 0.f;      // dL/ddisp of the smoothness term; disparity of the row
         if (a.do_smooth && sg >= 2 && sg < Lr + 4) {
-          // next row gy + 1
-          const int gn = gy + 1;
-          float tn[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dn[2] = {0.f, 0.f};
-          const bool nxt_in = (unsigned)gn < (unsigned)H;
-          if (nxt_in) {
-            const long long o = (long long)gn * W + gx;
-            if ((unsigned)gx < (unsigned)W) { tn[0] = __ldg(tg + o * 3); tn[1] = __ldg(tg + o * 3 + 1); tn[2] = __ldg(tg + o * 3 + 2); dn[0] = __ldg(dp + o); }
-            if ((unsigned)(gx + 1) < (unsigned)W) { tn[3] = __ldg(tg + o * 3 + 3); tn[4] = __ldg(tg + o * 3 + 4); tn[5] = __ldg(tg + o * 3 + 5); dn[1] = __ldg(dp + o + 1); }
-            if (DERIVE) {
+          const bool nxt_in = (unsigned)(gy + 1) < (unsigned)H;
+          float tn[6], dn[2];
 #pragma unroll
-              for (int k = 0; k < 2; ++k) dn[k] = dn[k] > 0.00001f ? __frcp_rn(dn[k]) : 0.f;   // safe_reciprocal_number
-            }
+          for (int k = 0; k < 6; ++k) tn[k] = cu[r].v[k];
+          dn[0] = cu[r].d[0]; dn[1] = cu[r].d[1];
+          if (DERIVE) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) dn[k] = dn[k] > 0.00001f ? __frcp_rn(dn[k]) : 0.f;     // safe_reciprocal_number
           }
           if (sg >= 3) {
             // vertical pairs (current row, next row) of both columns
@@ -198,10 +237,10 @@ __device__ __forceinline__ void strip_role_lo(const StripArgs& a, float* smem, c
               }
             }
             // horizontal pairs of the current row: (A, B) inside the lane, (B, right lane's A) across lanes
-            float rt[3], rd;
+            float rt[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) rt[c] = __shfl_down_sync(0xffffffffu, tc[c], 1);
-            rd = __shfl_down_sync(0xffffffffu, dc[0], 1);
+            const float rd = __shfl_down_sync(0xffffffffu, dc[0], 1);
             float txA = 0.f, txB = 0.f, sdxA = 0.f, sdxB = 0.f;
             if (cur_in) {
               if ((unsigned)gx < (unsigned)W && gx + 1 < W) {
@@ -223,18 +262,14 @@ __device__ __forceinline__ void strip_role_lo(const StripArgs& a, float* smem, c
             }
             const float txL = __shfl_up_sync(0xffffffffu, txB, 1);       // pair (left lane's B, A)
             if (out_row) {
-              // losses.py:409-440: forward terms of the pairs a pixel starts, gradient of all four pairs it is part of
-              if (cen0) lsum_sm += fabsf(sdxA) * nx + fabsf(sdy[0]) * ny;
-              if (cen1) lsum_sm += fabsf(sdxB) * nx + fabsf(sdy[1]) * ny;
+              // forward terms of the pairs a pixel starts, gradient of all four pairs it is part of
+              if (cen0) lsum_sm += fabsf(sdxA) * nx_ + fabsf(sdy[0]) * ny_;
+              if (cen1) lsum_sm += fabsf(sdxB) * nx_ + fabsf(sdy[1]) * ny_;
               gd0 = txA; gd0 += ty[0]; gd0 -= (lane > 0 ? txL : 0.f); gd0 -= ty_up[0];
               gd1 = txB; gd1 += ty[1]; gd1 -= txA; gd1 -= ty_up[1];
+              z0 = dc[0]; z1 = dc[1];
             }
             ty_up[0] = ty[0]; ty_up[1] = ty[1];
-          }
-          if (out_row) { zc[0] = dc[0]; zc[1] = dc[1]; }
-          // advance: next -> current (after the outputs of this row used dc)
-          if (!out_row || true) {
-            // dc of the output row is still needed below for DERIVE: keep it in zc
           }
 #pragma unroll
           for (int k = 0; k < 6; ++k) tc[k] = tn[k];
@@ -243,7 +278,7 @@ __device__ __forceinline__ void strip_role_lo(const StripArgs& a, float* smem, c
         }
         if (out_row) {
           float g0 = 0.f, g1 = 0.f;
-          if (DERIVE && a.do_smooth) { g0 = -(gd0 * zc[0]) * zc[0]; g1 = -(gd1 * zc[1]) * zc[1]; }
+          if (DERIVE && a.do_smooth) { g0 = -(gd0 * z0) * z0; g1 = -(gd1 * z1) * z1; }   // d disp / d depth = -disp^2
 #pragma unroll
           for (int n = 0; n < NS; ++n)
             if (n < a.N) {
@@ -262,7 +297,7 @@ __device__ __forceinline__ void strip_role_lo(const StripArgs& a, float* smem, c
         }
       }
       if (++oci == op.nch) {
-        // ---- piece done: loss partial record (S warps left their sums two ticks ago) -------------------------
+        // piece done: loss partial record (the S warps left their sums two ticks ago)
         const float sm = warp_sum(lsum_sm);
         if (lane == 0) {
           const float* lb = smem + SM::loss + (opi & 1) * (3 * NS * 2);
@@ -285,14 +320,15 @@ __device__ __forceinline__ void strip_role_lo(const StripArgs& a, float* smem, c
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Y: inverse warp of one source, one region row per step, two adjacent columns per lane
+// Y: inverse warp of one source, two region rows per tick, two adjacent columns per lane.  The sixteen 16-byte
+// gathers of a tick go global -> shared with cp.async (no registers in flight), both rows at once.
 // ---------------------------------------------------------------------------------------------------------
-struct StripSample {
-  float2 yxy; float yz;          // warped value
-  float2 guxy; float guz;        // dS/du
-  float2 gvxy; float gvz;        // dS/dv
-  float su, sv, si;              // u, v, 1/den (0 when invalid)
-};
+__device__ __forceinline__ void cp_async16(float* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
 
 template <int NS>
 __device__ __forceinline__ void strip_role_y(const StripArgs& a, float* smem, const int lane, const int n,
@@ -302,6 +338,7 @@ __device__ __forceinline__ void strip_role_y(const StripArgs& a, float* smem, co
   float* const Yr = smem + SM::src0 + n * SM::kSrc + SM::kY;
   float* const Jr = smem + SM::src0 + n * SM::kSrc + SM::kJ;
   float* const geo = smem + SM::geo + n * 32;
+  float* const stg = smem + SM::stage + n * (16 * 32 * 4) + lane * 4;     // [tap][lane] float4
   const int total = cta.chunks, pend = cta.first + cta.count;
   const bool live = n < a.N;
   int pi = cta.first, ci = 0;
@@ -326,12 +363,13 @@ __device__ __forceinline__ void strip_role_y(const StripArgs& a, float* smem, co
       const float fx0 = (float)(p.x0 - 2 + 2 * lane);
       const float2 fx = f2(fx0, fx0 + 1.f);
       const float wlim = (float)(W - 2), hlim = (float)(H - 2);
+      float wuf[4], wuc[4], wvf[4], wvc[4];
+      // ---- phase A: projection + taps of both rows, gathers requested --------------------------------------------
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         const int s = 2 * c + r, sg = 2 * ci + r;
         const float fy = (float)(p.ya - 2 + sg);
         const float2 D = lds2(T + (3 * kSTRows + (s & (kSTRows - 1))) * kSW + 2 * lane);
-        // ---- projection, both columns per instruction (reference order) -------------------------
         float2 pu, pv, inv;
         {
           const float4 gA = lds4(geo), gB = lds4(geo + 4), gC = lds4(geo + 8);      // K0..K5 | Ki0..Ki5
@@ -339,6 +377,7 @@ __device__ __forceinline__ void strip_role_y(const StripArgs& a, float* smem, co
           const float2 r0 = ray_pair(gB.z, gB.w, gC.x, fx, fy);
           const float2 r1 = ray_pair(gC.y, gC.z, gC.w, fx, fy);
           const float2 X0 = f2mul(r0, D), X1 = f2mul(r1, D);
+          // reference order: X = ray D, Y = R X + t, p = K_s Y, (u, v) = p.xy / (p.z + 1e-10)
           const float2 Y0 = f2add(f2fma(f2s(tA.z), D, f2fma(f2s(tA.x), X0, f2mul(f2s(tA.y), X1))), f2s(tC.y));
           const float2 Y1 = f2add(f2fma(f2s(tB.y), D, f2fma(f2s(tA.w), X0, f2mul(f2s(tB.x), X1))), f2s(tC.z));
           const float2 Y2 = f2add(f2fma(f2s(tC.x), D, f2fma(f2s(tB.z), X0, f2mul(f2s(tB.w), X1))), f2s(tC.w));
@@ -357,63 +396,73 @@ __device__ __forceinline__ void strip_role_y(const StripArgs& a, float* smem, co
           pv = f2fma(f2fma(nden, q1, p1), rr, q1);
           inv = rr;
         }
-        // ---- taps of both columns, then all eight 16-byte gathers, then the bilinear value + Jacobian ---------
         const float us[2] = {pu.x, pu.y}, vs[2] = {pv.x, pv.y}, Ds[2] = {D.x, D.y}, is[2] = {inv.x, inv.y};
-        float wuf[2], wuc[2], wvf[2], wvc[2];
-        bool val[2];
-        float4 t0[2], t1[2], t2[2], t3[2];
+        float su[2], sv[2], si[2];
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
+          const int q = 2 * r + k;
           const float uf = floorf(us[k]), vf = floorf(vs[k]);
           // valid <=> 0 <= floor(u) <= W-2 and 0 <= floor(v) <= H-2 and D != 0 (bilinear_interp.py:53-76); NaN -> false
-          val[k] = (uf >= 0.f) && (uf <= wlim) && (vf >= 0.f) && (vf <= hlim) && (Ds[k] != 0.f);
-          const int iu = val[k] ? (int)uf : 0, iv = val[k] ? (int)vf : 0;
+          const bool val = (uf >= 0.f) && (uf <= wlim) && (vf >= 0.f) && (vf <= hlim) && (Ds[k] != 0.f);
+          const int iu = val ? (int)uf : 0, iv = val ? (int)vf : 0;
           // weights * valid_mask (bilinear_interp.py:100): an invalid sample gathers texel (0,0) with zero weights
-          wuf[k] = val[k] ? (uf + 1.f) - us[k] : 0.f;
-          wuc[k] = val[k] ? us[k] - uf : 0.f;
-          wvf[k] = val[k] ? (vf + 1.f) - vs[k] : 0.f;
-          wvc[k] = val[k] ? vs[k] - vf : 0.f;
+          wuf[q] = val ? (uf + 1.f) - us[k] : 0.f;
+          wuc[q] = val ? us[k] - uf : 0.f;
+          wvf[q] = val ? (vf + 1.f) - vs[k] : 0.f;
+          wvc[q] = val ? vs[k] - vf : 0.f;
+          su[k] = val ? us[k] : 0.f; sv[k] = val ? vs[k] : 0.f; si[k] = val ? is[k] : 0.f;
+          // I0 = (vf,uf), I1 = (vc,uf), I2 = (vf,uc), I3 = (vc,uc)   (bilinear_interp.py:125-128)
           const float4* tp = img4 + (iv * W + iu);
-          t0[k] = __ldg(tp); t2[k] = __ldg(tp + 1); t1[k] = __ldg(tp + W); t3[k] = __ldg(tp + W + 1);
+          cp_async16(stg + (4 * q + 0) * 128, tp);
+          cp_async16(stg + (4 * q + 1) * 128, tp + W);
+          cp_async16(stg + (4 * q + 2) * 128, tp + 1);
+          cp_async16(stg + (4 * q + 3) * 128, tp + W + 1);
         }
-        StripSample o[2];
+        float* const j = Jr + (s & (kSJRows - 1)) * kSW + 2 * lane;
+        constexpr int JP = kSJRows * kSW;
+        sts2(j + 6 * JP, f2(su[0], su[1]));
+        sts2(j + 7 * JP, f2(sv[0], sv[1]));
+        sts2(j + 8 * JP, f2(si[0], si[1]));
+        sts2(j + 9 * JP, D);
+      }
+      cp_async_wait_all();
+      // ---- phase B: bilinear value + Jacobian of the four samples -> rings ------------------------------------------
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int s = 2 * c + r;
+        float2 yxy[2], guxy[2], gvxy[2];
+        float yz[2], guz[2], gvz[2];
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-          // I0 = (vf,uf), I1 = (vc,uf), I2 = (vf,uc), I3 = (vc,uc)   (bilinear_interp.py:125-128)
-          const float w0 = wuf[k] * wvf[k], w1 = wuf[k] * wvc[k], w2 = wuc[k] * wvf[k], w3 = wuc[k] * wvc[k];
-          const float2 a0 = f2(t0[k].x, t0[k].y), a1 = f2(t1[k].x, t1[k].y), a2 = f2(t2[k].x, t2[k].y), a3 = f2(t3[k].x, t3[k].y);
-          o[k].yxy = f2fma(a3, f2s(w3), f2fma(a2, f2s(w2), f2fma(a0, f2s(w0), f2mul(a1, f2s(w1)))));
-          o[k].yz = fmaf(t3[k].z, w3, fmaf(t2[k].z, w2, fmaf(t0[k].z, w0, t1[k].z * w1)));
+          const int q = 2 * r + k;
+          const float4 t0 = lds4(stg + (4 * q + 0) * 128), t1 = lds4(stg + (4 * q + 1) * 128);
+          const float4 t2 = lds4(stg + (4 * q + 2) * 128), t3 = lds4(stg + (4 * q + 3) * 128);
+          const float w0 = wuf[q] * wvf[q], w1 = wuf[q] * wvc[q], w2 = wuc[q] * wvf[q], w3 = wuc[q] * wvc[q];
+          const float2 a0 = f2(t0.x, t0.y), a1 = f2(t1.x, t1.y), a2 = f2(t2.x, t2.y), a3 = f2(t3.x, t3.y);
+          yxy[k] = f2fma(a3, f2s(w3), f2fma(a2, f2s(w2), f2fma(a0, f2s(w0), f2mul(a1, f2s(w1)))));
+          yz[k] = fmaf(t3.z, w3, fmaf(t2.z, w2, fmaf(t0.z, w0, t1.z * w1)));
           const float2 d20 = f2sub(a2, a0), d31 = f2sub(a3, a1), d10 = f2sub(a1, a0), d32 = f2sub(a3, a2);
-          o[k].guxy = f2fma(f2s(wvf[k]), d20, f2mul(f2s(wvc[k]), d31));
-          o[k].gvxy = f2fma(f2s(wuf[k]), d10, f2mul(f2s(wuc[k]), d32));
-          o[k].guz = fmaf(wvf[k], t2[k].z - t0[k].z, wvc[k] * (t3[k].z - t1[k].z));
-          o[k].gvz = fmaf(wuf[k], t1[k].z - t0[k].z, wuc[k] * (t3[k].z - t2[k].z));
-          o[k].su = val[k] ? us[k] : 0.f; o[k].sv = val[k] ? vs[k] : 0.f; o[k].si = val[k] ? is[k] : 0.f;
+          guxy[k] = f2fma(f2s(wvf[q]), d20, f2mul(f2s(wvc[q]), d31));
+          gvxy[k] = f2fma(f2s(wuf[q]), d10, f2mul(f2s(wuc[q]), d32));
+          guz[k] = fmaf(wvf[q], t2.z - t0.z, wvc[q] * (t3.z - t1.z));
+          gvz[k] = fmaf(wuf[q], t1.z - t0.z, wuc[q] * (t3.z - t2.z));
         }
-        // ---- rings ------------------------------------------------------------------------------------------
-        {
-          float* const q = Yr + (s & (kSYRows - 1)) * kSW + 2 * lane;
-          sts2(q, f2(o[0].yxy.x, o[1].yxy.x));
-          sts2(q + kSYRows * kSW, f2(o[0].yxy.y, o[1].yxy.y));
-          sts2(q + 2 * kSYRows * kSW, f2(o[0].yz, o[1].yz));
-          // mean_c(synth) == 0 marks an invalid pixel for the losses (loss_util.py:15-16)
-          const float nb0 = (((o[0].yxy.x + o[0].yxy.y) + o[0].yz) == 0.f) ? 0.f : 1.f;
-          const float nb1 = (((o[1].yxy.x + o[1].yxy.y) + o[1].yz) == 0.f) ? 0.f : 1.f;
-          sts2(q + 3 * kSYRows * kSW, f2(nb0, nb1));
-          float* const j = Jr + (s & (kSJRows - 1)) * kSW + 2 * lane;
-          constexpr int JP = kSJRows * kSW;
-          sts2(j, f2(o[0].guxy.x, o[1].guxy.x));
-          sts2(j + JP, f2(o[0].guxy.y, o[1].guxy.y));
-          sts2(j + 2 * JP, f2(o[0].guz, o[1].guz));
-          sts2(j + 3 * JP, f2(o[0].gvxy.x, o[1].gvxy.x));
-          sts2(j + 4 * JP, f2(o[0].gvxy.y, o[1].gvxy.y));
-          sts2(j + 5 * JP, f2(o[0].gvz, o[1].gvz));
-          sts2(j + 6 * JP, f2(o[0].su, o[1].su));
-          sts2(j + 7 * JP, f2(o[0].sv, o[1].sv));
-          sts2(j + 8 * JP, f2(o[0].si, o[1].si));
-          sts2(j + 9 * JP, D);
-        }
+        float* const q = Yr + (s & (kSYRows - 1)) * kSW + 2 * lane;
+        sts2(q, f2(yxy[0].x, yxy[1].x));
+        sts2(q + kSYRows * kSW, f2(yxy[0].y, yxy[1].y));
+        sts2(q + 2 * kSYRows * kSW, f2(yz[0], yz[1]));
+        // mean_c(synth) == 0 marks an invalid pixel for the losses (loss_util.py:15-16)
+        const float nb0 = (((yxy[0].x + yxy[0].y) + yz[0]) == 0.f) ? 0.f : 1.f;
+        const float nb1 = (((yxy[1].x + yxy[1].y) + yz[1]) == 0.f) ? 0.f : 1.f;
+        sts2(q + 3 * kSYRows * kSW, f2(nb0, nb1));
+        float* const j = Jr + (s & (kSJRows - 1)) * kSW + 2 * lane;
+        constexpr int JP = kSJRows * kSW;
+        sts2(j, f2(guxy[0].x, guxy[1].x));
+        sts2(j + JP, f2(guxy[0].y, guxy[1].y));
+        sts2(j + 2 * JP, f2(guz[0], guz[1]));
+        sts2(j + 3 * JP, f2(gvxy[0].x, gvxy[1].x));
+        sts2(j + 4 * JP, f2(gvxy[0].y, gvxy[1].y));
+        sts2(j + 5 * JP, f2(gvz[0], gvz[1]));
       }
       if (++ci == p.nch) { ci = 0; fresh = true; if (++pi < pend) p = load_piece(a.pieces, pi); }
     }
@@ -440,18 +489,35 @@ __device__ __forceinline__ float2 shfl_lr(float2 q) {   // (right column of the 
   return f2(__shfl_up_sync(0xffffffffu, q.y, 1), __shfl_down_sync(0xffffffffu, q.x, 1));
 }
 
+// per-lane column constants of a piece: 1/#taps for window rows with 3 / 2 in-image rows, centre-column flags
+struct StripCols { float2 ic3, ic2, cen; };
+__device__ __forceinline__ StripCols strip_cols(const StripPiece& p, int W, int lane) {
+  const int gx = p.x0 - 2 + 2 * lane;
+  const int cx0 = strip_cnt(gx, W), cx1 = strip_cnt(gx + 1, W);
+  StripCols c;
+  c.ic3 = f2(strip_box_inv(3, cx0), strip_box_inv(3, cx1));
+  c.ic2 = f2(strip_box_inv(2, cx0), strip_box_inv(2, cx1));
+  c.cen = f2((2 * lane >= 2 && 2 * lane < 2 + p.cw && gx < W) ? 1.f : 0.f,
+             (2 * lane + 1 >= 2 && 2 * lane + 1 < 2 + p.cw && gx + 1 < W) ? 1.f : 0.f);
+  return c;
+}
+
 template <int NS>
 __device__ __forceinline__ void strip_role_s(const StripArgs& a, float* smem, const int lane, const int n, const int ch,
                                              const StripCta cta) {
   using SM = StripSmem<NS>;
-  const float* const Tx = smem + SM::T + ch * kSTRows * kSW;
-  const float* const Yc = smem + SM::src0 + n * SM::kSrc + SM::kY + ch * kSYRows * kSW;
-  const float* const Ynb = smem + SM::src0 + n * SM::kSrc + SM::kY + 3 * kSYRows * kSW;
-  float* const Gc = smem + SM::src0 + n * SM::kSrc + SM::kG + ch * kSGRows * kSW;
+  const float* const Tx = smem + SM::T + ch * kSTRows * kSW + 2 * lane;
+  const float* const Yc = smem + SM::src0 + n * SM::kSrc + SM::kY + ch * kSYRows * kSW + 2 * lane;
+  const float* const Ynb = smem + SM::src0 + n * SM::kSrc + SM::kY + 3 * kSYRows * kSW + 2 * lane;
+  float* const Gc = smem + SM::src0 + n * SM::kSrc + SM::kG + ch * kSGRows * kSW + 2 * lane;
   const int total = cta.chunks, pend = cta.first + cta.count;
   const bool live = n < a.N;
   int pi = cta.first, ci = 0;
   StripPiece p = load_piece(a.pieces, pi);
+  // constants of the current piece (set when the piece starts)
+  StripCols col = strip_cols(p, a.lt.lv[p.l].W, lane);
+  int H = a.lt.lv[p.l].H, Lr = p.yb - p.ya;
+  float cl1 = a.gcoef_l1 * a.norm_photo[p.l], hss2 = -a.gcoef_ssim * a.norm_photo[p.l];
 
   Win2 wy, wyy, wxy, wx, wxx, wA, wB, wC;
   wy.clear(); wyy.clear(); wxy.clear(); wx.clear(); wxx.clear(); wA.clear(); wB.clear(); wC.clear();
@@ -462,23 +528,18 @@ __device__ __forceinline__ void strip_role_s(const StripArgs& a, float* smem, co
   for (int t = 0; t < total + kSLagO; ++t) {
     const int c = t - kSLagS;
     if (live && c >= 0 && c < total) {
-      const Level& L = a.lt.lv[p.l];
-      const int H = L.H, W = L.W, Lr = p.yb - p.ya;
-      const int gx = p.x0 - 2 + 2 * lane;
-      // per-lane column constants of this piece
-      const int cx0 = strip_cnt(gx, W), cx1 = strip_cnt(gx + 1, W);
-      const float2 ic3 = f2(strip_box_inv(3, cx0), strip_box_inv(3, cx1));
-      const float2 ic2 = f2(strip_box_inv(2, cx0), strip_box_inv(2, cx1));
-      const float2 cen = f2((2 * lane >= 2 && 2 * lane < 2 + p.cw && gx < W) ? 1.f : 0.f,
-                            (2 * lane + 1 >= 2 && 2 * lane + 1 < 2 + p.cw && gx + 1 < W) ? 1.f : 0.f);
-      const float cl1 = a.gcoef_l1 * a.norm_photo[p.l];
-      const float hss2 = -a.gcoef_ssim * a.norm_photo[p.l];
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         const int s = 2 * c + r, sg = 2 * ci + r;
-        const float2 y = lds2(Yc + (s & (kSYRows - 1)) * kSW + 2 * lane);
-        const float2 nb = lds2(Ynb + (s & (kSYRows - 1)) * kSW + 2 * lane);
-        const float2 x = lds2(Tx + (s & (kSTRows - 1)) * kSW + 2 * lane);
+        const float2 y = lds2(Yc + (s & (kSYRows - 1)) * kSW);
+        const float2 nb = lds2(Ynb + (s & (kSYRows - 1)) * kSW);
+        const float2 x = lds2(Tx + (s & (kSTRows - 1)) * kSW);
+        // statistics row sg-1 (image row gy1): 1/#taps, centre-row flag
+        const int gy1 = p.ya - 3 + sg;
+        const int cy = strip_cnt(gy1, H);
+        const float2 ic = cy == 3 ? col.ic3 : (cy == 2 ? col.ic2 : f2s(0.f));
+        const bool row_c = sg >= 3 && sg < Lr + 3;                  // a centre row of this piece
+        const float2 cnt_w = row_c ? f2mul(col.cen, nb1) : f2s(0.f);
         float2 g = f2s(0.f);
         if (a.do_ssim) {
           // ---- row sums of y, y^2, xy, x, x^2 over columns (c-1, c, c+1) -------------------------------------
@@ -488,11 +549,7 @@ __device__ __forceinline__ void strip_role_s(const StripArgs& a, float* smem, co
           const float2 hxy = hsum_nb(f2mul(x, y), f2mul(xn, yn));
           const float2 hxx = hsum_nb(f2mul(x, x), f2mul(xn, xn));
           const float2 Vy = wy.push(hy), Vyy = wyy.push(hyy), Vxy = wxy.push(hxy), Vx = wx.push(hx), Vxx = wxx.push(hxx);
-          // ---- statistics row sg-1 (image row gy1): SSIM, loss, adjoint coefficients (loss_util.py:52-96) ---------
-          const int gy1 = p.ya - 2 + sg - 1;
-          const int cy = strip_cnt(gy1, H);
-          const float2 ic = cy == 3 ? ic3 : (cy == 2 ? ic2 : f2s(0.f));
-          const bool row_c = sg - 1 >= 2 && sg - 1 < Lr + 2;            // a centre row of this piece
+          // ---- SSIM, loss, adjoint coefficients of row sg-1 (loss_util.py:52-96) -----------------------------
           const float2 mux = f2mul(Vx, ic), mux2 = f2mul(mux, mux);
           const float2 MUX2C = f2add(mux2, f2s(kC1));
           const float2 SGXC = f2add(f2fma(Vxx, ic, f2neg(mux2)), f2s(kC2));
@@ -508,7 +565,6 @@ __device__ __forceinline__ void strip_role_s(const StripArgs& a, float* smem, co
           const float2 ssim = f2mul(f2mul(a1, a2), r12);
           const float2 lv = f2fma(f2s(-0.5f), ssim, f2s(0.5f));
           const float lc0 = fminf(fmaxf(lv.x, 0.f), 1.f), lc1 = fminf(fmaxf(lv.y, 0.f), 1.f);
-          const float2 cnt_w = row_c ? f2mul(cen, nb1) : f2s(0.f);
           ls_ss = f2fma(cnt_w, f2(lc0, lc1), ls_ss);
           // clip_by_value passes the gradient inside [0,1]; Hh = 2 h / (#taps b1 b2), h = dTotal/d ssim
           const float2 hlive = f2mul(f2mul(ic, f2s(hss2)), nb1);
@@ -527,15 +583,13 @@ __device__ __forceinline__ void strip_role_s(const StripArgs& a, float* smem, co
         }
         // ---- L1 (loss_util.py:6-25): loss of row sg-1, gradient term of row sg-2 ------------------------------
         if (a.do_l1) {
-          const bool row_c = sg - 1 >= 2 && sg - 1 < Lr + 2;
-          const float2 cnt_w = row_c ? f2mul(cen, nb1) : f2s(0.f);
           const float2 d1 = f2sub(y1, x1);
           ls_l1 = f2fma(cnt_w, f2(fabsf(d1.x), fabsf(d1.y)), ls_l1);
           g = f2add(g, l1t2);
           const float2 nbc = f2mul(nb1, f2s(cl1));
           l1t2 = f2(d1.x == 0.f ? 0.f : copysignf(nbc.x, d1.x), d1.y == 0.f ? 0.f : copysignf(nbc.y, d1.y));
         }
-        sts2(Gc + ((s - 2) & (kSGRows - 1)) * kSW + 2 * lane, g);
+        sts2(Gc + ((s - 2) & (kSGRows - 1)) * kSW, g);
         y2 = y1; x2 = x1; y1 = y; x1 = x; nb1 = nb;
       }
       if (++ci == p.nch) {
@@ -549,7 +603,12 @@ __device__ __forceinline__ void strip_role_s(const StripArgs& a, float* smem, co
         wy.clear(); wyy.clear(); wxy.clear(); wx.clear(); wxx.clear(); wA.clear(); wB.clear(); wC.clear();
         y1 = x1 = nb1 = y2 = x2 = l1t2 = f2s(0.f);
         ci = 0;
-        if (++pi < pend) p = load_piece(a.pieces, pi);
+        if (++pi < pend) {
+          p = load_piece(a.pieces, pi);
+          col = strip_cols(p, a.lt.lv[p.l].W, lane);
+          H = a.lt.lv[p.l].H; Lr = p.yb - p.ya;
+          cl1 = a.gcoef_l1 * a.norm_photo[p.l]; hss2 = -a.gcoef_ssim * a.norm_photo[p.l];
+        }
       }
     }
     strip_bar();
@@ -557,48 +616,49 @@ __device__ __forceinline__ void strip_role_s(const StripArgs& a, float* smem, co
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// G: dL/dS x Jacobian -> projection adjoint: dL/ddepth per pixel, dL/dR, dL/dt sums per piece
+// G: dL/dS x Jacobian -> projection adjoint: dL/ddepth per pixel, dL/dR, dL/dt sums per piece.
+// One warp serves two sources (2 gw, 2 gw + 1), one after the other per row.
 // ---------------------------------------------------------------------------------------------------------
 template <int NS>
-__device__ __forceinline__ void strip_role_g(const StripArgs& a, float* smem, const int lane, const int n,
+__device__ __forceinline__ void strip_role_g(const StripArgs& a, float* smem, const int lane, const int gw,
                                              const StripCta cta) {
   using SM = StripSmem<NS>;
-  const float* const Jr = smem + SM::src0 + n * SM::kSrc + SM::kJ;
-  const float* const Gr = smem + SM::src0 + n * SM::kSrc + SM::kG;
-  float* const Dr = smem + SM::src0 + n * SM::kSrc + SM::kD;
+  constexpr int NG = NS >= 2 ? 2 : 1;           // sources of this warp
+  float* const geo = smem + SM::geoG + gw * 32;  // [R (9) of source 0 | pad | R (9) of source 1]
   const int total = cta.chunks, pend = cta.first + cta.count;
-  const bool live = n < a.N;
+  const int n0 = NG * gw;
+  const bool live = n0 < a.N;
   int pi = cta.first, ci = 0;
   StripPiece p = load_piece(a.pieces, pi);
   bool fresh = true;
-  float gk[6], ki[6], gt[9];
-  float2 acc[12];
+  float gk[6], ki[6];
+  float acc[NG][12];
 #pragma unroll
-  for (int k = 0; k < 12; ++k) acc[k] = f2s(0.f);
+  for (int q = 0; q < NG; ++q)
+#pragma unroll
+    for (int k = 0; k < 12; ++k) acc[q][k] = 0.f;
 #pragma unroll
   for (int k = 0; k < 6; ++k) { gk[k] = 0.f; ki[k] = 0.f; }
-#pragma unroll
-  for (int k = 0; k < 9; ++k) gt[k] = 0.f;
+  float2 cen = f2s(0.f), fx = f2s(0.f);
+  int Lr = 0;
 
   for (int t = 0; t < total + kSLagO; ++t) {
     const int c = t - kSLagG;
     if (live && c >= 0 && c < total) {
-      const Level& L = a.lt.lv[p.l];
-      const int W = L.W, Lr = p.yb - p.ya;
       if (fresh) {
         const float* K = a.geoK + (size_t)(p.b * a.S + p.l) * kGeoK;
-        const float* Tt = a.geoT + (size_t)(p.b * a.N + n) * kGeoT;
 #pragma unroll
         for (int k = 0; k < 6; ++k) { gk[k] = __ldg(K + k); ki[k] = __ldg(K + 9 + k); }
-#pragma unroll
-        for (int k = 0; k < 9; ++k) gt[k] = __ldg(Tt + k);
+        __syncwarp();
+        if (lane < 12 * NG && n0 + lane / 12 < a.N) geo[(lane / 12) * 12 + lane % 12] = __ldg(a.geoT + (size_t)(p.b * a.N + n0 + lane / 12) * kGeoT + lane % 12);
+        __syncwarp();
+        const int W = a.lt.lv[p.l].W, gx = p.x0 - 2 + 2 * lane;
+        cen = f2((2 * lane >= 2 && 2 * lane < 2 + p.cw && gx < W) ? 1.f : 0.f,
+                 (2 * lane + 1 >= 2 && 2 * lane + 1 < 2 + p.cw && gx + 1 < W) ? 1.f : 0.f);
+        fx = f2((float)gx, (float)gx + 1.f);
+        Lr = p.yb - p.ya;
         fresh = false;
       }
-      const int gx = p.x0 - 2 + 2 * lane;
-      const float fx0 = (float)gx;
-      const float2 fx = f2(fx0, fx0 + 1.f);
-      const float2 cen = f2((2 * lane >= 2 && 2 * lane < 2 + p.cw && gx < W) ? 1.f : 0.f,
-                            (2 * lane + 1 >= 2 && 2 * lane + 1 < 2 + p.cw && gx + 1 < W) ? 1.f : 0.f);
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         const int s = 2 * c + r, sg = 2 * ci + r;
@@ -606,43 +666,60 @@ __device__ __forceinline__ void strip_role_g(const StripArgs& a, float* smem, co
           const int kg = ((s - 2) & (kSGRows - 1)) * kSW + 2 * lane;
           const int kj = ((s - 2) & (kSJRows - 1)) * kSW + 2 * lane;
           constexpr int GP = kSGRows * kSW, JP = kSJRows * kSW;
-          const float2 g0 = f2mul(lds2(Gr + kg), cen), g1 = f2mul(lds2(Gr + GP + kg), cen), g2 = f2mul(lds2(Gr + 2 * GP + kg), cen);
-          const float2 gu2 = f2fma(g2, lds2(Jr + 2 * JP + kj), f2fma(g1, lds2(Jr + JP + kj), f2mul(g0, lds2(Jr + kj))));
-          const float2 gv2 = f2fma(g2, lds2(Jr + 5 * JP + kj), f2fma(g1, lds2(Jr + 4 * JP + kj), f2mul(g0, lds2(Jr + 3 * JP + kj))));
-          const float2 U = lds2(Jr + 6 * JP + kj), V = lds2(Jr + 7 * JP + kj), I = lds2(Jr + 8 * JP + kj), D = lds2(Jr + 9 * JP + kj);
-          // samples without a valid warp cached zero Jacobians and 1/den = 0: exact zeros below
-          const float2 gp0 = f2mul(gu2, I), gp1 = f2mul(gv2, I);
-          const float2 gp2 = f2mul(f2neg(f2fma(gv2, V, f2mul(gu2, U))), I);
           const float fy = (float)(p.ya + sg - 4);
           const float2 r0 = ray_pair(ki[0], ki[1], ki[2], fx, fy);
           const float2 r1 = ray_pair(ki[3], ki[4], ki[5], fx, fy);
-          const float2 X0 = f2mul(r0, D), X1 = f2mul(r1, D);
-          // dL/dY = K_s^T dL/dp (last row of K_s is (0,0,1))
-          const float2 gY0 = f2fma(f2s(gk[0]), gp0, f2mul(f2s(gk[3]), gp1));
-          const float2 gY1 = f2fma(f2s(gk[1]), gp0, f2mul(f2s(gk[4]), gp1));
-          const float2 gY2 = f2add(f2fma(f2s(gk[2]), gp0, f2mul(f2s(gk[5]), gp1)), gp2);
-          acc[0] = f2fma(gY0, X0, acc[0]); acc[1] = f2fma(gY0, X1, acc[1]); acc[2] = f2fma(gY0, D, acc[2]);
-          acc[3] = f2fma(gY1, X0, acc[3]); acc[4] = f2fma(gY1, X1, acc[4]); acc[5] = f2fma(gY1, D, acc[5]);
-          acc[6] = f2fma(gY2, X0, acc[6]); acc[7] = f2fma(gY2, X1, acc[7]); acc[8] = f2fma(gY2, D, acc[8]);
-          acc[9] = f2add(acc[9], gY0); acc[10] = f2add(acc[10], gY1); acc[11] = f2add(acc[11], gY2);
-          // dL/dX = R^T dL/dY, dL/dD = ray . dL/dX
-          const float2 gX0 = f2fma(f2s(gt[6]), gY2, f2fma(f2s(gt[0]), gY0, f2mul(f2s(gt[3]), gY1)));
-          const float2 gX1 = f2fma(f2s(gt[7]), gY2, f2fma(f2s(gt[1]), gY0, f2mul(f2s(gt[4]), gY1)));
-          const float2 gX2 = f2fma(f2s(gt[8]), gY2, f2fma(f2s(gt[2]), gY0, f2mul(f2s(gt[5]), gY1)));
-          const float2 gD = f2add(f2fma(gX0, r0, f2mul(gX1, r1)), gX2);
-          sts2(Dr + ((s - 2) & (kSDRows - 1)) * kSW + 2 * lane, gD);
+#pragma unroll
+          for (int q = 0; q < NG; ++q) {
+            if (n0 + q < a.N) {
+              const float* const Jr = smem + SM::src0 + (n0 + q) * SM::kSrc + SM::kJ;
+              const float* const Gr = smem + SM::src0 + (n0 + q) * SM::kSrc + SM::kG;
+              float* const Dr = smem + SM::src0 + (n0 + q) * SM::kSrc + SM::kD;
+              const float2 g0 = f2mul(lds2(Gr + kg), cen), g1 = f2mul(lds2(Gr + GP + kg), cen), g2 = f2mul(lds2(Gr + 2 * GP + kg), cen);
+              const float2 gu2 = f2fma(g2, lds2(Jr + 2 * JP + kj), f2fma(g1, lds2(Jr + JP + kj), f2mul(g0, lds2(Jr + kj))));
+              const float2 gv2 = f2fma(g2, lds2(Jr + 5 * JP + kj), f2fma(g1, lds2(Jr + 4 * JP + kj), f2mul(g0, lds2(Jr + 3 * JP + kj))));
+              const float2 U = lds2(Jr + 6 * JP + kj), V = lds2(Jr + 7 * JP + kj), I = lds2(Jr + 8 * JP + kj), D = lds2(Jr + 9 * JP + kj);
+              // samples without a valid warp cached zero Jacobians and 1/den = 0: exact zeros below
+              const float2 gp0 = f2mul(gu2, I), gp1 = f2mul(gv2, I);
+              const float2 gp2 = f2mul(f2neg(f2fma(gv2, V, f2mul(gu2, U))), I);
+              const float2 X0 = f2mul(r0, D), X1 = f2mul(r1, D);
+              // dL/dY = K_s^T dL/dp (last row of K_s is (0,0,1))
+              const float2 gY0 = f2fma(f2s(gk[0]), gp0, f2mul(f2s(gk[3]), gp1));
+              const float2 gY1 = f2fma(f2s(gk[1]), gp0, f2mul(f2s(gk[4]), gp1));
+              const float2 gY2 = f2add(f2fma(f2s(gk[2]), gp0, f2mul(f2s(gk[5]), gp1)), gp2);
+              const float2 gY[3] = {gY0, gY1, gY2};
+#pragma unroll
+              for (int i = 0; i < 3; ++i) {
+                acc[q][3 * i + 0] = fmaf(gY[i].y, X0.y, fmaf(gY[i].x, X0.x, acc[q][3 * i + 0]));
+                acc[q][3 * i + 1] = fmaf(gY[i].y, X1.y, fmaf(gY[i].x, X1.x, acc[q][3 * i + 1]));
+                acc[q][3 * i + 2] = fmaf(gY[i].y, D.y, fmaf(gY[i].x, D.x, acc[q][3 * i + 2]));
+                acc[q][9 + i] += gY[i].x + gY[i].y;
+              }
+              // dL/dX = R^T dL/dY, dL/dD = ray . dL/dX
+              const float4 ta = lds4(geo + q * 12), tb = lds4(geo + q * 12 + 4);
+              const float t8 = geo[q * 12 + 8];
+              const float2 gX0 = f2fma(f2s(tb.z), gY2, f2fma(f2s(ta.x), gY0, f2mul(f2s(ta.w), gY1)));
+              const float2 gX1 = f2fma(f2s(tb.w), gY2, f2fma(f2s(ta.y), gY0, f2mul(f2s(tb.x), gY1)));
+              const float2 gX2 = f2fma(f2s(t8), gY2, f2fma(f2s(ta.z), gY0, f2mul(f2s(tb.y), gY1)));
+              const float2 gD = f2add(f2fma(gX0, r0, f2mul(gX1, r1)), gX2);
+              sts2(Dr + ((s - 2) & (kSDRows - 1)) * kSW + 2 * lane, gD);
+            }
+          }
         }
       }
       if (++ci == p.nch) {
-        // piece done: 12 pose sums of (b, n) -> one partial record
-        float v[16];
+        // piece done: 12 pose sums of (b, n) -> one partial record per source
 #pragma unroll
-        for (int k = 0; k < 12; ++k) { v[k] = acc[k].x + acc[k].y; acc[k] = f2s(0.f); }
-        v[12] = v[13] = v[14] = v[15] = 0.f;
-        const float tot = warp_reduce16(v, lane);
-        const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-        if ((lane & 1) == 0 && idx < 12)
-          a.pose_part[(((size_t)p.b * a.slots_per_b + p.slot) * a.N + n) * 12 + idx] = tot;
+        for (int q = 0; q < NG; ++q) {
+          float v[16];
+#pragma unroll
+          for (int k = 0; k < 12; ++k) { v[k] = acc[q][k]; acc[q][k] = 0.f; }
+          v[12] = v[13] = v[14] = v[15] = 0.f;
+          const float tot = warp_reduce16(v, lane);
+          const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+          if ((lane & 1) == 0 && idx < 12 && n0 + q < a.N)
+            a.pose_part[(((size_t)p.b * a.slots_per_b + p.slot) * a.N + n0 + q) * 12 + idx] = tot;
+        }
         ci = 0; fresh = true;
         if (++pi < pend) p = load_piece(a.pieces, pi);
       }
@@ -652,15 +729,16 @@ __device__ __forceinline__ void strip_role_g(const StripArgs& a, float* smem, co
 }
 
 template <int NS, bool DERIVE>
-__global__ void __launch_bounds__(StripSmem<NS>::kThreads, NS == 1 ? 3 : 1) k_strip(const __grid_constant__ StripArgs a) {
+__global__ void __launch_bounds__(StripSmem<NS>::kThreads, NS == 1 ? 2 : 1) k_strip(const __grid_constant__ StripArgs a) {
   extern __shared__ __align__(16) float smem[];
   const StripCta cta = a.ctas[blockIdx.x];
   if (cta.count == 0) return;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (wid == 0) strip_role_lo<NS, DERIVE>(a, smem, lane, cta);
-  else if (wid <= NS) strip_role_y<NS>(a, smem, lane, wid - 1, cta);
-  else if (wid <= 4 * NS) strip_role_s<NS>(a, smem, lane, (wid - NS - 1) / 3, (wid - NS - 1) % 3, cta);
-  else strip_role_g<NS>(a, smem, lane, wid - 4 * NS - 1, cta);
+  if (wid == 0) strip_role_l<NS>(a, smem, lane, cta);
+  else if (wid == 1) strip_role_o<NS, DERIVE>(a, smem, lane, cta);
+  else if (wid < 2 + NS) strip_role_y<NS>(a, smem, lane, wid - 2, cta);
+  else if (wid < 2 + 4 * NS) strip_role_s<NS>(a, smem, lane, (wid - NS - 2) / 3, (wid - NS - 2) % 3, cta);
+  else strip_role_g<NS>(a, smem, lane, wid - 4 * NS - 2, cta);      // G warp gw serves sources 2 gw, 2 gw + 1
 }
 
 }  // namespace xpt

@@ -509,55 +509,93 @@ int prepare_strip(xpt_ctx* ctx) {
   XPT_CUDA(cudaGetDeviceProperties(&prop, ctx->cfg.device));
   int nctas = prop.multiProcessorCount * per_sm;
   if (const char* e = getenv("XPT_STRIP_CTAS")) { const int v = atoi(e); if (v > 0) nctas = v; }
-  // strips of every level
-  struct Unit { int b, l, x0, cw, rows; };
+  // The strips of ONE snippet, large levels first.  Every snippet is cut at the same rows (so a snippet's losses and
+  // gradients do not depend on its position in the batch) into R runs of equal cost; run r of snippet b goes to
+  // CTA (r * B + b) mod nctas.  R is chosen to minimise the largest per-CTA load.
+  struct Unit { int l, x0, cw, rows; };
   std::vector<Unit> units;
-  long long total = 0;
+  long long snip = 0;
   for (int l = 0; l < ctx->S; ++l) {
     const int W = ctx->w[l], ns = cdiv(W, kSCWMax);
     int cw = 2 * cdiv(W, 2 * ns);
     if (cw > kSCWMax) cw = kSCWMax;
-    for (int b = 0; b < ctx->B; ++b)
-      for (int k = 0; k < ns; ++k) {
-        const int x0 = k * cw;
-        if (x0 >= W) break;
-        units.push_back({b, l, x0, (W - x0 < cw ? W - x0 : cw), ctx->h[l]});
-        total += (ctx->h[l] + 4 + 1) / 2;
-      }
-  }
-  const int kMinRows = 8;
-  long long target = (total + 2LL * nctas + nctas - 1) / nctas;      // every cut adds two chunks of halo
-  if (target < 8) target = 8;
-  std::vector<StripPiece> pieces;
-  std::vector<StripCta> ctas(nctas, StripCta{0, 0, 0, 0});
-  std::vector<int> slot_of_b(ctx->B, 0);
-  int cur = 0;
-  for (const Unit& u : units) {
-    int ya = 0;
-    while (ya < u.rows) {
-      long long left = target - ctas[cur].chunks;
-      if (cur < nctas - 1 && left < (kMinRows + 4) / 2) { ++cur; ctas[cur].first = (int)pieces.size(); continue; }
-      int take = u.rows - ya;
-      if (cur < nctas - 1) {
-        const long long max_rows = 2 * left - 4;
-        if (take > max_rows) take = (int)max_rows;
-        if (u.rows - ya - take > 0 && u.rows - ya - take < kMinRows) take = u.rows - ya;     // no sliver pieces
-      }
-      StripPiece p;
-      p.b = u.b; p.l = u.l; p.x0 = u.x0; p.cw = u.cw; p.ya = ya; p.yb = ya + take;
-      p.slot = slot_of_b[u.b]++; p.nch = (take + 4 + 1) / 2;
-      if (ctas[cur].count == 0) ctas[cur].first = (int)pieces.size();
-      pieces.push_back(p);
-      ctas[cur].count += 1; ctas[cur].chunks += p.nch;
-      ya += take;
+    for (int k = 0; k < ns; ++k) {
+      const int x0 = k * cw;
+      if (x0 >= W) break;
+      units.push_back({l, x0, (W - x0 < cw ? W - x0 : cw), ctx->h[l]});
+      snip += (ctx->h[l] + 4 + 1) / 2;
     }
   }
-  int slots = 1;
-  for (int b = 0; b < ctx->B; ++b) if (slot_of_b[b] > slots) slots = slot_of_b[b];
+  const int kMinRows = 8;
+  struct Tpl { std::vector<StripPiece> pieces; std::vector<int> run_first; std::vector<int> run_cost; };
+  auto build = [&](int R, Tpl& t) {
+    t.pieces.clear(); t.run_first.assign(1, 0); t.run_cost.assign(1, 0);
+    long long target = (snip + 2LL * R + R - 1) / R;          // every cut adds two chunks of halo
+    if (target < 8) target = 8;
+    for (const Unit& u : units) {
+      int ya = 0;
+      while (ya < u.rows) {
+        const bool last = (int)t.run_cost.size() == R;
+        const long long left = target - t.run_cost.back();
+        if (!last && left < (kMinRows + 4) / 2) { t.run_first.push_back((int)t.pieces.size()); t.run_cost.push_back(0); continue; }
+        int take = u.rows - ya;
+        if (!last) {
+          const long long max_rows = 2 * left - 4;
+          if (take > max_rows) take = (int)max_rows;
+          if (u.rows - ya - take > 0 && u.rows - ya - take < kMinRows) take = u.rows - ya;     // no sliver pieces
+        }
+        StripPiece p;
+        p.b = 0; p.l = u.l; p.x0 = u.x0; p.cw = u.cw; p.ya = ya; p.yb = ya + take;
+        p.slot = (int)t.pieces.size(); p.nch = (take + 4 + 1) / 2;
+        t.pieces.push_back(p);
+        t.run_cost.back() += p.nch;
+        ya += take;
+      }
+    }
+    t.run_first.push_back((int)t.pieces.size());
+  };
+  auto makespan = [&](const Tpl& t) {
+    std::vector<long long> load(nctas, 0);
+    const int R = (int)t.run_cost.size();
+    long long mx = 0;
+    for (int r = 0; r < R; ++r)
+      for (int b = 0; b < ctx->B; ++b) {
+        long long& v = load[((long long)r * ctx->B + b) % nctas];
+        v += t.run_cost[r];
+        if (v > mx) mx = v;
+      }
+    return mx;
+  };
+  Tpl best, cand;
+  long long best_ms = -1;
+  int Rmax = (int)(snip / 6) + 1;
+  if (Rmax > 2 * nctas) Rmax = 2 * nctas;
+  if (const char* e = getenv("XPT_STRIP_RUNS")) { const int v = atoi(e); if (v > 0) { build(v, best); best_ms = makespan(best); Rmax = 0; } }
+  for (int R = 1; R <= Rmax; ++R) {
+    build(R, cand);
+    const long long ms = makespan(cand);
+    if (best_ms < 0 || ms < best_ms) { best_ms = ms; best = cand; }
+  }
+  const int R = (int)best.run_cost.size();
+  std::vector<StripPiece> pieces;
+  std::vector<StripCta> ctas(nctas, StripCta{0, 0, 0, 0});
+  for (int c = 0; c < nctas; ++c) {
+    ctas[c].first = (int)pieces.size();
+    for (long long i = c; i < (long long)R * ctx->B; i += nctas) {
+      const int r = (int)(i / ctx->B), b = (int)(i % ctx->B);
+      for (int k = best.run_first[r]; k < best.run_first[r + 1]; ++k) {
+        StripPiece p = best.pieces[k];
+        p.b = b;
+        pieces.push_back(p);
+        ctas[c].count += 1; ctas[c].chunks += p.nch;
+      }
+    }
+  }
+  const int slots = (int)best.pieces.size() > 0 ? (int)best.pieces.size() : 1;
   ctx->strip_nctas = nctas; ctx->strip_slots = slots; ctx->strip_ns = NS;
   {
     float* tmp = nullptr;
-    XPT_TRY(dev_alloc(ctx, &tmp, pieces.size() * sizeof(StripPiece) / sizeof(float)));
+    XPT_TRY(dev_alloc(ctx, &tmp, (pieces.size() + 1) * sizeof(StripPiece) / sizeof(float)));
     ctx->strip_pieces = reinterpret_cast<StripPiece*>(tmp);
     tmp = nullptr;
     XPT_TRY(dev_alloc(ctx, &tmp, ctas.size() * sizeof(StripCta) / sizeof(float)));
@@ -569,6 +607,9 @@ int prepare_strip(xpt_ctx* ctx) {
   XPT_TRY(dev_alloc(ctx, &ctx->strip_pose_part, (size_t)ctx->B * slots * ctx->N * 12));
   XPT_CUDA(cudaMemset(ctx->strip_loss_part, 0, (size_t)ctx->B * slots * 3 * sizeof(float)));
   XPT_CUDA(cudaMemset(ctx->strip_pose_part, 0, (size_t)ctx->B * slots * ctx->N * 12 * sizeof(float)));
+  if (getenv("XPT_STRIP_VERBOSE"))
+    fprintf(stderr, "xptwarp: strip partition B=%d: %d runs x %d snippets on %d CTAs, %zu pieces, %lld chunks per snippet, largest CTA %lld chunks (ideal %.1f)\n",
+            ctx->B, R, ctx->B, nctas, pieces.size(), snip, best_ms, (double)snip * ctx->B / nctas);
   ctx->strip_ready = true;
   return XPT_OK;
 }
