@@ -30,7 +30,8 @@ namespace xpt {
 
 constexpr int kSW = 64;                 // region columns of a strip (32 lanes x 2)
 constexpr int kSCWMax = 60;             // centre columns (halo 2 on both sides)
-constexpr int kSTRows = 8;              // ring rows: target/depth (L -> Y, S)
+constexpr int kSTRows = 16;             // ring rows: target/depth/disparity (L -> Y, S, O)
+constexpr int kSTPlanes = 5;            // x0 x1 x2 depth disparity
 constexpr int kSYRows = 4;              //            warped value (Y -> S)
 constexpr int kSJRows = 8;              //            Jacobian     (Y -> G)
 constexpr int kSGRows = 4;              //            dL/dS        (S -> G)
@@ -65,13 +66,13 @@ struct StripArgs {
 
 template <int NS>
 struct StripSmem {
-  static constexpr int T = 0;                                    // [4][8][64]: x0 x1 x2 depth
+  static constexpr int T = 0;                                    // [5][16][64]: x0 x1 x2 depth disparity
   static constexpr int kY = 0;                                   // per source: [4][4][64] y0 y1 y2 notblack
   static constexpr int kJ = kY + 4 * kSYRows * kSW;              //             [10][8][64]
   static constexpr int kG = kJ + kSJPlanes * kSJRows * kSW;      //             [3][4][64]
   static constexpr int kD = kG + 3 * kSGRows * kSW;              //             [4][64]
   static constexpr int kSrc = kD + kSDRows * kSW;                // floats per source
-  static constexpr int src0 = T + 4 * kSTRows * kSW;
+  static constexpr int src0 = T + kSTPlanes * kSTRows * kSW;
   static constexpr int geo = src0 + NS * kSrc;                   // [NS][32]: K rows 0-1, inv K rows 0-1, [R|t]
   static constexpr int geoG = geo + NS * 32;                     // [(NS+1)/2][32]: [R|t] of a G warp's sources
   static constexpr int loss = geoG + ((NS + 1) / 2) * 32;        // [2][3 NS][2]
@@ -110,23 +111,25 @@ __device__ __forceinline__ int strip_cnt(int g, int n) {      // in-image member
 // L: loader of the target / depth rows.  The rows of chunk t+1 are requested while chunk t is being stored, so the
 // HBM latency of a row sits behind one whole tick.
 // ---------------------------------------------------------------------------------------------------------
-struct StripRow { float v[6]; float d[2]; };     // two adjacent pixels: (A.c0 A.c1 A.c2 B.c0 B.c1 B.c2), depth or disparity
+struct StripRow { float v[6]; float d[2]; float e[2]; };     // two adjacent pixels: (A.c0 A.c1 A.c2 B.c0 B.c1 B.c2), depth, disparity
 
-__device__ __forceinline__ StripRow strip_load_row(const float* __restrict__ tg, const float* __restrict__ dp, int H, int W,
-                                                   int gy, int gx) {
+__device__ __forceinline__ StripRow strip_load_row(const float* __restrict__ tg, const float* __restrict__ dp,
+                                                   const float* __restrict__ ep, int H, int W, int gy, int gx) {
   StripRow r;
 #pragma unroll
   for (int k = 0; k < 6; ++k) r.v[k] = 0.f;
-  r.d[0] = r.d[1] = 0.f;
+  r.d[0] = r.d[1] = r.e[0] = r.e[1] = 0.f;
   if ((unsigned)gy < (unsigned)H) {
     const long long o = (long long)gy * W + gx;
     if ((unsigned)gx < (unsigned)W) {
       r.v[0] = __ldg(tg + o * 3); r.v[1] = __ldg(tg + o * 3 + 1); r.v[2] = __ldg(tg + o * 3 + 2);
-      if (dp) r.d[0] = __ldg(dp + o);
+      r.d[0] = __ldg(dp + o);
+      if (ep) r.e[0] = __ldg(ep + o);
     }
     if ((unsigned)(gx + 1) < (unsigned)W) {
       r.v[3] = __ldg(tg + o * 3 + 3); r.v[4] = __ldg(tg + o * 3 + 4); r.v[5] = __ldg(tg + o * 3 + 5);
-      if (dp) r.d[1] = __ldg(dp + o + 1);
+      r.d[1] = __ldg(dp + o + 1);
+      if (ep) r.e[1] = __ldg(ep + o + 1);
     }
   }
   return r;
@@ -144,8 +147,9 @@ __device__ __forceinline__ void strip_role_l(const StripArgs& a, float* smem, co
     const Level& L = a.lt.lv[p.l];
     const float* const tg = L.tgt + (long long)p.b * L.tgt_bs;
     const float* const dp = a.depth[p.l] + (long long)p.b * L.H * L.W;
+    const float* const ep = (a.do_smooth && a.disp[p.l]) ? a.disp[p.l] + (long long)p.b * L.H * L.W : nullptr;
 #pragma unroll
-    for (int r = 0; r < 2; ++r) nx[r] = strip_load_row(tg, dp, L.H, L.W, p.ya - 2 + 2 * ci + r, p.x0 - 2 + 2 * lane);
+    for (int r = 0; r < 2; ++r) nx[r] = strip_load_row(tg, dp, ep, L.H, L.W, p.ya - 2 + 2 * ci + r, p.x0 - 2 + 2 * lane);
     if (++ci == p.nch) { ci = 0; if (++pi < pend) p = load_piece(a.pieces, pi); }
   };
   fetch();
@@ -156,6 +160,7 @@ __device__ __forceinline__ void strip_role_l(const StripArgs& a, float* smem, co
         float* const q = T + ((2 * t + r) & (kSTRows - 1)) * kSW + 2 * lane;
         sts2(q, f2(nx[r].v[0], nx[r].v[3])); sts2(q + kSTRows * kSW, f2(nx[r].v[1], nx[r].v[4]));
         sts2(q + 2 * kSTRows * kSW, f2(nx[r].v[2], nx[r].v[5])); sts2(q + 3 * kSTRows * kSW, f2(nx[r].d[0], nx[r].d[1]));
+        sts2(q + 4 * kSTRows * kSW, f2(nx[r].e[0], nx[r].e[1]));
       }
       if (t + 1 < total) fetch();
     }
@@ -170,33 +175,17 @@ __device__ __forceinline__ void strip_role_l(const StripArgs& a, float* smem, co
 template <int NS, bool DERIVE>
 __device__ __forceinline__ void strip_role_o(const StripArgs& a, float* smem, const int lane, const StripCta cta) {
   using SM = StripSmem<NS>;
+  const float* const T = smem + SM::T + 2 * lane;
   const int total = cta.chunks, pend = cta.first + cta.count;
-  int opi = cta.first, oci = 0, qpi = cta.first, qci = 0;
-  StripPiece op = load_piece(a.pieces, opi), qp = op;
-  StripRow nx[2], cu[2];
-  auto fetch = [&]() {            // the "next rows" of chunk (qpi, qci): row ya + sg - 3 for step sg >= 2
-    const Level& L = a.lt.lv[qp.l];
-    const float* const tg = L.tgt + (long long)qp.b * L.tgt_bs;
-    const float* const ds = DERIVE ? a.depth[qp.l] : a.disp[qp.l];
-    const float* const dp = ds ? ds + (long long)qp.b * L.H * L.W : nullptr;
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int sg = 2 * qci + r;
-      nx[r] = strip_load_row(tg, dp, (a.do_smooth && sg >= 2 && sg < qp.yb - qp.ya + 4) ? L.H : 0, L.W, qp.ya + sg - 3,
-                             qp.x0 - 2 + 2 * lane);
-    }
-    if (++qci == qp.nch) { qci = 0; if (++qpi < pend) qp = load_piece(a.pieces, qpi); }
-  };
+  int opi = cta.first, oci = 0;
+  StripPiece op = load_piece(a.pieces, opi);
   // smoothness state: the current row (the row whose outputs are due) and the vertical terms of the pair above it
   float tc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dc[2] = {0.f, 0.f}, ty_up[2] = {0.f, 0.f};
   bool cur_in = false;
   float lsum_sm = 0.f;
-  fetch();
   for (int t = 0; t < total + kSLagO; ++t) {
     const int co = t - kSLagO;
     if (co >= 0) {
-      cu[0] = nx[0]; cu[1] = nx[1];
-      if (co + 1 < total) fetch();                 // one tick ahead of its use
       const Level& L = a.lt.lv[op.l];
       const int H = L.H, W = L.W, Lr = op.yb - op.ya;
       const int gx = op.x0 - 2 + 2 * lane;
@@ -213,10 +202,15 @@ __device__ __forceinline__ void strip_role_o(const StripArgs& a, float* smem, co
         float gd0 = 0.f, gd1 = 0.f, z0 = 0.f, z1 = 0.f;      // dL/ddisp of the smoothness term; disparity of the row
         if (a.do_smooth && sg >= 2 && sg < Lr + 4) {
           const bool nxt_in = (unsigned)(gy + 1) < (unsigned)H;
+          // the row below the output row (region row sg-1) was staged by the loader four ticks ago
           float tn[6], dn[2];
-#pragma unroll
-          for (int k = 0; k < 6; ++k) tn[k] = cu[r].v[k];
-          dn[0] = cu[r].d[0]; dn[1] = cu[r].d[1];
+          {
+            const float* q = T + ((s - 1) & (kSTRows - 1)) * kSW;
+            const float2 c0 = lds2(q), c1 = lds2(q + kSTRows * kSW), c2 = lds2(q + 2 * kSTRows * kSW);
+            const float2 dd = lds2(q + (DERIVE ? 3 : 4) * kSTRows * kSW);
+            tn[0] = c0.x; tn[1] = c1.x; tn[2] = c2.x; tn[3] = c0.y; tn[4] = c1.y; tn[5] = c2.y;
+            dn[0] = dd.x; dn[1] = dd.y;
+          }
           if (DERIVE) {
 #pragma unroll
             for (int k = 0; k < 2; ++k) dn[k] = dn[k] > 0.00001f ? __frcp_rn(dn[k]) : 0.f;     // safe_reciprocal_number
@@ -540,8 +534,8 @@ __device__ __forceinline__ void strip_role_s(const StripArgs& a, float* smem, co
         const float2 ic = cy == 3 ? col.ic3 : (cy == 2 ? col.ic2 : f2s(0.f));
         const bool row_c = sg >= 3 && sg < Lr + 3;                  // a centre row of this piece
         const float2 cnt_w = row_c ? f2mul(col.cen, nb1) : f2s(0.f);
-        float2 g = f2s(0.f);
-        if (a.do_ssim) {
+        float2 g;
+        {
           // ---- row sums of y, y^2, xy, x, x^2 over columns (c-1, c, c+1) -------------------------------------
           const float2 yn = shfl_lr(y), xn = shfl_lr(x);
           const float2 hy = hsum_nb(y, yn), hx = hsum_nb(x, xn);
@@ -582,7 +576,9 @@ __device__ __forceinline__ void strip_role_s(const StripArgs& a, float* smem, co
           g = f2fma(y2, sb, f2fma(x2, sc, sa));
         }
         // ---- L1 (loss_util.py:6-25): loss of row sg-1, gradient term of row sg-2 ------------------------------
-        if (a.do_l1) {
+        // (a term that is switched off has a zero coefficient -- hss2 or cl1 -- and its loss sum is dropped below:
+        //  no branch around the window state, so the row-to-row renaming costs no register moves)
+        {
           const float2 d1 = f2sub(y1, x1);
           ls_l1 = f2fma(cnt_w, f2(fabsf(d1.x), fabsf(d1.y)), ls_l1);
           g = f2add(g, l1t2);
@@ -597,7 +593,7 @@ __device__ __forceinline__ void strip_role_s(const StripArgs& a, float* smem, co
         const float v0 = warp_sum(ls_l1.x + ls_l1.y), v1 = warp_sum(ls_ss.x + ls_ss.y);
         if (lane == 0) {
           float* lb = smem + SM::loss + (pi & 1) * (3 * NS * 2) + (n * 3 + ch) * 2;
-          lb[0] = v0; lb[1] = v1;
+          lb[0] = a.do_l1 ? v0 : 0.f; lb[1] = a.do_ssim ? v1 : 0.f;
         }
         ls_l1 = f2s(0.f); ls_ss = f2s(0.f);
         wy.clear(); wyy.clear(); wxy.clear(); wx.clear(); wxx.clear(); wA.clear(); wB.clear(); wC.clear();
