@@ -74,8 +74,8 @@ struct StripSmem {
   static constexpr int kSrc = kD + kSDRows * kSW;                // floats per source
   static constexpr int src0 = T + kSTPlanes * kSTRows * kSW;
   static constexpr int geo = src0 + NS * kSrc;                   // [NS][32]: K rows 0-1, inv K rows 0-1, [R|t]
-  static constexpr int geoG = geo + NS * 32;                     // [(NS+1)/2][32]: [R|t] of a G warp's sources
-  static constexpr int loss = geoG + ((NS + 1) / 2) * 32;        // [2][3 NS][2]
+  static constexpr int geoG = geo + NS * 32;                     // [(NS+1)/2][48]: [R|t] of a G warp's sources, K, inv K
+  static constexpr int loss = geoG + ((NS + 1) / 2) * 48;        // [2][3 NS][2]
   static constexpr int stage = (loss + 2 * 3 * NS * 2 + 3) & ~3; // [NS][16 taps][32 lanes] float4: Y's gathers (cp.async)
   static constexpr int kFloats = stage + NS * 16 * 32 * 4;
   static constexpr size_t kBytes = sizeof(float) * kFloats;
@@ -620,21 +620,18 @@ __device__ __forceinline__ void strip_role_g(const StripArgs& a, float* smem, co
                                              const StripCta cta) {
   using SM = StripSmem<NS>;
   constexpr int NG = NS >= 2 ? 2 : 1;           // sources of this warp
-  float* const geo = smem + SM::geoG + gw * 32;  // [R (9) of source 0 | pad | R (9) of source 1]
+  float* const geo = smem + SM::geoG + gw * 48;  // [R|t] x 2 sources, K rows 0-1, inv K rows 0-1
   const int total = cta.chunks, pend = cta.first + cta.count;
   const int n0 = NG * gw;
   const bool live = n0 < a.N;
   int pi = cta.first, ci = 0;
   StripPiece p = load_piece(a.pieces, pi);
   bool fresh = true;
-  float gk[6], ki[6];
   float acc[NG][12];
 #pragma unroll
   for (int q = 0; q < NG; ++q)
 #pragma unroll
     for (int k = 0; k < 12; ++k) acc[q][k] = 0.f;
-#pragma unroll
-  for (int k = 0; k < 6; ++k) { gk[k] = 0.f; ki[k] = 0.f; }
   float2 cen = f2s(0.f), fx = f2s(0.f);
   int Lr = 0;
 
@@ -642,11 +639,15 @@ __device__ __forceinline__ void strip_role_g(const StripArgs& a, float* smem, co
     const int c = t - kSLagG;
     if (live && c >= 0 && c < total) {
       if (fresh) {
-        const float* K = a.geoK + (size_t)(p.b * a.S + p.l) * kGeoK;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) { gk[k] = __ldg(K + k); ki[k] = __ldg(K + 9 + k); }
+        // [R|t] of the two sources (24 words), then K rows 0-1 and inv K rows 0-1 (12 words)
         __syncwarp();
-        if (lane < 12 * NG && n0 + lane / 12 < a.N) geo[(lane / 12) * 12 + lane % 12] = __ldg(a.geoT + (size_t)(p.b * a.N + n0 + lane / 12) * kGeoT + lane % 12);
+        if (lane < 12 * NG) {
+          if (n0 + lane / 12 < a.N) geo[lane] = __ldg(a.geoT + (size_t)(p.b * a.N + n0 + lane / 12) * kGeoT + lane % 12);
+        } else if (lane >= 24) {
+          const int k = lane - 24;
+          if (k < 6) geo[24 + k] = __ldg(a.geoK + (size_t)(p.b * a.S + p.l) * kGeoK + k);
+        }
+        if (lane < 6) geo[30 + lane] = __ldg(a.geoK + (size_t)(p.b * a.S + p.l) * kGeoK + 9 + lane);
         __syncwarp();
         const int W = a.lt.lv[p.l].W, gx = p.x0 - 2 + 2 * lane;
         cen = f2((2 * lane >= 2 && 2 * lane < 2 + p.cw && gx < W) ? 1.f : 0.f,
@@ -663,8 +664,10 @@ __device__ __forceinline__ void strip_role_g(const StripArgs& a, float* smem, co
           const int kj = ((s - 2) & (kSJRows - 1)) * kSW + 2 * lane;
           constexpr int GP = kSGRows * kSW, JP = kSJRows * kSW;
           const float fy = (float)(p.ya + sg - 4);
-          const float2 r0 = ray_pair(ki[0], ki[1], ki[2], fx, fy);
-          const float2 r1 = ray_pair(ki[3], ki[4], ki[5], fx, fy);
+          const float4 kA = lds4(geo + 24), kB = lds4(geo + 28), kC = lds4(geo + 32);     // K0..K5 | Ki0..Ki5
+          const float gk[6] = {kA.x, kA.y, kA.z, kA.w, kB.x, kB.y};
+          const float2 r0 = ray_pair(kB.z, kB.w, kC.x, fx, fy);
+          const float2 r1 = ray_pair(kC.y, kC.z, kC.w, fx, fy);
 #pragma unroll
           for (int q = 0; q < NG; ++q) {
             if (n0 + q < a.N) {
@@ -724,17 +727,37 @@ __device__ __forceinline__ void strip_role_g(const StripArgs& a, float* smem, co
   }
 }
 
+// Warp order: L, O, G..., Y..., S...  For four sources the 20 warps are five aligned warpgroups -- {L, O, G0, G1},
+// {Y0..Y3} and three of statistics warps -- and the register file is re-divided with setmaxnreg: the statistics
+// role carries 16 sliding-window pairs and needs ~112 registers, every other role fits 72.
 template <int NS, bool DERIVE>
 __global__ void __launch_bounds__(StripSmem<NS>::kThreads, NS == 1 ? 2 : 1) k_strip(const __grid_constant__ StripArgs a) {
   extern __shared__ __align__(16) float smem[];
   const StripCta cta = a.ctas[blockIdx.x];
   if (cta.count == 0) return;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int NG = (NS + 1) / 2;
+  if (NS == 4) {
+    // one setmaxnreg per warpgroup, executed by its four warps together, then the warps part into their roles
+    if (wid < 4) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+      if (wid == 0) strip_role_l<NS>(a, smem, lane, cta);
+      else if (wid == 1) strip_role_o<NS, DERIVE>(a, smem, lane, cta);
+      else strip_role_g<NS>(a, smem, lane, wid - 2, cta);                       // G warp gw serves sources 2 gw, 2 gw + 1
+    } else if (wid < 8) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+      strip_role_y<NS>(a, smem, lane, wid - 4, cta);
+    } else {
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+      strip_role_s<NS>(a, smem, lane, (wid - 8) / 3, (wid - 8) % 3, cta);
+    }
+    return;
+  }
   if (wid == 0) strip_role_l<NS>(a, smem, lane, cta);
   else if (wid == 1) strip_role_o<NS, DERIVE>(a, smem, lane, cta);
-  else if (wid < 2 + NS) strip_role_y<NS>(a, smem, lane, wid - 2, cta);
-  else if (wid < 2 + 4 * NS) strip_role_s<NS>(a, smem, lane, (wid - NS - 2) / 3, (wid - NS - 2) % 3, cta);
-  else strip_role_g<NS>(a, smem, lane, wid - 4 * NS - 2, cta);      // G warp gw serves sources 2 gw, 2 gw + 1
+  else if (wid < 2 + NG) strip_role_g<NS>(a, smem, lane, wid - 2, cta);
+  else if (wid < 2 + NG + NS) strip_role_y<NS>(a, smem, lane, wid - 2 - NG, cta);
+  else strip_role_s<NS>(a, smem, lane, (wid - 2 - NG - NS) / 3, (wid - 2 - NG - NS) % 3, cta);
 }
 
 }  // namespace xpt
