@@ -17,7 +17,7 @@ src_lines = open(src).read().splitlines()
 role_of_line = {}
 for i, l in enumerate(src_lines, 1):
     m = re.search(r"strip_role_(\w)<", l)
-    if m and ("if (wid" in l or "else" in l):
+    if m and ("if (wid" in l or "else" in l or l.strip().startswith("strip_role")):
         role_of_line[i] = m.group(1).upper()
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, capture_output=True)

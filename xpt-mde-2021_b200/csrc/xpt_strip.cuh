@@ -32,12 +32,13 @@ constexpr int kSW = 64;                 // region columns of a strip (32 lanes x
 constexpr int kSCWMax = 60;             // centre columns (halo 2 on both sides)
 constexpr int kSTRows = 16;             // ring rows: target/depth/disparity (L -> Y, S, O)
 constexpr int kSTPlanes = 5;            // x0 x1 x2 depth disparity
-constexpr int kSYRows = 4;              //            warped value (Y -> S)
+constexpr int kSYRows = 8;              //            warped value (Y -> S; S re-reads the two rows before)
 constexpr int kSJRows = 8;              //            Jacobian     (Y -> G)
 constexpr int kSGRows = 4;              //            dL/dS        (S -> G)
 constexpr int kSDRows = 4;              //            dL/ddepth    (G -> O)
 constexpr int kSJPlanes = 10;           // gu[3], gv[3], u, v, 1/den, D
 constexpr int kSLagY = 1, kSLagS = 2, kSLagG = 3, kSLagO = 4;   // ticks behind the loader
+constexpr int kSLagEnd = kSLagO + 1;    // + one tick in which the output stage writes the last piece's loss record
 
 struct StripPiece { int b, l, x0, cw, ya, yb, slot, nch; };     // nch = ceil((yb - ya + 4) / 2) row chunks
 struct StripCta { int first, count, chunks, pad; };
@@ -67,19 +68,20 @@ struct StripArgs {
 template <int NS>
 struct StripSmem {
   static constexpr int T = 0;                                    // [5][16][64]: x0 x1 x2 depth disparity
-  static constexpr int kY = 0;                                   // per source: [4][4][64] y0 y1 y2 notblack
+  static constexpr int kY = 0;                                   // per source: [4][8][64] y0 y1 y2 notblack
   static constexpr int kJ = kY + 4 * kSYRows * kSW;              //             [10][8][64]
   static constexpr int kG = kJ + kSJPlanes * kSJRows * kSW;      //             [3][4][64]
   static constexpr int kD = kG + 3 * kSGRows * kSW;              //             [4][64]
   static constexpr int kSrc = kD + kSDRows * kSW;                // floats per source
   static constexpr int src0 = T + kSTPlanes * kSTRows * kSW;
   static constexpr int geo = src0 + NS * kSrc;                   // [NS][32]: K rows 0-1, inv K rows 0-1, [R|t]
-  static constexpr int geoG = geo + NS * 32;                     // [(NS+1)/2][48]: [R|t] of a G warp's sources, K, inv K
-  static constexpr int loss = geoG + ((NS + 1) / 2) * 48;        // [2][3 NS][2]
-  static constexpr int stage = (loss + 2 * 3 * NS * 2 + 3) & ~3; // [NS][16 taps][32 lanes] float4: Y's gathers (cp.async)
+  static constexpr int geoG = geo + NS * 32;                     // [NS][48]: [R|t] of a G warp's source, K, inv K
+  static constexpr int loss = geoG + NS * 48;                    // [2][3 NS][2]
+  static constexpr int lossO = loss + 2 * 3 * NS * 2;            // [2][2]: smoothness sums of the two output warps
+  static constexpr int stage = (lossO + 4 + 3) & ~3;             // [NS][16 taps][32 lanes] float4: Y's gathers (cp.async)
   static constexpr int kFloats = stage + NS * 16 * 32 * 4;
   static constexpr size_t kBytes = sizeof(float) * kFloats;
-  static constexpr int kWarps = 2 + NS + 3 * NS + (NS + 1) / 2;
+  static constexpr int kWarps = (NS == 4 ? 4 : 3) + NS + NS + 3 * NS;   // L (X) O0 O1 | G | Y | S
   static constexpr int kThreads = 32 * kWarps;
 };
 
@@ -105,6 +107,11 @@ __device__ __forceinline__ float2 ray_pair(float k0, float k1, float k2, float2 
 __device__ __forceinline__ float strip_box_inv(int cy, int cx) { return (cy > 0 && cx > 0) ? box_inv(cy * cx) : 0.f; }
 __device__ __forceinline__ int strip_cnt(int g, int n) {      // in-image members of {g-1, g, g+1}; 0 when g is outside
   return ((unsigned)g < (unsigned)n) ? (min(g + 1, n - 1) - max(g - 1, 0) + 1) : 0;
+}
+
+template <int NS>
+__device__ __forceinline__ void strip_role_idle(const StripCta cta) {
+  for (int t = 0; t < cta.chunks + kSLagEnd; ++t) strip_bar();
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -153,7 +160,7 @@ __device__ __forceinline__ void strip_role_l(const StripArgs& a, float* smem, co
     if (++ci == p.nch) { ci = 0; if (++pi < pend) p = load_piece(a.pieces, pi); }
   };
   fetch();
-  for (int t = 0; t < total + kSLagO; ++t) {
+  for (int t = 0; t < total + kSLagEnd; ++t) {
     if (t < total) {
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
@@ -173,139 +180,135 @@ __device__ __forceinline__ void strip_role_l(const StripArgs& a, float* smem, co
 // forward + backward on rows walked top to bottom, loss record of the piece.  Rows are requested one tick ahead.
 // ---------------------------------------------------------------------------------------------------------
 template <int NS, bool DERIVE>
-__device__ __forceinline__ void strip_role_o(const StripArgs& a, float* smem, const int lane, const StripCta cta) {
+__device__ __forceinline__ void strip_role_o(const StripArgs& a, float* smem, const int lane, const int k,
+                                             const StripCta cta) {
   using SM = StripSmem<NS>;
   const float* const T = smem + SM::T + 2 * lane;
   const int total = cta.chunks, pend = cta.first + cta.count;
   int opi = cta.first, oci = 0;
   StripPiece op = load_piece(a.pieces, opi);
-  // smoothness state: the current row (the row whose outputs are due) and the vertical terms of the pair above it
-  float tc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dc[2] = {0.f, 0.f}, ty_up[2] = {0.f, 0.f};
-  bool cur_in = false;
   float lsum_sm = 0.f;
-  for (int t = 0; t < total + kSLagO; ++t) {
+  // the loss record of a finished piece is written one tick later by warp 0 (both warps' sums are in shared memory then)
+  int pend_b = -1, pend_slot = 0, pend_l = 0, pend_par = 0;
+  for (int t = 0; t < total + kSLagEnd; ++t) {
     const int co = t - kSLagO;
-    if (co >= 0) {
+    if (k == 0 && pend_b >= 0) {
+      if (lane == 0) {
+        const float* lb = smem + SM::loss + pend_par * (3 * NS * 2);
+        float l1 = 0.f, ss = 0.f;
+        for (int q = 0; q < 3 * NS; ++q)
+          if (q < 3 * a.N) { l1 += lb[2 * q]; ss += lb[2 * q + 1]; }
+        const float* lo = smem + SM::lossO + pend_par * 2;
+        float* out = a.loss_part + ((size_t)pend_b * a.slots_per_b + pend_slot) * 3;
+        out[0] = l1 * a.norm_photo[pend_l]; out[1] = ss * a.norm_photo[pend_l]; out[2] = lo[0] + lo[1];
+      }
+      pend_b = -1;
+    }
+    if (co >= 0 && co < total) {
       const Level& L = a.lt.lv[op.l];
       const int H = L.H, W = L.W, Lr = op.yb - op.ya;
       const int gx = op.x0 - 2 + 2 * lane;
-      const float k3 = a.grad_factor;
-      const float nx_ = a.norm_sm_x[op.l], ny_ = a.norm_sm_y[op.l];
-      const float gcx = a.gcoef_smooth * nx_, gcy = a.gcoef_smooth * ny_;
       const bool cen0 = 2 * lane >= 2 && 2 * lane < 2 + op.cw && gx < W;
       const bool cen1 = 2 * lane + 1 >= 2 && 2 * lane + 1 < 2 + op.cw && gx + 1 < W;
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const int s = 2 * co + r, sg = 2 * oci + r;
-        const int gy = op.ya + sg - 4;                       // row whose outputs are due at this step
-        const bool out_row = sg >= 4 && sg < Lr + 4;
+      const int s = 2 * co + k, sg = 2 * oci + k;
+      const int gy = op.ya + sg - 4;                         // row whose outputs are due at this step
+      if (sg >= 4 && sg < Lr + 4) {
         float gd0 = 0.f, gd1 = 0.f, z0 = 0.f, z1 = 0.f;      // dL/ddisp of the smoothness term; disparity of the row
-        if (a.do_smooth && sg >= 2 && sg < Lr + 4) {
-          const bool nxt_in = (unsigned)(gy + 1) < (unsigned)H;
-          // the row below the output row (region row sg-1) was staged by the loader four ticks ago
-          float tn[6], dn[2];
-          {
-            const float* q = T + ((s - 1) & (kSTRows - 1)) * kSW;
+        if (a.do_smooth) {
+          const float k3 = a.grad_factor;
+          const float nx_ = a.norm_sm_x[op.l], ny_ = a.norm_sm_y[op.l];
+          const float gcx = a.gcoef_smooth * nx_, gcy = a.gcoef_smooth * ny_;
+          // rows gy-1, gy, gy+1 (region rows sg-3 .. sg-1) were staged by the loader; zero outside the image
+          float tr[3][6], dr[3][2];
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const float* q = T + ((s - 3 + j) & (kSTRows - 1)) * kSW;
             const float2 c0 = lds2(q), c1 = lds2(q + kSTRows * kSW), c2 = lds2(q + 2 * kSTRows * kSW);
             const float2 dd = lds2(q + (DERIVE ? 3 : 4) * kSTRows * kSW);
-            tn[0] = c0.x; tn[1] = c1.x; tn[2] = c2.x; tn[3] = c0.y; tn[4] = c1.y; tn[5] = c2.y;
-            dn[0] = dd.x; dn[1] = dd.y;
-          }
-          if (DERIVE) {
+            tr[j][0] = c0.x; tr[j][1] = c1.x; tr[j][2] = c2.x; tr[j][3] = c0.y; tr[j][4] = c1.y; tr[j][5] = c2.y;
+            dr[j][0] = dd.x; dr[j][1] = dd.y;
+            if (DERIVE) {
 #pragma unroll
-            for (int k = 0; k < 2; ++k) dn[k] = dn[k] > 0.00001f ? __frcp_rn(dn[k]) : 0.f;     // safe_reciprocal_number
-          }
-          if (sg >= 3) {
-            // vertical pairs (current row, next row) of both columns
-            float ty[2] = {0.f, 0.f}, sdy[2] = {0.f, 0.f};
-            if (cur_in && nxt_in) {
-#pragma unroll
-              for (int k = 0; k < 2; ++k) {
-                float e = 0.f;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) e += fabsf((tc[3 * k + c] - tn[3 * k + c]) * k3);
-                const float w = expf(-(e * (1.f / 3.f)));
-                const float sd = (dc[k] - dn[k]) * w;
-                sdy[k] = sd;
-                ty[k] = gcy * sgnf(sd) * w;
-              }
+              for (int i = 0; i < 2; ++i) dr[j][i] = dr[j][i] > 0.00001f ? __frcp_rn(dr[j][i]) : 0.f;   // safe_reciprocal_number
             }
-            // horizontal pairs of the current row: (A, B) inside the lane, (B, right lane's A) across lanes
-            float rt[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) rt[c] = __shfl_down_sync(0xffffffffu, tc[c], 1);
-            const float rd = __shfl_down_sync(0xffffffffu, dc[0], 1);
-            float txA = 0.f, txB = 0.f, sdxA = 0.f, sdxB = 0.f;
-            if (cur_in) {
-              if ((unsigned)gx < (unsigned)W && gx + 1 < W) {
-                float e = 0.f;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) e += fabsf((tc[c] - tc[3 + c]) * k3);
-                const float w = expf(-(e * (1.f / 3.f)));
-                sdxA = (dc[0] - dc[1]) * w;
-                txA = gcx * sgnf(sdxA) * w;
-              }
-              if (gx + 1 >= 0 && gx + 2 < W && lane < 31) {
-                float e = 0.f;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) e += fabsf((tc[3 + c] - rt[c]) * k3);
-                const float w = expf(-(e * (1.f / 3.f)));
-                sdxB = (dc[1] - rd) * w;
-                txB = gcx * sgnf(sdxB) * w;
-              }
-            }
-            const float txL = __shfl_up_sync(0xffffffffu, txB, 1);       // pair (left lane's B, A)
-            if (out_row) {
-              // forward terms of the pairs a pixel starts, gradient of all four pairs it is part of
-              if (cen0) lsum_sm += fabsf(sdxA) * nx_ + fabsf(sdy[0]) * ny_;
-              if (cen1) lsum_sm += fabsf(sdxB) * nx_ + fabsf(sdy[1]) * ny_;
-              gd0 = txA; gd0 += ty[0]; gd0 -= (lane > 0 ? txL : 0.f); gd0 -= ty_up[0];
-              gd1 = txB; gd1 += ty[1]; gd1 -= txA; gd1 -= ty_up[1];
-              z0 = dc[0]; z1 = dc[1];
-            }
-            ty_up[0] = ty[0]; ty_up[1] = ty[1];
           }
+          const bool up_in = gy >= 1, dn_in = gy + 1 < H;
+          // vertical pairs (gy-1, gy) and (gy, gy+1) of both columns
+          float ty_up[2] = {0.f, 0.f}, ty[2] = {0.f, 0.f}, sdy[2] = {0.f, 0.f};
 #pragma unroll
-          for (int k = 0; k < 6; ++k) tc[k] = tn[k];
-          dc[0] = dn[0]; dc[1] = dn[1];
-          cur_in = nxt_in;
+          for (int i = 0; i < 2; ++i) {
+            if (up_in) {
+              float e = 0.f;
+#pragma unroll
+              for (int c = 0; c < 3; ++c) e += fabsf((tr[0][3 * i + c] - tr[1][3 * i + c]) * k3);
+              const float w = expf(-(e * (1.f / 3.f)));
+              const float sd = (dr[0][i] - dr[1][i]) * w;
+              ty_up[i] = gcy * sgnf(sd) * w;
+            }
+            if (dn_in) {
+              float e = 0.f;
+#pragma unroll
+              for (int c = 0; c < 3; ++c) e += fabsf((tr[1][3 * i + c] - tr[2][3 * i + c]) * k3);
+              const float w = expf(-(e * (1.f / 3.f)));
+              const float sd = (dr[1][i] - dr[2][i]) * w;
+              sdy[i] = sd;
+              ty[i] = gcy * sgnf(sd) * w;
+            }
+          }
+          // horizontal pairs of row gy: (A, B) inside the lane, (B, right lane's A) across lanes
+          float rt[3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) rt[c] = __shfl_down_sync(0xffffffffu, tr[1][c], 1);
+          const float rd = __shfl_down_sync(0xffffffffu, dr[1][0], 1);
+          float txA = 0.f, txB = 0.f, sdxA = 0.f, sdxB = 0.f;
+          if ((unsigned)gx < (unsigned)W && gx + 1 < W) {
+            float e = 0.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) e += fabsf((tr[1][c] - tr[1][3 + c]) * k3);
+            const float w = expf(-(e * (1.f / 3.f)));
+            sdxA = (dr[1][0] - dr[1][1]) * w;
+            txA = gcx * sgnf(sdxA) * w;
+          }
+          if (gx + 1 >= 0 && gx + 2 < W && lane < 31) {
+            float e = 0.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) e += fabsf((tr[1][3 + c] - rt[c]) * k3);
+            const float w = expf(-(e * (1.f / 3.f)));
+            sdxB = (dr[1][1] - rd) * w;
+            txB = gcx * sgnf(sdxB) * w;
+          }
+          const float txL = __shfl_up_sync(0xffffffffu, txB, 1);       // pair (left lane's B, A)
+          // forward terms of the pairs a pixel starts, gradient of all four pairs it is part of (losses.py:409-440)
+          if (cen0) lsum_sm += fabsf(sdxA) * nx_ + fabsf(sdy[0]) * ny_;
+          if (cen1) lsum_sm += fabsf(sdxB) * nx_ + fabsf(sdy[1]) * ny_;
+          gd0 = txA; gd0 += ty[0]; gd0 -= (lane > 0 ? txL : 0.f); gd0 -= ty_up[0];
+          gd1 = txB; gd1 += ty[1]; gd1 -= txA; gd1 -= ty_up[1];
+          z0 = dr[1][0]; z1 = dr[1][1];
         }
-        if (out_row) {
-          float g0 = 0.f, g1 = 0.f;
-          if (DERIVE && a.do_smooth) { g0 = -(gd0 * z0) * z0; g1 = -(gd1 * z1) * z1; }   // d disp / d depth = -disp^2
+        float g0 = 0.f, g1 = 0.f;
+        if (DERIVE && a.do_smooth) { g0 = -(gd0 * z0) * z0; g1 = -(gd1 * z1) * z1; }   // d disp / d depth = -disp^2
 #pragma unroll
-          for (int n = 0; n < NS; ++n)
-            if (n < a.N) {
-              const float2 v = lds2(smem + SM::src0 + n * SM::kSrc + SM::kD + ((s - 2) & (kSDRows - 1)) * kSW + 2 * lane);
-              g0 += v.x; g1 += v.y;
-            }
-          const long long o = (long long)op.b * H * W + (long long)gy * W + gx;
-          if (a.d_depth[op.l]) {
-            if (cen0) a.d_depth[op.l][o] = g0;
-            if (cen1) a.d_depth[op.l][o + 1] = g1;
+        for (int n = 0; n < NS; ++n)
+          if (n < a.N) {
+            const float2 v = lds2(smem + SM::src0 + n * SM::kSrc + SM::kD + ((s - 2) & (kSDRows - 1)) * kSW + 2 * lane);
+            g0 += v.x; g1 += v.y;
           }
-          if (!DERIVE && a.do_smooth && a.d_disp[op.l]) {
-            if (cen0) a.d_disp[op.l][o] = gd0;
-            if (cen1) a.d_disp[op.l][o + 1] = gd1;
-          }
+        const long long o = (long long)op.b * H * W + (long long)gy * W + gx;
+        if (a.d_depth[op.l]) {
+          if (cen0) a.d_depth[op.l][o] = g0;
+          if (cen1) a.d_depth[op.l][o + 1] = g1;
+        }
+        if (!DERIVE && a.do_smooth && a.d_disp[op.l]) {
+          if (cen0) a.d_disp[op.l][o] = gd0;
+          if (cen1) a.d_disp[op.l][o + 1] = gd1;
         }
       }
       if (++oci == op.nch) {
-        // piece done: loss partial record (the S warps left their sums two ticks ago)
+        // piece done: this warp's smoothness sum -> shared memory; the record is written next tick
         const float sm = warp_sum(lsum_sm);
-        if (lane == 0) {
-          const float* lb = smem + SM::loss + (opi & 1) * (3 * NS * 2);
-          float l1 = 0.f, ss = 0.f;
-          for (int k = 0; k < 3 * NS; ++k)
-            if (k < 3 * a.N) { l1 += lb[2 * k]; ss += lb[2 * k + 1]; }
-          float* out = a.loss_part + ((size_t)op.b * a.slots_per_b + op.slot) * 3;
-          out[0] = l1 * a.norm_photo[op.l]; out[1] = ss * a.norm_photo[op.l]; out[2] = sm;
-        }
+        if (lane == 0) smem[SM::lossO + (opi & 1) * 2 + k] = sm;
+        pend_b = op.b; pend_slot = op.slot; pend_l = op.l; pend_par = opi & 1;
         lsum_sm = 0.f; oci = 0;
-        ty_up[0] = ty_up[1] = 0.f; cur_in = false;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) tc[k] = 0.f;
-        dc[0] = dc[1] = 0.f;
         if (++opi < pend) op = load_piece(a.pieces, opi);
       }
     }
@@ -339,7 +342,7 @@ __device__ __forceinline__ void strip_role_y(const StripArgs& a, float* smem, co
   StripPiece p = load_piece(a.pieces, pi);
   bool fresh = true;
 
-  for (int t = 0; t < total + kSLagO; ++t) {
+  for (int t = 0; t < total + kSLagEnd; ++t) {
     const int c = t - kSLagY;
     if (live && c >= 0 && c < total) {
       const Level& L = a.lt.lv[p.l];
@@ -515,19 +518,20 @@ __device__ __forceinline__ void strip_role_s(const StripArgs& a, float* smem, co
 
   Win2 wy, wyy, wxy, wx, wxx, wA, wB, wC;
   wy.clear(); wyy.clear(); wxy.clear(); wx.clear(); wxx.clear(); wA.clear(); wB.clear(); wC.clear();
-  float2 y1 = f2s(0.f), x1 = f2s(0.f), nb1 = f2s(0.f);       // row sg-1
-  float2 y2 = f2s(0.f), x2 = f2s(0.f), l1t2 = f2s(0.f);      // row sg-2
+  float2 l1t2 = f2s(0.f);                                    // L1 gradient term of row sg-2
   float2 ls_l1 = f2s(0.f), ls_ss = f2s(0.f);
 
-  for (int t = 0; t < total + kSLagO; ++t) {
+  for (int t = 0; t < total + kSLagEnd; ++t) {
     const int c = t - kSLagS;
     if (live && c >= 0 && c < total) {
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         const int s = 2 * c + r, sg = 2 * ci + r;
-        const float2 y = lds2(Yc + (s & (kSYRows - 1)) * kSW);
-        const float2 nb = lds2(Ynb + (s & (kSYRows - 1)) * kSW);
-        const float2 x = lds2(Tx + (s & (kSTRows - 1)) * kSW);
+        // rows sg (window sums), sg-1 (L1, loss masks) and sg-2 (dL/dS) straight from the rings: no row history in registers
+        const float2 y = lds2(Yc + (s & (kSYRows - 1)) * kSW), x = lds2(Tx + (s & (kSTRows - 1)) * kSW);
+        const float2 y1 = lds2(Yc + ((s - 1) & (kSYRows - 1)) * kSW), x1 = lds2(Tx + ((s - 1) & (kSTRows - 1)) * kSW);
+        const float2 nb1 = lds2(Ynb + ((s - 1) & (kSYRows - 1)) * kSW);
+        const float2 y2 = lds2(Yc + ((s - 2) & (kSYRows - 1)) * kSW), x2 = lds2(Tx + ((s - 2) & (kSTRows - 1)) * kSW);
         // statistics row sg-1 (image row gy1): 1/#taps, centre-row flag
         const int gy1 = p.ya - 3 + sg;
         const int cy = strip_cnt(gy1, H);
@@ -586,7 +590,6 @@ __device__ __forceinline__ void strip_role_s(const StripArgs& a, float* smem, co
           l1t2 = f2(d1.x == 0.f ? 0.f : copysignf(nbc.x, d1.x), d1.y == 0.f ? 0.f : copysignf(nbc.y, d1.y));
         }
         sts2(Gc + ((s - 2) & (kSGRows - 1)) * kSW, g);
-        y2 = y1; x2 = x1; y1 = y; x1 = x; nb1 = nb;
       }
       if (++ci == p.nch) {
         // piece done: loss sums of this (source, channel) -> scratch of the output stage; windows restart
@@ -597,7 +600,7 @@ __device__ __forceinline__ void strip_role_s(const StripArgs& a, float* smem, co
         }
         ls_l1 = f2s(0.f); ls_ss = f2s(0.f);
         wy.clear(); wyy.clear(); wxy.clear(); wx.clear(); wxx.clear(); wA.clear(); wB.clear(); wC.clear();
-        y1 = x1 = nb1 = y2 = x2 = l1t2 = f2s(0.f);
+        l1t2 = f2s(0.f);
         ci = 0;
         if (++pi < pend) {
           p = load_piece(a.pieces, pi);
@@ -613,13 +616,13 @@ __device__ __forceinline__ void strip_role_s(const StripArgs& a, float* smem, co
 
 // ---------------------------------------------------------------------------------------------------------
 // G: dL/dS x Jacobian -> projection adjoint: dL/ddepth per pixel, dL/dR, dL/dt sums per piece.
-// One warp serves two sources (2 gw, 2 gw + 1), one after the other per row.
+// One warp per source.
 // ---------------------------------------------------------------------------------------------------------
 template <int NS>
 __device__ __forceinline__ void strip_role_g(const StripArgs& a, float* smem, const int lane, const int gw,
                                              const StripCta cta) {
   using SM = StripSmem<NS>;
-  constexpr int NG = NS >= 2 ? 2 : 1;           // sources of this warp
+  constexpr int NG = 1;                         // sources of this warp
   float* const geo = smem + SM::geoG + gw * 48;  // [R|t] x 2 sources, K rows 0-1, inv K rows 0-1
   const int total = cta.chunks, pend = cta.first + cta.count;
   const int n0 = NG * gw;
@@ -635,7 +638,7 @@ __device__ __forceinline__ void strip_role_g(const StripArgs& a, float* smem, co
   float2 cen = f2s(0.f), fx = f2s(0.f);
   int Lr = 0;
 
-  for (int t = 0; t < total + kSLagO; ++t) {
+  for (int t = 0; t < total + kSLagEnd; ++t) {
     const int c = t - kSLagG;
     if (live && c >= 0 && c < total) {
       if (fresh) {
@@ -727,37 +730,40 @@ __device__ __forceinline__ void strip_role_g(const StripArgs& a, float* smem, co
   }
 }
 
-// Warp order: L, O, G..., Y..., S...  For four sources the 20 warps are five aligned warpgroups -- {L, O, G0, G1},
-// {Y0..Y3} and three of statistics warps -- and the register file is re-divided with setmaxnreg: the statistics
-// role carries 16 sliding-window pairs and needs ~112 registers, every other role fits 72.
+// Warp order: L (X) O0 O1 | G... | Y... | S...  For four sources the 24 warps are six aligned warpgroups -- {L, X, O0, O1},
+// {G0..G3}, {Y0..Y3} and three of statistics warps -- and the register file is re-divided with setmaxnreg: the
+// statistics role carries 16 sliding-window pairs (96 registers), the warp role 72, the adjoint role 64, the rest 56
+// (24 warps x 80 at launch = 12 x 96 + 4 x 72 + 4 x 64 + 4 x 56: the pool is used up exactly).
 template <int NS, bool DERIVE>
 __global__ void __launch_bounds__(StripSmem<NS>::kThreads, NS == 1 ? 2 : 1) k_strip(const __grid_constant__ StripArgs a) {
   extern __shared__ __align__(16) float smem[];
   const StripCta cta = a.ctas[blockIdx.x];
   if (cta.count == 0) return;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int NG = (NS + 1) / 2;
   if (NS == 4) {
     // one setmaxnreg per warpgroup, executed by its four warps together, then the warps part into their roles
     if (wid < 4) {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
       if (wid == 0) strip_role_l<NS>(a, smem, lane, cta);
-      else if (wid == 1) strip_role_o<NS, DERIVE>(a, smem, lane, cta);
-      else strip_role_g<NS>(a, smem, lane, wid - 2, cta);                       // G warp gw serves sources 2 gw, 2 gw + 1
+      else if (wid == 1) strip_role_idle<NS>(cta);
+      else strip_role_o<NS, DERIVE>(a, smem, lane, wid - 2, cta);
     } else if (wid < 8) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+      strip_role_g<NS>(a, smem, lane, wid - 4, cta);
+    } else if (wid < 12) {
       asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
-      strip_role_y<NS>(a, smem, lane, wid - 4, cta);
+      strip_role_y<NS>(a, smem, lane, wid - 8, cta);
     } else {
-      asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
-      strip_role_s<NS>(a, smem, lane, (wid - 8) / 3, (wid - 8) % 3, cta);
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
+      strip_role_s<NS>(a, smem, lane, (wid - 12) / 3, (wid - 12) % 3, cta);
     }
     return;
   }
   if (wid == 0) strip_role_l<NS>(a, smem, lane, cta);
-  else if (wid == 1) strip_role_o<NS, DERIVE>(a, smem, lane, cta);
-  else if (wid < 2 + NG) strip_role_g<NS>(a, smem, lane, wid - 2, cta);
-  else if (wid < 2 + NG + NS) strip_role_y<NS>(a, smem, lane, wid - 2 - NG, cta);
-  else strip_role_s<NS>(a, smem, lane, (wid - 2 - NG - NS) / 3, (wid - 2 - NG - NS) % 3, cta);
+  else if (wid < 3) strip_role_o<NS, DERIVE>(a, smem, lane, wid - 1, cta);
+  else if (wid < 3 + NS) strip_role_g<NS>(a, smem, lane, wid - 3, cta);
+  else if (wid < 3 + 2 * NS) strip_role_y<NS>(a, smem, lane, wid - 3 - NS, cta);
+  else strip_role_s<NS>(a, smem, lane, (wid - 3 - 2 * NS) / 3, (wid - 3 - 2 * NS) % 3, cta);
 }
 
 }  // namespace xpt
