@@ -12,7 +12,7 @@ import tempfile
 
 rep, so, fn_pat = sys.argv[1], sys.argv[2], sys.argv[3]
 detail = sys.argv[4] if len(sys.argv) > 4 else None
-src = os.path.join(os.path.dirname(os.path.abspath(so)), "..", "..", "csrc", "xpt_strip.cuh")
+src = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "xpt-mde-2021_b200", "csrc", "xpt_strip.cuh")
 src_lines = open(src).read().splitlines()
 role_of_line = {}
 for i, l in enumerate(src_lines, 1):

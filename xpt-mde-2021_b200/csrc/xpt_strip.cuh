@@ -37,7 +37,8 @@ constexpr int kSJRows = 8;              //            Jacobian     (Y -> G)
 constexpr int kSGRows = 4;              //            dL/dS        (S -> G)
 constexpr int kSDRows = 4;              //            dL/ddepth    (G -> O)
 constexpr int kSJPlanes = 10;           // gu[3], gv[3], u, v, 1/den, D
-constexpr int kSLagY = 1, kSLagS = 2, kSLagG = 3, kSLagO = 4;   // ticks behind the loader
+constexpr int kSLagY = 1, kSLagB = 2, kSLagX = 2, kSLagS = 3, kSLagG = 4, kSLagO = 5;   // ticks behind the loader
+constexpr int kSXRows = 4, kSXPlanes = 11;   // target-statistics ring (X -> S): mux[3], mux^2+c1 [3], sigma_x+c2 [3], 1/#taps, centre flags
 constexpr int kSLagEnd = kSLagO + 1;    // + one tick in which the output stage writes the last piece's loss record
 
 struct StripPiece { int b, l, x0, cw, ya, yb, slot, nch; };     // nch = ceil((yb - ya + 4) / 2) row chunks
@@ -74,18 +75,43 @@ struct StripSmem {
   static constexpr int kD = kG + 3 * kSGRows * kSW;              //             [4][64]
   static constexpr int kSrc = kD + kSDRows * kSW;                // floats per source
   static constexpr int src0 = T + kSTPlanes * kSTRows * kSW;
-  static constexpr int geo = src0 + NS * kSrc;                   // [NS][32]: K rows 0-1, inv K rows 0-1, [R|t]
+  static constexpr int X = src0 + NS * kSrc;                     // [11][4][64] target statistics of a row (X -> S)
+  static constexpr int geo = X + kSXPlanes * kSXRows * kSW;      // [NS][32]: K rows 0-1, inv K rows 0-1, [R|t]
   static constexpr int geoG = geo + NS * 32;                     // [NS][48]: [R|t] of a G warp's source, K, inv K
   static constexpr int loss = geoG + NS * 48;                    // [2][3 NS][2]
   static constexpr int lossO = loss + 2 * 3 * NS * 2;            // [2][2]: smoothness sums of the two output warps
-  static constexpr int stage = (lossO + 4 + 3) & ~3;             // [NS][16 taps][32 lanes] float4: Y's gathers (cp.async)
-  static constexpr int kFloats = stage + NS * 16 * 32 * 4;
+  static constexpr int stage = (lossO + 4 + 3) & ~3;             // [NS][16 taps + 8 aux][32 lanes] float4: Y's gathers (cp.async)
+  static constexpr int kStage = 24 * 32 * 4;                     //   and the per-sample weights / coordinates kept across the tick
+  static constexpr int kFloats = stage + NS * kStage;
   static constexpr size_t kBytes = sizeof(float) * kFloats;
-  static constexpr int kWarps = (NS == 4 ? 4 : 3) + NS + NS + 3 * NS;   // L (X) O0 O1 | G | Y | S
+  static constexpr int kWarps = 4 + NS + NS + 3 * NS;   // L X O0 O1 | G | Y | S
   static constexpr int kThreads = 32 * kWarps;
 };
 
+// XPT_STRIP_PROF (profiles/strip_roles_time.py only): every warp adds up the cycles between leaving a tick barrier and
+// arriving at the next one = its busy time per tick; the slowest role is the critical path of the pipeline
+#ifdef XPT_STRIP_PROF
+__device__ long long g_strip_busy[148 * 8 * 32];
+__device__ __forceinline__ long long strip_clock() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)); return t; }
+struct StripTimer {
+  long long busy, t0;
+  __device__ __forceinline__ StripTimer() : busy(0), t0(strip_clock()) {}
+  __device__ __forceinline__ ~StripTimer() { if ((threadIdx.x & 31) == 0 && blockIdx.x < 148 * 8) g_strip_busy[blockIdx.x * 32 + (threadIdx.x >> 5)] = busy; }
+};
+#define STRIP_TIMER() StripTimer strip_timer_
+// BAR.SYNC does not block at issue (the warp stalls at the next shared-memory access): touch shared memory after the
+// barrier and make the clock read depend on that load, so t0 is the release time
+__device__ __forceinline__ long long strip_clock_after_smem() {
+  unsigned v; long long t;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(0u) : "memory");
+  asm volatile("{ .reg .u64 c; mov.u64 c, %%clock64; and.b32 %1, %1, 0; cvt.u64.u32 %0, %1; add.u64 %0, %0, c; }" : "=l"(t), "+r"(v));
+  return t;
+}
+#define strip_bar() do { strip_timer_.busy += strip_clock() - strip_timer_.t0; asm volatile("bar.sync 0;" ::: "memory"); strip_timer_.t0 = strip_clock_after_smem(); } while (0)
+#else
+#define STRIP_TIMER() ((void)0)
 __device__ __forceinline__ void strip_bar() { asm volatile("bar.sync 0;" ::: "memory"); }
+#endif
 __device__ __forceinline__ void sts2(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float2 f2sub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
@@ -107,11 +133,6 @@ __device__ __forceinline__ float2 ray_pair(float k0, float k1, float k2, float2 
 __device__ __forceinline__ float strip_box_inv(int cy, int cx) { return (cy > 0 && cx > 0) ? box_inv(cy * cx) : 0.f; }
 __device__ __forceinline__ int strip_cnt(int g, int n) {      // in-image members of {g-1, g, g+1}; 0 when g is outside
   return ((unsigned)g < (unsigned)n) ? (min(g + 1, n - 1) - max(g - 1, 0) + 1) : 0;
-}
-
-template <int NS>
-__device__ __forceinline__ void strip_role_idle(const StripCta cta) {
-  for (int t = 0; t < cta.chunks + kSLagEnd; ++t) strip_bar();
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -160,6 +181,7 @@ __device__ __forceinline__ void strip_role_l(const StripArgs& a, float* smem, co
     if (++ci == p.nch) { ci = 0; if (++pi < pend) p = load_piece(a.pieces, pi); }
   };
   fetch();
+  STRIP_TIMER();
   for (int t = 0; t < total + kSLagEnd; ++t) {
     if (t < total) {
 #pragma unroll
@@ -190,6 +212,7 @@ __device__ __forceinline__ void strip_role_o(const StripArgs& a, float* smem, co
   float lsum_sm = 0.f;
   // the loss record of a finished piece is written one tick later by warp 0 (both warps' sums are in shared memory then)
   int pend_b = -1, pend_slot = 0, pend_l = 0, pend_par = 0;
+  STRIP_TIMER();
   for (int t = 0; t < total + kSLagEnd; ++t) {
     const int co = t - kSLagO;
     if (k == 0 && pend_b >= 0) {
@@ -335,14 +358,66 @@ __device__ __forceinline__ void strip_role_y(const StripArgs& a, float* smem, co
   float* const Yr = smem + SM::src0 + n * SM::kSrc + SM::kY;
   float* const Jr = smem + SM::src0 + n * SM::kSrc + SM::kJ;
   float* const geo = smem + SM::geo + n * 32;
-  float* const stg = smem + SM::stage + n * (16 * 32 * 4) + lane * 4;     // [tap][lane] float4
+  float* const stg = smem + SM::stage + n * SM::kStage + lane * 4;     // [16 taps + 8 aux][lane] float4
   const int total = cta.chunks, pend = cta.first + cta.count;
   const bool live = n < a.N;
   int pi = cta.first, ci = 0;
   StripPiece p = load_piece(a.pieces, pi);
   bool fresh = true;
 
+  STRIP_TIMER();
   for (int t = 0; t < total + kSLagEnd; ++t) {
+    // ---- phase B of chunk t-2: the gathers requested one tick ago have landed: bilinear value + Jacobian -> rings ----
+    const int cb = t - kSLagB;
+    if (live && cb >= 0 && cb < total) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int s = 2 * cb + r;
+        float2 yxy[2], guxy[2], gvxy[2];
+        float yz[2], guz[2], gvz[2], su[2], sv[2], si[2], Dd[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int q = 2 * r + k;
+          const float4 t0 = lds4(stg + (4 * q + 0) * 128), t1 = lds4(stg + (4 * q + 1) * 128);
+          const float4 t2 = lds4(stg + (4 * q + 2) * 128), t3 = lds4(stg + (4 * q + 3) * 128);
+          const float4 wq = lds4(stg + (16 + 2 * q) * 128), cq = lds4(stg + (17 + 2 * q) * 128);
+          const float wuf = wq.x, wuc = wq.y, wvf = wq.z, wvc = wq.w;
+          su[k] = cq.x; sv[k] = cq.y; si[k] = cq.z; Dd[k] = cq.w;
+          // I0 = (vf,uf), I1 = (vc,uf), I2 = (vf,uc), I3 = (vc,uc)   (bilinear_interp.py:125-128)
+          const float w0 = wuf * wvf, w1 = wuf * wvc, w2 = wuc * wvf, w3 = wuc * wvc;
+          const float2 a0 = f2(t0.x, t0.y), a1 = f2(t1.x, t1.y), a2 = f2(t2.x, t2.y), a3 = f2(t3.x, t3.y);
+          yxy[k] = f2fma(a3, f2s(w3), f2fma(a2, f2s(w2), f2fma(a0, f2s(w0), f2mul(a1, f2s(w1)))));
+          yz[k] = fmaf(t3.z, w3, fmaf(t2.z, w2, fmaf(t0.z, w0, t1.z * w1)));
+          const float2 d20 = f2sub(a2, a0), d31 = f2sub(a3, a1), d10 = f2sub(a1, a0), d32 = f2sub(a3, a2);
+          guxy[k] = f2fma(f2s(wvf), d20, f2mul(f2s(wvc), d31));
+          gvxy[k] = f2fma(f2s(wuf), d10, f2mul(f2s(wuc), d32));
+          guz[k] = fmaf(wvf, t2.z - t0.z, wvc * (t3.z - t1.z));
+          gvz[k] = fmaf(wuf, t1.z - t0.z, wuc * (t3.z - t2.z));
+        }
+        float* const q = Yr + (s & (kSYRows - 1)) * kSW + 2 * lane;
+        sts2(q, f2(yxy[0].x, yxy[1].x));
+        sts2(q + kSYRows * kSW, f2(yxy[0].y, yxy[1].y));
+        sts2(q + 2 * kSYRows * kSW, f2(yz[0], yz[1]));
+        // mean_c(synth) == 0 marks an invalid pixel for the losses (loss_util.py:15-16)
+        const float nb0 = (((yxy[0].x + yxy[0].y) + yz[0]) == 0.f) ? 0.f : 1.f;
+        const float nb1 = (((yxy[1].x + yxy[1].y) + yz[1]) == 0.f) ? 0.f : 1.f;
+        sts2(q + 3 * kSYRows * kSW, f2(nb0, nb1));
+        float* const j = Jr + (s & (kSJRows - 1)) * kSW + 2 * lane;
+        constexpr int JP = kSJRows * kSW;
+        sts2(j, f2(guxy[0].x, guxy[1].x));
+        sts2(j + JP, f2(guxy[0].y, guxy[1].y));
+        sts2(j + 2 * JP, f2(guz[0], guz[1]));
+        sts2(j + 3 * JP, f2(gvxy[0].x, gvxy[1].x));
+        sts2(j + 4 * JP, f2(gvxy[0].y, gvxy[1].y));
+        sts2(j + 5 * JP, f2(gvz[0], gvz[1]));
+        sts2(j + 6 * JP, f2(su[0], su[1]));
+        sts2(j + 7 * JP, f2(sv[0], sv[1]));
+        sts2(j + 8 * JP, f2(si[0], si[1]));
+        sts2(j + 9 * JP, f2(Dd[0], Dd[1]));
+      }
+    }
+    // ---- phase A of chunk t-1: projection + taps of both rows, the sixteen gathers requested (global -> shared) ------
     const int c = t - kSLagY;
     if (live && c >= 0 && c < total) {
       const Level& L = a.lt.lv[p.l];
@@ -360,8 +435,6 @@ __device__ __forceinline__ void strip_role_y(const StripArgs& a, float* smem, co
       const float fx0 = (float)(p.x0 - 2 + 2 * lane);
       const float2 fx = f2(fx0, fx0 + 1.f);
       const float wlim = (float)(W - 2), hlim = (float)(H - 2);
-      float wuf[4], wuc[4], wvf[4], wvc[4];
-      // ---- phase A: projection + taps of both rows, gathers requested --------------------------------------------
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         const int s = 2 * c + r, sg = 2 * ci + r;
@@ -394,7 +467,6 @@ __device__ __forceinline__ void strip_role_y(const StripArgs& a, float* smem, co
           inv = rr;
         }
         const float us[2] = {pu.x, pu.y}, vs[2] = {pv.x, pv.y}, Ds[2] = {D.x, D.y}, is[2] = {inv.x, inv.y};
-        float su[2], sv[2], si[2];
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
           const int q = 2 * r + k;
@@ -403,64 +475,22 @@ __device__ __forceinline__ void strip_role_y(const StripArgs& a, float* smem, co
           const bool val = (uf >= 0.f) && (uf <= wlim) && (vf >= 0.f) && (vf <= hlim) && (Ds[k] != 0.f);
           const int iu = val ? (int)uf : 0, iv = val ? (int)vf : 0;
           // weights * valid_mask (bilinear_interp.py:100): an invalid sample gathers texel (0,0) with zero weights
-          wuf[q] = val ? (uf + 1.f) - us[k] : 0.f;
-          wuc[q] = val ? us[k] - uf : 0.f;
-          wvf[q] = val ? (vf + 1.f) - vs[k] : 0.f;
-          wvc[q] = val ? vs[k] - vf : 0.f;
-          su[k] = val ? us[k] : 0.f; sv[k] = val ? vs[k] : 0.f; si[k] = val ? is[k] : 0.f;
-          // I0 = (vf,uf), I1 = (vc,uf), I2 = (vf,uc), I3 = (vc,uc)   (bilinear_interp.py:125-128)
+          float4 wq, cq;
+          wq.x = val ? (uf + 1.f) - us[k] : 0.f;
+          wq.y = val ? us[k] - uf : 0.f;
+          wq.z = val ? (vf + 1.f) - vs[k] : 0.f;
+          wq.w = val ? vs[k] - vf : 0.f;
+          cq.x = val ? us[k] : 0.f; cq.y = val ? vs[k] : 0.f; cq.z = val ? is[k] : 0.f; cq.w = Ds[k];
           const float4* tp = img4 + (iv * W + iu);
           cp_async16(stg + (4 * q + 0) * 128, tp);
           cp_async16(stg + (4 * q + 1) * 128, tp + W);
           cp_async16(stg + (4 * q + 2) * 128, tp + 1);
           cp_async16(stg + (4 * q + 3) * 128, tp + W + 1);
+          *reinterpret_cast<float4*>(stg + (16 + 2 * q) * 128) = wq;
+          *reinterpret_cast<float4*>(stg + (17 + 2 * q) * 128) = cq;
         }
-        float* const j = Jr + (s & (kSJRows - 1)) * kSW + 2 * lane;
-        constexpr int JP = kSJRows * kSW;
-        sts2(j + 6 * JP, f2(su[0], su[1]));
-        sts2(j + 7 * JP, f2(sv[0], sv[1]));
-        sts2(j + 8 * JP, f2(si[0], si[1]));
-        sts2(j + 9 * JP, D);
       }
-      cp_async_wait_all();
-      // ---- phase B: bilinear value + Jacobian of the four samples -> rings ------------------------------------------
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const int s = 2 * c + r;
-        float2 yxy[2], guxy[2], gvxy[2];
-        float yz[2], guz[2], gvz[2];
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const int q = 2 * r + k;
-          const float4 t0 = lds4(stg + (4 * q + 0) * 128), t1 = lds4(stg + (4 * q + 1) * 128);
-          const float4 t2 = lds4(stg + (4 * q + 2) * 128), t3 = lds4(stg + (4 * q + 3) * 128);
-          const float w0 = wuf[q] * wvf[q], w1 = wuf[q] * wvc[q], w2 = wuc[q] * wvf[q], w3 = wuc[q] * wvc[q];
-          const float2 a0 = f2(t0.x, t0.y), a1 = f2(t1.x, t1.y), a2 = f2(t2.x, t2.y), a3 = f2(t3.x, t3.y);
-          yxy[k] = f2fma(a3, f2s(w3), f2fma(a2, f2s(w2), f2fma(a0, f2s(w0), f2mul(a1, f2s(w1)))));
-          yz[k] = fmaf(t3.z, w3, fmaf(t2.z, w2, fmaf(t0.z, w0, t1.z * w1)));
-          const float2 d20 = f2sub(a2, a0), d31 = f2sub(a3, a1), d10 = f2sub(a1, a0), d32 = f2sub(a3, a2);
-          guxy[k] = f2fma(f2s(wvf[q]), d20, f2mul(f2s(wvc[q]), d31));
-          gvxy[k] = f2fma(f2s(wuf[q]), d10, f2mul(f2s(wuc[q]), d32));
-          guz[k] = fmaf(wvf[q], t2.z - t0.z, wvc[q] * (t3.z - t1.z));
-          gvz[k] = fmaf(wuf[q], t1.z - t0.z, wuc[q] * (t3.z - t2.z));
-        }
-        float* const q = Yr + (s & (kSYRows - 1)) * kSW + 2 * lane;
-        sts2(q, f2(yxy[0].x, yxy[1].x));
-        sts2(q + kSYRows * kSW, f2(yxy[0].y, yxy[1].y));
-        sts2(q + 2 * kSYRows * kSW, f2(yz[0], yz[1]));
-        // mean_c(synth) == 0 marks an invalid pixel for the losses (loss_util.py:15-16)
-        const float nb0 = (((yxy[0].x + yxy[0].y) + yz[0]) == 0.f) ? 0.f : 1.f;
-        const float nb1 = (((yxy[1].x + yxy[1].y) + yz[1]) == 0.f) ? 0.f : 1.f;
-        sts2(q + 3 * kSYRows * kSW, f2(nb0, nb1));
-        float* const j = Jr + (s & (kSJRows - 1)) * kSW + 2 * lane;
-        constexpr int JP = kSJRows * kSW;
-        sts2(j, f2(guxy[0].x, guxy[1].x));
-        sts2(j + JP, f2(guxy[0].y, guxy[1].y));
-        sts2(j + 2 * JP, f2(guz[0], guz[1]));
-        sts2(j + 3 * JP, f2(gvxy[0].x, gvxy[1].x));
-        sts2(j + 4 * JP, f2(gvxy[0].y, gvxy[1].y));
-        sts2(j + 5 * JP, f2(gvz[0], gvz[1]));
-      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
       if (++ci == p.nch) { ci = 0; fresh = true; if (++pi < pend) p = load_piece(a.pieces, pi); }
     }
     strip_bar();
@@ -468,7 +498,7 @@ __device__ __forceinline__ void strip_role_y(const StripArgs& a, float* smem, co
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// S: window statistics, SSIM + L1, adjoint coefficients and their box sums for one (source, channel)
+// window machinery shared by the X and S roles
 // ---------------------------------------------------------------------------------------------------------
 struct Win2 {        // sliding 3-row window of a row quantity h: sum(h[r-2], h[r-1], h[r]) in the order ((a + b) + c)
   float2 p1, p2;     // p1 = h[r-1], p2 = h[r-2] + h[r-1]
@@ -499,11 +529,75 @@ __device__ __forceinline__ StripCols strip_cols(const StripPiece& p, int W, int 
   return c;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// X: window statistics of the TARGET rows (the same for every source): mu_x, mu_x^2 + c1, sigma_x + c2 of the three
+// channels (loss_util.py:70-84), plus the row's 1/#taps and centre flags, one tick ahead of the statistics warps
+// ---------------------------------------------------------------------------------------------------------
+template <int NS>
+__device__ __forceinline__ void strip_role_x(const StripArgs& a, float* smem, const int lane, const StripCta cta) {
+  using SM = StripSmem<NS>;
+  const float* const T = smem + SM::T + 2 * lane;
+  float* const X = smem + SM::X + 2 * lane;
+  const int total = cta.chunks, pend = cta.first + cta.count;
+  int pi = cta.first, ci = 0;
+  StripPiece p = load_piece(a.pieces, pi);
+  StripCols col = strip_cols(p, a.lt.lv[p.l].W, lane);
+  int H = a.lt.lv[p.l].H, Lr = p.yb - p.ya;
+  Win2 wx[3], wxx[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { wx[c].clear(); wxx[c].clear(); }
+  STRIP_TIMER();
+  for (int t = 0; t < total + kSLagEnd; ++t) {
+    const int c = t - kSLagX;
+    if (c >= 0 && c < total) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int s = 2 * c + r, sg = 2 * ci + r;
+        // statistics row sg-1 (image row gy1): 1/#taps, centre flags of that row
+        const int gy1 = p.ya - 3 + sg;
+        const int cy = strip_cnt(gy1, H);
+        const float2 ic = cy == 3 ? col.ic3 : (cy == 2 ? col.ic2 : f2s(0.f));
+        const bool row_c = sg >= 3 && sg < Lr + 3;                  // a centre row of this piece
+        float* const q = X + ((s - 1) & (kSXRows - 1)) * kSW;
+        constexpr int XP = kSXRows * kSW;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          const float2 x = lds2(T + ch * kSTRows * kSW + (s & (kSTRows - 1)) * kSW);
+          const float2 xn = shfl_lr(x);
+          const float2 Vx = wx[ch].push(hsum_nb(x, xn));
+          const float2 Vxx = wxx[ch].push(hsum_nb(f2mul(x, x), f2mul(xn, xn)));
+          const float2 mux = f2mul(Vx, ic), mux2 = f2mul(mux, mux);
+          sts2(q + ch * XP, mux);
+          sts2(q + (3 + ch) * XP, f2add(mux2, f2s(kC1)));
+          sts2(q + (6 + ch) * XP, f2add(f2fma(Vxx, ic, f2neg(mux2)), f2s(kC2)));
+        }
+        sts2(q + 9 * XP, ic);
+        sts2(q + 10 * XP, row_c ? col.cen : f2s(0.f));
+      }
+      if (++ci == p.nch) {
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) { wx[ch].clear(); wxx[ch].clear(); }
+        ci = 0;
+        if (++pi < pend) {
+          p = load_piece(a.pieces, pi);
+          col = strip_cols(p, a.lt.lv[p.l].W, lane);
+          H = a.lt.lv[p.l].H; Lr = p.yb - p.ya;
+        }
+      }
+    }
+    strip_bar();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// S: window statistics of the warped rows, SSIM + L1, adjoint coefficients and their box sums for one (source, channel)
+// ---------------------------------------------------------------------------------------------------------
 template <int NS>
 __device__ __forceinline__ void strip_role_s(const StripArgs& a, float* smem, const int lane, const int n, const int ch,
                                              const StripCta cta) {
   using SM = StripSmem<NS>;
   const float* const Tx = smem + SM::T + ch * kSTRows * kSW + 2 * lane;
+  const float* const Xs = smem + SM::X + 2 * lane;
   const float* const Yc = smem + SM::src0 + n * SM::kSrc + SM::kY + ch * kSYRows * kSW + 2 * lane;
   const float* const Ynb = smem + SM::src0 + n * SM::kSrc + SM::kY + 3 * kSYRows * kSW + 2 * lane;
   float* const Gc = smem + SM::src0 + n * SM::kSrc + SM::kG + ch * kSGRows * kSW + 2 * lane;
@@ -511,46 +605,40 @@ __device__ __forceinline__ void strip_role_s(const StripArgs& a, float* smem, co
   const bool live = n < a.N;
   int pi = cta.first, ci = 0;
   StripPiece p = load_piece(a.pieces, pi);
-  // constants of the current piece (set when the piece starts)
-  StripCols col = strip_cols(p, a.lt.lv[p.l].W, lane);
-  int H = a.lt.lv[p.l].H, Lr = p.yb - p.ya;
   float cl1 = a.gcoef_l1 * a.norm_photo[p.l], hss2 = -a.gcoef_ssim * a.norm_photo[p.l];
 
-  Win2 wy, wyy, wxy, wx, wxx, wA, wB, wC;
-  wy.clear(); wyy.clear(); wxy.clear(); wx.clear(); wxx.clear(); wA.clear(); wB.clear(); wC.clear();
+  Win2 wy, wyy, wxy, wA, wB, wC;
+  wy.clear(); wyy.clear(); wxy.clear(); wA.clear(); wB.clear(); wC.clear();
   float2 l1t2 = f2s(0.f);                                    // L1 gradient term of row sg-2
   float2 ls_l1 = f2s(0.f), ls_ss = f2s(0.f);
 
+  STRIP_TIMER();
   for (int t = 0; t < total + kSLagEnd; ++t) {
     const int c = t - kSLagS;
     if (live && c >= 0 && c < total) {
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
-        const int s = 2 * c + r, sg = 2 * ci + r;
+        const int s = 2 * c + r;
         // rows sg (window sums), sg-1 (L1, loss masks) and sg-2 (dL/dS) straight from the rings: no row history in registers
         const float2 y = lds2(Yc + (s & (kSYRows - 1)) * kSW), x = lds2(Tx + (s & (kSTRows - 1)) * kSW);
         const float2 y1 = lds2(Yc + ((s - 1) & (kSYRows - 1)) * kSW), x1 = lds2(Tx + ((s - 1) & (kSTRows - 1)) * kSW);
         const float2 nb1 = lds2(Ynb + ((s - 1) & (kSYRows - 1)) * kSW);
         const float2 y2 = lds2(Yc + ((s - 2) & (kSYRows - 1)) * kSW), x2 = lds2(Tx + ((s - 2) & (kSTRows - 1)) * kSW);
-        // statistics row sg-1 (image row gy1): 1/#taps, centre-row flag
-        const int gy1 = p.ya - 3 + sg;
-        const int cy = strip_cnt(gy1, H);
-        const float2 ic = cy == 3 ? col.ic3 : (cy == 2 ? col.ic2 : f2s(0.f));
-        const bool row_c = sg >= 3 && sg < Lr + 3;                  // a centre row of this piece
-        const float2 cnt_w = row_c ? f2mul(col.cen, nb1) : f2s(0.f);
+        // target statistics, 1/#taps and centre flags of statistics row sg-1 (X role)
+        const float* const xq = Xs + ((s - 1) & (kSXRows - 1)) * kSW;
+        constexpr int XP = kSXRows * kSW;
+        const float2 mux = lds2(xq + ch * XP), MUX2C = lds2(xq + (3 + ch) * XP), SGXC = lds2(xq + (6 + ch) * XP);
+        const float2 ic = lds2(xq + 9 * XP);
+        const float2 cnt_w = f2mul(lds2(xq + 10 * XP), nb1);
         float2 g;
         {
-          // ---- row sums of y, y^2, xy, x, x^2 over columns (c-1, c, c+1) -------------------------------------
+          // ---- row sums of y, y^2, xy over columns (c-1, c, c+1) -----------------------------------------------
           const float2 yn = shfl_lr(y), xn = shfl_lr(x);
-          const float2 hy = hsum_nb(y, yn), hx = hsum_nb(x, xn);
+          const float2 hy = hsum_nb(y, yn);
           const float2 hyy = hsum_nb(f2mul(y, y), f2mul(yn, yn));
           const float2 hxy = hsum_nb(f2mul(x, y), f2mul(xn, yn));
-          const float2 hxx = hsum_nb(f2mul(x, x), f2mul(xn, xn));
-          const float2 Vy = wy.push(hy), Vyy = wyy.push(hyy), Vxy = wxy.push(hxy), Vx = wx.push(hx), Vxx = wxx.push(hxx);
+          const float2 Vy = wy.push(hy), Vyy = wyy.push(hyy), Vxy = wxy.push(hxy);
           // ---- SSIM, loss, adjoint coefficients of row sg-1 (loss_util.py:52-96) -----------------------------
-          const float2 mux = f2mul(Vx, ic), mux2 = f2mul(mux, mux);
-          const float2 MUX2C = f2add(mux2, f2s(kC1));
-          const float2 SGXC = f2add(f2fma(Vxx, ic, f2neg(mux2)), f2s(kC2));
           const float2 muy = f2mul(Vy, ic), muy2 = f2mul(muy, muy), mxy = f2mul(mux, muy);
           const float2 sgy = f2fma(Vyy, ic, f2neg(muy2));
           const float2 sgxy = f2fma(Vxy, ic, f2neg(mxy));
@@ -599,13 +687,11 @@ __device__ __forceinline__ void strip_role_s(const StripArgs& a, float* smem, co
           lb[0] = a.do_l1 ? v0 : 0.f; lb[1] = a.do_ssim ? v1 : 0.f;
         }
         ls_l1 = f2s(0.f); ls_ss = f2s(0.f);
-        wy.clear(); wyy.clear(); wxy.clear(); wx.clear(); wxx.clear(); wA.clear(); wB.clear(); wC.clear();
+        wy.clear(); wyy.clear(); wxy.clear(); wA.clear(); wB.clear(); wC.clear();
         l1t2 = f2s(0.f);
         ci = 0;
         if (++pi < pend) {
           p = load_piece(a.pieces, pi);
-          col = strip_cols(p, a.lt.lv[p.l].W, lane);
-          H = a.lt.lv[p.l].H; Lr = p.yb - p.ya;
           cl1 = a.gcoef_l1 * a.norm_photo[p.l]; hss2 = -a.gcoef_ssim * a.norm_photo[p.l];
         }
       }
@@ -638,6 +724,7 @@ __device__ __forceinline__ void strip_role_g(const StripArgs& a, float* smem, co
   float2 cen = f2s(0.f), fx = f2s(0.f);
   int Lr = 0;
 
+  STRIP_TIMER();
   for (int t = 0; t < total + kSLagEnd; ++t) {
     const int c = t - kSLagG;
     if (live && c >= 0 && c < total) {
@@ -732,8 +819,16 @@ __device__ __forceinline__ void strip_role_g(const StripArgs& a, float* smem, co
 
 // Warp order: L (X) O0 O1 | G... | Y... | S...  For four sources the 24 warps are six aligned warpgroups -- {L, X, O0, O1},
 // {G0..G3}, {Y0..Y3} and three of statistics warps -- and the register file is re-divided with setmaxnreg: the
-// statistics role carries 16 sliding-window pairs (96 registers), the warp role 72, the adjoint role 64, the rest 56
-// (24 warps x 80 at launch = 12 x 96 + 4 x 72 + 4 x 64 + 4 x 56: the pool is used up exactly).
+// statistics role carries 12 sliding-window pairs (88 registers), the warp role 72, the adjoint role 64, the rest 80
+// (24 warps x 80 at launch = 12 x 88 + 4 x 72 + 4 x 64 + 4 x 80: the pool is used up exactly).
+// registers per thread of the four-source layout: statistics / warp / adjoint / {L, X, O0, O1} warps; launch = 80
+#ifndef XPT_REG_S
+#define XPT_REG_S 88
+#define XPT_REG_Y 72
+#define XPT_REG_G 64
+#define XPT_REG_W 80
+#endif
+static_assert(12 * XPT_REG_S + 4 * XPT_REG_Y + 4 * XPT_REG_G + 4 * XPT_REG_W == 24 * 80, "setmaxnreg: the register pool of the CTA must be used up exactly");
 template <int NS, bool DERIVE>
 __global__ void __launch_bounds__(StripSmem<NS>::kThreads, NS == 1 ? 2 : 1) k_strip(const __grid_constant__ StripArgs a) {
   extern __shared__ __align__(16) float smem[];
@@ -743,27 +838,30 @@ __global__ void __launch_bounds__(StripSmem<NS>::kThreads, NS == 1 ? 2 : 1) k_st
   if (NS == 4) {
     // one setmaxnreg per warpgroup, executed by its four warps together, then the warps part into their roles
     if (wid < 4) {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+      if (XPT_REG_W < 80) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(XPT_REG_W));
       if (wid == 0) strip_role_l<NS>(a, smem, lane, cta);
-      else if (wid == 1) strip_role_idle<NS>(cta);
+      else if (wid == 1) strip_role_x<NS>(a, smem, lane, cta);
       else strip_role_o<NS, DERIVE>(a, smem, lane, wid - 2, cta);
     } else if (wid < 8) {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(XPT_REG_G));
       strip_role_g<NS>(a, smem, lane, wid - 4, cta);
     } else if (wid < 12) {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+      if (XPT_REG_Y > 80) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(XPT_REG_Y));
+      else if (XPT_REG_Y < 80) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(XPT_REG_Y));
       strip_role_y<NS>(a, smem, lane, wid - 8, cta);
     } else {
-      asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
+      if (XPT_REG_S > 80) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(XPT_REG_S));
+      else if (XPT_REG_S < 80) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(XPT_REG_S));
       strip_role_s<NS>(a, smem, lane, (wid - 12) / 3, (wid - 12) % 3, cta);
     }
     return;
   }
   if (wid == 0) strip_role_l<NS>(a, smem, lane, cta);
-  else if (wid < 3) strip_role_o<NS, DERIVE>(a, smem, lane, wid - 1, cta);
-  else if (wid < 3 + NS) strip_role_g<NS>(a, smem, lane, wid - 3, cta);
-  else if (wid < 3 + 2 * NS) strip_role_y<NS>(a, smem, lane, wid - 3 - NS, cta);
-  else strip_role_s<NS>(a, smem, lane, (wid - 3 - 2 * NS) / 3, (wid - 3 - 2 * NS) % 3, cta);
+  else if (wid == 1) strip_role_x<NS>(a, smem, lane, cta);
+  else if (wid < 4) strip_role_o<NS, DERIVE>(a, smem, lane, wid - 2, cta);
+  else if (wid < 4 + NS) strip_role_g<NS>(a, smem, lane, wid - 4, cta);
+  else if (wid < 4 + 2 * NS) strip_role_y<NS>(a, smem, lane, wid - 4 - NS, cta);
+  else strip_role_s<NS>(a, smem, lane, (wid - 4 - 2 * NS) / 3, (wid - 4 - 2 * NS) % 3, cta);
 }
 
 }  // namespace xpt

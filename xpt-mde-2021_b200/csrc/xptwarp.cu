@@ -680,6 +680,12 @@ int launch_loss_epilogue(xpt_ctx* ctx, int slots_used, float w0, float w1, float
 extern "C" {
 
 int xpt_version(void) { return XPT_VERSION; }
+#ifdef XPT_STRIP_PROF
+// profiling build only (profiles/strip_roles_time.py): busy cycles of every warp of the last k_strip launch
+__attribute__((visibility("default"))) int xpt_debug_strip_busy(long long* out, int n) {
+  return cudaMemcpyFromSymbol(out, g_strip_busy, sizeof(long long) * n) == cudaSuccess ? 0 : -1;
+}
+#endif
 const char* xpt_last_error(void) { return g_err; }
 
 const char* xpt_status_string(int status) {
