@@ -87,9 +87,11 @@ typedef struct {
 #define XPT_FLAG_GRAPH 2u
 /* xpt_total_loss_host runs the batch as ONE chunk (no copy/compute pipelining).                */
 #define XPT_FLAG_NO_PIPELINE 4u
-/* xpt_total_loss uses the round-1 tile kernel (k_fused, one CTA per 64x13 tile) instead of the streaming strip
- * kernel (k_strip) for training steps.  Same results; kept for A/B parity tests and profiling.               */
-#define XPT_FLAG_TILES 8u
+/* xpt_total_loss runs its training steps (gradients wanted, no synthesis tensors, no dL/dsource, <= 4 sources) on
+ * the streaming strip kernel (k_strip: warp-specialised roles marching down 64-column strips, no halo re-warp,
+ * per-ctx geometry from global memory) instead of the tile kernel (k_fused).  Same results to summation order.
+ * Opt-in: on B200 it reaches the tile kernel's speed but does not beat it yet.              */
+#define XPT_FLAG_STRIP 8u
 
 /* The snippet frames + intrinsics (features of losses.py:26-37).              */
 typedef struct {

@@ -50,7 +50,8 @@ ix = {h: i for i, h in enumerate(hdr)}
 body = [r for r in rows[2:] if len(r) >= len(hdr)]
 assert len(body) == len(locs), (len(body), len(locs))
 stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
-R = collections.defaultdict(lambda: dict(inst=0, smp=0, st=collections.Counter(), ops=collections.Counter(), lines=collections.Counter()))
+R = collections.defaultdict(lambda: dict(inst=0, smp=0, st=collections.Counter(), ops=collections.Counter(), lines=collections.Counter(),
+                                     lsmp=collections.Counter(), lst=collections.defaultdict(collections.Counter)))
 for r, (role, line, txt) in zip(body, locs):
     n = int(r[ix["Instructions Executed"]] or 0)
     d = R[role]
@@ -64,6 +65,11 @@ for r, (role, line, txt) in zip(body, locs):
     o = op[1] if op[0].startswith("@") and len(op) > 1 else op[0]
     d["ops"][o.split(".")[0]] += n
     d["lines"][line] += n
+    d["lsmp"][line] += int(r[ix["# Samples"]] or 0)
+    for s_ in stalls:
+        v = int(r[ix[s_]] or 0)
+        if v:
+            d["lst"][line][s_[6:]] += v
 tot = sum(d["inst"] for d in R.values())
 tots = sum(d["smp"] for d in R.values())
 print(f"total warp-inst {tot}, samples {tots}")
@@ -77,6 +83,8 @@ for role in "LOYSG-":
 if detail:
     d = R[detail]
     print(f"--- hottest lines of role {detail}")
-    for line, n in d["lines"].most_common(40):
-        txt = src_lines[line - 1].strip()[:110] if 0 < line <= len(src_lines) else ""
-        print(f"{line:4d} {100 * n / d['inst']:5.1f}%  {txt}")
+    print("line  inst%  samples%  top stalls")
+    for line, n in d["lsmp"].most_common(32):
+        txt = src_lines[line - 1].strip()[:90] if 0 < line <= len(src_lines) else ""
+        st = ", ".join(f"{k} {v}" for k, v in d["lst"][line].most_common(3))
+        print(f"{line:4d} {100 * d['lines'][line] / d['inst']:5.1f}% {100 * n / max(1, d['smp']):5.1f}%  [{st}]  {txt}")

@@ -16,7 +16,7 @@ import xptwarp  # noqa: E402
 from xptwarp.engine import infer_scales  # noqa: E402
 from oracle import xpt_oracle as orc  # noqa: E402
 
-TILES = 8
+STRIP = 8
 
 
 def rel(a, b):
@@ -31,7 +31,7 @@ def run(B, H, W, N, S, lw, sw, derive=False, seed=1):
          "pose": preds["pose"].cuda()}
     img = f["image5d"]
     out = {}
-    for name, flags in (("strip", 0), ("tiles", TILES)):
+    for name, flags in (("strip", STRIP), ("tiles", 0)):
         plan = xptwarp.get_plan(0, B, N, H, W, infer_scales(H, preds["depth_ms"]), sw, lw.get("L1", 0.0),
                                 lw.get("SSIM", 0.0), lw.get("smoothe", 0.0), B, flags)
         r = plan.total_loss(img[:, :-1], img[:, -1], f["intrinsic"], p["depth_ms"], None if derive else p["disp_ms"],
@@ -57,7 +57,7 @@ def timeit(B, H, W, N=4, S=4, iters=50):
          "pose": preds["pose"].cuda()}
     img = f["image5d"]
     lw, sw = orc.LOSS_RIGID_T1, orc.SCALE_WEIGHT_T1
-    for name, flags in (("strip", 2), ("tiles", TILES | 2)):
+    for name, flags in (("strip", STRIP | 2), ("tiles", 2)):
         plan = xptwarp.get_plan(0, B, N, H, W, infer_scales(H, preds["depth_ms"]), sw, lw["L1"], lw["SSIM"], lw["smoothe"],
                                 B, flags)
         st = torch.cuda.Stream()

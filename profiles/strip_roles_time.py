@@ -22,7 +22,7 @@ f = {k: v.cuda() for k, v in feats.items()}
 p = {"depth_ms": [d.cuda() for d in preds["depth_ms"]], "disp_ms": [d.cuda() for d in preds["disp_ms"]], "pose": preds["pose"].cuda()}
 img = f["image5d"]
 lw, sw = orc.LOSS_RIGID_T1, orc.SCALE_WEIGHT_T1
-plan = xptwarp.get_plan(0, B, 4, H, W, infer_scales(H, preds["depth_ms"]), sw, lw["L1"], lw["SSIM"], lw["smoothe"], B, 0)
+plan = xptwarp.get_plan(0, B, 4, H, W, infer_scales(H, preds["depth_ms"]), sw, lw["L1"], lw["SSIM"], lw["smoothe"], B, 8)
 for _ in range(5):
     plan.total_loss(img[:, :-1], img[:, -1], f["intrinsic"], p["depth_ms"], p["disp_ms"], p["pose"], want_grad=True)
 torch.cuda.synchronize()

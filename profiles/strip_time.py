@@ -11,7 +11,7 @@ import xptwarp  # noqa: E402
 from xptwarp.engine import infer_scales  # noqa: E402
 from oracle import xpt_oracle as orc  # noqa: E402
 
-flags = 2 | (8 if "tiles" in sys.argv[1:] else 0)
+flags = 2 | (0 if "tiles" in sys.argv[1:] else 8)
 out = []
 for (B, H, W, iters) in ((8, 128, 384, 100), (16, 256, 832, 30)):
     feats, preds = orc.make_inputs(B, H, W, seed=5)

@@ -367,12 +367,30 @@ __device__ __forceinline__ void strip_role_y(const StripArgs& a, float* smem, co
 
   STRIP_TIMER();
   for (int t = 0; t < total + kSLagEnd; ++t) {
-    // ---- phase B of chunk t-2: the gathers requested one tick ago have landed: bilinear value + Jacobian -> rings ----
-    const int cb = t - kSLagB;
-    if (live && cb >= 0 && cb < total) {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    const int cb = t - kSLagB, c = t - kSLagY;
+    const bool doB = live && cb >= 0 && cb < total, doA = live && c >= 0 && c < total;
+    const Level& L = a.lt.lv[p.l];
+    const int H = L.H, W = L.W;
+    if (doA && fresh) {
+      // camera geometry of this piece -> 24 shared-memory words of this warp (K rows 0-1, inv K rows 0-1, [R|t])
+      __syncwarp();
+      if (lane < 6) geo[lane] = __ldg(a.geoK + (size_t)(p.b * a.S + p.l) * kGeoK + lane);
+      else if (lane < 12) geo[lane] = __ldg(a.geoK + (size_t)(p.b * a.S + p.l) * kGeoK + 9 + (lane - 6));
+      else if (lane < 24) geo[lane] = __ldg(a.geoT + (size_t)(p.b * a.N + n) * kGeoT + (lane - 12));
+      __syncwarp();
+      fresh = false;
+    }
+    const float4* const img4 = a.src4[p.l] + (size_t)(p.b * a.N + n) * H * W;
+    const float fx0 = (float)(p.x0 - 2 + 2 * lane);
+    const float2 fx = f2(fx0, fx0 + 1.f);
+    const float wlim = (float)(W - 2), hlim = (float)(H - 2);
+    // Row by row: consume the gathers of row r of chunk t-2 (phase B), then request the gathers of row r of chunk
+    // t-1 into the half of the staging buffer that was just read (phase A): every gather has about half a tick to land.
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
+    for (int r = 0; r < 2; ++r) {
+      // ---- phase B: bilinear value + Jacobian of two samples -> rings -------------------------------------------
+      if (doB) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");      // all but the most recent request have landed
         const int s = 2 * cb + r;
         float2 yxy[2], guxy[2], gvxy[2];
         float yz[2], guz[2], gvz[2], su[2], sv[2], si[2], Dd[2];
@@ -416,27 +434,8 @@ __device__ __forceinline__ void strip_role_y(const StripArgs& a, float* smem, co
         sts2(j + 8 * JP, f2(si[0], si[1]));
         sts2(j + 9 * JP, f2(Dd[0], Dd[1]));
       }
-    }
-    // ---- phase A of chunk t-1: projection + taps of both rows, the sixteen gathers requested (global -> shared) ------
-    const int c = t - kSLagY;
-    if (live && c >= 0 && c < total) {
-      const Level& L = a.lt.lv[p.l];
-      const int H = L.H, W = L.W;
-      if (fresh) {
-        // camera geometry of this piece -> 24 shared-memory words of this warp (K rows 0-1, inv K rows 0-1, [R|t])
-        __syncwarp();
-        if (lane < 6) geo[lane] = __ldg(a.geoK + (size_t)(p.b * a.S + p.l) * kGeoK + lane);
-        else if (lane < 12) geo[lane] = __ldg(a.geoK + (size_t)(p.b * a.S + p.l) * kGeoK + 9 + (lane - 6));
-        else if (lane < 24) geo[lane] = __ldg(a.geoT + (size_t)(p.b * a.N + n) * kGeoT + (lane - 12));
-        __syncwarp();
-        fresh = false;
-      }
-      const float4* const img4 = a.src4[p.l] + (size_t)(p.b * a.N + n) * H * W;
-      const float fx0 = (float)(p.x0 - 2 + 2 * lane);
-      const float2 fx = f2(fx0, fx0 + 1.f);
-      const float wlim = (float)(W - 2), hlim = (float)(H - 2);
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
+      // ---- phase A: projection + taps of one row, its eight gathers requested (global -> shared) ------------------
+      if (doA) {
         const int s = 2 * c + r, sg = 2 * ci + r;
         const float fy = (float)(p.ya - 2 + sg);
         const float2 D = lds2(T + (3 * kSTRows + (s & (kSTRows - 1))) * kSW + 2 * lane);
@@ -490,9 +489,9 @@ __device__ __forceinline__ void strip_role_y(const StripArgs& a, float* smem, co
           *reinterpret_cast<float4*>(stg + (17 + 2 * q) * 128) = cq;
         }
       }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      if (++ci == p.nch) { ci = 0; fresh = true; if (++pi < pend) p = load_piece(a.pieces, pi); }
+      asm volatile("cp.async.commit_group;" ::: "memory");        // one group per row, empty when nothing was requested
     }
+    if (doA && ++ci == p.nch) { ci = 0; fresh = true; if (++pi < pend) p = load_piece(a.pieces, pi); }
     strip_bar();
   }
 }

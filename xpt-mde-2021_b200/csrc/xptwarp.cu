@@ -1182,7 +1182,7 @@ static int total_loss_body(xpt_ctx* ctx, const xpt_frames* frames, const float* 
     bool want_out0 = false;
     for (int l = 0; l < ctx->S; ++l) want_out0 = want_out0 || out->synth_ms[l] || out->mask_ms[l];
     // training step (gradients, no synthesis tensors, no dL/dsource, N <= 4): the streaming strip kernel
-    const bool use_strip = grad && !dsrc && !want_out0 && ctx->N <= 4 && !(c.flags & XPT_FLAG_TILES);
+    const bool use_strip = grad && !dsrc && !want_out0 && ctx->N <= 4 && (c.flags & XPT_FLAG_STRIP);
     if (use_strip) {
       XPT_TRY(prepare_strip(ctx));
       StripArgs sa;

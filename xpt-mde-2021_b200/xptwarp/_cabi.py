@@ -10,7 +10,7 @@ XPT_MAX_SCALES = 8
 XPT_FLAG_UNFUSED = 1
 XPT_FLAG_GRAPH = 2
 XPT_FLAG_NO_PIPELINE = 4
-XPT_FLAG_TILES = 8
+XPT_FLAG_STRIP = 8
 XPT_PHOTO_L1, XPT_PHOTO_L2, XPT_PHOTO_SSIM = 0, 1, 2
 
 _FP = C.POINTER(C.c_float)
