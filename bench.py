@@ -29,11 +29,20 @@ import torch  # noqa: E402
 METRIC = "fwd+bwd warp+loss Gpixels/s"
 UNIT = "Gpixel/s"
 WORKLOADS = {
-    # name: (B per rank, H, W)   -- BASELINE.json configs[1], [2], [4]
-    "cfg2": (8, 128, 384),
-    "cfg3": (16, 256, 832),
-    "cfg5": (128, 384, 1280),
+    # name: (B, H, W, scaling) -- BASELINE.json configs[1], [2], [3], [4]; "weak": B snippets per rank,
+    # "strong": B is the GLOBAL batch, sharded B / world per rank (configs[3]: 64 over 2/4/8 GPUs, configs[4]: 128)
+    "cfg2": (8, 128, 384, "weak"),
+    "cfg3": (16, 256, 832, "weak"),
+    "cfg4": (64, 128, 384, "strong"),
+    "cfg5": (128, 384, 1280, "strong"),
 }
+
+
+def workload_string(name, source_grad=False, adversarial=False):
+    """the same string in both arms (ours / reference), so the driver sees one config"""
+    B, H, W, scaling = WORKLOADS[name]
+    return (f"{name}: B={B}{'/gpu' if scaling == 'weak' else ' global'} {H}x{W} snippet=5 (4 sources) scales=4 LOSS_RIGID_T1 fwd+bwd"
+            + (" +dL/dsource" if source_grad else "") + (" ADVERSARIAL inputs (iid depth, large poses)" if adversarial else ""))
 N_SRC, N_SCALES = 4, 4
 GAMMA = sum(1.0 / (4 ** s) for s in range(N_SCALES))          # 85/64
 # algorithmic bytes per full-res target pixel (SURVEY 8d rows; DESIGN.md "Bytes model")
@@ -192,9 +201,10 @@ def run_reference(args, B, H, W):
     sample = f"{sb} of {B} snippets per step ({H}x{W}, 4 sources, 4 scales, fwd+bwd), {args.steps} steps"
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3 * (B / sb), "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": dt * 1e3 * (B / sb), "higher_is_better": True,
+        "scaling": WORKLOADS[args.workload][3],
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: B={B} {H}x{W} snippet=5 scales=4 LOSS_RIGID_T1",
+        "config": {"workload": workload_string(args.workload, args.source_grad, args.adversarial),
                    "note": "reference TF op graph restated on torch-CPU (TF 2.4.1 not installable offline)"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -220,11 +230,12 @@ def main():
     ap.add_argument("--adversarial", action="store_true",
                     help="SURVEY 8d's adversarial inputs: iid depth U(1,80) per pixel (worst-case gather locality) and "
                          "large poses (about half of the samples leave the image)")
+    ap.add_argument("--strip", action="store_true", help="the streaming strip kernel (XPT_FLAG_STRIP) instead of the tile kernel (A/B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=10)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    B, H, W = WORKLOADS[args.workload]
+    B, H, W, scaling = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, B, H, W)
         return
@@ -251,10 +262,20 @@ def main():
     from oracle import xpt_oracle as orc     # input generator + cpu_baseline checker only
 
     lw, sw = orc.LOSS_RIGID_T1, orc.SCALE_WEIGHT_T1
-    global_batch = B * world                # weak scaling: B snippets per rank (compute_average_loss divisor)
-    flags = (0 if args.no_graph else _cabi.XPT_FLAG_GRAPH) | (_cabi.XPT_FLAG_UNFUSED if args.unfused else 0)
+    if scaling == "strong":                 # B is the global batch: contiguous shards of B / world snippets
+        if B % world:
+            raise SystemExit(f"{args.workload}: global batch {B} does not divide over {world} ranks")
+        global_batch, B = B, B // world
+    else:
+        global_batch = B * world            # weak scaling: B snippets per rank (compute_average_loss divisor)
+    # world > 1: the path's only exchange -- the 4 loss scalars (distributer.py:93-110) -- is an ncclAllReduce the
+    # library enqueues on the step's own stream behind the epilogue kernel, i.e. one more node of the step's CUDA graph
+    flags = ((0 if args.no_graph else _cabi.XPT_FLAG_GRAPH) | (_cabi.XPT_FLAG_UNFUSED if args.unfused else 0)
+             | (_cabi.XPT_FLAG_STRIP if args.strip else 0) | (_cabi.XPT_FLAG_ALLREDUCE if world > 1 else 0))
     plan = xptwarp.get_plan(local_rank, B, N_SRC, H, W, [1, 2, 4, 8], sw, lw["L1"], lw["SSIM"], lw["smoothe"],
                             global_batch, flags)
+    if world > 1:
+        plan.comm_init(dist)
 
     # ---- inputs: enough distinct resident sets that a step never finds its inputs in the 126 MB L2
     probe_f, probe_p = orc.make_inputs(1, H, W, N=N_SRC, n_scales=N_SCALES, seed=1)
@@ -272,37 +293,25 @@ def main():
     torch.cuda.set_stream(side)
     stream = plan.stream()
 
-    pending = [None] * n_sets
     net_grad = None
-    net_pending = [None]
+    net_stream = None
     if dist is not None and args.net_grad_mb > 0:
-        from xptwarp.distributed import allreduce_gradient_buckets
         net_grad = torch.zeros(int(args.net_grad_mb * 1e6 / 4), dtype=torch.float32, device=device)
+        net_stream = torch.cuda.Stream(device)
 
     def step(i):
-        k = i % n_sets
-        if pending[k] is not None:            # this set's loss buffer is about to be rewritten
-            pending[k].wait()
-            pending[k] = None
-        c = calls[k]
-        c.run(stream)
-        if dist is not None:
-            # the path's only exchange: the 4 loss scalars (replaces distributer.py:93-110); asynchronous, so
-            # the NCCL kernel overlaps with the next step's launches instead of serialising the stream
-            pending[k] = dist.all_reduce(c.out["losses"], async_op=True)
-            if net_grad is not None:          # stand-in for the nets' gradient buckets (one bucket in flight)
-                if net_pending[0] is not None:
-                    net_pending[0].wait()
-                net_pending[0] = allreduce_gradient_buckets([net_grad])[0]
+        c = calls[i % n_sets]
+        c.run(stream)                         # world > 1: includes the in-graph all-reduce of the loss vector
+        if net_grad is not None:
+            # stand-in for the nets' gradient buckets: the library's NCCL group on a second stream,
+            # overlapped with the next step's kernels; one bucket in flight
+            net_stream.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(net_stream):
+                plan.allreduce([net_grad])
 
     def drain():
-        for k in range(n_sets):
-            if pending[k] is not None:
-                pending[k].wait()             # current stream waits for the collective
-                pending[k] = None
-        if net_pending[0] is not None:
-            net_pending[0].wait()
-            net_pending[0] = None
+        if net_stream is not None:
+            torch.cuda.current_stream(device).wait_stream(net_stream)
 
     def barrier():
         drain()
@@ -366,7 +375,7 @@ def main():
     pyr_ms = None
     if not args.unfused:
         eager = xptwarp.get_plan(local_rank, B, N_SRC, H, W, [1, 2, 4, 8], sw, lw["L1"], lw["SSIM"], lw["smoothe"],
-                                 global_batch, flags & ~_cabi.XPT_FLAG_GRAPH)
+                                 global_batch, flags & ~(_cabi.XPT_FLAG_GRAPH | _cabi.XPT_FLAG_ALLREDUCE))
         ecalls = []
         for (f, p), c in zip(sets, calls):
             img = f["image5d"]
@@ -403,7 +412,7 @@ def main():
                 rec = json.load(tf_).get(args.workload)
             if rec:
                 traffic = rec["dram_bytes_per_launch"]        # bytes per launch, from the committed ncu --set full capture
-        roofline = {"bound": "hbm", "kernel": "k_fused<grad>", "achieved": ach, "peak": peak, "unit": "GB/s",
+        roofline = {"bound": "hbm", "kernel": "k_strip" if args.strip else "k_fused<grad>", "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": ach / peak, "traffic": traffic, "algorithmic_bytes_per_launch": px_rank * fused_bytes,
                     "peak_source": peak_src, "kernel_ms": kern_ms, "kernel_ms_percentiles": kern_pct,
                     "bytes_per_pixel": fused_bytes, "kernel_share_of_step": kern_ms / ms_step if world == 1 else None}
@@ -484,17 +493,17 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": n_warm, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: B={B}/gpu {H}x{W} snippet=5 (4 sources) scales=4 LOSS_RIGID_T1 fwd+bwd"
-                                   + (" +dL/dsource" if args.source_grad else "")
-                                   + (" ADVERSARIAL inputs (iid depth, large poses)" if args.adversarial else ""),
-                       "global_batch": global_batch, "parallelism": f"dp{world}",
+            "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_string(args.workload, args.source_grad, args.adversarial),
+                       "global_batch": global_batch, "batch_per_gpu": B, "parallelism": f"dp{world}",
+                       "kernel": "k_strip (XPT_FLAG_STRIP)" if args.strip else "k_fused (tiles)",
                        "l2": f"rotating {n_sets} resident input sets ({n_sets * per_set / 1e6:.0f} MB > 126 MB L2)",
                        "launch": "eager" if args.no_graph else "cuda-graph replay", "fused": not args.unfused,
                        "host_affinity": numa or "unbound",
                        "collectives": ("none (1 GPU)" if world == 1 else
-                                       "all-reduce of the 4 loss scalars per step" +
-                                       (f" + a {args.net_grad_mb:g} MB stand-in net-gradient bucket" if args.net_grad_mb > 0 else ""))},
+                                       "ncclAllReduce of the 4 loss scalars inside the step's CUDA graph (XPT_FLAG_ALLREDUCE)" +
+                                       (f" + a {args.net_grad_mb:g} MB stand-in net-gradient bucket per step on a second stream"
+                                        if args.net_grad_mb > 0 else ""))},
             "roofline": roofline, "step_model": step_model, "cpu_baseline": cpu, "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches_per_step * args.steps,

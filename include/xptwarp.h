@@ -23,11 +23,10 @@
  *    the thread-local message.  There is no CPU fallback.
  *  - one xpt_ctx per (device, host thread); calls on one ctx must be serialised
  *    by the caller (stream order is enough when one stream is used).
- *  - the fused kernel reads the camera geometry from ONE __constant__ block per
- *    device, uploaded in stream order right before each launch: xpt_total_loss
- *    calls of DIFFERENT contexts on the same device must therefore also be ordered
- *    with respect to each other (issue them on one stream, as the Python host does,
- *    or synchronise between them).
+ *  - the fused tile kernel reads the camera geometry through the constant bank; every ctx owns a private slot
+ *    of it, so calls of different contexts on different streams of one device do not interfere.  (Only when
+ *    the 60 KB bank is exhausted -- more than ~15 live contexts of config-2 size -- does a new ctx share a slot;
+ *    such contexts must be ordered by their caller.  xpt_scratch_bytes' sibling xpt_geometry_slot_shared tells.)
  */
 #ifndef XPTWARP_H_
 #define XPTWARP_H_
@@ -45,7 +44,7 @@ extern "C" {
 #define XPT_API
 #endif
 
-#define XPT_VERSION 101        /* 0.1.1 */
+#define XPT_VERSION 200        /* 0.2.0 */
 #define XPT_MAX_SCALES 8
 
 typedef enum {
@@ -54,7 +53,11 @@ typedef enum {
   XPT_BAD_SHAPE = -2,      /* sizes not divisible by the scales, too small, ...   */
   XPT_CUDA_ERROR = -3,     /* a CUDA runtime call or kernel launch failed         */
   XPT_NO_DEVICE = -4,      /* no usable sm_100 device                            */
-  XPT_OUT_OF_MEMORY = -5   /* scratch allocation failed                          */
+  XPT_OUT_OF_MEMORY = -5,  /* scratch allocation failed                          */
+  XPT_BAD_DTYPE = -6,      /* a tensor that is not float32 (xpt_check_dlpack)     */
+  XPT_BAD_DEVICE = -7,     /* a tensor that does not live on the ctx's CUDA device */
+  XPT_NOT_CONTIGUOUS = -8, /* inner dimensions not dense (xpt_check_dlpack)       */
+  XPT_NCCL_ERROR = -9      /* libnccl missing, or an NCCL call failed             */
 } xpt_status;
 
 /* photometric term selector: reference loss_util.py:6-25 / :29-48 / :52-96 */
@@ -92,6 +95,17 @@ typedef struct {
  * per-ctx geometry from global memory) instead of the tile kernel (k_fused).  Same results to summation order.
  * Opt-in: on B200 it reaches the tile kernel's speed but does not beat it yet.              */
 #define XPT_FLAG_STRIP 8u
+/* multi-rank data parallelism (reference distributer.py:93-110 ReplicaOutputIntegrator): xpt_total_loss ends with an
+ * in-place ncclAllReduce(sum) of out->losses[4] over the communicator bound by xpt_comm_init / xpt_comm_attach,
+ * enqueued on the call's own stream right behind the epilogue kernel -- and therefore captured in the same CUDA
+ * graph as the step under XPT_FLAG_GRAPH.                                                                      */
+#define XPT_FLAG_ALLREDUCE 16u
+/* depth_ms[] holds the depth net's LOGITS.  xpt_total_loss applies the net's last op itself --
+ * InverseSigmoidActivation, depth = safe_reciprocal_number(sigmoid(x) + 0.01) (model/build_model/model_factory.py:
+ * 133-137) -- when it loads a depth tile, and d_depth_ms[] receives dL/dlogit.  With disp_ms == NULL the disparity
+ * of the smoothness term is formed in the kernel as well (model_wrappers.py:47-48), so the boundary takes one
+ * tensor per level from the net and returns one gradient per level.  Fused path only.                           */
+#define XPT_FLAG_DEPTH_LOGIT 32u
 
 /* The snippet frames + intrinsics (features of losses.py:26-37).              */
 typedef struct {
@@ -132,6 +146,8 @@ XPT_API void xpt_destroy(xpt_ctx* ctx);
 XPT_API int xpt_get_config(const xpt_ctx* ctx, xpt_config* out);
 /* bytes of device scratch held by the ctx */
 XPT_API size_t xpt_scratch_bytes(const xpt_ctx* ctx);
+/* 1 if this ctx found no private constant-bank slot for its camera geometry (see Conventions), else 0 */
+XPT_API int xpt_geometry_slot_shared(const xpt_ctx* ctx);
 
 /* utils/convert_pose.py:32-71  pose_rvec2matr_batch_tf: [B,N,6] -> [B,N,4,4] */
 XPT_API int xpt_pose_rvec2matr(xpt_ctx* ctx, const float* pose, float* matr, void* stream);
@@ -261,6 +277,30 @@ XPT_API int xpt_profile_begin(xpt_ctx* ctx, int max_records);
 #define XPT_PROFILE_PYRAMID 1      /* the single-pass tiled pyramid + geometry kernel (scales within 1,2,4,8) */
 XPT_API int xpt_profile_select(xpt_ctx* ctx, int kernel);
 XPT_API int xpt_profile_end(xpt_ctx* ctx, float* ms_out, int capacity);
+
+/* Validation of a tensor exchanged through DLPack, for hosts that unwrap capsules themselves: `dl_managed_tensor`
+ * points at a DLManagedTensor (dlpack.h v0.8 layout; a void* so that this header needs no DLPack include).
+ * Returns XPT_BAD_DTYPE unless float32 x 1 lane, XPT_BAD_DEVICE unless kDLCUDA on `device`,
+ * XPT_NOT_CONTIGUOUS unless the dimensions >= dense_from_dim are C-contiguous (leading dimensions may be strided:
+ * source = image5d[:, :-1] is legal with dense_from_dim = 2).                                                  */
+XPT_API int xpt_check_dlpack(const void* dl_managed_tensor, int device, int dense_from_dim);
+
+/* dst[i][j] = src[i][j] * scale[0] for `num` dense fp32 device tensors of counts[i] elements in ONE launch
+ * (`scale` is a DEVICE scalar: the upstream gradient of an autograd node, losses.py:49-54 under
+ * train_val.py:85).  dst[i] may equal src[i].                                                                  */
+XPT_API int xpt_scale_tensors(int device, const float* const src[], float* const dst[], const int64_t counts[], int num,
+                              const float* scale, void* stream);
+
+/* ---- multi-rank: one process per GPU, NCCL over NVLink (reference distributer.py:93-110) ----------------------
+ * libnccl.so.2 is bound at run time (dlopen; the copy PyTorch ships is found when torch is loaded).
+ * xpt_comm_unique_id: rank 0 creates the 128-byte rendezvous id and hands it to the other ranks (any channel).
+ * xpt_comm_init: every rank joins; the ctx owns the communicator.  xpt_comm_attach: borrow an existing ncclComm_t.
+ * xpt_allreduce: in-place sum of `num` dense fp32 device buffers as ONE NCCL group on `stream` (the loss vector and
+ * the pose / depth net gradient buckets of a step).                                                            */
+XPT_API int xpt_comm_unique_id(unsigned char id[128]);
+XPT_API int xpt_comm_init(xpt_ctx* ctx, const unsigned char id[128], int nranks, int rank);
+XPT_API int xpt_comm_attach(xpt_ctx* ctx, void* nccl_comm);
+XPT_API int xpt_allreduce(xpt_ctx* ctx, float* const bufs[], const int64_t counts[], int num, void* stream);
 
 /* number of kernels the last call on this ctx launched (bench's gpu_launches) */
 XPT_API int xpt_last_launch_count(const xpt_ctx* ctx);

@@ -103,6 +103,12 @@ def safe_reciprocal_number(x: torch.Tensor) -> torch.Tensor:
     return (1.0 / x) * mask
 
 
+def inverse_sigmoid_activation(x: torch.Tensor) -> torch.Tensor:
+    """model/build_model/model_factory.py:133-137 InverseSigmoidActivation: the depth nets' last op,
+    depth = safe_reciprocal_number(sigmoid(x) + 0.01)."""
+    return safe_reciprocal_number(torch.sigmoid(x) + 0.01)
+
+
 # --------------------------------------------------------------------------
 # synthesis  (reference synthesize_base.py:39-178, bilinear_interp.py:7-147)
 # --------------------------------------------------------------------------

@@ -186,6 +186,53 @@ def run_stereo_case(name, B, H, W, N, loss_set, scale_weights, seed, global_batc
     print("wrote", path, {k: float(v) for k, v in by_type.items()}, float(total))
 
 
+def reference_class(path, name, namespace):
+    """exec ONE class of a reference module that cannot be imported whole (model_factory.py pulls in the Keras nets):
+    its unmodified source lines, cut out with ast, run over the shim"""
+    import ast
+    src = open(os.path.join(REF, path)).read()
+    node = next(n for n in ast.parse(src).body if isinstance(n, ast.ClassDef) and n.name == name)
+    code = "\n".join(src.splitlines()[node.lineno - 1:node.end_lineno])
+    exec(compile(code, os.path.join(REF, path), "exec"), namespace)
+    return namespace[name]
+
+
+def run_logit_case(name, B, H, W, N, loss_set, seed):
+    """the depth net's last op is InverseSigmoidActivation (model_factory.py:133-137), then
+    predict_batch forms disp_ms = safe_reciprocal_number_ms(depth_ms) (model_wrappers.py:47-48), then TotalLoss.
+    Inputs: logits; outputs: losses and dL/dlogit (autograd through the reference's activation and reciprocal)."""
+    import tensorflow as tf
+    act = reference_class("model/build_model/model_factory.py", "InverseSigmoidActivation", {"tf": tf, "uf": uf})()
+    feats, preds = make_inputs(B, H, W, N=N, seed=seed)
+    g = torch.Generator().manual_seed(seed + 7)
+    logit = [(torch.rand(d.shape, generator=g, dtype=torch.float64) * 6.0 - 4.5).float().to(DT).requires_grad_(True)
+             for d in preds["depth_ms"]]                          # depth = 1 / (sigmoid + 0.01) in [1.2, 46]
+    depth = [act(x) for x in logit]
+    disp = uf.safe_reciprocal_number_ms(depth)
+    pose = preds["pose"].clone().requires_grad_(True)
+    loss_weights, scale_weights = LOSS_SETS[loss_set]
+    total_obj = loss_factory({"image": 1, "intrinsic": 1}, loss_weights, scale_weights, stereo=False, batch_size=B)
+    features = {"image5d": feats["image5d"], "intrinsic": feats["intrinsic"]}
+    total, by_type = total_obj({"depth_ms": depth, "disp_ms": disp, "pose": pose}, features)
+    total.backward()
+    out = {"B": B, "H": H, "W": W, "N": N, "global_batch": B, "loss_set": loss_set,
+           "loss_names": np.array(list(total_obj.loss_objects.keys())),
+           "loss_weights": np.array([total_obj.loss_weights[k] for k in total_obj.loss_objects]),
+           "scale_weights": scale_weights, "total": np_(total), "d_pose": np_(pose.grad)}
+    for k, v in by_type.items():
+        out["loss_" + k] = np_(v)
+    for s_ in range(len(logit)):
+        out[f"d_logit_{s_}"] = np_(logit[s_].grad)
+        out[f"act_depth_{s_}"] = np_(depth[s_])
+    if not F64:
+        out.update({"image5d": np_(feats["image5d"]), "intrinsic": np_(feats["intrinsic"]), "pose": np_(preds["pose"])})
+        for s_ in range(len(logit)):
+            out[f"logit_{s_}"] = np_(logit[s_])
+    path = os.path.join(HERE, f"{name}_{'f64' if F64 else 'f32'}.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, {k: float(v) for k, v in by_type.items()}, float(total))
+
+
 def run_pieces():
     """Per-function vectors: pose conversion (tf and numpy twins), per-pixel
     photometric terms, safe reciprocal, SynthesizeMultiScale alone."""
@@ -224,7 +271,11 @@ def run_pieces():
 
 
 if __name__ == "__main__":
+    if "--logit-only" in sys.argv:
+        run_logit_case("logit_t1", B=2, H=32, W=64, N=4, loss_set="T1", seed=111)
+        sys.exit(0)
     run_pieces()
+    run_logit_case("logit_t1", B=2, H=32, W=64, N=4, loss_set="T1", seed=111)
     run_case("case_small_t1", B=2, H=32, W=64, N=4, loss_set="T1", seed=101)
     run_case("case_n2_t2", B=3, H=48, W=40, N=2, loss_set="T2", seed=202, global_batch=6)
     run_case("case_adv_t1", B=2, H=32, W=48, N=4, loss_set="T1", seed=303, adversarial=True)

@@ -174,6 +174,11 @@ def exp(x, **_):
     return torch.exp(_t(x))
 
 
+def sigmoid(x, **_):
+    """tf.math.sigmoid: 1 / (1 + exp(-x))"""
+    return 1.0 / (1.0 + torch.exp(-_t(x)))
+
+
 def sin(x, **_):
     return torch.sin(_t(x))
 
@@ -372,7 +377,7 @@ def install(opts_overrides=None):
         setattr(tf, name, fn)
     tf.linalg = types.SimpleNamespace(inv=linalg_inv, trace=linalg_trace)
     tf.math = types.SimpleNamespace(not_equal=not_equal, equal=equal, sin=sin, cos=cos,
-                                    acos=acos, is_nan=torch.isnan,
+                                    acos=acos, is_nan=torch.isnan, sigmoid=sigmoid,
                                     count_nonzero=_unsupported("math.count_nonzero"))
     tf.image = types.SimpleNamespace(resize=image_resize,
                                      convert_image_dtype=_unsupported("image.convert_image_dtype"))

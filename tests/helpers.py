@@ -94,3 +94,26 @@ def grad_close(cuda, ref32, ref64, tol=1e-4, outlier_frac=1e-4, self_factor=0):
     l2_c, l2_a = np.linalg.norm((c - b)[near]) / nb, np.linalg.norm(a - b) / nb
     ok = n_out <= budget and l2_c <= 2 * l2_a + tol
     return ok, f"outliers {n_out}/{c.size} (budget {budget}), rel-L2 vs f64: cuda {l2_c:.3e}, fp32 oracle {l2_a:.3e}"
+
+
+# ---- achieved-error record: every tolerance check that goes through margin() is kept and written to
+# gpurun_out/parity_margins.json at the end of the session (and printed with -s), so that the distance to the
+# tolerance of BASELINE.json is visible, not only pass / fail
+_MARGINS = []
+
+
+def margin(name, err, tol):
+    """assert err < tol and remember how close it was"""
+    _MARGINS.append({"check": name, "achieved": float(err), "tolerance": float(tol)})
+    assert err < tol, f"{name}: {err:.3e} >= {tol:.3e}"
+    return err
+
+
+def dump_margins(path):
+    import json
+    if _MARGINS:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        worst = sorted(_MARGINS, key=lambda m: -m["achieved"] / m["tolerance"])
+        with open(path, "w") as f:
+            json.dump({"n": len(_MARGINS), "worst_fraction_of_tolerance": worst[0]["achieved"] / worst[0]["tolerance"],
+                       "checks": worst}, f, indent=1)

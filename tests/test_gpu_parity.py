@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import CASES, case_inputs, grad_close, load_case, relerr
+from helpers import CASES, case_inputs, grad_close, load_case, margin, relerr
 
 pytestmark = pytest.mark.gpu
 
@@ -940,3 +940,216 @@ def test_whole_step_under_torch_cuda_graph(xw):
         assert torch.equal(a_, t.grad)
     ref = orc.loss_and_grads(feats2, preds2, lw, sw)
     assert relerr(got_total, ref["total"].numpy()) < LOSS_TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# round 2: constant-bank slots, chunked launches, config-5 shape, in-stream collective, helper kernels
+# ---------------------------------------------------------------------------------------------------------------
+def test_batch_above_one_constant_bank_chunk(xw):
+    """B = 130 > 128 snippets: the camera geometry of the batch does not fit one constant-bank slot (60 KB /
+    (4 x 18 + 4 x 12) floats), so k_fused is launched in chunks (b_off > 0).  Checked against the oracle on the
+    first and the last snippet and through sum_b loss_batch = by-type means; also with synthesis outputs."""
+    from oracle import xpt_oracle as orc
+    B, H, W = 130, 16, 16
+    feats, preds = orc.make_inputs(B, H, W, seed=1300)
+    lw, sw = orc.LOSS_RIGID_T1, orc.SCALE_WEIGHT_T1
+    f, p = _to_cuda(feats, preds)
+    r = _run_total(_plan_for(xw, f, p, lw, sw, B), f, p, want_grad=True, want_loss_batch=True, want_synth=True)
+    losses = r["losses"].cpu().numpy()
+    assert np.allclose(r["loss_batch"].cpu().numpy().sum(axis=1) / B, losses[1:4], rtol=1e-5)
+    for b in (0, 128, 129):
+        f1 = {k: v[b:b + 1] for k, v in feats.items()}
+        p1 = {"depth_ms": [d[b:b + 1] for d in preds["depth_ms"]], "disp_ms": [d[b:b + 1] for d in preds["disp_ms"]],
+              "pose": preds["pose"][b:b + 1]}
+        ref = orc.loss_and_grads(f1, p1, lw, sw, global_batch=B)
+        lb = r["loss_batch"].cpu().numpy()[:, b] / B
+        for i, k in enumerate(("L1", "SSIM", "smoothe")):
+            margin(f"chunked b={b} {k}", relerr(lb[i], ref["by_type"][k].numpy()), LOSS_TOL)
+        margin(f"chunked b={b} d_pose", relerr(r["d_pose"][b:b + 1].cpu().numpy(), ref["d_pose"].numpy()), 5 * GRAD_TOL)
+        margin(f"chunked b={b} d_depth0", relerr(r["d_depth_ms"][0][b:b + 1].cpu().numpy(), ref["d_depth_ms"][0].numpy()), 5 * GRAD_TOL)
+        margin(f"chunked b={b} synth0", float(np.abs(r["synth_ms"][0][b:b + 1].cpu().numpy() - ref["synth_ms"][0].numpy()).max()), IMG_TOL)
+
+
+def test_contexts_on_two_streams_do_not_share_geometry(xw):
+    """two contexts with different cameras run interleaved on two streams; each owns a private
+    constant-bank slot, so neither can project with the other's K / [R|t]."""
+    from oracle import xpt_oracle as orc
+    lw, sw = orc.LOSS_RIGID_T1, orc.SCALE_WEIGHT_T1
+    cases = []
+    for seed, (B, H, W) in ((11, (4, 64, 128)), (12, (4, 64, 128))):
+        feats, preds = orc.make_inputs(B, H, W, seed=seed)
+        f, p = _to_cuda(feats, preds)
+        plan = xw.engine.Plan(0, B, 4, H, W, [1, 2, 4, 8], sw, lw["L1"], lw["SSIM"], lw["smoothe"], B, 0)
+        assert not plan.geometry_slot_shared()
+        ref = _run_total(plan, f, p, want_grad=True)
+        ref = {k: ([t.clone() for t in v] if isinstance(v, list) else v.clone()) for k, v in ref.items() if v is not None}
+        cases.append((plan, f, p, ref, torch.cuda.Stream()))
+    torch.cuda.synchronize()
+    outs = [[], []]
+    for it in range(40):
+        for i, (plan, f, p, ref, st) in enumerate(cases):
+            with torch.cuda.stream(st):
+                img = f["image5d"]
+                r = plan.total_loss(img[:, :-1], img[:, -1], f["intrinsic"], p["depth_ms"], p["disp_ms"], p["pose"], want_grad=True)
+                outs[i].append((r["losses"].clone(), r["d_pose"].clone()))
+    torch.cuda.synchronize()
+    for i, (plan, f, p, ref, st) in enumerate(cases):
+        for losses, d_pose in outs[i]:
+            assert torch.equal(losses, ref["losses"]) and torch.equal(d_pose, ref["d_pose"]), i
+        plan.close()
+
+
+def test_config5_shape_properties(xw):
+    """BASELINE config 5's frame size (384 x 1280), 4 snippets: tile kernel == strip kernel == unfused kernels,
+    per-snippet losses add up, and one snippet against the oracle."""
+    from oracle import xpt_oracle as orc
+    from xptwarp import _cabi
+    B, H, W = 4, 384, 1280
+    feats, preds = orc.make_inputs(B, H, W, seed=20211 + 5000)
+    lw, sw = orc.LOSS_RIGID_T1, orc.SCALE_WEIGHT_T1
+    f, p = _to_cuda(feats, preds)
+    keep = lambda r: {k: ([t.clone() for t in v] if isinstance(v, list) else v.clone()) for k, v in r.items() if v is not None}
+    r1 = keep(_run_total(_plan_for(xw, f, p, lw, sw, B), f, p, want_grad=True, want_loss_batch=True))
+    for name, flags, tol_d in (("unfused", _cabi.XPT_FLAG_UNFUSED, 1e-4), ("strip", _cabi.XPT_FLAG_STRIP, 5e-5)):
+        r2 = _run_total(_plan_for(xw, f, p, lw, sw, B, flags=flags), f, p, want_grad=True)
+        margin(f"cfg5-shape {name} losses", relerr(r2["losses"].cpu().numpy(), r1["losses"].cpu().numpy()), 2e-6)
+        margin(f"cfg5-shape {name} d_pose", relerr(r2["d_pose"].cpu().numpy(), r1["d_pose"].cpu().numpy()), 2e-5)
+        for s in range(4):
+            margin(f"cfg5-shape {name} d_depth[{s}]", relerr(r2["d_depth_ms"][s].cpu().numpy(), r1["d_depth_ms"][s].cpu().numpy()), tol_d)
+    losses = r1["losses"].cpu().numpy()
+    assert np.allclose(r1["loss_batch"].cpu().numpy().sum(axis=1) / B, losses[1:4], rtol=1e-5)
+    f1 = {k: v[1:2] for k, v in feats.items()}
+    p1 = {"depth_ms": [d[1:2] for d in preds["depth_ms"]], "disp_ms": [d[1:2] for d in preds["disp_ms"]], "pose": preds["pose"][1:2]}
+    ref = orc.loss_and_grads(f1, p1, lw, sw, global_batch=B)
+    lb = r1["loss_batch"].cpu().numpy()[:, 1] / B
+    for i, k in enumerate(("L1", "SSIM", "smoothe")):
+        margin(f"cfg5-shape oracle {k}", relerr(lb[i], ref["by_type"][k].numpy()), LOSS_TOL)
+    ref64 = orc.loss_and_grads({k: v.double() for k, v in f1.items()},
+                               {"depth_ms": [d.double() for d in p1["depth_ms"]], "disp_ms": [d.double() for d in p1["disp_ms"]],
+                                "pose": p1["pose"].double()}, lw, sw, global_batch=B)
+    pose_tol = max(GRAD_TOL, 3 * relerr(ref["d_pose"].numpy(), ref64["d_pose"].numpy()))
+    margin("cfg5-shape oracle d_pose", relerr(r1["d_pose"][1:2].cpu().numpy(), ref64["d_pose"].numpy()), pose_tol)
+    ok, msg = grad_close(r1["d_depth_ms"][0][1:2].cpu().numpy(), ref["d_depth_ms"][0].numpy(), ref64["d_depth_ms"][0].numpy(), GRAD_TOL)
+    assert ok, msg
+
+
+def test_scale_tensors_and_upstream_gradient(xw):
+    """xpt_scale_tensors (one launch for every stored gradient) and the autograd node built on it: a non-unit
+    upstream gradient scales pose / depth / disparity gradients exactly like PyTorch's own multiply would."""
+    from oracle import xpt_oracle as orc
+    from xptwarp.engine import scale_tensors
+    ts = [torch.randn(n, device="cuda") for n in (1, 7, 1024, 100003)]
+    sc = torch.tensor(-2.5, device="cuda")
+    for a, b in zip(scale_tensors(ts, sc), ts):
+        assert torch.equal(a, b * sc)
+    feats, preds = orc.make_inputs(2, 32, 64, seed=5)
+    f = {k: v.cuda() for k, v in feats.items()}
+    lw, sw = orc.LOSS_RIGID_T1, orc.SCALE_WEIGHT_T1
+    grads = []
+    for k in (1.0, 3.0):
+        p = {"depth_ms": [d.cuda().requires_grad_(True) for d in preds["depth_ms"]],
+             "disp_ms": [d.cuda().requires_grad_(True) for d in preds["disp_ms"]], "pose": preds["pose"].cuda().requires_grad_(True)}
+        total, _ = xw.loss_factory({"image": 1, "intrinsic": 1}, lw, np.array(sw), batch_size=2)(p, f)
+        (total * k).backward()
+        grads.append([p["pose"].grad] + [d.grad for d in p["depth_ms"]] + [d.grad for d in p["disp_ms"]])
+    for a, b in zip(*grads):
+        assert torch.equal(a * 3.0, b)
+
+
+def _nccl_worker(rank, world, port, q):
+    import os
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import xptwarp
+    from oracle import xpt_oracle as orc
+    from xptwarp import _cabi
+    from xptwarp.distributed import shard_bounds
+    B, H, W = 8, 64, 128
+    feats, preds = orc.make_inputs(B, H, W, seed=4321)
+    lw, sw = orc.LOSS_RIGID_T1, orc.SCALE_WEIGHT_T1
+    lo, hi = shard_bounds(B, rank, world)
+    f = {k: v[lo:hi].cuda() for k, v in feats.items()}
+    p = {"depth_ms": [d[lo:hi].cuda() for d in preds["depth_ms"]], "disp_ms": [d[lo:hi].cuda() for d in preds["disp_ms"]],
+         "pose": preds["pose"][lo:hi].cuda()}
+    out = {}
+    for name, flags in (("eager", _cabi.XPT_FLAG_ALLREDUCE), ("graph", _cabi.XPT_FLAG_ALLREDUCE | _cabi.XPT_FLAG_GRAPH)):
+        plan = xptwarp.get_plan(rank, hi - lo, 4, H, W, [1, 2, 4, 8], sw, lw["L1"], lw["SSIM"], lw["smoothe"], B, flags)
+        plan.comm_init()
+        img = f["image5d"]
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            for _ in range(3):          # the third call of the graph variant is a replay
+                r = plan.total_loss(img[:, :-1], img[:, -1], f["intrinsic"], p["depth_ms"], p["disp_ms"], p["pose"], want_grad=True)
+            st.synchronize()
+        out[name] = (r["losses"].cpu().numpy(), r["d_pose"].cpu().numpy(), lo, hi)
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_sharded_losses_equal_the_global_batch(xw):
+    """SURVEY 8e / losses.py:49 / distributer.py:93-96: every rank scores its shard normalised by the GLOBAL batch;
+    the library's in-stream ncclAllReduce (XPT_FLAG_ALLREDUCE, eager and as a node of the step's CUDA graph) of the
+    loss vector equals the single-GPU loss of the whole batch; per-snippet gradients are the single-GPU ones."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 CUDA devices")
+    import socket
+    import torch.multiprocessing as mp
+    from oracle import xpt_oracle as orc
+    B, H, W = 8, 64, 128
+    feats, preds = orc.make_inputs(B, H, W, seed=4321)
+    lw, sw = orc.LOSS_RIGID_T1, orc.SCALE_WEIGHT_T1
+    f, p = _to_cuda(feats, preds)
+    ref = _run_total(_plan_for(xw, f, p, lw, sw, B), f, p, want_grad=True)
+    ref_l, ref_dp = ref["losses"].cpu().numpy(), ref["d_pose"].cpu().numpy()
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    got = dict(q.get(timeout=240) for _ in procs)
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    for rank in (0, 1):
+        for name in ("eager", "graph"):
+            losses, d_pose, lo, hi = got[rank][name]
+            margin(f"2-GPU {name} rank{rank} losses", relerr(losses, ref_l), 2e-6)
+            margin(f"2-GPU {name} rank{rank} d_pose", relerr(d_pose, ref_dp[lo:hi]), 1e-6)
+
+
+def test_depth_logit_boundary_against_golden(xw):
+    """SURVEY 8f rank 3 (row f3): predictions carry the depth net's LOGITS ("depth_logit_ms", no depth_ms / disp_ms);
+    the kernels apply InverseSigmoidActivation (model_factory.py:133-137) and safe_reciprocal_number themselves and
+    return ONE gradient per level, dL/dlogit -- against vectors made by the reference's own activation class, through
+    the reference call surface (TotalLoss + autograd), tile kernel and strip kernel."""
+    from xptwarp import _cabi
+    g = load_case("logit_t1", "f32")
+    S = sum(1 for k in g.files if k.startswith("logit_"))
+    cv = lambda a: torch.tensor(a, dtype=torch.float32, device="cuda")
+    feats = {"image5d": cv(g["image5d"]), "intrinsic": cv(g["intrinsic"])}
+    lw = dict(zip(g["loss_names"].tolist(), [float(w) for w in g["loss_weights"]]))
+    sw = [float(w) for w in g["scale_weights"]]
+    preds = {"depth_logit_ms": [cv(g[f"logit_{s}"]).requires_grad_(True) for s in range(S)], "pose": cv(g["pose"]).requires_grad_(True)}
+    total, by_type = xw.loss_factory({"image": 1, "intrinsic": 1}, lw, np.array(sw), batch_size=int(g["global_batch"]))(preds, feats)
+    total.backward()
+    margin("logit total", relerr(total.detach().cpu().numpy(), g["total"]), LOSS_TOL)
+    for k in ("L1", "SSIM", "smoothe"):
+        margin(f"logit {k}", relerr(by_type[k].detach().cpu().numpy(), g["loss_" + k]), LOSS_TOL)
+    margin("logit d_pose", relerr(preds["pose"].grad.cpu().numpy(), g["d_pose"]), GRAD_TOL)
+    for s in range(S):
+        margin(f"logit d_logit[{s}]", relerr(preds["depth_logit_ms"][s].grad.cpu().numpy(), g[f"d_logit_{s}"]), GRAD_TOL)
+    # the strip kernel through the plan API
+    B, F, H, W, _ = feats["image5d"].shape
+    for flags in (_cabi.XPT_FLAG_DEPTH_LOGIT, _cabi.XPT_FLAG_DEPTH_LOGIT | _cabi.XPT_FLAG_STRIP):
+        plan = xw.get_plan(0, B, F - 1, H, W, [1, 2, 4, 8], sw, lw["L1"], lw["SSIM"], lw["smoothe"], int(g["global_batch"]), flags)
+        img = feats["image5d"]
+        r = plan.total_loss(img[:, :-1], img[:, -1], feats["intrinsic"], [t.detach() for t in preds["depth_logit_ms"]], None,
+                            preds["pose"].detach(), want_grad=True)
+        torch.cuda.synchronize()
+        margin(f"logit flags={flags} total", relerr(r["losses"][0].cpu().numpy(), g["total"]), LOSS_TOL)
+        for s in range(S):
+            margin(f"logit flags={flags} d_logit[{s}]", relerr(r["d_depth_ms"][s].cpu().numpy(), g[f"d_logit_{s}"]), GRAD_TOL)

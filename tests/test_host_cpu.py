@@ -195,3 +195,32 @@ def test_sharded_losses_allreduce_to_the_global_batch_mean_gloo():
     for rank, vec, b0 in res:
         assert np.allclose(vec, want, rtol=1e-5), (rank, vec, want)
         assert b0 == 3.0
+
+
+def test_check_dlpack_status_codes(built):
+    """xpt_check_dlpack: the dtype / device / contiguity codes of SURVEY 8b live on the C side and need no GPU."""
+    from xptwarp import dlpack
+    lib = built.lib()
+
+    def managed(t):
+        cap = t.__dlpack__()
+        ptr = dlpack._PyCapsule_GetPointer(cap, b"dltensor")
+        return cap, ptr
+    cap, ptr = managed(torch.zeros(2, 3, 4, dtype=torch.float64))
+    assert lib.xpt_check_dlpack(ptr, 0, 0) == built.XPT_BAD_DTYPE
+    assert b"float32" in lib.xpt_last_error()
+    cap, ptr = managed(torch.zeros(2, 3, 4, dtype=torch.float32))
+    assert lib.xpt_check_dlpack(ptr, 0, 0) == built.XPT_BAD_DEVICE          # a CPU tensor: no CPU path
+    assert lib.xpt_check_dlpack(None, 0, 0) == built.XPT_BAD_ARGUMENT
+    assert lib.xpt_status_string(built.XPT_NOT_CONTIGUOUS) == b"XPT_NOT_CONTIGUOUS"
+    assert lib.xpt_status_string(built.XPT_NCCL_ERROR) == b"XPT_NCCL_ERROR"
+    del cap
+
+
+def test_strided_inputs_are_refused_not_copied(built):
+    """engine._dense / _frame_view raise on non-dense inputs instead of calling .contiguous() behind the caller"""
+    from xptwarp import engine
+    t = torch.zeros(4, 6, 8)[:, ::2]
+    for fn in (lambda: engine._dense(t, "x"), lambda: engine._frame_view(torch.zeros(2, 8, 8, 6)[..., ::2], "img", 1)):
+        with pytest.raises(engine.WrongInputException):
+            fn()

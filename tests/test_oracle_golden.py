@@ -144,3 +144,29 @@ def test_gradients_match_finite_differences_fp64():
             vals.append(orc.total_loss(p, feats, lw, sw)[0].item())
         fd = (vals[0] - vals[1]) / (2 * eps)
         assert abs(fd - r["d_pose"][idx].item()) < 1e-5 * max(1.0, abs(fd)) + 1e-7
+
+
+def test_depth_activation_against_the_reference_class():
+    """oracle.inverse_sigmoid_activation against vectors produced by the reference's own
+    InverseSigmoidActivation source (model_factory.py:133-137, cut out and executed by make_golden.py), and the
+    total loss + dL/dlogit through it."""
+    import torch
+    from helpers import load_case
+    from oracle import xpt_oracle as orc
+    for kind, dt, tol in (("f32", torch.float32, 2e-6), ("f64", torch.float64, 1e-12)):
+        g = load_case("logit_t1", kind)
+        g32 = load_case("logit_t1", "f32")
+        S = sum(1 for k in g32.files if k.startswith("logit_"))
+        logit = [torch.tensor(g32[f"logit_{s}"], dtype=dt).requires_grad_(True) for s in range(S)]
+        depth = [orc.inverse_sigmoid_activation(x) for x in logit]
+        for s in range(S):
+            assert relerr(depth[s].detach().numpy(), g[f"act_depth_{s}"]) < tol
+        feats = {"image5d": torch.tensor(g32["image5d"], dtype=dt), "intrinsic": torch.tensor(g32["intrinsic"], dtype=dt)}
+        pose = torch.tensor(g32["pose"], dtype=dt).requires_grad_(True)
+        lw = dict(zip(g["loss_names"].tolist(), [float(w) for w in g["loss_weights"]]))
+        total, by_type = orc.total_loss({"depth_ms": depth, "disp_ms": [orc.safe_reciprocal_number(d) for d in depth],
+                                         "pose": pose}, feats, lw, [float(w) for w in g["scale_weights"]], int(g["global_batch"]))
+        total.backward()
+        assert relerr(total.detach().numpy(), g["total"]) < (1e-5 if kind == "f32" else 1e-9)
+        for s in range(S):
+            assert relerr(logit[s].grad.numpy(), g[f"d_logit_{s}"]) < (1e-4 if kind == "f32" else 1e-8), s

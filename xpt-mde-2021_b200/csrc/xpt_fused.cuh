@@ -52,7 +52,9 @@ static_assert(kFYTail <= 2 * kFTailThreads && kFYMain >= (kFCH + 2) * kFP, "tail
 constexpr int kFRedSrc = 4;                    // sources whose pose partials are buffered before the cross-warp sum
 constexpr int kFRedFloats = kFRedSrc * kFCH * 16;                  // 832 (>= 48 floats of loss scratch)
 
-// camera geometry in the constant bank: [Bc][S][18] (K_s, inv K_s) then [Bc][N][12] ([R|t])
+
+// camera geometry in the constant bank (uniform-register operands of the projection): a ctx owns a slot of it
+// (xptwarp.cu: geo_slot_*), laid out [Bc][S][18] (K_s, inv K_s) then [Bc][N][12] ([R|t]) for the Bc snippets of a launch
 constexpr int kGeoConstFloats = 15360;         // 60 KB
 __constant__ float c_geo[kGeoConstFloats];
 
@@ -128,14 +130,15 @@ __device__ __forceinline__ float warp_reduce16(float v[16], int lane) {
 struct FusedArgs {
   LevelTable lt;                       // Level.tiles_x/y/slot_base describe the 64x13 tiling
   int B, N;
-  int b_off;                           // first snippet of this launch (constant-bank chunking)
-  int geo_t_off;                       // float offset of the [R|t] block inside c_geo
+  int b_off, Bc;                       // first snippet / snippets of this launch (constant-bank chunking)
+  int geo_k_off, geo_t_off;            // float offsets of this launch's K and [R|t] blocks inside c_geo (the ctx's slot)
   int tiles_per_b;
   int first_tile[kMaxScales + 1];
   const float* depth[kMaxScales];
   const float* disp[kMaxScales];
   const float4* src4[kMaxScales];      // RGBx texels of the source levels [B,N,h,w] (written by the pyramid kernels)
   int do_l1, do_ssim, do_smooth;
+  int logit;                           // depth[] holds the depth net's logits (XPT_FLAG_DEPTH_LOGIT): activation at load, dL/dlogit out
   float norm_photo[kMaxScales];        // sw_s / (N*h*w*3)
   float norm_sm_x[kMaxScales];
   float norm_sm_y[kMaxScales];
@@ -220,7 +223,8 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
 
   // ---- which tile -------------------------------------------------------------
   // grid = (snippets, tiles): all snippets' tile 0 first, ... the cheap small-level tiles last, so that the
-  // final partial wave is filled with short CTAs
+  // final partial wave is filled with short CTAs.  (A persistent grid drawing tiles from a ticket was measured in
+  // round 2: +2 % time at config 2 and config 3 -- the ticket's two barriers per tile cost more than the tail.)
   int t = blockIdx.y;
   const int bl = blockIdx.x;               // snippet inside this launch's constant-bank chunk
   const int b = a.b_off + bl;
@@ -232,7 +236,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
   const int ty0 = (t / L.tiles_x) * kFCH, tx0 = (t % L.tiles_x) * kFCW;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int slot = L.slot_base + t;
-  const float* const gk = c_geo + (bl * a.lt.S + l) * kGeoK;     // K_s (9), inv K_s (9): uniform registers
+  const float* const gk = c_geo + a.geo_k_off + (bl * a.lt.S + l) * kGeoK;     // K_s (9), inv K_s (9): uniform registers
 
   // ---- target tile, depth tile and pixel rays (halo 2); zero outside the image ---------------------
   // depth 0 marks "no sample": the reference's D != 0 validity test (bilinear_interp.py:53-76) then also
@@ -251,6 +255,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
           const float* p = tgt + ((long long)gy * W + gx) * 3;
           v0 = __ldg(p); v1 = __ldg(p + 1); v2 = __ldg(p + 2);
           d = __ldg(dep + (long long)gy * W + gx);
+          if (a.logit) d = depth_of_logit(d);
           // reference order.  The last rows of K_s and inv(K_s) are exactly (0,0,1)
           // (synthesize_base.py:66-71), so ray.z = 1 and p.z = Y.z hold bit-exactly and are not recomputed.
           const float fx = (float)gx, fy = (float)gy;
@@ -665,7 +670,8 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
 #pragma unroll
     for (int o = 0; o < 2; ++o) {
       const int gx = tx0 + c0 + o;
-      if (gy < H && gx < W) a.d_depth[l][(long long)b * P + gy * W + gx] = gD[o];
+      if (gy < H && gx < W)
+        a.d_depth[l][(long long)b * P + gy * W + gx] = a.logit ? gD[o] * ddepth_dlogit(sD[(cyy + 2) * kFP + c0 + o + 2]) : gD[o];
     }
   }
 

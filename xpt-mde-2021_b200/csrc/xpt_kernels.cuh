@@ -42,6 +42,20 @@ struct PtrTable {
 constexpr int kGeoK = 18;
 constexpr int kGeoT = 12;
 
+// model/build_model/model_factory.py:133-137 InverseSigmoidActivation, the depth nets' last op:
+// depth = safe_reciprocal_number(sigmoid(x) + 0.01), and its derivative expressed through the depth itself
+// (y = 1/depth = sigmoid + 0.01, d depth / d x = -depth^2 s (1 - s) with s = y - 0.01)
+__device__ __forceinline__ float depth_of_logit(float x) {
+  const float s = __fdiv_rn(1.f, 1.f + expf(-x));
+  const float y = s + 0.01f;
+  return y > 0.00001f ? __fdiv_rn(1.f, y) : 0.f;
+}
+__device__ __forceinline__ float ddepth_dlogit(float D) {
+  if (!(D > 0.f)) return 0.f;
+  const float s = __fdiv_rn(1.f, D) - 0.01f;
+  return -(D * D) * (s * (1.f - s));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -55,6 +55,7 @@ struct StripArgs {
   const float* disp[kMaxScales];
   const float4* src4[kMaxScales];      // RGBx source levels [B,N,h,w]
   int do_l1, do_ssim, do_smooth;
+  int logit;                           // depth[] holds logits (XPT_FLAG_DEPTH_LOGIT)
   float norm_photo[kMaxScales];
   float norm_sm_x[kMaxScales];
   float norm_sm_y[kMaxScales];
@@ -177,7 +178,16 @@ __device__ __forceinline__ void strip_role_l(const StripArgs& a, float* smem, co
     const float* const dp = a.depth[p.l] + (long long)p.b * L.H * L.W;
     const float* const ep = (a.do_smooth && a.disp[p.l]) ? a.disp[p.l] + (long long)p.b * L.H * L.W : nullptr;
 #pragma unroll
-    for (int r = 0; r < 2; ++r) nx[r] = strip_load_row(tg, dp, ep, L.H, L.W, p.ya - 2 + 2 * ci + r, p.x0 - 2 + 2 * lane);
+    for (int r = 0; r < 2; ++r) {
+      nx[r] = strip_load_row(tg, dp, ep, L.H, L.W, p.ya - 2 + 2 * ci + r, p.x0 - 2 + 2 * lane);
+      if (a.logit) {           // InverseSigmoidActivation at load; pixels outside the image keep depth 0 = "no sample"
+        const int gy = p.ya - 2 + 2 * ci + r, gx = p.x0 - 2 + 2 * lane;
+        const bool in0 = (unsigned)gy < (unsigned)L.H && (unsigned)gx < (unsigned)L.W;
+        const bool in1 = (unsigned)gy < (unsigned)L.H && (unsigned)(gx + 1) < (unsigned)L.W;
+        nx[r].d[0] = in0 ? depth_of_logit(nx[r].d[0]) : 0.f;
+        nx[r].d[1] = in1 ? depth_of_logit(nx[r].d[1]) : 0.f;
+      }
+    }
     if (++ci == p.nch) { ci = 0; if (++pi < pend) p = load_piece(a.pieces, pi); }
   };
   fetch();
@@ -317,6 +327,10 @@ __device__ __forceinline__ void strip_role_o(const StripArgs& a, float* smem, co
             g0 += v.x; g1 += v.y;
           }
         const long long o = (long long)op.b * H * W + (long long)gy * W + gx;
+        if (a.logit) {           // dL/dlogit = dL/ddepth * d depth / d logit
+          const float2 D = lds2(T + 3 * kSTRows * kSW + ((s - 2) & (kSTRows - 1)) * kSW);
+          g0 *= ddepth_dlogit(D.x); g1 *= ddepth_dlogit(D.y);
+        }
         if (a.d_depth[op.l]) {
           if (cen0) a.d_depth[op.l][o] = g0;
           if (cen1) a.d_depth[op.l][o + 1] = g1;

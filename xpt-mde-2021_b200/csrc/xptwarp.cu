@@ -5,12 +5,15 @@
 #include "../../include/xptwarp.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <cstdarg>
 #include <cstdio>
 #include <cstdint>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "xpt_kernels.cuh"
@@ -88,8 +91,9 @@ struct xpt_ctx {
   StripPiece* strip_pieces; StripCta* strip_ctas;
   int strip_nctas, strip_slots, strip_ns; bool strip_ready;
   float* strip_loss_part; float* strip_pose_part;
-  float* c_geo_dev;             // device address of the constant-bank geometry block (c_geo)
-  bool geo_direct;              // this call's geometry is produced straight into c_geo (no staging copy)
+  void* nccl_comm; bool nccl_owned;   // communicator of XPT_FLAG_ALLREDUCE / xpt_allreduce
+  int geo_off, geo_len;         // this ctx's slot of the constant-bank geometry block (floats); geo_shared: the whole bank,
+  bool geo_shared;              //   shared with other contexts because no private slot was free at xpt_create
   // staging for the host-buffer entry point
   float* st_frames; float* st_K; float* st_pose; float* st_losses; float* st_loss_batch; float* st_dpose;
   float* st_dsource;
@@ -188,10 +192,6 @@ GeoArgs make_geo(xpt_ctx* ctx, const float* pose, const float* intrinsic, float*
   memset(&g, 0, sizeof(g));
   g.pose = pose; g.intrinsic = intrinsic;
   g.geoK = intrinsic ? ctx->geoK : nullptr; g.geoT = pose ? ctx->geoT : nullptr; g.matr_out = matr_out;
-  if (ctx->geo_direct && intrinsic && pose) {      // same [K block | [R|t] block] layout, inside the constant bank
-    g.geoK = ctx->c_geo_dev;
-    g.geoT = ctx->c_geo_dev + (size_t)ctx->B * ctx->S * kGeoK;
-  }
   g.B = ctx->B; g.N = ctx->N; g.S = ctx->S;
   for (int l = 0; l < ctx->S; ++l) g.s[l] = ctx->s[l];
   return g;
@@ -451,30 +451,66 @@ int launch_photo(xpt_ctx* ctx, const PhotoArgs& a, cudaStream_t st) {
   return XPT_OK;
 }
 
+// Constant-bank slots: k_fused reads the camera geometry through uniform-register operands, i.e. from the 60 KB
+// __constant__ block c_geo.  Every ctx owns a private slot of it (first fit, per device), so launches of DIFFERENT
+// contexts on different streams never touch each other's geometry.  A ctx that finds no free slot shares the whole
+// bank (geo_shared) and must then be ordered against the other contexts of the device by its caller.
+struct GeoSlotTable { std::mutex m; std::vector<std::pair<int, int>> used; };     // (offset, length), sorted by offset
+GeoSlotTable g_geo_slots[64];
+
+void geo_slot_acquire(xpt_ctx* ctx) {
+  const int per_b = ctx->S * kGeoK + ctx->N * kGeoT;
+  int want = ctx->B * per_b;
+  if (want > kGeoConstFloats) want = (kGeoConstFloats / per_b) * per_b;      // larger batches launch in chunks
+  GeoSlotTable& t = g_geo_slots[ctx->cfg.device & 63];
+  std::lock_guard<std::mutex> lk(t.m);
+  int pos = 0;
+  size_t i = 0;
+  for (; i <= t.used.size(); ++i) {
+    const int end = i < t.used.size() ? t.used[i].first : kGeoConstFloats;
+    if (end - pos >= want) break;
+    if (i < t.used.size()) pos = t.used[i].first + t.used[i].second;
+  }
+  if (i <= t.used.size() && (i < t.used.size() ? t.used[i].first : kGeoConstFloats) - pos >= want) {
+    t.used.insert(t.used.begin() + i, std::make_pair(pos, want));
+    ctx->geo_off = pos; ctx->geo_len = want; ctx->geo_shared = false;
+  } else {
+    ctx->geo_off = 0; ctx->geo_len = (kGeoConstFloats / per_b) * per_b; ctx->geo_shared = true;
+  }
+}
+
+void geo_slot_release(xpt_ctx* ctx) {
+  if (ctx->geo_shared || ctx->geo_len == 0) return;
+  GeoSlotTable& t = g_geo_slots[ctx->cfg.device & 63];
+  std::lock_guard<std::mutex> lk(t.m);
+  for (size_t i = 0; i < t.used.size(); ++i)
+    if (t.used[i].first == ctx->geo_off && t.used[i].second == ctx->geo_len) { t.used.erase(t.used.begin() + i); break; }
+  ctx->geo_len = 0;
+}
+
 template <bool GRAD, bool OUT, bool DSRC, bool DERIVE>
 int launch_fused(xpt_ctx* ctx, FusedArgs& a, cudaStream_t st) {
   static unsigned long long attr_done = 0;
   const size_t smem = FusedSmem<GRAD>::kBytes;
   XPT_TRY(ensure_dyn_smem(k_fused<GRAD, OUT, DSRC, DERIVE>, smem, ctx->cfg.device, &attr_done));
-  // camera geometry goes to the constant bank (uniform registers in the kernel); 60 KB hold
-  // kGeoConstFloats / (S*18 + N*12) snippets, larger batches are launched in chunks
+  // the geometry of up to `cap` snippets fits this ctx's constant-bank slot; larger batches are launched in chunks
   const int per_b = ctx->S * kGeoK + ctx->N * kGeoT;
-  const int cap = kGeoConstFloats / per_b;
+  const int cap = ctx->geo_len / per_b;
   const bool prof = ctx->prof_on > 0 && ctx->prof_count < ctx->prof_on && ctx->prof_kind == XPT_PROFILE_FUSED;
   if (prof) XPT_CUDA(cudaEventRecord((*ctx->prof_events)[2 * ctx->prof_count], st));
   for (int b0 = 0; b0 < ctx->B; b0 += cap) {
     const int bc = ctx->B - b0 < cap ? ctx->B - b0 : cap;
     const size_t kbytes = (size_t)bc * ctx->S * kGeoK * sizeof(float), tbytes = (size_t)bc * ctx->N * kGeoT * sizeof(float);
-    if (ctx->geo_direct) {
-      // the pyramid launch wrote the geometry of the whole batch straight into the constant bank
-    } else if (bc == ctx->B) {       // K block and [R|t] block are adjacent in the scratch: one copy
-      XPT_CUDA(cudaMemcpyToSymbolAsync(c_geo, ctx->geoK, kbytes + tbytes, 0, cudaMemcpyDeviceToDevice, st));
+    const size_t off = (size_t)ctx->geo_off * sizeof(float);
+    if (bc == ctx->B) {       // K block and [R|t] block are adjacent in the scratch: one copy
+      XPT_CUDA(cudaMemcpyToSymbolAsync(c_geo, ctx->geoK, kbytes + tbytes, off, cudaMemcpyDeviceToDevice, st));
     } else {
-      XPT_CUDA(cudaMemcpyToSymbolAsync(c_geo, ctx->geoK + (size_t)b0 * ctx->S * kGeoK, kbytes, 0, cudaMemcpyDeviceToDevice, st));
-      XPT_CUDA(cudaMemcpyToSymbolAsync(c_geo, ctx->geoT + (size_t)b0 * ctx->N * kGeoT, tbytes, kbytes, cudaMemcpyDeviceToDevice, st));
+      XPT_CUDA(cudaMemcpyToSymbolAsync(c_geo, ctx->geoK + (size_t)b0 * ctx->S * kGeoK, kbytes, off, cudaMemcpyDeviceToDevice, st));
+      XPT_CUDA(cudaMemcpyToSymbolAsync(c_geo, ctx->geoT + (size_t)b0 * ctx->N * kGeoT, tbytes, off + kbytes, cudaMemcpyDeviceToDevice, st));
     }
-    a.b_off = b0;
-    a.geo_t_off = bc * ctx->S * kGeoK;
+    a.b_off = b0; a.Bc = bc;
+    a.geo_k_off = ctx->geo_off;
+    a.geo_t_off = ctx->geo_off + bc * ctx->S * kGeoK;
     dim3 grid(bc, a.tiles_per_b);
     k_fused<GRAD, OUT, DSRC, DERIVE><<<grid, kFThreads, smem, st>>>(a);
     XPT_LAUNCH_CHECK("k_fused");
@@ -674,6 +710,90 @@ int launch_loss_epilogue(xpt_ctx* ctx, int slots_used, float w0, float w1, float
 
 }  // namespace
 
+// ---- NCCL, bound at run time ---------------------------------------------------------------------------------
+struct NcclId { char b[128]; };          // ncclUniqueId (passed BY VALUE to ncclCommInitRank)
+struct NcclApi {
+  void* so = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+typedef decltype(NcclApi::CommInitRank) nccl_init_fn;
+
+NcclApi* nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    // the copy already loaded by the host process (PyTorch ships libnccl.so.2) wins, then the system one
+    void* so = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!so) so = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!so) so = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!so) return;
+    api.GetUniqueId = reinterpret_cast<int (*)(void*)>(dlsym(so, "ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<nccl_init_fn>(dlsym(so, "ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(so, "ncclCommDestroy"));
+    api.AllReduce = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)>(dlsym(so, "ncclAllReduce"));
+    api.GroupStart = reinterpret_cast<int (*)()>(dlsym(so, "ncclGroupStart"));
+    api.GroupEnd = reinterpret_cast<int (*)()>(dlsym(so, "ncclGroupEnd"));
+    api.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(so, "ncclGetErrorString"));
+    if (api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GroupStart && api.GroupEnd) api.so = so;
+  });
+  return api.so ? &api : nullptr;
+}
+
+int nccl_fail(NcclApi* n, int rc, const char* what) {
+  return fail(XPT_NCCL_ERROR, "%s failed: %s", what, (n && n->GetErrorString) ? n->GetErrorString(rc) : "NCCL error");
+}
+constexpr int kNcclFloat32 = 7, kNcclSum = 0;
+
+int allreduce_on(xpt_ctx* ctx, float* const bufs[], const int64_t counts[], int num, cudaStream_t st) {
+  NcclApi* n = nccl_api();
+  if (!n) return fail(XPT_NCCL_ERROR, "libnccl.so.2 not found (dlopen)");
+  if (!ctx->nccl_comm) return fail(XPT_BAD_ARGUMENT, "no communicator bound: call xpt_comm_init or xpt_comm_attach first");
+  int rc = n->GroupStart();
+  if (rc != 0) return nccl_fail(n, rc, "ncclGroupStart");
+  for (int i = 0; i < num; ++i) {
+    if (!bufs[i] || counts[i] < 0) { n->GroupEnd(); return fail(XPT_BAD_ARGUMENT, "xpt_allreduce: bufs[%d] is NULL or has a negative count", i); }
+    if (counts[i] == 0) continue;
+    rc = n->AllReduce(bufs[i], bufs[i], (size_t)counts[i], kNcclFloat32, kNcclSum, ctx->nccl_comm, st);
+    if (rc != 0) { n->GroupEnd(); return nccl_fail(n, rc, "ncclAllReduce"); }
+  }
+  rc = n->GroupEnd();
+  if (rc != 0) return nccl_fail(n, rc, "ncclGroupEnd");
+  return XPT_OK;
+}
+
+struct ScaleArgs { const float* src[16]; float* dst[16]; long long count[16]; int n; const float* scale; };
+__global__ void __launch_bounds__(256) k_scale_tensors(ScaleArgs a) {
+  const int seg = blockIdx.y;
+  if (seg >= a.n) return;
+  const float sc = __ldg(a.scale);
+  const float* __restrict__ src = a.src[seg];
+  float* __restrict__ dst = a.dst[seg];
+  const long long n = a.count[seg], stride = (long long)gridDim.x * blockDim.x, t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((((uintptr_t)src | (uintptr_t)dst) & 15u) == 0) {
+    const long long n4 = n >> 2;
+    for (long long i = t; i < n4; i += stride) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+      v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+      reinterpret_cast<float4*>(dst)[i] = v;
+    }
+    for (long long i = (n4 << 2) + t; i < n; i += stride) dst[i] = src[i] * sc;
+  } else {
+    for (long long i = t; i < n; i += stride) dst[i] = src[i] * sc;
+  }
+}
+
+// dlpack.h v0.8 (ABI-stable): just enough of DLManagedTensor to validate a tensor
+struct DlTensorView {
+  void* data; int32_t device_type, device_id; int32_t ndim; uint8_t code, bits; uint16_t lanes;
+  int64_t* shape; int64_t* strides; uint64_t byte_offset;
+};
+
 // ===========================================================================
 // C-ABI
 // ===========================================================================
@@ -696,6 +816,10 @@ const char* xpt_status_string(int status) {
     case XPT_CUDA_ERROR: return "XPT_CUDA_ERROR";
     case XPT_NO_DEVICE: return "XPT_NO_DEVICE";
     case XPT_OUT_OF_MEMORY: return "XPT_OUT_OF_MEMORY";
+    case XPT_BAD_DTYPE: return "XPT_BAD_DTYPE";
+    case XPT_BAD_DEVICE: return "XPT_BAD_DEVICE";
+    case XPT_NOT_CONTIGUOUS: return "XPT_NOT_CONTIGUOUS";
+    case XPT_NCCL_ERROR: return "XPT_NCCL_ERROR";
     default: return "XPT_UNKNOWN";
   }
 }
@@ -745,15 +869,11 @@ int xpt_create(xpt_ctx** out, const xpt_config* cfg) {
     ctx->sm_chunks[l] = cdiv((long long)ctx->h[l] * ctx->w[l], 256);
     ctx->first_sm_chunk[l + 1] = ctx->first_sm_chunk[l] + ctx->sm_chunks[l];
   }
+  geo_slot_acquire(ctx);
   ctx->slots_per_b = ctx->first_tile[ctx->S] + ctx->first_sm_chunk[ctx->S];
   if (ctx->first_chunk[ctx->S] > ctx->slots_per_b) ctx->slots_per_b = ctx->first_chunk[ctx->S];
   if (ctx->ffirst_tile[ctx->S] > ctx->slots_per_b) ctx->slots_per_b = ctx->ffirst_tile[ctx->S];
 
-  {
-    void* cg = nullptr;
-    if (cudaGetSymbolAddress(&cg, c_geo) == cudaSuccess) ctx->c_geo_dev = static_cast<float*>(cg);
-    else (void)cudaGetLastError();
-  }
   int rc = XPT_OK;
   auto A = [&](float** p, size_t n) { if (rc == XPT_OK) rc = dev_alloc(ctx, p, n); };
   A(&ctx->geoK, (size_t)ctx->B * ctx->S * kGeoK + (size_t)ctx->B * ctx->N * kGeoT);   // K block, then [R|t] block
@@ -781,9 +901,11 @@ int xpt_create(xpt_ctx** out, const xpt_config* cfg) {
 
 void xpt_destroy(xpt_ctx* ctx) {
   if (!ctx) return;
+  geo_slot_release(ctx);
+  if (ctx->nccl_comm && ctx->nccl_owned) { NcclApi* n = nccl_api(); if (n) n->CommDestroy(ctx->nccl_comm); }
   cudaSetDevice(ctx->cfg.device);
   auto F = [](float* p) { if (p) cudaFree(p); };
-  F(ctx->geoK); F(reinterpret_cast<float*>(ctx->loss_sum_b)); F(ctx->loss_part); F(ctx->pose_part); F(ctx->tgt0_copy); F(ctx->min_part); F(ctx->l2_part);
+  F(ctx->geoK); F(reinterpret_cast<float*>(ctx->strip_pieces)); F(reinterpret_cast<float*>(ctx->strip_ctas)); F(ctx->strip_loss_part); F(ctx->strip_pose_part); F(reinterpret_cast<float*>(ctx->loss_sum_b)); F(ctx->loss_part); F(ctx->pose_part); F(ctx->tgt0_copy); F(ctx->min_part); F(ctx->l2_part);
   F(ctx->st_frames); F(ctx->st_K); F(ctx->st_pose); F(ctx->st_losses); F(ctx->st_loss_batch); F(ctx->st_dpose);
   F(ctx->st_dsource);
   for (int l = 0; l < kMaxScales; ++l) {
@@ -821,6 +943,88 @@ int xpt_get_config(const xpt_ctx* ctx, xpt_config* out) {
 
 size_t xpt_scratch_bytes(const xpt_ctx* ctx) { return ctx ? ctx->scratch_bytes : 0; }
 int xpt_last_launch_count(const xpt_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int xpt_geometry_slot_shared(const xpt_ctx* ctx) { return (ctx && ctx->geo_shared) ? 1 : 0; }
+
+int xpt_check_dlpack(const void* dl_managed_tensor, int device, int dense_from_dim) {
+  if (!dl_managed_tensor) return fail(XPT_BAD_ARGUMENT, "xpt_check_dlpack: NULL tensor");
+  const DlTensorView* t = static_cast<const DlTensorView*>(dl_managed_tensor);
+  if (t->code != 2 /* kDLFloat */ || t->bits != 32 || t->lanes != 1)
+    return fail(XPT_BAD_DTYPE, "tensor is not float32 (DLPack dtype code=%d bits=%d lanes=%d)", t->code, t->bits, t->lanes);
+  if (t->device_type != 2 /* kDLCUDA */) return fail(XPT_BAD_DEVICE, "tensor is not on a CUDA device (DLPack device_type %d): there is no CPU path", t->device_type);
+  if (device >= 0 && t->device_id != device) return fail(XPT_BAD_DEVICE, "tensor lives on cuda:%d, the ctx on cuda:%d", t->device_id, device);
+  if (t->strides) {
+    int64_t expect = 1;
+    for (int d = t->ndim - 1; d >= (dense_from_dim < 0 ? 0 : dense_from_dim); --d) {
+      if (t->shape[d] != 1 && t->strides[d] != expect)
+        return fail(XPT_NOT_CONTIGUOUS, "dimension %d has stride %lld, dense layout needs %lld", d, (long long)t->strides[d], (long long)expect);
+      expect *= t->shape[d];
+    }
+  }
+  return XPT_OK;
+}
+
+int xpt_scale_tensors(int device, const float* const src[], float* const dst[], const int64_t counts[], int num,
+                      const float* scale, void* stream) {
+  if (num < 0 || (num > 0 && (!src || !dst || !counts)) || !scale) return fail(XPT_BAD_ARGUMENT, "xpt_scale_tensors: NULL argument");
+  XPT_CUDA(cudaSetDevice(device));
+  for (int i0 = 0; i0 < num; i0 += 16) {
+    ScaleArgs a;
+    memset(&a, 0, sizeof(a));
+    a.scale = scale;
+    long long mx = 0;
+    for (int i = i0; i < num && i < i0 + 16; ++i) {
+      if (!src[i] || !dst[i] || counts[i] < 0) return fail(XPT_BAD_ARGUMENT, "xpt_scale_tensors: tensor %d is NULL or has a negative count", i);
+      a.src[a.n] = src[i]; a.dst[a.n] = dst[i]; a.count[a.n] = counts[i];
+      if (counts[i] > mx) mx = counts[i];
+      ++a.n;
+    }
+    if (mx == 0) continue;
+    int gx = cdiv(mx, 256 * 8);
+    if (gx > 1184) gx = 1184;
+    k_scale_tensors<<<dim3(gx, a.n), 256, 0, (cudaStream_t)stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(XPT_CUDA_ERROR, "launch of k_scale_tensors failed: %s", cudaGetErrorString(e));
+  }
+  return XPT_OK;
+}
+
+int xpt_comm_unique_id(unsigned char id[128]) {
+  if (!id) return fail(XPT_BAD_ARGUMENT, "xpt_comm_unique_id: NULL id");
+  NcclApi* n = nccl_api();
+  if (!n) return fail(XPT_NCCL_ERROR, "libnccl.so.2 not found (dlopen)");
+  const int rc = n->GetUniqueId(id);
+  return rc == 0 ? XPT_OK : nccl_fail(n, rc, "ncclGetUniqueId");
+}
+
+int xpt_comm_init(xpt_ctx* ctx, const unsigned char id[128], int nranks, int rank) {
+  if (!ctx || !id || nranks < 1 || rank < 0 || rank >= nranks) return fail(XPT_BAD_ARGUMENT, "xpt_comm_init: bad argument");
+  NcclApi* n = nccl_api();
+  if (!n) return fail(XPT_NCCL_ERROR, "libnccl.so.2 not found (dlopen)");
+  XPT_CUDA(cudaSetDevice(ctx->cfg.device));
+  if (ctx->nccl_comm && ctx->nccl_owned) n->CommDestroy(ctx->nccl_comm);
+  ctx->nccl_comm = nullptr;
+  NcclId uid;
+  memcpy(uid.b, id, 128);
+  void* comm = nullptr;
+  const int rc = n->CommInitRank(&comm, nranks, uid, rank);
+  if (rc != 0) return nccl_fail(n, rc, "ncclCommInitRank");
+  ctx->nccl_comm = comm; ctx->nccl_owned = true;
+  return XPT_OK;
+}
+
+int xpt_comm_attach(xpt_ctx* ctx, void* nccl_comm) {
+  if (!ctx) return fail(XPT_BAD_ARGUMENT, "xpt_comm_attach: NULL ctx");
+  NcclApi* n = nccl_api();
+  if (ctx->nccl_comm && ctx->nccl_owned && n) n->CommDestroy(ctx->nccl_comm);
+  ctx->nccl_comm = nccl_comm; ctx->nccl_owned = false;
+  return XPT_OK;
+}
+
+int xpt_allreduce(xpt_ctx* ctx, float* const bufs[], const int64_t counts[], int num, void* stream) {
+  if (!ctx || num < 0 || (num > 0 && (!bufs || !counts))) return fail(XPT_BAD_ARGUMENT, "xpt_allreduce: NULL argument");
+  XPT_CUDA(cudaSetDevice(ctx->cfg.device));
+  return allreduce_on(ctx, bufs, counts, num, (cudaStream_t)stream);
+}
 
 int xpt_pose_matr2rvec(int device, const float* matr, int count, int invert, float* rvec, void* stream) {
   if (!matr || !rvec || count < 0) return fail(XPT_BAD_ARGUMENT, "xpt_pose_matr2rvec: bad argument");
@@ -1116,6 +1320,8 @@ static int total_loss_body(xpt_ctx* ctx, const xpt_frames* frames, const float* 
   if (do_smooth && !derive_disp) XPT_TRY(check_list(ctx, (const void* const*)disp_ms, "disp_ms", true));
   if (derive_disp && (c.flags & XPT_FLAG_UNFUSED))
     return fail(XPT_BAD_ARGUMENT, "disp_ms == NULL (disparity derived from depth) needs the fused path");
+  if ((c.flags & XPT_FLAG_DEPTH_LOGIT) && (c.flags & XPT_FLAG_UNFUSED))
+    return fail(XPT_BAD_ARGUMENT, "XPT_FLAG_DEPTH_LOGIT (depth activation in the kernel) needs the fused path");
   cudaStream_t st = (cudaStream_t)stream;
   XPT_CUDA(cudaSetDevice(c.device));
   ctx->launches = 0;
@@ -1126,14 +1332,8 @@ static int total_loss_body(xpt_ctx* ctx, const xpt_frames* frames, const float* 
   const float inv_gb = 1.0f / (float)c.global_batch;
 
   const bool fused = !(c.flags & XPT_FLAG_UNFUSED);
-#ifdef XPT_GEO_DIRECT
-  // fused path, whole batch in one constant-bank chunk: the geometry slice of the pyramid launch writes c_geo itself
-  // (a kernel may write a __constant__ variable through its device address; later LAUNCHES on the stream see it)
-  ctx->geo_direct = fused && ctx->c_geo_dev != nullptr &&
-                    ctx->B * (ctx->S * kGeoK + ctx->N * kGeoT) <= kGeoConstFloats;
-#endif
   const int rc_pyr = launch_pyramids(ctx, frames, out->target_ms, true, st, pose, fused);   // + camera geometry in the same launch
-  if (rc_pyr != XPT_OK) { ctx->geo_direct = false; return rc_pyr; }
+  if (rc_pyr != XPT_OK) return rc_pyr;
   LevelTable lt = make_levels(ctx, frames, nullptr);
 
   PhotoArgs a;
@@ -1198,6 +1398,7 @@ static int total_loss_body(xpt_ctx* ctx, const xpt_frames* frames, const float* 
         sa.d_depth[l] = a.d_depth[l]; sa.d_disp[l] = a.d_disp[l];
       }
       sa.do_l1 = a.l1_kind != 0; sa.do_ssim = a.do_ssim; sa.do_smooth = a.do_smooth;
+      sa.logit = (c.flags & XPT_FLAG_DEPTH_LOGIT) ? 1 : 0;
       sa.grad_factor = a.grad_factor;
       sa.gcoef_l1 = a.gcoef_l1; sa.gcoef_ssim = a.gcoef_ssim; sa.gcoef_smooth = a.gcoef_smooth;
       sa.loss_part = ctx->strip_loss_part; sa.slots_per_b = ctx->strip_slots; sa.pose_part = ctx->strip_pose_part;
@@ -1220,6 +1421,7 @@ static int total_loss_body(xpt_ctx* ctx, const xpt_frames* frames, const float* 
     fa.tiles_per_b = ftiles;
     fa.B = ctx->B; fa.N = ctx->N;
     fa.do_l1 = a.l1_kind != 0; fa.do_ssim = a.do_ssim; fa.do_smooth = a.do_smooth;
+    fa.logit = (c.flags & XPT_FLAG_DEPTH_LOGIT) ? 1 : 0;
     fa.grad_factor = a.grad_factor;
     fa.gcoef_l1 = a.gcoef_l1; fa.gcoef_ssim = a.gcoef_ssim; fa.gcoef_smooth = a.gcoef_smooth;
     fa.loss_part = ctx->loss_part; fa.slots_per_b = ctx->slots_per_b; fa.pose_part = ctx->pose_part;
@@ -1310,8 +1512,14 @@ static int total_loss_body(xpt_ctx* ctx, const xpt_frames* frames, const float* 
 
 static int total_loss_impl(xpt_ctx* ctx, const xpt_frames* frames, const float* const depth_ms[],
                            const float* const disp_ms[], const float* pose, const xpt_loss_outputs* out, void* stream) {
-  const int rc = total_loss_body(ctx, frames, depth_ms, disp_ms, pose, out, stream);
-  if (ctx) ctx->geo_direct = false;      // per-call state of the fused path
+  int rc = total_loss_body(ctx, frames, depth_ms, disp_ms, pose, out, stream);
+  if (rc == XPT_OK && ctx && (ctx->cfg.flags & XPT_FLAG_ALLREDUCE)) {
+    // reference distributer.py:93-110: the replicas' loss scalars are summed; here on the step's own stream, so the
+    // collective is one more node of the step's CUDA graph
+    float* bufs[1] = {out->losses};
+    const int64_t counts[1] = {4};
+    rc = allreduce_on(ctx, bufs, counts, 1, (cudaStream_t)stream);
+  }
   return rc;
 }
 

@@ -11,6 +11,10 @@ XPT_FLAG_UNFUSED = 1
 XPT_FLAG_GRAPH = 2
 XPT_FLAG_NO_PIPELINE = 4
 XPT_FLAG_STRIP = 8
+XPT_FLAG_ALLREDUCE = 16
+XPT_FLAG_DEPTH_LOGIT = 32
+XPT_OK, XPT_BAD_ARGUMENT, XPT_BAD_SHAPE, XPT_CUDA_ERROR, XPT_NO_DEVICE, XPT_OUT_OF_MEMORY = 0, -1, -2, -3, -4, -5
+XPT_BAD_DTYPE, XPT_BAD_DEVICE, XPT_NOT_CONTIGUOUS, XPT_NCCL_ERROR = -6, -7, -8, -9
 XPT_PHOTO_L1, XPT_PHOTO_L2, XPT_PHOTO_SSIM = 0, 1, 2
 
 _FP = C.POINTER(C.c_float)
@@ -90,6 +94,14 @@ SYMBOLS = {
     "xpt_profile_select": (C.c_int, [C.c_void_p, C.c_int]),
     "xpt_profile_end": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "xpt_last_launch_count": (C.c_int, [C.c_void_p]),
+    "xpt_geometry_slot_shared": (C.c_int, [C.c_void_p]),
+    "xpt_check_dlpack": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "xpt_scale_tensors": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int,
+                                    C.c_void_p, C.c_void_p]),
+    "xpt_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "xpt_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "xpt_comm_attach": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "xpt_allreduce": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int, C.c_void_p]),
 }
 
 # XPTWARP_LIB: explicit path of another BUILD of the same library (profiling ablations); never a fallback

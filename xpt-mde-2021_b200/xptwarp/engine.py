@@ -50,8 +50,30 @@ def require_cuda_f32(**named):
 
 
 def _dense(t: torch.Tensor, name: str) -> torch.Tensor:
+    """The C-ABI takes dense tensors and the library never copies behind the caller's back (a silent
+    .contiguous() would be a hidden read + write of the tensor through a PyTorch kernel on the hot path)."""
     _check_cuda_f32(t, name)
-    return t if t.is_contiguous() else t.contiguous()
+    if not t.is_contiguous():
+        raise WrongInputException(f"{name} must be contiguous (shape {tuple(t.shape)}, strides {t.stride()}): "
+                                  "xptwarp does not copy its inputs; call .contiguous() where the tensor is produced")
+    return t
+
+
+def scale_tensors(tensors, scale: torch.Tensor):
+    """[t * scale for t in tensors] in ONE launch (xpt_scale_tensors); `scale` is a device scalar"""
+    ts = [t if t.is_contiguous() else t.contiguous() for t in tensors]
+    outs = [torch.empty_like(t) for t in ts]
+    n = len(ts)
+    if n == 0:
+        return outs
+    dev = ts[0].device
+    sc = scale.reshape(-1)[:1].to(device=dev, dtype=torch.float32).contiguous()
+    src = (C.c_void_p * n)(*[t.data_ptr() for t in ts])
+    dst = (C.c_void_p * n)(*[t.data_ptr() for t in outs])
+    cnt = (C.c_int64 * n)(*[t.numel() for t in ts])
+    _cabi.check(_cabi.lib().xpt_scale_tensors(dev.index or 0, src, dst, cnt, n, sc.data_ptr(),
+                                              C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return outs
 
 
 def _frame_view(t: torch.Tensor, name: str, lead: int) -> torch.Tensor:
@@ -61,7 +83,8 @@ def _frame_view(t: torch.Tensor, name: str, lead: int) -> torch.Tensor:
     if Cn != 3:
         raise WrongInputException(f"{name}: channel-last RGB expected, got {tuple(t.shape)}")
     if t.stride(-1) != 1 or t.stride(-2) != 3 or t.stride(-3) != W * 3:
-        t = t.contiguous()
+        raise WrongInputException(f"{name}: the inner (H, W, 3) dimensions must be dense, got strides {t.stride()}: "
+                                  "xptwarp does not copy its inputs (leading batch / frame dimensions may be strided views)")
     return t
 
 
@@ -116,6 +139,37 @@ class Plan:
 
     def scratch_bytes(self):
         return self._lib.xpt_scratch_bytes(self.handle)
+
+    def geometry_slot_shared(self):
+        return bool(self._lib.xpt_geometry_slot_shared(self.handle))
+
+    # ---- multi-rank (reference distributer.py:93-110) ---------------------------------------
+    def comm_init(self, dist=None):
+        """Create this plan's NCCL communicator: rank 0 makes the rendezvous id, torch.distributed (any backend)
+        carries its 128 bytes to the other ranks -- plumbing only, the collectives themselves are the library's."""
+        import torch.distributed as td
+        dist = dist or td
+        rank, world = dist.get_rank(), dist.get_world_size()
+        ident = (C.c_ubyte * 128)()
+        if rank == 0:
+            _cabi.check(self._lib.xpt_comm_unique_id(ident))
+        t = torch.tensor(list(ident), dtype=torch.uint8)
+        backend = dist.get_backend()
+        if backend == "nccl":
+            t = t.to(self.device)
+        dist.broadcast(t, 0)
+        raw = bytes(t.cpu().tolist())
+        buf = (C.c_ubyte * 128).from_buffer_copy(raw)
+        _cabi.check(self._lib.xpt_comm_init(self.handle, buf, world, rank))
+
+    def allreduce(self, tensors):
+        """in-place sum over the ranks of dense fp32 device tensors, one NCCL group on the current stream"""
+        ts = [_dense(t, f"tensors[{i}]") for i, t in enumerate(tensors)]
+        n = len(ts)
+        ptrs = (C.c_void_p * max(n, 1))(*[t.data_ptr() for t in ts])
+        cnt = (C.c_int64 * max(n, 1))(*[t.numel() for t in ts])
+        _cabi.check(self._lib.xpt_allreduce(self.handle, ptrs, cnt, n, self.stream()))
+        return tensors
 
     def _frames(self, source, target, intrinsic):
         f = XptFrames()

@@ -9,7 +9,7 @@ import torch
 
 from . import _cabi
 from .convert_pose import pose_matr2rvec_batch
-from .engine import WrongInputException, as_torch, get_plan, infer_scales, require_cuda_f32
+from .engine import WrongInputException, as_torch, get_plan, infer_scales, require_cuda_f32, scale_tensors
 from .flow_warping import FlowWarpMultiScale, infer_flow_scales
 from .synthesize import SynthesizeMultiScale
 from .util_funcs import multi_scale_like_depth, multi_scale_like_flow
@@ -59,9 +59,11 @@ class _TotalLossFn(torch.autograd.Function):
     def backward(ctx, g_total, _g_by_type):
         if not ctx.want_grad:
             raise RuntimeError("TotalLoss was evaluated without gradients")
-        d_pose, *d_maps = ctx.saved_tensors
-        outs = [g_total * d.reshape(s) for d, s in zip(d_maps, ctx.shapes)]
-        return (None, None, None, None, None, None, g_total * d_pose, *outs)
+        # the stored gradients are for an upstream of 1; the actual upstream (a device scalar) is applied to all of
+        # them in ONE launch of the library instead of one PyTorch multiply per tensor
+        d_pose, *d_maps = scale_tensors(list(ctx.saved_tensors), g_total)
+        outs = [d.reshape(s) for d, s in zip(d_maps, ctx.shapes)]
+        return (None, None, None, None, None, None, d_pose, *outs)
 
 
 class _StereoPoseFn(torch.autograd.Function):
@@ -355,7 +357,8 @@ class TotalLoss:
             if sw is not None and w != sw:
                 return False
             sw = w
-        return sw is not None and "depth_ms" in predictions and "pose" in predictions and "flow_ms" not in predictions
+        have_depth = "depth_ms" in predictions or "depth_logit_ms" in predictions
+        return sw is not None and have_depth and "pose" in predictions and "flow_ms" not in predictions
 
     def __call__(self, predictions, features):
         """
@@ -379,12 +382,13 @@ class TotalLoss:
             loss_by_type[loss_name] = loss_mean
         return torch.stack(losses).sum(), loss_by_type
 
-    def _fused_group(self, source, target, intrinsic, depth_ms, disp_ms, pose, w_l1, w_ssim, w_smooth, sw, split=0):
+    def _fused_group(self, source, target, intrinsic, depth_ms, disp_ms, pose, w_l1, w_ssim, w_smooth, sw, split=0,
+                     logit=False):
         """one fused launch: (total contribution, [L1, SSIM, smoothe] unweighted means -- [2, 3] per group of
         snippets when split > 0)"""
         B, N, H, W, _ = source.shape
         plan = get_plan(source.device.index or 0, B, N, H, W, infer_scales(H, depth_ms), sw, w_l1, w_ssim, w_smooth,
-                        self.batch_size)
+                        self.batch_size, _cabi.XPT_FLAG_DEPTH_LOGIT if logit else 0)
         maps = list(depth_ms) + (list(disp_ms) if (w_smooth != 0.0 and disp_ms is not None) else [])
         want_grad = torch.is_grad_enabled() and any(t.requires_grad for t in [pose, *maps])
         return _TotalLossFn.apply(plan, want_grad, int(split), source, target, intrinsic, pose, *maps)
@@ -405,7 +409,7 @@ class TotalLoss:
                   if v is not None)
         stereo = self._stereo_on(features)
         totals, by = [], {}
-        eyes, groups = {}, {}
+        eyes, groups, logits = {}, {}, {}
         for sfx in ("", "_R"):
             names = [n + sfx for n in _TEMPORAL if n + sfx in w]
             need = names or (stereo and ("stereoL1" in w or "stereoSSIM" in w))
@@ -414,7 +418,10 @@ class TotalLoss:
             if sfx and not stereo:
                 raise WrongInputException(f"losses {names} need a stereo rig: TotalLoss(stereo=True) and image5d_R in features")
             image5d, K = as_torch(features["image5d" + sfx]), as_torch(features["intrinsic" + sfx])
-            depth_ms = [as_torch(d) for d in predictions["depth_ms" + sfx]]
+            # "depth_logit_ms": the depth net's output BEFORE its last op; the kernel applies InverseSigmoidActivation
+            # (model_factory.py:133-137) at load and the gradient comes back on the logits
+            logit = ("depth_ms" + sfx) not in predictions
+            depth_ms = [as_torch(d) for d in predictions[("depth_logit_ms" if logit else "depth_ms") + sfx]]
             require_cuda_f32(**{"image5d" + sfx: image5d, "intrinsic" + sfx: K, "depth_ms" + sfx: depth_ms})
             eyes[sfx] = (image5d, K, depth_ms)
             if not names:
@@ -426,6 +433,9 @@ class TotalLoss:
                        if ("smoothe" + sfx in w and "disp_ms" + sfx in predictions) else None)
             groups[sfx] = (image5d, K, depth_ms, disp_ms, pose,
                            (w.get("L1" + sfx, 0.0), w.get("SSIM" + sfx, 0.0), w.get("smoothe" + sfx, 0.0)))
+            logits[sfx] = logit
+        if any(logits.values()) and stereo:
+            raise WrongInputException("depth_logit_ms is served for the temporal losses of one eye; a stereo rig needs depth_ms")
         if self._same_launch(groups):
             # both eyes of the rig in ONE fused launch (twice the batch): same kernels, half the launches and a
             # better filled last wave; the by-type means come back per eye from the per-snippet losses
@@ -443,7 +453,8 @@ class TotalLoss:
                         by[n + sfx] = by_eye[e, i]
         else:
             for sfx, (image5d, K, depth_ms, disp_ms, pose, wts) in groups.items():
-                total, by_type = self._fused_group(image5d[:, :-1], image5d[:, -1], K, depth_ms, disp_ms, pose, *wts, sw)
+                total, by_type = self._fused_group(image5d[:, :-1], image5d[:, -1], K, depth_ms, disp_ms, pose, *wts, sw,
+                                                   logit=logits.get(sfx, False))
                 totals.append(total)
                 for i, n in enumerate(_TEMPORAL):
                     if n + sfx in w:
