@@ -224,3 +224,19 @@ def test_strided_inputs_are_refused_not_copied(built):
     for fn in (lambda: engine._dense(t, "x"), lambda: engine._frame_view(torch.zeros(2, 8, 8, 6)[..., ::2], "img", 1)):
         with pytest.raises(engine.WrongInputException):
             fn()
+
+
+def test_fused_path_is_gated_on_the_loss_objects(built):
+    """TotalLoss takes the fused launch only when the object under each name is the stock one."""
+    import xptwarp
+    from xptwarp import losses as lm
+    sw = np.ones((4, 1), dtype=np.float32)
+    stock = xptwarp.loss_factory({"image": 1, "intrinsic": 1}, {"L1": 0.5, "SSIM": 0.5, "smoothe": 1.0}, sw, batch_size=2)
+    preds = {"depth_ms": [None], "pose": None}
+    assert stock._fused_ok(preds, {})
+    odd = lm.TotalLoss({"L1": lm.MonoDepth2LossMultiScale("SSIM", sw)}, {"L1": 1.0}, False, 2)
+    assert not odd._fused_ok(preds, {})
+    swapped = lm.TotalLoss({"L1": lm.PhotometricLossMultiScale("SSIM", sw)}, {"L1": 1.0}, False, 2)
+    assert not swapped._fused_ok(preds, {})
+    wrong_eye = lm.TotalLoss({"L1_R": lm.PhotometricLossMultiScale("L1", sw)}, {"L1_R": 1.0}, True, 2)
+    assert not wrong_eye._fused_ok(preds, {})

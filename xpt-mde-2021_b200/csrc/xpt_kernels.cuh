@@ -6,6 +6,7 @@
 // contraction here, so no tensor cores: the kernels are gather / stencil /
 // reduction work bounded by HBM and L1/shared-memory bandwidth.
 #pragma once
+#include <cuda.h>            // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -223,11 +224,11 @@ struct PyramidTiledArgs {
   GeoArgs geo;
 };
 
-// tile -> outputs.  FULL: the tile is kPyrTW wide, so every division below has a compile-time divisor.
-template <bool FULL>
-__device__ __forceinline__ void pyramid_emit(const PyramidTiledArgs& a, const float (*tile)[kPyrTW * 3], int tw_rt,
+// tile -> outputs.  FULL: the tile is TW wide, so every division below has a compile-time divisor.
+template <bool FULL, int TW = kPyrTW>
+__device__ __forceinline__ void pyramid_emit(const PyramidTiledArgs& a, const float (*tile)[TW * 3], int tw_rt,
                                              bool is_tgt, long long frame, int x0, int y0) {
-  const int tw = FULL ? kPyrTW : tw_rt;
+  const int tw = FULL ? TW : tw_rt;
   if (!is_tgt) {
     // RGBx texels (16 bytes) of every source level for the fused kernel's 128-bit gathers
 #pragma unroll
@@ -317,6 +318,61 @@ __global__ void __launch_bounds__(kPyrThreads, XPT_PYR_MINB) k_pyramid_tiled(con
     __syncthreads();
     pyramid_emit<false>(a, tile, tw, is_tgt, frame, x0, y0);
   }
+}
+
+// ---- the same pass with the tile loaded by the TMA unit -------------------------------------------------------
+// One elected thread arms an mbarrier with the tile's byte count and issues ONE bulk tensor copy
+// (cp.async.bulk.tensor -> UTMALDG): an 8-row x 64-pixel x 3-channel box of the frame lands in shared memory without
+// a single LDG / STS of the CTA; columns and rows beyond the frame are zero-filled by the unit.  The tensor maps
+// describe the caller's frames as they lie in HBM: source [B][N][H][W*3] (any batch / frame stride, e.g. the
+// image5d[:, :-1] view), target [B][H][W*3].
+constexpr int kPyrTmaTW = 64;                  // box = 192 floats x 8 rows (a box dimension may not exceed 256 elements)
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(kPyrThreads, 8) k_pyramid_tma(const __grid_constant__ PyramidTiledArgs a,
+                                                                 const __grid_constant__ CUtensorMap tm_src,
+                                                                 const __grid_constant__ CUtensorMap tm_tgt) {
+  __shared__ __align__(128) float tile[kPyrTH][kPyrTmaTW * 3];
+  __shared__ __align__(8) unsigned long long mbar;
+  const int nfr = a.N + 1;
+  if ((int)blockIdx.z == a.B * nfr) {           // geometry slice
+    if (a.with_geometry && blockIdx.y == 0) geometry_item(a.geo, blockIdx.x * blockDim.x + threadIdx.x);
+    return;
+  }
+  const int b = blockIdx.z / nfr, f = blockIdx.z % nfr;
+  const bool is_tgt = f == a.N;
+  if (is_tgt && a.target == nullptr) return;
+  const int x0 = blockIdx.x * kPyrTmaTW, y0 = blockIdx.y * kPyrTH;
+  if (x0 >= a.W) return;
+  const int tw = min(kPyrTmaTW, a.W - x0);      // multiple of 8
+  const unsigned bar = smem_u32(&mbar), dst = smem_u32(&tile[0][0]);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    constexpr unsigned kBytes = kPyrTH * kPyrTmaTW * 3 * sizeof(float);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kBytes) : "memory");
+    if (is_tgt)
+      asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                   ::"r"(dst), "l"(&tm_tgt), "r"(bar), "r"(x0 * 3), "r"(y0), "r"(b) : "memory");
+    else
+      asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                   ::"r"(dst), "l"(&tm_src), "r"(bar), "r"(x0 * 3), "r"(y0), "r"(f), "r"(b) : "memory");
+  }
+  // every thread waits for the transaction bytes (phase 0 of the barrier)
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar), "r"(0) : "memory");
+  const long long frame = is_tgt ? (long long)b : (long long)(b * a.N + f);
+  if (tw == kPyrTmaTW) pyramid_emit<true, kPyrTmaTW>(a, tile, tw, is_tgt, frame, x0, y0);
+  else pyramid_emit<false, kPyrTmaTW>(a, tile, tw, is_tgt, frame, x0, y0);
 }
 
 // adjoint of the source pyramid: d_source[full] += resize^T(d_source_level) for s > 1

@@ -92,6 +92,7 @@ struct xpt_ctx {
   int strip_nctas, strip_slots, strip_ns; bool strip_ready;
   float* strip_loss_part; float* strip_pose_part;
   void* nccl_comm; bool nccl_owned;   // communicator of XPT_FLAG_ALLREDUCE / xpt_allreduce
+  float** alloc_slot[160]; size_t alloc_floats[160]; int n_allocs;   // sizes of the lazily allocated scratch slots
   int geo_off, geo_len;         // this ctx's slot of the constant-bank geometry block (floats); geo_shared: the whole bank,
   bool geo_shared;              //   shared with other contexts because no private slot was free at xpt_create
   // staging for the host-buffer entry point
@@ -121,8 +122,19 @@ struct xpt_ctx {
 
 namespace {
 
+// Lazily allocated scratch: a slot is allocated once; its size is remembered, and a later request for MORE than that
+// (a call site that reuses the slot for another purpose) grows it instead of silently overrunning it.
 int dev_alloc(xpt_ctx* ctx, float** p, size_t nfloats) {
-  if (*p) return XPT_OK;
+  size_t* have = nullptr;
+  for (int i = 0; i < ctx->n_allocs; ++i)
+    if (ctx->alloc_slot[i] == p) { have = &ctx->alloc_floats[i]; break; }
+  if (*p && have && *have >= nfloats) return XPT_OK;
+  if (*p && !have) return XPT_OK;                  // allocated before tracking (xpt_create): sizes are fixed there
+  if (*p) {                                        // grow: the old contents are scratch, nothing to preserve
+    cudaFree(*p);
+    ctx->scratch_bytes -= *have * sizeof(float);
+    *p = nullptr;
+  }
   void* q = nullptr;
   cudaError_t e = cudaMalloc(&q, nfloats * sizeof(float));
   if (e != cudaSuccess) {
@@ -132,6 +144,8 @@ int dev_alloc(xpt_ctx* ctx, float** p, size_t nfloats) {
   }
   *p = static_cast<float*>(q);
   ctx->scratch_bytes += nfloats * sizeof(float);
+  if (have) *have = nfloats;
+  else if (ctx->n_allocs < 160) { ctx->alloc_slot[ctx->n_allocs] = p; ctx->alloc_floats[ctx->n_allocs] = nfloats; ++ctx->n_allocs; }
   return XPT_OK;
 }
 
@@ -204,6 +218,46 @@ int launch_geometry(xpt_ctx* ctx, const float* pose, const float* intrinsic, flo
   return XPT_OK;
 }
 
+// cuTensorMapEncodeTiled through the runtime (no link against libcuda): NULL when the driver has none
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TmapEncodeFn tmap_encoder() {
+  static TmapEncodeFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<TmapEncodeFn>(p);
+    else
+      (void)cudaGetLastError();
+  });
+  return getenv("XPT_NO_TMA") ? nullptr : fn;
+}
+
+// fp32 frames [outer...][H][W*3] as a TMA tensor: dim 0 = W*3 floats (dense), dim 1 = rows, then the frame / batch dims
+bool make_frame_tmap(CUtensorMap* tm, const float* base, int W, int H, int rank, const long long outer_dims[],
+                     const long long outer_strides_elems[]) {
+  TmapEncodeFn enc = tmap_encoder();
+  if (!enc) return false;
+  cuuint64_t dims[5] = {(cuuint64_t)W * 3, (cuuint64_t)H, 1, 1, 1};
+  cuuint64_t strides[4] = {(cuuint64_t)W * 3 * sizeof(float), 0, 0, 0};      // strides of dims 1.. in bytes
+  cuuint32_t box[5] = {(cuuint32_t)kPyrTmaTW * 3, (cuuint32_t)kPyrTH, 1, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  for (int i = 0; i < rank - 2; ++i) {
+    dims[2 + i] = (cuuint64_t)outer_dims[i];
+    strides[1 + i] = (cuuint64_t)outer_strides_elems[i] * sizeof(float);
+    if (outer_dims[i] > 1 && (strides[1 + i] % 16 || strides[1 + i] == 0)) return false;
+  }
+  // a dimension of extent 1 still needs a legal (multiple of 16, non-zero) stride
+  for (int i = 0; i < rank - 2; ++i)
+    if (strides[1 + i] == 0 || strides[1 + i] % 16) strides[1 + i] = (cuuint64_t)W * 3 * sizeof(float) * H;
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // source pyramid into the ctx (+ target pyramid into ctx or user buffers)
 // rgba: write the source levels (incl. full resolution) as RGBx texels for the fused kernel INSTEAD of the 3-channel levels
 int launch_pyramids(xpt_ctx* ctx, const xpt_frames* f, float* const target_ms[], bool want_source,
@@ -243,8 +297,29 @@ int launch_pyramids(xpt_ctx* ctx, const xpt_frames* f, float* const target_ms[],
         if (!any) grid = dim3(need, 1, ctx->B * (ctx->N + 1) + 1);
         const bool prof = ctx->prof_on > 0 && ctx->prof_count < ctx->prof_on && ctx->prof_kind == XPT_PROFILE_PYRAMID;
         if (prof) XPT_CUDA(cudaEventRecord((*ctx->prof_events)[2 * ctx->prof_count], st));
-        k_pyramid_tiled<<<grid, kPyrThreads, 0, st>>>(t);
-        XPT_LAUNCH_CHECK("k_pyramid_tiled");
+        // tile loads by the TMA unit (k_pyramid_tma) when tensor maps over the caller's frames can be encoded
+        CUtensorMap tm_src, tm_tgt;
+        bool tma = any;
+        if (tma) {
+          const long long sd[2] = {ctx->N, ctx->B}, ss[2] = {(long long)f->source_frame_stride, (long long)f->source_batch_stride};
+          tma = make_frame_tmap(&tm_src, f->source, ctx->W, ctx->H, 4, sd, ss);
+          if (tma && f->target) {
+            const long long td[1] = {ctx->B}, ts[1] = {(long long)f->target_batch_stride};
+            tma = make_frame_tmap(&tm_tgt, f->target, ctx->W, ctx->H, 3, td, ts);
+          } else if (tma) {
+            tm_tgt = tm_src;
+          }
+        }
+        if (tma) {
+          int gxt = cdiv(ctx->W, kPyrTmaTW);
+          if (geo_pose && need > gxt) gxt = need;
+          dim3 gridt(gxt, ctx->H / kPyrTH, ctx->B * (ctx->N + 1) + 1);
+          k_pyramid_tma<<<gridt, kPyrThreads, 0, st>>>(t, tm_src, tm_tgt);
+          XPT_LAUNCH_CHECK("k_pyramid_tma");
+        } else {
+          k_pyramid_tiled<<<grid, kPyrThreads, 0, st>>>(t);
+          XPT_LAUNCH_CHECK("k_pyramid_tiled");
+        }
         if (prof) { XPT_CUDA(cudaEventRecord((*ctx->prof_events)[2 * ctx->prof_count + 1], st)); ++ctx->prof_count; }
       }
       if (target_ms && f->target)

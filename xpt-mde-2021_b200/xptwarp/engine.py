@@ -132,6 +132,8 @@ class Plan:
         return self.H // self.scales[l], self.W // self.scales[l]
 
     def stream(self):
+        if not getattr(self, "pinned", False) and torch.cuda.is_current_stream_capturing():
+            self.pinned = True        # a capture now holds pointers into this plan's scratch: keep the ctx alive
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def launches(self):
@@ -440,7 +442,10 @@ class BoundTotalLoss:
 
 
 _PLANS: "collections.OrderedDict[tuple, Plan]" = collections.OrderedDict()
-_MAX_PLANS = 8
+# Large enough that one rig + flow loss set (about 8 plans per step) and a validation batch never evict a live plan;
+# a plan that a CUDA-graph capture has used is PINNED: the captured graph keeps raw pointers into the plan's scratch
+# (source pyramid, partial sums), so its ctx must outlive every replay.
+_MAX_PLANS = 64
 
 
 def get_plan(device_index, B, N, H, W, scales, scale_weights=None, w_l1=0.0, w_ssim=0.0, w_smooth=0.0,
@@ -454,10 +459,11 @@ def get_plan(device_index, B, N, H, W, scales, scale_weights=None, w_l1=0.0, w_s
         p = Plan(device_index, B, N, H, W, scales, sw, w_l1, w_ssim, w_smooth, int(global_batch) or B, flags,
                  img_grad_factor)
         _PLANS[key] = p
-        while len(_PLANS) > _MAX_PLANS:
+        if len(_PLANS) > _MAX_PLANS:
             # only drop the cache's reference: an autograd graph may still hold the plan for its backward;
-            # Plan.__del__ destroys the xpt_ctx when the last reference goes
-            _PLANS.popitem(last=False)
+            # Plan.__del__ destroys the xpt_ctx when the last reference goes.  Pinned plans are never dropped.
+            for k in [k for k, v in _PLANS.items() if not getattr(v, "pinned", False)][:len(_PLANS) - _MAX_PLANS]:
+                del _PLANS[k]
     else:
         _PLANS.move_to_end(key)
     return p

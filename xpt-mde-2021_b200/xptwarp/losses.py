@@ -346,8 +346,27 @@ class TotalLoss:
         dataset carries right frames (the reference tests the key "image_R" and then reads "image5d_R")."""
         return bool(self.stereo) and ("image_R" in features or "image5d_R" in features)
 
+    @staticmethod
+    def _is_stock(name, obj):
+        """the fused launch stands for the loss OBJECT the reference's loop would call, so the object under a name
+        must be the stock one (type, method, key suffix): TotalLoss({"L1": MonoDepth2LossMultiScale(...)}) takes the
+        generic loop below instead of silently being scored as plain L1"""
+        sfx = "_R" if name.endswith("_R") else ""
+        base = name[:-2] if sfx else name
+        if base in ("L1", "SSIM"):
+            return type(obj) is PhotometricLossMultiScale and obj.method == base and obj.key_suffix == sfx
+        if base == "smoothe":
+            return type(obj) is SmoothenessLossMultiScale and obj.key_suffix == sfx
+        if base in ("stereoL1", "stereoSSIM"):
+            return type(obj) is StereoDepthLoss and obj.method == base[6:]
+        if base == "stereoPose":
+            return type(obj) is StereoPoseLoss
+        return False
+
     def _fused_ok(self, predictions, features):
         if not self.loss_objects or any(k not in _FUSED_SET for k in self.loss_objects):
+            return False
+        if not all(self._is_stock(k, o) for k, o in self.loss_objects.items()):
             return False
         sw = None
         for obj in self.loss_objects.values():
