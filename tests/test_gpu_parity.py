@@ -974,14 +974,17 @@ def test_contexts_on_two_streams_do_not_share_geometry(xw):
     """two contexts with different cameras run interleaved on two streams; each owns a private
     constant-bank slot, so neither can project with the other's K / [R|t]."""
     from oracle import xpt_oracle as orc
+    import gc
     lw, sw = orc.LOSS_RIGID_T1, orc.SCALE_WEIGHT_T1
+    xw.engine._PLANS.clear()          # the cached plans of earlier tests hold constant-bank slots
+    gc.collect()
     cases = []
     for seed, (B, H, W) in ((11, (4, 64, 128)), (12, (4, 64, 128))):
         feats, preds = orc.make_inputs(B, H, W, seed=seed)
         f, p = _to_cuda(feats, preds)
         plan = xw.engine.Plan(0, B, 4, H, W, [1, 2, 4, 8], sw, lw["L1"], lw["SSIM"], lw["smoothe"], B, 0)
-        assert not plan.geometry_slot_shared()
         ref = _run_total(plan, f, p, want_grad=True)
+        assert not plan.geometry_slot_shared()
         ref = {k: ([t.clone() for t in v] if isinstance(v, list) else v.clone()) for k, v in ref.items() if v is not None}
         cases.append((plan, f, p, ref, torch.cuda.Stream()))
     torch.cuda.synchronize()

@@ -53,9 +53,13 @@ constexpr int kFRedSrc = 4;                    // sources whose pose partials ar
 constexpr int kFRedFloats = kFRedSrc * kFCH * 16;                  // 832 (>= 48 floats of loss scratch)
 
 
-// camera geometry in the constant bank (uniform-register operands of the projection): a ctx owns a slot of it
-// (xptwarp.cu: geo_slot_*), laid out [Bc][S][18] (K_s, inv K_s) then [Bc][N][12] ([R|t]) for the Bc snippets of a launch
+// Camera geometry in the constant bank (uniform-register operands of the projection).  The bank has a K region
+// (records of S x 18 floats: K_s, inv K_s per level) and a [R|t] region (records of N x 12 floats); a ctx owns a run of
+// records in each (xptwarp.cu: geo_slot_*).  A launch addresses its records through blockIdx.x itself -- the grid's x
+// extent starts at the ctx's first K record and the CTAs below it exit at once -- so the K block's address stays
+// blockIdx.x * S * 18 + level * 18 with a compile-time base (a run-time base offset cost 4 % of the kernel in spills).
 constexpr int kGeoConstFloats = 15360;         // 60 KB
+constexpr int kGeoKRegion = 9216;              // floats of the K region (60 %: S x 18 against N x 12 at S = N = 4)
 __constant__ float c_geo[kGeoConstFloats];
 
 template <bool GRAD>
@@ -130,15 +134,15 @@ __device__ __forceinline__ float warp_reduce16(float v[16], int lane) {
 struct FusedArgs {
   LevelTable lt;                       // Level.tiles_x/y/slot_base describe the 64x13 tiling
   int B, N;
-  int b_off, Bc;                       // first snippet / snippets of this launch (constant-bank chunking)
-  int geo_k_off, geo_t_off;            // float offsets of this launch's K and [R|t] blocks inside c_geo (the ctx's slot)
+  int b_off;                           // snippet of blockIdx.x = 0 (first snippet of this launch minus the K record offset)
+  int k_rec0;                          // first K record of the ctx's slot: CTAs with blockIdx.x < k_rec0 have no work
+  int geo_t_off;                       // float offset such that [R|t] of (blockIdx.x, n) sits at geo_t_off + (blockIdx.x * N + n) * 12
   int tiles_per_b;
   int first_tile[kMaxScales + 1];
   const float* depth[kMaxScales];
   const float* disp[kMaxScales];
   const float4* src4[kMaxScales];      // RGBx texels of the source levels [B,N,h,w] (written by the pyramid kernels)
   int do_l1, do_ssim, do_smooth;
-  int logit;                           // depth[] holds the depth net's logits (XPT_FLAG_DEPTH_LOGIT): activation at load, dL/dlogit out
   float norm_photo[kMaxScales];        // sw_s / (N*h*w*3)
   float norm_sm_x[kMaxScales];
   float norm_sm_y[kMaxScales];
@@ -201,8 +205,10 @@ __device__ __forceinline__ void halo_sample(const float* __restrict__ gk, const 
 }
 
 // GRAD: backward in the same launch.  OUT: synth_ms / mask_ms are written.  DSRC: dL/dsource scatter.
-// DERIVE: the disparity of the smoothness term is safe_reciprocal_number(depth) formed in the kernel.
-template <bool GRAD, bool OUT, bool DSRC, bool DERIVE>
+// DERIVE 1: the disparity of the smoothness term is safe_reciprocal_number(depth) formed in the kernel.
+// DERIVE 2: in addition depth[] holds the depth net's LOGITS (XPT_FLAG_DEPTH_LOGIT): InverseSigmoidActivation is
+//           applied when the depth tile is loaded and d_depth[] receives dL/dlogit.
+template <bool GRAD, bool OUT, bool DSRC, int DERIVE>
 __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ FusedArgs a) {
   using SM = FusedSmem<GRAD>;
   extern __shared__ __align__(16) float smem[];
@@ -226,7 +232,8 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
   // final partial wave is filled with short CTAs.  (A persistent grid drawing tiles from a ticket was measured in
   // round 2: +2 % time at config 2 and config 3 -- the ticket's two barriers per tile cost more than the tail.)
   int t = blockIdx.y;
-  const int bl = blockIdx.x;               // snippet inside this launch's constant-bank chunk
+  const int bl = blockIdx.x;               // K record of this snippet inside the constant bank
+  if (bl < a.k_rec0) return;
   const int b = a.b_off + bl;
   int l = 0;
   while (l + 1 < a.lt.S && t >= a.first_tile[l + 1]) ++l;
@@ -236,7 +243,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
   const int ty0 = (t / L.tiles_x) * kFCH, tx0 = (t % L.tiles_x) * kFCW;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int slot = L.slot_base + t;
-  const float* const gk = c_geo + a.geo_k_off + (bl * a.lt.S + l) * kGeoK;     // K_s (9), inv K_s (9): uniform registers
+  const float* const gk = c_geo + (bl * a.lt.S + l) * kGeoK;     // K_s (9), inv K_s (9): uniform registers
 
   // ---- target tile, depth tile and pixel rays (halo 2); zero outside the image ---------------------
   // depth 0 marks "no sample": the reference's D != 0 validity test (bilinear_interp.py:53-76) then also
@@ -255,7 +262,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
           const float* p = tgt + ((long long)gy * W + gx) * 3;
           v0 = __ldg(p); v1 = __ldg(p + 1); v2 = __ldg(p + 2);
           d = __ldg(dep + (long long)gy * W + gx);
-          if (a.logit) d = depth_of_logit(d);
+          if (DERIVE == 2) d = depth_of_logit(d);
           // reference order.  The last rows of K_s and inv(K_s) are exactly (0,0,1)
           // (synthesize_base.py:66-71), so ray.z = 1 and p.z = Y.z hold bit-exactly and are not recomputed.
           const float fx = (float)gx, fy = (float)gy;
@@ -671,7 +678,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
     for (int o = 0; o < 2; ++o) {
       const int gx = tx0 + c0 + o;
       if (gy < H && gx < W)
-        a.d_depth[l][(long long)b * P + gy * W + gx] = a.logit ? gD[o] * ddepth_dlogit(sD[(cyy + 2) * kFP + c0 + o + 2]) : gD[o];
+        a.d_depth[l][(long long)b * P + gy * W + gx] = DERIVE == 2 ? gD[o] * ddepth_dlogit(sD[(cyy + 2) * kFP + c0 + o + 2]) : gD[o];
     }
   }
 

@@ -327,13 +327,14 @@ __global__ void __launch_bounds__(kPyrThreads, XPT_PYR_MINB) k_pyramid_tiled(con
 // describe the caller's frames as they lie in HBM: source [B][N][H][W*3] (any batch / frame stride, e.g. the
 // image5d[:, :-1] view), target [B][H][W*3].
 constexpr int kPyrTmaTW = 64;                  // box = 192 floats x 8 rows (a box dimension may not exceed 256 elements)
+constexpr int kPyrTmaBoxes = 2;                // boxes per CTA: a 128-pixel tile like k_pyramid_tiled, two copies in flight
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-__global__ void __launch_bounds__(kPyrThreads, 8) k_pyramid_tma(const __grid_constant__ PyramidTiledArgs a,
-                                                                 const __grid_constant__ CUtensorMap tm_src,
-                                                                 const __grid_constant__ CUtensorMap tm_tgt) {
-  __shared__ __align__(128) float tile[kPyrTH][kPyrTmaTW * 3];
+__global__ void __launch_bounds__(kPyrThreads, XPT_PYR_MINB) k_pyramid_tma(const __grid_constant__ PyramidTiledArgs a,
+                                                                            const __grid_constant__ CUtensorMap tm_src,
+                                                                            const __grid_constant__ CUtensorMap tm_tgt) {
+  __shared__ __align__(128) float tile[kPyrTmaBoxes][kPyrTH][kPyrTmaTW * 3];
   __shared__ __align__(8) unsigned long long mbar;
   const int nfr = a.N + 1;
   if ((int)blockIdx.z == a.B * nfr) {           // geometry slice
@@ -343,24 +344,32 @@ __global__ void __launch_bounds__(kPyrThreads, 8) k_pyramid_tma(const __grid_con
   const int b = blockIdx.z / nfr, f = blockIdx.z % nfr;
   const bool is_tgt = f == a.N;
   if (is_tgt && a.target == nullptr) return;
-  const int x0 = blockIdx.x * kPyrTmaTW, y0 = blockIdx.y * kPyrTH;
+  const int x0 = blockIdx.x * (kPyrTmaTW * kPyrTmaBoxes), y0 = blockIdx.y * kPyrTH;
   if (x0 >= a.W) return;
-  const int tw = min(kPyrTmaTW, a.W - x0);      // multiple of 8
-  const unsigned bar = smem_u32(&mbar), dst = smem_u32(&tile[0][0]);
+  const unsigned bar = smem_u32(&mbar);
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    constexpr unsigned kBytes = kPyrTH * kPyrTmaTW * 3 * sizeof(float);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kBytes) : "memory");
-    if (is_tgt)
-      asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                   ::"r"(dst), "l"(&tm_tgt), "r"(bar), "r"(x0 * 3), "r"(y0), "r"(b) : "memory");
-    else
-      asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                   ::"r"(dst), "l"(&tm_src), "r"(bar), "r"(x0 * 3), "r"(y0), "r"(f), "r"(b) : "memory");
+    constexpr unsigned kBoxBytes = kPyrTH * kPyrTmaTW * 3 * sizeof(float);
+    int nbox = 0;
+#pragma unroll
+    for (int k = 0; k < kPyrTmaBoxes; ++k) nbox += (x0 + k * kPyrTmaTW < a.W) ? 1 : 0;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kBoxBytes * nbox) : "memory");
+#pragma unroll
+    for (int k = 0; k < kPyrTmaBoxes; ++k) {
+      const int xk = x0 + k * kPyrTmaTW;
+      if (xk >= a.W) continue;
+      const unsigned dst = smem_u32(&tile[k][0][0]);
+      if (is_tgt)
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                     ::"r"(dst), "l"(&tm_tgt), "r"(bar), "r"(xk * 3), "r"(y0), "r"(b) : "memory");
+      else
+        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                     ::"r"(dst), "l"(&tm_src), "r"(bar), "r"(xk * 3), "r"(y0), "r"(f), "r"(b) : "memory");
+    }
   }
   // every thread waits for the transaction bytes (phase 0 of the barrier)
   asm volatile(
@@ -371,8 +380,14 @@ __global__ void __launch_bounds__(kPyrThreads, 8) k_pyramid_tma(const __grid_con
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t}" ::"r"(bar), "r"(0) : "memory");
   const long long frame = is_tgt ? (long long)b : (long long)(b * a.N + f);
-  if (tw == kPyrTmaTW) pyramid_emit<true, kPyrTmaTW>(a, tile, tw, is_tgt, frame, x0, y0);
-  else pyramid_emit<false, kPyrTmaTW>(a, tile, tw, is_tgt, frame, x0, y0);
+#pragma unroll
+  for (int k = 0; k < kPyrTmaBoxes; ++k) {
+    const int xk = x0 + k * kPyrTmaTW;
+    if (xk >= a.W) continue;
+    const int tw = min(kPyrTmaTW, a.W - xk);    // multiple of 8
+    if (tw == kPyrTmaTW) pyramid_emit<true, kPyrTmaTW>(a, tile[k], tw, is_tgt, frame, xk, y0);
+    else pyramid_emit<false, kPyrTmaTW>(a, tile[k], tw, is_tgt, frame, xk, y0);
+  }
 }
 
 // adjoint of the source pyramid: d_source[full] += resize^T(d_source_level) for s > 1

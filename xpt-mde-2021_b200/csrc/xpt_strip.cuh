@@ -848,6 +848,10 @@ __global__ void __launch_bounds__(StripSmem<NS>::kThreads, NS == 1 ? 2 : 1) k_st
   const StripCta cta = a.ctas[blockIdx.x];
   if (cta.count == 0) return;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // The first steps of a CTA read ring rows "before the beginning" (row s-1, s-2 of step 0) with zero weights: the
+  // rings must hold finite numbers then, not whatever an earlier kernel left in shared memory (0 x NaN = NaN).
+  for (int i = threadIdx.x; i < StripSmem<NS>::kFloats; i += StripSmem<NS>::kThreads) smem[i] = 0.f;
+  __syncthreads();
   if (NS == 4) {
     // one setmaxnreg per warpgroup, executed by its four warps together, then the warps part into their roles
     if (wid < 4) {

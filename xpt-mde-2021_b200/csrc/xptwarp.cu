@@ -93,8 +93,8 @@ struct xpt_ctx {
   float* strip_loss_part; float* strip_pose_part;
   void* nccl_comm; bool nccl_owned;   // communicator of XPT_FLAG_ALLREDUCE / xpt_allreduce
   float** alloc_slot[160]; size_t alloc_floats[160]; int n_allocs;   // sizes of the lazily allocated scratch slots
-  int geo_off, geo_len;         // this ctx's slot of the constant-bank geometry block (floats); geo_shared: the whole bank,
-  bool geo_shared;              //   shared with other contexts because no private slot was free at xpt_create
+  int geo_k_off, geo_t_off, geo_cap;   // this ctx's runs of K / [R|t] records in the constant bank (float offsets), snippets per launch
+  bool geo_shared;              // no private run was free: the start of both regions, shared with other such contexts
   // staging for the host-buffer entry point
   float* st_frames; float* st_K; float* st_pose; float* st_losses; float* st_loss_batch; float* st_dpose;
   float* st_dsource;
@@ -311,7 +311,7 @@ int launch_pyramids(xpt_ctx* ctx, const xpt_frames* f, float* const target_ms[],
           }
         }
         if (tma) {
-          int gxt = cdiv(ctx->W, kPyrTmaTW);
+          int gxt = cdiv(ctx->W, kPyrTmaTW * kPyrTmaBoxes);
           if (geo_pose && need > gxt) gxt = need;
           dim3 gridt(gxt, ctx->H / kPyrTH, ctx->B * (ctx->N + 1) + 1);
           k_pyramid_tma<<<gridt, kPyrThreads, 0, st>>>(t, tm_src, tm_tgt);
@@ -527,66 +527,78 @@ int launch_photo(xpt_ctx* ctx, const PhotoArgs& a, cudaStream_t st) {
 }
 
 // Constant-bank slots: k_fused reads the camera geometry through uniform-register operands, i.e. from the 60 KB
-// __constant__ block c_geo.  Every ctx owns a private slot of it (first fit, per device), so launches of DIFFERENT
-// contexts on different streams never touch each other's geometry.  A ctx that finds no free slot shares the whole
-// bank (geo_shared) and must then be ordered against the other contexts of the device by its caller.
-struct GeoSlotTable { std::mutex m; std::vector<std::pair<int, int>> used; };     // (offset, length), sorted by offset
+// __constant__ block c_geo: a K region (records of S x 18 floats) and a [R|t] region (records of N x 12 floats).
+// Every ctx owns a private run of records in both (first fit, per device), so launches of DIFFERENT contexts on
+// different streams never touch each other's geometry.  A ctx that finds no free run shares the start of both
+// regions (geo_shared) and must then be ordered against the other contexts of the device by its caller.
+struct GeoSlotTable { std::mutex m; std::vector<std::pair<int, int>> used_k, used_t; };     // (offset, length) in floats, sorted
 GeoSlotTable g_geo_slots[64];
 
+// first fit of `want` floats inside [lo, hi) with the offset (relative to lo) a multiple of `align`; -1 = none
+int geo_first_fit(std::vector<std::pair<int, int>>& used, int lo, int hi, int want, int align, size_t* at) {
+  int pos = lo;
+  for (size_t i = 0; i <= used.size(); ++i) {
+    const int end = i < used.size() ? used[i].first : hi;
+    const int p = lo + ((pos - lo + align - 1) / align) * align;
+    if (end - p >= want) { *at = i; return p; }
+    if (i < used.size()) pos = used[i].first + used[i].second;
+  }
+  return -1;
+}
+
 void geo_slot_acquire(xpt_ctx* ctx) {
-  const int per_b = ctx->S * kGeoK + ctx->N * kGeoT;
-  int want = ctx->B * per_b;
-  if (want > kGeoConstFloats) want = (kGeoConstFloats / per_b) * per_b;      // larger batches launch in chunks
+  const int krec = ctx->S * kGeoK, trec = ctx->N * kGeoT;
+  int cap = kGeoKRegion / krec;
+  if ((kGeoConstFloats - kGeoKRegion) / trec < cap) cap = (kGeoConstFloats - kGeoKRegion) / trec;
+  const int nb = ctx->B < cap ? ctx->B : cap;             // snippets per launch; larger batches launch in chunks
   GeoSlotTable& t = g_geo_slots[ctx->cfg.device & 63];
   std::lock_guard<std::mutex> lk(t.m);
-  int pos = 0;
-  size_t i = 0;
-  for (; i <= t.used.size(); ++i) {
-    const int end = i < t.used.size() ? t.used[i].first : kGeoConstFloats;
-    if (end - pos >= want) break;
-    if (i < t.used.size()) pos = t.used[i].first + t.used[i].second;
-  }
-  if (i <= t.used.size() && (i < t.used.size() ? t.used[i].first : kGeoConstFloats) - pos >= want) {
-    t.used.insert(t.used.begin() + i, std::make_pair(pos, want));
-    ctx->geo_off = pos; ctx->geo_len = want; ctx->geo_shared = false;
+  size_t ik = 0, it = 0;
+  const int pk = geo_first_fit(t.used_k, 0, kGeoKRegion, nb * krec, krec, &ik);
+  const int pt = geo_first_fit(t.used_t, kGeoKRegion, kGeoConstFloats, nb * trec, 1, &it);
+  ctx->geo_cap = nb;
+  if (pk >= 0 && pt >= 0) {
+    t.used_k.insert(t.used_k.begin() + ik, std::make_pair(pk, nb * krec));
+    t.used_t.insert(t.used_t.begin() + it, std::make_pair(pt, nb * trec));
+    ctx->geo_k_off = pk; ctx->geo_t_off = pt; ctx->geo_shared = false;
   } else {
-    ctx->geo_off = 0; ctx->geo_len = (kGeoConstFloats / per_b) * per_b; ctx->geo_shared = true;
+    ctx->geo_k_off = 0; ctx->geo_t_off = kGeoKRegion; ctx->geo_shared = true;
   }
 }
 
 void geo_slot_release(xpt_ctx* ctx) {
-  if (ctx->geo_shared || ctx->geo_len == 0) return;
+  if (ctx->geo_shared || ctx->geo_cap == 0) return;
   GeoSlotTable& t = g_geo_slots[ctx->cfg.device & 63];
   std::lock_guard<std::mutex> lk(t.m);
-  for (size_t i = 0; i < t.used.size(); ++i)
-    if (t.used[i].first == ctx->geo_off && t.used[i].second == ctx->geo_len) { t.used.erase(t.used.begin() + i); break; }
-  ctx->geo_len = 0;
+  for (size_t i = 0; i < t.used_k.size(); ++i)
+    if (t.used_k[i].first == ctx->geo_k_off) { t.used_k.erase(t.used_k.begin() + i); break; }
+  for (size_t i = 0; i < t.used_t.size(); ++i)
+    if (t.used_t[i].first == ctx->geo_t_off) { t.used_t.erase(t.used_t.begin() + i); break; }
+  ctx->geo_cap = 0;
 }
 
-template <bool GRAD, bool OUT, bool DSRC, bool DERIVE>
+template <bool GRAD, bool OUT, bool DSRC, int DERIVE>
 int launch_fused(xpt_ctx* ctx, FusedArgs& a, cudaStream_t st) {
   static unsigned long long attr_done = 0;
   const size_t smem = FusedSmem<GRAD>::kBytes;
   XPT_TRY(ensure_dyn_smem(k_fused<GRAD, OUT, DSRC, DERIVE>, smem, ctx->cfg.device, &attr_done));
-  // the geometry of up to `cap` snippets fits this ctx's constant-bank slot; larger batches are launched in chunks
-  const int per_b = ctx->S * kGeoK + ctx->N * kGeoT;
-  const int cap = ctx->geo_len / per_b;
+  // the geometry of up to `cap` snippets fits this ctx's constant-bank records; larger batches are launched in chunks
+  if (ctx->geo_cap == 0) geo_slot_acquire(ctx);        // taken at the first fused launch: other entry points need none
+  const int cap = ctx->geo_cap;
+  const int krec = ctx->S * kGeoK, trec = ctx->N * kGeoT;
+  const int k_rec0 = ctx->geo_k_off / krec;            // blockIdx.x of the first snippet of a launch
   const bool prof = ctx->prof_on > 0 && ctx->prof_count < ctx->prof_on && ctx->prof_kind == XPT_PROFILE_FUSED;
   if (prof) XPT_CUDA(cudaEventRecord((*ctx->prof_events)[2 * ctx->prof_count], st));
   for (int b0 = 0; b0 < ctx->B; b0 += cap) {
     const int bc = ctx->B - b0 < cap ? ctx->B - b0 : cap;
-    const size_t kbytes = (size_t)bc * ctx->S * kGeoK * sizeof(float), tbytes = (size_t)bc * ctx->N * kGeoT * sizeof(float);
-    const size_t off = (size_t)ctx->geo_off * sizeof(float);
-    if (bc == ctx->B) {       // K block and [R|t] block are adjacent in the scratch: one copy
-      XPT_CUDA(cudaMemcpyToSymbolAsync(c_geo, ctx->geoK, kbytes + tbytes, off, cudaMemcpyDeviceToDevice, st));
-    } else {
-      XPT_CUDA(cudaMemcpyToSymbolAsync(c_geo, ctx->geoK + (size_t)b0 * ctx->S * kGeoK, kbytes, off, cudaMemcpyDeviceToDevice, st));
-      XPT_CUDA(cudaMemcpyToSymbolAsync(c_geo, ctx->geoT + (size_t)b0 * ctx->N * kGeoT, tbytes, off + kbytes, cudaMemcpyDeviceToDevice, st));
-    }
-    a.b_off = b0; a.Bc = bc;
-    a.geo_k_off = ctx->geo_off;
-    a.geo_t_off = ctx->geo_off + bc * ctx->S * kGeoK;
-    dim3 grid(bc, a.tiles_per_b);
+    XPT_CUDA(cudaMemcpyToSymbolAsync(c_geo, ctx->geoK + (size_t)b0 * krec, (size_t)bc * krec * sizeof(float),
+                                     (size_t)ctx->geo_k_off * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    XPT_CUDA(cudaMemcpyToSymbolAsync(c_geo, ctx->geoT + (size_t)b0 * trec, (size_t)bc * trec * sizeof(float),
+                                     (size_t)ctx->geo_t_off * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    a.k_rec0 = k_rec0;
+    a.b_off = b0 - k_rec0;                               // snippet of blockIdx.x = 0
+    a.geo_t_off = ctx->geo_t_off - k_rec0 * trec;        // [R|t] of (blockIdx.x, n) at geo_t_off + (blockIdx.x * N + n) * 12
+    dim3 grid(k_rec0 + bc, a.tiles_per_b);
     k_fused<GRAD, OUT, DSRC, DERIVE><<<grid, kFThreads, smem, st>>>(a);
     XPT_LAUNCH_CHECK("k_fused");
   }
@@ -944,7 +956,6 @@ int xpt_create(xpt_ctx** out, const xpt_config* cfg) {
     ctx->sm_chunks[l] = cdiv((long long)ctx->h[l] * ctx->w[l], 256);
     ctx->first_sm_chunk[l + 1] = ctx->first_sm_chunk[l] + ctx->sm_chunks[l];
   }
-  geo_slot_acquire(ctx);
   ctx->slots_per_b = ctx->first_tile[ctx->S] + ctx->first_sm_chunk[ctx->S];
   if (ctx->first_chunk[ctx->S] > ctx->slots_per_b) ctx->slots_per_b = ctx->first_chunk[ctx->S];
   if (ctx->ffirst_tile[ctx->S] > ctx->slots_per_b) ctx->slots_per_b = ctx->ffirst_tile[ctx->S];
@@ -1496,27 +1507,39 @@ static int total_loss_body(xpt_ctx* ctx, const xpt_frames* frames, const float* 
     fa.tiles_per_b = ftiles;
     fa.B = ctx->B; fa.N = ctx->N;
     fa.do_l1 = a.l1_kind != 0; fa.do_ssim = a.do_ssim; fa.do_smooth = a.do_smooth;
-    fa.logit = (c.flags & XPT_FLAG_DEPTH_LOGIT) ? 1 : 0;
     fa.grad_factor = a.grad_factor;
     fa.gcoef_l1 = a.gcoef_l1; fa.gcoef_ssim = a.gcoef_ssim; fa.gcoef_smooth = a.gcoef_smooth;
     fa.loss_part = ctx->loss_part; fa.slots_per_b = ctx->slots_per_b; fa.pose_part = ctx->pose_part;
     bool want_out = false;
     for (int l = 0; l < ctx->S; ++l) want_out = want_out || out->synth_ms[l] || out->mask_ms[l];
-    // template dispatch: (GRAD, OUT, DSRC, DERIVE)
+    // template dispatch: (GRAD, OUT, DSRC, DERIVE mode); the logit mode is compiled for training steps only
+    const bool logit = (c.flags & XPT_FLAG_DEPTH_LOGIT) != 0;
+    if (logit && do_smooth && !derive_disp)
+      return fail(XPT_BAD_ARGUMENT, "XPT_FLAG_DEPTH_LOGIT: pass disp_ms == NULL (the disparity is formed from the activated depth)");
     const int sel = (grad ? 8 : 0) | (want_out ? 4 : 0) | (dsrc ? 2 : 0) | (derive_disp ? 1 : 0);
-    switch (sel) {
-      case 0: XPT_TRY((launch_fused<false, false, false, false>(ctx, fa, st))); break;
-      case 1: XPT_TRY((launch_fused<false, false, false, true>(ctx, fa, st))); break;
-      case 4: XPT_TRY((launch_fused<false, true, false, false>(ctx, fa, st))); break;
-      case 5: XPT_TRY((launch_fused<false, true, false, true>(ctx, fa, st))); break;
-      case 8: XPT_TRY((launch_fused<true, false, false, false>(ctx, fa, st))); break;
-      case 9: XPT_TRY((launch_fused<true, false, false, true>(ctx, fa, st))); break;
-      case 10: XPT_TRY((launch_fused<true, false, true, false>(ctx, fa, st))); break;
-      case 11: XPT_TRY((launch_fused<true, false, true, true>(ctx, fa, st))); break;
-      case 12: XPT_TRY((launch_fused<true, true, false, false>(ctx, fa, st))); break;
-      case 13: XPT_TRY((launch_fused<true, true, false, true>(ctx, fa, st))); break;
-      case 14: XPT_TRY((launch_fused<true, true, true, false>(ctx, fa, st))); break;
-      default: XPT_TRY((launch_fused<true, true, true, true>(ctx, fa, st))); break;
+    if (logit) {
+      switch ((grad ? 4 : 0) | (want_out ? 2 : 0) | (dsrc ? 1 : 0)) {
+        case 0: XPT_TRY((launch_fused<false, false, false, 2>(ctx, fa, st))); break;
+        case 2: XPT_TRY((launch_fused<false, true, false, 2>(ctx, fa, st))); break;
+        case 4: XPT_TRY((launch_fused<true, false, false, 2>(ctx, fa, st))); break;
+        case 5: XPT_TRY((launch_fused<true, false, true, 2>(ctx, fa, st))); break;
+        case 6: XPT_TRY((launch_fused<true, true, false, 2>(ctx, fa, st))); break;
+        case 7: XPT_TRY((launch_fused<true, true, true, 2>(ctx, fa, st))); break;
+        default: return fail(XPT_BAD_ARGUMENT, "dL/dsource without other gradients is not served");
+      }
+    } else switch (sel) {
+      case 0: XPT_TRY((launch_fused<false, false, false, 0>(ctx, fa, st))); break;
+      case 1: XPT_TRY((launch_fused<false, false, false, 1>(ctx, fa, st))); break;
+      case 4: XPT_TRY((launch_fused<false, true, false, 0>(ctx, fa, st))); break;
+      case 5: XPT_TRY((launch_fused<false, true, false, 1>(ctx, fa, st))); break;
+      case 8: XPT_TRY((launch_fused<true, false, false, 0>(ctx, fa, st))); break;
+      case 9: XPT_TRY((launch_fused<true, false, false, 1>(ctx, fa, st))); break;
+      case 10: XPT_TRY((launch_fused<true, false, true, 0>(ctx, fa, st))); break;
+      case 11: XPT_TRY((launch_fused<true, false, true, 1>(ctx, fa, st))); break;
+      case 12: XPT_TRY((launch_fused<true, true, false, 0>(ctx, fa, st))); break;
+      case 13: XPT_TRY((launch_fused<true, true, false, 1>(ctx, fa, st))); break;
+      case 14: XPT_TRY((launch_fused<true, true, true, 0>(ctx, fa, st))); break;
+      default: XPT_TRY((launch_fused<true, true, true, 1>(ctx, fa, st))); break;
     }
     EpilogueArgs ea;
     memset(&ea, 0, sizeof(ea));
