@@ -274,8 +274,12 @@ def main():
              | (_cabi.XPT_FLAG_STRIP if args.strip else 0) | (_cabi.XPT_FLAG_ALLREDUCE if world > 1 else 0))
     plan = xptwarp.get_plan(local_rank, B, N_SRC, H, W, [1, 2, 4, 8], sw, lw["L1"], lw["SSIM"], lw["smoothe"],
                             global_batch, flags)
+    exchange = "none (1 GPU)"
     if world > 1:
         plan.comm_init(dist)
+        exchange = ("the 4 loss scalars summed INSIDE k_epilogue through peer memory (CUDA IPC inboxes over NVLink), part of "
+                    "the step's CUDA graph, no collective launch" if plan.comm_status()[0] else
+                    "ncclAllReduce of the 4 loss scalars inside the step's CUDA graph (XPT_FLAG_ALLREDUCE)")
 
     # ---- inputs: enough distinct resident sets that a step never finds its inputs in the 126 MB L2
     probe_f, probe_p = orc.make_inputs(1, H, W, N=N_SRC, n_scales=N_SCALES, seed=1)
@@ -354,12 +358,13 @@ def main():
     barrier()
     ms_total = e0.elapsed_time(e1)
     if ms_total < 400:      # keep the clock sampler meaningful on tiny workloads: same kernels, untimed.
-        # No collective in here: ranks run different numbers of filler steps, and unmatched all-reduces deadlock.
-        t_end = time.time() + 0.6
-        i = 0
-        while time.time() < t_end:
+        # The steps carry the in-graph all-reduce when world > 1, so every rank must issue the SAME number of them:
+        # the count comes from rank 0's timing (unmatched all-reduces deadlock).
+        fill = torch.tensor([min(20000, int(600.0 / max(ms_total / args.steps, 1e-3)))], dtype=torch.int64, device=device)
+        if dist is not None:
+            dist.broadcast(fill, src=0)
+        for i in range(int(fill.item())):
             calls[i % n_sets].run(stream)
-            i += 1
         torch.cuda.synchronize()
     clocks = sampler.stop()
     t = torch.tensor([ms_total], dtype=torch.float64, device=device)
@@ -421,7 +426,7 @@ def main():
         # levels s > 1 ((gamma - 1) x 12) per full-resolution target pixel
         pyr_bytes = 60 + N_SRC * GAMMA * 16 + (GAMMA - 1) * 12
         pach = px_rank * pyr_bytes / (pyr_ms * 1e-3) / 1e9
-        roofline["secondary"] = {"bound": "hbm", "kernel": "k_pyramid_tiled", "achieved": pach, "peak": peak, "unit": "GB/s",
+        roofline["secondary"] = {"bound": "hbm", "kernel": "k_pyramid_tma", "achieved": pach, "peak": peak, "unit": "GB/s",
                                  "frac": pach / peak, "kernel_ms": pyr_ms, "bytes_per_pixel": pyr_bytes,
                                  "algorithmic_bytes_per_launch": px_rank * pyr_bytes}
     step_model = {"bytes_per_pixel": BYTES_SURVEY_STEP,
@@ -450,11 +455,16 @@ def main():
     h2d = 4 * (himg.numel() + hK.numel() + hpose.numel() + sum(d.numel() for d in hdepth) + sum(d.numel() for d in hdisp))
     d2h = 4 * (4 + hdpose.numel() + sum(d.numel() for d in hdd) + sum(d.numel() for d in hds))
 
+    dev_losses = torch.zeros(4, device=device)
+
     def host_step():
         rc = plan._lib.xpt_total_loss_host(plan.handle, C.byref(fr), C.byref(dptr), C.byref(sptr), hpose.data_ptr(),
                                            C.byref(o), stream)
         if rc != 0:
             _cabi.check(rc)
+        if dist is not None:             # the host entry point's losses are rank-local: sum the 4 floats over the ranks
+            dev_losses.copy_(hlosses, non_blocking=True)
+            plan.allreduce([dev_losses])
     for _ in range(20):                  # the call is captured as a graph on its third use; then let the link settle
         host_step()
     barrier()
@@ -500,17 +510,18 @@ def main():
                        "l2": f"rotating {n_sets} resident input sets ({n_sets * per_set / 1e6:.0f} MB > 126 MB L2)",
                        "launch": "eager" if args.no_graph else "cuda-graph replay", "fused": not args.unfused,
                        "host_affinity": numa or "unbound",
-                       "collectives": ("none (1 GPU)" if world == 1 else
-                                       "ncclAllReduce of the 4 loss scalars inside the step's CUDA graph (XPT_FLAG_ALLREDUCE)" +
-                                       (f" + a {args.net_grad_mb:g} MB stand-in net-gradient bucket per step on a second stream"
-                                        if args.net_grad_mb > 0 else ""))},
+                       "collectives": exchange + (f" + a {args.net_grad_mb:g} MB stand-in net-gradient bucket per step on a second stream"
+                                                  if (world > 1 and args.net_grad_mb > 0) else "")},
             "roofline": roofline, "step_model": step_model, "cpu_baseline": cpu, "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches_per_step * args.steps,
         }
         print(json.dumps(line))
     if dist is not None:
+        if plan.comm_status()[1]:
+            raise SystemExit("loss exchange: a peer's record did not arrive (ranks ran different numbers of steps)")
         dist.barrier()
+        plan.comm_destroy()              # collective teardown while the process group is alive, not at interpreter exit
         dist.destroy_process_group()
 
 

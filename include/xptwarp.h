@@ -98,7 +98,10 @@ typedef struct {
 /* multi-rank data parallelism (reference distributer.py:93-110 ReplicaOutputIntegrator): xpt_total_loss ends with an
  * in-place ncclAllReduce(sum) of out->losses[4] over the communicator bound by xpt_comm_init / xpt_comm_attach,
  * enqueued on the call's own stream right behind the epilogue kernel -- and therefore captured in the same CUDA
- * graph as the step under XPT_FLAG_GRAPH.                                                                      */
+ * graph as the step under XPT_FLAG_GRAPH.  After xpt_comm_init across processes of one node the fused path does not
+ * even launch that collective: the epilogue kernel itself pushes the 4 scalars into every rank's inbox with peer
+ * stores over NVLink and sums what it received (xpt_comm_status tells which).  xpt_total_loss_host does NOT reduce: its losses land in host memory
+ * chunk by chunk and stay rank-local (a host caller sums the 4 floats with whatever host-side collective it has). */
 #define XPT_FLAG_ALLREDUCE 16u
 /* depth_ms[] holds the depth net's LOGITS.  xpt_total_loss applies the net's last op itself --
  * InverseSigmoidActivation, depth = safe_reciprocal_number(sigmoid(x) + 0.01) (model/build_model/model_factory.py:
@@ -301,6 +304,15 @@ XPT_API int xpt_comm_unique_id(unsigned char id[128]);
 XPT_API int xpt_comm_init(xpt_ctx* ctx, const unsigned char id[128], int nranks, int rank);
 XPT_API int xpt_comm_attach(xpt_ctx* ctx, void* nccl_comm);
 XPT_API int xpt_allreduce(xpt_ctx* ctx, float* const bufs[], const int64_t counts[], int num, void* stream);
+/* Releases the ctx's communicator and peer mappings while the process group is still alive (collective teardown must
+ * not be left to interpreter exit).  Synchronises the device and drops the ctx's captured graphs first: a captured
+ * step references the communicator.                                                                               */
+XPT_API int xpt_comm_destroy(xpt_ctx* ctx);
+/* uses_peer_memory: 1 when XPT_FLAG_ALLREDUCE sums the loss scalars INSIDE the epilogue kernel through peer memory
+ * (every rank's inbox mapped with CUDA IPC over NVLink) -- no collective launch behind the step; 0 = ncclAllReduce.
+ * exchange_error: 1 after a step in which a peer's record did not arrive within ~2 s (ranks issuing different numbers
+ * of steps); the losses of that step are invalid.  Synchronising (reads a device flag).                             */
+XPT_API int xpt_comm_status(xpt_ctx* ctx, int* uses_peer_memory, int* exchange_error);
 
 /* number of kernels the last call on this ctx launched (bench's gpu_launches) */
 XPT_API int xpt_last_launch_count(const xpt_ctx* ctx);

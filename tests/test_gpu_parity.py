@@ -1077,16 +1077,25 @@ def _nccl_worker(rank, world, port, q):
     p = {"depth_ms": [d[lo:hi].cuda() for d in preds["depth_ms"]], "disp_ms": [d[lo:hi].cuda() for d in preds["disp_ms"]],
          "pose": preds["pose"][lo:hi].cuda()}
     out = {}
-    for name, flags in (("eager", _cabi.XPT_FLAG_ALLREDUCE), ("graph", _cabi.XPT_FLAG_ALLREDUCE | _cabi.XPT_FLAG_GRAPH)):
+    plans = []
+    for name, flags, no_p2p in (("eager", _cabi.XPT_FLAG_ALLREDUCE, False),
+                                ("graph", _cabi.XPT_FLAG_ALLREDUCE | _cabi.XPT_FLAG_GRAPH, False),
+                                ("nccl", _cabi.XPT_FLAG_ALLREDUCE | _cabi.XPT_FLAG_GRAPH, True)):
         plan = xptwarp.get_plan(rank, hi - lo, 4, H, W, [1, 2, 4, 8], sw, lw["L1"], lw["SSIM"], lw["smoothe"], B, flags)
+        if no_p2p:
+            os.environ["XPT_NO_P2P"] = "1"
         plan.comm_init()
+        os.environ.pop("XPT_NO_P2P", None)
+        plans.append(plan)
         img = f["image5d"]
         st = torch.cuda.Stream()
         with torch.cuda.stream(st):
-            for _ in range(3):          # the third call of the graph variant is a replay
+            for _ in range(4):          # the third call of the graph variants is a replay
                 r = plan.total_loss(img[:, :-1], img[:, -1], f["intrinsic"], p["depth_ms"], p["disp_ms"], p["pose"], want_grad=True)
             st.synchronize()
-        out[name] = (r["losses"].cpu().numpy(), r["d_pose"].cpu().numpy(), lo, hi)
+        p2p, err = plan.comm_status()
+        out[name] = (r["losses"].cpu().numpy(), r["d_pose"].cpu().numpy(), lo, hi, p2p, err)
+        plan.comm_destroy()             # before the next variant re-binds the cached plan / before the group goes away
     q.put((rank, out))
     dist.barrier()
     dist.destroy_process_group()
@@ -1118,10 +1127,15 @@ def test_two_gpu_sharded_losses_equal_the_global_batch(xw):
         pr.join(timeout=60)
         assert pr.exitcode == 0
     for rank in (0, 1):
-        for name in ("eager", "graph"):
-            losses, d_pose, lo, hi = got[rank][name]
+        for name in ("eager", "graph", "nccl"):
+            losses, d_pose, lo, hi, p2p, err = got[rank][name]
+            assert not err, f"{name}: a peer's loss record did not arrive"
+            assert p2p == (name != "nccl"), f"{name}: peer-memory exchange {'not ' if not p2p else ''}in use"
             margin(f"2-GPU {name} rank{rank} losses", relerr(losses, ref_l), 2e-6)
             margin(f"2-GPU {name} rank{rank} d_pose", relerr(d_pose, ref_dp[lo:hi]), 1e-6)
+    # every rank holds the bit-identical sum (rank-ordered addition in the epilogue kernel)
+    for name in ("eager", "graph"):
+        assert np.array_equal(got[0][name][0], got[1][name][0])
 
 
 def test_depth_logit_boundary_against_golden(xw):

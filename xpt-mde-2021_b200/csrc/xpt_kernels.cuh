@@ -1342,7 +1342,50 @@ struct EpilogueArgs {
   float* losses; float* loss_batch;            // loss_batch may be NULL
   double* loss_sum_b;                          // [B][3] scratch
   unsigned int* ticket;                        // zero before the first launch; self-resetting
+  // multi-rank (reference distributer.py:93-110): nranks > 1 sums the 4 loss scalars over the ranks INSIDE this kernel,
+  // through peer memory over NVLink -- no collective launch behind the step (see loss_exchange below)
+  int nranks, rank;
+  float* const* peer_inbox;                    // device table [nranks]: every rank's inbox [2][nranks][kInboxSlot] (own included)
+  unsigned int* seq;                           // this rank's step counter
+  unsigned int* exchange_error;                // set when a peer did not arrive within the spin budget
+  long long spin_budget;                       // clock64 ticks
 };
+constexpr int kInboxSlot = 8;                  // floats per (parity, source rank): 4 x (value, step number) pairs (32 bytes)
+constexpr int kMaxRanks = 64;
+
+// The path's only exchange, fused into the epilogue: every rank PUSHES its 4 loss scalars into slot [step parity][rank]
+// of every rank's inbox with peer stores (P2P over NVLink / NVSwitch, mapped through CUDA IPC), then waits until its
+// own inbox holds this step's record of every rank and adds them up in rank order -- so all ranks obtain the
+// bit-identical sum.  One thread per peer.  Each scalar travels as ONE aligned 8-byte store {value, step number}
+// (single-copy atomic), so a record validates itself and neither side needs a fence: the latency is one NVLink write.
+// Two parity slots are enough: a rank cannot start step s+2 before every rank has published step s+1, i.e. after
+// every rank has consumed step s.  A peer that does not arrive within the budget (ranks issuing different numbers of
+// steps) raises *exchange_error instead of hanging the GPU.
+__device__ __forceinline__ void loss_exchange(const EpilogueArgs& a, const float loc[4], unsigned s, float (*got)[4], int r) {
+  const int par = (int)(s & 1u);
+  {
+    float* slot = a.peer_inbox[r] + (size_t)(par * a.nranks + a.rank) * kInboxSlot;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      asm volatile("st.relaxed.sys.global.v2.b32 [%0], {%1, %2};" ::"l"(slot + 2 * k), "r"(__float_as_uint(loc[k])), "r"(s) : "memory");
+  }
+  {
+    const float* slot = a.peer_inbox[a.rank] + (size_t)(par * a.nranks + r) * kInboxSlot;
+    const long long t0 = clock64();
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      unsigned v = 0u, seen = 0u;
+      while (ok) {
+        asm volatile("ld.relaxed.sys.global.v2.b32 {%0, %1}, [%2];" : "=r"(v), "=r"(seen) : "l"(slot + 2 * k) : "memory");
+        if (seen == s) break;
+        if (clock64() - t0 > a.spin_budget) ok = false;
+      }
+      got[r][k] = ok ? __uint_as_float(v) : 0.f;
+    }
+    if (!ok) *a.exchange_error = 1u;
+  }
+}
 
 __global__ void __launch_bounds__(128) k_epilogue(EpilogueArgs a) {
   __shared__ double red[4][3];
@@ -1373,15 +1416,30 @@ __global__ void __launch_bounds__(128) k_epilogue(EpilogueArgs a) {
   __syncthreads();
   if (threadIdx.x == 0) last = atomicAdd(a.ticket, 1u) == (unsigned)(a.B - 1);
   __syncthreads();
-  if (last && threadIdx.x == 0) {
+  if (!last) return;                            // block-uniform
+  __shared__ float loc[4];
+  __shared__ unsigned step;
+  __shared__ float got[kMaxRanks][4];
+  if (threadIdx.x == 0) {
     __threadfence();
     double tot[3] = {0.0, 0.0, 0.0};
     for (int bb = 0; bb < a.B; ++bb)
       for (int k = 0; k < 3; ++k) tot[k] += ((volatile double*)a.loss_sum_b)[bb * 3 + k];
     const double m0 = tot[0] * a.inv_global_batch, m1 = tot[1] * a.inv_global_batch, m2 = tot[2] * a.inv_global_batch;
-    a.losses[0] = (float)(a.w0 * m0 + a.w1 * m1 + a.w2 * m2);
-    a.losses[1] = (float)m0; a.losses[2] = (float)m1; a.losses[3] = (float)m2;
+    loc[0] = (float)(a.w0 * m0 + a.w1 * m1 + a.w2 * m2);
+    loc[1] = (float)m0; loc[2] = (float)m1; loc[3] = (float)m2;
     *a.ticket = 0u;
+    if (a.nranks > 1) { step = *a.seq + 1u; *a.seq = step; }
+    else { a.losses[0] = loc[0]; a.losses[1] = loc[1]; a.losses[2] = loc[2]; a.losses[3] = loc[3]; }
+  }
+  if (a.nranks <= 1) return;
+  __syncthreads();
+  if ((int)threadIdx.x < a.nranks) loss_exchange(a, loc, step, got, threadIdx.x);
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float v = 0.f;
+    for (int r = 0; r < a.nranks; ++r) v += got[r][threadIdx.x];      // rank order: the same sum on every rank
+    a.losses[threadIdx.x] = v;
   }
 }
 

@@ -92,6 +92,12 @@ struct xpt_ctx {
   int strip_nctas, strip_slots, strip_ns; bool strip_ready;
   float* strip_loss_part; float* strip_pose_part;
   void* nccl_comm; bool nccl_owned;   // communicator of XPT_FLAG_ALLREDUCE / xpt_allreduce
+  // peer-memory loss exchange (k_epilogue / loss_exchange): inbox of this rank, the table of every rank's inbox as
+  // mapped into this process (CUDA IPC), the step counter and the error flag; p2p = all ranks agreed to use it
+  bool p2p; int nranks, rank;
+  float* inbox; float** peer_host; float** peer_table; unsigned int* exch_seq; unsigned int* exch_err;
+  bool exchanged;                     // the last fused epilogue already summed the losses over the ranks
+  bool host_call;                     // inside xpt_total_loss_host: the chunks' losses are rank-local (no collective per chunk)
   float** alloc_slot[160]; size_t alloc_floats[160]; int n_allocs;   // sizes of the lazily allocated scratch slots
   int geo_k_off, geo_t_off, geo_cap;   // this ctx's runs of K / [R|t] records in the constant bank (float offsets), snippets per launch
   bool geo_shared;              // no private run was free: the start of both regions, shared with other such contexts
@@ -805,6 +811,7 @@ struct NcclApi {
   int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
@@ -824,6 +831,7 @@ NcclApi* nccl_api() {
     api.CommInitRank = reinterpret_cast<nccl_init_fn>(dlsym(so, "ncclCommInitRank"));
     api.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(so, "ncclCommDestroy"));
     api.AllReduce = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)>(dlsym(so, "ncclAllReduce"));
+    api.AllGather = reinterpret_cast<int (*)(const void*, void*, size_t, int, void*, cudaStream_t)>(dlsym(so, "ncclAllGather"));
     api.GroupStart = reinterpret_cast<int (*)()>(dlsym(so, "ncclGroupStart"));
     api.GroupEnd = reinterpret_cast<int (*)()>(dlsym(so, "ncclGroupEnd"));
     api.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(so, "ncclGetErrorString"));
@@ -852,6 +860,17 @@ int allreduce_on(xpt_ctx* ctx, float* const bufs[], const int64_t counts[], int 
   rc = n->GroupEnd();
   if (rc != 0) return nccl_fail(n, rc, "ncclGroupEnd");
   return XPT_OK;
+}
+
+// exchange fields of the fused epilogue: the losses are summed over the ranks inside k_epilogue when the ctx asks for
+// the collective (XPT_FLAG_ALLREDUCE), the peer inboxes are mapped, and the call is not a chunk of the host entry point
+void set_exchange(xpt_ctx* ctx, EpilogueArgs& ea) {
+  ctx->exchanged = false;
+  if (!(ctx->cfg.flags & XPT_FLAG_ALLREDUCE) || ctx->host_call || !ctx->p2p || ctx->nranks < 2) return;
+  ea.nranks = ctx->nranks; ea.rank = ctx->rank;
+  ea.peer_inbox = ctx->peer_table; ea.seq = ctx->exch_seq; ea.exchange_error = ctx->exch_err;
+  ea.spin_budget = 4000000000LL;           // ~2 s at 1.9 GHz
+  ctx->exchanged = true;
 }
 
 struct ScaleArgs { const float* src[16]; float* dst[16]; long long count[16]; int n; const float* scale; };
@@ -985,11 +1004,35 @@ int xpt_create(xpt_ctx** out, const xpt_config* cfg) {
   return XPT_OK;
 }
 
+// unmap the peers' inboxes, free this rank's, destroy an owned communicator
+static void comm_release(xpt_ctx* ctx) {
+  if (ctx->peer_host) {
+    for (int r = 0; r < ctx->nranks; ++r)
+      if (r != ctx->rank && ctx->peer_host[r]) cudaIpcCloseMemHandle(ctx->peer_host[r]);
+    delete[] ctx->peer_host; ctx->peer_host = nullptr;
+  }
+  if (ctx->inbox) { cudaFree(ctx->inbox); ctx->inbox = nullptr; }
+  if (ctx->peer_table) { cudaFree(ctx->peer_table); ctx->peer_table = nullptr; }
+  if (ctx->exch_seq) { cudaFree(ctx->exch_seq); ctx->exch_seq = nullptr; ctx->exch_err = nullptr; }
+  ctx->p2p = false;
+  if (ctx->nccl_comm && ctx->nccl_owned) { NcclApi* n = nccl_api(); if (n) n->CommDestroy(ctx->nccl_comm); }
+  ctx->nccl_comm = nullptr; ctx->nccl_owned = false;
+}
+
 void xpt_destroy(xpt_ctx* ctx) {
   if (!ctx) return;
   geo_slot_release(ctx);
-  if (ctx->nccl_comm && ctx->nccl_owned) { NcclApi* n = nccl_api(); if (n) n->CommDestroy(ctx->nccl_comm); }
   cudaSetDevice(ctx->cfg.device);
+  // captured steps hold references on the communicator (NCCL waits for them in ncclCommDestroy): graphs go first
+  if (ctx->graphs) {
+    for (auto& e : *ctx->graphs) cudaGraphExecDestroy(e.exec);
+    delete ctx->graphs; ctx->graphs = nullptr;
+  }
+  if (ctx->host_graphs) {
+    for (auto& e : *ctx->host_graphs) cudaGraphExecDestroy(e.exec);
+    delete ctx->host_graphs; ctx->host_graphs = nullptr;
+  }
+  comm_release(ctx);
   auto F = [](float* p) { if (p) cudaFree(p); };
   F(ctx->geoK); F(reinterpret_cast<float*>(ctx->strip_pieces)); F(reinterpret_cast<float*>(ctx->strip_ctas)); F(ctx->strip_loss_part); F(ctx->strip_pose_part); F(reinterpret_cast<float*>(ctx->loss_sum_b)); F(ctx->loss_part); F(ctx->pose_part); F(ctx->tgt0_copy); F(ctx->min_part); F(ctx->l2_part);
   F(ctx->st_frames); F(ctx->st_K); F(ctx->st_pose); F(ctx->st_losses); F(ctx->st_loss_batch); F(ctx->st_dpose);
@@ -1005,14 +1048,6 @@ void xpt_destroy(xpt_ctx* ctx) {
     cudaStreamDestroy(ctx->s_in); cudaStreamDestroy(ctx->s_out); cudaStreamDestroy(ctx->s_in2); cudaEventDestroy(ctx->ev_small);
     cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
     for (int k = 0; k < kMaxChunks; ++k) { cudaEventDestroy(ctx->ev_in[k]); cudaEventDestroy(ctx->ev_done[k]); }
-  }
-  if (ctx->graphs) {
-    for (auto& e : *ctx->graphs) cudaGraphExecDestroy(e.exec);
-    delete ctx->graphs;
-  }
-  if (ctx->host_graphs) {
-    for (auto& e : *ctx->host_graphs) cudaGraphExecDestroy(e.exec);
-    delete ctx->host_graphs;
   }
   if (ctx->prof_events) {
     for (auto e : *ctx->prof_events) cudaEventDestroy(e);
@@ -1074,6 +1109,59 @@ int xpt_scale_tensors(int device, const float* const src[], float* const dst[], 
   return XPT_OK;
 }
 
+// Map every rank's loss inbox into this process (CUDA IPC over NVLink peer access).  The 64-byte handles travel through
+// one ncclAllGather on the new communicator; a second tiny all-reduce makes the ranks agree: either all of them use
+// the peer-memory exchange of k_epilogue, or all fall back to ncclAllReduce behind the epilogue (XPT_NO_P2P=1 forces it).
+static int p2p_setup(xpt_ctx* ctx, NcclApi* n) {
+  const int R = ctx->nranks, me = ctx->rank;
+  ctx->p2p = false;
+  if (R < 2) return XPT_OK;
+  if (R > kMaxRanks) return fail(XPT_BAD_ARGUMENT, "xpt_comm_init: more than %d ranks", kMaxRanks);
+  float ok = (n->AllGather && !getenv("XPT_NO_P2P")) ? 1.f : 0.f;
+  const size_t inbox_floats = (size_t)2 * R * kInboxSlot;
+  unsigned char* hbuf = nullptr;          // device: [R][64] handles + 1 float of agreement
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  XPT_CUDA(cudaMalloc(&ctx->inbox, inbox_floats * sizeof(float)));
+  XPT_CUDA(cudaMemset(ctx->inbox, 0, inbox_floats * sizeof(float)));
+  XPT_CUDA(cudaMalloc(&ctx->exch_seq, 2 * sizeof(unsigned)));
+  XPT_CUDA(cudaMemset(ctx->exch_seq, 0, 2 * sizeof(unsigned)));
+  ctx->exch_err = ctx->exch_seq + 1;
+  if (cudaIpcGetMemHandle(&mine, ctx->inbox) != cudaSuccess) { (void)cudaGetLastError(); ok = 0.f; }
+  XPT_CUDA(cudaMalloc(&hbuf, (size_t)R * 64 + 16));
+  std::vector<cudaIpcMemHandle_t> all(R);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  if (n->AllGather) {
+    XPT_CUDA(cudaMemcpy(hbuf + (size_t)me * 64, &mine, 64, cudaMemcpyHostToDevice));
+    int rc = n->AllGather(hbuf + (size_t)me * 64, hbuf, 64, /*ncclUint8*/ 1, ctx->nccl_comm, nullptr);
+    if (rc != 0) { cudaFree(hbuf); return nccl_fail(n, rc, "ncclAllGather"); }
+    XPT_CUDA(cudaStreamSynchronize(nullptr));
+    XPT_CUDA(cudaMemcpy(all.data(), hbuf, (size_t)R * 64, cudaMemcpyDeviceToHost));
+  }
+  ctx->peer_host = new float*[R]();
+  for (int r = 0; r < R && ok != 0.f; ++r) {
+    if (r == me) { ctx->peer_host[r] = ctx->inbox; continue; }
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { (void)cudaGetLastError(); ok = 0.f; break; }
+    ctx->peer_host[r] = static_cast<float*>(p);
+  }
+  // agreement: min over the ranks (sum of R ones == R)
+  float* agree = reinterpret_cast<float*>(hbuf + (size_t)R * 64);
+  XPT_CUDA(cudaMemcpy(agree, &ok, sizeof(float), cudaMemcpyHostToDevice));
+  int rc = n->AllReduce(agree, agree, 1, kNcclFloat32, kNcclSum, ctx->nccl_comm, nullptr);
+  if (rc != 0) { cudaFree(hbuf); return nccl_fail(n, rc, "ncclAllReduce"); }
+  XPT_CUDA(cudaStreamSynchronize(nullptr));
+  float sum = 0.f;
+  XPT_CUDA(cudaMemcpy(&sum, agree, sizeof(float), cudaMemcpyDeviceToHost));
+  cudaFree(hbuf);
+  if (sum == (float)R) {
+    XPT_CUDA(cudaMalloc(&ctx->peer_table, (size_t)R * sizeof(float*)));
+    XPT_CUDA(cudaMemcpy(ctx->peer_table, ctx->peer_host, (size_t)R * sizeof(float*), cudaMemcpyHostToDevice));
+    ctx->p2p = true;
+  }
+  return XPT_OK;
+}
+
 int xpt_comm_unique_id(unsigned char id[128]) {
   if (!id) return fail(XPT_BAD_ARGUMENT, "xpt_comm_unique_id: NULL id");
   NcclApi* n = nccl_api();
@@ -1087,21 +1175,47 @@ int xpt_comm_init(xpt_ctx* ctx, const unsigned char id[128], int nranks, int ran
   NcclApi* n = nccl_api();
   if (!n) return fail(XPT_NCCL_ERROR, "libnccl.so.2 not found (dlopen)");
   XPT_CUDA(cudaSetDevice(ctx->cfg.device));
-  if (ctx->nccl_comm && ctx->nccl_owned) n->CommDestroy(ctx->nccl_comm);
-  ctx->nccl_comm = nullptr;
+  comm_release(ctx);
   NcclId uid;
   memcpy(uid.b, id, 128);
   void* comm = nullptr;
   const int rc = n->CommInitRank(&comm, nranks, uid, rank);
   if (rc != 0) return nccl_fail(n, rc, "ncclCommInitRank");
   ctx->nccl_comm = comm; ctx->nccl_owned = true;
+  ctx->nranks = nranks; ctx->rank = rank;
+  return p2p_setup(ctx, n);
+}
+
+int xpt_comm_destroy(xpt_ctx* ctx) {
+  if (!ctx) return fail(XPT_BAD_ARGUMENT, "xpt_comm_destroy: NULL ctx");
+  XPT_CUDA(cudaSetDevice(ctx->cfg.device));
+  XPT_CUDA(cudaDeviceSynchronize());
+  // graphs that captured the collective reference the communicator
+  if (ctx->graphs) { for (auto& e : *ctx->graphs) cudaGraphExecDestroy(e.exec); ctx->graphs->clear(); }
+  if (ctx->host_graphs) { for (auto& e : *ctx->host_graphs) cudaGraphExecDestroy(e.exec); ctx->host_graphs->clear(); }
+  comm_release(ctx);
+  return XPT_OK;
+}
+
+int xpt_comm_status(xpt_ctx* ctx, int* uses_peer_memory, int* exchange_error) {
+  if (!ctx) return fail(XPT_BAD_ARGUMENT, "xpt_comm_status: NULL ctx");
+  if (uses_peer_memory) *uses_peer_memory = ctx->p2p ? 1 : 0;
+  if (exchange_error) {
+    *exchange_error = 0;
+    if (ctx->exch_err) {
+      XPT_CUDA(cudaSetDevice(ctx->cfg.device));
+      unsigned v = 0;
+      XPT_CUDA(cudaMemcpy(&v, ctx->exch_err, sizeof(v), cudaMemcpyDeviceToHost));
+      *exchange_error = (int)v;
+    }
+  }
   return XPT_OK;
 }
 
 int xpt_comm_attach(xpt_ctx* ctx, void* nccl_comm) {
   if (!ctx) return fail(XPT_BAD_ARGUMENT, "xpt_comm_attach: NULL ctx");
-  NcclApi* n = nccl_api();
-  if (ctx->nccl_comm && ctx->nccl_owned && n) n->CommDestroy(ctx->nccl_comm);
+  cudaSetDevice(ctx->cfg.device);
+  comm_release(ctx);                 // an attached communicator carries no rank table: the losses go through ncclAllReduce
   ctx->nccl_comm = nccl_comm; ctx->nccl_owned = false;
   return XPT_OK;
 }
@@ -1497,6 +1611,7 @@ static int total_loss_body(xpt_ctx* ctx, const xpt_frames* frames, const float* 
       ea.inv_global_batch = inv_gb; ea.w0 = c.w_l1; ea.w1 = c.w_ssim; ea.w2 = c.w_smooth;
       ea.losses = out->losses; ea.loss_batch = out->loss_batch;
       ea.loss_sum_b = ctx->loss_sum_b; ea.ticket = ctx->ticket;
+      set_exchange(ctx, ea);
       k_epilogue<<<(ea.d_pose ? ctx->B * ctx->N : 0) + ctx->B, 128, 0, st>>>(ea);
       XPT_LAUNCH_CHECK("k_epilogue");
       return XPT_OK;
@@ -1549,6 +1664,7 @@ static int total_loss_body(xpt_ctx* ctx, const xpt_frames* frames, const float* 
     ea.inv_global_batch = inv_gb; ea.w0 = c.w_l1; ea.w1 = c.w_ssim; ea.w2 = c.w_smooth;
     ea.losses = out->losses; ea.loss_batch = out->loss_batch;
     ea.loss_sum_b = ctx->loss_sum_b; ea.ticket = ctx->ticket;
+    set_exchange(ctx, ea);
     k_epilogue<<<(ea.d_pose ? ctx->B * ctx->N : 0) + ctx->B, 128, 0, st>>>(ea);
     XPT_LAUNCH_CHECK("k_epilogue");
     if (dsrc) XPT_TRY(finish_dsource4(ctx, out->d_source, st));
@@ -1610,8 +1726,10 @@ static int total_loss_body(xpt_ctx* ctx, const xpt_frames* frames, const float* 
 
 static int total_loss_impl(xpt_ctx* ctx, const xpt_frames* frames, const float* const depth_ms[],
                            const float* const disp_ms[], const float* pose, const xpt_loss_outputs* out, void* stream) {
+  if (ctx) ctx->exchanged = false;
   int rc = total_loss_body(ctx, frames, depth_ms, disp_ms, pose, out, stream);
-  if (rc == XPT_OK && ctx && (ctx->cfg.flags & XPT_FLAG_ALLREDUCE)) {
+  if (rc == XPT_OK && ctx && (ctx->cfg.flags & XPT_FLAG_ALLREDUCE) && !ctx->host_call && !ctx->exchanged) {
+    // (the fused path sums the losses inside k_epilogue through peer memory when the inboxes are mapped: no launch here)
     // reference distributer.py:93-110: the replicas' loss scalars are summed; here on the step's own stream, so the
     // collective is one more node of the step's CUDA graph
     float* bufs[1] = {out->losses};
@@ -1643,6 +1761,7 @@ int xpt_total_loss(xpt_ctx* ctx, const xpt_frames* frames, const float* const de
   K(frames->source); key.push_back((uint64_t)frames->source_batch_stride); key.push_back((uint64_t)frames->source_frame_stride);
   K(frames->target); key.push_back((uint64_t)frames->target_batch_stride); K(frames->intrinsic);
   K(pose); K(stream); K(out->losses); K(out->loss_batch); K(out->d_pose); K(out->d_source);
+  key.push_back(ctx->host_call ? 1u : 0u);
   uint32_t gsbits; memcpy(&gsbits, &out->grad_scale, 4); key.push_back(gsbits);
   for (int l = 0; l < ctx->S; ++l) {
     K(depth_ms[l]); K(disp_ms ? disp_ms[l] : nullptr); K(out->synth_ms[l]); K(out->mask_ms[l]);
@@ -1881,7 +2000,10 @@ static int host_enqueue(xpt_ctx* ctx, const xpt_frames* frames, const float* con
       if (out->mask_ms[l]) dout.mask_ms[l] = ctx->st_mask[l] + off * N;
       if (out->target_ms[l]) dout.target_ms[l] = ctx->st_target[l] + off * 3;
     }
-    XPT_TRY(xpt_total_loss(child, &df, cdepth, do_smooth ? cdisp : nullptr, ctx->st_pose + (size_t)b0 * N * 6, &dout, stream));
+    child->host_call = true;          // rank-local losses: a collective per chunk would be N x nc tiny all-reduces
+    const int crc = xpt_total_loss(child, &df, cdepth, do_smooth ? cdisp : nullptr, ctx->st_pose + (size_t)b0 * N * 6, &dout, stream);
+    child->host_call = false;
+    XPT_TRY(crc);
     if (nc > 1) {
       XPT_CUDA(cudaEventRecord(ctx->ev_done[k], st));
       XPT_CUDA(cudaStreamWaitEvent(s_out, ctx->ev_done[k], 0));

@@ -102,6 +102,8 @@ SYMBOLS = {
     "xpt_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "xpt_comm_attach": (C.c_int, [C.c_void_p, C.c_void_p]),
     "xpt_allreduce": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int, C.c_void_p]),
+    "xpt_comm_destroy": (C.c_int, [C.c_void_p]),
+    "xpt_comm_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
 }
 
 # XPTWARP_LIB: explicit path of another BUILD of the same library (profiling ablations); never a fallback

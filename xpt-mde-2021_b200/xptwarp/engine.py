@@ -164,6 +164,16 @@ class Plan:
         buf = (C.c_ubyte * 128).from_buffer_copy(raw)
         _cabi.check(self._lib.xpt_comm_init(self.handle, buf, world, rank))
 
+    def comm_destroy(self):
+        """Release the communicator and peer mappings (call before torch.distributed.destroy_process_group)."""
+        _cabi.check(self._lib.xpt_comm_destroy(self.handle))
+
+    def comm_status(self):
+        """(uses_peer_memory, exchange_error) of this plan's multi-rank loss exchange; synchronising."""
+        p2p, err = C.c_int(0), C.c_int(0)
+        _cabi.check(self._lib.xpt_comm_status(self.handle, C.byref(p2p), C.byref(err)))
+        return bool(p2p.value), bool(err.value)
+
     def allreduce(self, tensors):
         """in-place sum over the ranks of dense fp32 device tensors, one NCCL group on the current stream"""
         ts = [_dense(t, f"tensors[{i}]") for i, t in enumerate(tensors)]
