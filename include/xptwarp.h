@@ -109,6 +109,10 @@ typedef struct {
  * of the smoothness term is formed in the kernel as well (model_wrappers.py:47-48), so the boundary takes one
  * tensor per level from the net and returns one gradient per level.  Fused path only.                           */
 #define XPT_FLAG_DEPTH_LOGIT 32u
+/* xpt_photometric_min_loss runs on the round-1 tile kernel (k_photo_min: 32x16 tiles, one thread per statistics
+ * position) instead of the strip kernel (k_min_strip: 64x13 tiles, 2-pixel strips, running minimum in registers,
+ * in-tile reduction of the up-sampling adjoint).  Same results to summation order; kept for A/B parity tests.    */
+#define XPT_FLAG_MIN_TILES 64u
 
 /* The snippet frames + intrinsics (features of losses.py:26-37).              */
 typedef struct {
@@ -209,6 +213,20 @@ XPT_API int xpt_photometric_min_loss(xpt_ctx* ctx, int method,
                              const float* target, int64_t target_batch_stride, float* loss_batch,
                              const float* grad_loss_batch, float* const d_synth_ms[],
                              float* const d_stereo_synth_ms[], void* stream);
+
+/* The "L1" and the "SSIM" loss object of one min-over-sources loss set -- moaL1 + moaSSIM or md2L1 + md2SSIM of
+ * config-example.py:97-121, which the reference's loop (losses.py:43-47) evaluates one after the other over the same
+ * augm_data -- in ONE launch: the up-sampled syntheses, the black-pixel masks and the up-sampling adjoint are shared,
+ * the two minima are tracked independently.  loss_batch_l1 / loss_batch_ssim [B] as two calls of
+ * xpt_photometric_min_loss would return them.  If d_synth_ms != NULL it receives
+ * d(grad_l1 * sum_b loss_batch_l1[b] + grad_ssim * sum_b loss_batch_ssim[b]) / d synth_ms[s] (likewise
+ * d_stereo_synth_ms): grad_l1 / grad_ssim are the two losses' upstream weights, loss_weight / global_batch in
+ * TotalLoss (losses.py:48-49).  Needs every level at full or at most half resolution (XPT_BAD_SHAPE otherwise).   */
+XPT_API int xpt_photometric_min_pair_loss(xpt_ctx* ctx, const float* const synth_ms[],
+                                  const float* const stereo_synth_ms[], const float* target,
+                                  int64_t target_batch_stride, float* loss_batch_l1, float* loss_batch_ssim,
+                                  float grad_l1, float grad_ssim, float* const d_synth_ms[],
+                                  float* const d_stereo_synth_ms[], void* stream);
 
 /* losses.py:235-279 CombinedLossMultiScale(method).__call__: every scale's synthesis [B,N,h,w,3] and the
  * flow-warped view `warped` = warped_target_ms[0] [B,N,warped_height,warped_width,3] are bilinearly up-sampled to

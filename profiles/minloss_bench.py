@@ -11,7 +11,10 @@ src, tgt = feats["image5d"][:, :-1].cuda(), feats["image5d"][:, -1].cuda()
 synth = xptwarp.SynthesizeMultiScale()(src, feats["intrinsic"].cuda(), [d.cuda() for d in preds["depth_ms"]], preds["pose"].cuda())
 stereo = [s[:, :1].contiguous() for s in synth]
 warped0 = synth[2].clone()
-plan = xptwarp.get_plan(0, B, N, H, W, [1, 2, 4, 8], [1, 1, 1, 1])
+import sys as _s
+from xptwarp import _cabi
+plan = xptwarp.get_plan(0, B, N, H, W, [1, 2, 4, 8], [1, 1, 1, 1], flags=_cabi.XPT_FLAG_MIN_TILES if "tiles" in _s.argv else 0)
+print("kernel:", "k_photo_min (tiles)" if "tiles" in _s.argv else "k_min_strip")
 def timed(fn, n=20):
     for _ in range(3): fn()
     torch.cuda.synchronize()
@@ -26,3 +29,7 @@ for method, mname in ((0, "L1"), (2, "SSIM")):
         t_moa = timed(lambda: plan.photometric_min_loss(method, synth, stereo, tgt, want_grad=grad))
         t_cmb = timed(lambda: plan.photometric_cmb_loss(method, synth, warped0, tgt, want_grad=grad))
         print(f"{mname:4s} grad={int(grad)}  md2 {t_md2:7.1f} us   moa {t_moa:7.1f} us   cmb {t_cmb:7.1f} us")
+for grad in (False, True):
+    t_md2 = timed(lambda: plan.photometric_min_pair_loss(synth, None, tgt, 1.0, 1.0, want_grad=grad))
+    t_moa = timed(lambda: plan.photometric_min_pair_loss(synth, stereo, tgt, 1.0, 1.0, want_grad=grad))
+    print(f"PAIR grad={int(grad)}  md2 {t_md2:7.1f} us   moa {t_moa:7.1f} us   (L1 + SSIM in one launch)")

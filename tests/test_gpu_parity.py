@@ -830,6 +830,87 @@ def test_min_and_combined_losses_on_ragged_tiles(xw, B, H, W, N, method):
                 assert ok, (name, "stereo", s, msg)
 
 
+@pytest.mark.parametrize("B,H,W,N,scales", [(2, 40, 72, 3, (1, 2, 4, 8)), (1, 26, 130, 5, (1, 2)), (3, 128, 384, 4, (1, 2, 4, 8)),
+                                            (2, 13, 64, 1, (1,)), (1, 96, 200, 2, (2, 4)), (2, 48, 96, 4, (1, 3))])
+@pytest.mark.parametrize("method", [0, 1, 2], ids=["L1", "L2", "SSIM"])
+def test_min_strip_kernel_matches_tile_kernel(xw, B, H, W, N, scales, method):
+    """k_min_strip (64x13 strips, minimum in registers, in-tile reduction of the up-sampling adjoint: the default) against
+    k_photo_min (XPT_FLAG_MIN_TILES, the round-1 kernel the oracle tests pinned): same loss per snippet and the same
+    dL/dsynth -- only the summation order differs -- with black bands, exact ties between sources (a duplicated source:
+    the gradient is split equally) and an upstream gradient per snippet."""
+    from xptwarp import _cabi
+    g = torch.Generator().manual_seed(H * 977 + W * 31 + N + method)
+    U = lambda *shape: (torch.rand(*shape, generator=g) * 2 - 1).cuda()
+    target = U(B, H, W, 3)
+    synth, stereo = [], []
+    for s in scales:
+        t = U(B, N, H // s, W // s, 3)
+        t[:, :, : max(1, H // s // 5), :, :] = 0
+        t[:, 0, :, : max(1, W // s // 7), :] = 0
+        if N >= 3:
+            t[:, 2] = t[:, 1]                                         # exact ties between two sources
+        st = U(B, 1, H // s, W // s, 3)
+        st[:, :, -1, :, :] = 0
+        synth.append(t.contiguous()); stereo.append(st.contiguous())
+    gl = (torch.rand(B, generator=g) + 0.5).cuda()
+    sw = [0.4, 0.8, 1.2, 1.6][:len(scales)]
+    for use_stereo in (False, True):
+        out = {}
+        for name, flags in (("strip", 0), ("tiles", _cabi.XPT_FLAG_MIN_TILES)):
+            plan = xw.get_plan(0, B, N, H, W, list(scales), sw, flags=flags)
+            loss, d_synth, d_stereo, _ = plan.photometric_min_loss(method, synth, stereo if use_stereo else None, target,
+                                                                   grad_loss_batch=gl, want_grad=True)
+            loss_fwd = plan.photometric_min_loss(method, synth, stereo if use_stereo else None, target)[0]
+            torch.cuda.synchronize()
+            assert relerr(loss_fwd.cpu().numpy(), loss.cpu().numpy()) < 1e-6, name     # forward-only variant: the same sweep
+            out[name] = (loss.cpu().numpy(), [t.cpu().numpy() for t in d_synth],
+                         [t.cpu().numpy() for t in d_stereo] if use_stereo else [])
+        a, b = out["strip"], out["tiles"]
+        assert relerr(a[0], b[0]) < 2e-6, (use_stereo, a[0], b[0])
+        for s in range(len(scales)):
+            # an argmin that flips on the last bit of the SSIM quotient (division vs refined reciprocal) moves one
+            # pixel's gradient to another source: allow a handful of such pixels, compare the rest tightly
+            for x, y in [(a[1][s], b[1][s])] + ([(a[2][s], b[2][s])] if use_stereo else []):
+                scale = np.abs(y).max() + 1e-30
+                bad = np.abs(x - y) > 2e-5 * scale
+                assert bad.sum() <= max(3, 2e-4 * x.size), (use_stereo, s, int(bad.sum()), x.size)
+                assert np.abs((x - y)[~bad]).max() <= 2e-5 * scale
+
+
+@pytest.mark.parametrize("B,H,W,N,scales", [(2, 40, 72, 3, (1, 2, 4, 8)), (1, 26, 130, 5, (1, 2)), (2, 128, 384, 4, (1, 2, 4, 8)),
+                                            (1, 96, 200, 2, (2, 4))])
+def test_min_pair_launch_matches_two_launches(xw, B, H, W, N, scales):
+    """xpt_photometric_min_pair_loss (moaL1 + moaSSIM / md2L1 + md2SSIM of one eye in ONE launch): the two per-snippet
+    losses equal the single-method launches, the gradient is w_l1 dL1 + w_ssim dSSIM."""
+    g = torch.Generator().manual_seed(H * 31 + W + N)
+    U = lambda *shape: (torch.rand(*shape, generator=g) * 2 - 1).cuda()
+    target = U(B, H, W, 3)
+    synth, stereo = [], []
+    for s in scales:
+        t = U(B, N, H // s, W // s, 3)
+        t[:, :, : max(1, H // s // 5), :, :] = 0
+        if N >= 3:
+            t[:, 2] = t[:, 1]
+        synth.append(t.contiguous()); stereo.append(U(B, 1, H // s, W // s, 3))
+    sw = [0.4, 0.8, 1.2, 1.6][:len(scales)]
+    plan = xw.get_plan(0, B, N, H, W, list(scales), sw)
+    c1, c2 = 0.85 * 10 / 7, 0.15 / 7
+    for st in (None, stereo):
+        l1, d1, ds1, _ = plan.photometric_min_loss(0, synth, st, target, want_grad=True)
+        ls, d2, ds2, _ = plan.photometric_min_loss(2, synth, st, target, want_grad=True)
+        loss2, dp, dsp = plan.photometric_min_pair_loss(synth, st, target, c1, c2, want_grad=True)
+        loss2_fwd = plan.photometric_min_pair_loss(synth, st, target)[0]
+        torch.cuda.synchronize()
+        assert relerr(loss2[0].cpu().numpy(), l1.cpu().numpy()) < 1e-6 and relerr(loss2[1].cpu().numpy(), ls.cpu().numpy()) < 1e-6
+        assert relerr(loss2_fwd.cpu().numpy(), loss2.cpu().numpy()) < 1e-6
+        for s in range(len(scales)):
+            want = (c1 * d1[s] + c2 * d2[s]).cpu().numpy()
+            assert relerr(dp[s].cpu().numpy(), want) < 2e-5, (s, relerr(dp[s].cpu().numpy(), want))
+            if st is not None:
+                want = (c1 * ds1[s] + c2 * ds2[s]).cpu().numpy()
+                assert relerr(dsp[s].cpu().numpy(), want) < 2e-5, ("stereo", s)
+
+
 @pytest.mark.parametrize("derive", [False, True], ids=["disp_given", "disp_from_depth"])
 def test_host_entry_point_all_outputs(xw, derive):
     """xpt_total_loss_host with EVERY optional output (synth_ms, mask_ms, target_ms, loss_batch, d_source) and with

@@ -22,6 +22,11 @@
 #ifndef XPT_EXP
 #define XPT_EXP 0
 #endif
+// XPT_YPIPE bit 0: phase Y keeps both samples of a thread in flight (eight texel loads issued together);
+//           bit 1: the tile prologue issues the loads of its three iterations together
+#ifndef XPT_YPIPE
+#define XPT_YPIPE 2
+#endif
 #if XPT_EXP & 1
 #define XPT_SYNC() ((void)0)
 #else
@@ -251,6 +256,39 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
   {
     const float* tgt = L.tgt + b * L.tgt_bs;
     const float* dep = a.depth[l] + (long long)b * P;
+#if XPT_YPIPE & 2
+    // all loads of the three iterations are issued before the first store (clamped addresses, zero by select): one
+    // exposed memory latency at the start of a tile instead of three
+    float tv[kFYIters][3], td[kFYIters];
+    bool tin[kFYIters];
+#pragma unroll
+    for (int it = 0; it < kFYIters; ++it) {
+      const int i = min(tid + it * kFThreads, kFRegion - 1);
+      const int ry = i / kFP, rx = i - ry * kFP;
+      const int gy = ty0 - 2 + ry, gx = tx0 - 2 + rx;
+      tin[it] = gy >= 0 && gy < H && gx >= 0 && gx < W;
+      const long long o = (long long)min(max(gy, 0), H - 1) * W + min(max(gx, 0), W - 1);
+      const float* p = tgt + o * 3;
+      tv[it][0] = __ldg(p); tv[it][1] = __ldg(p + 1); tv[it][2] = __ldg(p + 2);
+      td[it] = __ldg(dep + o);
+    }
+#pragma unroll
+    for (int it = 0; it < kFYIters; ++it) {
+      const int i = tid + it * kFThreads;
+      if (i < kFRegion) {
+        const int ry = i / kFP, rx = i - ry * kFP;
+        const int gy = ty0 - 2 + ry, gx = tx0 - 2 + rx;
+        float d = td[it];
+        if (DERIVE == 2) d = depth_of_logit(d);
+        const float fx = (float)gx, fy = (float)gy;
+        const float r0 = gk[9] * fx + gk[10] * fy + gk[11];
+        const float r1 = gk[12] * fx + gk[13] * fy + gk[14];
+        const bool in = tin[it];
+        sx[i] = in ? tv[it][0] : 0.f; sx[kFRegion + i] = in ? tv[it][1] : 0.f; sx[2 * kFRegion + i] = in ? tv[it][2] : 0.f;
+        sD[i] = in ? d : 0.f; sR0[i] = in ? r0 : 0.f; sR1[i] = in ? r1 : 0.f;
+      }
+    }
+#else
 #pragma unroll
     for (int it = 0; it < kFYIters; ++it) {
       const int i = tid + it * kFThreads;
@@ -273,6 +311,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
         sD[i] = d; sR0[i] = r0; sR1[i] = r1;
       }
     }
+#endif
   }
   __syncthreads();
 
@@ -430,6 +469,70 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
     // ---- phase Y: inverse warp of the region into shared memory ---------------------------------
     // GRAD: two balanced iterations, the tail comes from warps 13..15 (above / adjoint phase); forward only: no idle
     // phase to hide the tail in, so a third, partly filled iteration takes it
+#if XPT_YPIPE & 1
+    if (GRAD && !(XPT_EXP & 2)) {
+      // both samples of a thread in flight together: the two projection chains run first, the eight texel loads are
+      // issued back to back (unconditional: a sample without a valid warp reads texel (0,0) and is zeroed by select),
+      // then both are consumed -- one exposed gather latency per source instead of two
+      constexpr int kS = kFYMain / kFThreads;
+      float pu[kS], pv[kS], inv_den[kS];
+      Taps tp[kS];
+      float4 tx[kS][4];
+#pragma unroll
+      for (int it = 0; it < kS; ++it) {
+        const int i = tid + it * kFThreads;
+        const float D = sD[i];
+        const float X0 = sR0[i] * D, X1 = sR1[i] * D, X2 = D;
+        const float Y0 = gt[0] * X0 + gt[1] * X1 + gt[2] * X2 + gt[9];
+        const float Y1 = gt[3] * X0 + gt[4] * X1 + gt[5] * X2 + gt[10];
+        const float Y2 = gt[6] * X0 + gt[7] * X1 + gt[8] * X2 + gt[11];
+        const float p0 = gk[0] * Y0 + gk[1] * Y1 + gk[2] * Y2;
+        const float p1 = gk[3] * Y0 + gk[4] * Y1 + gk[5] * Y2;
+        const float den = Y2 + 1e-10f;
+        div_pair(p0, p1, den, pu[it], pv[it], inv_den[it]);
+        tp[it] = make_taps(pu[it], pv[it], D, W, H);
+        const float4* tp0 = img4 + (tp[it].iv * W + tp[it].iu);      // (0,0) when not valid
+        tx[it][0] = __ldg(tp0); tx[it][2] = __ldg(tp0 + 1); tx[it][1] = __ldg(tp0 + W); tx[it][3] = __ldg(tp0 + W + 1);
+      }
+#pragma unroll
+      for (int it = 0; it < kS; ++it) {
+        const int i = tid + it * kFThreads;
+        const int ry = i / kFP, rx = i - ry * kFP;
+        const bool centre = (unsigned)(ry - 2) < (unsigned)kFCH && (unsigned)(rx - 2) < (unsigned)kFCW;
+        const Taps& q = tp[it];
+        const float4 t0 = tx[it][0], t1 = tx[it][1], t2 = tx[it][2], t3 = tx[it][3];
+        const float I0[3] = {t0.x, t0.y, t0.z}, I1[3] = {t1.x, t1.y, t1.z}, I2[3] = {t2.x, t2.y, t2.z}, I3[3] = {t3.x, t3.y, t3.z};
+        const float w0 = q.w_uf * q.w_vf, w1 = q.w_uf * q.w_vc, w2 = q.w_uc * q.w_vf, w3 = q.w_uc * q.w_vc;
+        float yv[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float y = ((I0[c] * w0 + I1[c] * w1) + I2[c] * w2) + I3[c] * w3;
+          yv[c] = q.valid ? y : 0.f;
+        }
+        sy[i] = yv[0]; sy[kFRegion + i] = yv[1]; sy[2 * kFRegion + i] = yv[2];
+        if (centre) {
+          const int ci = i - (2 * kFP + 2) - (ry - 2) * (kFP - kFCP);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float gu = q.w_vf * (I2[c] - I0[c]) + q.w_vc * (I3[c] - I1[c]);
+            const float gv = q.w_uf * (I1[c] - I0[c]) + q.w_uc * (I3[c] - I2[c]);
+            sGU[c * kFCentre + ci] = q.valid ? gu : 0.f;
+            sGV[c * kFCentre + ci] = q.valid ? gv : 0.f;
+          }
+          sU[ci] = q.valid ? pu[it] : 0.f; sV[ci] = q.valid ? pv[it] : 0.f; sI[ci] = q.valid ? inv_den[it] : 0.f;
+          if (OUT) {
+            const int gy = ty0 - 2 + ry, gx = tx0 - 2 + rx;
+            if (gy < H && gx < W) {
+              const long long o = (long long)(b * a.N + n) * P + gy * W + gx;
+              if (a.synth_out[l]) { float* so = a.synth_out[l] + o * 3; so[0] = yv[0]; so[1] = yv[1]; so[2] = yv[2]; }
+              if (a.mask_out[l]) a.mask_out[l][o] = q.valid ? 1.f : 0.f;
+            }
+          }
+        }
+      }
+    } else
+#endif
+    {
 #pragma unroll
     for (int it = 0; it < (GRAD ? kFYMain / kFThreads : kFYIters); ++it) {
       const int i = tid + it * kFThreads;
@@ -485,6 +588,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
           }
         }
       }
+    }
     }
     XPT_SYNC();
 

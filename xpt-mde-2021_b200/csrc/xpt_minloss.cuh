@@ -37,6 +37,9 @@ struct MinLossArgs {
   // where it is smaller than the term of the flow-warped view `cmb_flow` [B,N,cmb_h,cmb_w,3] (level 0 of
   // warped_target_ms), both up-sampled to H x W; norm[] then carries 1/(N*H*W*3).  NULL = min-over-sources mode.
   const float* cmb_flow; int cmb_h, cmb_w;
+  // k_min_strip<.., PAIR>: L1 and SSIM of one loss set in one launch -- loss_part holds L1, loss_part2 SSIM, the
+  // gradient is pair_c_l1 dL1 + pair_c_ssim dSSIM (the upstream weights of the two losses, uniform over the batch)
+  float* loss_part2; float pair_c_l1, pair_c_ssim;
 };
 
 template <bool GRAD>

@@ -21,6 +21,7 @@
 #include "xpt_strip.cuh"
 #include "xpt_flow.cuh"
 #include "xpt_minloss.cuh"
+#include "xpt_minstrip.cuh"
 
 using namespace xpt;
 
@@ -1334,7 +1335,9 @@ static int min_loss_impl(xpt_ctx* ctx, int method, const float* const synth_ms[]
                          const float* cmb_flow, int cmb_h, int cmb_w,
                          const float* target, int64_t target_batch_stride, float* loss_batch,
                          const float* grad_loss_batch, float* const d_synth_ms[], float* const d_stereo_synth_ms[],
-                         void* stream) {
+                         void* stream, float* loss_batch_pair_ssim = nullptr, float pair_c_l1 = 0.f, float pair_c_ssim = 0.f) {
+  // loss_batch_pair_ssim != NULL: the L1 + SSIM pair in one launch (loss_batch receives L1); method is ignored
+  const bool pair = loss_batch_pair_ssim != nullptr;
   if (!ctx || !loss_batch || !target) return fail(XPT_BAD_ARGUMENT, "xpt_photometric_min_loss: NULL argument");
   if (method != XPT_PHOTO_L1 && method != XPT_PHOTO_L2 && method != XPT_PHOTO_SSIM)
     return fail(XPT_BAD_ARGUMENT, "unknown photometric method %d", method);
@@ -1353,10 +1356,19 @@ static int min_loss_impl(xpt_ctx* ctx, int method, const float* const synth_ms[]
   a.method = method == XPT_PHOTO_L1 ? 0 : (method == XPT_PHOTO_L2 ? 1 : 2);
   a.gbatch = grad_loss_batch;
   a.cmb_flow = cmb_flow; a.cmb_h = cmb_h; a.cmb_w = cmb_w;
-  a.tiles_x = cdiv(ctx->W, kTW);
-  a.tiles = a.tiles_x * cdiv(ctx->H, kTH);
-  XPT_TRY(dev_alloc(ctx, &ctx->min_part, (size_t)ctx->B * ctx->S * a.tiles));
+  // min-over-sources mode runs on the strip kernel (64x13 tiles); the combined loss, XPT_FLAG_MIN_TILES (A/B) and
+  // levels between full and half resolution (footprint wider than the strip kernel's buffer) keep the 32x16 tile kernel
+  bool strip = !cmb_flow && !(ctx->cfg.flags & XPT_FLAG_MIN_TILES);
+  for (int l = 0; l < ctx->S; ++l)
+    if (!((ctx->h[l] == ctx->H && ctx->w[l] == ctx->W) || (2 * ctx->w[l] <= ctx->W && 2 * ctx->h[l] <= ctx->H))) strip = false;
+  a.tiles_x = strip ? cdiv(ctx->W, kFCW) : cdiv(ctx->W, kTW);
+  a.tiles = a.tiles_x * (strip ? cdiv(ctx->H, kFCH) : cdiv(ctx->H, kTH));
+  if (pair && !strip) return fail(XPT_BAD_SHAPE, "xpt_photometric_min_pair_loss: every level must be at full or at most half resolution");
+  const size_t n_part = (size_t)ctx->B * ctx->S * a.tiles;
+  XPT_TRY(dev_alloc(ctx, &ctx->min_part, 2 * n_part));
   a.loss_part = ctx->min_part;
+  a.loss_part2 = ctx->min_part + n_part;
+  a.pair_c_l1 = pair_c_l1; a.pair_c_ssim = pair_c_ssim;
   for (int l = 0; l < ctx->S; ++l) {
     a.h[l] = ctx->h[l]; a.w[l] = ctx->w[l];
     a.synth[l] = synth_ms[l]; a.stereo[l] = stereo_synth_ms ? stereo_synth_ms[l] : nullptr;
@@ -1372,7 +1384,35 @@ static int min_loss_impl(xpt_ctx* ctx, int method, const float* const synth_ms[]
     }
   }
   dim3 grid(ctx->S * a.tiles, ctx->B);
-  if (d_synth_ms) {
+  if (strip && pair) {
+    const dim3 sgrid(ctx->B, ctx->S * a.tiles);
+    if (d_synth_ms) {
+      static unsigned long long attr_done = 0;
+      const size_t smem = MinStripSmem<true, true>::kBytes;
+      XPT_TRY(ensure_dyn_smem(k_min_strip<true, true>, smem, ctx->cfg.device, &attr_done));
+      k_min_strip<true, true><<<sgrid, kFThreads, smem, st>>>(a);
+    } else {
+      static unsigned long long attr_done = 0;
+      const size_t smem = MinStripSmem<false, true>::kBytes;
+      XPT_TRY(ensure_dyn_smem(k_min_strip<false, true>, smem, ctx->cfg.device, &attr_done));
+      k_min_strip<false, true><<<sgrid, kFThreads, smem, st>>>(a);
+    }
+    XPT_LAUNCH_CHECK("k_min_strip<pair>");
+  } else if (strip) {
+    const dim3 sgrid(ctx->B, ctx->S * a.tiles);
+    if (d_synth_ms) {
+      static unsigned long long attr_done = 0;
+      const size_t smem = MinStripSmem<true, false>::kBytes;
+      XPT_TRY(ensure_dyn_smem(k_min_strip<true, false>, smem, ctx->cfg.device, &attr_done));
+      k_min_strip<true, false><<<sgrid, kFThreads, smem, st>>>(a);
+    } else {
+      static unsigned long long attr_done = 0;
+      const size_t smem = MinStripSmem<false, false>::kBytes;
+      XPT_TRY(ensure_dyn_smem(k_min_strip<false, false>, smem, ctx->cfg.device, &attr_done));
+      k_min_strip<false, false><<<sgrid, kFThreads, smem, st>>>(a);
+    }
+    XPT_LAUNCH_CHECK("k_min_strip");
+  } else if (d_synth_ms) {
     static unsigned long long attr_done = 0;
     const size_t smem = MinLossSmem<true>::kBytes;
     XPT_TRY(ensure_dyn_smem(k_photo_min<true>, smem, ctx->cfg.device, &attr_done));
@@ -1383,10 +1423,23 @@ static int min_loss_impl(xpt_ctx* ctx, int method, const float* const synth_ms[]
     XPT_TRY(ensure_dyn_smem(k_photo_min<false>, smem, ctx->cfg.device, &attr_done));
     k_photo_min<false><<<grid, kPhotoThreads, smem, st>>>(a);
   }
-  XPT_LAUNCH_CHECK("k_photo_min");
+  if (!strip) XPT_LAUNCH_CHECK("k_photo_min");
   k_sum_slots<<<ctx->B, 128, 0, st>>>(ctx->min_part, ctx->S * a.tiles, loss_batch);
   XPT_LAUNCH_CHECK("k_sum_slots");
+  if (pair) {
+    k_sum_slots<<<ctx->B, 128, 0, st>>>(ctx->min_part + n_part, ctx->S * a.tiles, loss_batch_pair_ssim);
+    XPT_LAUNCH_CHECK("k_sum_slots");
+  }
   return XPT_OK;
+}
+
+int xpt_photometric_min_pair_loss(xpt_ctx* ctx, const float* const synth_ms[], const float* const stereo_synth_ms[],
+                                  const float* target, int64_t target_batch_stride, float* loss_batch_l1,
+                                  float* loss_batch_ssim, float grad_l1, float grad_ssim, float* const d_synth_ms[],
+                                  float* const d_stereo_synth_ms[], void* stream) {
+  if (!loss_batch_ssim) return fail(XPT_BAD_ARGUMENT, "xpt_photometric_min_pair_loss: NULL argument");
+  return min_loss_impl(ctx, XPT_PHOTO_L1, synth_ms, stereo_synth_ms, nullptr, 0, 0, target, target_batch_stride, loss_batch_l1,
+                       nullptr, d_synth_ms, d_stereo_synth_ms, stream, loss_batch_ssim, grad_l1, grad_ssim);
 }
 
 int xpt_photometric_min_loss(xpt_ctx* ctx, int method, const float* const synth_ms[], const float* const stereo_synth_ms[],

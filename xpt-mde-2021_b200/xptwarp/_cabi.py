@@ -13,6 +13,7 @@ XPT_FLAG_NO_PIPELINE = 4
 XPT_FLAG_STRIP = 8
 XPT_FLAG_ALLREDUCE = 16
 XPT_FLAG_DEPTH_LOGIT = 32
+XPT_FLAG_MIN_TILES = 64
 XPT_OK, XPT_BAD_ARGUMENT, XPT_BAD_SHAPE, XPT_CUDA_ERROR, XPT_NO_DEVICE, XPT_OUT_OF_MEMORY = 0, -1, -2, -3, -4, -5
 XPT_BAD_DTYPE, XPT_BAD_DEVICE, XPT_NOT_CONTIGUOUS, XPT_NCCL_ERROR = -6, -7, -8, -9
 XPT_PHOTO_L1, XPT_PHOTO_L2, XPT_PHOTO_SSIM = 0, 1, 2
@@ -75,6 +76,9 @@ SYMBOLS = {
     "xpt_photometric_min_loss": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(PtrArray), C.POINTER(PtrArray), C.c_void_p,
                                            C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(PtrArray), C.POINTER(PtrArray),
                                            C.c_void_p]),
+    "xpt_photometric_min_pair_loss": (C.c_int, [C.c_void_p, C.POINTER(PtrArray), C.POINTER(PtrArray), C.c_void_p, C.c_int64,
+                                                C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.POINTER(PtrArray),
+                                                C.POINTER(PtrArray), C.c_void_p]),
     "xpt_photometric_cmb_loss": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(PtrArray), C.c_void_p, C.c_int, C.c_int,
                                            C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(PtrArray),
                                            C.c_void_p]),

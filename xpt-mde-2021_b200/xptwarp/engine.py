@@ -291,6 +291,25 @@ class Plan:
             C.byref(ptr_array([t.data_ptr() for t in d_stereo])) if d_stereo is not None else None, self.stream()))
         return loss, d_synth, d_stereo, (target, synth_ms, stereo_synth_ms)
 
+    def photometric_min_pair_loss(self, synth_ms, stereo_synth_ms, target, grad_l1=1.0, grad_ssim=1.0, want_grad=False):
+        """xpt_photometric_min_pair_loss: the L1 and the SSIM min-over-sources loss of one loss set in ONE launch;
+        the gradient is grad_l1 * dL1 + grad_ssim * dSSIM (the two losses' upstream weights)."""
+        synth_ms = self._level_list(synth_ms, "synth_target_ms", self.N * 3)
+        have_st = stereo_synth_ms is not None
+        if have_st:
+            stereo_synth_ms = self._level_list(stereo_synth_ms, "stereo_synth_ms", 3)
+        target = _frame_view(target, "target", 1)
+        loss = torch.empty((2, self.B), dtype=torch.float32, device=self.device)
+        d_synth = self._empty_levels((self.N,), 3) if want_grad else None
+        d_stereo = self._empty_levels((1,), 3) if (want_grad and have_st) else None
+        _cabi.check(self._lib.xpt_photometric_min_pair_loss(
+            self.handle, C.byref(ptr_array([t.data_ptr() for t in synth_ms])),
+            C.byref(ptr_array([t.data_ptr() for t in stereo_synth_ms])) if have_st else None,
+            target.data_ptr(), target.stride(0), loss[0].data_ptr(), loss[1].data_ptr(), float(grad_l1), float(grad_ssim),
+            C.byref(ptr_array([t.data_ptr() for t in d_synth])) if want_grad else None,
+            C.byref(ptr_array([t.data_ptr() for t in d_stereo])) if d_stereo is not None else None, self.stream()))
+        return loss, d_synth, d_stereo
+
     def photometric_cmb_loss(self, method, synth_ms, warped, target, grad_loss_batch=None, want_grad=False):
         """xpt_photometric_cmb_loss: static term where it beats the optical-flow term (CombinedLossMultiScale)."""
         synth_ms = self._level_list(synth_ms, "synth_target_ms", self.N * 3)

@@ -134,6 +134,33 @@ class _PhotoMinFn(torch.autograd.Function):
         return (None, None, None, None, None, *_scale_by_snippet(g, ctx.saved_tensors))
 
 
+class _PhotoMinPairFn(torch.autograd.Function):
+    """The "L1" and the "SSIM" min-over-sources loss of one loss set (moaL1 + moaSSIM, md2L1 + md2SSIM) in ONE launch
+    (xpt_photometric_min_pair_loss).  Returns their weighted contribution to the total loss and the two unweighted means;
+    the gradient of the contribution is formed by the same launch (the weights are known here, as in _TotalLossFn) and the
+    backward applies the upstream scalar to all stored gradients in one launch of the library."""
+
+    @staticmethod
+    def forward(ctx, plan, S, have_stereo, w_l1, w_ssim, batch_size, target, *ts):
+        synth_ms = ts[:S]
+        stereo_ms = ts[S:] if have_stereo else None
+        want = any(ctx.needs_input_grad[7:])
+        loss2, d_synth, d_stereo = plan.photometric_min_pair_loss(synth_ms, stereo_ms, target, w_l1 / batch_size,
+                                                                  w_ssim / batch_size, want_grad=want)
+        ctx.want = want
+        if want:
+            ctx.save_for_backward(*d_synth, *(d_stereo if have_stereo else ()))
+        means = loss2.sum(dim=1) / batch_size                       # tf.nn.compute_average_loss, per loss
+        ctx.mark_non_differentiable(means)
+        return means[0] * w_l1 + means[1] * w_ssim, means
+
+    @staticmethod
+    def backward(ctx, g, _g_means):
+        if not ctx.want:
+            raise RuntimeError("the loss pair was evaluated without gradients")
+        return (None, None, None, None, None, None, None, *scale_tensors(list(ctx.saved_tensors), g))
+
+
 class _PhotoCmbFn(torch.autograd.Function):
     """CombinedLossMultiScale: static term where it beats the flow term (xpt_photometric_cmb_loss).  The flow-warped
     view only enters through a comparison, so it receives no gradient (as in the reference's graph).  Forward and
@@ -220,27 +247,29 @@ class MonoDepth2LossMultiScale(PhotometricLoss):
     """reference losses.py:198-232: every scale's synthesis is up-sampled to the original size, the per-pixel
     photometric term is taken against the full-resolution target and the minimum over the sources is averaged."""
 
-    def _call(self, augm_data, stereo_key):
+    STEREO_KEY = None
+
+    def _inputs(self, augm_data):
         synth_ms = [as_torch(t) for t in augm_data["synth_target_ms" + self.key_suffix]]
-        stereo_ms = [as_torch(t) for t in augm_data[stereo_key]] if stereo_key else None
+        stereo_ms = [as_torch(t) for t in augm_data[self.STEREO_KEY]] if self.STEREO_KEY else None
         target = as_torch(augm_data["target" + self.key_suffix])
         require_cuda_f32(synth_target_ms=synth_ms, target=target)
         B, N, H, W = synth_ms[0].shape[0], synth_ms[0].shape[1], target.shape[1], target.shape[2]
         scales = [H // s.shape[2] for s in synth_ms]
         plan = get_plan(target.device.index or 0, B, N, H, W, scales, _scale_weights_list(self.scale_weights))
-        return _PhotoMinFn.apply(plan, self._METHODS[self.method], plan.S, stereo_ms is not None, target,
-                                 *synth_ms, *(stereo_ms or ()))
+        return plan, target, synth_ms, stereo_ms
 
     def __call__(self, features, predictions, augm_data):
-        return self._call(augm_data, None)
+        plan, target, synth_ms, stereo_ms = self._inputs(augm_data)
+        return _PhotoMinFn.apply(plan, self._METHODS[self.method], plan.S, stereo_ms is not None, target,
+                                 *synth_ms, *(stereo_ms or ()))
 
 
 class MoALossMultiScale(MonoDepth2LossMultiScale):
     """reference losses.py:282-321: minimum over the temporal syntheses AND the stereo synthesis.  As in the
     reference the stereo entry is always augm_data["stereo_synth_ms"] (the left one), also for key_suffix "_R"."""
 
-    def __call__(self, features, predictions, augm_data):
-        return self._call(augm_data, "stereo_synth_ms")
+    STEREO_KEY = "stereo_synth_ms"
 
 
 class CombinedLossMultiScale(PhotometricLoss):
@@ -363,6 +392,20 @@ class TotalLoss:
             return type(obj) is StereoPoseLoss
         return False
 
+    def _min_pairs(self):
+        """{L1 name: SSIM name, SSIM name: None} for every stock (moa|md2)L1 + (moa|md2)SSIM pair of one eye with the
+        same scale weights: the pair shares one launch (xpt_photometric_min_pair_loss)"""
+        pairs = {}
+        for sfx in ("", "_R"):
+            for base, cls in (("moa", MoALossMultiScale), ("md2", MonoDepth2LossMultiScale)):
+                n1, n2 = base + "L1" + sfx, base + "SSIM" + sfx
+                o1, o2 = self.loss_objects.get(n1), self.loss_objects.get(n2)
+                if (type(o1) is cls and type(o2) is cls and o1.method == "L1" and o2.method == "SSIM"
+                        and o1.key_suffix == sfx and o2.key_suffix == sfx
+                        and _scale_weights_list(o1.scale_weights) == _scale_weights_list(o2.scale_weights)):
+                    pairs[n1], pairs[n2] = n2, None
+        return pairs
+
     def _fused_ok(self, predictions, features):
         if not self.loss_objects or any(k not in _FUSED_SET for k in self.loss_objects):
             return False
@@ -394,7 +437,20 @@ class TotalLoss:
             augm_data.update(self.append_data(features, predictions, "_R"))
             augm_data.update(self.synethesize_stereo(features, predictions, augm_data))
         losses, loss_by_type = [], dict()
+        pairs = self._min_pairs()
         for loss_name in self.loss_objects:
+            if loss_name in pairs:
+                if pairs[loss_name] is None:                          # the SSIM half: evaluated with its L1 partner
+                    continue
+                # moaL1 + moaSSIM (md2L1 + md2SSIM) of one eye: ONE launch for both loss objects
+                ssim_name, obj = pairs[loss_name], self.loss_objects[loss_name]
+                plan, target, synth_ms, stereo_ms = obj._inputs(augm_data)
+                part, means = _PhotoMinPairFn.apply(plan, plan.S, stereo_ms is not None, float(self.loss_weights[loss_name]),
+                                                    float(self.loss_weights[ssim_name]), float(self.batch_size), target,
+                                                    *synth_ms, *(stereo_ms or ()))
+                losses.append(part)
+                loss_by_type[loss_name], loss_by_type[ssim_name] = means[0], means[1]
+                continue
             loss_batch = self.loss_objects[loss_name](features, predictions, augm_data)
             loss_mean = loss_batch.sum() / self.batch_size          # tf.nn.compute_average_loss
             losses.append(loss_mean * self.loss_weights[loss_name])
