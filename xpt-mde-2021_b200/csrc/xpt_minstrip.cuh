@@ -10,7 +10,8 @@
 //     first) on 8-byte shared-memory rows and run on the packed FP32 pipe (FFMA2 / FADD2 / FMUL2);
 //   * the running minimum, the tie count and the first winner of every (pixel, channel) of a strip live in REGISTERS
 //     across both sweeps (k_photo_min kept them in shared memory and re-read them per source);
-//   * the target's window statistics are formed once per tile and kept in registers;
+//   * the target's window statistics are re-formed per source from the rows the cross term loads anyway (18 registers
+//     of statistics kept across the source loop pushed the running minima into local memory: -25 % time without);
 //   * up-sampling taps (lo, hi, lerp per tile row / column) are tabulated once per tile;
 //   * the adjoint of the up-sampling is reduced inside the tile first: dL/dS of the centre goes to shared memory, a
 //     horizontal and a vertical pass fold it onto the tile's low-resolution footprint, and ONE atomic per low-resolution
@@ -142,32 +143,14 @@ __global__ void __launch_bounds__(kFThreads, 2) k_min_strip(const __grid_constan
     inv_cnt = f2(iv[0], iv[1]); s_centre = f2(ce[0], ce[1]);
     asm volatile("" : "+f"(inv_cnt.x), "+f"(inv_cnt.y), "+f"(s_centre.x), "+f"(s_centre.y));
   }
-  float2 MUX[3], MUX2C[3], SGXC[3];
-  if (ssim && s_active) {
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float* px = sx + c * kFRegion + qy * kFP + q0;
-      const float2 a0 = lds2(px), b0 = lds2(px + 2), a1 = lds2(px + kFP), b1 = lds2(px + kFP + 2);
-      const float2 a2 = lds2(px + 2 * kFP), b2 = lds2(px + 2 * kFP + 2);
-      const float2 v1a = f2add(f2add(a0, a1), a2), v1b = f2add(f2add(b0, b1), b2);
-      const float2 v2a = f2fma(a2, a2, f2fma(a1, a1, f2mul(a0, a0))), v2b = f2fma(b2, b2, f2fma(b1, b1, f2mul(b0, b0)));
-      const float2 s1 = hsum3(v1a, v1b);
-      const float2 s2 = hsum3(v2a, v2b);
-      const float2 mu = f2mul(s1, inv_cnt);
-      const float2 mu2 = f2mul(mu, mu);
-      MUX[c] = mu;
-      MUX2C[c] = f2add(mu2, f2s(kC1));
-      SGXC[c] = f2add(f2fma(s2, inv_cnt, f2neg(mu2)), f2s(kC2));
-    }
-  }
-
-  // running minimum per (channel, pixel of the strip); code = (first winner << 8) | number of sources at the minimum
+  // running minimum per (channel, pixel of the strip); code = both pixels' (first winner << 8 | number of sources at
+  // the minimum), 16 bits each
   float vmin[NM][3][2];
-  int code[NM][3][2];
+  unsigned code[NM][3];
 #pragma unroll
   for (int k = 0; k < NM; ++k)
 #pragma unroll
-    for (int c = 0; c < 3; ++c) { vmin[k][c][0] = vmin[k][c][1] = 3.0e38f; code[k][c][0] = code[k][c][1] = 0; }
+    for (int c = 0; c < 3; ++c) { vmin[k][c][0] = vmin[k][c][1] = 3.0e38f; code[k][c] = 0u; }
 
   // ---- up-sampled region of source m into sy (zero outside the image) ---------------------------------------
   auto upsample = [&](int m) {
@@ -222,16 +205,29 @@ __global__ void __launch_bounds__(kFThreads, 2) k_min_strip(const __grid_constan
     }
     // one method's value at the strip's two pixels: running minimum (sweep 1) or the share of the upstream gradient
     // this source receives (sweep 2; tf.reduce_min splits it equally among the sources attaining the minimum)
-    auto update = [&](int k, int c, float v0, float v1) {
-      if (v0 < vmin[k][c][0]) { vmin[k][c][0] = v0; code[k][c][0] = (m << 8) | 1; } else if (v0 == vmin[k][c][0]) ++code[k][c][0];
-      if (v1 < vmin[k][c][1]) { vmin[k][c][1] = v1; code[k][c][1] = (m << 8) | 1; } else if (v1 == vmin[k][c][1]) ++code[k][c][1];
+    auto update = [&](int k, int c, float v0, float v1) {         // (branch-free)
+      const unsigned fresh = ((unsigned)m << 8) | 1u;
+      const bool lt0 = v0 < vmin[k][c][0], eq0 = v0 == vmin[k][c][0];
+      const bool lt1 = v1 < vmin[k][c][1], eq1 = v1 == vmin[k][c][1];
+      unsigned c0_ = code[k][c] & 0xffffu, c1_ = code[k][c] >> 16;
+      c0_ = lt0 ? fresh : c0_ + (eq0 ? 1u : 0u);
+      c1_ = lt1 ? fresh : c1_ + (eq1 ? 1u : 0u);
+      vmin[k][c][0] = lt0 ? v0 : vmin[k][c][0];
+      vmin[k][c][1] = lt1 ? v1 : vmin[k][c][1];
+      code[k][c] = c0_ | (c1_ << 16);
     };
     auto share = [&](int k, int c, float v0, float v1, bool ok0, bool ok1, float coef, float& g0, float& g1) {
-      const int n0 = code[k][c][0] & 0xff, n1 = code[k][c][1] & 0xff;
-      const bool win0 = n0 == 1 ? (code[k][c][0] >> 8) == m : v0 == vmin[k][c][0];
-      const bool win1 = n1 == 1 ? (code[k][c][1] >> 8) == m : v1 == vmin[k][c][1];
-      g0 = (win0 && ok0 && !bk0 && inv_cnt.x != 0.f) ? coef / (float)n0 : 0.f;
-      g1 = (win1 && ok1 && !bk1 && inv_cnt.y != 0.f) ? coef / (float)n1 : 0.f;
+      // (opaque per source: otherwise the compiler hoists the shares of all twelve minima out of the source loop and
+      // keeps them in local memory -- 45 local loads per source)
+      unsigned cd = code[k][c];
+      asm volatile("" : "+r"(cd));
+      const unsigned c0_ = cd & 0xffffu, c1_ = cd >> 16;
+      const int n0 = c0_ & 0xff, n1 = c1_ & 0xff;
+      const bool win0 = n0 == 1 ? (int)(c0_ >> 8) == m : v0 == vmin[k][c][0];
+      const bool win1 = n1 == 1 ? (int)(c1_ >> 8) == m : v1 == vmin[k][c][1];
+      const float s0 = n0 <= 1 ? coef : coef / (float)n0, s1 = n1 <= 1 ? coef : coef / (float)n1;
+      g0 = (win0 && ok0 && !bk0 && inv_cnt.x != 0.f) ? s0 : 0.f;
+      g1 = (win1 && ok1 && !bk1 && inv_cnt.y != 0.f) ? s1 : 0.f;
     };
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -260,7 +256,14 @@ __global__ void __launch_bounds__(kFThreads, 2) k_min_strip(const __grid_constan
         const float2 v3a = f2fma(xa2, ya2, f2fma(xa1, ya1, f2mul(xa0, ya0)));
         const float2 v3b = f2fma(xb2, yb2, f2fma(xb1, yb1, f2mul(xb0, yb0)));
         const float2 s1 = hsum3(v1a, v1b), s2 = hsum3(v2a, v2b), s3 = hsum3(v3a, v3b);
-        const float2 mux = MUX[c];
+        // the target's window statistics from the rows just loaded: mu_x, mu_x^2 + c1, sigma_x + c2
+        const float2 w1a = f2add(f2add(xa0, xa1), xa2), w1b = f2add(f2add(xb0, xb1), xb2);
+        const float2 w2a = f2fma(xa2, xa2, f2fma(xa1, xa1, f2mul(xa0, xa0)));
+        const float2 w2b = f2fma(xb2, xb2, f2fma(xb1, xb1, f2mul(xb0, xb0)));
+        const float2 mux = f2mul(hsum3(w1a, w1b), inv_cnt);
+        const float2 mux2 = f2mul(mux, mux);
+        const float2 mux2c = f2add(mux2, f2s(kC1));
+        const float2 sgxc = f2add(f2fma(hsum3(w2a, w2b), inv_cnt, f2neg(mux2)), f2s(kC2));
         const float2 muy = f2mul(s1, inv_cnt);
         const float2 muy2 = f2mul(muy, muy);
         const float2 mxy = f2mul(mux, muy);
@@ -268,8 +271,8 @@ __global__ void __launch_bounds__(kFThreads, 2) k_min_strip(const __grid_constan
         const float2 sgxy = f2fma(s3, inv_cnt, f2neg(mxy));
         const float2 a1 = f2fma(f2s(2.f), mxy, f2s(kC1));
         const float2 a2 = f2fma(f2s(2.f), sgxy, f2s(kC2));
-        const float2 b1 = f2add(MUX2C[c], muy2);
-        const float2 b2 = f2add(SGXC[c], sgy);
+        const float2 b1 = f2add(mux2c, muy2);
+        const float2 b2 = f2add(sgxc, sgy);
         const float2 den = f2mul(b1, b2);
         const float2 r12 = f2(rcp_nr(den.x), rcp_nr(den.y));
         const float2 ssv = f2mul(f2mul(a1, a2), r12);
