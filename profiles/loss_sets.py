@@ -21,6 +21,8 @@ flow = {"flow_ms": orc.make_flow(B, H, W, seed=4), "flow_ms_R": orc.make_flow(B,
 f = {k: v.cuda() for k, v in feats.items()}
 cfg = {"image": 1, "intrinsic": 1, "image_R": 1, "intrinsic_R": 1, "stereo_T_LR": 1}
 for name, lw in SETS.items():
+    if os.environ.get("XPT_LS_ONLY") and name != os.environ["XPT_LS_ONLY"]:
+        continue
     src = dict(preds)
     if name == "LOSS_RIGID_COMB":
         src.update(flow)
