@@ -238,6 +238,14 @@ XPT_API int xpt_photometric_cmb_loss(xpt_ctx* ctx, int method, const float* cons
                              int64_t target_batch_stride, float* loss_batch, const float* grad_loss_batch,
                              float* const d_synth_ms[], void* stream);
 
+/* cmbL1 + cmbSSIM of one eye (config-example.py:90-96) in ONE launch, as xpt_photometric_min_pair_loss does for the
+ * min-over-sources pair: loss_batch_l1 / loss_batch_ssim [B] as two calls of xpt_photometric_cmb_loss would return them,
+ * d_synth_ms = d(grad_l1 * sum_b loss_batch_l1[b] + grad_ssim * sum_b loss_batch_ssim[b]) / d synth_ms[s].         */
+XPT_API int xpt_photometric_cmb_pair_loss(xpt_ctx* ctx, const float* const synth_ms[], const float* warped,
+                                  int warped_height, int warped_width, const float* target,
+                                  int64_t target_batch_stride, float* loss_batch_l1, float* loss_batch_ssim,
+                                  float grad_l1, float grad_ssim, float* const d_synth_ms[], void* stream);
+
 /* model/synthesize/flow_warping.py:11-49 FlowWarpMultiScale.__call__: flow_ms[s] [B,N,H_s,W_s,2] (the ctx's
  * scales are the FLOW scales, e.g. 4,8,16,32 for PWC-Net, flow_net.py:44-48) -> warped_ms[s] [B,N,H_s,W_s,3]:
  * the source frames resized to the flow's size (flow_warping.py:36-49) and sampled at grid - flow (:51-71) by

@@ -1,10 +1,7 @@
 #!/bin/bash
-# round 2: the min-over-sources strip kernel -- parity (new vs old kernel, pair launch, oracle, goldens), device time,
-# then the per-kernel launch list of one LOSS_RIGID_MOA_WST step
+# round 2: the min-over-sources / combined strip kernel -- parity (new vs old kernel, pair launch, oracle, goldens), device time
+# (per-kernel launch list of one step: XPT_LS_ONLY=LOSS_RIGID_MOA_WST XPT_LS_STEPS=1 ncu --metrics gpu__time_duration.sum ... python profiles/loss_sets.py)
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -x -q -m gpu -k "min_ or stereo_total or golden" 2>&1 | tail -15 | tee gpurun_out/pytest_min.txt
 timeout 300 python profiles/minloss_bench.py 2>&1 | tail -8 | tee gpurun_out/minloss_strip.txt
 timeout 300 python profiles/loss_sets.py 2>&1 | tail -12 | tee gpurun_out/loss_sets.txt
-XPT_LS_ONLY=LOSS_RIGID_MOA_WST XPT_LS_STEPS=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv \
-   --log-file gpurun_out/launches_moa.csv python profiles/loss_sets.py > gpurun_out/ncu_moa.log 2>&1
-tail -2 gpurun_out/ncu_moa.log

@@ -865,16 +865,28 @@ def test_min_strip_kernel_matches_tile_kernel(xw, B, H, W, N, scales, method):
             assert relerr(loss_fwd.cpu().numpy(), loss.cpu().numpy()) < 1e-6, name     # forward-only variant: the same sweep
             out[name] = (loss.cpu().numpy(), [t.cpu().numpy() for t in d_synth],
                          [t.cpu().numpy() for t in d_stereo] if use_stereo else [])
-        a, b = out["strip"], out["tiles"]
-        assert relerr(a[0], b[0]) < 2e-6, (use_stereo, a[0], b[0])
-        for s in range(len(scales)):
-            # an argmin that flips on the last bit of the SSIM quotient (division vs refined reciprocal) moves one
-            # pixel's gradient to another source: allow a handful of such pixels, compare the rest tightly
-            for x, y in [(a[1][s], b[1][s])] + ([(a[2][s], b[2][s])] if use_stereo else []):
-                scale = np.abs(y).max() + 1e-30
-                bad = np.abs(x - y) > 2e-5 * scale
-                assert bad.sum() <= max(3, 2e-4 * x.size), (use_stereo, s, int(bad.sum()), x.size)
-                assert np.abs((x - y)[~bad]).max() <= 2e-5 * scale
+        if not use_stereo and H // scales[0] >= 4:
+            # CombinedLossMultiScale on the same kernels: the flow-warped view at a quarter of the first level
+            warped0 = U(B, N, max(1, H // scales[0] // 4), max(1, W // scales[0] // 4), 3)
+            for name, flags in (("strip", 0), ("tiles", _cabi.XPT_FLAG_MIN_TILES)):
+                plan = xw.get_plan(0, B, N, H, W, list(scales), sw, flags=flags)
+                loss, d_synth, _ = plan.photometric_cmb_loss(method, synth, warped0, target, grad_loss_batch=gl, want_grad=True)
+                torch.cuda.synchronize()
+                out[name + "_cmb"] = (loss.cpu().numpy(), [t.cpu().numpy() for t in d_synth], [])
+            pairs = [("strip", "tiles"), ("strip_cmb", "tiles_cmb")]
+        else:
+            pairs = [("strip", "tiles")]
+        for ka, kb in pairs:
+            a, b = out[ka], out[kb]
+            assert relerr(a[0], b[0]) < 2e-6, (use_stereo, ka, a[0], b[0])
+            for s in range(len(scales)):
+                # an argmin that flips on the last bit of the SSIM quotient (division vs refined reciprocal) moves one
+                # pixel's gradient to another source: allow a handful of such pixels, compare the rest tightly
+                for x, y in [(a[1][s], b[1][s])] + ([(a[2][s], b[2][s])] if use_stereo else []):
+                    scale = np.abs(y).max() + 1e-30
+                    bad = np.abs(x - y) > 2e-5 * scale
+                    assert bad.sum() <= max(3, 2e-4 * x.size), (use_stereo, s, int(bad.sum()), x.size)
+                    assert np.abs((x - y)[~bad]).max() <= 2e-5 * scale
 
 
 @pytest.mark.parametrize("B,H,W,N,scales", [(2, 40, 72, 3, (1, 2, 4, 8)), (1, 26, 130, 5, (1, 2)), (2, 128, 384, 4, (1, 2, 4, 8)),
@@ -909,6 +921,18 @@ def test_min_pair_launch_matches_two_launches(xw, B, H, W, N, scales):
             if st is not None:
                 want = (c1 * ds1[s] + c2 * ds2[s]).cpu().numpy()
                 assert relerr(dsp[s].cpu().numpy(), want) < 2e-5, ("stereo", s)
+    # cmbL1 + cmbSSIM (CombinedLossMultiScale) in one launch against two launches
+    warped0 = U(B, N, max(1, H // scales[0] // 4), max(1, W // scales[0] // 4), 3)
+    l1, d1, _ = plan.photometric_cmb_loss(0, synth, warped0, target, want_grad=True)
+    ls, d2, _ = plan.photometric_cmb_loss(2, synth, warped0, target, want_grad=True)
+    loss2, dp = plan.photometric_cmb_pair_loss(synth, warped0, target, c1, c2, want_grad=True)
+    loss2_fwd = plan.photometric_cmb_pair_loss(synth, warped0, target)[0]
+    torch.cuda.synchronize()
+    assert relerr(loss2[0].cpu().numpy(), l1.cpu().numpy()) < 1e-6 and relerr(loss2[1].cpu().numpy(), ls.cpu().numpy()) < 1e-6
+    assert relerr(loss2_fwd.cpu().numpy(), loss2.cpu().numpy()) < 1e-6
+    for s in range(len(scales)):
+        want = (c1 * d1[s] + c2 * d2[s]).cpu().numpy()
+        assert relerr(dp[s].cpu().numpy(), want) < 2e-5, ("cmb", s, relerr(dp[s].cpu().numpy(), want))
 
 
 @pytest.mark.parametrize("derive", [False, True], ids=["disp_given", "disp_from_depth"])

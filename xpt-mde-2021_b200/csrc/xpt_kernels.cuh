@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(kPyrThreads, XPT_PYR_MINB) k_pyramid_tma(const
                                                                             const __grid_constant__ CUtensorMap tm_src,
                                                                             const __grid_constant__ CUtensorMap tm_tgt) {
   __shared__ __align__(128) float tile[kPyrTmaBoxes][kPyrTH][kPyrTmaTW * 3];
-  __shared__ __align__(8) unsigned long long mbar;
+  __shared__ __align__(8) unsigned long long mbar[kPyrTmaBoxes];
   const int nfr = a.N + 1;
   if ((int)blockIdx.z == a.B * nfr) {           // geometry slice
     if (a.with_geometry && blockIdx.y == 0) geometry_item(a.geo, blockIdx.x * blockDim.x + threadIdx.x);
@@ -346,22 +346,22 @@ __global__ void __launch_bounds__(kPyrThreads, XPT_PYR_MINB) k_pyramid_tma(const
   if (is_tgt && a.target == nullptr) return;
   const int x0 = blockIdx.x * (kPyrTmaTW * kPyrTmaBoxes), y0 = blockIdx.y * kPyrTH;
   if (x0 >= a.W) return;
-  const unsigned bar = smem_u32(&mbar);
+  // one mbarrier per box: the levels of box 0 are emitted while box 1 is still in flight
   if (threadIdx.x == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
+#pragma unroll
+    for (int k = 0; k < kPyrTmaBoxes; ++k)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mbar[k])), "r"(1));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     constexpr unsigned kBoxBytes = kPyrTH * kPyrTmaTW * 3 * sizeof(float);
-    int nbox = 0;
-#pragma unroll
-    for (int k = 0; k < kPyrTmaBoxes; ++k) nbox += (x0 + k * kPyrTmaTW < a.W) ? 1 : 0;
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kBoxBytes * nbox) : "memory");
 #pragma unroll
     for (int k = 0; k < kPyrTmaBoxes; ++k) {
       const int xk = x0 + k * kPyrTmaTW;
       if (xk >= a.W) continue;
+      const unsigned bar = smem_u32(&mbar[k]);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kBoxBytes) : "memory");
       const unsigned dst = smem_u32(&tile[k][0][0]);
       if (is_tgt)
         asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -371,19 +371,19 @@ __global__ void __launch_bounds__(kPyrThreads, XPT_PYR_MINB) k_pyramid_tma(const
                      ::"r"(dst), "l"(&tm_src), "r"(bar), "r"(xk * 3), "r"(y0), "r"(f), "r"(b) : "memory");
     }
   }
-  // every thread waits for the transaction bytes (phase 0 of the barrier)
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(bar), "r"(0) : "memory");
   const long long frame = is_tgt ? (long long)b : (long long)(b * a.N + f);
 #pragma unroll
   for (int k = 0; k < kPyrTmaBoxes; ++k) {
     const int xk = x0 + k * kPyrTmaTW;
     if (xk >= a.W) continue;
+    // every thread waits for the box's transaction bytes (phase 0 of its barrier)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(&mbar[k])), "r"(0) : "memory");
     const int tw = min(kPyrTmaTW, a.W - xk);    // multiple of 8
     if (tw == kPyrTmaTW) pyramid_emit<true, kPyrTmaTW>(a, tile[k], tw, is_tgt, frame, xk, y0);
     else pyramid_emit<false, kPyrTmaTW>(a, tile[k], tw, is_tgt, frame, xk, y0);

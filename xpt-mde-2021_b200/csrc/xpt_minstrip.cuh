@@ -25,8 +25,9 @@
 namespace xpt {
 
 constexpr int kMSTPitch = 36;                   // low-resolution footprint columns of a 64-wide tile at scale >= 2: <= 34
-constexpr int kMSTabs = 384;                    // x0/x1/fx [68] + y0/y1/fy [17], then the footprint's column / row ranges
+constexpr int kMSTabs = 640;                    // x0/x1/fx [68] + y0/y1/fy [17], then the footprint's column / row ranges
 constexpr int kMSRanges = 256;                  // offset of rXa[36], rXb[36], rYa[16], rYb[16] inside the table block
+constexpr int kMSFlowTabs = 368;                // offset of the tap tables of the flow-warped view (CMB), same layout as the first 255
 
 template <bool GRAD, bool PAIR>
 struct MinStripSmem {
@@ -47,7 +48,11 @@ struct MinStripSmem {
 // PAIR: the L1 and the SSIM loss of one loss set (moaL1 + moaSSIM, md2L1 + md2SSIM) in ONE launch -- the two minima are
 // independent, but the up-sampled tiles, the black-pixel masks, the target tile and the up-sampling adjoint are shared;
 // the gradient written is pair_c_l1 dL1/dS + pair_c_ssim dSSIM/dS.
-template <bool GRAD, bool PAIR>
+// CMB: CombinedLossMultiScale (losses.py:235-279) instead of the minimum over sources -- per source, the static term
+// counts where it is smaller than the term of the flow-warped view (a.cmb_flow, up-sampled from its own size); one sweep:
+// the flow term of a source goes to the registers the minimum lives in, the static term is compared with it, and the
+// gradient of the kept terms is formed and reduced right away.
+template <bool GRAD, bool PAIR, bool CMB>
 __global__ void __launch_bounds__(kFThreads, 2) k_min_strip(const __grid_constant__ MinLossArgs a) {
   using SM = MinStripSmem<GRAD, PAIR>;
   constexpr int NM = PAIR ? 2 : 1;              // minima tracked: [0] = the method (PAIR: L1), [1] = SSIM of the pair
@@ -66,6 +71,12 @@ __global__ void __launch_bounds__(kFThreads, 2) k_min_strip(const __grid_constan
   int* const rXb = rXa + kMSTPitch;
   int* const rYa = rXb + kMSTPitch;
   int* const rYb = rYa + 16;
+  int* const fX0 = reinterpret_cast<int*>(smem + SM::tab + kMSFlowTabs);
+  int* const fX1 = fX0 + kFRW;
+  float* const fFX = smem + SM::tab + kMSFlowTabs + 2 * kFRW;
+  int* const fY0 = reinterpret_cast<int*>(smem + SM::tab + kMSFlowTabs + 3 * kFRW);
+  int* const fY1 = fY0 + kFRH;
+  float* const fFY = smem + SM::tab + kMSFlowTabs + 3 * kFRW + 2 * kFRH;
   float* const red = smem + SM::red;
   float* const sA = smem + SM::sA;
   float* const sB = smem + SM::sB;
@@ -84,7 +95,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_min_strip(const __grid_constan
   const bool ssim = PAIR || a.method == 2, do_l1 = PAIR || a.method != 2, l2 = !PAIR && a.method == 1;
   constexpr int iS = PAIR ? 1 : 0;              // index of the SSIM minimum
   const bool identity = (h == H) && (w == W);
-  const int nsrc = a.N + a.NS;
+  const int nsrc = CMB ? a.N : a.N + a.NS;
 
   // ---- tap tables (resize_bilinear, half-pixel centres) of the tile's rows and columns, target tile ----------
   if (tid < kFRW) {
@@ -95,6 +106,14 @@ __global__ void __launch_bounds__(kFThreads, 2) k_min_strip(const __grid_constan
     int lo, hi; float f;
     up_taps(min(max(ty0 - 2 + (tid - 96), 0), H - 1), h, (float)h / (float)H, lo, hi, f);
     tY0[tid - 96] = lo; tY1[tid - 96] = hi; tFY[tid - 96] = f;
+  } else if (CMB && tid >= 128 && tid < 128 + kFRW) {
+    int lo, hi; float f;
+    up_taps(min(max(tx0 - 2 + (tid - 128), 0), W - 1), a.cmb_w, (float)a.cmb_w / (float)W, lo, hi, f);
+    fX0[tid - 128] = lo; fX1[tid - 128] = hi; fFX[tid - 128] = f;
+  } else if (CMB && tid >= 224 && tid < 224 + kFRH) {
+    int lo, hi; float f;
+    up_taps(min(max(ty0 - 2 + (tid - 224), 0), H - 1), a.cmb_h, (float)a.cmb_h / (float)H, lo, hi, f);
+    fY0[tid - 224] = lo; fY1[tid - 224] = hi; fFY[tid - 224] = f;
   }
   {
     const float* tgt = a.target + b * a.tgt_bs;
@@ -155,9 +174,8 @@ __global__ void __launch_bounds__(kFThreads, 2) k_min_strip(const __grid_constan
     for (int c = 0; c < 3; ++c) { vmin[k][c][0] = vmin[k][c][1] = 3.0e38f; code[k][c] = 0u; }
 
   // ---- up-sampled region of source m into sy (zero outside the image) ---------------------------------------
-  auto upsample = [&](int m) {
-    const float* low = m < a.N ? a.synth[l] + ((size_t)b * a.N + m) * h * w * 3
-                               : a.stereo[l] + ((size_t)b * a.NS + (m - a.N)) * h * w * 3;
+  auto upsample_from = [&](const float* low, int lw, bool ident, const int* X0, const int* X1, const float* FX,
+                           const int* Y0, const int* Y1, const float* FY) {
 #pragma unroll
     for (int it = 0; it < kFYIters; ++it) {
       const int i = tid + it * kFThreads;
@@ -166,14 +184,14 @@ __global__ void __launch_bounds__(kFThreads, 2) k_min_strip(const __grid_constan
         const int gy = ty0 - 2 + ry, gx = tx0 - 2 + rx;
         float yv[3] = {0.f, 0.f, 0.f};
         if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-          if (identity) {
-            const float* p = low + ((size_t)gy * w + gx) * 3;
+          if (ident) {
+            const float* p = low + ((size_t)gy * lw + gx) * 3;
             yv[0] = __ldg(p); yv[1] = __ldg(p + 1); yv[2] = __ldg(p + 2);
           } else {
-            const int x0 = tX0[rx] * 3, x1 = tX1[rx] * 3;
-            const float fx = tFX[rx], fy = tFY[ry];
-            const float* r0 = low + (size_t)tY0[ry] * w * 3;
-            const float* r1 = low + (size_t)tY1[ry] * w * 3;
+            const int x0 = X0[rx] * 3, x1 = X1[rx] * 3;
+            const float fx = FX[rx], fy = FY[ry];
+            const float* r0 = low + (size_t)Y0[ry] * lw * 3;
+            const float* r1 = low + (size_t)Y1[ry] * lw * 3;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
               const float tl = __ldg(r0 + x0 + c), tr = __ldg(r0 + x1 + c);
@@ -189,12 +207,26 @@ __global__ void __launch_bounds__(kFThreads, 2) k_min_strip(const __grid_constan
       }
     }
   };
+  auto upsample = [&](int m) {
+    upsample_from(m < a.N ? a.synth[l] + ((size_t)b * a.N + m) * h * w * 3
+                          : a.stereo[l] + ((size_t)b * a.NS + (m - a.N)) * h * w * 3, w, identity, tX0, tX1, tFX, tY0, tY1, tFY);
+  };
+  auto upsample_flow = [&](int m) {
+    upsample_from(a.cmb_flow + ((size_t)b * a.N + m) * a.cmb_h * a.cmb_w * 3, a.cmb_w, a.cmb_h == H && a.cmb_w == W,
+                  fX0, fX1, fFX, fY0, fY1, fFY);
+  };
 
   // ---- the strip's terms of the source in sy.  COEF = false (sweep 1): update the running minimum.  COEF = true
   // (sweep 2): route the upstream gradient to the winners and leave the adjoint coefficients in sA / sB / sC
   // (SSIM: Hh a-terms as in k_fused, summed over the 3x3 window later; L1 / L2: the local derivative in sA). --------
-  auto strip_terms = [&](int m, auto coef_tag) {
-    constexpr bool COEF = decltype(coef_tag)::value;
+  // MODE 0: sweep 1 of the minimum.  1: sweep 2 of the minimum.  2 (CMB): the flow term of source m -> vmin.
+  // 3 (CMB): the static term of source m, kept where it is smaller than the flow term: loss sum and, GRAD, coefficients.
+  float lacc[NM];
+#pragma unroll
+  for (int k = 0; k < NM; ++k) lacc[k] = 0.f;
+  auto strip_terms = [&](int m, auto mode_tag) {
+    constexpr int MODE = decltype(mode_tag)::value;
+    constexpr bool COEF = MODE == 1 || (MODE == 3 && GRAD);
     if (!s_active) return;
     const int mid = (qy + 1) * kFP + q0;
     bool bk0, bk1;              // black (invalid) synthesised pixel: tf.where(mask, 0, loss) -- value 0, no gradient
@@ -219,6 +251,15 @@ __global__ void __launch_bounds__(kFThreads, 2) k_min_strip(const __grid_constan
       code[k][c] = c0_ | (c1_ << 16);
     };
     auto share = [&](int k, int c, float v0, float v1, bool ok0, bool ok1, float coef, float& g0, float& g1) {
+      if constexpr (MODE == 3) {
+        // tf.cast(static_loss < flow_loss): a constant mask; the kept terms are summed over the tile's centre
+        const bool keep0 = v0 < vmin[k][c][0], keep1 = v1 < vmin[k][c][1];
+        if (keep0 && s_centre.x != 0.f) lacc[k] += v0;
+        if (keep1 && s_centre.y != 0.f) lacc[k] += v1;
+        g0 = (keep0 && ok0 && !bk0 && inv_cnt.x != 0.f) ? coef : 0.f;
+        g1 = (keep1 && ok1 && !bk1 && inv_cnt.y != 0.f) ? coef : 0.f;
+        return;
+      }
       // (opaque per source: otherwise the compiler hoists the shares of all twelve minima out of the source loop and
       // keeps them in local memory -- 45 local loads per source)
       unsigned cd = code[k][c];
@@ -242,11 +283,13 @@ __global__ void __launch_bounds__(kFThreads, 2) k_min_strip(const __grid_constan
         float v0 = l2 ? __fmul_rn(d0, d0) : fabsf(d0), v1 = l2 ? __fmul_rn(d1, d1) : fabsf(d1);
         if (bk0) v0 = 0.f;
         if (bk1) v1 = 0.f;
-        if constexpr (!COEF) update(0, c, v0, v1);
+        if constexpr (MODE == 0) update(0, c, v0, v1);
+        else if constexpr (MODE == 2) { vmin[0][c][0] = v0; vmin[0][c][1] = v1; }
         else {
           float g0, g1;
           share(0, c, v0, v1, true, true, coefL, g0, g1);
-          *reinterpret_cast<float2*>(sLp + so) = f2(l2 ? g0 * 2.f * d0 : g0 * sgnf(d0), l2 ? g1 * 2.f * d1 : g1 * sgnf(d1));
+          if constexpr (COEF)
+            *reinterpret_cast<float2*>(sLp + so) = f2(l2 ? g0 * 2.f * d0 : g0 * sgnf(d0), l2 ? g1 * 2.f * d1 : g1 * sgnf(d1));
         }
       }
       if (ssim) {
@@ -283,10 +326,12 @@ __global__ void __launch_bounds__(kFThreads, 2) k_min_strip(const __grid_constan
         const bool pass0 = v0 == lv.x, pass1 = v1 == lv.y;       // clip_by_value passes the gradient inside [0,1]
         if (bk0) v0 = 0.f;
         if (bk1) v1 = 0.f;
-        if constexpr (!COEF) update(iS, c, v0, v1);
+        if constexpr (MODE == 0) update(iS, c, v0, v1);
+        else if constexpr (MODE == 2) { vmin[iS][c][0] = v0; vmin[iS][c][1] = v1; }
         else {
           float g0, g1;
           share(iS, c, v0, v1, pass0, pass1, coefS, g0, g1);
+          if constexpr (COEF) {
           // h = dL/d ssim = -g/2; Hh = 2 h / (#taps b1 b2); A, 2B, C as in k_fused
           const float2 Hh = f2mul(f2(-g0 * inv_cnt.x, -g1 * inv_cnt.y), r12);
           const float2 Hs = f2mul(Hh, ssv);
@@ -295,47 +340,21 @@ __global__ void __launch_bounds__(kFThreads, 2) k_min_strip(const __grid_constan
           *reinterpret_cast<float2*>(sA + so) = f2fma(Hh, t1, f2neg(f2mul(Hs, t2)));
           *reinterpret_cast<float2*>(sB + so) = f2mul(f2neg(Hs), b1);
           *reinterpret_cast<float2*>(sC + so) = f2mul(Hh, a1);
+          }
         }
       }
     }
   };
 
-  // ---- sweep 1: minimum, tie count and first winner per (pixel, channel) --------------------------------------
-  for (int m = 0; m < nsrc; ++m) {
-    upsample(m);
-    __syncthreads();
-    strip_terms(m, std::false_type{});
-    __syncthreads();
-  }
-  // loss of this tile: sum of the minima over its in-image centre pixels
-  {
-    float lsum[NM];
-#pragma unroll
-    for (int k = 0; k < NM; ++k) {
-      lsum[k] = 0.f;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        if (s_centre.x != 0.f) lsum[k] += vmin[k][c][0];
-        if (s_centre.y != 0.f) lsum[k] += vmin[k][c][1];
-      }
-      lsum[k] = warp_sum(lsum[k]);
-      if (lane == 0) red[k * 16 + wid] = lsum[k];
-    }
-    __syncthreads();
-    if (tid < NM) {
-      float v = 0.f;
-#pragma unroll
-      for (int k = 0; k < kFThreads / 32; ++k) v += red[tid * 16 + k];
-      (tid == 0 ? a.loss_part : a.loss_part2)[(size_t)b * a.S * a.tiles + blockIdx.y] = v * a.norm[l];
-    }
-  }
-
-  // ---- sweep 2: gradient of the winners ----------------------------------------------------------------------
+  // ---- adjoint of one source: dL/dS on the centre strip from the coefficient planes, then (levels below full
+  // resolution) the up-sampling adjoint reduced inside the tile ----------------------------------------------------
+  int cw = 0, ch = 0, X_lo = 0, FW = 1, Y_lo = 0, FHt = 1;
+  float inv_FW = 0.f, inv_chFW = 0.f, inv_FHFW = 0.f;
   if constexpr (GRAD) {
     // low-resolution footprint of the tile's centre and, per footprint column / row, the tile columns / rows feeding it
-    const int cw = min(kFCW, W - tx0), ch = min(kFCH, H - ty0);        // in-image centre extent
-    const int X_lo = tX0[2], FW = tX1[2 + cw - 1] - X_lo + 1;
-    const int Y_lo = tY0[2], FHt = min(tY1[2 + ch - 1] - Y_lo + 1, 16);
+    cw = min(kFCW, W - tx0); ch = min(kFCH, H - ty0);        // in-image centre extent
+    X_lo = tX0[2]; FW = tX1[2 + cw - 1] - X_lo + 1;
+    Y_lo = tY0[2]; FHt = min(tY1[2 + ch - 1] - Y_lo + 1, 16);
     if (!identity) {
       auto ranges = [](const int* lo, const int* hi, int n, int V, int& ra, int& rb) {
         int a0 = 1, a1 = 0, b0 = 1, b1 = 0;
@@ -350,81 +369,141 @@ __global__ void __launch_bounds__(kFThreads, 2) k_min_strip(const __grid_constan
       else if (tid >= 64 && tid < 64 + FHt) ranges(tY0, tY1, ch, Y_lo + (tid - 64), rYa[tid - 64], rYb[tid - 64]);
       // (visible to the reduction passes behind the barriers of the first source)
     }
-    const float inv_FW = 1.f / (float)FW, inv_chFW = 1.f / (float)(ch * FW), inv_FHFW = 1.f / (float)(FHt * FW);
+    inv_FW = 1.f / (float)FW; inv_chFW = 1.f / (float)(ch * FW); inv_FHFW = 1.f / (float)(FHt * FW);
+  }
+  auto adjoint = [&](int m) {
+    float* glow = m < a.N ? a.gsynth[l] + ((size_t)b * a.N + m) * h * w * 3
+                          : a.gstereo[l] + ((size_t)b * a.NS + (m - a.N)) * h * w * 3;
+    if (g_active) {           // warps 0..12 own one centre row each
+      const int rrow = (cyy + 2) * kFP + c0 + 2;
+      float2 g[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float2 gc = f2s(0.f);
+        if (ssim) {
+          const float2 yv = lds2(sy + c * kFRegion + rrow), xv = lds2(sx + c * kFRegion + rrow);
+          const int so = c * kFStats + cyy * kFP + c0;
+          float2 va, vb;
+          va = f2add(f2add(lds2(sA + so), lds2(sA + so + kFP)), lds2(sA + so + 2 * kFP));
+          vb = f2add(f2add(lds2(sA + so + 2), lds2(sA + so + kFP + 2)), lds2(sA + so + 2 * kFP + 2));
+          const float2 sa = hsum3(va, vb);
+          va = f2add(f2add(lds2(sB + so), lds2(sB + so + kFP)), lds2(sB + so + 2 * kFP));
+          vb = f2add(f2add(lds2(sB + so + 2), lds2(sB + so + kFP + 2)), lds2(sB + so + 2 * kFP + 2));
+          const float2 sb = hsum3(va, vb);
+          va = f2add(f2add(lds2(sC + so), lds2(sC + so + kFP)), lds2(sC + so + 2 * kFP));
+          vb = f2add(f2add(lds2(sC + so + 2), lds2(sC + so + kFP + 2)), lds2(sC + so + 2 * kFP + 2));
+          const float2 sc = hsum3(va, vb);
+          gc = f2fma(yv, sb, f2fma(xv, sc, sa));               // sB holds 2 dL/dP(y^2)
+        }
+        if (do_l1) {
+          const int so = c * kFStats + (cyy + 1) * kFP + c0 + 1;
+          gc = f2add(gc, f2(sLp[so], sLp[so + 1]));
+        }
+        g[c] = gc;
+      }
+      const int gy = ty0 + cyy;
+      const bool in0 = tx0 + c0 < W, in1 = tx0 + c0 + 1 < W;     // (gy < H: g_active)
+      if (identity) {
+        float* o = glow + ((size_t)gy * w + tx0 + c0) * 3;
+        if (in0) { o[0] = g[0].x; o[1] = g[1].x; o[2] = g[2].x; }
+        if (in1) { o[3] = g[0].y; o[4] = g[1].y; o[5] = g[2].y; }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          *reinterpret_cast<float2*>(sG + c * kFCentre + cyy * kFCP + c0) = f2(in0 ? g[c].x : 0.f, in1 ? g[c].y : 0.f);
+      }
+    }
+    if (!identity) {
+      __syncthreads();
+      // adjoint of the up-sampling, horizontal pass: T[c][r][X] = sum over the tile's columns o of wx(o, X) g[c][r][o]
+      for (int j = tid; j < 3 * ch * FW; j += kFThreads) {
+        const int c = (int)(((float)j + 0.5f) * inv_chFW), k = j - c * ch * FW;      // exact for these small integers
+        const int r = (int)(((float)k + 0.5f) * inv_FW), Xi = k - r * FW;
+        const int pa = rXa[Xi], pb = rXb[Xi];
+        const float* gr = sG + c * kFCentre + r * kFCP;
+        float v = 0.f;
+        for (int o = pa & 0xff; o <= (pa >> 8); ++o) v = fmaf(1.f - tFX[o + 2], gr[o], v);
+        for (int o = pb & 0xff; o <= (pb >> 8); ++o) v = fmaf(tFX[o + 2], gr[o], v);
+        sT[(c * kFCH + r) * kMSTPitch + Xi] = v;
+      }
+      __syncthreads();
+      // vertical pass and ONE atomic per low-resolution value of the footprint
+      for (int j = tid; j < 3 * FHt * FW; j += kFThreads) {
+        const int c = (int)(((float)j + 0.5f) * inv_FHFW), k = j - c * FHt * FW;
+        const int Yi = (int)(((float)k + 0.5f) * inv_FW), Xi = k - Yi * FW;
+        const int pa = rYa[Yi], pb = rYb[Yi];
+        const float* tc = sT + c * kFCH * kMSTPitch + Xi;
+        float v = 0.f;
+        for (int r = pa & 0xff; r <= (pa >> 8); ++r) v = fmaf(1.f - tFY[r + 2], tc[r * kMSTPitch], v);
+        for (int r = pb & 0xff; r <= (pb >> 8); ++r) v = fmaf(tFY[r + 2], tc[r * kMSTPitch], v);
+        if (v != 0.f) atomicAdd(glow + ((size_t)(Y_lo + Yi) * w + (X_lo + Xi)) * 3 + c, v);
+      }
+    } else {
+      __syncthreads();      // the next source's up-sampling rewrites sy
+    }
+  };
+
+  auto reduce_loss = [&](float (&lsum)[NM]) {
+#pragma unroll
+    for (int k = 0; k < NM; ++k) {
+      lsum[k] = warp_sum(lsum[k]);
+      if (lane == 0) red[k * 16 + wid] = lsum[k];
+    }
+    __syncthreads();
+    if (tid < NM) {
+      float v = 0.f;
+#pragma unroll
+      for (int k = 0; k < kFThreads / 32; ++k) v += red[tid * 16 + k];
+      (tid == 0 ? a.loss_part : a.loss_part2)[(size_t)b * a.S * a.tiles + blockIdx.y] = v * a.norm[l];
+    }
+  };
+
+  if constexpr (CMB) {
+    for (int m = 0; m < nsrc; ++m) {
+      upsample_flow(m);
+      __syncthreads();
+      strip_terms(m, std::integral_constant<int, 2>{});
+      __syncthreads();
+      upsample(m);
+      __syncthreads();
+      strip_terms(m, std::integral_constant<int, 3>{});
+      __syncthreads();
+      if constexpr (GRAD) adjoint(m);
+    }
+    reduce_loss(lacc);
+    return;
+  }
+
+  // ---- sweep 1: minimum, tie count and first winner per (pixel, channel) --------------------------------------
+  for (int m = 0; m < nsrc; ++m) {
+    upsample(m);
+    __syncthreads();
+    strip_terms(m, std::integral_constant<int, 0>{});
+    __syncthreads();
+  }
+  // loss of this tile: sum of the minima over its in-image centre pixels
+  {
+    float lsum[NM];
+#pragma unroll
+    for (int k = 0; k < NM; ++k) {
+      lsum[k] = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        if (s_centre.x != 0.f) lsum[k] += vmin[k][c][0];
+        if (s_centre.y != 0.f) lsum[k] += vmin[k][c][1];
+      }
+    }
+    reduce_loss(lsum);
+  }
+
+  // ---- sweep 2: gradient of the winners ----------------------------------------------------------------------
+  if constexpr (GRAD) {
     for (int m = 0; m < nsrc; ++m) {
       upsample(m);
       __syncthreads();
-      strip_terms(m, std::true_type{});
+      strip_terms(m, std::integral_constant<int, 1>{});
       __syncthreads();
-      float* glow = m < a.N ? a.gsynth[l] + ((size_t)b * a.N + m) * h * w * 3
-                            : a.gstereo[l] + ((size_t)b * a.NS + (m - a.N)) * h * w * 3;
-      if (g_active) {           // warps 0..12 own one centre row each
-        const int rrow = (cyy + 2) * kFP + c0 + 2;
-        float2 g[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          float2 gc = f2s(0.f);
-          if (ssim) {
-            const float2 yv = lds2(sy + c * kFRegion + rrow), xv = lds2(sx + c * kFRegion + rrow);
-            const int so = c * kFStats + cyy * kFP + c0;
-            float2 va, vb;
-            va = f2add(f2add(lds2(sA + so), lds2(sA + so + kFP)), lds2(sA + so + 2 * kFP));
-            vb = f2add(f2add(lds2(sA + so + 2), lds2(sA + so + kFP + 2)), lds2(sA + so + 2 * kFP + 2));
-            const float2 sa = hsum3(va, vb);
-            va = f2add(f2add(lds2(sB + so), lds2(sB + so + kFP)), lds2(sB + so + 2 * kFP));
-            vb = f2add(f2add(lds2(sB + so + 2), lds2(sB + so + kFP + 2)), lds2(sB + so + 2 * kFP + 2));
-            const float2 sb = hsum3(va, vb);
-            va = f2add(f2add(lds2(sC + so), lds2(sC + so + kFP)), lds2(sC + so + 2 * kFP));
-            vb = f2add(f2add(lds2(sC + so + 2), lds2(sC + so + kFP + 2)), lds2(sC + so + 2 * kFP + 2));
-            const float2 sc = hsum3(va, vb);
-            gc = f2fma(yv, sb, f2fma(xv, sc, sa));               // sB holds 2 dL/dP(y^2)
-          }
-          if (do_l1) {
-            const int so = c * kFStats + (cyy + 1) * kFP + c0 + 1;
-            gc = f2add(gc, f2(sLp[so], sLp[so + 1]));
-          }
-          g[c] = gc;
-        }
-        const int gy = ty0 + cyy;
-        const bool in0 = tx0 + c0 < W, in1 = tx0 + c0 + 1 < W;     // (gy < H: g_active)
-        if (identity) {
-          float* o = glow + ((size_t)gy * w + tx0 + c0) * 3;
-          if (in0) { o[0] = g[0].x; o[1] = g[1].x; o[2] = g[2].x; }
-          if (in1) { o[3] = g[0].y; o[4] = g[1].y; o[5] = g[2].y; }
-        } else {
-#pragma unroll
-          for (int c = 0; c < 3; ++c)
-            *reinterpret_cast<float2*>(sG + c * kFCentre + cyy * kFCP + c0) = f2(in0 ? g[c].x : 0.f, in1 ? g[c].y : 0.f);
-        }
-      }
-      if (!identity) {
-        __syncthreads();
-        // adjoint of the up-sampling, horizontal pass: T[c][r][X] = sum over the tile's columns o of wx(o, X) g[c][r][o]
-        for (int j = tid; j < 3 * ch * FW; j += kFThreads) {
-          const int c = (int)(((float)j + 0.5f) * inv_chFW), k = j - c * ch * FW;      // exact for these small integers
-          const int r = (int)(((float)k + 0.5f) * inv_FW), Xi = k - r * FW;
-          const int pa = rXa[Xi], pb = rXb[Xi];
-          const float* gr = sG + c * kFCentre + r * kFCP;
-          float v = 0.f;
-          for (int o = pa & 0xff; o <= (pa >> 8); ++o) v = fmaf(1.f - tFX[o + 2], gr[o], v);
-          for (int o = pb & 0xff; o <= (pb >> 8); ++o) v = fmaf(tFX[o + 2], gr[o], v);
-          sT[(c * kFCH + r) * kMSTPitch + Xi] = v;
-        }
-        __syncthreads();
-        // vertical pass and ONE atomic per low-resolution value of the footprint
-        for (int j = tid; j < 3 * FHt * FW; j += kFThreads) {
-          const int c = (int)(((float)j + 0.5f) * inv_FHFW), k = j - c * FHt * FW;
-          const int Yi = (int)(((float)k + 0.5f) * inv_FW), Xi = k - Yi * FW;
-          const int pa = rYa[Yi], pb = rYb[Yi];
-          const float* tc = sT + c * kFCH * kMSTPitch + Xi;
-          float v = 0.f;
-          for (int r = pa & 0xff; r <= (pa >> 8); ++r) v = fmaf(1.f - tFY[r + 2], tc[r * kMSTPitch], v);
-          for (int r = pb & 0xff; r <= (pb >> 8); ++r) v = fmaf(tFY[r + 2], tc[r * kMSTPitch], v);
-          if (v != 0.f) atomicAdd(glow + ((size_t)(Y_lo + Yi) * w + (X_lo + Xi)) * 3 + c, v);
-        }
-      } else {
-        __syncthreads();      // the next source's up-sampling rewrites sy
-      }
+      adjoint(m);
     }
   }
 }

@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -306,7 +307,9 @@ int launch_pyramids(xpt_ctx* ctx, const xpt_frames* f, float* const target_ms[],
         if (prof) XPT_CUDA(cudaEventRecord((*ctx->prof_events)[2 * ctx->prof_count], st));
         // tile loads by the TMA unit (k_pyramid_tma) when tensor maps over the caller's frames can be encoded
         CUtensorMap tm_src, tm_tgt;
-        bool tma = any;
+        // XPT_PYRAMID=tiled: the LDG/STS tile kernel instead (A/B switch for profiling, read once)
+        static const bool force_tiled = [] { const char* e = getenv("XPT_PYRAMID"); return e && !strcmp(e, "tiled"); }();
+        bool tma = any && !force_tiled;
         if (tma) {
           const long long sd[2] = {ctx->N, ctx->B}, ss[2] = {(long long)f->source_frame_stride, (long long)f->source_batch_stride};
           tma = make_frame_tmap(&tm_src, f->source, ctx->W, ctx->H, 4, sd, ss);
@@ -1356,9 +1359,9 @@ static int min_loss_impl(xpt_ctx* ctx, int method, const float* const synth_ms[]
   a.method = method == XPT_PHOTO_L1 ? 0 : (method == XPT_PHOTO_L2 ? 1 : 2);
   a.gbatch = grad_loss_batch;
   a.cmb_flow = cmb_flow; a.cmb_h = cmb_h; a.cmb_w = cmb_w;
-  // min-over-sources mode runs on the strip kernel (64x13 tiles); the combined loss, XPT_FLAG_MIN_TILES (A/B) and
-  // levels between full and half resolution (footprint wider than the strip kernel's buffer) keep the 32x16 tile kernel
-  bool strip = !cmb_flow && !(ctx->cfg.flags & XPT_FLAG_MIN_TILES);
+  // the strip kernel (64x13 tiles) serves both modes; XPT_FLAG_MIN_TILES (A/B) and levels between full and half
+  // resolution (footprint wider than the strip kernel's buffer) keep the 32x16 tile kernel
+  bool strip = !(ctx->cfg.flags & XPT_FLAG_MIN_TILES);
   for (int l = 0; l < ctx->S; ++l)
     if (!((ctx->h[l] == ctx->H && ctx->w[l] == ctx->W) || (2 * ctx->w[l] <= ctx->W && 2 * ctx->h[l] <= ctx->H))) strip = false;
   a.tiles_x = strip ? cdiv(ctx->W, kFCW) : cdiv(ctx->W, kTW);
@@ -1384,33 +1387,25 @@ static int min_loss_impl(xpt_ctx* ctx, int method, const float* const synth_ms[]
     }
   }
   dim3 grid(ctx->S * a.tiles, ctx->B);
-  if (strip && pair) {
+  if (strip) {
     const dim3 sgrid(ctx->B, ctx->S * a.tiles);
-    if (d_synth_ms) {
-      static unsigned long long attr_done = 0;
-      const size_t smem = MinStripSmem<true, true>::kBytes;
-      XPT_TRY(ensure_dyn_smem(k_min_strip<true, true>, smem, ctx->cfg.device, &attr_done));
-      k_min_strip<true, true><<<sgrid, kFThreads, smem, st>>>(a);
+    const bool grad = d_synth_ms != nullptr, cmb = cmb_flow != nullptr;
+    // one instantiation per (gradient, pair, combined)
+#define XPT_MIN_STRIP(G, P, C)                                                                              \
+    do {                                                                                                    \
+      static unsigned long long attr_done = 0;                                                              \
+      const size_t smem = MinStripSmem<G, P>::kBytes;                                                       \
+      XPT_TRY(ensure_dyn_smem(k_min_strip<G, P, C>, smem, ctx->cfg.device, &attr_done));                    \
+      k_min_strip<G, P, C><<<sgrid, kFThreads, smem, st>>>(a);                                              \
+    } while (0)
+    if (grad) {
+      if (pair) { if (cmb) XPT_MIN_STRIP(true, true, true); else XPT_MIN_STRIP(true, true, false); }
+      else { if (cmb) XPT_MIN_STRIP(true, false, true); else XPT_MIN_STRIP(true, false, false); }
     } else {
-      static unsigned long long attr_done = 0;
-      const size_t smem = MinStripSmem<false, true>::kBytes;
-      XPT_TRY(ensure_dyn_smem(k_min_strip<false, true>, smem, ctx->cfg.device, &attr_done));
-      k_min_strip<false, true><<<sgrid, kFThreads, smem, st>>>(a);
+      if (pair) { if (cmb) XPT_MIN_STRIP(false, true, true); else XPT_MIN_STRIP(false, true, false); }
+      else { if (cmb) XPT_MIN_STRIP(false, false, true); else XPT_MIN_STRIP(false, false, false); }
     }
-    XPT_LAUNCH_CHECK("k_min_strip<pair>");
-  } else if (strip) {
-    const dim3 sgrid(ctx->B, ctx->S * a.tiles);
-    if (d_synth_ms) {
-      static unsigned long long attr_done = 0;
-      const size_t smem = MinStripSmem<true, false>::kBytes;
-      XPT_TRY(ensure_dyn_smem(k_min_strip<true, false>, smem, ctx->cfg.device, &attr_done));
-      k_min_strip<true, false><<<sgrid, kFThreads, smem, st>>>(a);
-    } else {
-      static unsigned long long attr_done = 0;
-      const size_t smem = MinStripSmem<false, false>::kBytes;
-      XPT_TRY(ensure_dyn_smem(k_min_strip<false, false>, smem, ctx->cfg.device, &attr_done));
-      k_min_strip<false, false><<<sgrid, kFThreads, smem, st>>>(a);
-    }
+#undef XPT_MIN_STRIP
     XPT_LAUNCH_CHECK("k_min_strip");
   } else if (d_synth_ms) {
     static unsigned long long attr_done = 0;
@@ -1457,6 +1452,16 @@ int xpt_photometric_cmb_loss(xpt_ctx* ctx, int method, const float* const synth_
   if (warped_height < 1 || warped_width < 1) return fail(XPT_BAD_SHAPE, "warped view %dx%d", warped_height, warped_width);
   return min_loss_impl(ctx, method, synth_ms, nullptr, warped, warped_height, warped_width, target, target_batch_stride,
                        loss_batch, grad_loss_batch, d_synth_ms, nullptr, stream);
+}
+
+int xpt_photometric_cmb_pair_loss(xpt_ctx* ctx, const float* const synth_ms[], const float* warped, int warped_height,
+                                  int warped_width, const float* target, int64_t target_batch_stride, float* loss_batch_l1,
+                                  float* loss_batch_ssim, float grad_l1, float grad_ssim, float* const d_synth_ms[],
+                                  void* stream) {
+  if (!warped || !loss_batch_ssim) return fail(XPT_BAD_ARGUMENT, "xpt_photometric_cmb_pair_loss: NULL argument");
+  if (warped_height < 1 || warped_width < 1) return fail(XPT_BAD_SHAPE, "warped view %dx%d", warped_height, warped_width);
+  return min_loss_impl(ctx, XPT_PHOTO_L1, synth_ms, nullptr, warped, warped_height, warped_width, target, target_batch_stride,
+                       loss_batch_l1, nullptr, d_synth_ms, nullptr, stream, loss_batch_ssim, grad_l1, grad_ssim);
 }
 
 // ---- optical-flow warping (flow_warping.py) -------------------------------------------------------------

@@ -82,6 +82,9 @@ SYMBOLS = {
     "xpt_photometric_cmb_loss": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(PtrArray), C.c_void_p, C.c_int, C.c_int,
                                            C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(PtrArray),
                                            C.c_void_p]),
+    "xpt_photometric_cmb_pair_loss": (C.c_int, [C.c_void_p, C.POINTER(PtrArray), C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                                C.c_int64, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.POINTER(PtrArray),
+                                                C.c_void_p]),
     "xpt_flow_warp": (C.c_int, [C.c_void_p, C.POINTER(XptFrames), C.POINTER(PtrArray), C.POINTER(PtrArray),
                                 C.POINTER(PtrArray), C.c_void_p]),
     "xpt_flow_warp_backward": (C.c_int, [C.c_void_p, C.POINTER(XptFrames), C.POINTER(PtrArray), C.POINTER(PtrArray),

@@ -327,6 +327,22 @@ class Plan:
             C.byref(ptr_array([t.data_ptr() for t in d_synth])) if want_grad else None, self.stream()))
         return loss, d_synth, (target, synth_ms, warped)
 
+    def photometric_cmb_pair_loss(self, synth_ms, warped, target, grad_l1=1.0, grad_ssim=1.0, want_grad=False):
+        """xpt_photometric_cmb_pair_loss: cmbL1 + cmbSSIM of one eye in ONE launch."""
+        synth_ms = self._level_list(synth_ms, "synth_target_ms", self.N * 3)
+        warped = _dense(warped, "warped_target_ms[0]")
+        if warped.dim() != 5 or warped.shape[0] != self.B or warped.shape[1] != self.N or warped.shape[4] != 3:
+            raise WrongInputException(f"warped_target_ms[0]: expected [{self.B},{self.N},h,w,3], got {tuple(warped.shape)}")
+        target = _frame_view(target, "target", 1)
+        loss = torch.empty((2, self.B), dtype=torch.float32, device=self.device)
+        d_synth = self._empty_levels((self.N,), 3) if want_grad else None
+        _cabi.check(self._lib.xpt_photometric_cmb_pair_loss(
+            self.handle, C.byref(ptr_array([t.data_ptr() for t in synth_ms])), warped.data_ptr(),
+            int(warped.shape[2]), int(warped.shape[3]), target.data_ptr(), target.stride(0), loss[0].data_ptr(),
+            loss[1].data_ptr(), float(grad_l1), float(grad_ssim),
+            C.byref(ptr_array([t.data_ptr() for t in d_synth])) if want_grad else None, self.stream()))
+        return loss, d_synth
+
     def flow_warp(self, source, flow_ms, want_mask=False):
         """xpt_flow_warp (FlowWarpMultiScale.__call__); the plan's scales are the flow scales."""
         source = _frame_view(source, "source", 2)

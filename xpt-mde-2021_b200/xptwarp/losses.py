@@ -134,22 +134,30 @@ class _PhotoMinFn(torch.autograd.Function):
         return (None, None, None, None, None, *_scale_by_snippet(g, ctx.saved_tensors))
 
 
-class _PhotoMinPairFn(torch.autograd.Function):
-    """The "L1" and the "SSIM" min-over-sources loss of one loss set (moaL1 + moaSSIM, md2L1 + md2SSIM) in ONE launch
-    (xpt_photometric_min_pair_loss).  Returns their weighted contribution to the total loss and the two unweighted means;
-    the gradient of the contribution is formed by the same launch (the weights are known here, as in _TotalLossFn) and the
-    backward applies the upstream scalar to all stored gradients in one launch of the library."""
+class _PhotoPairFn(torch.autograd.Function):
+    """The "L1" and the "SSIM" loss object of one loss set (moaL1 + moaSSIM, md2L1 + md2SSIM: xpt_photometric_min_pair_loss;
+    cmbL1 + cmbSSIM: xpt_photometric_cmb_pair_loss) in ONE launch.  Returns their weighted contribution to the total loss
+    and the two unweighted means; the gradient of the contribution is formed by the same launch (the weights are known
+    here, as in _TotalLossFn) and the backward applies the upstream scalar to all stored gradients in one launch of the
+    library.  `extra`: the stereo syntheses (MoA), none (MonoDepth2) or the flow-warped view (Combined; no gradient)."""
 
     @staticmethod
-    def forward(ctx, plan, S, have_stereo, w_l1, w_ssim, batch_size, target, *ts):
-        synth_ms = ts[:S]
-        stereo_ms = ts[S:] if have_stereo else None
+    def forward(ctx, plan, kind, S, w_l1, w_ssim, batch_size, target, *ts):
+        synth_ms, extra = ts[:S], ts[S:]
         want = any(ctx.needs_input_grad[7:])
-        loss2, d_synth, d_stereo = plan.photometric_min_pair_loss(synth_ms, stereo_ms, target, w_l1 / batch_size,
-                                                                  w_ssim / batch_size, want_grad=want)
-        ctx.want = want
+        c1, c2 = w_l1 / batch_size, w_ssim / batch_size
+        if kind == "cmb":
+            loss2, d_synth = plan.photometric_cmb_pair_loss(synth_ms, extra[0], target, c1, c2, want_grad=want)
+            grads = list(d_synth) + [None] if want else None
+            n_saved = S
+        else:
+            loss2, d_synth, d_stereo = plan.photometric_min_pair_loss(synth_ms, extra if extra else None, target, c1, c2,
+                                                                      want_grad=want)
+            grads = list(d_synth) + (list(d_stereo) if extra else []) if want else None
+            n_saved = len(grads) if want else 0
+        ctx.want, ctx.n_saved, ctx.n_in = want, n_saved, len(ts)
         if want:
-            ctx.save_for_backward(*d_synth, *(d_stereo if have_stereo else ()))
+            ctx.save_for_backward(*[g for g in grads if g is not None])
         means = loss2.sum(dim=1) / batch_size                       # tf.nn.compute_average_loss, per loss
         ctx.mark_non_differentiable(means)
         return means[0] * w_l1 + means[1] * w_ssim, means
@@ -158,7 +166,8 @@ class _PhotoMinPairFn(torch.autograd.Function):
     def backward(ctx, g, _g_means):
         if not ctx.want:
             raise RuntimeError("the loss pair was evaluated without gradients")
-        return (None, None, None, None, None, None, None, *scale_tensors(list(ctx.saved_tensors), g))
+        scaled = scale_tensors(list(ctx.saved_tensors), g)
+        return (None, None, None, None, None, None, None, *scaled, *([None] * (ctx.n_in - ctx.n_saved)))
 
 
 class _PhotoCmbFn(torch.autograd.Function):
@@ -276,7 +285,7 @@ class CombinedLossMultiScale(PhotometricLoss):
     """reference losses.py:235-279: the static (depth + pose) photometric term of every scale, kept only where it
     is smaller than the optical-flow term of warped_target_ms[0]; both compared at the original resolution."""
 
-    def __call__(self, features, predictions, augm_data):
+    def _inputs(self, augm_data):
         synth_ms = [as_torch(t) for t in augm_data["synth_target_ms" + self.key_suffix]]
         warped = as_torch(augm_data["warped_target_ms" + self.key_suffix][0])
         target = as_torch(augm_data["target" + self.key_suffix])
@@ -284,7 +293,11 @@ class CombinedLossMultiScale(PhotometricLoss):
         B, N, H, W = synth_ms[0].shape[0], synth_ms[0].shape[1], target.shape[1], target.shape[2]
         scales = [H // s.shape[2] for s in synth_ms]
         plan = get_plan(target.device.index or 0, B, N, H, W, scales, _scale_weights_list(self.scale_weights))
-        return _PhotoCmbFn.apply(plan, self._METHODS[self.method], target, warped.detach(), *synth_ms)
+        return plan, target, synth_ms, [warped.detach()]
+
+    def __call__(self, features, predictions, augm_data):
+        plan, target, synth_ms, (warped,) = self._inputs(augm_data)
+        return _PhotoCmbFn.apply(plan, self._METHODS[self.method], target, warped, *synth_ms)
 
 
 class FlowWarpLossMultiScale(PhotometricLoss):
@@ -393,11 +406,11 @@ class TotalLoss:
         return False
 
     def _min_pairs(self):
-        """{L1 name: SSIM name, SSIM name: None} for every stock (moa|md2)L1 + (moa|md2)SSIM pair of one eye with the
-        same scale weights: the pair shares one launch (xpt_photometric_min_pair_loss)"""
+        """{L1 name: SSIM name, SSIM name: None} for every stock (moa|md2|cmb)L1 + (moa|md2|cmb)SSIM pair of one eye with
+        the same scale weights: the pair shares one launch (xpt_photometric_min_pair_loss / xpt_photometric_cmb_pair_loss)"""
         pairs = {}
         for sfx in ("", "_R"):
-            for base, cls in (("moa", MoALossMultiScale), ("md2", MonoDepth2LossMultiScale)):
+            for base, cls in (("moa", MoALossMultiScale), ("md2", MonoDepth2LossMultiScale), ("cmb", CombinedLossMultiScale)):
                 n1, n2 = base + "L1" + sfx, base + "SSIM" + sfx
                 o1, o2 = self.loss_objects.get(n1), self.loss_objects.get(n2)
                 if (type(o1) is cls and type(o2) is cls and o1.method == "L1" and o2.method == "SSIM"
@@ -442,12 +455,12 @@ class TotalLoss:
             if loss_name in pairs:
                 if pairs[loss_name] is None:                          # the SSIM half: evaluated with its L1 partner
                     continue
-                # moaL1 + moaSSIM (md2L1 + md2SSIM) of one eye: ONE launch for both loss objects
+                # moaL1 + moaSSIM (md2L1 + md2SSIM, cmbL1 + cmbSSIM) of one eye: ONE launch for both loss objects
                 ssim_name, obj = pairs[loss_name], self.loss_objects[loss_name]
-                plan, target, synth_ms, stereo_ms = obj._inputs(augm_data)
-                part, means = _PhotoMinPairFn.apply(plan, plan.S, stereo_ms is not None, float(self.loss_weights[loss_name]),
-                                                    float(self.loss_weights[ssim_name]), float(self.batch_size), target,
-                                                    *synth_ms, *(stereo_ms or ()))
+                plan, target, synth_ms, extra = obj._inputs(augm_data)
+                part, means = _PhotoPairFn.apply(plan, "cmb" if type(obj) is CombinedLossMultiScale else "min", plan.S,
+                                                 float(self.loss_weights[loss_name]), float(self.loss_weights[ssim_name]),
+                                                 float(self.batch_size), target, *synth_ms, *(extra or ()))
                 losses.append(part)
                 loss_by_type[loss_name], loss_by_type[ssim_name] = means[0], means[1]
                 continue
