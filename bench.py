@@ -426,7 +426,7 @@ def main():
         # levels s > 1 ((gamma - 1) x 12) per full-resolution target pixel
         pyr_bytes = 60 + N_SRC * GAMMA * 16 + (GAMMA - 1) * 12
         pach = px_rank * pyr_bytes / (pyr_ms * 1e-3) / 1e9
-        roofline["secondary"] = {"bound": "hbm", "kernel": "k_pyramid_tma", "achieved": pach, "peak": peak, "unit": "GB/s",
+        roofline["secondary"] = {"bound": "hbm", "kernel": "k_pyramid_tiled" if os.environ.get("XPT_PYRAMID") == "tiled" else "k_pyramid_tma", "achieved": pach, "peak": peak, "unit": "GB/s",
                                  "frac": pach / peak, "kernel_ms": pyr_ms, "bytes_per_pixel": pyr_bytes,
                                  "algorithmic_bytes_per_launch": px_rank * pyr_bytes}
     step_model = {"bytes_per_pixel": BYTES_SURVEY_STEP,

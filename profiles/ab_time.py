@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "xpt-mde-2021_b2
 import torch, xptwarp
 from oracle import xpt_oracle as orc
 
-SH = {"cfg2": (8, 128, 384), "cfg3": (16, 256, 832), "cfg4": (64, 128, 384)}
+SH = {"cfg2": (8, 128, 384), "cfg3": (16, 256, 832), "cfg4": (64, 128, 384), "cfg5": (128, 384, 1280)}
 for name in sys.argv[1:] or ["cfg2"]:
     B, H, W = SH[name]
     feats, preds = orc.make_inputs(B, H, W, seed=5)
@@ -17,8 +17,9 @@ for name in sys.argv[1:] or ["cfg2"]:
     plan = xptwarp.get_plan(0, B, 4, H, W, [1, 2, 4, 8], [1, 1, 1, 1], 0.5, 0.5, 1.0, B)
     call = plan.bind_total_loss(img[:, :-1], img[:, -1], f["intrinsic"], p["depth_ms"], p["disp_ms"], p["pose"],
                                 want_grad=True, want_synth=False, want_mask=False, want_source_grad=False)
-    n = 100 if B * H * W < 1e6 else 40
-    for _ in range(2000 if B * H * W < 1e6 else 300): call.run()
+    big = B * H * W > 2e7
+    n = 100 if B * H * W < 1e6 else (10 if big else 40)
+    for _ in range(2000 if B * H * W < 1e6 else (20 if big else 300)): call.run()
     torch.cuda.synchronize()
     res = []
     for rep in range(3):

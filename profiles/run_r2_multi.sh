@@ -14,4 +14,4 @@ run cfg4 29512 --steps 200 --warmup 20 --workload cfg4
 run cfg5_srcgrad 29513 --steps 20 --warmup 5 --workload cfg5 --source-grad
 timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29514 \
   bench.py --gpus $N --impl reference --steps 3 --warmup 1 2>>gpurun_out/bench_n${N}_ref.err | tail -1 | tee gpurun_out/bench_n${N}_reference.json
-tail -3 gpurun_out/bench_n${N}_*.err
+for e in gpurun_out/bench_n${N}_*.err; do tail -n 3 "$e"; done

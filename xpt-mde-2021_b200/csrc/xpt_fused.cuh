@@ -27,6 +27,11 @@
 #ifndef XPT_YPIPE
 #define XPT_YPIPE 2
 #endif
+// XPT_GRID_TILE_MAJOR 1: grid = (tiles, snippets) -- a snippet's tiles are consecutive CTAs, so the halo rows a tile shares
+// with its vertical neighbour are still in L2 whatever the batch size (A/B against grid = (snippets, tiles))
+#ifndef XPT_GRID_TILE_MAJOR
+#define XPT_GRID_TILE_MAJOR 1
+#endif
 #if XPT_EXP & 1
 #define XPT_SYNC() ((void)0)
 #else
@@ -233,11 +238,18 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
   float* const sI = smem + SM::sI;
 
   // ---- which tile -------------------------------------------------------------
-  // grid = (snippets, tiles): all snippets' tile 0 first, ... the cheap small-level tiles last, so that the
-  // final partial wave is filled with short CTAs.  (A persistent grid drawing tiles from a ticket was measured in
+  // grid = (tiles, snippets): a snippet's tiles are consecutive CTAs (large levels first), so the halo rows a tile shares
+  // with its vertical neighbour are still in L2 whatever the batch size -- at config 5 (B = 128) the snippet-major order
+  // of round 1 re-read them from HBM (12.9 GB DRAM traffic for 6.4 GB algorithmic; -4.5 % kernel time with this order,
+  // +-0 at config 2 / 3: profiles/r02_ab_grid_order.txt).  (A persistent grid drawing tiles from a ticket was measured in
   // round 2: +2 % time at config 2 and config 3 -- the ticket's two barriers per tile cost more than the tail.)
+#if XPT_GRID_TILE_MAJOR
+  int t = blockIdx.x;
+  const int bl = blockIdx.y;               // K record of this snippet inside the constant bank
+#else
   int t = blockIdx.y;
   const int bl = blockIdx.x;               // K record of this snippet inside the constant bank
+#endif
   if (bl < a.k_rec0) return;
   const int b = a.b_off + bl;
   int l = 0;

@@ -471,9 +471,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_min_strip(const __grid_constan
       if constexpr (GRAD) adjoint(m);
     }
     reduce_loss(lacc);
-    return;
-  }
-
+  } else {
   // ---- sweep 1: minimum, tie count and first winner per (pixel, channel) --------------------------------------
   for (int m = 0; m < nsrc; ++m) {
     upsample(m);
@@ -505,6 +503,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_min_strip(const __grid_constan
       __syncthreads();
       adjoint(m);
     }
+  }
   }
 }
 

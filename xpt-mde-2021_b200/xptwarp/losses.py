@@ -4,6 +4,7 @@ loss_util.py through the same kernels)."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -484,7 +485,7 @@ class TotalLoss:
     @staticmethod
     def _same_launch(groups):
         """both eyes can share a launch: same weights, same shapes, disparities given for both or for neither"""
-        if len(groups) != 2:
+        if len(groups) != 2 or os.environ.get("XPT_EYES") == "separate":      # (A/B switch: one launch per eye, no torch.cat)
             return False
         (img_l, K_l, dep_l, dsp_l, pose_l, w_l), (img_r, K_r, dep_r, dsp_r, pose_r, w_r) = groups[""], groups["_R"]
         return (w_l == w_r and img_l.shape == img_r.shape and pose_l.shape == pose_r.shape
