@@ -93,7 +93,7 @@ typedef struct {
 /* xpt_total_loss runs its training steps (gradients wanted, no synthesis tensors, no dL/dsource, <= 4 sources) on
  * the streaming strip kernel (k_strip: warp-specialised roles marching down 64-column strips, no halo re-warp,
  * per-ctx geometry from global memory) instead of the tile kernel (k_fused).  Same results to summation order.
- * Opt-in: on B200 it reaches the tile kernel's speed but does not beat it yet.              */
+ * Opt-in: on B200 it is 13-24 % slower than the tile kernel; kept for A/B.                   */
 #define XPT_FLAG_STRIP 8u
 /* multi-rank data parallelism (reference distributer.py:93-110 ReplicaOutputIntegrator): xpt_total_loss ends with an
  * in-place ncclAllReduce(sum) of out->losses[4] over the communicator bound by xpt_comm_init / xpt_comm_attach,

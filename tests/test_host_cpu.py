@@ -240,3 +240,23 @@ def test_fused_path_is_gated_on_the_loss_objects(built):
     assert not swapped._fused_ok(preds, {})
     wrong_eye = lm.TotalLoss({"L1_R": lm.PhotometricLossMultiScale("L1", sw)}, {"L1_R": 1.0}, True, 2)
     assert not wrong_eye._fused_ok(preds, {})
+
+
+def test_loss_pairs_share_a_launch_only_when_stock(built):
+    """TotalLoss._min_pairs: (moa|md2|cmb)L1 + ...SSIM of ONE eye, stock objects with equal scale weights -> one pair launch
+    (xpt_photometric_min_pair_loss / xpt_photometric_cmb_pair_loss); anything else keeps the reference's loop."""
+    import xptwarp
+    rig = {"image": 1, "intrinsic": 1, "image_R": 1, "intrinsic_R": 1, "stereo_T_LR": 1}
+    lw = {"moaL1": 8.5, "moaL1_R": 8.5, "moaSSIM": 0.15, "moaSSIM_R": 0.15, "md2L1": 1.0, "cmbL1_R": 1.0, "cmbSSIM_R": 0.5,
+          "smoothe": 1.0, "stereoPose": 1.0}
+    tl = xptwarp.loss_factory(rig, lw, np.ones(4), stereo=True, batch_size=4)
+    pairs = tl._min_pairs()
+    assert pairs == {"moaL1": "moaSSIM", "moaSSIM": None, "moaL1_R": "moaSSIM_R", "moaSSIM_R": None,
+                     "cmbL1_R": "cmbSSIM_R", "cmbSSIM_R": None}           # md2L1 has no SSIM partner
+    # different scale weights, a swapped method, a subclass or a foreign object under the name: no pair
+    tl.loss_objects["moaSSIM"].scale_weights = np.array([1, 2, 3, 4.0])
+    assert "moaL1" not in tl._min_pairs() and "moaL1_R" in tl._min_pairs()
+    tl.loss_objects["moaSSIM_R"] = xptwarp.MonoDepth2LossMultiScale("SSIM", np.ones(4), "_R")
+    assert "moaL1_R" not in tl._min_pairs()
+    tl.loss_objects["cmbL1_R"] = xptwarp.CombinedLossMultiScale("SSIM", np.ones(4), "_R")
+    assert "cmbL1_R" not in tl._min_pairs()

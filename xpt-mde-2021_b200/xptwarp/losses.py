@@ -484,8 +484,11 @@ class TotalLoss:
 
     @staticmethod
     def _same_launch(groups):
-        """both eyes can share a launch: same weights, same shapes, disparities given for both or for neither"""
-        if len(groups) != 2 or os.environ.get("XPT_EYES") == "separate":      # (A/B switch: one launch per eye, no torch.cat)
+        """both eyes COULD share a launch (same weights, same shapes, disparities given for both or for neither) -- but
+        only by concatenating every input of the two eyes with torch.cat first.  Measured on the stereo LOSS_RIGID_T1 step at
+        config-2 size, replayed as a CUDA graph: 0.43 ms with the shared launch + cat, 0.39 ms with one launch per eye and no
+        copy (profiles/r02_stereo_t1_eyes.txt), so one launch per eye is the default and XPT_EYES=cat keeps the A/B."""
+        if len(groups) != 2 or os.environ.get("XPT_EYES") != "cat":
             return False
         (img_l, K_l, dep_l, dsp_l, pose_l, w_l), (img_r, K_r, dep_r, dsp_r, pose_r, w_r) = groups[""], groups["_R"]
         return (w_l == w_r and img_l.shape == img_r.shape and pose_l.shape == pose_r.shape
@@ -551,14 +554,15 @@ class TotalLoss:
         if "stereoL1" in w or "stereoSSIM" in w:
             # StereoDepthLoss (losses.py:443-478) over the two syntheses of losses.py:105-140: the fused kernel with
             # ONE source frame (the other eye's target), the rig transform as the pose and -- like the reference --
-            # the LEFT intrinsics for both directions.  Both directions share one launch (the loss is their sum).
+            # the LEFT intrinsics for both directions.  One launch per direction (the loss is their sum): no copies.
             if not stereo or "stereo_T_LR" not in features:
                 raise WrongInputException("stereoL1 / stereoSSIM need TotalLoss(stereo=True), image5d_R and stereo_T_LR")
             T = as_torch(features["stereo_T_LR"])
             require_cuda_f32(stereo_T_LR=T)
             (img_l, K_l, depth_l), (img_r, _, depth_r) = eyes[""], eyes["_R"]
             ws = (w.get("stereoL1", 0.0), w.get("stereoSSIM", 0.0), 0.0)
-            if img_l.shape == img_r.shape and all(a.shape == b.shape for a, b in zip(depth_l, depth_r)):
+            if (os.environ.get("XPT_EYES") == "cat" and img_l.shape == img_r.shape
+                    and all(a.shape == b.shape for a, b in zip(depth_l, depth_r))):       # (A/B: see _same_launch)
                 rig = torch.cat([pose_matr2rvec_batch(T.unsqueeze(1), invert=True), pose_matr2rvec_batch(T.unsqueeze(1))], dim=0)
                 tgt = torch.cat([img_l[:, -1], img_r[:, -1]], dim=0)         # [2B,H,W,3]: left targets, then right targets
                 src = torch.cat([img_r[:, -1:], img_l[:, -1:]], dim=0)       # the other eye's frame as the single source
