@@ -295,6 +295,16 @@ XPT_API int xpt_total_loss(xpt_ctx* ctx, const xpt_frames* frames,
 XPT_API int xpt_total_loss_host(xpt_ctx* ctx, const xpt_frames* frames,
                         const float* const depth_ms[], const float* const disp_ms[],
                         const float* pose, const xpt_loss_outputs* out, void* stream);
+/* The same call split in two, so that a training loop can keep TWO steps in flight (two contexts, two streams, two sets
+ * of pinned buffers): while one ctx computes and drains step i, the other already copies in step i+1 -- what the
+ * reference's tf.data prefetch (tfrecords/tfrecord_reader.py) does for its input pipeline.  _begin enqueues the whole
+ * call (one graph launch once the ctx is warm and every buffer is pinned) and returns; _end waits for THAT call only (an
+ * event, not the stream) and finishes out->losses.  The buffers passed to _begin must stay untouched until _end returns.
+ * Calls that cannot be replayed as a graph (cold ctx, pageable buffers) complete inside _begin.  One call in flight per ctx. */
+XPT_API int xpt_total_loss_host_begin(xpt_ctx* ctx, const xpt_frames* frames,
+                              const float* const depth_ms[], const float* const disp_ms[],
+                              const float* pose, const xpt_loss_outputs* out, void* stream);
+XPT_API int xpt_total_loss_host_end(xpt_ctx* ctx);
 
 /* Device timing of the dominant kernel (the fused photometric tile kernel): after
  * xpt_profile_begin, each of the next `max_records` eager launches of that kernel is bracketed

@@ -472,6 +472,66 @@ def test_host_pipeline_full_size(xw):
             assert torch.equal(d_disp[s], r["d_disp_ms"][s].cpu().reshape(d_disp[s].shape)), (call, s)
 
 
+def test_host_calls_two_in_flight(xw):
+    """xpt_total_loss_host_begin / _end: two steps in flight on two contexts, two streams and two sets of pinned buffers
+    (different inputs) -- every step's losses and gradients are bit-identical to the device entry point's, across six
+    alternating steps; a second _begin without _end and an _end without _begin are refused."""
+    import ctypes as C
+    from xptwarp import _cabi
+    from xptwarp.engine import Plan
+    from oracle import xpt_oracle as orc
+    B, H, W = 4, 64, 128
+    lw, sw = orc.LOSS_RIGID_T1, orc.SCALE_WEIGHT_T1
+    pin = lambda t: t.contiguous().pin_memory()
+    sides = []
+    for k in range(2):
+        feats, preds = orc.make_inputs(B, H, W, seed=500 + k)
+        f, p = _to_cuda(feats, preds)
+        ref = _run_total(_plan_for(xw, f, p, lw, sw, B), f, p, want_grad=True)
+        ref = {"losses": ref["losses"].cpu().clone(), "d_pose": ref["d_pose"].cpu().clone(),
+               "d_depth_ms": [t.cpu().clone() for t in ref["d_depth_ms"]]}
+        plan = Plan(0, B, 4, H, W, [1, 2, 4, 8], list(sw), lw["L1"], lw["SSIM"], lw["smoothe"], B, 0)
+        img, K, pose = pin(feats["image5d"]), pin(feats["intrinsic"]), pin(preds["pose"])
+        depth_h, disp_h = [pin(d) for d in preds["depth_ms"]], [pin(d) for d in preds["disp_ms"]]
+        fr = _cabi.XptFrames()
+        fr.source, fr.source_batch_stride, fr.source_frame_stride = img.data_ptr(), img.stride(0), img.stride(1)
+        fr.target, fr.target_batch_stride = img.data_ptr() + 4 * img.stride(1) * 4, img.stride(0)
+        fr.intrinsic = K.data_ptr()
+        out = _cabi.XptLossOutputs()
+        losses, d_pose = pin(torch.zeros(4)), pin(torch.zeros(B, 4, 6))
+        d_depth = [pin(torch.zeros_like(d)) for d in preds["depth_ms"]]
+        d_disp = [pin(torch.zeros_like(d)) for d in preds["disp_ms"]]
+        out.losses, out.d_pose, out.grad_scale = losses.data_ptr(), d_pose.data_ptr(), 1.0
+        for s in range(4):
+            out.d_depth_ms[s], out.d_disp_ms[s] = d_depth[s].data_ptr(), d_disp[s].data_ptr()
+        sides.append(dict(plan=plan, fr=fr, out=out, dptr=_cabi.ptr_array([d.data_ptr() for d in depth_h]),
+                          sptr=_cabi.ptr_array([d.data_ptr() for d in disp_h]), pose=pose, stream=torch.cuda.Stream(), ref=ref,
+                          losses=losses, d_pose=d_pose, d_depth=d_depth, keep=(img, K, depth_h, disp_h, d_disp)))
+
+    def begin(q):
+        return q["plan"]._lib.xpt_total_loss_host_begin(q["plan"].handle, C.byref(q["fr"]), C.byref(q["dptr"]), C.byref(q["sptr"]),
+                                                        q["pose"].data_ptr(), C.byref(q["out"]), C.c_void_p(q["stream"].cuda_stream))
+
+    def end_and_check(q, tag):
+        _cabi.check(q["plan"]._lib.xpt_total_loss_host_end(q["plan"].handle))
+        assert relerr(q["losses"].numpy(), q["ref"]["losses"].numpy()) < 1e-6, tag
+        assert torch.equal(q["d_pose"], q["ref"]["d_pose"]), tag
+        for s in range(4):
+            assert torch.equal(q["d_depth"][s], q["ref"]["d_depth_ms"][s].reshape(q["d_depth"][s].shape)), (tag, s)
+        for t in (q["losses"], q["d_pose"], *q["d_depth"]):
+            t.zero_()
+    for q in sides:                       # warm each ctx (the third call is captured as a graph)
+        for _ in range(3):
+            _cabi.check(begin(q)); end_and_check(q, "warm")
+    _cabi.check(begin(sides[0]))
+    assert begin(sides[0]) == _cabi.XPT_BAD_ARGUMENT               # one call in flight per ctx
+    for i in range(1, 6):
+        _cabi.check(begin(sides[i % 2]))
+        end_and_check(sides[(i - 1) % 2], i)
+    end_and_check(sides[1], "last")
+    assert sides[1]["plan"]._lib.xpt_total_loss_host_end(sides[1]["plan"].handle) == _cabi.XPT_BAD_ARGUMENT
+
+
 def test_dlpack_only_producer_and_errors(xw):
     class OnlyDLPack:            # stands in for a TF/CuPy tensor: nothing but the DLPack protocol
         def __init__(self, t):

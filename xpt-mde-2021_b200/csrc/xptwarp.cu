@@ -121,6 +121,10 @@ struct xpt_ctx {
   bool host_warm;
   cudaEvent_t ev_in[kMaxChunks], ev_done[kMaxChunks];
   float* h_losses;              // pinned [4][4]: a pageable destination would block the host per chunk
+  bool host_pending = false, host_pending_async = false;   // xpt_total_loss_host_begin without its _end yet
+  int host_pending_nc = 0;
+  float* host_pending_losses = nullptr;
+  cudaEvent_t host_done_ev = nullptr;
   // per-launch device timing of the dominant kernel (xpt_profile_*)
   std::vector<cudaEvent_t>* prof_events;
   int prof_count;
@@ -1052,6 +1056,7 @@ void xpt_destroy(xpt_ctx* ctx) {
   }
   if (ctx->child) xpt_destroy(ctx->child);
   if (ctx->h_losses) cudaFreeHost(ctx->h_losses);
+  if (ctx->host_done_ev) cudaEventDestroy(ctx->host_done_ev);
   if (ctx->s_in) {
     cudaStreamDestroy(ctx->s_in); cudaStreamDestroy(ctx->s_out); cudaStreamDestroy(ctx->s_in2); cudaEventDestroy(ctx->ev_small);
     cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
@@ -2128,9 +2133,10 @@ static bool is_pinned(const void* p) {
   return at.type == cudaMemoryTypeHost;
 }
 
-int xpt_total_loss_host(xpt_ctx* ctx, const xpt_frames* frames, const float* const depth_ms[],
-                        const float* const disp_ms[], const float* pose, const xpt_loss_outputs* out, void* stream) {
+int xpt_total_loss_host_begin(xpt_ctx* ctx, const xpt_frames* frames, const float* const depth_ms[],
+                              const float* const disp_ms[], const float* pose, const xpt_loss_outputs* out, void* stream) {
   if (!ctx || !frames || !pose || !out || !depth_ms) return fail(XPT_BAD_ARGUMENT, "xpt_total_loss_host: NULL argument");
+  if (ctx->host_pending) return fail(XPT_BAD_ARGUMENT, "xpt_total_loss_host_begin: the previous call on this ctx was not ended");
   cudaStream_t st = (cudaStream_t)stream;
   XPT_CUDA(cudaSetDevice(ctx->cfg.device));
   int nc = 1, rc = XPT_OK;
@@ -2190,15 +2196,38 @@ int xpt_total_loss_host(xpt_ctx* ctx, const xpt_frames* frames, const float* con
       ctx->host_graphs->push_back({key, exec, nc});      // `launches` carries the chunk count here
     }
     XPT_CUDA(cudaGraphLaunch(exec, st));
-    XPT_CUDA(cudaStreamSynchronize(st));
+    // the replayed call is left in flight: xpt_total_loss_host_end waits for this event (not for the whole stream)
+    if (!ctx->host_done_ev) XPT_CUDA(cudaEventCreateWithFlags(&ctx->host_done_ev, cudaEventDisableTiming));
+    XPT_CUDA(cudaEventRecord(ctx->host_done_ev, st));
+    ctx->host_pending_async = true;
+  }
+  ctx->host_pending = true;
+  ctx->host_pending_nc = nc;
+  ctx->host_pending_losses = out->losses;
+  return XPT_OK;
+}
+
+int xpt_total_loss_host_end(xpt_ctx* ctx) {
+  if (!ctx) return fail(XPT_BAD_ARGUMENT, "xpt_total_loss_host_end: ctx is NULL");
+  if (!ctx->host_pending) return fail(XPT_BAD_ARGUMENT, "xpt_total_loss_host_end: no call in flight on this ctx");
+  ctx->host_pending = false;
+  if (ctx->host_pending_async) {
+    ctx->host_pending_async = false;
+    XPT_CUDA(cudaEventSynchronize(ctx->host_done_ev));
   }
   float (*h_losses)[4] = reinterpret_cast<float (*)[4]>(ctx->h_losses);
   for (int j = 0; j < 4; ++j) {
     double v = 0.0;
-    for (int k = 0; k < nc; ++k) v += (double)h_losses[k][j];
-    out->losses[j] = (float)v;
+    for (int k = 0; k < ctx->host_pending_nc; ++k) v += (double)h_losses[k][j];
+    ctx->host_pending_losses[j] = (float)v;
   }
   return XPT_OK;
+}
+
+int xpt_total_loss_host(xpt_ctx* ctx, const xpt_frames* frames, const float* const depth_ms[],
+                        const float* const disp_ms[], const float* pose, const xpt_loss_outputs* out, void* stream) {
+  XPT_TRY(xpt_total_loss_host_begin(ctx, frames, depth_ms, disp_ms, pose, out, stream));
+  return xpt_total_loss_host_end(ctx);
 }
 
 }  // extern "C"

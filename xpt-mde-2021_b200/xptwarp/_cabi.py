@@ -97,6 +97,9 @@ SYMBOLS = {
                                  C.c_void_p, C.POINTER(XptLossOutputs), C.c_void_p]),
     "xpt_total_loss_host": (C.c_int, [C.c_void_p, C.POINTER(XptFrames), C.POINTER(PtrArray), C.POINTER(PtrArray),
                                       C.c_void_p, C.POINTER(XptLossOutputs), C.c_void_p]),
+    "xpt_total_loss_host_begin": (C.c_int, [C.c_void_p, C.POINTER(XptFrames), C.POINTER(PtrArray), C.POINTER(PtrArray),
+                                      C.c_void_p, C.POINTER(XptLossOutputs), C.c_void_p]),
+    "xpt_total_loss_host_end": (C.c_int, [C.c_void_p]),
     "xpt_profile_begin": (C.c_int, [C.c_void_p, C.c_int]),
     "xpt_profile_select": (C.c_int, [C.c_void_p, C.c_int]),
     "xpt_profile_end": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
