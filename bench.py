@@ -232,6 +232,7 @@ def main():
                          "large poses (about half of the samples leave the image)")
     ap.add_argument("--strip", action="store_true", help="the streaming strip kernel (XPT_FLAG_STRIP) instead of the tile kernel (A/B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-depth", type=int, default=2, help="host-buffer steps kept in flight by the e2e leg (1 = synchronous calls)")
     ap.add_argument("--cpu-steps", type=int, default=10)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -441,9 +442,10 @@ def main():
     # synchronous xpt_total_loss_host) is reported next to it as e2e.sync_value.
     import ctypes as C
     from xptwarp.engine import Plan
-    plan_b = Plan(local_rank, B, N_SRC, H, W, [1, 2, 4, 8], sw, lw["L1"], lw["SSIM"], lw["smoothe"], global_batch,
-                  flags & ~_cabi.XPT_FLAG_ALLREDUCE)
-    stream_b = torch.cuda.Stream(device)
+    depth = max(1, args.e2e_depth)
+    extra_plans = [Plan(local_rank, B, N_SRC, H, W, [1, 2, 4, 8], sw, lw["L1"], lw["SSIM"], lw["smoothe"], global_batch,
+                        flags & ~_cabi.XPT_FLAG_ALLREDUCE) for _ in range(depth - 1)]
+    extra_streams = [torch.cuda.Stream(device) for _ in range(depth - 1)]
 
     def host_side(pl, fcpu, pcpu, st):
         himg = fcpu["image5d"].contiguous().pin_memory()
@@ -466,7 +468,8 @@ def main():
         nout = 4 * (4 + hdpose.numel() + sum(d.numel() for d in hdd) + sum(d.numel() for d in hds))
         return {"plan": pl, "fr": fr, "o": o, "dptr": dptr, "sptr": sptr, "hpose": hpose, "hlosses": hlosses, "stream": st,
                 "keep": (himg, hK, hdepth, hdisp, hdpose, hdd, hds), "h2d": nin, "d2h": nout}
-    sides = [host_side(plan, *sets_cpu[0], stream), host_side(plan_b, *sets_cpu[1 % len(sets_cpu)], stream_b.cuda_stream)]
+    sides = [host_side(plan, *sets_cpu[0], stream)] + [host_side(pl, *sets_cpu[(k + 1) % len(sets_cpu)], st.cuda_stream)
+                                                       for k, (pl, st) in enumerate(zip(extra_plans, extra_streams))]
     h2d, d2h = sides[0]["h2d"], sides[0]["d2h"]
     dev_losses = torch.zeros(4, device=device)
 
@@ -485,8 +488,8 @@ def main():
         if dist is not None:             # the host entry point's losses are rank-local: sum the 4 floats over the ranks
             dev_losses.copy_(q["hlosses"], non_blocking=True)
             plan.allreduce([dev_losses])
-    for i in range(40):                  # a call is captured as a graph on its third use; then let the link settle
-        host_begin(i % 2); host_end(i % 2)
+    for i in range(20 * depth):          # a call is captured as a graph on its third use; then let the link settle
+        host_begin(i % depth); host_end(i % depth)
     barrier()
     n_e2e = max(10, min(args.steps, 100))
     t0 = time.perf_counter()
@@ -496,11 +499,11 @@ def main():
     t_sync = (time.perf_counter() - t0) / n_e2e
     barrier()
     t0 = time.perf_counter()
-    host_begin(0)
-    for i in range(1, n_e2e):            # two steps in flight
-        host_begin(i % 2)
-        host_end((i - 1) % 2)
-    host_end((n_e2e - 1) % 2)
+    for i in range(n_e2e + depth - 1):   # `depth` steps in flight
+        if i < n_e2e:
+            host_begin(i % depth)
+        if i >= depth - 1:
+            host_end((i - depth + 1) % depth)
     torch.cuda.synchronize()
     t_e2e = torch.tensor([(time.perf_counter() - t0) / n_e2e, t_sync], dtype=torch.float64, device=device)
     if dist is not None:
@@ -544,8 +547,8 @@ def main():
                                                   if (world > 1 and args.net_grad_mb > 0) else "")},
             "roofline": roofline, "step_model": step_model, "cpu_baseline": cpu, "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "in_flight": 2, "sync_value": e2e_sync,
-                    "note": "xpt_total_loss_host_begin/_end, two steps in flight (two contexts, streams and pinned buffer sets); "
+                    "in_flight": depth, "sync_value": e2e_sync,
+                    "note": f"xpt_total_loss_host_begin/_end, {depth} steps in flight (as many contexts, streams and pinned buffer sets); "
                             "sync_value = one synchronous xpt_total_loss_host call at a time"},
             "gpu_launches": launches_per_step * args.steps,
         }
