@@ -18,9 +18,21 @@
 //     value and tile reaches L2 (k_photo_min: 12 atomics per full-resolution pixel and source).  A level at full
 //     resolution owns its pixels: plain stores.
 #pragma once
+#include <cassert>
 #include <type_traits>
 #include "xpt_fused.cuh"
 #include "xpt_minloss.cuh"
+
+// XPT_MS_CHECK 1: device-side bounds assertions of every table-driven index (a checking build for the parity tests;
+// compute-sanitizer is not available on the pool)
+#ifndef XPT_MS_CHECK
+#define XPT_MS_CHECK 0
+#endif
+#if XPT_MS_CHECK
+#define XPT_MS_ASSERT(c) assert(c)
+#else
+#define XPT_MS_ASSERT(c) ((void)0)
+#endif
 
 namespace xpt {
 
@@ -192,6 +204,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_min_strip(const __grid_constan
             const float fx = FX[rx], fy = FY[ry];
             const float* r0 = low + (size_t)Y0[ry] * lw * 3;
             const float* r1 = low + (size_t)Y1[ry] * lw * 3;
+            XPT_MS_ASSERT(x0 >= 0 && x1 >= x0 && x1 < lw * 3 && Y0[ry] >= 0 && Y1[ry] >= Y0[ry]);
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
               const float tl = __ldg(r0 + x0 + c), tr = __ldg(r0 + x1 + c);
@@ -369,6 +382,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_min_strip(const __grid_constan
       else if (tid >= 64 && tid < 64 + FHt) ranges(tY0, tY1, ch, Y_lo + (tid - 64), rYa[tid - 64], rYb[tid - 64]);
       // (visible to the reduction passes behind the barriers of the first source)
     }
+    XPT_MS_ASSERT(FW >= 1 && (identity || FW <= kMSTPitch) && FHt >= 1 && FHt <= 16 && cw >= 1 && ch >= 1 && ch <= kFCH);
     inv_FW = 1.f / (float)FW; inv_chFW = 1.f / (float)(ch * FW); inv_FHFW = 1.f / (float)(FHt * FW);
   }
   auto adjoint = [&](int m) {
@@ -420,6 +434,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_min_strip(const __grid_constan
         const int c = (int)(((float)j + 0.5f) * inv_chFW), k = j - c * ch * FW;      // exact for these small integers
         const int r = (int)(((float)k + 0.5f) * inv_FW), Xi = k - r * FW;
         const int pa = rXa[Xi], pb = rXb[Xi];
+        XPT_MS_ASSERT(c >= 0 && c < 3 && r >= 0 && r < ch && Xi >= 0 && Xi < FW && (pa >> 8) < cw && (pb >> 8) < cw);
         const float* gr = sG + c * kFCentre + r * kFCP;
         float v = 0.f;
         for (int o = pa & 0xff; o <= (pa >> 8); ++o) v = fmaf(1.f - tFX[o + 2], gr[o], v);
@@ -432,6 +447,8 @@ __global__ void __launch_bounds__(kFThreads, 2) k_min_strip(const __grid_constan
         const int c = (int)(((float)j + 0.5f) * inv_FHFW), k = j - c * FHt * FW;
         const int Yi = (int)(((float)k + 0.5f) * inv_FW), Xi = k - Yi * FW;
         const int pa = rYa[Yi], pb = rYb[Yi];
+        XPT_MS_ASSERT(c >= 0 && c < 3 && Yi >= 0 && Yi < FHt && Xi >= 0 && Xi < FW && (pa >> 8) < ch && (pb >> 8) < ch);
+        XPT_MS_ASSERT(Y_lo + Yi < h && X_lo + Xi < w);
         const float* tc = sT + c * kFCH * kMSTPitch + Xi;
         float v = 0.f;
         for (int r = pa & 0xff; r <= (pa >> 8); ++r) v = fmaf(1.f - tFY[r + 2], tc[r * kMSTPitch], v);
