@@ -390,6 +390,97 @@ __global__ void __launch_bounds__(kPyrThreads, XPT_PYR_MINB) k_pyramid_tma(const
   }
 }
 
+// ---- persistent, double-buffered form of k_pyramid_tma --------------------------------------------------------------
+// grid = a few CTAs per SM; every CTA walks the list of (frame, row band, 128-pixel column pair) items with a stride of
+// gridDim.x and keeps TWO stages of boxes in shared memory: while the levels of item i are emitted, the bulk copies of
+// item i+1 are already in flight (one mbarrier per stage, phase = use count parity).  The grid-shaped kernel above runs
+// its CTAs in lock step -- all load, then all store, then a partial second wave.  MEASURED SLOWER than the grid form
+// (18.9 vs 17.9 us at config 2, 94.6 vs 86.0 us at config 3): the per-item CTA barrier and the 40-register budget of six
+// resident CTAs cost more than the overlap gains; opt-in through XPT_PYRAMID=tma_persistent, parity-tested.
+constexpr int kPyrStages = 2;
+
+struct PyrItem { int b, f, x0, y0; bool is_tgt, skip; };
+
+__device__ __forceinline__ PyrItem pyr_item(const PyramidTiledArgs& a, int item, int ntx, int nty) {
+  PyrItem it;
+  const int nfr = a.N + 1;
+  const int tx = item % ntx, r = item / ntx;
+  const int ty = r % nty, z = r / nty;
+  it.b = z / nfr; it.f = z % nfr;
+  it.is_tgt = it.f == a.N;
+  it.skip = it.is_tgt && a.target == nullptr;
+  it.x0 = tx * (kPyrTmaTW * kPyrTmaBoxes); it.y0 = ty * kPyrTH;
+  return it;
+}
+
+__global__ void __launch_bounds__(kPyrThreads, XPT_PYR_MINB) k_pyramid_tma_p(const __grid_constant__ PyramidTiledArgs a,
+                                                                              const __grid_constant__ CUtensorMap tm_src,
+                                                                              const __grid_constant__ CUtensorMap tm_tgt,
+                                                                              int ntx, int nty, int total) {
+  __shared__ __align__(128) float tile[kPyrStages][kPyrTmaBoxes][kPyrTH][kPyrTmaTW * 3];
+  __shared__ __align__(8) unsigned long long mbar[kPyrStages];
+  if (a.with_geometry) geometry_item(a.geo, blockIdx.x * blockDim.x + threadIdx.x);       // (the host sizes the grid for it)
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < kPyrStages; ++k)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mbar[k])), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  constexpr unsigned kBoxBytes = kPyrTH * kPyrTmaTW * 3 * sizeof(float);
+  auto issue = [&](int item, int stage) {            // thread 0: arm the stage's barrier and start its copies
+    const PyrItem it = pyr_item(a, item, ntx, nty);
+    if (it.skip) return;
+    const unsigned bar = smem_u32(&mbar[stage]);
+    int nbox = 0;
+#pragma unroll
+    for (int k = 0; k < kPyrTmaBoxes; ++k) nbox += (it.x0 + k * kPyrTmaTW < a.W) ? 1 : 0;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kBoxBytes * nbox) : "memory");
+#pragma unroll
+    for (int k = 0; k < kPyrTmaBoxes; ++k) {
+      const int xk = it.x0 + k * kPyrTmaTW;
+      if (xk >= a.W) continue;
+      const unsigned dst = smem_u32(&tile[stage][k][0][0]);
+      if (it.is_tgt)
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                     ::"r"(dst), "l"(&tm_tgt), "r"(bar), "r"(xk * 3), "r"(it.y0), "r"(it.b) : "memory");
+      else
+        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                     ::"r"(dst), "l"(&tm_src), "r"(bar), "r"(xk * 3), "r"(it.y0), "r"(it.f), "r"(it.b) : "memory");
+    }
+  };
+  int item = blockIdx.x;
+  if (item < total && threadIdx.x == 0) issue(item, 0);
+  unsigned phase[kPyrStages] = {0u, 0u};
+  for (int n = 0; item < total; item += gridDim.x, ++n) {
+    const int stage = n & 1;
+    const int next = item + gridDim.x;
+    // stage^1 was last read in the previous iteration, which ended with a CTA barrier: it may be refilled now
+    if (next < total && threadIdx.x == 0) issue(next, stage ^ 1);
+    const PyrItem it = pyr_item(a, item, ntx, nty);
+    if (!it.skip) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "WAIT_%=:\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+          "@p bra DONE_%=;\n\t"
+          "bra WAIT_%=;\n\t"
+          "DONE_%=:\n\t}" ::"r"(smem_u32(&mbar[stage])), "r"(phase[stage]) : "memory");
+      phase[stage] ^= 1u;
+      const long long frame = it.is_tgt ? (long long)it.b : (long long)(it.b * a.N + it.f);
+#pragma unroll
+      for (int k = 0; k < kPyrTmaBoxes; ++k) {
+        const int xk = it.x0 + k * kPyrTmaTW;
+        if (xk >= a.W) continue;
+        const int tw = min(kPyrTmaTW, a.W - xk);    // multiple of 8
+        if (tw == kPyrTmaTW) pyramid_emit<true, kPyrTmaTW>(a, tile[stage][k], tw, it.is_tgt, frame, xk, it.y0);
+        else pyramid_emit<false, kPyrTmaTW>(a, tile[stage][k], tw, it.is_tgt, frame, xk, it.y0);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // adjoint of the source pyramid: d_source[full] += resize^T(d_source_level) for s > 1
 // (each level pixel spreads 1/4 to its centre 2x2 / 1 to the centre pixel).
 struct PyramidAdjArgs {

@@ -324,7 +324,21 @@ int launch_pyramids(xpt_ctx* ctx, const xpt_frames* f, float* const target_ms[],
             tm_tgt = tm_src;
           }
         }
-        if (tma) {
+        // XPT_PYRAMID=tma_persistent: the persistent, double-buffered form (k_pyramid_tma_p) instead of one CTA per tile
+        // pair.  Measured slower (18.9 vs 17.9 us at config 2, 94.6 vs 86.0 us at config 3: profiles/r02_pyramid_ab.txt),
+        // so it is opt-in.
+        static const bool persistent = [] { const char* e = getenv("XPT_PYRAMID"); return e && !strcmp(e, "tma_persistent"); }();
+        if (tma && persistent) {
+          const int ntx = cdiv(ctx->W, kPyrTmaTW * kPyrTmaBoxes), nty = ctx->H / kPyrTH;
+          const long long total = (long long)ntx * nty * ctx->B * (ctx->N + 1);
+          int dev_sms = 148;
+          cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, ctx->cfg.device);
+          long long gp = (long long)dev_sms * XPT_PYR_MINB;
+          if (gp > total) gp = total;
+          if (geo_pose && need > gp) gp = need;
+          k_pyramid_tma_p<<<(unsigned)gp, kPyrThreads, 0, st>>>(t, tm_src, tm_tgt, ntx, nty, (int)total);
+          XPT_LAUNCH_CHECK("k_pyramid_tma_p");
+        } else if (tma) {
           int gxt = cdiv(ctx->W, kPyrTmaTW * kPyrTmaBoxes);
           if (geo_pose && need > gxt) gxt = need;
           dim3 gridt(gxt, ctx->H / kPyrTH, ctx->B * (ctx->N + 1) + 1);
