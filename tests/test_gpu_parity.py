@@ -1,6 +1,9 @@
 """GPU parity tests: the CUDA path (through the ctypes C-ABI) against the golden vectors and
 against the CPU oracle on the same seeded inputs.  Tolerances are BASELINE.json's:
 warped images 1e-4 max-abs, losses 1e-5 relative, gradients 1e-4 relative (max-norm)."""
+import os
+import sys
+
 import numpy as np
 import pytest
 import torch
@@ -71,6 +74,19 @@ def test_total_loss_against_golden(xw, name, flags):
     assert relerr(r["d_pose"].cpu().numpy(), g["d_pose"]) < GRAD_TOL
     assert relerr(r["d_pose"].cpu().numpy(), g64["d_pose"]) < GRAD_TOL
     assert relerr(r["d_source"].cpu().numpy(), g["d_source"]) < GRAD_TOL
+
+
+@pytest.mark.parametrize("mode", ["tiled", "tma_persistent"])
+def test_pyramid_kernel_variants_against_golden(mode):
+    """XPT_PYRAMID selects the pyramid pass (read once per process, hence a subprocess): the LDG->STS tile kernel and the
+    persistent double-buffered TMA kernel reproduce the golden case exactly like the default k_pyramid_tma."""
+    import subprocess
+    env = dict(os.environ, XPT_PYRAMID=mode)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider",
+                        "-k", "test_total_loss_against_golden or test_pieces_against_golden"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
 
 
 @pytest.mark.parametrize("name", CASES)
