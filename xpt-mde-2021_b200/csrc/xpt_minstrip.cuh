@@ -147,7 +147,14 @@ __global__ void __launch_bounds__(kFThreads, 2) k_min_strip(const __grid_constan
   // (staging each source's low-resolution footprint in shared memory, next source prefetched during the terms, was
   // measured: +10 % time -- the taps already hit L1)
   if (GRAD && (ty0 == 0 || ty0 + kFCH + 1 > H))    // block-uniform: a statistics row outside the image is never written
-    for (int i = tid; i < SM::sG - SM::sA; i += kFThreads) sA[i] = 0.f;       // (incl. the pair's local plane)
+    for (int i = tid; i < kFStats; i += kFThreads)
+      if ((unsigned)(ty0 - 1 + i / kFP) >= (unsigned)H) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          sA[c * kFStats + i] = 0.f; sB[c * kFStats + i] = 0.f; sC[c * kFStats + i] = 0.f;
+          if (PAIR) sLp[c * kFStats + i] = 0.f;
+        }
+      }
   __syncthreads();
 
   // ---- strip coordinates (as in k_fused) -------------------------------------------------------------------
@@ -281,7 +288,10 @@ __global__ void __launch_bounds__(kFThreads, 2) k_min_strip(const __grid_constan
       const int n0 = c0_ & 0xff, n1 = c1_ & 0xff;
       const bool win0 = n0 == 1 ? (int)(c0_ >> 8) == m : v0 == vmin[k][c][0];
       const bool win1 = n1 == 1 ? (int)(c1_ >> 8) == m : v1 == vmin[k][c][1];
-      const float s0 = n0 <= 1 ? coef : coef / (float)n0, s1 = n1 <= 1 ? coef : coef / (float)n1;
+      float s0 = coef, s1 = coef;
+      if (n0 > 1 || n1 > 1) {       // a real tie is rare: keep the two IEEE divisions (10 % of the kernel's instructions
+        s0 = coef / (float)max(n0, 1); s1 = coef / (float)max(n1, 1);     // when evaluated unconditionally) off the common path
+      }
       g0 = (win0 && ok0 && !bk0 && inv_cnt.x != 0.f) ? s0 : 0.f;
       g1 = (win1 && ok1 && !bk1 && inv_cnt.y != 0.f) ? s1 : 0.f;
     };
@@ -512,10 +522,14 @@ __global__ void __launch_bounds__(kFThreads, 2) k_min_strip(const __grid_constan
   }
 
   // ---- sweep 2: gradient of the winners ----------------------------------------------------------------------
+  // (sources in reverse order: the up-sampled tile of the last source of sweep 1 is still in sy)
   if constexpr (GRAD) {
-    for (int m = 0; m < nsrc; ++m) {
-      upsample(m);
-      __syncthreads();
+    __syncthreads();          // reduce_loss's scratch reads are done; sy of source nsrc-1 is complete since sweep 1's barrier
+    for (int m = nsrc - 1; m >= 0; --m) {
+      if (m != nsrc - 1) {
+        upsample(m);
+        __syncthreads();
+      }
       strip_terms(m, std::integral_constant<int, 1>{});
       __syncthreads();
       adjoint(m);
