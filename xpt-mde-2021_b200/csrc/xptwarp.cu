@@ -1389,7 +1389,9 @@ static int min_loss_impl(xpt_ctx* ctx, int method, const float* const synth_ms[]
     if (!((ctx->h[l] == ctx->H && ctx->w[l] == ctx->W) || (2 * ctx->w[l] <= ctx->W && 2 * ctx->h[l] <= ctx->H))) strip = false;
   a.tiles_x = strip ? cdiv(ctx->W, kFCW) : cdiv(ctx->W, kTW);
   a.tiles = a.tiles_x * (strip ? cdiv(ctx->H, kFCH) : cdiv(ctx->H, kTH));
-  if (pair && !strip) return fail(XPT_BAD_SHAPE, "xpt_photometric_min_pair_loss: every level must be at full or at most half resolution");
+  if (pair && (ctx->cfg.flags & XPT_FLAG_MIN_TILES))
+    return fail(XPT_BAD_ARGUMENT, "the pair launches run on the strip kernel only: ctx created with XPT_FLAG_MIN_TILES");
+  if (pair && !strip) return fail(XPT_BAD_SHAPE, "pair launch: every level must be at full or at most half resolution");
   const size_t n_part = (size_t)ctx->B * ctx->S * a.tiles;
   XPT_TRY(dev_alloc(ctx, &ctx->min_part, 2 * n_part));
   a.loss_part = ctx->min_part;
