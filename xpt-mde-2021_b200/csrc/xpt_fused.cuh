@@ -30,7 +30,7 @@
 // XPT_GRID_TILE_MAJOR 1: grid = (tiles, snippets) -- a snippet's tiles are consecutive CTAs, so the halo rows a tile shares
 // with its vertical neighbour are still in L2 whatever the batch size (A/B against grid = (snippets, tiles))
 #ifndef XPT_GRID_TILE_MAJOR
-#define XPT_GRID_TILE_MAJOR 1
+#define XPT_GRID_TILE_MAJOR 2          // 2 = by grid size (host), 0 / 1 = forced
 #endif
 #if XPT_EXP & 1
 #define XPT_SYNC() ((void)0)
@@ -148,6 +148,7 @@ struct FusedArgs {
   int k_rec0;                          // first K record of the ctx's slot: CTAs with blockIdx.x < k_rec0 have no work
   int geo_t_off;                       // float offset such that [R|t] of (blockIdx.x, n) sits at geo_t_off + (blockIdx.x * N + n) * 12
   int tiles_per_b;
+  int tile_major;                      // grid = (tiles, snippets) instead of (snippets, tiles)
   int first_tile[kMaxScales + 1];
   const float* depth[kMaxScales];
   const float* disp[kMaxScales];
@@ -243,13 +244,10 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused(const __grid_constant__ 
   // of round 1 re-read them from HBM (12.9 GB DRAM traffic for 6.4 GB algorithmic; -4.5 % kernel time with this order,
   // +-0 at config 2 / 3: profiles/r02_ab_grid_order.txt).  (A persistent grid drawing tiles from a ticket was measured in
   // round 2: +2 % time at config 2 and config 3 -- the ticket's two barriers per tile cost more than the tail.)
-#if XPT_GRID_TILE_MAJOR
-  int t = blockIdx.x;
-  const int bl = blockIdx.y;               // K record of this snippet inside the constant bank
-#else
-  int t = blockIdx.y;
-  const int bl = blockIdx.x;               // K record of this snippet inside the constant bank
-#endif
+  // a.tile_major (host: grids of more than a few waves): see above; small grids keep the snippet-major order of round 1,
+  // whose LAST CTAs are the cheap small-level tiles of all snippets (config 2: 97.3 vs 98-99 us)
+  int t = a.tile_major ? blockIdx.x : blockIdx.y;
+  const int bl = a.tile_major ? blockIdx.y : blockIdx.x;      // K record of this snippet inside the constant bank
   if (bl < a.k_rec0) return;
   const int b = a.b_off + bl;
   int l = 0;

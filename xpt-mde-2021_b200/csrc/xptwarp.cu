@@ -626,11 +626,9 @@ int launch_fused(xpt_ctx* ctx, FusedArgs& a, cudaStream_t st) {
     a.k_rec0 = k_rec0;
     a.b_off = b0 - k_rec0;                               // snippet of blockIdx.x = 0
     a.geo_t_off = ctx->geo_t_off - k_rec0 * trec;        // [R|t] of (blockIdx.x, n) at geo_t_off + (blockIdx.x * N + n) * 12
-#if XPT_GRID_TILE_MAJOR
-    dim3 grid(a.tiles_per_b, k_rec0 + bc);
-#else
-    dim3 grid(k_rec0 + bc, a.tiles_per_b);
-#endif
+    // tile-major once the grid is more than ~4 waves of the device (XPT_GRID_TILE_MAJOR = 0 / 1 forces the A/B)
+    a.tile_major = XPT_GRID_TILE_MAJOR == 2 ? ((long long)bc * a.tiles_per_b > 4 * 296) : XPT_GRID_TILE_MAJOR;
+    dim3 grid = a.tile_major ? dim3(a.tiles_per_b, k_rec0 + bc) : dim3(k_rec0 + bc, a.tiles_per_b);
     k_fused<GRAD, OUT, DSRC, DERIVE><<<grid, kFThreads, smem, st>>>(a);
     XPT_LAUNCH_CHECK("k_fused");
   }
