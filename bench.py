@@ -535,11 +535,14 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": n_warm, "ms_per_step": ms_step, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_string(args.workload, args.source_grad, args.adversarial),
                        "global_batch": global_batch, "batch_per_gpu": B, "parallelism": f"dp{world}",
                        "kernel": "k_strip (XPT_FLAG_STRIP)" if args.strip else "k_fused (tiles)",
+                       # --warmup steps as asked, then untimed filler steps of the same kind until the device has been
+                       # busy for ~0.3 s (a device coming out of idle measured up to 8 % slow): the total before the clock
+                       "untimed_steps_before_clock": n_warm,
                        "l2": f"rotating {n_sets} resident input sets ({n_sets * per_set / 1e6:.0f} MB > 126 MB L2)",
                        "launch": "eager" if args.no_graph else "cuda-graph replay", "fused": not args.unfused,
                        "host_affinity": numa or "unbound",
