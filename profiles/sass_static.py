@@ -2,7 +2,7 @@
 usage: python profiles/sass_static.py [path/to/libxptwarp.so]"""
 import subprocess, sys, collections, re, os
 so = sys.argv[1] if len(sys.argv) > 1 else os.path.join(os.path.dirname(__file__), '..', 'xpt-mde-2021_b200', 'xptwarp', '_lib', 'libxptwarp.so')
-txt = subprocess.run(['cuobjdump', '-sass', '-fun', '_ZN3xpt7k_fusedILb1ELb0ELb0EEEvNS_9FusedArgsE', so], capture_output=True, text=True).stdout
+txt = subprocess.run(['cuobjdump', '-sass', '-fun', '_ZN3xpt7k_fusedILb1ELb0ELb0ELi0EEEvNS_9FusedArgsE', so], capture_output=True, text=True).stdout
 ins = []
 for line in txt.splitlines():
     m = re.match(r'\s+/\*[0-9a-f]+\*/\s+(.*?);', line)
