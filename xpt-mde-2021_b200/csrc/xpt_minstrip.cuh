@@ -355,14 +355,14 @@ __global__ void __launch_bounds__(kFThreads, 2) k_min_strip(const __grid_constan
           float g0, g1;
           share(iS, c, v0, v1, pass0, pass1, coefS, g0, g1);
           if constexpr (COEF) {
-          // h = dL/d ssim = -g/2; Hh = 2 h / (#taps b1 b2); A, 2B, C as in k_fused
-          const float2 Hh = f2mul(f2(-g0 * inv_cnt.x, -g1 * inv_cnt.y), r12);
-          const float2 Hs = f2mul(Hh, ssv);
-          const float2 t1 = f2mul(mux, f2add(a2, f2neg(a1)));
-          const float2 t2 = f2mul(muy, f2add(b2, f2neg(b1)));
-          *reinterpret_cast<float2*>(sA + so) = f2fma(Hh, t1, f2neg(f2mul(Hs, t2)));
-          *reinterpret_cast<float2*>(sB + so) = f2mul(f2neg(Hs), b1);
-          *reinterpret_cast<float2*>(sC + so) = f2mul(Hh, a1);
+            // h = dL/d ssim = -g/2; Hh = 2 h / (#taps b1 b2); A, 2B, C as in k_fused
+            const float2 Hh = f2mul(f2(-g0 * inv_cnt.x, -g1 * inv_cnt.y), r12);
+            const float2 Hs = f2mul(Hh, ssv);
+            const float2 t1 = f2mul(mux, f2add(a2, f2neg(a1)));
+            const float2 t2 = f2mul(muy, f2add(b2, f2neg(b1)));
+            *reinterpret_cast<float2*>(sA + so) = f2fma(Hh, t1, f2neg(f2mul(Hs, t2)));
+            *reinterpret_cast<float2*>(sB + so) = f2mul(f2neg(Hs), b1);
+            *reinterpret_cast<float2*>(sC + so) = f2mul(Hh, a1);
           }
         }
       }
@@ -499,42 +499,42 @@ __global__ void __launch_bounds__(kFThreads, 2) k_min_strip(const __grid_constan
     }
     reduce_loss(lacc);
   } else {
-  // ---- sweep 1: minimum, tie count and first winner per (pixel, channel) --------------------------------------
-  for (int m = 0; m < nsrc; ++m) {
-    upsample(m);
-    __syncthreads();
-    strip_terms(m, std::integral_constant<int, 0>{});
-    __syncthreads();
-  }
-  // loss of this tile: sum of the minima over its in-image centre pixels
-  {
-    float lsum[NM];
-#pragma unroll
-    for (int k = 0; k < NM; ++k) {
-      lsum[k] = 0.f;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        if (s_centre.x != 0.f) lsum[k] += vmin[k][c][0];
-        if (s_centre.y != 0.f) lsum[k] += vmin[k][c][1];
-      }
-    }
-    reduce_loss(lsum);
-  }
-
-  // ---- sweep 2: gradient of the winners ----------------------------------------------------------------------
-  // (sources in reverse order: the up-sampled tile of the last source of sweep 1 is still in sy)
-  if constexpr (GRAD) {
-    __syncthreads();          // reduce_loss's scratch reads are done; sy of source nsrc-1 is complete since sweep 1's barrier
-    for (int m = nsrc - 1; m >= 0; --m) {
-      if (m != nsrc - 1) {
-        upsample(m);
-        __syncthreads();
-      }
-      strip_terms(m, std::integral_constant<int, 1>{});
+    // ---- sweep 1: minimum, tie count and first winner per (pixel, channel) --------------------------------------
+    for (int m = 0; m < nsrc; ++m) {
+      upsample(m);
       __syncthreads();
-      adjoint(m);
+      strip_terms(m, std::integral_constant<int, 0>{});
+      __syncthreads();
     }
-  }
+    // loss of this tile: sum of the minima over its in-image centre pixels
+    {
+      float lsum[NM];
+#pragma unroll
+      for (int k = 0; k < NM; ++k) {
+        lsum[k] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          if (s_centre.x != 0.f) lsum[k] += vmin[k][c][0];
+          if (s_centre.y != 0.f) lsum[k] += vmin[k][c][1];
+        }
+      }
+      reduce_loss(lsum);
+    }
+
+    // ---- sweep 2: gradient of the winners ----------------------------------------------------------------------
+    // (sources in reverse order: the up-sampled tile of the last source of sweep 1 is still in sy)
+    if constexpr (GRAD) {
+      __syncthreads();          // reduce_loss's scratch reads are done; sy of source nsrc-1 is complete since sweep 1's barrier
+      for (int m = nsrc - 1; m >= 0; --m) {
+        if (m != nsrc - 1) {
+          upsample(m);
+          __syncthreads();
+        }
+        strip_terms(m, std::integral_constant<int, 1>{});
+        __syncthreads();
+        adjoint(m);
+      }
+    }
   }
 }
 
