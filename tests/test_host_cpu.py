@@ -260,3 +260,19 @@ def test_loss_pairs_share_a_launch_only_when_stock(built):
     assert "moaL1_R" not in tl._min_pairs()
     tl.loss_objects["cmbL1_R"] = xptwarp.CombinedLossMultiScale("SSIM", np.ones(4), "_R")
     assert "cmbL1_R" not in tl._min_pairs()
+
+
+def test_round2_entry_points_refuse_null_arguments(built):
+    """The round-2 entry points validate before they touch CUDA: a NULL ctx (all a machine without a GPU can offer) is
+    XPT_BAD_ARGUMENT with a message, never a crash."""
+    lib = built.lib()
+    assert lib.xpt_total_loss_host_end(None) == built.XPT_BAD_ARGUMENT
+    assert b"ctx is NULL" in lib.xpt_last_error()
+    fr, o = built.XptFrames(), built.XptLossOutputs()
+    empty = built.ptr_array([0])
+    assert lib.xpt_total_loss_host_begin(None, C.byref(fr), C.byref(empty), None, None, C.byref(o), None) == built.XPT_BAD_ARGUMENT
+    assert lib.xpt_photometric_min_pair_loss(None, C.byref(empty), None, None, 0, None, None, 1.0, 1.0, None, None,
+                                             None) == built.XPT_BAD_ARGUMENT
+    assert lib.xpt_photometric_cmb_pair_loss(None, C.byref(empty), None, 4, 4, None, 0, None, None, 1.0, 1.0, None,
+                                             None) == built.XPT_BAD_ARGUMENT
+    assert lib.xpt_comm_status(None, None, None) == built.XPT_BAD_ARGUMENT
