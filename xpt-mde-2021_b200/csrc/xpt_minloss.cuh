@@ -1,4 +1,8 @@
-// xpt_minloss.cuh -- per-pixel minimum over sources at full resolution:
+// xpt_minloss.cuh -- per-pixel minimum over sources at full resolution, the ROUND-1 kernel (k_photo_min).  Since round 2 the
+// default is k_min_strip (xpt_minstrip.cuh); this one serves XPT_FLAG_MIN_TILES (A/B parity tests) and scale sets with a
+// level between full and half resolution.  The argument struct and up_taps() below are shared by both kernels.
+//
+// Per-pixel minimum over sources at full resolution:
 // MonoDepth2LossMultiScale (reference losses.py:198-232) and MoALossMultiScale (:282-321).
 //
 // For every scale the synthesised views [B,N,h,w,3] (plus, for MoA, the stereo synthesis [B,1,h,w,3]) are
